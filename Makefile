@@ -1,0 +1,39 @@
+# Build of the product library (host C++ + sm_100a CUDA) and of the test oracle.
+#   make            -> mujoco_ros_pkgs_b200/libb2mj.so  oracle/liboracle.so
+#   make lib / make oracle
+ROOT    := $(abspath $(dir $(lastword $(MAKEFILE_LIST))))
+CSRC    := $(ROOT)/mujoco_ros_pkgs_b200/csrc
+BUILD   := $(ROOT)/build
+NVCC    ?= /usr/local/cuda/bin/nvcc
+CXX     ?= g++
+CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wextra -I$(ROOT)/include -I$(CSRC)
+NVFLAGS := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
+           -I$(ROOT)/include -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v
+
+HOST_SRCS := $(wildcard $(CSRC)/model/*.cpp) $(wildcard $(CSRC)/host/*.cpp)
+CUDA_SRCS := $(wildcard $(CSRC)/kernels/*.cu)
+HOST_OBJS := $(patsubst $(CSRC)/%.cpp,$(BUILD)/%.o,$(HOST_SRCS))
+CUDA_OBJS := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.cu.o,$(CUDA_SRCS))
+LIB := $(ROOT)/mujoco_ros_pkgs_b200/libb2mj.so
+
+all: lib oracle
+lib: $(LIB)
+oracle:
+	$(MAKE) -C $(ROOT)/oracle
+
+$(BUILD)/%.o: $(CSRC)/%.cpp $(ROOT)/include/b2mj.h $(wildcard $(CSRC)/*/*.h)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(BUILD)/%.cu.o: $(CSRC)/%.cu $(ROOT)/include/b2mj.h $(wildcard $(CSRC)/*/*.h) $(wildcard $(CSRC)/*/*.cuh)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
+
+$(LIB): $(HOST_OBJS) $(CUDA_OBJS)
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $^ -cudart static
+
+clean:
+	rm -rf $(BUILD) $(LIB)
+	$(MAKE) -C $(ROOT)/oracle clean
+
+.PHONY: all lib oracle clean

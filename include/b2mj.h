@@ -1,0 +1,377 @@
+/* b2mj.h — C-ABI of the B200-native batched physics step.
+ *
+ * This is the drop-in boundary for the one hot path of ubi-agni/mujoco_ros_pkgs: the
+ * `mj_step(model, data)` call made by MujocoEnv::physicsLoop (reference
+ * mujoco_ros/src/mujoco_env.cpp:498,552,593) plus the data paths either side of it
+ * (mj_resetData :252, mj_forward :329/:621, the plugin-visible mjModel/mjData fields of
+ * SURVEY.md Appendix B).  Plain C: pointers, sizes, ints.  No torch / C++ types cross it.
+ *
+ * Conventions: every function returns 0 on success and a negative B2MJ_E* code on error (never
+ * aborts, never throws); b2mj_last_error() returns a thread-local description.  One stepping
+ * thread per handle (the reference serialises on physics_thread_mutex_, mujoco_env.cpp:456).
+ *
+ * Field names follow mjModel / mjData (MuJoCo 2.3.7, the version the reference pins:
+ * mujoco_ros/CMakeLists.txt:61) so plugin code ports by search-and-replace.
+ */
+#ifndef B2MJ_H_
+#define B2MJ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2MJ_VERSION 100
+
+/* ---- constants (values pinned by reference mujoco_env_fixture.h:145-156, GeomType.msg:2-9) ---- */
+#define B2MJ_MINVAL 1E-15
+#define B2MJ_MAXVAL 1E+10
+#define B2MJ_MINMU 1E-5
+#define B2MJ_MINIMP 0.0001
+#define B2MJ_MAXIMP 0.9999
+#define B2MJ_NEQDATA 11
+#define B2MJ_NIMP 5
+#define B2MJ_NREF 2
+#define B2MJ_NGAIN 10
+#define B2MJ_NBIAS 10
+#define B2MJ_NDYN 10
+#define B2MJ_NWARNING 8
+
+enum { B2MJ_JNT_FREE = 0, B2MJ_JNT_BALL = 1, B2MJ_JNT_SLIDE = 2, B2MJ_JNT_HINGE = 3 };
+enum {
+  B2MJ_GEOM_PLANE = 0, B2MJ_GEOM_HFIELD = 1, B2MJ_GEOM_SPHERE = 2, B2MJ_GEOM_CAPSULE = 3,
+  B2MJ_GEOM_ELLIPSOID = 4, B2MJ_GEOM_CYLINDER = 5, B2MJ_GEOM_BOX = 6, B2MJ_GEOM_MESH = 7
+};
+enum { B2MJ_INT_EULER = 0, B2MJ_INT_RK4 = 1, B2MJ_INT_IMPLICIT = 2, B2MJ_INT_IMPLICITFAST = 3 };
+enum { B2MJ_CONE_PYRAMIDAL = 0, B2MJ_CONE_ELLIPTIC = 1 };
+enum { B2MJ_SOL_PGS = 0, B2MJ_SOL_CG = 1, B2MJ_SOL_NEWTON = 2 };
+enum { B2MJ_EQ_CONNECT = 0, B2MJ_EQ_WELD = 1, B2MJ_EQ_JOINT = 2, B2MJ_EQ_TENDON = 3 };
+enum {
+  B2MJ_CNSTR_EQUALITY = 0, B2MJ_CNSTR_FRICTION_DOF = 1, B2MJ_CNSTR_FRICTION_TENDON = 2,
+  B2MJ_CNSTR_LIMIT_JOINT = 3, B2MJ_CNSTR_LIMIT_TENDON = 4, B2MJ_CNSTR_CONTACT_FRICTIONLESS = 5,
+  B2MJ_CNSTR_CONTACT_PYRAMIDAL = 6, B2MJ_CNSTR_CONTACT_ELLIPTIC = 7
+};
+enum {
+  B2MJ_CSTATE_SATISFIED = 0, B2MJ_CSTATE_QUADRATIC = 1, B2MJ_CSTATE_LINEARNEG = 2,
+  B2MJ_CSTATE_LINEARPOS = 3, B2MJ_CSTATE_CONE = 4
+};
+enum { B2MJ_TRN_JOINT = 0, B2MJ_TRN_JOINTINPARENT = 1, B2MJ_TRN_TENDON = 3 };
+enum { B2MJ_DYN_NONE = 0, B2MJ_DYN_INTEGRATOR = 1, B2MJ_DYN_FILTER = 2 };
+enum { B2MJ_GAIN_FIXED = 0, B2MJ_GAIN_AFFINE = 1 };
+enum { B2MJ_BIAS_NONE = 0, B2MJ_BIAS_AFFINE = 1 };
+enum { B2MJ_OBJ_UNKNOWN = 0, B2MJ_OBJ_BODY = 1, B2MJ_OBJ_XBODY = 2, B2MJ_OBJ_JOINT = 3, B2MJ_OBJ_DOF = 4,
+       B2MJ_OBJ_GEOM = 5, B2MJ_OBJ_SITE = 6, B2MJ_OBJ_CAMERA = 7, B2MJ_OBJ_TENDON = 16,
+       B2MJ_OBJ_ACTUATOR = 17, B2MJ_OBJ_SENSOR = 18, B2MJ_OBJ_EQUALITY = 15 };
+enum { B2MJ_STAGE_NONE = 0, B2MJ_STAGE_POS = 1, B2MJ_STAGE_VEL = 2, B2MJ_STAGE_ACC = 3 };
+enum { B2MJ_DATATYPE_REAL = 0, B2MJ_DATATYPE_POSITIVE = 1, B2MJ_DATATYPE_AXIS = 2, B2MJ_DATATYPE_QUATERNION = 3 };
+/* sensor enum: the 36 types the reference's sensor plugin names (mujoco_sensor_handler_plugin.cpp:70-105) */
+enum {
+  B2MJ_SENS_TOUCH = 0, B2MJ_SENS_ACCELEROMETER, B2MJ_SENS_VELOCIMETER, B2MJ_SENS_GYRO, B2MJ_SENS_FORCE,
+  B2MJ_SENS_TORQUE, B2MJ_SENS_MAGNETOMETER, B2MJ_SENS_RANGEFINDER, B2MJ_SENS_JOINTPOS, B2MJ_SENS_JOINTVEL,
+  B2MJ_SENS_TENDONPOS, B2MJ_SENS_TENDONVEL, B2MJ_SENS_ACTUATORPOS, B2MJ_SENS_ACTUATORVEL,
+  B2MJ_SENS_ACTUATORFRC, B2MJ_SENS_JOINTACTFRC, B2MJ_SENS_BALLQUAT, B2MJ_SENS_BALLANGVEL,
+  B2MJ_SENS_JOINTLIMITPOS, B2MJ_SENS_JOINTLIMITVEL, B2MJ_SENS_JOINTLIMITFRC, B2MJ_SENS_TENDONLIMITPOS,
+  B2MJ_SENS_TENDONLIMITVEL, B2MJ_SENS_TENDONLIMITFRC, B2MJ_SENS_FRAMEPOS, B2MJ_SENS_FRAMEQUAT,
+  B2MJ_SENS_FRAMEXAXIS, B2MJ_SENS_FRAMEYAXIS, B2MJ_SENS_FRAMEZAXIS, B2MJ_SENS_FRAMELINVEL,
+  B2MJ_SENS_FRAMEANGVEL, B2MJ_SENS_FRAMELINACC, B2MJ_SENS_FRAMEANGACC, B2MJ_SENS_SUBTREECOM,
+  B2MJ_SENS_SUBTREELINVEL, B2MJ_SENS_SUBTREEANGMOM, B2MJ_SENS_CLOCK, B2MJ_NSENSORTYPE
+};
+/* disable flags (subset of mjtDisableBit, same bit positions as MuJoCo 2.3.7) */
+enum {
+  B2MJ_DSBL_CONSTRAINT = 1 << 0, B2MJ_DSBL_EQUALITY = 1 << 1, B2MJ_DSBL_FRICTIONLOSS = 1 << 2,
+  B2MJ_DSBL_LIMIT = 1 << 3, B2MJ_DSBL_CONTACT = 1 << 4, B2MJ_DSBL_PASSIVE = 1 << 5,
+  B2MJ_DSBL_GRAVITY = 1 << 6, B2MJ_DSBL_CLAMPCTRL = 1 << 7, B2MJ_DSBL_WARMSTART = 1 << 8,
+  B2MJ_DSBL_FILTERPARENT = 1 << 9, B2MJ_DSBL_ACTUATION = 1 << 10, B2MJ_DSBL_REFSAFE = 1 << 11,
+  B2MJ_DSBL_SENSOR = 1 << 12, B2MJ_DSBL_MIDPHASE = 1 << 13, B2MJ_DSBL_EULERDAMP = 1 << 14
+};
+/* warnings (mjtWarning order) */
+enum {
+  B2MJ_WARN_INERTIA = 0, B2MJ_WARN_CONTACTFULL = 1, B2MJ_WARN_CNSTRFULL = 2, B2MJ_WARN_VGEOMFULL = 3,
+  B2MJ_WARN_BADQPOS = 4, B2MJ_WARN_BADQVEL = 5, B2MJ_WARN_BADQACC = 6, B2MJ_WARN_BADCTRL = 7
+};
+
+/* error codes */
+enum {
+  B2MJ_OK = 0, B2MJ_EINVAL = -1, B2MJ_ENOMEM = -2, B2MJ_ECUDA = -3, B2MJ_EPARSE = -4,
+  B2MJ_EUNSUPPORTED = -5, B2MJ_ESTATE = -6, B2MJ_ENODEVICE = -7
+};
+
+/* ---- mjOption mirror (fields the reference exposes: viewer.cpp:1624-1647) ---- */
+typedef struct b2mjOption {
+  double timestep;
+  double impratio;
+  double tolerance;
+  double ls_tolerance;
+  double noslip_tolerance;
+  double mpr_tolerance;
+  double gravity[3];
+  double wind[3];
+  double magnetic[3];
+  double density;
+  double viscosity;
+  double o_margin;
+  double o_solref[2];
+  double o_solimp[5];
+  int integrator;
+  int collision;
+  int cone;
+  int jacobian;
+  int solver;
+  int iterations;
+  int ls_iterations;
+  int noslip_iterations;
+  int mpr_iterations;
+  int disableflags;
+  int enableflags;
+  int _pad;
+} b2mjOption;
+
+typedef struct b2mjStatistic {
+  double meaninertia;
+  double meanmass;
+  double meansize;
+  double extent;
+  double center[3];
+} b2mjStatistic;
+
+/* ---- model sizes and arrays, X-macro lists (one source for struct, alloc, device upload, reflection) ---- */
+#define B2MJ_MODEL_SIZES(X)                                                                       \
+  X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(nwrap) X(neq)          \
+  X(nsensor) X(nsensordata) X(nM) X(nmocap) X(nexclude) X(ncollpair) X(nconmax) X(njmax)          \
+  X(nnames) X(nlevel) X(ntree)
+
+/* X(ctype, name, rows(size field), cols) */
+#define B2MJ_MODEL_ARRAYS(X)                                                                      \
+  X(double, qpos0, nq, 1) X(double, qpos_spring, nq, 1)                                           \
+  X(int, body_parentid, nbody, 1) X(int, body_rootid, nbody, 1) X(int, body_weldid, nbody, 1)     \
+  X(int, body_mocapid, nbody, 1) X(int, body_jntnum, nbody, 1) X(int, body_jntadr, nbody, 1)      \
+  X(int, body_dofnum, nbody, 1) X(int, body_dofadr, nbody, 1) X(int, body_geomnum, nbody, 1)      \
+  X(int, body_geomadr, nbody, 1) X(int, body_level, nbody, 1)                                     \
+  X(double, body_pos, nbody, 3) X(double, body_quat, nbody, 4)                                    \
+  X(double, body_ipos, nbody, 3) X(double, body_iquat, nbody, 4) X(double, body_mass, nbody, 1)   \
+  X(double, body_subtreemass, nbody, 1) X(double, body_inertia, nbody, 3)                         \
+  X(double, body_invweight0, nbody, 2) X(double, body_gravcomp, nbody, 1)                         \
+  X(int, level_bodyadr, nlevel, 1) X(int, level_bodynum, nlevel, 1) X(int, level_body, nbody, 1) \
+  X(int, jnt_type, njnt, 1) X(int, jnt_qposadr, njnt, 1) X(int, jnt_dofadr, njnt, 1)              \
+  X(int, jnt_bodyid, njnt, 1) X(int, jnt_limited, njnt, 1)                                        \
+  X(double, jnt_solref, njnt, 2) X(double, jnt_solimp, njnt, 5) X(double, jnt_pos, njnt, 3)       \
+  X(double, jnt_axis, njnt, 3) X(double, jnt_stiffness, njnt, 1) X(double, jnt_range, njnt, 2)    \
+  X(double, jnt_margin, njnt, 1)                                                                  \
+  X(int, dof_bodyid, nv, 1) X(int, dof_jntid, nv, 1) X(int, dof_parentid, nv, 1)                  \
+  X(int, dof_Madr, nv, 1) X(int, dof_treeid, nv, 1)                                               \
+  X(double, dof_solref, nv, 2) X(double, dof_solimp, nv, 5)                                       \
+  X(double, dof_frictionloss, nv, 1) X(double, dof_armature, nv, 1) X(double, dof_damping, nv, 1) \
+  X(double, dof_invweight0, nv, 1) X(double, dof_M0, nv, 1)                                       \
+  X(int, geom_type, ngeom, 1) X(int, geom_contype, ngeom, 1) X(int, geom_conaffinity, ngeom, 1)   \
+  X(int, geom_condim, ngeom, 1) X(int, geom_bodyid, ngeom, 1) X(int, geom_priority, ngeom, 1)     \
+  X(double, geom_solmix, ngeom, 1) X(double, geom_solref, ngeom, 2)                               \
+  X(double, geom_solimp, ngeom, 5) X(double, geom_size, ngeom, 3) X(double, geom_rbound, ngeom, 1)\
+  X(double, geom_pos, ngeom, 3) X(double, geom_quat, ngeom, 4) X(double, geom_friction, ngeom, 3) \
+  X(double, geom_margin, ngeom, 1) X(double, geom_gap, ngeom, 1)                                  \
+  X(int, site_bodyid, nsite, 1) X(int, site_type, nsite, 1) X(double, site_size, nsite, 3)        \
+  X(double, site_pos, nsite, 3) X(double, site_quat, nsite, 4)                                    \
+  X(int, tendon_adr, ntendon, 1) X(int, tendon_num, ntendon, 1) X(int, tendon_limited, ntendon, 1)\
+  X(double, tendon_solref_lim, ntendon, 2) X(double, tendon_solimp_lim, ntendon, 5)               \
+  X(double, tendon_solref_fri, ntendon, 2) X(double, tendon_solimp_fri, ntendon, 5)               \
+  X(double, tendon_range, ntendon, 2) X(double, tendon_margin, ntendon, 1)                        \
+  X(double, tendon_stiffness, ntendon, 1) X(double, tendon_damping, ntendon, 1)                   \
+  X(double, tendon_frictionloss, ntendon, 1) X(double, tendon_lengthspring, ntendon, 2)           \
+  X(double, tendon_length0, ntendon, 1) X(double, tendon_invweight0, ntendon, 1)                  \
+  X(int, wrap_type, nwrap, 1) X(int, wrap_objid, nwrap, 1) X(double, wrap_prm, nwrap, 1)          \
+  X(int, actuator_trntype, nu, 1) X(int, actuator_dyntype, nu, 1) X(int, actuator_gaintype, nu, 1)\
+  X(int, actuator_biastype, nu, 1) X(int, actuator_trnid, nu, 2) X(int, actuator_actadr, nu, 1)   \
+  X(int, actuator_ctrllimited, nu, 1) X(int, actuator_forcelimited, nu, 1)                        \
+  X(int, actuator_actlimited, nu, 1)                                                              \
+  X(double, actuator_dynprm, nu, B2MJ_NDYN) X(double, actuator_gainprm, nu, B2MJ_NGAIN)           \
+  X(double, actuator_biasprm, nu, B2MJ_NBIAS) X(double, actuator_ctrlrange, nu, 2)                \
+  X(double, actuator_forcerange, nu, 2) X(double, actuator_actrange, nu, 2)                       \
+  X(double, actuator_gear, nu, 6) X(double, actuator_acc0, nu, 1) X(double, actuator_length0, nu, 1) \
+  X(int, eq_type, neq, 1) X(int, eq_obj1id, neq, 1) X(int, eq_obj2id, neq, 1)                     \
+  X(int, eq_active, neq, 1) X(double, eq_solref, neq, 2) X(double, eq_solimp, neq, 5)             \
+  X(double, eq_data, neq, B2MJ_NEQDATA)                                                           \
+  X(int, exclude_signature, nexclude, 1)                                                          \
+  X(int, collpair_geom1, ncollpair, 1) X(int, collpair_geom2, ncollpair, 1)                       \
+  X(int, collpair_slotadr, ncollpair, 1) X(int, collpair_maxcon, ncollpair, 1)                    \
+  X(int, sensor_type, nsensor, 1) X(int, sensor_datatype, nsensor, 1)                             \
+  X(int, sensor_needstage, nsensor, 1) X(int, sensor_objtype, nsensor, 1)                         \
+  X(int, sensor_objid, nsensor, 1) X(int, sensor_reftype, nsensor, 1)                             \
+  X(int, sensor_refid, nsensor, 1) X(int, sensor_dim, nsensor, 1) X(int, sensor_adr, nsensor, 1)  \
+  X(double, sensor_cutoff, nsensor, 1) X(double, sensor_noise, nsensor, 1)                        \
+  X(int, name_bodyadr, nbody, 1) X(int, name_jntadr, njnt, 1) X(int, name_geomadr, ngeom, 1)      \
+  X(int, name_siteadr, nsite, 1) X(int, name_tendonadr, ntendon, 1)                               \
+  X(int, name_actuatoradr, nu, 1) X(int, name_sensoradr, nsensor, 1) X(int, name_eqadr, neq, 1)   \
+  X(char, names, nnames, 1)
+
+typedef struct b2mjModel {
+#define B2MJ_X_SIZE(n) int n;
+  B2MJ_MODEL_SIZES(B2MJ_X_SIZE)
+#undef B2MJ_X_SIZE
+  int _pad0;
+  b2mjOption opt;
+  b2mjStatistic stat;
+#define B2MJ_X_ARR(t, n, r, c) t* n;
+  B2MJ_MODEL_ARRAYS(B2MJ_X_ARR)
+#undef B2MJ_X_ARR
+  void* _owner; /* library-private allocation record */
+} b2mjModel;
+
+/* ---- per-env data fields (mjData names).  One list drives: the device arena layout, b2mj_get/set,
+ *      the CPU oracle's data struct, and the Python reflection used by the tests. ---- */
+typedef enum b2mj_field {
+  /* state + inputs (resident in HBM between steps) */
+  B2MJ_F_QPOS = 0, B2MJ_F_QVEL, B2MJ_F_ACT, B2MJ_F_CTRL, B2MJ_F_QFRC_APPLIED, B2MJ_F_XFRC_APPLIED,
+  B2MJ_F_MOCAP_POS, B2MJ_F_MOCAP_QUAT, B2MJ_F_QACC_WARMSTART, B2MJ_F_TIME,
+  /* outputs written every step */
+  B2MJ_F_QACC, B2MJ_F_SENSORDATA, B2MJ_F_ACT_DOT,
+  /* position stage */
+  B2MJ_F_XPOS, B2MJ_F_XQUAT, B2MJ_F_XMAT, B2MJ_F_XIPOS, B2MJ_F_XIMAT, B2MJ_F_XANCHOR, B2MJ_F_XAXIS,
+  B2MJ_F_GEOM_XPOS, B2MJ_F_GEOM_XMAT, B2MJ_F_SITE_XPOS, B2MJ_F_SITE_XMAT, B2MJ_F_SUBTREE_COM,
+  B2MJ_F_CINERT, B2MJ_F_CDOF, B2MJ_F_CRB, B2MJ_F_TEN_LENGTH, B2MJ_F_TEN_J, B2MJ_F_ACTUATOR_LENGTH,
+  B2MJ_F_ACTUATOR_MOMENT, B2MJ_F_QM, B2MJ_F_QLD, B2MJ_F_QLDIAGINV, B2MJ_F_QLDIAGSQRTINV,
+  /* velocity stage */
+  B2MJ_F_TEN_VELOCITY, B2MJ_F_ACTUATOR_VELOCITY, B2MJ_F_CVEL, B2MJ_F_CDOF_DOT, B2MJ_F_QFRC_BIAS,
+  B2MJ_F_QFRC_PASSIVE,
+  /* acceleration stage */
+  B2MJ_F_ACTUATOR_FORCE, B2MJ_F_QFRC_ACTUATOR, B2MJ_F_QFRC_SMOOTH, B2MJ_F_QACC_SMOOTH,
+  B2MJ_F_QFRC_CONSTRAINT, B2MJ_F_CACC, B2MJ_F_CFRC_INT, B2MJ_F_CFRC_EXT,
+  /* contacts: fixed-stride records, nconmax per env */
+  B2MJ_F_CONTACT_DIST, B2MJ_F_CONTACT_POS, B2MJ_F_CONTACT_FRAME, B2MJ_F_CONTACT_INCLUDEMARGIN,
+  B2MJ_F_CONTACT_FRICTION, B2MJ_F_CONTACT_SOLREF, B2MJ_F_CONTACT_SOLIMP, B2MJ_F_CONTACT_MU,
+  B2MJ_F_CONTACT_DIM, B2MJ_F_CONTACT_GEOM1, B2MJ_F_CONTACT_GEOM2, B2MJ_F_CONTACT_EXCLUDE,
+  B2MJ_F_CONTACT_EFC_ADDRESS,
+  /* constraints: njmax rows per env */
+  B2MJ_F_EFC_TYPE, B2MJ_F_EFC_ID, B2MJ_F_EFC_J, B2MJ_F_EFC_POS, B2MJ_F_EFC_MARGIN,
+  B2MJ_F_EFC_FRICTIONLOSS, B2MJ_F_EFC_DIAGAPPROX, B2MJ_F_EFC_KBIP, B2MJ_F_EFC_D, B2MJ_F_EFC_R,
+  B2MJ_F_EFC_VEL, B2MJ_F_EFC_AREF, B2MJ_F_EFC_B, B2MJ_F_EFC_FORCE, B2MJ_F_EFC_STATE, B2MJ_F_EFC_AR,
+  /* counters */
+  B2MJ_F_NCON, B2MJ_F_NEFC, B2MJ_F_SOLVER_ITER, B2MJ_F_WARNING,
+  B2MJ_NFIELD
+} b2mj_field;
+
+/* element type and per-env element count of a field for a given model; returns count (<0 on error);
+ * *is_int = 1 for int32 fields, 0 for float64 */
+int b2mj_field_size(const b2mjModel* m, b2mj_field f, int* is_int);
+const char* b2mj_field_name(b2mj_field f);
+int b2mj_field_by_name(const char* name); /* -1 if unknown */
+
+/* ---- model compile / ownership (replaces mj_loadXML / mj_deleteModel at mujoco_env.cpp:840-843,747) ---- */
+int b2mj_model_from_xml_file(const char* path, b2mjModel** out);
+int b2mj_model_from_xml_string(const char* xml, b2mjModel** out);
+void b2mj_model_free(b2mjModel* m);
+/* re-derive qpos0-dependent constants after mass / geometry edits (replaces mj_setConst,
+ * reference callbacks.cpp:254,582) */
+int b2mj_model_set_const(b2mjModel* m);
+/* name lookup (replaces mj_name2id / mj_id2name; reference uses them 45x) */
+int b2mj_name2id(const b2mjModel* m, int objtype, const char* name);
+const char* b2mj_id2name(const b2mjModel* m, int objtype, int id);
+/* reflection over B2MJ_MODEL_ARRAYS / B2MJ_MODEL_SIZES (used by bindings; index 0..n-1) */
+int b2mj_model_narrays(void);
+int b2mj_model_array_info(const b2mjModel* m, int idx, const char** name, int* elem_kind /*0 f64,1 i32,2 char*/,
+                          int* rows, int* cols, void** ptr);
+int b2mj_model_nsizes(void);
+int b2mj_model_size_info(const b2mjModel* m, int idx, const char** name, int* value);
+
+/* ---- batched environment handle ---- */
+typedef struct b2mj_handle b2mj_handle;
+
+/* create nenv independent envs of model m on CUDA device `device` (one process per GPU).
+ * The model is copied; later host-side edits need b2mj_model_update.  Replaces mj_makeData
+ * (mujoco_env.cpp:872).  State starts as after mj_resetData. */
+int b2mj_create(const b2mjModel* m, int nenv, int device, b2mj_handle** out);
+void b2mj_destroy(b2mj_handle* h);
+int b2mj_nenv(const b2mj_handle* h);
+const b2mjModel* b2mj_model(const b2mj_handle* h);
+/* run launches on this CUDA stream (cudaStream_t as void*); default: the legacy default stream */
+int b2mj_set_stream(b2mj_handle* h, void* cuda_stream);
+
+/* mj_resetData semantics per env (mujoco_env.cpp:252); env_mask NULL = all, else nenv bytes (host) */
+int b2mj_reset(b2mj_handle* h, const uint8_t* env_mask);
+/* mj_forward on all envs (mujoco_env.cpp:329,621): all stages, no integration */
+int b2mj_forward(b2mj_handle* h);
+/* nsteps x mj_step on all envs, asynchronous on the handle's stream; no host callbacks inside
+ * (mujoco_env.cpp:498,552,593).  ctrl/qfrc_applied/xfrc_applied are read as currently set. */
+int b2mj_step(b2mj_handle* h, int nsteps);
+/* split step around the control hook (mjcb_control fires between the velocity stage and actuation:
+ * mujoco_env.h:242-246).  step_begin: checks + position + velocity stages (+pos/vel sensors);
+ * step_end: actuation, acceleration, constraint solve, acc sensors, check, integrate. Euler only. */
+int b2mj_step_begin(b2mj_handle* h);
+int b2mj_step_end(b2mj_handle* h);
+/* block until all queued work on the handle's stream has finished */
+int b2mj_sync(b2mj_handle* h);
+
+/* keep the full per-env mjData arena (every field of b2mj_field) readable after step/forward.
+ * Off by default: the fused step then touches HBM only for the state record. */
+int b2mj_set_keep_intermediates(b2mj_handle* h, int on);
+
+/* host <-> device field copies.  Layout: [nenv][count] row-major, float64 or int32 (see b2mj_field_size).
+ * bytes must equal nenv*count*elemsize.  Synchronous w.r.t. the handle's stream. */
+int b2mj_get(b2mj_handle* h, b2mj_field f, void* host_dst, size_t bytes);
+int b2mj_set(b2mj_handle* h, b2mj_field f, const void* host_src, size_t bytes);
+/* device pointer + env pitch (in elements) of a resident state/input/output field, for device-side
+ * plugins and policies (valid until destroy).  Element k of env e is ptr[e*pitch + k]. */
+int b2mj_device_ptr(b2mj_handle* h, b2mj_field f, void** dev_ptr, size_t* pitch_elems);
+
+/* re-upload model constants after host-side edits (mirrors the mutating services,
+ * callbacks.cpp:462-738: gravity, body_mass, geom_*, eq_*) */
+int b2mj_model_update(b2mj_handle* h, const b2mjModel* m);
+
+/* batched plugin data paths (device kernels):
+ *  robot_hw_write — DefaultRobotHWSim::writeSim (default_robot_hw_sim.cpp:248-326)
+ *  sensor_readout — MujocoRosSensorsPlugin::lastStageCallback arithmetic (mujoco_sensor_handler_plugin.cpp:175-437) */
+enum { B2MJ_CTRL_EFFORT = 0, B2MJ_CTRL_POSITION = 1, B2MJ_CTRL_POSITION_PID = 2, B2MJ_CTRL_VELOCITY = 3,
+       B2MJ_CTRL_VELOCITY_PID = 4 };
+typedef struct b2mjRobotHW {
+  int njoint;                /* controlled joints */
+  const int* joint_id;       /* [njoint] model joint ids (hinge/slide) */
+  const int* control_mode;   /* [njoint] B2MJ_CTRL_* */
+  const double* effort_limit;/* [njoint] */
+  const double* pid_gains;   /* [njoint][5] p,i,d,i_max,i_min */
+  const double* lower_limit; /* [njoint] joint limits (for limit-aware position error) */
+  const double* upper_limit; /* [njoint] */
+  const int* joint_kind;     /* [njoint] 0 revolute (limited), 1 continuous, 2 prismatic */
+} b2mjRobotHW;
+int b2mj_robot_hw_configure(b2mj_handle* h, const b2mjRobotHW* cfg);
+/* cmd: DEVICE or HOST pointer [nenv][njoint] (is_device flag); e_stop: 0/1; period: control dt for PID */
+int b2mj_robot_hw_write(b2mj_handle* h, const double* cmd, int is_device, int e_stop, double period);
+/* pos/vel/eff: HOST [nenv][njoint] each (any may be NULL) — DefaultRobotHWSim::readSim (:230-246) */
+int b2mj_robot_hw_read(b2mj_handle* h, double* pos, double* vel, double* eff);
+
+typedef struct b2mjSensorNoise {
+  int sensor_id;
+  double mean[3];
+  double sigma[3];
+  int set_flag; /* bit k set => dimension k noisy (SensorNoiseModel.msg semantics) */
+} b2mjSensorNoise;
+int b2mj_sensor_configure_noise(b2mj_handle* h, const b2mjSensorNoise* models, int nmodels, uint64_t seed);
+/* values/gt: HOST float32 [nenv][nsensordata]: value = float(sensordata/cutoff) (+noise), gt without noise.
+ * gt may be NULL (eval mode publishes no ground truth: mujoco_sensor_handler_plugin.cpp:65-67). */
+int b2mj_sensor_readout(b2mj_handle* h, float* values, float* gt);
+
+/* multi-GPU publish: gather this rank's [nenv][count] slab of field f into dev_dst_all
+ * ([world][nenv][count], device pointer) using the NCCL communicator passed as void* (ncclComm_t).
+ * Only exchange step on the path. */
+int b2mj_allgather_publish(b2mj_handle* h, b2mj_field f, void* nccl_comm, void* dev_dst_all);
+
+/* introspection for the benchmark / roofline */
+typedef struct b2mjLaunchInfo {
+  int warps_per_cta;
+  int ctas;
+  int smem_bytes_per_cta;
+  int arena_doubles_per_env;
+  int arena_in_smem;      /* 1 if the whole arena is shared-memory resident */
+  int state_record_bytes; /* bytes per env of the HBM-resident state record (read + written per step) */
+  int regs_per_thread;
+  uint64_t launches;      /* kernels launched through this handle so far */
+} b2mjLaunchInfo;
+int b2mj_launch_info(b2mj_handle* h, b2mjLaunchInfo* out);
+
+const char* b2mj_last_error(void);
+int b2mj_version(void);
+int b2mj_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2MJ_H_ */
