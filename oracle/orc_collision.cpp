@@ -1,0 +1,346 @@
+// orc_collision.cpp — collision detection of the CPU oracle.
+// TEST INFRASTRUCTURE ONLY (see orc_math.h).  Restates MuJoCo 2.3.7 engine_collision_driver.c
+// (pair filtering, parameter mixing, contact ordering) and engine_collision_primitive.c (plane-*,
+// sphere-*, capsule-capsule) — the mj_collision stage inside the `mj_step` call at reference
+// mujoco_env.cpp:498; the narrowphase table is what MujocoEnv::registerCollisionFunction overrides
+// (mujoco_env.cpp:163-176).  sphere-box / capsule-box follow closest-feature constructions of our own
+// (MuJoCo's box routines are not reproducible from memory; parity unpinned).
+//
+// Candidate pairs come pre-filtered and pre-ordered from the model (collpair_*): body-pair signature
+// ascending, then geom ids — the order the driver emits contacts in.  Only the data-dependent tests
+// (bounding sphere, narrowphase distance vs margin) run here.
+#include <algorithm>
+#include <cmath>
+
+#include "orc_math.h"
+#include "orc_types.h"
+
+namespace orc {
+
+struct Con {
+  double dist, pos[3], frame[9];
+};
+
+static int planeSphere(Con* con, double margin, const double* pos1, const double* mat1, const double* pos2, double radius) {
+  double normal[3] = {mat1[2], mat1[5], mat1[8]}, tmp[3];
+  sub3(tmp, pos2, pos1);
+  double cdist = dot3(tmp, normal);
+  if (cdist > margin + radius) return 0;
+  con->dist = cdist - radius;
+  zero(con->frame, 9);
+  copy3(con->frame, normal);
+  scl3(tmp, normal, -con->dist / 2 - radius);
+  add3(con->pos, pos2, tmp);
+  return 1;
+}
+
+static int planeCapsule(Con* con, double margin, const double* pos1, const double* mat1, const double* pos2,
+                        const double* mat2, const double* size2) {
+  double axis[3] = {mat2[2], mat2[5], mat2[8]}, seg[3], p[3];
+  scl3(seg, axis, size2[1]);
+  int n = 0;
+  add3(p, pos2, seg);
+  n += planeSphere(con + n, margin, pos1, mat1, p, size2[0]);
+  sub3(p, pos2, seg);
+  n += planeSphere(con + n, margin, pos1, mat1, p, size2[0]);
+  for (int i = 0; i < n; i++) copy3(con[i].frame + 3, axis);  // align the tangent with the capsule axis
+  return n;
+}
+
+static int planeBox(Con* con, double margin, const double* pos1, const double* mat1, const double* pos2,
+                    const double* mat2, const double* size2) {
+  double normal[3] = {mat1[2], mat1[5], mat1[8]}, dif[3];
+  sub3(dif, pos2, pos1);
+  double dist = dot3(dif, normal);
+  int cnt = 0;
+  for (int i = 0; i < 8; i++) {
+    double vec[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])};
+    double corner[3];
+    rotVecMat(corner, vec, mat2);
+    double ldist = dot3(normal, corner);
+    if (dist + ldist > margin || ldist > 0) continue;
+    con[cnt].dist = dist + ldist;
+    zero(con[cnt].frame, 9);
+    copy3(con[cnt].frame, normal);
+    addTo3(corner, pos2);
+    scl3(vec, normal, -con[cnt].dist / 2);
+    add3(con[cnt].pos, corner, vec);
+    if (++cnt >= 4) return 4;
+  }
+  return cnt;
+}
+
+static int sphereSphere(Con* con, double margin, const double* pos1, double r1, const double* pos2, double r2) {
+  double dif[3];
+  sub3(dif, pos2, pos1);
+  double cdist2 = dot3(dif, dif), bound = margin + r1 + r2;
+  if (cdist2 > bound * bound) return 0;
+  double cdist = normalize3(dif);
+  con->dist = cdist - r1 - r2;
+  zero(con->frame, 9);
+  copy3(con->frame, dif);
+  scl3(con->pos, dif, r1 + con->dist / 2);
+  addTo3(con->pos, pos1);
+  return 1;
+}
+
+static int sphereCapsule(Con* con, double margin, const double* pos1, double r1, const double* pos2, const double* mat2,
+                         const double* size2) {
+  double axis[3] = {mat2[2], mat2[5], mat2[8]}, vec[3], p[3];
+  sub3(vec, pos1, pos2);
+  double x = clampd(dot3(axis, vec), -size2[1], size2[1]);
+  scl3(p, axis, x);
+  addTo3(p, pos2);
+  return sphereSphere(con, margin, pos1, r1, p, size2[0]);
+}
+
+static int capsuleCapsule(Con* con, double margin, const double* pos1, const double* mat1, const double* size1,
+                          const double* pos2, const double* mat2, const double* size2) {
+  double axis1[3] = {mat1[2], mat1[5], mat1[8]}, axis2[3] = {mat2[2], mat2[5], mat2[8]}, dif[3];
+  sub3(dif, pos1, pos2);
+  double ma = dot3(axis1, axis1), mb = -dot3(axis1, axis2), mc = dot3(axis2, axis2);
+  double u = -dot3(axis1, dif), v = dot3(axis2, dif);
+  double det = ma * mc - mb * mb;
+  double vec1[3], vec2[3];
+  if (std::fabs(det) >= MINVAL) {
+    double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > size1[1]) { x1 = size1[1]; x2 = (v - mb * size1[1]) / mc; }
+    else if (x1 < -size1[1]) { x1 = -size1[1]; x2 = (v + mb * size1[1]) / mc; }
+    if (x2 > size2[1]) { x2 = size2[1]; x1 = clampd((u - mb * size2[1]) / ma, -size1[1], size1[1]); }
+    else if (x2 < -size2[1]) { x2 = -size2[1]; x1 = clampd((u + mb * size2[1]) / ma, -size1[1], size1[1]); }
+    scl3(vec1, axis1, x1); addTo3(vec1, pos1);
+    scl3(vec2, axis2, x2); addTo3(vec2, pos2);
+    return sphereSphere(con, margin, vec1, size1[0], vec2, size2[0]);
+  }
+  // parallel axes: up to two contacts at the segment ends
+  int n = 0;
+  double x1, x2;
+  x1 = size1[1]; x2 = clampd((v - mb * size1[1]) / mc, -size2[1], size2[1]);
+  scl3(vec1, axis1, x1); addTo3(vec1, pos1); scl3(vec2, axis2, x2); addTo3(vec2, pos2);
+  n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+  x1 = -size1[1]; x2 = clampd((v + mb * size1[1]) / mc, -size2[1], size2[1]);
+  scl3(vec1, axis1, x1); addTo3(vec1, pos1); scl3(vec2, axis2, x2); addTo3(vec2, pos2);
+  n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+  if (n >= 2) return n;
+  x2 = size2[1]; x1 = clampd((u - mb * size2[1]) / ma, -size1[1], size1[1]);
+  scl3(vec1, axis1, x1); addTo3(vec1, pos1); scl3(vec2, axis2, x2); addTo3(vec2, pos2);
+  n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+  if (n >= 2) return n;
+  x2 = -size2[1]; x1 = clampd((u + mb * size2[1]) / ma, -size1[1], size1[1]);
+  scl3(vec1, axis1, x1); addTo3(vec1, pos1); scl3(vec2, axis2, x2); addTo3(vec2, pos2);
+  n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+  return n;
+}
+
+// sphere (geom1) vs box (geom2): closest feature of the box to the sphere centre
+static int sphereBox(Con* con, double margin, const double* pos1, double radius, const double* pos2, const double* mat2,
+                     const double* size2) {
+  double tmp[3], center[3], clamped[3], dif[3];
+  sub3(tmp, pos1, pos2);
+  rotVecMatT(center, tmp, mat2);
+  for (int i = 0; i < 3; i++) clamped[i] = clampd(center[i], -size2[i], size2[i]);
+  sub3(dif, center, clamped);
+  double dist = norm3(dif);
+  if (dist - radius > margin) return 0;
+  double nloc[3], ploc[3];
+  if (dist <= MINVAL) {
+    // centre inside the box: push out through the nearest face
+    int k = 0;
+    double depth = size2[0] - std::fabs(center[0]);
+    for (int i = 1; i < 3; i++) {
+      double di = size2[i] - std::fabs(center[i]);
+      if (di < depth) { depth = di; k = i; }
+    }
+    double e = center[k] >= 0 ? 1.0 : -1.0;
+    zero3(nloc);
+    nloc[k] = -e;
+    con->dist = -(depth + radius);
+    copy3(ploc, center);
+    ploc[k] += e * (depth - radius) / 2;
+  } else {
+    scl3(nloc, dif, -1.0 / dist);
+    con->dist = dist - radius;
+    // midpoint between sphere surface (centre + n*r) and box surface (clamped)
+    for (int i = 0; i < 3; i++) ploc[i] = 0.5 * (center[i] + nloc[i] * radius + clamped[i]);
+  }
+  zero(con->frame, 9);
+  rotVecMat(con->frame, nloc, mat2);
+  rotVecMat(con->pos, ploc, mat2);
+  addTo3(con->pos, pos2);
+  return 1;
+}
+
+// squared distance from point c + t*a (box frame) to the box, minimised exactly over t in [-h, h]:
+// the function is convex piecewise quadratic with breakpoints where a coordinate crosses +-size.
+static double segmentBoxClosest(const double* c, const double* a, double h, const double* size) {
+  double bp[8];
+  int nbp = 0;
+  bp[nbp++] = -h;
+  bp[nbp++] = h;
+  for (int i = 0; i < 3; i++) {
+    if (std::fabs(a[i]) < MINVAL) continue;
+    double t1 = (size[i] - c[i]) / a[i], t2 = (-size[i] - c[i]) / a[i];
+    if (t1 > -h && t1 < h) bp[nbp++] = t1;
+    if (t2 > -h && t2 < h) bp[nbp++] = t2;
+  }
+  std::sort(bp, bp + nbp);
+  auto d2 = [&](double t) {
+    double s = 0;
+    for (int i = 0; i < 3; i++) {
+      double p = c[i] + t * a[i];
+      double e = std::fabs(p) - size[i];
+      if (e > 0) s += e * e;
+    }
+    return s;
+  };
+  double best_t = bp[0], best = d2(bp[0]);
+  for (int k = 0; k + 1 < nbp; k++) {
+    double lo = bp[k], hi = bp[k + 1];
+    if (hi - lo < MINVAL) continue;
+    // quadratic on this interval: active coordinates decided at the midpoint
+    double mid = 0.5 * (lo + hi), A = 0, B = 0;
+    for (int i = 0; i < 3; i++) {
+      double p = c[i] + mid * a[i];
+      if (std::fabs(p) > size[i]) {
+        double sgn = p > 0 ? 1.0 : -1.0;
+        // (sgn*(c+t a) - size)^2 -> derivative terms
+        A += a[i] * a[i];
+        B += a[i] * (c[i] - sgn * size[i]);
+      }
+    }
+    double cand[2] = {hi, hi};
+    int nc = 1;
+    if (A > MINVAL) {
+      double t = clampd(-B / A, lo, hi);
+      cand[0] = t;
+      cand[1] = hi;
+      nc = 2;
+    }
+    for (int q = 0; q < nc; q++) {
+      double v = d2(cand[q]);
+      if (v < best) { best = v; best_t = cand[q]; }
+    }
+  }
+  return best_t;
+}
+
+// capsule (geom1) vs box (geom2): sphere-box at the segment point closest to the box, plus the far end
+static int capsuleBox(Con* con, double margin, const double* pos1, const double* mat1, const double* size1,
+                      const double* pos2, const double* mat2, const double* size2) {
+  double axis[3] = {mat1[2], mat1[5], mat1[8]}, tmp[3], c[3], a[3], p[3];
+  sub3(tmp, pos1, pos2);
+  rotVecMatT(c, tmp, mat2);
+  rotVecMatT(a, axis, mat2);
+  const double h = size1[1];
+  double t = segmentBoxClosest(c, a, h, size2);
+  int n = 0;
+  scl3(p, axis, t); addTo3(p, pos1);
+  n += sphereBox(con + n, margin, p, size1[0], pos2, mat2, size2);
+  double t2 = t >= 0 ? -h : h;
+  if (std::fabs(t2 - t) > 1e-3 * h) {
+    scl3(p, axis, t2); addTo3(p, pos1);
+    n += sphereBox(con + n, margin, p, size1[0], pos2, mat2, size2);
+  }
+  return n;
+}
+
+// narrowphase dispatch; geoms already ordered so that type1 <= type2.  Returns -1 if unsupported.
+static int narrowphase(const b2mjModel* m, const OrcData* d, Con* con, int g1, int g2, double margin) {
+  const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  const double *pos1 = d->geom_xpos + 3 * g1, *mat1 = d->geom_xmat + 9 * g1, *size1 = m->geom_size + 3 * g1;
+  const double *pos2 = d->geom_xpos + 3 * g2, *mat2 = d->geom_xmat + 9 * g2, *size2 = m->geom_size + 3 * g2;
+  if (t1 == B2MJ_GEOM_PLANE) {
+    if (t2 == B2MJ_GEOM_SPHERE) return planeSphere(con, margin, pos1, mat1, pos2, size2[0]);
+    if (t2 == B2MJ_GEOM_CAPSULE) return planeCapsule(con, margin, pos1, mat1, pos2, mat2, size2);
+    if (t2 == B2MJ_GEOM_BOX) return planeBox(con, margin, pos1, mat1, pos2, mat2, size2);
+    return -1;
+  }
+  if (t1 == B2MJ_GEOM_SPHERE) {
+    if (t2 == B2MJ_GEOM_SPHERE) return sphereSphere(con, margin, pos1, size1[0], pos2, size2[0]);
+    if (t2 == B2MJ_GEOM_CAPSULE) return sphereCapsule(con, margin, pos1, size1[0], pos2, mat2, size2);
+    if (t2 == B2MJ_GEOM_BOX) return sphereBox(con, margin, pos1, size1[0], pos2, mat2, size2);
+    return -1;
+  }
+  if (t1 == B2MJ_GEOM_CAPSULE) {
+    if (t2 == B2MJ_GEOM_CAPSULE) return capsuleCapsule(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+    if (t2 == B2MJ_GEOM_BOX) return capsuleBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+    return -1;
+  }
+  return -1;
+}
+
+// mj_collision
+void collision(const b2mjModel* m, OrcData* d) {
+  d->ncon() = 0;
+  if (m->opt.disableflags & (B2MJ_DSBL_CONSTRAINT | B2MJ_DSBL_CONTACT)) return;
+  if (m->nconmax == 0) return;
+  for (int p = 0; p < m->ncollpair; p++) {
+    const int g1 = m->collpair_geom1[p], g2 = m->collpair_geom2[p];
+    const double margin = std::fmax(m->geom_margin[g1], m->geom_margin[g2]);
+    const double gap = std::fmax(m->geom_gap[g1], m->geom_gap[g2]);
+    // bounding-sphere filter (planes: signed distance to the plane)
+    const double r1 = m->geom_rbound[g1], r2 = m->geom_rbound[g2];
+    if (r1 > 0 && r2 > 0) {
+      double dif[3];
+      sub3(dif, d->geom_xpos + 3 * g1, d->geom_xpos + 3 * g2);
+      double bound = r1 + r2 + margin;
+      if (dot3(dif, dif) > bound * bound) continue;
+    } else if (m->geom_type[g1] == B2MJ_GEOM_PLANE && r2 > 0) {
+      const double* mat1 = d->geom_xmat + 9 * g1;
+      double normal[3] = {mat1[2], mat1[5], mat1[8]}, dif[3];
+      sub3(dif, d->geom_xpos + 3 * g2, d->geom_xpos + 3 * g1);
+      if (dot3(dif, normal) > margin + r2) continue;
+    }
+    Con con[8];
+    int num = narrowphase(m, d, con, g1, g2, margin);
+    if (num <= 0) continue;
+    // contact parameters (mixing rules of mj_collideGeoms)
+    int condim;
+    double solref[2], solimp[5], fri[3];
+    if (m->geom_priority[g1] != m->geom_priority[g2]) {
+      int gi = m->geom_priority[g1] > m->geom_priority[g2] ? g1 : g2;
+      condim = m->geom_condim[gi];
+      copy(solref, m->geom_solref + 2 * gi, 2);
+      copy(solimp, m->geom_solimp + 5 * gi, 5);
+      copy3(fri, m->geom_friction + 3 * gi);
+    } else {
+      condim = std::max(m->geom_condim[g1], m->geom_condim[g2]);
+      double s1 = m->geom_solmix[g1], s2 = m->geom_solmix[g2], mix;
+      if (s1 >= MINVAL && s2 >= MINVAL) mix = s1 / (s1 + s2);
+      else if (s1 < MINVAL && s2 < MINVAL) mix = 0.5;
+      else if (s1 < MINVAL) mix = 0.0;
+      else mix = 1.0;
+      const double *a = m->geom_solref + 2 * g1, *b = m->geom_solref + 2 * g2;
+      if (a[0] > 0 && b[0] > 0) for (int i = 0; i < 2; i++) solref[i] = mix * a[i] + (1 - mix) * b[i];
+      else for (int i = 0; i < 2; i++) solref[i] = std::fmin(a[i], b[i]);
+      for (int i = 0; i < 5; i++) solimp[i] = mix * m->geom_solimp[5 * g1 + i] + (1 - mix) * m->geom_solimp[5 * g2 + i];
+      for (int i = 0; i < 3; i++) fri[i] = std::fmax(m->geom_friction[3 * g1 + i], m->geom_friction[3 * g2 + i]);
+    }
+    for (int i = 0; i < num; i++) {
+      if (d->ncon() >= m->nconmax) {
+        d->warning[B2MJ_WARN_CONTACTFULL]++;
+        return;
+      }
+      const int c = d->ncon()++;
+      d->contact_dist[c] = con[i].dist;
+      copy3(d->contact_pos + 3 * c, con[i].pos);
+      copy(d->contact_frame + 9 * c, con[i].frame, 9);
+      makeFrame(d->contact_frame + 9 * c);
+      d->contact_includemargin[c] = margin - gap;
+      double* f = d->contact_friction + 5 * c;
+      f[0] = f[1] = std::fmax(B2MJ_MINMU, fri[0]);
+      f[2] = std::fmax(B2MJ_MINMU, fri[1]);
+      f[3] = f[4] = std::fmax(B2MJ_MINMU, fri[2]);
+      copy(d->contact_solref + 2 * c, solref, 2);
+      copy(d->contact_solimp + 5 * c, solimp, 5);
+      d->contact_mu[c] = 0;
+      d->contact_dim[c] = condim;
+      d->contact_geom1[c] = g1;
+      d->contact_geom2[c] = g2;
+      d->contact_exclude[c] = con[i].dist >= d->contact_includemargin[c];
+      d->contact_efc_address[c] = -1;
+    }
+  }
+}
+
+}  // namespace orc
