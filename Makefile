@@ -11,7 +11,7 @@ NVFLAGS := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xco
            -I$(ROOT)/include -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v
 
 HOST_SRCS := $(wildcard $(CSRC)/model/*.cpp) $(wildcard $(CSRC)/host/*.cpp)
-CUDA_SRCS := $(wildcard $(CSRC)/kernels/*.cu)
+CUDA_SRCS := $(wildcard $(CSRC)/kernels/*.cu) $(wildcard $(CSRC)/host/*.cu)
 HOST_OBJS := $(patsubst $(CSRC)/%.cpp,$(BUILD)/%.o,$(HOST_SRCS))
 CUDA_OBJS := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.cu.o,$(CUDA_SRCS))
 LIB := $(ROOT)/mujoco_ros_pkgs_b200/libb2mj.so

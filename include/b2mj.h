@@ -345,9 +345,11 @@ typedef struct b2mjSensorNoise {
   int set_flag; /* bit k set => dimension k noisy (SensorNoiseModel.msg semantics) */
 } b2mjSensorNoise;
 int b2mj_sensor_configure_noise(b2mj_handle* h, const b2mjSensorNoise* models, int nmodels, uint64_t seed);
-/* values/gt: HOST float32 [nenv][nsensordata]: value = float(sensordata/cutoff) (+noise), gt without noise.
+/* values/gt: HOST float64 [nenv][nsensordata] holding float32-rounded numbers exactly as the reference
+ * publishes them: value = float(sensordata/cutoff), noisy value = float(sensordata + noise/cutoff)
+ * (noisy quaternions stay float64, as tf2 composes them); gt is the noise-free value.
  * gt may be NULL (eval mode publishes no ground truth: mujoco_sensor_handler_plugin.cpp:65-67). */
-int b2mj_sensor_readout(b2mj_handle* h, float* values, float* gt);
+int b2mj_sensor_readout(b2mj_handle* h, double* values, double* gt);
 
 /* multi-GPU publish: gather this rank's [nenv][count] slab of field f into dev_dst_all
  * ([world][nenv][count], device pointer) using the NCCL communicator passed as void* (ncclComm_t).

@@ -1,0 +1,160 @@
+"""Thin Python view of a b2mj_handle (tests and bench drive the C-ABI through this).
+
+No compute happens in Python: every method is one C-ABI call into libb2mj.so (CUDA).  There is no
+CPU fallback — creating a BatchSim without a GPU raises B2mjError(B2MJ_ENODEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import B2mjError, Model, check, lib
+
+_vp = C.c_void_p
+lib.b2mj_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
+lib.b2mj_destroy.argtypes = [_vp]
+lib.b2mj_destroy.restype = None
+lib.b2mj_nenv.argtypes = [_vp]
+lib.b2mj_set_stream.argtypes = [_vp, _vp]
+lib.b2mj_reset.argtypes = [_vp, _vp]
+lib.b2mj_forward.argtypes = [_vp]
+lib.b2mj_step.argtypes = [_vp, C.c_int]
+lib.b2mj_step_begin.argtypes = [_vp]
+lib.b2mj_step_end.argtypes = [_vp]
+lib.b2mj_sync.argtypes = [_vp]
+lib.b2mj_set_keep_intermediates.argtypes = [_vp, C.c_int]
+lib.b2mj_get.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
+lib.b2mj_set.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
+lib.b2mj_device_ptr.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t)]
+lib.b2mj_model_update.argtypes = [_vp, _vp]
+lib.b2mj_launch_info.argtypes = [_vp, C.POINTER(_capi.B2mjLaunchInfo)]
+lib.b2mj_robot_hw_configure.argtypes = [_vp, C.POINTER(_capi.B2mjRobotHW)]
+lib.b2mj_robot_hw_write.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_double]
+lib.b2mj_robot_hw_read.argtypes = [_vp, _vp, _vp, _vp]
+lib.b2mj_sensor_configure_noise.argtypes = [_vp, C.POINTER(_capi.B2mjSensorNoise), C.c_int, C.c_uint64]
+lib.b2mj_sensor_readout.argtypes = [_vp, _vp, _vp]
+lib.b2mj_allgather_publish.argtypes = [_vp, C.c_int, _vp, _vp]
+
+
+class BatchSim:
+    def __init__(self, model: Model, nenv: int, device: int = 0):
+        self.model = model
+        self.nenv = nenv
+        self._h = _vp()
+        check(lib.b2mj_create(model.ptr, nenv, device, C.byref(self._h)), "b2mj_create")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.b2mj_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream_ptr: int):
+        check(lib.b2mj_set_stream(self._h, _vp(cuda_stream_ptr)), "set_stream")
+
+    def reset(self, mask=None):
+        if mask is None:
+            check(lib.b2mj_reset(self._h, None), "reset")
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            assert m.size == self.nenv
+            check(lib.b2mj_reset(self._h, m.ctypes.data), "reset")
+
+    def forward(self):
+        check(lib.b2mj_forward(self._h), "forward")
+
+    def step(self, n: int = 1):
+        check(lib.b2mj_step(self._h, n), "step")
+
+    def step_begin(self):
+        check(lib.b2mj_step_begin(self._h), "step_begin")
+
+    def step_end(self):
+        check(lib.b2mj_step_end(self._h), "step_end")
+
+    def sync(self):
+        check(lib.b2mj_sync(self._h), "sync")
+
+    def keep_intermediates(self, on: bool = True):
+        check(lib.b2mj_set_keep_intermediates(self._h, int(on)), "keep_intermediates")
+
+    def get(self, name: str) -> np.ndarray:
+        f = _capi.field_id(name)
+        n, is_int = self.model.field_size(f)
+        out = np.zeros((self.nenv, max(n, 0)), dtype=np.int32 if is_int else np.float64)
+        check(lib.b2mj_get(self._h, f, out.ctypes.data, out.nbytes), f"get {name}")
+        return out
+
+    def set(self, name: str, value):
+        f = _capi.field_id(name)
+        n, is_int = self.model.field_size(f)
+        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.int32 if is_int else np.float64),
+                                                   (self.nenv, n)))
+        check(lib.b2mj_set(self._h, f, arr.ctypes.data, arr.nbytes), f"set {name}")
+
+    def device_ptr(self, name: str):
+        p, pitch = _vp(), C.c_size_t()
+        check(lib.b2mj_device_ptr(self._h, _capi.field_id(name), C.byref(p), C.byref(pitch)), f"device_ptr {name}")
+        return p.value, pitch.value
+
+    def model_update(self, model: Model = None):
+        check(lib.b2mj_model_update(self._h, (model or self.model).ptr), "model_update")
+
+    def launch_info(self) -> dict:
+        li = _capi.B2mjLaunchInfo()
+        check(lib.b2mj_launch_info(self._h, C.byref(li)), "launch_info")
+        return {k: getattr(li, k) for k, _ in li._fields_}
+
+    # ---- plugin data paths ----
+    def robot_hw_configure(self, joint_ids, modes, effort_limit=None, pid=None, lower=None, upper=None, kind=None):
+        nj = len(joint_ids)
+        self._hw_keep = []
+
+        def arr(x, dt):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(x, dtype=dt)
+            self._hw_keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int if dt == np.int32 else C.c_double))
+        cfg = _capi.B2mjRobotHW(nj, arr(joint_ids, np.int32), arr(modes, np.int32), arr(effort_limit, np.float64),
+                                arr(pid, np.float64), arr(lower, np.float64), arr(upper, np.float64), arr(kind, np.int32))
+        check(lib.b2mj_robot_hw_configure(self._h, C.byref(cfg)), "robot_hw_configure")
+        self._hw_nj = nj
+
+    def robot_hw_write(self, cmd, e_stop=False, period=0.001):
+        c = np.ascontiguousarray(cmd, dtype=np.float64)
+        assert c.shape == (self.nenv, self._hw_nj)
+        check(lib.b2mj_robot_hw_write(self._h, c.ctypes.data, 0, int(e_stop), float(period)), "robot_hw_write")
+
+    def robot_hw_read(self):
+        outs = [np.zeros((self.nenv, self._hw_nj)) for _ in range(3)]
+        check(lib.b2mj_robot_hw_read(self._h, *[o.ctypes.data for o in outs]), "robot_hw_read")
+        return outs
+
+    def sensor_configure_noise(self, models, seed=0):
+        arr = (_capi.B2mjSensorNoise * max(1, len(models)))()
+        for i, (sid, mean, sigma, flag) in enumerate(models):
+            arr[i].sensor_id = sid
+            for k in range(3):
+                arr[i].mean[k] = mean[k]
+                arr[i].sigma[k] = sigma[k]
+            arr[i].set_flag = flag
+        check(lib.b2mj_sensor_configure_noise(self._h, arr, len(models), seed), "sensor_configure_noise")
+
+    def sensor_readout(self, want_gt=True):
+        n = self.model.nsensordata
+        v = np.zeros((self.nenv, n))
+        g = np.zeros((self.nenv, n)) if want_gt else None
+        check(lib.b2mj_sensor_readout(self._h, v.ctypes.data, g.ctypes.data if want_gt else None), "sensor_readout")
+        return v, g

@@ -1,0 +1,640 @@
+// handle.cu — the batched-environment handle behind the C-ABI (include/b2mj.h).
+//
+// Host side of the boundary: owns the device copy of the model, the HBM state records and arenas,
+// decides the shared-memory layout / launch shape, and launches the fused step kernel.  Mirrors what
+// MujocoEnv owns around its mj_step call (reference mujoco_ros/src/mujoco_env.cpp: model_/data_
+// :747-748, mj_makeData :872, mj_resetData :252, mj_forward :329/:621, mj_step :498/:552/:593).
+// No CPU fallback: every entry point that needs the GPU fails with B2MJ_ECUDA / B2MJ_ENODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2mj.h"
+#include "handle.h"
+#include "kernels/step_launch.h"
+#include "model/model_core.h"
+
+using namespace b2mj;
+using namespace b2k;
+
+namespace b2mj {
+
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+      return B2MJ_ECUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+static bool is_record_field(int f) {
+  switch (f) {
+    case B2MJ_F_QPOS: case B2MJ_F_QVEL: case B2MJ_F_ACT: case B2MJ_F_CTRL: case B2MJ_F_QFRC_APPLIED:
+    case B2MJ_F_QACC_WARMSTART: case B2MJ_F_TIME: case B2MJ_F_QACC: case B2MJ_F_SENSORDATA: case B2MJ_F_ACT_DOT:
+      return true;
+    default: return false;
+  }
+}
+
+// ---- kernels local to the handle ----
+__global__ void reset_kernel(double* rec, const double* rec_init, int pitch, int nenv, const unsigned char* mask,
+                             int* warning, int* stats, double* xfrc, int nxfrc, double* mocap, const double* mocap_init,
+                             int nmocap7) {
+  const int env = blockIdx.x;
+  if (env >= nenv || (mask && !mask[env])) return;
+  for (int k = threadIdx.x; k < pitch; k += blockDim.x) rec[(size_t)env * pitch + k] = rec_init[k];
+  for (int k = threadIdx.x; k < B2MJ_NWARNING; k += blockDim.x) warning[(size_t)env * B2MJ_NWARNING + k] = 0;
+  for (int k = threadIdx.x; k < 4; k += blockDim.x) stats[(size_t)env * 4 + k] = 0;
+  if (xfrc) for (int k = threadIdx.x; k < nxfrc; k += blockDim.x) xfrc[(size_t)env * nxfrc + k] = 0;
+  if (mocap) for (int k = threadIdx.x; k < nmocap7; k += blockDim.x) mocap[(size_t)env * nmocap7 + k] = mocap_init[k];
+}
+
+static int field_count(const b2mjModel* m, int f, int* is_int) {
+  if (f == B2MJ_F_EFC_AR) {  // the GPU solver is matrix-free: AR is never materialised
+    if (is_int) *is_int = 0;
+    return 0;
+  }
+  return b2mj_field_size(m, (b2mj_field)f, is_int);
+}
+
+// upload model arrays into one device blob and fill the DevModel pointers
+static int upload_model(Handle* h) {
+  const b2mjModel* m = h->model;
+  DevModel& d = h->dm;
+  size_t total = 0;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+#define X(t, n, r, c) total += al(sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c) + 16);
+  B2MJ_MODEL_ARRAYS(X)
+#undef X
+  // dof-chain masks
+  d.nmaskword = std::max(1, (m->nv + 31) / 32);
+  std::vector<unsigned> mask((size_t)m->nbody * d.nmaskword, 0u);
+  for (int b = 1; b < m->nbody; b++) {
+    int bb = b;
+    while (bb && !m->body_dofnum[bb]) bb = m->body_parentid[bb];
+    if (!bb) continue;
+    for (int k = m->body_dofadr[bb] + m->body_dofnum[bb] - 1; k >= 0; k = m->dof_parentid[k])
+      mask[(size_t)b * d.nmaskword + (k >> 5)] |= 1u << (k & 31);
+  }
+  total += al(mask.size() * sizeof(unsigned) + 16);
+  if (h->model_blob && h->model_blob_bytes < total) {
+    cudaFree(h->model_blob);
+    h->model_blob = nullptr;
+  }
+  if (!h->model_blob) {
+    CUDA_OK(cudaMalloc(&h->model_blob, total));
+    h->model_blob_bytes = total;
+  }
+  std::vector<unsigned char> host(total, 0);
+  size_t off = 0;
+#define X(t, n, r, c)                                                               \
+  {                                                                                 \
+    size_t bytes = sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c);             \
+    if (bytes) std::memcpy(host.data() + off, m->n, bytes);                         \
+    d.n = reinterpret_cast<const t*>((unsigned char*)h->model_blob + off);          \
+    off += al(bytes + 16);                                                          \
+  }
+  B2MJ_MODEL_ARRAYS(X)
+#undef X
+  std::memcpy(host.data() + off, mask.data(), mask.size() * sizeof(unsigned));
+  d.body_dofmask = reinterpret_cast<const unsigned*>((unsigned char*)h->model_blob + off);
+  CUDA_OK(cudaMemcpy(h->model_blob, host.data(), total, cudaMemcpyHostToDevice));
+#define X(n) d.n = m->n;
+  B2MJ_MODEL_SIZES(X)
+#undef X
+  d.opt = m->opt;
+  d.meaninertia = m->stat.meaninertia;
+  d.any_damping = 0;
+  for (int i = 0; i < m->nv; i++) d.any_damping |= m->dof_damping[i] > 0;
+  d.need_rnepost = d.need_subtreevel = 0;
+  for (int i = 0; i < m->nsensor; i++) {
+    const int t = m->sensor_type[i];
+    if (t == B2MJ_SENS_ACCELEROMETER || t == B2MJ_SENS_FORCE || t == B2MJ_SENS_TORQUE || t == B2MJ_SENS_FRAMELINACC ||
+        t == B2MJ_SENS_FRAMEANGACC)
+      d.need_rnepost = 1;
+    if (t == B2MJ_SENS_SUBTREELINVEL || t == B2MJ_SENS_SUBTREEANGMOM) d.need_subtreevel = 1;
+  }
+  return 0;
+}
+
+static int check_supported(const b2mjModel* m) {
+  for (int p = 0; p < m->ncollpair; p++) {
+    const int t1 = m->geom_type[m->collpair_geom1[p]], t2 = m->geom_type[m->collpair_geom2[p]];
+    const bool ok = (t1 == B2MJ_GEOM_PLANE && (t2 == B2MJ_GEOM_SPHERE || t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
+                    (t1 == B2MJ_GEOM_SPHERE && (t2 == B2MJ_GEOM_SPHERE || t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
+                    (t1 == B2MJ_GEOM_CAPSULE && (t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX));
+    if (!ok) {
+      set_error("collision between geom types " + std::to_string(t1) + " and " + std::to_string(t2) +
+                " is not implemented in the CUDA narrowphase (cylinder/ellipsoid/box-box)");
+      return B2MJ_EUNSUPPORTED;
+    }
+  }
+  for (int i = 0; i < m->nsensor; i++)
+    if (m->sensor_type[i] == B2MJ_SENS_RANGEFINDER) {
+      set_error("rangefinder sensors need a ray caster: not implemented");
+      return B2MJ_EUNSUPPORTED;
+    }
+  if (m->opt.integrator != B2MJ_INT_EULER && m->opt.integrator != B2MJ_INT_RK4) {
+    set_error("implicit / implicitfast integrators are not implemented (Euler and RK4 are)");
+    return B2MJ_EUNSUPPORTED;
+  }
+  if (m->opt.solver != B2MJ_SOL_PGS && m->opt.solver != B2MJ_SOL_NEWTON && m->opt.solver != B2MJ_SOL_CG) {
+    set_error("unknown solver");
+    return B2MJ_EUNSUPPORTED;
+  }
+  if (m->opt.noslip_iterations > 0) {
+    set_error("noslip post-solver is not implemented");
+    return B2MJ_EUNSUPPORTED;
+  }
+  return 0;
+}
+
+// arena + record layout and the launch shape
+static int make_layout(Handle* h) {
+  const b2mjModel* m = h->model;
+  DevModel& d = h->dm;
+  const int nv = m->nv, nq = m->nq, na = m->na, nu = m->nu;
+  auto even = [](int x) { return (x + 1) & ~1; };
+  // record
+  int o = 0;
+  d.rec_A_begin = o;
+  d.rec_ctrl = o; o += nu;
+  d.rec_qfrc_applied = o; o += nv;
+  o = even(o);
+  d.rec_B_begin = o;
+  d.rec_qpos = o; o += nq;
+  d.rec_qvel = o; o += nv;
+  d.rec_act = o; o += na;
+  d.rec_warm = o; o += nv;
+  d.rec_time = o; o += 1;
+  o = even(o);
+  d.rec_C_begin = o;
+  d.rec_qacc = o; o += nv;
+  d.rec_sensordata = o; o += m->nsensordata;
+  d.rec_act_dot = o; o += na;
+  o = even(o);
+  d.rec_end = o;
+  d.rec_pitch = o;
+  // field sizes
+  for (int f = 0; f < B2MJ_NFIELD; f++) {
+    int is_int = 0;
+    d.fsize[f] = std::max(0, field_count(m, f, &is_int));
+    d.fis_int[f] = (unsigned char)is_int;
+  }
+  const bool pgs = m->opt.solver == B2MJ_SOL_PGS, newton = m->opt.solver == B2MJ_SOL_NEWTON;
+  const bool rk4 = m->opt.integrator == B2MJ_INT_RK4;
+  int* xs = d.xsize;
+  for (int i = 0; i < XF_COUNT; i++) xs[i] = 0;
+  xs[XF_QLOC] = 4 * m->njnt;
+  xs[XF_QH] = m->nM;
+  xs[XF_QHDIAGINV] = nv;
+  xs[XF_EFC_MINVJT] = pgs ? m->njmax * nv : 0;
+  xs[XF_EFC_ARDIAG] = pgs ? m->njmax : 0;
+  for (int i = XF_VEC0; i <= XF_VEC5; i++) xs[i] = nv;
+  xs[XF_EFC_JAREF] = m->njmax;
+  xs[XF_EFC_JV] = pgs ? 0 : m->njmax;
+  xs[XF_EFC_QUAD] = pgs ? 0 : 3 * m->njmax;
+  xs[XF_NEWTON_H] = newton ? nv * nv : 0;
+  xs[XF_CONTACT_H] = (newton && m->opt.cone == B2MJ_CONE_ELLIPTIC) ? 36 * m->nconmax : 0;
+  xs[XF_SUBTREE_LINVEL] = d.need_subtreevel ? 3 * m->nbody : 0;
+  xs[XF_SUBTREE_ANGMOM] = d.need_subtreevel ? 3 * m->nbody : 0;
+  xs[XF_BODYVEL] = d.need_subtreevel ? 6 * m->nbody : 0;
+  xs[XF_RK_X0] = rk4 ? nq + nv + na : 0;
+  xs[XF_RK_XF] = rk4 ? 4 * nv : 0;
+  xs[XF_RK_F] = rk4 ? 4 * (nv + na) : 0;
+  xs[XF_RK_DX] = rk4 ? 2 * nv + na : 0;
+  // xfrc_applied / mocap live in their own HBM arrays (read only when the surface is enabled)
+  d.fsize[B2MJ_F_XFRC_APPLIED] = 0;
+
+  // global (full) arena offsets
+  int gd = 0, gi = 0;
+  for (int f = 0; f < B2MJ_NFIELD; f++) {
+    if (d.fis_int[f]) { d.off_g[f] = gi; gi += d.fsize[f]; }
+    else { d.off_g[f] = gd; gd += d.fsize[f]; }
+  }
+  for (int i = 0; i < XF_COUNT; i++) { d.xoff_g[i] = gd; gd += xs[i]; }
+  d.arena_g_doubles = even(gd);
+  d.arena_g_ints = even(gi);
+
+  // shared placement: record image first, then hot fields; big constraint arrays are demoted to the
+  // global arena (L2) when the per-env footprint would starve occupancy
+  std::vector<char> cold(B2MJ_NFIELD, 0), xcold(XF_COUNT, 0);
+  auto smem_bytes_env = [&]() {
+    size_t dbl = d.rec_end, ints = 0;
+    for (int f = 0; f < B2MJ_NFIELD; f++) {
+      if (cold[f] || is_record_field(f)) continue;
+      if (d.fis_int[f]) ints += d.fsize[f];
+      else dbl += d.fsize[f];
+    }
+    for (int i = 0; i < XF_COUNT; i++)
+      if (!xcold[i]) dbl += xs[i];
+    return ((dbl * 8 + ((ints + 1) & ~(size_t)1) * 4) + 15) & ~(size_t)15;
+  };
+  const size_t kSmPerSM = 228 * 1024, kCtaReserve = 1024, kMaxCta = 227 * 1024;
+  const size_t target = h->smem_target_bytes ? h->smem_target_bytes : 28 * 1024;  // ~8 envs per SM
+  struct Cand { int is_x, id; };
+  const Cand demote[] = {{1, XF_NEWTON_H}, {1, XF_EFC_MINVJT}, {0, B2MJ_F_EFC_J}, {1, XF_EFC_QUAD}, {1, XF_CONTACT_H},
+                         {0, B2MJ_F_CONTACT_FRAME}, {0, B2MJ_F_EFC_KBIP}, {0, B2MJ_F_CONTACT_SOLIMP},
+                         {0, B2MJ_F_CONTACT_FRICTION}, {0, B2MJ_F_CONTACT_POS}};
+  for (const Cand& c : demote) {
+    if (smem_bytes_env() <= target) break;
+    if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1;
+  }
+  if (smem_bytes_env() + 16 > kMaxCta - kCtaReserve) {
+    // last resort: everything except the record image goes global
+    for (int f = 0; f < B2MJ_NFIELD; f++) cold[f] = !is_record_field(f);
+    for (int i = 0; i < XF_COUNT; i++) xcold[i] = 1;
+  }
+  int sdo = d.rec_end, sio = 0;
+  for (int f = 0; f < B2MJ_NFIELD; f++) d.off_s[f] = -1;
+  d.off_s[B2MJ_F_CTRL] = d.rec_ctrl; d.off_s[B2MJ_F_QFRC_APPLIED] = d.rec_qfrc_applied;
+  d.off_s[B2MJ_F_QPOS] = d.rec_qpos; d.off_s[B2MJ_F_QVEL] = d.rec_qvel; d.off_s[B2MJ_F_ACT] = d.rec_act;
+  d.off_s[B2MJ_F_QACC_WARMSTART] = d.rec_warm; d.off_s[B2MJ_F_TIME] = d.rec_time; d.off_s[B2MJ_F_QACC] = d.rec_qacc;
+  d.off_s[B2MJ_F_SENSORDATA] = d.rec_sensordata; d.off_s[B2MJ_F_ACT_DOT] = d.rec_act_dot;
+  for (int f = 0; f < B2MJ_NFIELD; f++) {
+    if (is_record_field(f) || cold[f]) continue;
+    if (d.fis_int[f]) { d.off_s[f] = sio; sio += d.fsize[f]; }
+    else { d.off_s[f] = sdo; sdo += d.fsize[f]; }
+  }
+  for (int i = 0; i < XF_COUNT; i++) {
+    if (xcold[i]) { d.xoff_s[i] = -1; continue; }
+    d.xoff_s[i] = sdo;
+    sdo += xs[i];
+  }
+  d.arena_s_doubles = even(sdo);
+  d.arena_s_ints = even(sio);
+  const size_t env_bytes = (((size_t)d.arena_s_doubles * 8 + (size_t)d.arena_s_ints * 4) + 15) & ~(size_t)15;
+  // launch shape: warps per CTA maximising resident envs per SM
+  int bestW = 1, bestEnv = 0;
+  const int tryW[] = {4, 8, 2, 1};
+  for (int W : tryW) {
+    if (h->force_warps_per_cta && W != h->force_warps_per_cta) continue;
+    const size_t cta = (size_t)W * (env_bytes + 16);
+    if (cta > kMaxCta) continue;
+    int ctas = (int)(kSmPerSM / (cta + kCtaReserve));
+    ctas = std::min(ctas, 2048 / (W * 32));
+    ctas = std::min(ctas, 32);
+    const int envs = ctas * W;
+    if (envs > bestEnv) { bestEnv = envs; bestW = W; }
+  }
+  if (bestEnv == 0) {
+    set_error("model does not fit the shared-memory arena even with all optional arrays in HBM");
+    return B2MJ_EUNSUPPORTED;
+  }
+  h->warps_per_cta = bestW;
+  h->smem_bytes = (size_t)bestW * (env_bytes + 16);
+  h->arena_in_smem = 1;
+  for (int f = 0; f < B2MJ_NFIELD; f++) if (!is_record_field(f) && d.fsize[f] && d.off_s[f] < 0) h->arena_in_smem = 0;
+  for (int i = 0; i < XF_COUNT; i++) if (xs[i] && d.xoff_s[i] < 0) h->arena_in_smem = 0;
+  return 0;
+}
+
+static int alloc_state(Handle* h) {
+  const b2mjModel* m = h->model;
+  DevModel& d = h->dm;
+  const size_t n = (size_t)h->nenv;
+  CUDA_OK(cudaMalloc(&h->rec, n * d.rec_pitch * sizeof(double)));
+  CUDA_OK(cudaMalloc(&h->rec_init, (size_t)d.rec_pitch * sizeof(double)));
+  CUDA_OK(cudaMalloc(&h->garena_d, std::max<size_t>(1, n * d.arena_g_doubles) * sizeof(double)));
+  CUDA_OK(cudaMalloc(&h->garena_i, std::max<size_t>(1, n * d.arena_g_ints) * sizeof(int)));
+  CUDA_OK(cudaMemset(h->garena_d, 0, std::max<size_t>(1, n * d.arena_g_doubles) * sizeof(double)));
+  CUDA_OK(cudaMemset(h->garena_i, 0, std::max<size_t>(1, n * d.arena_g_ints) * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->warning, n * B2MJ_NWARNING * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->stats, n * 4 * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->xfrc, n * 6 * m->nbody * sizeof(double)));
+  CUDA_OK(cudaMemset(h->xfrc, 0, n * 6 * m->nbody * sizeof(double)));
+  if (m->nmocap) {
+    CUDA_OK(cudaMalloc(&h->mocap, n * 7 * m->nmocap * sizeof(double)));
+    CUDA_OK(cudaMalloc(&h->mocap_init, (size_t)7 * m->nmocap * sizeof(double)));
+  }
+  CUDA_OK(cudaMalloc(&h->mask_dev, n));
+  return 0;
+}
+
+static int upload_init_templates(Handle* h) {
+  const b2mjModel* m = h->model;
+  DevModel& d = h->dm;
+  std::vector<double> rec(d.rec_pitch, 0.0);
+  for (int i = 0; i < m->nq; i++) rec[d.rec_qpos + i] = m->qpos0[i];
+  CUDA_OK(cudaMemcpy(h->rec_init, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (m->nmocap) {
+    std::vector<double> mc(7 * m->nmocap, 0.0);
+    for (int b = 0; b < m->nbody; b++) {
+      const int id = m->body_mocapid[b];
+      if (id < 0) continue;
+      for (int k = 0; k < 3; k++) mc[3 * id + k] = m->body_pos[3 * b + k];
+      for (int k = 0; k < 4; k++) mc[3 * m->nmocap + 4 * id + k] = m->body_quat[4 * b + k];
+    }
+    CUDA_OK(cudaMemcpy(h->mocap_init, mc.data(), mc.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int handle_launch(Handle* h, int mode, int nsteps) {
+  LaunchArgs a;
+  a.rec = h->rec;
+  a.garena_d = h->garena_d;
+  a.garena_i = h->garena_i;
+  a.xfrc = h->dm.has_xfrc ? h->xfrc : nullptr;
+  a.mocap = h->mocap;
+  a.warning = h->warning;
+  a.stats = h->stats;
+  a.nenv = h->nenv;
+  a.nsteps = nsteps;
+  a.mode = mode;
+  a.dump = h->keep_intermediates;
+  const int rc = b2k_launch_step(&h->dm, &a, h->warps_per_cta, h->smem_bytes, h->stream);
+  if (rc != 0) {
+    set_error(std::string("step kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    return B2MJ_ECUDA;
+  }
+  h->launches++;
+  h->dump_valid = (h->keep_intermediates || mode == MODE_STEP_BEGIN);
+  return 0;
+}
+
+}  // namespace b2mj
+
+extern "C" {
+
+int b2mj_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int b2mj_create(const b2mjModel* m, int nenv, int device, b2mj_handle** out) {
+  if (!m || !out || nenv <= 0) {
+    set_error("b2mj_create: bad argument");
+    return B2MJ_EINVAL;
+  }
+  *out = nullptr;
+  if (int rc = check_supported(m)) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: the batched step has no CPU fallback");
+    return B2MJ_ENODEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("b2mj_create: device index out of range");
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  Handle* h = new Handle();
+  h->device = device;
+  h->nenv = nenv;
+  h->model = model_clone(m);
+  int rc = upload_model(h);
+  if (!rc) rc = make_layout(h);
+  if (!rc) rc = alloc_state(h);
+  if (!rc) rc = upload_init_templates(h);
+  if (rc) {
+    b2mj_destroy(reinterpret_cast<b2mj_handle*>(h));
+    return rc;
+  }
+  *out = reinterpret_cast<b2mj_handle*>(h);
+  return b2mj_reset(*out, nullptr);
+}
+
+void b2mj_destroy(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->model_blob); cudaFree(h->rec); cudaFree(h->rec_init); cudaFree(h->garena_d); cudaFree(h->garena_i);
+  cudaFree(h->warning); cudaFree(h->stats); cudaFree(h->xfrc); cudaFree(h->mocap); cudaFree(h->mocap_init);
+  cudaFree(h->mask_dev);
+  handle_free_plugins(h);
+  b2mj_model_free(h->model);
+  delete h;
+}
+
+int b2mj_nenv(const b2mj_handle* hh) { return hh ? reinterpret_cast<const Handle*>(hh)->nenv : B2MJ_EINVAL; }
+const b2mjModel* b2mj_model(const b2mj_handle* hh) { return hh ? reinterpret_cast<const Handle*>(hh)->model : nullptr; }
+
+int b2mj_set_stream(b2mj_handle* hh, void* stream) {
+  if (!hh) return B2MJ_EINVAL;
+  reinterpret_cast<Handle*>(hh)->stream = (cudaStream_t)stream;
+  return 0;
+}
+
+int b2mj_reset(b2mj_handle* hh, const uint8_t* env_mask) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  const unsigned char* dmask = nullptr;
+  if (env_mask) {
+    CUDA_OK(cudaMemcpyAsync(h->mask_dev, env_mask, h->nenv, cudaMemcpyHostToDevice, h->stream));
+    dmask = h->mask_dev;
+  }
+  const b2mjModel* m = h->model;
+  reset_kernel<<<h->nenv, 64, 0, h->stream>>>(h->rec, h->rec_init, h->dm.rec_pitch, h->nenv, dmask, h->warning, h->stats,
+                                              h->xfrc, 6 * m->nbody, h->mocap, h->mocap_init, 7 * m->nmocap);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  h->dump_valid = 0;
+  if (!env_mask) h->dm.has_xfrc = 0;
+  handle_reset_plugins(h, env_mask);
+  return 0;
+}
+
+int b2mj_forward(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  return handle_launch(h, MODE_FORWARD, 1);
+}
+
+int b2mj_step(b2mj_handle* hh, int nsteps) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  if (nsteps <= 0) {
+    set_error("b2mj_step: nsteps must be positive");  // MujocoEnv::step returns false for n<=0 (mujoco_env.cpp:925)
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  h->in_split_step = 0;
+  return handle_launch(h, MODE_STEP, nsteps);
+}
+
+int b2mj_step_begin(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  if (h->model->opt.integrator != B2MJ_INT_EULER) {
+    set_error("split step needs the Euler integrator (RK4 re-enters the control hook 4x per step)");
+    return B2MJ_EUNSUPPORTED;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  int rc = handle_launch(h, MODE_STEP_BEGIN, 1);
+  if (!rc) h->in_split_step = 1;
+  return rc;
+}
+
+int b2mj_step_end(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  if (!h->in_split_step) {
+    set_error("b2mj_step_end without b2mj_step_begin");
+    return B2MJ_ESTATE;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  h->in_split_step = 0;
+  return handle_launch(h, MODE_STEP_END, 1);
+}
+
+int b2mj_sync(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b2mj_set_keep_intermediates(b2mj_handle* hh, int on) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  h->keep_intermediates = on ? 1 : 0;
+  return 0;
+}
+
+static int rec_offset(const DevModel& d, int f) {
+  switch (f) {
+    case B2MJ_F_QPOS: return d.rec_qpos;
+    case B2MJ_F_QVEL: return d.rec_qvel;
+    case B2MJ_F_ACT: return d.rec_act;
+    case B2MJ_F_CTRL: return d.rec_ctrl;
+    case B2MJ_F_QFRC_APPLIED: return d.rec_qfrc_applied;
+    case B2MJ_F_QACC_WARMSTART: return d.rec_warm;
+    case B2MJ_F_TIME: return d.rec_time;
+    case B2MJ_F_QACC: return d.rec_qacc;
+    case B2MJ_F_SENSORDATA: return d.rec_sensordata;
+    case B2MJ_F_ACT_DOT: return d.rec_act_dot;
+    default: return -1;
+  }
+}
+
+// resolve a field to (device base pointer, env pitch in bytes, element size, count)
+static int locate(Handle* h, int f, bool for_write, unsigned char** base, size_t* pitch, size_t* esize, int* count) {
+  if (f < 0 || f >= B2MJ_NFIELD) { set_error("unknown field"); return B2MJ_EINVAL; }
+  const b2mjModel* m = h->model;
+  const DevModel& d = h->dm;
+  int is_int = 0;
+  int n = b2mj_field_size(m, (b2mj_field)f, &is_int);
+  *esize = is_int ? sizeof(int) : sizeof(double);
+  *count = n;
+  const int ro = rec_offset(d, f);
+  if (ro >= 0) { *base = (unsigned char*)(h->rec + ro); *pitch = (size_t)d.rec_pitch * sizeof(double); return 0; }
+  if (f == B2MJ_F_XFRC_APPLIED) { *base = (unsigned char*)h->xfrc; *pitch = (size_t)6 * m->nbody * sizeof(double); return 0; }
+  if (f == B2MJ_F_MOCAP_POS) { *base = (unsigned char*)h->mocap; *pitch = (size_t)7 * m->nmocap * sizeof(double); return 0; }
+  if (f == B2MJ_F_MOCAP_QUAT) { *base = (unsigned char*)(h->mocap + 3 * m->nmocap); *pitch = (size_t)7 * m->nmocap * sizeof(double); return 0; }
+  if (for_write) { set_error(std::string("field '") + b2mj_field_name((b2mj_field)f) + "' is computed, not settable"); return B2MJ_EINVAL; }
+  if (f == B2MJ_F_NCON || f == B2MJ_F_NEFC || f == B2MJ_F_SOLVER_ITER) {
+    *base = (unsigned char*)(h->stats + (f == B2MJ_F_NCON ? 0 : f == B2MJ_F_NEFC ? 1 : 2));
+    *pitch = 4 * sizeof(int);
+    return 0;
+  }
+  if (f == B2MJ_F_WARNING) { *base = (unsigned char*)h->warning; *pitch = B2MJ_NWARNING * sizeof(int); return 0; }
+  if (f == B2MJ_F_EFC_AR) { set_error("efc_AR is never materialised: the CUDA PGS is matrix-free"); return B2MJ_EUNSUPPORTED; }
+  if (!h->dump_valid) {
+    set_error(std::string("field '") + b2mj_field_name((b2mj_field)f) +
+              "' is an intermediate: call b2mj_set_keep_intermediates(h,1) before the step/forward");
+    return B2MJ_ESTATE;
+  }
+  if (is_int) { *base = (unsigned char*)(h->garena_i + d.off_g[f]); *pitch = (size_t)d.arena_g_ints * sizeof(int); }
+  else { *base = (unsigned char*)(h->garena_d + d.off_g[f]); *pitch = (size_t)d.arena_g_doubles * sizeof(double); }
+  return 0;
+}
+
+int b2mj_get(b2mj_handle* hh, b2mj_field f, void* host_dst, size_t bytes) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !host_dst) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  unsigned char* base; size_t pitch, es; int n;
+  if (int rc = locate(h, f, false, &base, &pitch, &es, &n)) return rc;
+  if (bytes != (size_t)h->nenv * n * es) { set_error("b2mj_get: byte count mismatch"); return B2MJ_EINVAL; }
+  if (n == 0) return 0;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy2D(host_dst, n * es, base, pitch, n * es, h->nenv, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b2mj_set(b2mj_handle* hh, b2mj_field f, const void* host_src, size_t bytes) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !host_src) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  unsigned char* base; size_t pitch, es; int n;
+  if (int rc = locate(h, f, true, &base, &pitch, &es, &n)) return rc;
+  if (bytes != (size_t)h->nenv * n * es) { set_error("b2mj_set: byte count mismatch"); return B2MJ_EINVAL; }
+  if (n == 0) return 0;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy2D(base, pitch, host_src, n * es, n * es, h->nenv, cudaMemcpyHostToDevice));
+  if (f == B2MJ_F_XFRC_APPLIED) h->dm.has_xfrc = 1;
+  return 0;
+}
+
+int b2mj_device_ptr(b2mj_handle* hh, b2mj_field f, void** dev_ptr, size_t* pitch_elems) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !dev_ptr) return B2MJ_EINVAL;
+  unsigned char* base; size_t pitch, es; int n;
+  const int ro = rec_offset(h->dm, f);
+  if (ro < 0 && f != B2MJ_F_XFRC_APPLIED && f != B2MJ_F_MOCAP_POS && f != B2MJ_F_MOCAP_QUAT && f != B2MJ_F_WARNING &&
+      f != B2MJ_F_NCON && f != B2MJ_F_NEFC && f != B2MJ_F_SOLVER_ITER) {
+    set_error("b2mj_device_ptr: only resident state / input / output fields have stable device pointers");
+    return B2MJ_EINVAL;
+  }
+  if (int rc = locate(h, f, false, &base, &pitch, &es, &n)) return rc;
+  *dev_ptr = base;
+  if (pitch_elems) *pitch_elems = pitch / es;
+  if (f == B2MJ_F_XFRC_APPLIED) h->dm.has_xfrc = 1;  // the caller may write through the pointer
+  return 0;
+}
+
+int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !m) return B2MJ_EINVAL;
+  const b2mjModel* o = h->model;
+#define X(n) if (m->n != o->n) { set_error("b2mj_model_update: size field '" #n "' changed; create a new handle"); return B2MJ_EINVAL; }
+  B2MJ_MODEL_SIZES(X)
+#undef X
+  if (m->opt.solver != o->opt.solver || m->opt.integrator != o->opt.integrator || m->opt.cone != o->opt.cone) {
+    set_error("b2mj_model_update: solver / integrator / cone changes alter the arena layout; create a new handle");
+    return B2MJ_EINVAL;
+  }
+  if (int rc = check_supported(m)) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  b2mjModel* clone = model_clone(m);
+  b2mj_model_free(h->model);
+  h->model = clone;
+  const int has_xfrc = h->dm.has_xfrc;
+  if (int rc = upload_model(h)) return rc;
+  h->dm.has_xfrc = has_xfrc;
+  return upload_init_templates(h);
+}
+
+int b2mj_launch_info(b2mj_handle* hh, b2mjLaunchInfo* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out) return B2MJ_EINVAL;
+  const DevModel& d = h->dm;
+  out->warps_per_cta = h->warps_per_cta;
+  out->ctas = (h->nenv + h->warps_per_cta - 1) / h->warps_per_cta;
+  out->smem_bytes_per_cta = (int)h->smem_bytes;
+  out->arena_doubles_per_env = d.arena_g_doubles;
+  out->arena_in_smem = h->arena_in_smem;
+  // bytes the fused step moves per env: load A+B, store B+C
+  out->state_record_bytes = ((d.rec_C_begin - d.rec_A_begin) + (d.rec_end - d.rec_B_begin)) * 8;
+  int regs = 0;
+  b2k_step_kernel_attrs(&regs, nullptr, nullptr);
+  out->regs_per_thread = regs;
+  out->launches = h->launches;
+  return 0;
+}
+
+}  // extern "C"

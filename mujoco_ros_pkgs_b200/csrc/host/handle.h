@@ -1,0 +1,52 @@
+// handle.h — internal definition of b2mj_handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b2mj.h"
+#include "kernels/dev_model.h"
+
+namespace b2mj {
+
+struct RobotHWState;
+struct SensorReadoutState;
+
+struct Handle {
+  int device = 0;
+  int nenv = 0;
+  b2mjModel* model = nullptr;     // host clone
+  b2k::DevModel dm{};             // device view (pointers into model_blob) + layouts
+  void* model_blob = nullptr;
+  size_t model_blob_bytes = 0;
+  cudaStream_t stream = nullptr;
+
+  double* rec = nullptr;          // [nenv][rec_pitch] state records
+  double* rec_init = nullptr;     // reset template
+  double* garena_d = nullptr;     // [nenv][arena_g_doubles]
+  int* garena_i = nullptr;        // [nenv][arena_g_ints]
+  int* warning = nullptr;         // [nenv][8]
+  int* stats = nullptr;           // [nenv][4]
+  double* xfrc = nullptr;         // [nenv][6*nbody]
+  double* mocap = nullptr;        // [nenv][7*nmocap]
+  double* mocap_init = nullptr;
+  unsigned char* mask_dev = nullptr;
+
+  int warps_per_cta = 4;
+  size_t smem_bytes = 0;
+  size_t smem_target_bytes = 0;   // 0 = default policy
+  int force_warps_per_cta = 0;
+  int arena_in_smem = 0;
+  int keep_intermediates = 0;
+  int dump_valid = 0;
+  int in_split_step = 0;
+  uint64_t launches = 0;
+
+  RobotHWState* robot_hw = nullptr;
+  SensorReadoutState* sensor_ro = nullptr;
+};
+
+int handle_launch(Handle* h, int mode, int nsteps);
+void handle_free_plugins(Handle* h);
+void handle_reset_plugins(Handle* h, const uint8_t* env_mask);
+
+}  // namespace b2mj

@@ -1,0 +1,93 @@
+// dev_model.h — device-side view of a compiled model + the per-env arena layout.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//  * model constants: one blob per handle, shared by all envs (read through the read-only path);
+//  * state record: rec[nenv][rec_pitch] doubles, per env
+//        [ ctrl | qfrc_applied | pad ][ qpos | qvel | act | qacc_warmstart | time | pad ][ qacc | sensordata | act_dot | pad ]
+//          \__________ segment A (inputs) ______/\______________ segment B (state) ___________/\_______ segment C (outputs) ___/
+//    A+B is one contiguous 16B-aligned span (one bulk load per env), B+C likewise (one bulk store);
+//  * arena: every other mjData field of one env (b2mj_field order).  The "hot" part is shared-memory
+//    resident for the duration of a launch, the "cold" part (big constraint arrays when they do not
+//    fit) lives in garena[nenv][arena_g_doubles] in HBM/L2.  With keep_intermediates the hot part is
+//    dumped to garena at the end of the launch so b2mj_get can read any field.
+#pragma once
+#include <stdint.h>
+
+#include "b2mj.h"
+
+namespace b2k {
+
+// extra per-env scratch arrays that are not b2mj_field entries
+enum XField {
+  XF_QLOC = 0,      // 4*njnt  local joint quaternions (hinge: axis-angle; ball: qpos)
+  XF_QH,            // nM      M + h*diag(damping), factorised
+  XF_QHDIAGINV,     // nv
+  XF_EFC_MINVJT,    // njmax*nv rows of inv(M) J'   (matrix-free PGS / Newton helpers)
+  XF_EFC_ARDIAG,    // njmax   diagonal of AR = J inv(M) J' + R
+  XF_VEC0,          // nv scratch vectors
+  XF_VEC1, XF_VEC2, XF_VEC3, XF_VEC4, XF_VEC5,
+  XF_EFC_JAREF,     // njmax
+  XF_EFC_JV,        // njmax
+  XF_EFC_QUAD,      // 3*njmax
+  XF_NEWTON_H,      // nv*nv
+  XF_CONTACT_H,     // 36*nconmax
+  XF_SUBTREE_LINVEL,// 3*nbody
+  XF_SUBTREE_ANGMOM,// 3*nbody
+  XF_BODYVEL,       // 6*nbody
+  XF_RK_X0,         // nq+nv+na   RK4 saved state
+  XF_RK_XF,         // 4*nv       RK4 stage velocities
+  XF_RK_F,          // 4*(nv+na)  RK4 stage accelerations / act_dot
+  XF_RK_DX,         // 2*nv+na
+  XF_COUNT
+};
+
+struct DevModel {
+#define B2K_X_SIZE(n) int n;
+  B2MJ_MODEL_SIZES(B2K_X_SIZE)
+#undef B2K_X_SIZE
+  int nmaskword;  // words per body of body_dofmask
+  b2mjOption opt;
+  double meaninertia;
+#define B2K_X_ARR(t, n, r, c) const t* n;
+  B2MJ_MODEL_ARRAYS(B2K_X_ARR)
+#undef B2K_X_ARR
+  const unsigned* body_dofmask;  // [nbody][nmaskword]: bit k set if dof k is on the chain from the body to its root
+
+  // ---- arena layout (element offsets; doubles for f64 fields, ints for i32 fields) ----
+  int off_g[B2MJ_NFIELD];   // offset in the full per-env arena (always valid)
+  int off_s[B2MJ_NFIELD];   // offset in the shared-memory arena, -1 if the field is cold (global only)
+  int xoff_g[XF_COUNT];
+  int xoff_s[XF_COUNT];
+  int fsize[B2MJ_NFIELD];   // per-env element count of each field
+  unsigned char fis_int[B2MJ_NFIELD];
+  int xsize[XF_COUNT];
+  int arena_g_doubles, arena_g_ints;  // full arena sizes per env
+  int arena_s_doubles, arena_s_ints;  // shared-memory resident sizes per env
+  // ---- state record layout (doubles) ----
+  int rec_pitch;
+  int rec_ctrl, rec_qfrc_applied, rec_qpos, rec_qvel, rec_act, rec_warm, rec_time, rec_qacc, rec_sensordata, rec_act_dot;
+  int rec_A_begin, rec_B_begin, rec_C_begin, rec_end;  // 2-double aligned segment starts
+  // flags
+  int has_xfrc;            // xfrc_applied / mocap arrays are read (plugin-visible surface enabled)
+  int need_rnepost;        // some sensor needs cacc / cfrc_int
+  int need_subtreevel;
+  int any_damping;         // Euler implicit damping active
+};
+
+struct LaunchArgs {
+  double* rec;             // [nenv][rec_pitch]
+  double* garena_d;        // [nenv][arena_g_doubles]
+  int* garena_i;           // [nenv][arena_g_ints]
+  const double* xfrc;      // [nenv][6*nbody] or null
+  const double* mocap;     // [nenv][7*nmocap] (pos then quat) or null
+  int* warning;            // [nenv][B2MJ_NWARNING] cumulative
+  int* stats;              // [nenv][4]: ncon, nefc, solver_iter, reserved
+  int nenv;
+  int nsteps;
+  int mode;                // 0 step, 1 forward only, 2 step_begin (to control hook), 3 step_end
+  int dump;                // copy the shared arena to garena at the end
+};
+
+enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_STEP_BEGIN = 2, MODE_STEP_END = 3 };
+
+}  // namespace b2k

@@ -1,0 +1,304 @@
+// step_kernel.cu — the fused batched physics step for sm_100a: one env per warp, the env's mjData
+// arena resident in shared memory, state record moved HBM<->SMEM with 1-D TMA bulk copies.
+//
+// Replaces the `mj_step(model_.get(), data_.get())` call of the reference's physics loop
+// (mujoco_ros/src/mujoco_env.cpp:498,552,593) for a whole batch of independent envs; also
+// mj_forward (:329,:621) and the two halves around the control hook (mjcb_control placement,
+// mujoco_env.h:242-246).  Pipeline order follows SURVEY.md Appendix A.
+#include <cuda_runtime.h>
+
+#include "dev_model.h"
+#include "env_ctx.cuh"
+#include "stages_collision.cuh"
+#include "stages_constraint.cuh"
+#include "stages_sensor.cuh"
+#include "stages_smooth.cuh"
+#include "stages_solver.cuh"
+#include "step_launch.h"
+
+namespace b2k {
+
+__device__ __forceinline__ bool isBad(double x) { return isnan(x) || x > B2MJ_MAXVAL || x < -B2MJ_MAXVAL; }
+
+// mj_resetData on the resident state of one env
+__device__ void resetEnv(const Env& e, int* warning, int which) {
+  const DevModel& m = e.m;
+  double* qpos = e.D(B2MJ_F_QPOS);
+  FORL(i, m.nq) qpos[i] = m.qpos0[i];
+  double* qvel = e.D(B2MJ_F_QVEL);
+  double* warm = e.D(B2MJ_F_QACC_WARMSTART);
+  double* qap = e.D(B2MJ_F_QFRC_APPLIED);
+  double* qacc = e.D(B2MJ_F_QACC);
+  FORL(i, m.nv) { qvel[i] = 0; warm[i] = 0; qap[i] = 0; qacc[i] = 0; }
+  if (m.na) { double* act = e.D(B2MJ_F_ACT); FORL(i, m.na) act[i] = 0; }
+  if (m.nu) { double* ctrl = e.D(B2MJ_F_CTRL); FORL(i, m.nu) ctrl[i] = 0; }
+  if (m.nsensordata) { double* sd = e.D(B2MJ_F_SENSORDATA); FORL(i, m.nsensordata) sd[i] = 0; }
+  if (e.lane == 0) {
+    e.D(B2MJ_F_TIME)[0] = 0;
+    const int w = warning[which] + 1;
+    for (int k = 0; k < B2MJ_NWARNING; k++) warning[k] = 0;
+    warning[which] = w;
+  }
+  WSYNC();
+}
+
+struct StepCtx {
+  int ncon, nefc, iters;
+};
+
+// mj_forwardSkip split at the control hook
+__device__ void forwardPass(const Env& e, const LaunchArgs& a, int env, StepCtx& sc, bool skipsensor, bool first_half,
+                            bool second_half) {
+  const DevModel& m = e.m;
+  int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
+  const double* xfrc = (m.has_xfrc && a.xfrc) ? a.xfrc + (size_t)env * 6 * m.nbody : nullptr;
+  if (first_half) {
+    stage_kinematics(e);
+    stage_comPos(e);
+    stage_tendon_transmission(e);
+    stage_crb_factor(e);
+    sc.ncon = stage_collision(e, warning);
+    sc.nefc = stage_makeConstraint(e, sc.ncon, warning);
+    if (m.opt.solver == B2MJ_SOL_PGS) stage_projectConstraint(e, sc.nefc);
+    if (!skipsensor) stage_sensorPos(e, sc.nefc);
+    stage_velocity_head(e);
+    stage_comVel(e);
+    stage_passive(e);
+    stage_referenceConstraint(e, sc.nefc);
+    stage_rne_bias(e);
+    if (!skipsensor) stage_sensorVel(e, sc.nefc);
+  }
+  if (second_half) {
+    stage_actuation(e, warning);
+    stage_acceleration(e, xfrc);
+    sc.iters = stage_fwdConstraint(e, sc.nefc, sc.ncon);
+    if (!skipsensor) stage_sensorAcc(e, sc.nefc, sc.ncon, xfrc);
+  }
+}
+
+// mj_RungeKutta(4)
+__device__ void stage_rk4(const Env& e, const LaunchArgs& a, int env, StepCtx& sc) {
+  const DevModel& m = e.m;
+  const int nq = m.nq, nv = m.nv, na = m.na;
+  const double h = m.opt.timestep;
+  double* qpos = e.D(B2MJ_F_QPOS);
+  double* qvel = e.D(B2MJ_F_QVEL);
+  double* qacc = e.D(B2MJ_F_QACC);
+  double* act = na ? e.D(B2MJ_F_ACT) : nullptr;
+  double* act_dot = na ? e.D(B2MJ_F_ACT_DOT) : nullptr;
+  double* timep = e.D(B2MJ_F_TIME);
+  double* X0 = e.X(XF_RK_X0);      // nq + nv + na
+  double* Xf = e.X(XF_RK_XF);      // 4 * nv   stage velocities
+  double* F = e.X(XF_RK_F);        // 4 * (nv + na) stage accelerations / act_dot
+  double* dX = e.X(XF_RK_DX);      // 2*nv + na
+  const double time0 = timep[0];
+  const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1};
+  const double Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+  FORL(i, nq) X0[i] = qpos[i];
+  FORL(i, nv) { X0[nq + i] = qvel[i]; Xf[i] = qvel[i]; F[i] = qacc[i]; }
+  FORL(i, na) { X0[nq + nv + i] = act[i]; F[nv + i] = act_dot[i]; }
+  WSYNC();
+  for (int s = 1; s < 4; s++) {
+    FORL(k, nv) {
+      double dv = 0, da = 0;
+      for (int j = 0; j < 3; j++) {
+        const double c = A[(s - 1) * 3 + j];
+        if (c == 0) continue;
+        dv += c * Xf[j * nv + k];
+        da += c * F[j * (nv + na) + k];
+      }
+      dX[k] = dv;
+      dX[nv + k] = da;
+    }
+    FORL(k, na) {
+      double d = 0;
+      for (int j = 0; j < 3; j++) {
+        const double c = A[(s - 1) * 3 + j];
+        if (c != 0) d += c * F[j * (nv + na) + nv + k];
+      }
+      dX[2 * nv + k] = d;
+    }
+    FORL(i, nq) qpos[i] = X0[i];
+    WSYNC();
+    integratePos_warp(e, qpos, dX, h);
+    FORL(k, nv) qvel[k] = X0[nq + k] + h * dX[nv + k];
+    FORL(k, na) act[k] = X0[nq + nv + k] + h * dX[2 * nv + k];
+    if (e.lane == 0) timep[0] = time0 + (s == 3 ? 1.0 : 0.5) * h;
+    WSYNC();
+    forwardPass(e, a, env, sc, true, true, true);
+    FORL(k, nv) { Xf[s * nv + k] = qvel[k]; F[s * (nv + na) + k] = qacc[k]; }
+    FORL(k, na) F[s * (nv + na) + nv + k] = act_dot[k];
+    WSYNC();
+  }
+  FORL(k, nv) {
+    double dv = 0, da = 0;
+    for (int j = 0; j < 4; j++) { dv += Bw[j] * Xf[j * nv + k]; da += Bw[j] * F[j * (nv + na) + k]; }
+    dX[k] = dv;
+    dX[nv + k] = da;
+  }
+  FORL(k, na) {
+    double d = 0;
+    for (int j = 0; j < 4; j++) d += Bw[j] * F[j * (nv + na) + nv + k];
+    dX[2 * nv + k] = d;
+  }
+  FORL(i, nq) qpos[i] = X0[i];
+  FORL(i, nv) qvel[i] = X0[nq + i];
+  FORL(i, na) act[i] = X0[nq + nv + i];
+  if (e.lane == 0) timep[0] = time0;
+  WSYNC();
+  advance_warp(e, dX + 2 * nv, dX + nv, dX);
+}
+
+__global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_constant__ DevModel m, const LaunchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int env = blockIdx.x * nwarp + warp;
+  if (env >= a.nenv) return;  // whole warp exits; no CTA-wide barrier is used below
+
+  // shared layout: [nwarp mbarriers, 16B each][nwarp env blocks: doubles | ints]
+  const size_t env_bytes = (((size_t)m.arena_s_doubles * 8 + (size_t)m.arena_s_ints * 4) + 15) & ~(size_t)15;
+  unsigned char* base = smem_raw + 16 * nwarp + (size_t)warp * env_bytes;
+  double* sd = reinterpret_cast<double*>(base);
+  int* si = reinterpret_cast<int*>(base + (size_t)m.arena_s_doubles * 8);
+  double* gd = a.garena_d + (size_t)env * m.arena_g_doubles;
+  int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
+  Env e{m, sd, si, gd, gi, lane};
+  int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
+  double* rec = a.rec + (size_t)env * m.rec_pitch;
+
+  // ---- resume a split step: bring the arena back from HBM ----
+  if (a.mode == MODE_STEP_END) {
+    for (int f = 0; f < B2MJ_NFIELD; f++) {
+      const int os = m.off_s[f];
+      if (os < 0) continue;
+      if (m.fis_int[f]) { FORL(k, m.fsize[f]) si[os + k] = gi[m.off_g[f] + k]; }
+      else { FORL(k, m.fsize[f]) sd[os + k] = gd[m.off_g[f] + k]; }
+    }
+    for (int f = 0; f < XF_COUNT; f++) {
+      const int os = m.xoff_s[f];
+      if (os < 0) continue;
+      FORL(k, m.xsize[f]) sd[os + k] = gd[m.xoff_g[f] + k];
+    }
+    WSYNC();
+  }
+
+  // ---- state record: HBM -> SMEM with one TMA bulk copy (segments A+B are contiguous) ----
+  const unsigned bar = smem_u32(smem_raw + 16 * warp);
+  const unsigned load_bytes = (unsigned)(m.rec_C_begin - m.rec_A_begin) * 8u;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  WSYNC();
+  if (lane == 0) {
+    mbar_expect_tx(bar, load_bytes);
+    bulk_g2s(smem_u32(sd + m.rec_A_begin), rec + m.rec_A_begin, load_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  if (m.nmocap && a.mocap) {
+    const double* src = a.mocap + (size_t)env * 7 * m.nmocap;
+    double* mp = e.D(B2MJ_F_MOCAP_POS);
+    double* mq = e.D(B2MJ_F_MOCAP_QUAT);
+    FORL(k, 3 * m.nmocap) mp[k] = src[k];
+    FORL(k, 4 * m.nmocap) mq[k] = src[3 * m.nmocap + k];
+  }
+  WSYNC();
+
+  StepCtx sc;
+  sc.ncon = 0; sc.nefc = 0; sc.iters = 0;
+  if (a.mode == MODE_STEP_END) {
+    sc.ncon = e.I(B2MJ_F_NCON)[0];
+    sc.nefc = e.I(B2MJ_F_NEFC)[0];
+  }
+
+  const int nsteps = (a.mode == MODE_STEP) ? a.nsteps : 1;
+  for (int step = 0; step < nsteps; step++) {
+    if (a.mode != MODE_STEP_END && a.mode != MODE_FORWARD) {
+      // mj_checkPos / mj_checkVel
+      int bad = 0;
+      { const double* q = e.D(B2MJ_F_QPOS); FORL(i, m.nq) bad |= isBad(q[i]); }
+      if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQPOS);
+      bad = 0;
+      { const double* v = e.D(B2MJ_F_QVEL); FORL(i, m.nv) bad |= isBad(v[i]); }
+      if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
+    }
+    const bool first = a.mode != MODE_STEP_END, second = a.mode != MODE_STEP_BEGIN;
+    forwardPass(e, a, env, sc, false, first, second);
+    if (a.mode == MODE_FORWARD || a.mode == MODE_STEP_BEGIN) break;
+    // mj_checkAcc
+    {
+      int bad = 0;
+      const double* qa = e.D(B2MJ_F_QACC);
+      FORL(i, m.nv) bad |= isBad(qa[i]);
+      if (__any_sync(0xffffffffu, bad)) {
+        resetEnv(e, warning, B2MJ_WARN_BADQACC);
+        forwardPass(e, a, env, sc, false, true, true);
+      }
+    }
+    if (m.opt.integrator == B2MJ_INT_RK4 && a.mode == MODE_STEP) stage_rk4(e, a, env, sc);
+    else stage_euler(e);
+  }
+
+  // ---- results: counters, state record SMEM -> HBM (segments B+C contiguous), optional arena dump ----
+  if (lane == 0) {
+    int* st = a.stats + (size_t)env * 4;
+    st[0] = sc.ncon; st[1] = sc.nefc; st[2] = sc.iters; st[3] = 0;
+    e.I(B2MJ_F_SOLVER_ITER)[0] = sc.iters;
+    for (int k = 0; k < B2MJ_NWARNING; k++) e.I(B2MJ_F_WARNING)[k] = warning[k];
+  }
+  fence_async_smem();
+  WSYNC();
+  if (lane == 0) {
+    // MODE_STEP_BEGIN keeps qpos (normalised quaternions) consistent too: store B+C in every mode
+    bulk_s2g(rec + m.rec_B_begin, smem_u32(sd + m.rec_B_begin), (unsigned)(m.rec_end - m.rec_B_begin) * 8u);
+    bulk_commit_wait();
+  }
+  if (a.dump || a.mode == MODE_STEP_BEGIN) {
+    for (int f = 0; f < B2MJ_NFIELD; f++) {
+      const int os = m.off_s[f];
+      if (os < 0) continue;
+      if (m.fis_int[f]) { FORL(k, m.fsize[f]) gi[m.off_g[f] + k] = si[os + k]; }
+      else { FORL(k, m.fsize[f]) gd[m.off_g[f] + k] = sd[os + k]; }
+    }
+    for (int f = 0; f < XF_COUNT; f++) {
+      const int os = m.xoff_s[f];
+      if (os < 0) continue;
+      FORL(k, m.xsize[f]) gd[m.xoff_g[f] + k] = sd[os + k];
+    }
+  }
+  WSYNC();
+}
+
+}  // namespace b2k
+
+using namespace b2k;
+
+extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps_per_cta, size_t smem_bytes,
+                               cudaStream_t stream) {
+  static bool attr_set = false;
+  static size_t attr_bytes = 0;
+  if (!attr_set || smem_bytes > attr_bytes) {
+    cudaError_t err = cudaFuncSetAttribute(b2k_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return (int)err;
+    attr_set = true;
+    attr_bytes = smem_bytes;
+  }
+  const int ctas = (a->nenv + warps_per_cta - 1) / warps_per_cta;
+  b2k_step_kernel<<<ctas, warps_per_cta * 32, smem_bytes, stream>>>(*m, *a);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2k_step_kernel_attrs(int* regs, int* static_smem, int* max_threads) {
+  cudaFuncAttributes at;
+  cudaError_t err = cudaFuncGetAttributes(&at, b2k_step_kernel);
+  if (err != cudaSuccess) return (int)err;
+  if (regs) *regs = at.numRegs;
+  if (static_smem) *static_smem = (int)at.sharedSizeBytes;
+  if (max_threads) *max_threads = at.maxThreadsPerBlock;
+  return 0;
+}
+
+extern "C" int b2k_occupancy(int threads, size_t smem_bytes, int* ctas_per_sm) {
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, b2k_step_kernel, threads, smem_bytes);
+  return (int)err;
+}

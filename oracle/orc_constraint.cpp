@@ -218,6 +218,7 @@ static void instantiateContact(const b2mjModel* m, OrcData* d) {
       ok = addConstraint(m, d, jac.data(), cpos, cmargin, 0, dim, B2MJ_CNSTR_CONTACT_ELLIPTIC, c);
     }
     d->contact_efc_address[c] = ok ? adr : -1;
+    if (!ok) break;  // row capacity reached: this and all later contacts are dropped (CNSTRFULL)
   }
 }
 
