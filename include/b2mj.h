@@ -309,6 +309,11 @@ int b2mj_set_keep_intermediates(b2mj_handle* h, int on);
  * bytes must equal nenv*count*elemsize.  Synchronous w.r.t. the handle's stream. */
 int b2mj_get(b2mj_handle* h, b2mj_field f, void* host_dst, size_t bytes);
 int b2mj_set(b2mj_handle* h, b2mj_field f, const void* host_src, size_t bytes);
+/* device-side write of a settable field from a DEVICE buffer laid out [nenv][src_pitch_elems]
+ * (src_pitch_elems 0 = tightly packed), asynchronous on the handle's stream: what a device-resident
+ * controller / policy uses where a host plugin would write d->ctrl inside controlCallback
+ * (plugin_utils.h:89-97). */
+int b2mj_set_device(b2mj_handle* h, b2mj_field f, const void* dev_src, size_t src_pitch_elems);
 /* device pointer + env pitch (in elements) of a resident state/input/output field, for device-side
  * plugins and policies (valid until destroy).  Element k of env e is ptr[e*pitch + k]. */
 int b2mj_device_ptr(b2mj_handle* h, b2mj_field f, void** dev_ptr, size_t* pitch_elems);
@@ -368,6 +373,13 @@ typedef struct b2mjLaunchInfo {
   uint64_t launches;      /* kernels launched through this handle so far */
 } b2mjLaunchInfo;
 int b2mj_launch_info(b2mj_handle* h, b2mjLaunchInfo* out);
+
+/* per-stage SM-cycle profile of the fused step (the kernel-internal counterpart of MuJoCo's d->timer[],
+ * which the reference's viewer profiler pane reads: viewer.cpp:283-380).  enable=1 starts / clears the
+ * counters, enable=0 stops; cycles (may be NULL) receives the totals accumulated so far, summed over
+ * envs, one entry per stage (b2mj_stage_name).  Returns the number of stages. */
+int b2mj_stage_profile(b2mj_handle* h, int enable, uint64_t* cycles, int ncycles);
+const char* b2mj_stage_name(int stage);
 
 const char* b2mj_last_error(void);
 int b2mj_version(void);

@@ -27,6 +27,10 @@ lib.b2mj_sync.argtypes = [_vp]
 lib.b2mj_set_keep_intermediates.argtypes = [_vp, C.c_int]
 lib.b2mj_get.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
 lib.b2mj_set.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
+lib.b2mj_set_device.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
+lib.b2mj_stage_profile.argtypes = [_vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
+lib.b2mj_stage_name.argtypes = [C.c_int]
+lib.b2mj_stage_name.restype = C.c_char_p
 lib.b2mj_device_ptr.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t)]
 lib.b2mj_model_update.argtypes = [_vp, _vp]
 lib.b2mj_launch_info.argtypes = [_vp, C.POINTER(_capi.B2mjLaunchInfo)]
@@ -103,6 +107,17 @@ class BatchSim:
                                                    (self.nenv, n)))
         check(lib.b2mj_set(self._h, f, arr.ctypes.data, arr.nbytes), f"set {name}")
 
+    def get_into(self, name: str, out: np.ndarray):
+        """b2mj_get into a caller-provided (e.g. pinned) host array."""
+        check(lib.b2mj_get(self._h, _capi.field_id(name), out.ctypes.data, out.nbytes), f"get {name}")
+
+    def set_from(self, name: str, arr: np.ndarray):
+        """b2mj_set from a caller-provided (e.g. pinned) contiguous host array."""
+        check(lib.b2mj_set(self._h, _capi.field_id(name), arr.ctypes.data, arr.nbytes), f"set {name}")
+
+    def set_device(self, name: str, dev_ptr: int, pitch_elems: int = 0):
+        check(lib.b2mj_set_device(self._h, _capi.field_id(name), _vp(dev_ptr), pitch_elems), f"set_device {name}")
+
     def device_ptr(self, name: str):
         p, pitch = _vp(), C.c_size_t()
         check(lib.b2mj_device_ptr(self._h, _capi.field_id(name), C.byref(p), C.byref(pitch)), f"device_ptr {name}")
@@ -115,6 +130,12 @@ class BatchSim:
         li = _capi.B2mjLaunchInfo()
         check(lib.b2mj_launch_info(self._h, C.byref(li)), "launch_info")
         return {k: getattr(li, k) for k, _ in li._fields_}
+
+    def stage_profile(self, enable: bool = True) -> dict:
+        """Read (then clear / stop) the per-stage cycle counters: {stage: cycles summed over envs}."""
+        buf = (C.c_uint64 * 64)()
+        n = check(lib.b2mj_stage_profile(self._h, int(enable), buf, 64), "stage_profile")
+        return {lib.b2mj_stage_name(i).decode(): int(buf[i]) for i in range(n)}
 
     # ---- plugin data paths ----
     def robot_hw_configure(self, joint_ids, modes, effort_limit=None, pid=None, lower=None, upper=None, kind=None):

@@ -53,6 +53,15 @@ __global__ void reset_kernel(double* rec, const double* rec_init, int pitch, int
   if (mocap) for (int k = threadIdx.x; k < nmocap7; k += blockDim.x) mocap[(size_t)env * nmocap7 + k] = mocap_init[k];
 }
 
+// device-to-device field write: dst[env*dpitch + k] = src[env*spitch + k] (32-bit words)
+__global__ void scatter_field_kernel(unsigned* dst, int dpitch, const unsigned* src, int spitch, int words, int nenv) {
+  const long long total = (long long)nenv * words;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int env = (int)(i / words), k = (int)(i - (long long)env * words);
+    dst[(size_t)env * dpitch + k] = src[(size_t)env * spitch + k];
+  }
+}
+
 static int field_count(const b2mjModel* m, int f, int* is_int) {
   if (f == B2MJ_F_EFC_AR) {  // the GPU solver is matrix-free: AR is never materialised
     if (is_int) *is_int = 0;
@@ -347,6 +356,7 @@ int handle_launch(Handle* h, int mode, int nsteps) {
   a.nsteps = nsteps;
   a.mode = mode;
   a.dump = h->keep_intermediates;
+  a.prof = h->prof;
   const int rc = b2k_launch_step(&h->dm, &a, h->warps_per_cta, h->smem_bytes, h->stream);
   if (rc != 0) {
     set_error(std::string("step kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
@@ -411,6 +421,7 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->model_blob); cudaFree(h->rec); cudaFree(h->rec_init); cudaFree(h->garena_d); cudaFree(h->garena_i);
   cudaFree(h->warning); cudaFree(h->stats); cudaFree(h->xfrc); cudaFree(h->mocap); cudaFree(h->mocap_init);
   cudaFree(h->mask_dev);
+  cudaFree(h->prof);
   handle_free_plugins(h);
   b2mj_model_free(h->model);
   delete h;
@@ -560,8 +571,9 @@ int b2mj_get(b2mj_handle* hh, b2mj_field f, void* host_dst, size_t bytes) {
   if (int rc = locate(h, f, false, &base, &pitch, &es, &n)) return rc;
   if (bytes != (size_t)h->nenv * n * es) { set_error("b2mj_get: byte count mismatch"); return B2MJ_EINVAL; }
   if (n == 0) return 0;
+  // ordered on the handle's stream (full-speed DMA when host_dst is pinned), then waited for
+  CUDA_OK(cudaMemcpy2DAsync(host_dst, n * es, base, pitch, n * es, h->nenv, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
-  CUDA_OK(cudaMemcpy2D(host_dst, n * es, base, pitch, n * es, h->nenv, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -573,8 +585,31 @@ int b2mj_set(b2mj_handle* hh, b2mj_field f, const void* host_src, size_t bytes) 
   if (int rc = locate(h, f, true, &base, &pitch, &es, &n)) return rc;
   if (bytes != (size_t)h->nenv * n * es) { set_error("b2mj_set: byte count mismatch"); return B2MJ_EINVAL; }
   if (n == 0) return 0;
+  CUDA_OK(cudaMemcpy2DAsync(base, pitch, host_src, n * es, n * es, h->nenv, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
-  CUDA_OK(cudaMemcpy2D(base, pitch, host_src, n * es, n * es, h->nenv, cudaMemcpyHostToDevice));
+  if (f == B2MJ_F_XFRC_APPLIED) h->dm.has_xfrc = 1;
+  return 0;
+}
+
+int b2mj_set_device(b2mj_handle* hh, b2mj_field f, const void* dev_src, size_t src_pitch_elems) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !dev_src) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  unsigned char* base; size_t pitch, es; int n;
+  if (int rc = locate(h, f, true, &base, &pitch, &es, &n)) return rc;
+  if (n == 0) return 0;
+  if (src_pitch_elems == 0) src_pitch_elems = (size_t)n;
+  if (src_pitch_elems < (size_t)n) { set_error("b2mj_set_device: source pitch smaller than the field"); return B2MJ_EINVAL; }
+  // both element sizes are multiples of 4 bytes: scatter as 32-bit words
+  const int words = (int)(n * es / 4);
+  const long long total = (long long)h->nenv * words;
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148 * 16);
+  scatter_field_kernel<<<blocks, threads, 0, h->stream>>>(reinterpret_cast<unsigned*>(base), (int)(pitch / 4),
+                                                          reinterpret_cast<const unsigned*>(dev_src),
+                                                          (int)(src_pitch_elems * es / 4), words, h->nenv);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
   if (f == B2MJ_F_XFRC_APPLIED) h->dm.has_xfrc = 1;
   return 0;
 }
@@ -617,6 +652,32 @@ int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
   if (int rc = upload_model(h)) return rc;
   h->dm.has_xfrc = has_xfrc;
   return upload_init_templates(h);
+}
+
+int b2mj_stage_profile(b2mj_handle* hh, int enable, uint64_t* cycles, int ncycles) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (cycles && h->prof) {
+    unsigned long long host[PROF_COUNT];
+    CUDA_OK(cudaMemcpy(host, h->prof, sizeof(host), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < ncycles; i++) cycles[i] = i < PROF_COUNT ? host[i] : 0;
+  } else if (cycles) {
+    for (int i = 0; i < ncycles; i++) cycles[i] = 0;
+  }
+  if (enable && !h->prof) CUDA_OK(cudaMalloc(&h->prof, PROF_COUNT * sizeof(unsigned long long)));
+  if (enable) CUDA_OK(cudaMemset(h->prof, 0, PROF_COUNT * sizeof(unsigned long long)));
+  if (!enable && h->prof) { cudaFree(h->prof); h->prof = nullptr; }
+  return PROF_COUNT;
+}
+
+const char* b2mj_stage_name(int stage) {
+  static const char* names[PROF_COUNT] = {"load", "kinematics", "comPos", "tendon_transmission", "crb_factorM", "collision",
+                                          "makeConstraint", "projectConstraint", "sensorPos", "velocity_head", "comVel",
+                                          "passive", "referenceConstraint", "rne_bias", "sensorVel", "actuation",
+                                          "acceleration", "solve", "sensorAcc", "integrate", "store"};
+  return stage >= 0 && stage < PROF_COUNT ? names[stage] : nullptr;
 }
 
 int b2mj_launch_info(b2mj_handle* hh, b2mjLaunchInfo* out) {

@@ -30,6 +30,7 @@ struct Handle {
   double* mocap = nullptr;        // [nenv][7*nmocap]
   double* mocap_init = nullptr;
   unsigned char* mask_dev = nullptr;
+  unsigned long long* prof = nullptr;  // [PROF_COUNT] stage cycle totals (b2mj_stage_profile), null = off
 
   int warps_per_cta = 4;
   size_t smem_bytes = 0;

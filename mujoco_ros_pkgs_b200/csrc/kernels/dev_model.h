@@ -86,6 +86,14 @@ struct LaunchArgs {
   int nsteps;
   int mode;                // 0 step, 1 forward only, 2 step_begin (to control hook), 3 step_end
   int dump;                // copy the shared arena to garena at the end
+  unsigned long long* prof; // [PROF_COUNT] per-stage SM-cycle totals over all envs, or null (b2mj_stage_profile)
+};
+
+// stage ids of the optional cycle profile
+enum ProfStage {
+  PROF_LOAD = 0, PROF_KINEMATICS, PROF_COMPOS, PROF_TENDON, PROF_CRB_FACTOR, PROF_COLLISION, PROF_MAKECONSTRAINT,
+  PROF_PROJECT, PROF_SENSORPOS, PROF_VELHEAD, PROF_COMVEL, PROF_PASSIVE, PROF_REFCONSTRAINT, PROF_RNE, PROF_SENSORVEL,
+  PROF_ACTUATION, PROF_ACCELERATION, PROF_SOLVE, PROF_SENSORACC, PROF_INTEGRATE, PROF_STORE, PROF_COUNT
 };
 
 enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_STEP_BEGIN = 2, MODE_STEP_END = 3 };

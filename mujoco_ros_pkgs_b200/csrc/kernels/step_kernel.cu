@@ -44,7 +44,15 @@ __device__ void resetEnv(const Env& e, int* warning, int which) {
 
 struct StepCtx {
   int ncon, nefc, iters;
+  long long t_prev;  // stage profile (only touched when LaunchArgs::prof is set)
 };
+
+#define PROF_MARK(id)                                                              \
+  if (a.prof) {                                                                    \
+    const long long _now = clock64();                                              \
+    if (e.lane == 0) atomicAdd(a.prof + (id), (unsigned long long)(_now - sc.t_prev)); \
+    sc.t_prev = _now;                                                              \
+  }
 
 // mj_forwardSkip split at the control hook
 __device__ void forwardPass(const Env& e, const LaunchArgs& a, int env, StepCtx& sc, bool skipsensor, bool first_half,
@@ -53,26 +61,30 @@ __device__ void forwardPass(const Env& e, const LaunchArgs& a, int env, StepCtx&
   int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
   const double* xfrc = (m.has_xfrc && a.xfrc) ? a.xfrc + (size_t)env * 6 * m.nbody : nullptr;
   if (first_half) {
-    stage_kinematics(e);
-    stage_comPos(e);
-    stage_tendon_transmission(e);
-    stage_crb_factor(e);
-    sc.ncon = stage_collision(e, warning);
-    sc.nefc = stage_makeConstraint(e, sc.ncon, warning);
+    stage_kinematics(e); PROF_MARK(PROF_KINEMATICS)
+    stage_comPos(e); PROF_MARK(PROF_COMPOS)
+    stage_tendon_transmission(e); PROF_MARK(PROF_TENDON)
+    stage_crb_factor(e); PROF_MARK(PROF_CRB_FACTOR)
+    sc.ncon = stage_collision(e, warning); PROF_MARK(PROF_COLLISION)
+    sc.nefc = stage_makeConstraint(e, sc.ncon, warning); PROF_MARK(PROF_MAKECONSTRAINT)
     if (m.opt.solver == B2MJ_SOL_PGS) stage_projectConstraint(e, sc.nefc);
+    PROF_MARK(PROF_PROJECT)
     if (!skipsensor) stage_sensorPos(e, sc.nefc);
-    stage_velocity_head(e);
-    stage_comVel(e);
-    stage_passive(e);
-    stage_referenceConstraint(e, sc.nefc);
-    stage_rne_bias(e);
+    PROF_MARK(PROF_SENSORPOS)
+    stage_velocity_head(e); PROF_MARK(PROF_VELHEAD)
+    stage_comVel(e); PROF_MARK(PROF_COMVEL)
+    stage_passive(e); PROF_MARK(PROF_PASSIVE)
+    stage_referenceConstraint(e, sc.nefc); PROF_MARK(PROF_REFCONSTRAINT)
+    stage_rne_bias(e); PROF_MARK(PROF_RNE)
     if (!skipsensor) stage_sensorVel(e, sc.nefc);
+    PROF_MARK(PROF_SENSORVEL)
   }
   if (second_half) {
-    stage_actuation(e, warning);
-    stage_acceleration(e, xfrc);
-    sc.iters = stage_fwdConstraint(e, sc.nefc, sc.ncon);
+    stage_actuation(e, warning); PROF_MARK(PROF_ACTUATION)
+    stage_acceleration(e, xfrc); PROF_MARK(PROF_ACCELERATION)
+    sc.iters = stage_fwdConstraint(e, sc.nefc, sc.ncon); PROF_MARK(PROF_SOLVE)
     if (!skipsensor) stage_sensorAcc(e, sc.nefc, sc.ncon, xfrc);
+    PROF_MARK(PROF_SENSORACC)
   }
 }
 
@@ -166,6 +178,10 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_
   int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
   double* rec = a.rec + (size_t)env * m.rec_pitch;
 
+  StepCtx sc;
+  sc.ncon = 0; sc.nefc = 0; sc.iters = 0;
+  sc.t_prev = a.prof ? clock64() : 0;
+
   // ---- resume a split step: bring the arena back from HBM ----
   if (a.mode == MODE_STEP_END) {
     for (int f = 0; f < B2MJ_NFIELD; f++) {
@@ -204,8 +220,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_
   }
   WSYNC();
 
-  StepCtx sc;
-  sc.ncon = 0; sc.nefc = 0; sc.iters = 0;
+  PROF_MARK(PROF_LOAD)
   if (a.mode == MODE_STEP_END) {
     sc.ncon = e.I(B2MJ_F_NCON)[0];
     sc.nefc = e.I(B2MJ_F_NEFC)[0];
@@ -237,6 +252,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_
     }
     if (m.opt.integrator == B2MJ_INT_RK4 && a.mode == MODE_STEP) stage_rk4(e, a, env, sc);
     else stage_euler(e);
+    PROF_MARK(PROF_INTEGRATE)
   }
 
   // ---- results: counters, state record SMEM -> HBM (segments B+C contiguous), optional arena dump ----
@@ -267,6 +283,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_
     }
   }
   WSYNC();
+  PROF_MARK(PROF_STORE)
 }
 
 }  // namespace b2k

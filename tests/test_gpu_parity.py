@@ -1,0 +1,302 @@
+"""GPU parity tests proper: the CUDA batched step (through the C-ABI) against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and through size-independent properties
+at the BASELINE batch size.  Tolerance: 1e-5 relative per step in FP64 (BASELINE.json north_star);
+time and contact-pair indexing bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b) / (1.0 + np.abs(b)))) if a.size else 0.0
+
+
+def perturbed(model, nenv, seed, amp=0.1):
+    rng = np.random.default_rng(seed)
+    qpos = np.tile(model.qpos0, (nenv, 1))
+    qvel = np.zeros((nenv, model.nv))
+    for j in range(model.njnt):
+        t, qa, da = model.jnt_type[j], model.jnt_qposadr[j], model.jnt_dofadr[j]
+        if t == 0:
+            qpos[:, qa:qa + 2] += rng.uniform(-amp, amp, (nenv, 2))
+            q = qpos[:, qa + 3:qa + 7] + rng.uniform(-amp, amp, (nenv, 4))
+            qpos[:, qa + 3:qa + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+            qvel[:, da:da + 6] = rng.uniform(-amp, amp, (nenv, 6))
+        elif t == 1:
+            q = qpos[:, qa:qa + 4] + rng.uniform(-amp, amp, (nenv, 4))
+            qpos[:, qa:qa + 4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+            qvel[:, da:da + 3] = rng.uniform(-amp, amp, (nenv, 3))
+        else:
+            qpos[:, qa] += rng.uniform(-amp, amp, nenv)
+            qvel[:, da] = rng.uniform(-amp, amp, nenv)
+    return qpos, qvel
+
+
+def ctrl_sample(model, rng, nenv):
+    if not model.nu:
+        return np.zeros((nenv, 0))
+    lo, hi = model.actuator_ctrlrange[:, 0], model.actuator_ctrlrange[:, 1]
+    return rng.uniform(lo, hi, (nenv, model.nu))
+
+
+@pytest.fixture(scope="module")
+def BatchSim():
+    from mujoco_ros_pkgs_b200.batch import BatchSim as B
+
+    return B
+
+
+@pytest.mark.parametrize("name", ["panda_like.xml", "pendulum_scene.xml", "equality_scene.xml"])
+def test_forward_fields_match_oracle(name, load_model, orc, capi, BatchSim):
+    """Every mjData field after mj_forward, env by env (per-stage diff)."""
+    model = load_model(name)
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 11)
+    ctrl = ctrl_sample(model, np.random.default_rng(5), nenv)
+    sim = BatchSim(model, nenv)
+    sim.keep_intermediates(True)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    if model.nu:
+        sim.set("ctrl", ctrl)
+    sim.forward()
+    ncon_g, nefc_g = sim.get("ncon")[:, 0], sim.get("nefc")[:, 0]
+    skip = {"efc_AR", "xfrc_applied", "warning", "solver_iter", "cacc", "cfrc_int", "cfrc_ext", "efc_state"}
+    for e in range(nenv):
+        o = orc.Oracle(model)
+        o.set("qpos", qpos[e])
+        o.set("qvel", qvel[e])
+        if model.nu:
+            o.set("ctrl", ctrl[e])
+        o.forward()
+        assert o.get("ncon")[0] == ncon_g[e] and o.get("nefc")[0] == nefc_g[e]
+        for fname in capi.FIELD_NAMES:
+            n, is_int = model.field_size(capi.field_id(fname))
+            if fname in skip or n <= 0:
+                continue
+            gv, ov = sim.get(fname)[e], o.get(fname)
+            if fname.startswith("contact_"):
+                k = (n // model.nconmax) * ncon_g[e]
+                gv, ov = gv[:k], ov[:k]
+            elif fname.startswith("efc_"):
+                k = (n // model.njmax) * nefc_g[e]
+                gv, ov = gv[:k], ov[:k]
+            if is_int:
+                np.testing.assert_array_equal(gv, ov, err_msg=f"{name}:{fname} env {e}")
+            else:
+                scale = 1e-12 + np.max(np.abs(ov)) if ov.size else 1.0
+                assert np.max(np.abs(gv - ov)) / scale < 1e-8 if ov.size else True, f"{name}:{fname} env {e}"
+
+
+@pytest.mark.parametrize("name,nsteps", [("panda_like.xml", 1000), ("pendulum_scene.xml", 300), ("equality_scene.xml", 300)])
+def test_rollout_matches_oracle(name, nsteps, load_model, orc, BatchSim):
+    """State divergence vs the oracle < 1e-5 per step and over the rollout; time bit-exact;
+    contact-pair indices identical (checked at every 50th step)."""
+    model = load_model(name)
+    nenv = 16
+    qpos, qvel = perturbed(model, nenv, 21)
+    rng = np.random.default_rng(9)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = []
+    for e in range(nenv):
+        o = orc.Oracle(model)
+        o.set("qpos", qpos[e])
+        o.set("qvel", qvel[e])
+        oracles.append(o)
+    worst = 0.0
+    for s in range(1, nsteps + 1):
+        ctrl = ctrl_sample(model, rng, nenv)
+        if model.nu:
+            sim.set("ctrl", ctrl)
+        sim.step(1)
+        for e, o in enumerate(oracles):
+            if model.nu:
+                o.set("ctrl", ctrl[e])
+            o.step(1)
+        if s % 50 == 0 or s == 1 or s == nsteps:
+            gq, gv, gt = sim.get("qpos"), sim.get("qvel"), sim.get("time")[:, 0]
+            oq = np.stack([o.get("qpos") for o in oracles])
+            ov = np.stack([o.get("qvel") for o in oracles])
+            worst = max(worst, rel(gq, oq), rel(gv, ov))
+            np.testing.assert_array_equal(gt, [o.time for o in oracles])
+            assert worst < TOL, f"{name}: state diverged at step {s}: {worst:.3e}"
+    sim.keep_intermediates(True)
+    sim.forward()
+    ncon = sim.get("ncon")[:, 0]
+    g1, g2 = sim.get("contact_geom1"), sim.get("contact_geom2")
+    for e, o in enumerate(oracles):
+        o.forward()
+        assert o.get("ncon")[0] == ncon[e]
+        np.testing.assert_array_equal(g1[e][:ncon[e]], o.get("contact_geom1")[:ncon[e]])
+        np.testing.assert_array_equal(g2[e][:ncon[e]], o.get("contact_geom2")[:ncon[e]])
+
+
+@pytest.mark.parametrize("name", ["panda_like", "pendulum_scene", "equality_scene"])
+def test_golden_trajectories(name, load_model, BatchSim):
+    """Committed fixtures (tools/make_golden.py): same inputs in every env, same trajectory out."""
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    model = load_model(f"{name}.xml")
+    nenv = 5
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", np.tile(g["qpos_init"], (nenv, 1)))
+    sim.set("qvel", np.tile(g["qvel_init"], (nenv, 1)))
+    for k in range(g["qpos"].shape[0]):
+        if model.nu:
+            sim.set("ctrl", np.tile(g["ctrl"][k], (nenv, 1)))
+        sim.step(int(g["stride"]))
+        q, v = sim.get("qpos"), sim.get("qvel")
+        assert rel(q, np.tile(g["qpos"][k], (nenv, 1))) < TOL, (name, k)
+        assert rel(v, np.tile(g["qvel"][k], (nenv, 1))) < TOL, (name, k)
+        np.testing.assert_array_equal(q, np.tile(q[0], (nenv, 1)))  # envs are bitwise replicas
+
+
+def test_time_and_guards(load_model, capi, BatchSim):
+    # mujoco_env_test.cpp:198-200,219-221 (time), :255-275 (n <= 0 refused)
+    model = load_model("pendulum_scene.xml")
+    sim = BatchSim(model, 3)
+    sim.step(1)
+    np.testing.assert_array_equal(sim.get("time")[:, 0], model.opt.timestep)
+    sim.step(99)
+    assert np.all(np.abs(sim.get("time")[:, 0] - 100 * model.opt.timestep) < 1e-6)
+    with pytest.raises(capi.B2mjError):
+        sim.step(0)
+    with pytest.raises(capi.B2mjError):
+        sim.step(-3)
+    with pytest.raises(capi.B2mjError):
+        sim.step_end()  # without step_begin
+
+
+def test_reset_all_and_masked(load_model, BatchSim):
+    # mujoco_env_test.cpp:507,519-526; masked form = per-env mj_resetData
+    model = load_model("pendulum_scene.xml")
+    nenv = 6
+    sim = BatchSim(model, nenv)
+    qpos, qvel = perturbed(model, nenv, 3)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    sim.step(25)
+    before_q = sim.get("qpos")
+    mask = np.array([1, 0, 1, 0, 0, 1], dtype=np.uint8)
+    sim.reset(mask)
+    q, v, t = sim.get("qpos"), sim.get("qvel"), sim.get("time")[:, 0]
+    for e in range(nenv):
+        if mask[e]:
+            np.testing.assert_array_equal(q[e], model.qpos0)
+            np.testing.assert_array_equal(v[e], 0)
+            assert t[e] == 0
+        else:
+            np.testing.assert_array_equal(q[e], before_q[e])
+            assert t[e] > 0
+    sim.reset()
+    np.testing.assert_array_equal(sim.get("qpos"), np.tile(model.qpos0, (nenv, 1)))
+    np.testing.assert_array_equal(sim.get("time"), 0)
+
+
+def test_hanging_pendulum_bitwise_static(load_model, BatchSim):
+    # mujoco_sensors_test.cpp:389-391,584: sensor GT variance exactly 0 over 1001 single steps
+    model = load_model("pendulum_scene.xml")
+    sim = BatchSim(model, 4)
+    s0 = None
+    for _ in range(1001):
+        sim.step(1)
+        s = sim.get("sensordata")
+        s0 = s if s0 is None else s0
+        np.testing.assert_array_equal(s, s0)
+    np.testing.assert_array_equal(sim.get("qvel")[:, :5], 0.0)
+    assert np.all(sim.get("ncon")[:, 0] == 1)
+
+
+def test_split_step_equals_step(load_model, BatchSim):
+    # control hook placement (mujoco_env.h:242-246): begin -> host writes ctrl -> end == one step
+    model = load_model("panda_like.xml")
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 4)
+    rng = np.random.default_rng(2)
+    a, b = BatchSim(model, nenv), BatchSim(model, nenv)
+    for s in (a, b):
+        s.set("qpos", qpos)
+        s.set("qvel", qvel)
+    for _ in range(30):
+        ctrl = ctrl_sample(model, rng, nenv)
+        a.set("ctrl", ctrl)
+        a.step(1)
+        b.step_begin()
+        b.set("ctrl", ctrl)  # what a controlCallback would do
+        b.step_end()
+    assert rel(a.get("qpos"), b.get("qpos")) < 1e-12
+    assert rel(a.get("qvel"), b.get("qvel")) < 1e-12
+
+
+def test_multi_step_launch_equals_single_steps(load_model, BatchSim):
+    model = load_model("pendulum_scene.xml")
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 8)
+    a, b = BatchSim(model, nenv), BatchSim(model, nenv)
+    for s in (a, b):
+        s.set("qpos", qpos)
+        s.set("qvel", qvel)
+    a.step(40)
+    for _ in range(40):
+        b.step(1)
+    np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
+    np.testing.assert_array_equal(a.get("qvel"), b.get("qvel"))
+
+
+def test_set_device_matches_host_set(load_model, BatchSim):
+    import torch
+
+    model = load_model("panda_like.xml")
+    nenv = 32
+    sim = BatchSim(model, nenv)
+    ctrl = ctrl_sample(model, np.random.default_rng(1), nenv)
+    t = torch.from_numpy(ctrl).cuda()
+    sim.set_device("ctrl", t.data_ptr(), model.nu)
+    sim.sync()
+    np.testing.assert_array_equal(sim.get("ctrl"), ctrl)
+
+
+def test_bad_state_triggers_reset_and_warning(load_model, BatchSim):
+    # mj_checkPos semantics: NaN qpos -> warning counter + mj_resetData for that env only
+    model = load_model("pendulum_scene.xml")
+    nenv = 4
+    sim = BatchSim(model, nenv)
+    q = np.tile(model.qpos0, (nenv, 1))
+    q[2, 4] = np.nan
+    sim.set("qpos", q)
+    sim.step(1)
+    w = sim.get("warning")
+    assert w[2, 4] == 1 and w[[0, 1, 3]].sum() == 0  # B2MJ_WARN_BADQPOS = 4
+    assert np.all(np.isfinite(sim.get("qpos")))
+
+
+def test_full_batch_properties(load_model, BatchSim):
+    """BASELINE size (4096 envs): replicas of one input stay bitwise identical across the batch and
+    equal the 1-env run (batch independence), quaternions stay unit, no warnings."""
+    model = load_model("panda_like.xml")
+    nenv = 4096
+    qpos, qvel = perturbed(model, 4, 31)
+    rng = np.random.default_rng(6)
+    big, small = BatchSim(model, nenv), BatchSim(model, 4)
+    big.set("qpos", np.tile(qpos, (nenv // 4, 1)))
+    big.set("qvel", np.tile(qvel, (nenv // 4, 1)))
+    small.set("qpos", qpos)
+    small.set("qvel", qvel)
+    for _ in range(50):
+        c = ctrl_sample(model, rng, 4)
+        big.set("ctrl", np.tile(c, (nenv // 4, 1)))
+        small.set("ctrl", c)
+        big.step(1)
+        small.step(1)
+    q = big.get("qpos").reshape(nenv // 4, 4, model.nq)
+    np.testing.assert_array_equal(q, np.broadcast_to(q[0], q.shape))
+    np.testing.assert_array_equal(q[0], small.get("qpos"))
+    assert big.get("warning").sum() == 0

@@ -1,0 +1,94 @@
+"""MJCF compiler facts pinned by the reference's tests and by closed-form values."""
+import numpy as np
+import pytest
+
+
+def test_pendulum_qpos0_pinned(load_model):
+    # reference ros_interface_test.cpp:290-298
+    m = load_model("pendulum_scene.xml")
+    assert (m.nq, m.nv, m.nbody, m.njnt, m.ngeom) == (13, 11, 6, 4, 6)
+    np.testing.assert_array_equal(m.qpos0, [1, 0, 0, 0, 0, 0, 1, 0, 0.06, 1, 0, 0, 0])
+    assert m.opt.timestep == 0.001 and m.opt.cone == 1 and m.opt.solver == 2 and m.opt.integrator == 0
+    np.testing.assert_array_equal(m.opt.gravity[:], [0, 0, -9.81])
+
+
+def test_enum_values_pinned(capi):
+    # mujoco_env_fixture.h:145-156, GeomType.msg:2-9, EqualityConstraintType.msg:2-5
+    import re, os
+    from conftest import ROOT
+    h = open(os.path.join(ROOT, "include", "b2mj.h")).read()
+    for name, val in (("B2MJ_NEQDATA", 11), ("B2MJ_NIMP", 5), ("B2MJ_NREF", 2)):
+        assert re.search(rf"#define {name} {val}\b", h)
+    assert "B2MJ_EQ_CONNECT = 0, B2MJ_EQ_WELD = 1, B2MJ_EQ_JOINT = 2, B2MJ_EQ_TENDON = 3" in h
+    assert "B2MJ_GEOM_PLANE = 0, B2MJ_GEOM_HFIELD = 1, B2MJ_GEOM_SPHERE = 2, B2MJ_GEOM_CAPSULE = 3" in h
+
+
+def test_capsule_inertia_closed_form(capi, load_model):
+    # density 1000 capsules
+    m = load_model("pendulum_scene.xml")
+    b = m.name2id(capi.OBJ_BODY, "base_link")
+    assert m.body_mass[b] == pytest.approx(5.428672, rel=1e-6)
+    assert sorted(m.body_inertia[b]) == pytest.approx([0.00944589, 0.11002712, 0.11002712], rel=1e-6)
+    np.testing.assert_allclose(m.body_ipos[b], [0, 0, 0.8], atol=1e-12)
+    b = m.name2id(capi.OBJ_BODY, "middle_link")
+    assert m.body_mass[b] == pytest.approx(1.776047, rel=1e-6)
+    b = m.name2id(capi.OBJ_BODY, "end_link")
+    assert m.body_mass[b] == pytest.approx(0.284838, rel=2e-6)
+    assert sorted(m.body_inertia[b]) == pytest.approx([0.00005563, 0.00125362, 0.00125362], rel=2e-4)
+    b = m.name2id(capi.OBJ_BODY, "body_ball")
+    assert m.body_mass[b] == pytest.approx(0.1)
+    np.testing.assert_allclose(m.body_inertia[b], 1e-4, rtol=1e-12)
+    b = m.name2id(capi.OBJ_BODY, "immovable")
+    np.testing.assert_allclose(m.body_inertia[b], [4.369e-5, 4.028e-5, 1.407e-5])
+
+
+def test_equality_compile_facts(capi, load_model):
+    # reference ros_interface_test.cpp:769-829
+    m = load_model("equality_scene.xml")
+    assert m.neq == 4
+    w = m.name2id(capi.OBJ_EQUALITY, "weld_eq")
+    assert m.eq_type[w] == 1 and m.eq_obj2id[w] == 0 and m.eq_active[w] == 1
+    np.testing.assert_allclose(m.eq_solref[w], [0.3, 0.9])
+    np.testing.assert_allclose(m.eq_solimp[w], [0.8, 0.95, 0.002, 0.4, 2])
+    d = m.eq_data[w]
+    # anchor (3) | relpose pos (3) | relpose quat normalised (4) | torquescale
+    np.testing.assert_allclose(d[3:6], [1.1, 1.2, 1.3])
+    q = np.array([0.358, -0.003, -0.886, 0.295])
+    np.testing.assert_allclose(d[6:10], q / np.linalg.norm(q), atol=1e-12)
+    assert d[10] == pytest.approx(0.9)
+    j = m.name2id(capi.OBJ_EQUALITY, "joint_eq")
+    assert m.eq_type[j] == 2
+    np.testing.assert_allclose(m.eq_data[j][:5], [0.5, 0.25, 0.76, 0.66, 1])
+    t = m.name2id(capi.OBJ_EQUALITY, "tendon_eq")
+    assert m.eq_type[t] == 3
+    c = m.name2id(capi.OBJ_EQUALITY, "connect_eq")
+    assert m.eq_type[c] == 0 and m.eq_obj2id[c] == 0
+    np.testing.assert_allclose(m.eq_solimp[c], [0.8, 0.95, 0.002, 0.4, 1])
+
+
+def test_name_lookup_roundtrip(capi, load_model):
+    m = load_model("panda_like.xml")
+    for j in range(m.njnt):
+        name = m.id2name(capi.OBJ_JOINT, j)
+        assert name and m.name2id(capi.OBJ_JOINT, name) == j
+    assert m.name2id(capi.OBJ_JOINT, "no_such_joint") == -1
+
+
+def test_panda_like_shape(load_model):
+    m = load_model("panda_like.xml")
+    assert (m.nq, m.nv, m.nu, m.nbody) == (9, 9, 8, 12)
+    assert m.opt.solver == 0 and m.opt.integrator == 0 and m.opt.cone == 0 and m.opt.timestep == 0.002
+    # every candidate pair references valid geoms, ordered, no duplicates
+    pairs = list(zip(m.collpair_geom1.tolist(), m.collpair_geom2.tolist()))
+    assert len(set(pairs)) == len(pairs) == m.ncollpair
+
+
+def test_set_const_is_idempotent(load_model, capi):
+    from conftest import model_path
+    m = capi.Model.from_xml_file(model_path("panda_like.xml"))
+    a = {k: np.array(getattr(m, k)) for k in ("dof_invweight0", "body_invweight0", "body_subtreemass", "actuator_acc0")}
+    mi = m.stat.meaninertia
+    m.set_const()
+    for k, v in a.items():
+        np.testing.assert_allclose(getattr(m, k), v, rtol=1e-13, atol=0)
+    assert m.stat.meaninertia == pytest.approx(mi, rel=1e-13)
