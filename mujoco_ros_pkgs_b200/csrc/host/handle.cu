@@ -79,17 +79,93 @@ static int upload_model(Handle* h) {
 #define X(t, n, r, c) total += al(sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c) + 16);
   B2MJ_MODEL_ARRAYS(X)
 #undef X
-  // dof-chain masks
-  d.nmaskword = std::max(1, (m->nv + 31) / 32);
-  std::vector<unsigned> mask((size_t)m->nbody * d.nmaskword, 0u);
-  for (int b = 1; b < m->nbody; b++) {
+  // ---- derived topology tables (dof-chain masks, subtree masks, scan jump tables, sparse-M indices) ----
+  const int nbody = m->nbody, nv = m->nv, nM = m->nM;
+  d.nmaskword = std::max(1, (nv + 31) / 32);
+  d.nbodyword = std::max(1, (nbody + 31) / 32);
+  std::vector<unsigned> mask((size_t)nbody * d.nmaskword, 0u);
+  for (int b = 1; b < nbody; b++) {
     int bb = b;
     while (bb && !m->body_dofnum[bb]) bb = m->body_parentid[bb];
     if (!bb) continue;
     for (int k = m->body_dofadr[bb] + m->body_dofnum[bb] - 1; k >= 0; k = m->dof_parentid[k])
       mask[(size_t)b * d.nmaskword + (k >> 5)] |= 1u << (k & 31);
   }
-  total += al(mask.size() * sizeof(unsigned) + 16);
+  std::vector<unsigned> submask((size_t)nbody * d.nbodyword, 0u);
+  int maxlevel = 0;
+  for (int i = 0; i < nbody; i++) {
+    maxlevel = std::max(maxlevel, m->body_level[i]);
+    for (int b = i;; b = m->body_parentid[b]) {
+      submask[(size_t)b * d.nbodyword + (i >> 5)] |= 1u << (i & 31);
+      if (b == 0) break;
+    }
+  }
+  d.njump = 0;
+  while ((1 << d.njump) < maxlevel) d.njump++;
+  std::vector<int> jump((size_t)std::max(1, d.njump) * nbody, 0);
+  for (int r = 0; r < d.njump; r++)
+    for (int i = 0; i < nbody; i++) {
+      // ancestor 2^r levels up; world (0) carries the identity transform, so "none" == 0
+      int a = i;
+      for (int s = 0; s < (1 << r) && a > 0; s++) a = m->body_parentid[a];
+      jump[(size_t)r * nbody + i] = (m->body_level[i] > (1 << r)) ? a : 0;
+    }
+  std::vector<int> M_row(std::max(1, nM)), M_col(std::max(1, nM)), M_ancadr(std::max(1, nM)), nanc(std::max(1, nv), 0);
+  for (int i = 0; i < nv; i++) {
+    int adr = m->dof_Madr[i];
+    for (int j = i; j >= 0; j = m->dof_parentid[j], adr++) {
+      M_row[adr] = i;
+      M_col[adr] = j;
+      M_ancadr[adr] = m->dof_Madr[j];
+      if (j != i) nanc[i]++;
+    }
+  }
+  // dofs whose motion is accumulated into cvel BEFORE a dof's cdof_dot is taken (mj_comVel order):
+  // all chain dofs of earlier joints; for a free joint's rotational dofs also its translational ones
+  std::vector<unsigned> premask((size_t)std::max(1, nv) * d.nmaskword, 0u);
+  for (int k = 0; k < nv; k++) {
+    const int jid = m->dof_jntid[k];
+    const int jt = m->jnt_type[jid], jda = m->jnt_dofadr[jid];
+    int first = jda;                                   // first dof of this dof's velocity group
+    if (jt == B2MJ_JNT_FREE && k >= jda + 3) first = jda + 3;
+    for (int j = m->dof_parentid[k]; j >= 0; j = m->dof_parentid[j])
+      if (j < first) premask[(size_t)k * d.nmaskword + (j >> 5)] |= 1u << (j & 31);
+  }
+  int maxdepth = 0;
+  for (int i = 0; i < nv; i++) maxdepth = std::max(maxdepth, nanc[i]);
+  d.ndoflevel = nv ? maxdepth + 1 : 0;
+  std::vector<int> lvl_adr(d.ndoflevel + 1, 0), lvl_dof(std::max(1, nv));
+  for (int i = 0; i < nv; i++) lvl_adr[nanc[i] + 1]++;
+  for (int l = 0; l < d.ndoflevel; l++) lvl_adr[l + 1] += lvl_adr[l];
+  {
+    std::vector<int> fill(lvl_adr.begin(), lvl_adr.end());
+    for (int i = 0; i < nv; i++) lvl_dof[fill[nanc[i]]++] = i;
+  }
+  std::vector<int> desc_adr(nv + 1, 0), desc_dof(std::max(1, nM - nv)), desc_t(std::max(1, nM - nv));
+  for (int t = 0; t < nM; t++) if (M_row[t] != M_col[t]) desc_adr[M_col[t] + 1]++;
+  for (int k = 0; k < nv; k++) desc_adr[k + 1] += desc_adr[k];
+  {
+    std::vector<int> fill(desc_adr.begin(), desc_adr.end());
+    for (int t = 0; t < nM; t++)
+      if (M_row[t] != M_col[t]) { const int k = M_col[t]; desc_dof[fill[k]] = M_row[t]; desc_t[fill[k]] = t; fill[k]++; }
+  }
+  struct Extra { const void* src; size_t bytes; const void** slot; };
+  const Extra extras[] = {
+      {mask.data(), mask.size() * sizeof(unsigned), (const void**)&d.body_dofmask},
+      {submask.data(), submask.size() * sizeof(unsigned), (const void**)&d.body_submask},
+      {jump.data(), jump.size() * sizeof(int), (const void**)&d.body_jump},
+      {M_row.data(), M_row.size() * sizeof(int), (const void**)&d.M_row},
+      {M_col.data(), M_col.size() * sizeof(int), (const void**)&d.M_col},
+      {M_ancadr.data(), M_ancadr.size() * sizeof(int), (const void**)&d.M_ancadr},
+      {nanc.data(), nanc.size() * sizeof(int), (const void**)&d.dof_nanc},
+      {premask.data(), premask.size() * sizeof(unsigned), (const void**)&d.dof_premask},
+      {lvl_adr.data(), lvl_adr.size() * sizeof(int), (const void**)&d.doflevel_adr},
+      {lvl_dof.data(), lvl_dof.size() * sizeof(int), (const void**)&d.doflevel_dof},
+      {desc_adr.data(), desc_adr.size() * sizeof(int), (const void**)&d.dof_descadr},
+      {desc_dof.data(), desc_dof.size() * sizeof(int), (const void**)&d.dof_desc_dof},
+      {desc_t.data(), desc_t.size() * sizeof(int), (const void**)&d.dof_desc_adr},
+  };
+  for (const Extra& x : extras) total += al(x.bytes + 16);
   if (h->model_blob && h->model_blob_bytes < total) {
     cudaFree(h->model_blob);
     h->model_blob = nullptr;
@@ -109,8 +185,11 @@ static int upload_model(Handle* h) {
   }
   B2MJ_MODEL_ARRAYS(X)
 #undef X
-  std::memcpy(host.data() + off, mask.data(), mask.size() * sizeof(unsigned));
-  d.body_dofmask = reinterpret_cast<const unsigned*>((unsigned char*)h->model_blob + off);
+  for (const Extra& x : extras) {
+    if (x.bytes) std::memcpy(host.data() + off, x.src, x.bytes);
+    *x.slot = (unsigned char*)h->model_blob + off;
+    off += al(x.bytes + 16);
+  }
   CUDA_OK(cudaMemcpy(h->model_blob, host.data(), total, cudaMemcpyHostToDevice));
 #define X(n) d.n = m->n;
   B2MJ_MODEL_SIZES(X)
@@ -216,6 +295,13 @@ static int make_layout(Handle* h) {
   xs[XF_RK_XF] = rk4 ? 4 * nv : 0;
   xs[XF_RK_F] = rk4 ? 4 * (nv + na) : 0;
   xs[XF_RK_DX] = rk4 ? 2 * nv + na : 0;
+  xs[XF_TLOC] = 14 * m->nbody;
+  xs[XF_QW] = m->nM;
+  xs[XF_QHW] = m->nM;
+  xs[XF_DOFBUF] = 6 * nv;
+  xs[XF_BODYBUF] = 6 * m->nbody;
+  xs[XF_EFC_AR] = pgs ? m->njmax * m->njmax : 0;
+  xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * m->njmax, 400) : 0;
   // xfrc_applied / mocap live in their own HBM arrays (read only when the surface is enabled)
   d.fsize[B2MJ_F_XFRC_APPLIED] = 0;
 
@@ -232,6 +318,7 @@ static int make_layout(Handle* h) {
   // shared placement: record image first, then hot fields; big constraint arrays are demoted to the
   // global arena (L2) when the per-env footprint would starve occupancy
   std::vector<char> cold(B2MJ_NFIELD, 0), xcold(XF_COUNT, 0);
+  xcold[XF_EFC_AR] = 1;
   auto smem_bytes_env = [&]() {
     size_t dbl = d.rec_end, ints = 0;
     for (int f = 0; f < B2MJ_NFIELD; f++) {

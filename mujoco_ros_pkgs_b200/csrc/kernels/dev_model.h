@@ -38,6 +38,13 @@ enum XField {
   XF_RK_XF,         // 4*nv       RK4 stage velocities
   XF_RK_F,          // 4*(nv+na)  RK4 stage accelerations / act_dot
   XF_RK_DX,         // 2*nv+na
+  XF_TLOC,          // 14*nbody  ping-pong buffers of the kinematic scan (pos 3 + quat 4 per body)
+  XF_QW,            // nM   off-diagonal entries of inv(L) for qLD (sparse layout of qM)
+  XF_QHW,           // nM   same for qH
+  XF_DOFBUF,        // 6*nv  crb * cdof per dof
+  XF_BODYBUF,       // 6*nbody  per-body RNE force before the subtree sum
+  XF_EFC_AR,        // njmax*njmax  dense AR = J inv(M) J' + R (PGS); always in the HBM/L2 arena
+  XF_EFC_AR_S,      // shared-memory home of AR when nefc*nefc fits (the common case)
   XF_COUNT
 };
 
@@ -52,6 +59,22 @@ struct DevModel {
   B2MJ_MODEL_ARRAYS(B2K_X_ARR)
 #undef B2K_X_ARR
   const unsigned* body_dofmask;  // [nbody][nmaskword]: bit k set if dof k is on the chain from the body to its root
+  // ---- derived topology tables (host-built, handle.cu::upload_model) for the wide-parallel stages ----
+  int nbodyword;                 // words per body of body_submask
+  int njump;                     // pointer-jumping rounds of the kinematic scan = ceil(log2(max body level))
+  int ndoflevel;                 // number of dof depth levels (max #ancestors + 1)
+  const unsigned* body_submask;  // [nbody][nbodyword]: bit i set if body i is in the subtree of the body (incl. itself)
+  const int* body_jump;          // [njump][nbody]: ancestor 2^r levels up, 0 (world) if there is none
+  const int* M_row;              // [nM] dof i of sparse inertia entry t  (entry t = M(i, j), j = i or an ancestor of i)
+  const int* M_col;              // [nM] dof j
+  const int* M_ancadr;           // [nM] dof_Madr[j]: start of the ancestor's own row
+  const int* dof_nanc;           // [nv] number of ancestors of the dof (row length - 1)
+  const unsigned* dof_premask;   // [nv][nmaskword]: dofs whose velocity is accumulated before this dof's joint (cdof_dot)
+  const int* doflevel_adr;       // [ndoflevel+1] offsets into doflevel_dof
+  const int* doflevel_dof;       // [nv] dofs sorted by depth
+  const int* dof_descadr;        // [nv+1] CSR of strict descendants of a dof
+  const int* dof_desc_dof;       // [nM-nv] descendant dof m
+  const int* dof_desc_adr;       // [nM-nv] sparse address of entry (m, k)
 
   // ---- arena layout (element offsets; doubles for f64 fields, ints for i32 fields) ----
   int off_g[B2MJ_NFIELD];   // offset in the full per-env arena (always valid)

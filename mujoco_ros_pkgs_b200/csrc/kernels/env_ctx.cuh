@@ -5,25 +5,43 @@
 
 namespace b2k {
 
+// The device view of the model of the handle that is currently stepping lives in constant memory:
+// sizes, options, layout offsets and array pointers become constant-bank operands of the instructions
+// that use them.  b2k_launch_step re-uploads it when a different handle (or an edited model) launches.
+__constant__ DevModel c_dm;
+
+// dynamic shared memory of the step kernel: [nwarp mbarriers, 16 B each][nwarp env blocks: doubles | ints].
+// Declared at namespace scope so every accessor forms its address from the shared symbol itself and
+// the compiler emits LDS / STS (not generic LD / ST) for arena traffic.
+extern __shared__ __align__(16) unsigned char b2k_smem[];
+
 struct Env {
-  const DevModel& m;
-  double* sd;  // shared arena (doubles); starts with the image of the HBM state record
-  int* si;     // shared arena (ints)
-  double* gd;  // this env's global arena (doubles)
-  int* gi;     // this env's global arena (ints)
+  unsigned sbd;  // byte offset in b2k_smem of this env's shared arena (doubles; starts with the record image)
+  unsigned sbi;  // byte offset of the int part
+  double* gd;    // this env's HBM/L2 arena (doubles)
+  int* gi;       // this env's HBM/L2 arena (ints)
   int lane;
 
+  __device__ __forceinline__ double* sd() const { return reinterpret_cast<double*>(b2k_smem + sbd); }
+  __device__ __forceinline__ int* si() const { return reinterpret_cast<int*>(b2k_smem + sbi); }
+  // fields that are always shared-memory resident (everything the host never demotes)
   __device__ __forceinline__ double* D(int f) const {
-    const int o = m.off_s[f];
-    return o >= 0 ? sd + o : gd + m.off_g[f];
+    return reinterpret_cast<double*>(b2k_smem + sbd + 8u * (unsigned)c_dm.off_s[f]);
   }
   __device__ __forceinline__ int* I(int f) const {
-    const int o = m.off_s[f];
-    return o >= 0 ? si + o : gi + m.off_g[f];
+    return reinterpret_cast<int*>(b2k_smem + sbi + 4u * (unsigned)c_dm.off_s[f]);
   }
   __device__ __forceinline__ double* X(int xf) const {
-    const int o = m.xoff_s[xf];
-    return o >= 0 ? sd + o : gd + m.xoff_g[xf];
+    return reinterpret_cast<double*>(b2k_smem + sbd + 8u * (unsigned)c_dm.xoff_s[xf]);
+  }
+  // fields the host may demote to the env's HBM/L2 arena when they are large (handle.cu::make_layout)
+  __device__ __forceinline__ double* DG(int f) const {
+    const int o = c_dm.off_s[f];
+    return o >= 0 ? sd() + o : gd + c_dm.off_g[f];
+  }
+  __device__ __forceinline__ double* XG(int xf) const {
+    const int o = c_dm.xoff_s[xf];
+    return o >= 0 ? sd() + o : gd + c_dm.xoff_g[xf];
   }
 };
 

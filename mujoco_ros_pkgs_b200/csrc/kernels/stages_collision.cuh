@@ -137,8 +137,9 @@ __device__ __forceinline__ double segmentBoxClosest(const double* c, const doubl
   return best_t;
 }
 
-__device__ int narrowphase(const DevModel& m, const double* gxpos, const double* gxmat, PairCon& o, int g1, int g2,
+__device__ int narrowphase(const double* gxpos, const double* gxmat, PairCon& o, int g1, int g2,
                            double margin) {
+  const DevModel& m = c_dm;
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   const double *pos1 = gxpos + 3 * g1, *mat1 = gxmat + 9 * g1, *size1 = m.geom_size + 3 * g1;
   const double *pos2 = gxpos + 3 * g2, *mat2 = gxmat + 9 * g2, *size2 = m.geom_size + 3 * g2;
@@ -250,8 +251,8 @@ __device__ int narrowphase(const DevModel& m, const double* gxpos, const double*
 }
 
 // mj_collision; returns ncon (also stored)
-__device__ int stage_collision(const Env& e, int* warning) {
-  const DevModel& m = e.m;
+__device__ int stage_collision(const Env e, int* warning) {
+  const DevModel& m = c_dm;
   int* ncon_p = e.I(B2MJ_F_NCON);
   if ((m.opt.disableflags & (B2MJ_DSBL_CONSTRAINT | B2MJ_DSBL_CONTACT)) || m.nconmax == 0 || m.ncollpair == 0) {
     if (e.lane == 0) ncon_p[0] = 0;
@@ -261,12 +262,12 @@ __device__ int stage_collision(const Env& e, int* warning) {
   const double* gxpos = e.D(B2MJ_F_GEOM_XPOS);
   const double* gxmat = e.D(B2MJ_F_GEOM_XMAT);
   double* c_dist = e.D(B2MJ_F_CONTACT_DIST);
-  double* c_pos = e.D(B2MJ_F_CONTACT_POS);
-  double* c_frame = e.D(B2MJ_F_CONTACT_FRAME);
+  double* c_pos = e.DG(B2MJ_F_CONTACT_POS);
+  double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);
   double* c_inc = e.D(B2MJ_F_CONTACT_INCLUDEMARGIN);
-  double* c_fri = e.D(B2MJ_F_CONTACT_FRICTION);
+  double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
   double* c_solref = e.D(B2MJ_F_CONTACT_SOLREF);
-  double* c_solimp = e.D(B2MJ_F_CONTACT_SOLIMP);
+  double* c_solimp = e.DG(B2MJ_F_CONTACT_SOLIMP);
   double* c_mu = e.D(B2MJ_F_CONTACT_MU);
   int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
   int* c_g1 = e.I(B2MJ_F_CONTACT_GEOM1);
@@ -297,7 +298,7 @@ __device__ int stage_collision(const Env& e, int* warning) {
         sub3(dif, gxpos + 3 * g2, gxpos + 3 * g1);
         cull = dot3(dif, normal) > margin + r2;
       }
-      if (!cull) num = narrowphase(m, gxpos, gxmat, pc, g1, g2, margin);
+      if (!cull) num = narrowphase(gxpos, gxmat, pc, g1, g2, margin);
     }
     const int incl = warpInclusiveScan(num, e.lane);
     const int total = __shfl_sync(0xffffffffu, incl, 31);

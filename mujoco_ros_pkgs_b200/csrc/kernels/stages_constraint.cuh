@@ -12,8 +12,9 @@
 namespace b2k {
 
 // column k of the translational / rotational Jacobian of a world point on `body` (zero if off-chain)
-__device__ __forceinline__ bool jacColumn(const DevModel& m, const double* cdof, const double* com, int body, int k,
+__device__ __forceinline__ bool jacColumn(const double* cdof, const double* com, int body, int k,
                                           const double* point, double* jp, double* jr) {
+  const DevModel& m = c_dm;
   const unsigned* mask = m.body_dofmask + body * m.nmaskword;
   if (!((mask[k >> 5] >> (k & 31)) & 1u)) {
     zero3(jp);
@@ -34,10 +35,10 @@ struct EfcPtrs {
   int *type, *id, *state;
 };
 
-__device__ __forceinline__ EfcPtrs efcPtrs(const Env& e) {
+__device__ __forceinline__ EfcPtrs efcPtrs(const Env e) {
   EfcPtrs p;
-  p.J = e.D(B2MJ_F_EFC_J); p.pos = e.D(B2MJ_F_EFC_POS); p.margin = e.D(B2MJ_F_EFC_MARGIN);
-  p.floss = e.D(B2MJ_F_EFC_FRICTIONLOSS); p.diag = e.D(B2MJ_F_EFC_DIAGAPPROX); p.KBIP = e.D(B2MJ_F_EFC_KBIP);
+  p.J = e.DG(B2MJ_F_EFC_J); p.pos = e.D(B2MJ_F_EFC_POS); p.margin = e.D(B2MJ_F_EFC_MARGIN);
+  p.floss = e.D(B2MJ_F_EFC_FRICTIONLOSS); p.diag = e.D(B2MJ_F_EFC_DIAGAPPROX); p.KBIP = e.DG(B2MJ_F_EFC_KBIP);
   p.D = e.D(B2MJ_F_EFC_D); p.R = e.D(B2MJ_F_EFC_R); p.vel = e.D(B2MJ_F_EFC_VEL); p.aref = e.D(B2MJ_F_EFC_AREF);
   p.b = e.D(B2MJ_F_EFC_B); p.force = e.D(B2MJ_F_EFC_FORCE);
   p.type = e.I(B2MJ_F_EFC_TYPE); p.id = e.I(B2MJ_F_EFC_ID); p.state = e.I(B2MJ_F_EFC_STATE);
@@ -60,8 +61,8 @@ __device__ __forceinline__ double getImpedance(const double* solimp, double pos,
 }
 
 // mj_makeConstraint; returns nefc (also stored)
-__device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
-  const DevModel& m = e.m;
+__device__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   int* nefc_p = e.I(B2MJ_F_NEFC);
   int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
@@ -107,8 +108,8 @@ __device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
         }
         FORL(k, nv) {
           double jp0[3], jp1[3], jr0[3], jr1[3];
-          jacColumn(m, cdof, com, id0, k, pos0, jp0, jr0);
-          jacColumn(m, cdof, com, id1, k, pos1, jp1, jr1);
+          jacColumn(cdof, com, id0, k, pos0, jp0, jr0);
+          jacColumn(cdof, com, id1, k, pos1, jp1, jr1);
           for (int r = 0; r < 3; r++) P.J[(row + r) * nv + k] = jp0[r] - jp1[r];
           if (et == B2MJ_EQ_WELD) {
             double axis[3], q2[4], q3[4];
@@ -265,9 +266,9 @@ __device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
     const int* c_g2 = e.I(B2MJ_F_CONTACT_GEOM2);
     const double* c_dist = e.D(B2MJ_F_CONTACT_DIST);
     const double* c_inc = e.D(B2MJ_F_CONTACT_INCLUDEMARGIN);
-    const double* c_pos = e.D(B2MJ_F_CONTACT_POS);
-    const double* c_frame = e.D(B2MJ_F_CONTACT_FRAME);
-    const double* c_fri = e.D(B2MJ_F_CONTACT_FRICTION);
+    const double* c_pos = e.DG(B2MJ_F_CONTACT_POS);
+    const double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);
+    const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
     bool contacts_full = false;  // uniform: once a contact does not fit, all later ones are dropped
     for (int base = 0; base < ncon && !contacts_full; base += 32) {
       const int c = base + e.lane;
@@ -317,8 +318,8 @@ __device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
       const int dim = c_dim[c];
       const int b1 = m.geom_bodyid[c_g1[c]], b2 = m.geom_bodyid[c_g2[c]];
       double jp1[3], jp2[3], jr1[3], jr2[3], dp[3], dr[3], v[6];
-      jacColumn(m, cdof, com, b1, k, c_pos + 3 * c, jp1, jr1);
-      jacColumn(m, cdof, com, b2, k, c_pos + 3 * c, jp2, jr2);
+      jacColumn(cdof, com, b1, k, c_pos + 3 * c, jp1, jr1);
+      jacColumn(cdof, com, b2, k, c_pos + 3 * c, jp2, jr2);
       sub3(dp, jp2, jp1);
       sub3(dr, jr2, jr1);
       const double* fr = c_frame + 9 * c;
@@ -346,7 +347,7 @@ __device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
   // ---------------- impedance: KBIP, R, D (mj_makeImpedance) ----------------
   const bool refsafe = !(m.opt.disableflags & B2MJ_DSBL_REFSAFE);
   const double* c_solref = e.D(B2MJ_F_CONTACT_SOLREF);
-  const double* c_solimp = e.D(B2MJ_F_CONTACT_SOLIMP);
+  const double* c_solimp = e.DG(B2MJ_F_CONTACT_SOLIMP);
   FORL(i, nefc) {
     const int id = P.id[i], type = P.type[i];
     const double *solref, *solimp;
@@ -381,7 +382,7 @@ __device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
   WSYNC();
   if (ncon > 0) {
     const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
-    const double* c_fri = e.D(B2MJ_F_CONTACT_FRICTION);
+    const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
     double* c_mu = e.D(B2MJ_F_CONTACT_MU);
     FORL(c, ncon) {
       const int adr = c_adr[c], dim = c_dim[c];
@@ -406,9 +407,9 @@ __device__ int stage_makeConstraint(const Env& e, int ncon, int* warning) {
 }
 
 // mj_referenceConstraint: efc_vel = J qvel, aref = -B vel - K imp (pos - margin)
-__device__ void stage_referenceConstraint(const Env& e, int nefc) {
+__device__ void stage_referenceConstraint(const Env e, int nefc) {
   if (!nefc) return;
-  const DevModel& m = e.m;
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   EfcPtrs P = efcPtrs(e);
   const double* qvel = e.D(B2MJ_F_QVEL);
@@ -422,9 +423,9 @@ __device__ void stage_referenceConstraint(const Env& e, int nefc) {
 }
 
 // res[k] = sum_i J[i][k] * f[i]   (J' f), one lane per dof
-__device__ void mulJacTVec_warp(const Env& e, int nefc, double* res, const double* f) {
-  const int nv = e.m.nv;
-  const double* J = e.D(B2MJ_F_EFC_J);
+__device__ void mulJacTVec_warp(const Env e, int nefc, double* res, const double* f) {
+  const int nv = c_dm.nv;
+  const double* J = e.DG(B2MJ_F_EFC_J);
   FORL(k, nv) {
     double s = 0;
     for (int i = 0; i < nefc; i++) {
@@ -438,8 +439,8 @@ __device__ void mulJacTVec_warp(const Env& e, int nefc, double* res, const doubl
 
 // mj_constraintUpdate: force / state / cost for jar = J qacc - aref; returns the constraint cost
 // (identical on all lanes).  Does NOT compute qfrc_constraint (callers do, when they need it).
-__device__ double constraintUpdate_warp(const Env& e, int nefc, int ncon, const double* jar, bool coneHessian) {
-  const DevModel& m = e.m;
+__device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const double* jar, bool coneHessian) {
+  const DevModel& m = c_dm;
   EfcPtrs P = efcPtrs(e);
   double s = 0;
   FORL(i, nefc) {
@@ -466,8 +467,8 @@ __device__ double constraintUpdate_warp(const Env& e, int nefc, int ncon, const 
     const int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
     const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
     const double* c_mu = e.D(B2MJ_F_CONTACT_MU);
-    const double* c_fri = e.D(B2MJ_F_CONTACT_FRICTION);
-    double* cH = e.X(XF_CONTACT_H);
+    const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
+    double* cH = e.XG(XF_CONTACT_H);
     FORL(c, ncon) {
       const int i = c_adr[c], dim = c_dim[c];
       if (i < 0 || dim == 1) continue;

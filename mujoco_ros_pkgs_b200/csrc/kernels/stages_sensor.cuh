@@ -9,7 +9,8 @@
 
 namespace b2k {
 
-__device__ __forceinline__ void sens_cutoff(const DevModel& m, int i, double* out) {
+__device__ __forceinline__ void sens_cutoff(int i, double* out) {
+  const DevModel& m = c_dm;
   const double cutoff = m.sensor_cutoff[i];
   if (cutoff <= 0) return;
   const int dt = m.sensor_datatype[i];
@@ -19,9 +20,9 @@ __device__ __forceinline__ void sens_cutoff(const DevModel& m, int i, double* ou
   }
 }
 
-__device__ __forceinline__ void sens_frame(const Env& e, int type, int id, const double** pos, const double** mat,
+__device__ __forceinline__ void sens_frame(const Env e, int type, int id, const double** pos, const double** mat,
                                            double* quat) {
-  const DevModel& m = e.m;
+  const DevModel& m = c_dm;
   const double* xquat = e.D(B2MJ_F_XQUAT);
   switch (type) {
     case B2MJ_OBJ_BODY:
@@ -42,25 +43,26 @@ __device__ __forceinline__ void sens_frame(const Env& e, int type, int id, const
   }
 }
 
-__device__ __forceinline__ int sens_body(const DevModel& m, int type, int id) {
+__device__ __forceinline__ int sens_body(int type, int id) {
+  const DevModel& m = c_dm;
   return type == B2MJ_OBJ_GEOM ? m.geom_bodyid[id] : type == B2MJ_OBJ_SITE ? m.site_bodyid[id] : id;
 }
 
 // mj_objectVelocity / mj_objectAcceleration
-__device__ __forceinline__ void objVelocity(const Env& e, int type, int id, double* res, int local) {
-  const DevModel& m = e.m;
+__device__ __forceinline__ void objVelocity(const Env e, int type, int id, double* res, int local) {
+  const DevModel& m = c_dm;
   const double *pos, *mat;
   double q[4];
   sens_frame(e, type, id, &pos, &mat, q);
-  const int b = sens_body(m, type, id);
+  const int b = sens_body(type, id);
   transformSpatial(res, e.D(B2MJ_F_CVEL) + 6 * b, 0, pos, e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b], local ? mat : nullptr);
 }
-__device__ __forceinline__ void objAcceleration(const Env& e, int type, int id, double* res, int local) {
-  const DevModel& m = e.m;
+__device__ __forceinline__ void objAcceleration(const Env e, int type, int id, double* res, int local) {
+  const DevModel& m = c_dm;
   const double *pos, *mat;
   double q[4], vel[6], corr[3];
   sens_frame(e, type, id, &pos, &mat, q);
-  const int b = sens_body(m, type, id);
+  const int b = sens_body(type, id);
   const double* com = e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b];
   transformSpatial(res, e.D(B2MJ_F_CACC) + 6 * b, 0, pos, com, local ? mat : nullptr);
   transformSpatial(vel, e.D(B2MJ_F_CVEL) + 6 * b, 0, pos, com, local ? mat : nullptr);
@@ -68,7 +70,7 @@ __device__ __forceinline__ void objAcceleration(const Env& e, int type, int id, 
   addTo3(res + 3, corr);
 }
 
-__device__ __forceinline__ int findLimitRow(const Env& e, int nefc, int want, int id) {
+__device__ __forceinline__ int findLimitRow(const Env e, int nefc, int want, int id) {
   const int* type = e.I(B2MJ_F_EFC_TYPE);
   const int* eid = e.I(B2MJ_F_EFC_ID);
   for (int r = 0; r < nefc; r++)
@@ -76,8 +78,8 @@ __device__ __forceinline__ int findLimitRow(const Env& e, int nefc, int want, in
   return -1;
 }
 
-__device__ void stage_sensorPos(const Env& e, int nefc) {
-  const DevModel& m = e.m;
+__device__ void stage_sensorPos(const Env e, int nefc) {
+  const DevModel& m = c_dm;
   if (!m.nsensor || (m.opt.disableflags & B2MJ_DSBL_SENSOR)) return;
   double* sd = e.D(B2MJ_F_SENSORDATA);
   const double* qpos = e.D(B2MJ_F_QPOS);
@@ -126,14 +128,14 @@ __device__ void stage_sensorPos(const Env& e, int nefc) {
       case B2MJ_SENS_CLOCK: out[0] = e.D(B2MJ_F_TIME)[0]; break;
       default: break;
     }
-    sens_cutoff(m, i, out);
+    sens_cutoff(i, out);
   }
   WSYNC();
 }
 
 // mj_subtreeVel (serial over bodies on lane 0; only runs when a subtree sensor exists)
-__device__ void subtreeVel_lane0(const Env& e) {
-  const DevModel& m = e.m;
+__device__ void subtreeVel_lane0(const Env e) {
+  const DevModel& m = c_dm;
   if (e.lane == 0) {
     double* linvel = e.X(XF_SUBTREE_LINVEL);
     double* angmom = e.X(XF_SUBTREE_ANGMOM);
@@ -173,8 +175,8 @@ __device__ void subtreeVel_lane0(const Env& e) {
   WSYNC();
 }
 
-__device__ void stage_sensorVel(const Env& e, int nefc) {
-  const DevModel& m = e.m;
+__device__ void stage_sensorVel(const Env e, int nefc) {
+  const DevModel& m = c_dm;
   if (!m.nsensor || (m.opt.disableflags & B2MJ_DSBL_SENSOR)) return;
   if (m.need_subtreevel) subtreeVel_lane0(e);
   double* sd = e.D(B2MJ_F_SENSORDATA);
@@ -226,20 +228,20 @@ __device__ void stage_sensorVel(const Env& e, int nefc) {
       case B2MJ_SENS_SUBTREEANGMOM: copy3(out, e.X(XF_SUBTREE_ANGMOM) + 3 * objid); break;
       default: break;
     }
-    sens_cutoff(m, i, out);
+    sens_cutoff(i, out);
   }
   WSYNC();
 }
 
 // local contact force [normal, tangents..., torques...] of contact c
-__device__ __forceinline__ void contactForce(const Env& e, int c, double* lfrc) {
+__device__ __forceinline__ void contactForce(const Env e, int c, double* lfrc) {
   const int adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS)[c];
   const int dim = e.I(B2MJ_F_CONTACT_DIM)[c];
   const double* f = e.D(B2MJ_F_EFC_FORCE);
   for (int k = 0; k < 6; k++) lfrc[k] = 0;
   if (adr < 0) return;
   if (e.I(B2MJ_F_EFC_TYPE)[adr] == B2MJ_CNSTR_CONTACT_PYRAMIDAL) {
-    const double* mu = e.D(B2MJ_F_CONTACT_FRICTION) + 5 * c;
+    const double* mu = e.DG(B2MJ_F_CONTACT_FRICTION) + 5 * c;
     for (int k = 0; k < 2 * (dim - 1); k++) lfrc[0] += f[adr + k];
     for (int k = 1; k < dim; k++) lfrc[k] = (f[adr + 2 * (k - 1)] - f[adr + 2 * (k - 1) + 1]) * mu[k - 1];
   } else {
@@ -248,8 +250,8 @@ __device__ __forceinline__ void contactForce(const Env& e, int c, double* lfrc) 
 }
 
 // mj_rnePostConstraint: cacc, cfrc_int, cfrc_ext
-__device__ void stage_rnePost(const Env& e, int ncon, const double* xfrc) {
-  const DevModel& m = e.m;
+__device__ void stage_rnePost(const Env e, int ncon, const double* xfrc) {
+  const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
   const double* cvel = e.D(B2MJ_F_CVEL);
@@ -281,10 +283,10 @@ __device__ void stage_rnePost(const Env& e, int ncon, const double* xfrc) {
         if (b1 != b && b2 != b) continue;
         double lfrc[6], cf[6], f[6];
         contactForce(e, c, lfrc);
-        const double* fr = e.D(B2MJ_F_CONTACT_FRAME) + 9 * c;
+        const double* fr = e.DG(B2MJ_F_CONTACT_FRAME) + 9 * c;
         rotVecMatT(cf + 3, lfrc, fr);
         rotVecMatT(cf, lfrc + 3, fr);
-        transformSpatial(f, cf, 1, com + 3 * m.body_rootid[b], e.D(B2MJ_F_CONTACT_POS) + 3 * c, nullptr);
+        transformSpatial(f, cf, 1, com + 3 * m.body_rootid[b], e.DG(B2MJ_F_CONTACT_POS) + 3 * c, nullptr);
         if (b1 == b) for (int k = 0; k < 6; k++) acc[k] -= f[k];
         if (b2 == b) for (int k = 0; k < 6; k++) acc[k] += f[k];
       }
@@ -326,8 +328,8 @@ __device__ void stage_rnePost(const Env& e, int ncon, const double* xfrc) {
   WSYNC();
 }
 
-__device__ __forceinline__ bool pointInSite(const Env& e, int site, const double* p) {
-  const DevModel& m = e.m;
+__device__ __forceinline__ bool pointInSite(const Env e, int site, const double* p) {
+  const DevModel& m = c_dm;
   double dif[3], loc[3];
   sub3(dif, p, e.D(B2MJ_F_SITE_XPOS) + 3 * site);
   rotVecMatT(loc, dif, e.D(B2MJ_F_SITE_XMAT) + 9 * site);
@@ -346,8 +348,8 @@ __device__ __forceinline__ bool pointInSite(const Env& e, int site, const double
   }
 }
 
-__device__ void stage_sensorAcc(const Env& e, int nefc, int ncon, const double* xfrc) {
-  const DevModel& m = e.m;
+__device__ void stage_sensorAcc(const Env e, int nefc, int ncon, const double* xfrc) {
+  const DevModel& m = c_dm;
   if (!m.nsensor || (m.opt.disableflags & B2MJ_DSBL_SENSOR)) return;
   if (m.need_rnepost) stage_rnePost(e, ncon, xfrc);
   double* sd = e.D(B2MJ_F_SENSORDATA);
@@ -369,7 +371,7 @@ __device__ void stage_sensorAcc(const Env& e, int nefc, int ncon, const double* 
           double lfrc[6];
           contactForce(e, c, lfrc);
           if (lfrc[0] <= 0) continue;
-          if (pointInSite(e, objid, e.D(B2MJ_F_CONTACT_POS) + 3 * c)) s += lfrc[0];
+          if (pointInSite(e, objid, e.DG(B2MJ_F_CONTACT_POS) + 3 * c)) s += lfrc[0];
         }
         out[0] = s;
         break;
@@ -402,7 +404,7 @@ __device__ void stage_sensorAcc(const Env& e, int nefc, int ncon, const double* 
         break;
       default: break;
     }
-    sens_cutoff(m, i, out);
+    sens_cutoff(i, out);
   }
   WSYNC();
 }

@@ -12,9 +12,33 @@
 
 namespace b2k {
 
-// mj_kinematics
-__device__ void stage_kinematics(const Env& e) {
-  const DevModel& m = e.m;
+// v' = q v q* for a unit quaternion, without forming the matrix; exact for identity q / zero v
+B2K_DI void rotQ(double* r, const double* v, const double* q) {
+  const double tx = 2 * (q[2] * v[2] - q[3] * v[1]);
+  const double ty = 2 * (q[3] * v[0] - q[1] * v[2]);
+  const double tz = 2 * (q[1] * v[1] - q[2] * v[0]);
+  const double x = v[0] + q[0] * tx + (q[2] * tz - q[3] * ty);
+  const double y = v[1] + q[0] * ty + (q[3] * tx - q[1] * tz);
+  const double z = v[2] + q[0] * tz + (q[1] * ty - q[2] * tx);
+  r[0] = x; r[1] = y; r[2] = z;
+}
+
+// iterate the set bits of a multi-word mask: BODY is executed with `IDX` = bit index
+#define FOR_MASK_BITS(IDX, MASKPTR, NWORD, BODY)                \
+  for (int _w = 0; _w < (NWORD); _w++) {                        \
+    unsigned _bits = (MASKPTR)[_w];                             \
+    while (_bits) {                                             \
+      const int IDX = (_w << 5) + __ffs(_bits) - 1;             \
+      _bits &= _bits - 1;                                       \
+      BODY                                                      \
+    }                                                           \
+  }
+
+// mj_kinematics.  The tree recursion is replaced by (A) body-local transforms for all bodies at once,
+// (B) a pointer-jumping scan that composes them along the ancestor chains in ceil(log2(depth)) rounds,
+// (C) one parallel pass for matrices, inertial / joint / geom / site frames.
+__device__ void stage_kinematics(const Env e) {
+  const DevModel& m = c_dm;
   double* qpos = e.D(B2MJ_F_QPOS);
   double* xpos = e.D(B2MJ_F_XPOS);
   double* xquat = e.D(B2MJ_F_XQUAT);
@@ -23,85 +47,113 @@ __device__ void stage_kinematics(const Env& e) {
   double* ximat = e.D(B2MJ_F_XIMAT);
   double* xanchor = e.D(B2MJ_F_XANCHOR);
   double* xaxis = e.D(B2MJ_F_XAXIS);
-  double* qloc = e.X(XF_QLOC);
+  double* T0 = e.X(XF_TLOC);
+  double* T1 = T0 + 7 * m.nbody;
   double* mocap_pos = m.nmocap ? e.D(B2MJ_F_MOCAP_POS) : nullptr;
   double* mocap_quat = m.nmocap ? e.D(B2MJ_F_MOCAP_QUAT) : nullptr;
 
-  // joint-local quaternions, all joints in parallel (takes sincos off the serial chain);
-  // free / ball quaternions are normalised in place in qpos
-  FORL(j, m.njnt) {
-    const int t = m.jnt_type[j], qa = m.jnt_qposadr[j];
-    if (t == B2MJ_JNT_FREE) normalize4(qpos + qa + 3);
-    else if (t == B2MJ_JNT_BALL) { normalize4(qpos + qa); copy4(qloc + 4 * j, qpos + qa); }
-    else if (t == B2MJ_JNT_HINGE) axisAngle2Quat(qloc + 4 * j, m.jnt_axis + 3 * j, qpos[qa] - m.qpos0[qa]);
-  }
-  FORL(i, m.nmocap) normalize4(mocap_quat + 4 * i);
-  if (e.lane == 0) {
-    zero3(xpos); zero3(xipos);
-    xquat[0] = 1; xquat[1] = 0; xquat[2] = 0; xquat[3] = 0;
-    for (int k = 0; k < 9; k++) { xmat[k] = (k % 4 == 0) ? 1.0 : 0.0; ximat[k] = (k % 4 == 0) ? 1.0 : 0.0; }
-  }
-  WSYNC();
-  for (int l = 1; l < m.nlevel; l++) {
-    const int ladr = m.level_bodyadr[l], lnum = m.level_bodynum[l];
-    FORL(k, lnum) {
-      const int i = m.level_body[ladr + k];
-      double p[3], q[4];
+  // (A) transform of every body relative to its parent; joint anchors / axes in the parent frame
+  FORL(i, m.nbody) {
+    double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0};
+    if (i) {
       const int jntadr = m.body_jntadr[i], jntnum = m.body_jntnum[i];
       if (jntnum == 1 && m.jnt_type[jntadr] == B2MJ_JNT_FREE) {
         const int qa = m.jnt_qposadr[jntadr];
+        normalize4(qpos + qa + 3);
         copy3(p, qpos + qa);
         copy4(q, qpos + qa + 3);
         copy3(xanchor + 3 * jntadr, p);
         copy3(xaxis + 3 * jntadr, m.jnt_axis + 3 * jntadr);
       } else {
-        const int pid = m.body_parentid[i];
-        const double *bpos, *bquat;
         const int mid = m.body_mocapid[i];
-        if (mid >= 0) { bpos = mocap_pos + 3 * mid; bquat = mocap_quat + 4 * mid; }
-        else { bpos = m.body_pos + 3 * i; bquat = m.body_quat + 4 * i; }
-        if (pid) {
-          double v[3];
-          rotVecMat(v, bpos, xmat + 9 * pid);
-          add3(p, v, xpos + 3 * pid);
-          mulQuat(q, xquat + 4 * pid, bquat);
+        if (mid >= 0) {
+          normalize4(mocap_quat + 4 * mid);
+          copy3(p, mocap_pos + 3 * mid);
+          copy4(q, mocap_quat + 4 * mid);
         } else {
-          copy3(p, bpos);
-          copy4(q, bquat);
+          copy3(p, m.body_pos + 3 * i);
+          copy4(q, m.body_quat + 4 * i);
         }
         for (int j = 0; j < jntnum; j++) {
-          const int jid = jntadr + j, jt = m.jnt_type[jid];
-          double anchor[3], axis[3], v[3];
-          rotVecQuat(axis, m.jnt_axis + 3 * jid, q);
-          rotVecQuat(anchor, m.jnt_pos + 3 * jid, q);
+          const int jid = jntadr + j, jt = m.jnt_type[jid], qa = m.jnt_qposadr[jid];
+          double anchor[3], axis[3];
+          rotQ(axis, m.jnt_axis + 3 * jid, q);
+          rotQ(anchor, m.jnt_pos + 3 * jid, q);
           addTo3(anchor, p);
           if (jt == B2MJ_JNT_SLIDE) {
-            const int qa = m.jnt_qposadr[jid];
             addToScl3(p, axis, qpos[qa] - m.qpos0[qa]);
-          } else if (jt == B2MJ_JNT_BALL || jt == B2MJ_JNT_HINGE) {
-            mulQuat(q, q, qloc + 4 * jid);
-            rotVecQuat(v, m.jnt_pos + 3 * jid, q);
+          } else {
+            double ql[4], qn[4], v[3];
+            if (jt == B2MJ_JNT_BALL) { normalize4(qpos + qa); copy4(ql, qpos + qa); }
+            else axisAngle2Quat(ql, m.jnt_axis + 3 * jid, qpos[qa] - m.qpos0[qa]);
+            mulQuat(qn, q, ql);
+            copy4(q, qn);
+            rotQ(v, m.jnt_pos + 3 * jid, q);
             sub3(p, anchor, v);
           }
           copy3(xanchor + 3 * jid, anchor);
           copy3(xaxis + 3 * jid, axis);
         }
       }
-      normalize4(q);
-      copy4(xquat + 4 * i, q);
-      copy3(xpos + 3 * i, p);
-      quat2Mat(xmat + 9 * i, q);
+    }
+    copy3(T0 + 7 * i, p);
+    copy4(T0 + 7 * i + 3, q);
+  }
+  WSYNC();
+  // (B) pointer jumping: after round r, T[i] maps body i to the frame of its ancestor 2^(r+1) levels up
+  double* src = T0;
+  double* dst = T1;
+  for (int r = 0; r < m.njump; r++) {
+    const int* jump = m.body_jump + r * m.nbody;
+    FORL(i, m.nbody) {
+      const int a = jump[i];
+      const double* ti = src + 7 * i;
+      if (a == 0) {
+        for (int k = 0; k < 7; k++) dst[7 * i + k] = ti[k];
+      } else {
+        const double* ta = src + 7 * a;
+        double v[3], q[4];
+        rotQ(v, ti, ta + 3);
+        mulQuat(q, ta + 3, ti + 3);
+        dst[7 * i] = ta[0] + v[0]; dst[7 * i + 1] = ta[1] + v[1]; dst[7 * i + 2] = ta[2] + v[2];
+        copy4(dst + 7 * i + 3, q);
+      }
     }
     WSYNC();
+    double* t = src; src = dst; dst = t;
   }
-  // inertial, geom and site frames
+  // (C) world frames
   FORL(i, m.nbody) {
-    if (i == 0) continue;
-    double v[3], q[4];
-    rotVecMat(v, m.body_ipos + 3 * i, xmat + 9 * i);
-    add3(xipos + 3 * i, v, xpos + 3 * i);
-    mulQuat(q, xquat + 4 * i, m.body_iquat + 4 * i);
-    quat2Mat(ximat + 9 * i, q);
+    double q[4], p[3], mat[9];
+    copy3(p, src + 7 * i);
+    copy4(q, src + 7 * i + 3);
+    normalize4(q);
+    quat2Mat(mat, q);
+    copy3(xpos + 3 * i, p);
+    copy4(xquat + 4 * i, q);
+    for (int k = 0; k < 9; k++) xmat[9 * i + k] = mat[k];
+    if (i) {
+      double v[3], qi[4];
+      rotVecMat(v, m.body_ipos + 3 * i, mat);
+      add3(xipos + 3 * i, v, p);
+      mulQuat(qi, q, m.body_iquat + 4 * i);
+      quat2Mat(ximat + 9 * i, qi);
+    } else {
+      zero3(xipos);
+      for (int k = 0; k < 9; k++) ximat[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    }
+  }
+  WSYNC();
+  FORL(j, m.njnt) {
+    if (m.jnt_type[j] == B2MJ_JNT_FREE) continue;  // already in the world frame
+    const int pid = m.body_parentid[m.jnt_bodyid[j]];
+    if (pid) {
+      double a[3], x[3];
+      rotVecMat(a, xanchor + 3 * j, xmat + 9 * pid);
+      add3(xanchor + 3 * j, a, xpos + 3 * pid);
+      rotVecMat(x, xaxis + 3 * j, xmat + 9 * pid);
+      copy3(xaxis + 3 * j, x);
+    }
   }
   double* gxpos = e.D(B2MJ_F_GEOM_XPOS);
   double* gxmat = e.D(B2MJ_F_GEOM_XMAT);
@@ -128,9 +180,9 @@ __device__ void stage_kinematics(const Env& e) {
   WSYNC();
 }
 
-// mj_comPos
-__device__ void stage_comPos(const Env& e) {
-  const DevModel& m = e.m;
+// mj_comPos: subtree sums are gathers over the subtree bit masks (one lane per body)
+__device__ void stage_comPos(const Env e) {
+  const DevModel& m = c_dm;
   const double* xipos = e.D(B2MJ_F_XIPOS);
   const double* ximat = e.D(B2MJ_F_XIMAT);
   const double* xmat = e.D(B2MJ_F_XMAT);
@@ -139,15 +191,19 @@ __device__ void stage_comPos(const Env& e) {
   double* com = e.D(B2MJ_F_SUBTREE_COM);
   double* cinert = e.D(B2MJ_F_CINERT);
   double* cdof = e.D(B2MJ_F_CDOF);
-  FORL(k, 3 * m.nbody) com[k] = 0;
-  WSYNC();
-  if (e.lane < 3) {
-    const int c = e.lane;
-    for (int i = m.nbody - 1; i >= 0; i--) {
-      double s = com[3 * i + c] + xipos[3 * i + c] * m.body_mass[i];
-      if (i) com[3 * m.body_parentid[i] + c] += s;
-      const double sm = m.body_subtreemass[i];
-      com[3 * i + c] = (sm < B2K_MINVAL) ? xipos[3 * i + c] : s * (1.0 / fmax(B2K_MINVAL, sm));
+  FORL(b, m.nbody) {
+    const double sm = m.body_subtreemass[b];
+    if (sm < B2K_MINVAL) {
+      copy3(com + 3 * b, xipos + 3 * b);
+    } else {
+      double s0 = 0, s1 = 0, s2 = 0;
+      const unsigned* mask = m.body_submask + b * m.nbodyword;
+      FOR_MASK_BITS(i, mask, m.nbodyword, {
+        const double mi = m.body_mass[i];
+        s0 += xipos[3 * i] * mi; s1 += xipos[3 * i + 1] * mi; s2 += xipos[3 * i + 2] * mi;
+      })
+      const double inv = 1.0 / fmax(B2K_MINVAL, sm);
+      com[3 * b] = s0 * inv; com[3 * b + 1] = s1 * inv; com[3 * b + 2] = s2 * inv;
     }
   }
   WSYNC();
@@ -188,8 +244,8 @@ __device__ void stage_comPos(const Env& e) {
 }
 
 // mj_tendon (fixed) + mj_transmission
-__device__ void stage_tendon_transmission(const Env& e) {
-  const DevModel& m = e.m;
+__device__ void stage_tendon_transmission(const Env e) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* qpos = e.D(B2MJ_F_QPOS);
   if (m.ntendon) {
@@ -211,58 +267,111 @@ __device__ void stage_tendon_transmission(const Env& e) {
   if (m.nu) {
     double* al = e.D(B2MJ_F_ACTUATOR_LENGTH);
     double* am = e.D(B2MJ_F_ACTUATOR_MOMENT);
-    FORL(k, m.nu * nv) am[k] = 0;
-    WSYNC();
+    const double* tl = m.ntendon ? e.D(B2MJ_F_TEN_LENGTH) : nullptr;
+    const double* tJ = m.ntendon ? e.D(B2MJ_F_TEN_J) : nullptr;
+    // one lane per (actuator, dof) entry of the moment matrix
+    FORL(item, m.nu * nv) {
+      const int i = item / nv, k = item - i * nv;
+      const int id = m.actuator_trnid[2 * i];
+      const double gear = m.actuator_gear[6 * i];
+      double v;
+      if (m.actuator_trntype[i] == B2MJ_TRN_TENDON) v = tJ[id * nv + k] * gear;
+      else v = (k == m.jnt_dofadr[id]) ? gear : 0.0;
+      am[item] = v;
+    }
     FORL(i, m.nu) {
       const int id = m.actuator_trnid[2 * i];
       const double gear = m.actuator_gear[6 * i];
-      if (m.actuator_trntype[i] == B2MJ_TRN_TENDON) {
-        const double* tl = e.D(B2MJ_F_TEN_LENGTH);
-        const double* tJ = e.D(B2MJ_F_TEN_J);
-        al[i] = tl[id] * gear;
-        for (int k = 0; k < nv; k++) am[i * nv + k] = tJ[id * nv + k] * gear;
-      } else {
-        al[i] = qpos[m.jnt_qposadr[id]] * gear;
-        am[i * nv + m.jnt_dofadr[id]] = gear;
-      }
+      al[i] = (m.actuator_trntype[i] == B2MJ_TRN_TENDON ? tl[id] : qpos[m.jnt_qposadr[id]]) * gear;
     }
     WSYNC();
   }
 }
 
-// sparse L'DL factorisation in place (mj_factorI); lane 0 walks dofs, lanes share each row update
-__device__ void factorLD(const Env& e, double* LD, double* diaginv, double* sqrtdiaginv) {
-  const DevModel& m = e.m;
+// In-place sparse L'DL factorisation (mj_factorI) of up to two matrices with the same sparsity at once:
+// lanes 0-15 factor A, lanes 16-31 factor B (B = null: all 32 lanes on A).  Per pivot k the rank-1
+// update of the ancestor rows runs one lane per (ancestor row, column) pair.
+__device__ void factorLD2(const Env e, double* A, double* Bm, double* dinvA, double* sqrtinvA, double* dinvB) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
+  const int half = Bm ? (e.lane >> 4) : 0, sub = Bm ? (e.lane & 15) : e.lane, stride = Bm ? 16 : 32;
+  double* LD = half ? Bm : A;
   for (int k = nv - 1; k >= 0; k--) {
+    const int d = m.dof_nanc[k];
+    if (d == 0) continue;
     const int Mkk = m.dof_Madr[k];
-    // ancestors of k: a = 0.. ; entry M(k, anc_a) at Mkk+1+a.  All ancestor rows update independently
-    // from the *original* row k, so: phase 1 rows, phase 2 scale row k.
-    const double dkk = LD[Mkk];
-    int i = m.dof_parentid[k];
-    int a = 0;
-    while (i >= 0) {
-      const double tmp = LD[Mkk + 1 + a] / dkk;
-      const int rowadr = m.dof_Madr[i];
-      const int cnt = (i < nv - 1 ? m.dof_Madr[i + 1] : m.nM) - rowadr;
-      FORL(c, cnt) LD[rowadr + c] -= LD[Mkk + 1 + a + c] * tmp;
-      i = m.dof_parentid[i];
-      a++;
+    const double inv = 1.0 / LD[Mkk];
+    for (int idx = sub; idx < d * d; idx += stride) {
+      const int a = idx / d, c = idx - a * d;
+      if (c < d - a) LD[m.M_ancadr[Mkk + 1 + a] + c] -= LD[Mkk + 1 + a] * LD[Mkk + 1 + a + c] * inv;
     }
     WSYNC();
-    FORL(c, a) LD[Mkk + 1 + c] = LD[Mkk + 1 + c] / dkk;
+    for (int c = sub; c < d; c += stride) LD[Mkk + 1 + c] *= inv;
     WSYNC();
   }
-  FORL(i, nv) {
+  for (int i = sub; i < nv; i += stride) {
     const double Dv = LD[m.dof_Madr[i]];
-    diaginv[i] = 1.0 / Dv;
-    if (sqrtdiaginv) sqrtdiaginv[i] = 1.0 / sqrt(Dv);
+    if (half) dinvB[i] = 1.0 / Dv;
+    else {
+      dinvA[i] = 1.0 / Dv;
+      if (sqrtinvA) sqrtinvA[i] = 1.0 / sqrt(Dv);
+    }
+  }
+  WSYNC();
+}
+
+// W = inv(L) (unit lower triangular, same tree sparsity as L) for up to two factorisations at once.
+// Off-diagonals only, stored in the sparse layout of qM.  Rows depend on the rows of their ancestors,
+// so dofs are processed by depth level, one lane per (dof, ancestor) entry.
+__device__ void invL2(const Env e, const double* LA, double* WA, const double* LB, double* WB) {
+  const DevModel& m = c_dm;
+  const int half = LB ? (e.lane >> 4) : 0, sub = LB ? (e.lane & 15) : e.lane, stride = LB ? 16 : 32;
+  const double* LD = half ? LB : LA;
+  double* W = half ? WB : WA;
+  for (int l = 1; l < m.ndoflevel; l++) {
+    const int adr0 = m.doflevel_adr[l], cnt = m.doflevel_adr[l + 1] - adr0;
+    for (int item = sub; item < cnt * l; item += stride) {
+      const int i = m.doflevel_dof[adr0 + item / l], a = item % l;
+      const int row = m.dof_Madr[i] + 1;
+      double s = -LD[row + a];
+      for (int b = 0; b < a; b++) s -= LD[row + b] * W[m.M_ancadr[row + b] + (a - b)];
+      W[row + a] = s;
+    }
+    WSYNC();
+  }
+}
+
+// y = W' x (gather over the descendants of each dof); in place is NOT allowed
+__device__ __forceinline__ void mulWT(const Env e, double* y, const double* W, const double* x) {
+  const DevModel& m = c_dm;
+  FORL(k, m.nv) {
+    double s = x[k];
+    for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
+    y[k] = s;
+  }
+}
+
+// x <- inv(L'DL) x = W diag(dinv) W' x for one right-hand side, whole warp; tmp: nv scratch
+__device__ void solveW_warp(const Env e, double* x, const double* W, const double* dinv, double* tmp) {
+  const DevModel& m = c_dm;
+  FORL(k, m.nv) {
+    double s = x[k];
+    for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
+    tmp[k] = s * dinv[k];
+  }
+  WSYNC();
+  FORL(i, m.nv) {
+    const int row = m.dof_Madr[i] + 1, d = m.dof_nanc[i];
+    double s = tmp[i];
+    for (int a = 0; a < d; a++) s += W[row + a] * tmp[m.M_col[row + a]];
+    x[i] = s;
   }
   WSYNC();
 }
 
 // x <- inv(L'DL) x, executed by ONE lane (callers distribute independent right-hand sides over lanes)
-__device__ __forceinline__ void solveLD_lane(const DevModel& m, double* x, const double* LD, const double* diaginv) {
+__device__ __forceinline__ void solveLD_lane(double* x, const double* LD, const double* diaginv) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   for (int i = nv - 1; i >= 0; i--) {
     const double t = x[i];
@@ -279,67 +388,55 @@ __device__ __forceinline__ void solveLD_lane(const DevModel& m, double* x, const
   }
 }
 
-// res = M * vec with one lane per output row (gather form of mj_mulM)
-__device__ void mulM_warp(const Env& e, double* res, const double* vec) {
-  const DevModel& m = e.m;
+// res = M * vec: one lane per output row; row part over ancestors, column part over descendants
+__device__ void mulM_warp(const Env e, double* res, const double* vec) {
+  const DevModel& m = c_dm;
   const double* qM = e.D(B2MJ_F_QM);
-  FORL(i, m.nv) res[i] = 0;
-  WSYNC();
-  // scatter form keeps MuJoCo's summation structure; executed per dof with atomics avoided by
-  // splitting into the "row" part (lane i) and the "column" part (lane j) below
   FORL(i, m.nv) {
-    int adr = m.dof_Madr[i];
-    double s = qM[adr] * vec[i];
-    adr++;
-    for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) s += qM[adr++] * vec[j];
+    const int row = m.dof_Madr[i], d = m.dof_nanc[i];
+    double s = qM[row] * vec[i];
+    for (int a = 0; a < d; a++) s += qM[row + 1 + a] * vec[m.M_col[row + 1 + a]];
+    for (int p = m.dof_descadr[i]; p < m.dof_descadr[i + 1]; p++) s += qM[m.dof_desc_adr[p]] * vec[m.dof_desc_dof[p]];
     res[i] = s;
-  }
-  WSYNC();
-  // contributions M(i,j)*vec[i] to res[j] for descendants i of j: serial over i per lane j via mask
-  FORL(j, m.nv) {
-    double s = res[j];
-    for (int i = j + 1; i < m.nv; i++) {
-      // is j an ancestor of i?  walk is short (tree depth)
-      int adr = m.dof_Madr[i] + 1;
-      for (int p = m.dof_parentid[i]; p >= 0; p = m.dof_parentid[p], adr++)
-        if (p == j) { s += qM[adr] * vec[i]; break; }
-        else if (p < j) break;
-    }
-    res[j] = s;
   }
   WSYNC();
 }
 
-// mj_crb + mj_factorM
-__device__ void stage_crb_factor(const Env& e) {
-  const DevModel& m = e.m;
+// mj_crb + mj_factorM, plus the Euler-damping matrix qH = qM + h diag(damping) factored alongside
+__device__ void stage_crb_factor(const Env e) {
+  const DevModel& m = c_dm;
   const double* cinert = e.D(B2MJ_F_CINERT);
   const double* cdof = e.D(B2MJ_F_CDOF);
   double* crb = e.D(B2MJ_F_CRB);
   double* qM = e.D(B2MJ_F_QM);
   double* qLD = e.D(B2MJ_F_QLD);
-  FORL(k, 10 * m.nbody) crb[k] = cinert[k];
-  WSYNC();
-  if (e.lane < 10) {
-    const int c = e.lane;
-    for (int i = m.nbody - 1; i > 0; i--) {
-      const int p = m.body_parentid[i];
-      if (p > 0) crb[10 * p + c] += crb[10 * i + c];
+  double* buf = e.X(XF_DOFBUF);
+  const bool damped = m.any_damping && !(m.opt.disableflags & B2MJ_DSBL_EULERDAMP) && m.opt.integrator == B2MJ_INT_EULER;
+  double* qH = damped ? e.X(XF_QH) : nullptr;
+  FORL(b, m.nbody) {
+    double s[10];
+    for (int k = 0; k < 10; k++) s[k] = 0;
+    if (b) {
+      const unsigned* mask = m.body_submask + b * m.nbodyword;
+      FOR_MASK_BITS(i, mask, m.nbodyword, { for (int k = 0; k < 10; k++) s[k] += cinert[10 * i + k]; })
     }
+    for (int k = 0; k < 10; k++) crb[10 * b + k] = s[k];
   }
   WSYNC();
-  FORL(i, m.nv) {
-    int adr = m.dof_Madr[i];
-    double buf[6];
-    mulInertVec(buf, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
-    qM[adr] = m.dof_armature[i] + dot6(cdof + 6 * i, buf);
-    adr++;
-    for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) qM[adr++] = dot6(cdof + 6 * j, buf);
+  FORL(k, m.nv) mulInertVec(buf + 6 * k, crb + 10 * m.dof_bodyid[k], cdof + 6 * k);
+  WSYNC();
+  FORL(t, m.nM) {
+    const int i = m.M_row[t], j = m.M_col[t];
+    double v = dot6(cdof + 6 * j, buf + 6 * i);
+    double hv = v;
+    if (i == j) { v += m.dof_armature[i]; hv = v + m.opt.timestep * m.dof_damping[i]; }
+    qM[t] = v;
+    qLD[t] = v;
+    if (qH) qH[t] = hv;
   }
   WSYNC();
-  FORL(k, m.nM) qLD[k] = qM[k];
-  WSYNC();
-  factorLD(e, qLD, e.D(B2MJ_F_QLDIAGINV), e.D(B2MJ_F_QLDIAGSQRTINV));
+  factorLD2(e, qLD, qH, e.D(B2MJ_F_QLDIAGINV), e.D(B2MJ_F_QLDIAGSQRTINV), qH ? e.X(XF_QHDIAGINV) : nullptr);
+  invL2(e, qLD, e.X(XF_QW), qH, qH ? e.X(XF_QHW) : nullptr);
 }
 
 __device__ __forceinline__ void mulDofVec(double* res, const double* dof, const double* vec, int n) {
@@ -348,52 +445,39 @@ __device__ __forceinline__ void mulDofVec(double* res, const double* dof, const 
     for (int k = 0; k < 6; k++) res[k] += dof[6 * i + k] * vec[i];
 }
 
-// mj_comVel (level-parallel)
-__device__ void stage_comVel(const Env& e) {
-  const DevModel& m = e.m;
+// mj_comVel: cvel of a body is the sum of cdof*qvel over the dofs of its chain (all cdof share the
+// subtree-com frame), so every body / dof is computed independently from the chain bit masks.
+__device__ void stage_comVel(const Env e) {
+  const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* qvel = e.D(B2MJ_F_QVEL);
   double* cvelA = e.D(B2MJ_F_CVEL);
   double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
-  if (e.lane < 6) cvelA[e.lane] = 0;
-  WSYNC();
-  for (int l = 1; l < m.nlevel; l++) {
-    const int ladr = m.level_bodyadr[l], lnum = m.level_bodynum[l];
-    FORL(k, lnum) {
-      const int i = m.level_body[ladr + k];
-      const int bda = m.body_dofadr[i], dofnum = m.body_dofnum[i];
-      double cvel[6], tmp[6];
-      for (int c = 0; c < 6; c++) cvel[c] = cvelA[6 * m.body_parentid[i] + c];
-      for (int j = 0; j < dofnum; j++) {
-        const int jt = m.jnt_type[m.dof_jntid[bda + j]];
-        if (jt == B2MJ_JNT_FREE) {
-          for (int c = 0; c < 18; c++) cdof_dot[6 * bda + c] = 0;
-          mulDofVec(tmp, cdof + 6 * bda, qvel + bda, 3);
-          for (int c = 0; c < 6; c++) cvel[c] += tmp[c];
-          j += 3;
-        }
-        if (jt == B2MJ_JNT_FREE || jt == B2MJ_JNT_BALL) {
-          for (int c = 0; c < 3; c++) crossMotion(cdof_dot + 6 * (bda + j + c), cvel, cdof + 6 * (bda + j + c));
-          mulDofVec(tmp, cdof + 6 * (bda + j), qvel + bda + j, 3);
-          for (int c = 0; c < 6; c++) cvel[c] += tmp[c];
-          j += 2;
-        } else {
-          crossMotion(cdof_dot + 6 * (bda + j), cvel, cdof + 6 * (bda + j));
-          mulDofVec(tmp, cdof + 6 * (bda + j), qvel + bda + j, 1);
-          for (int c = 0; c < 6; c++) cvel[c] += tmp[c];
-        }
-      }
-      for (int c = 0; c < 6; c++) cvelA[6 * i + c] = cvel[c];
-    }
-    WSYNC();
+  FORL(b, m.nbody) {
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    const unsigned* mask = m.body_dofmask + b * m.nmaskword;
+    FOR_MASK_BITS(k, mask, m.nmaskword, { const double v = qvel[k]; for (int c = 0; c < 6; c++) s[c] += cdof[6 * k + c] * v; })
+    for (int c = 0; c < 6; c++) cvelA[6 * b + c] = s[c];
   }
+  FORL(k, m.nv) {
+    const int jid = m.dof_jntid[k];
+    if (m.jnt_type[jid] == B2MJ_JNT_FREE && k < m.jnt_dofadr[jid] + 3) {
+      for (int c = 0; c < 6; c++) cdof_dot[6 * k + c] = 0;
+      continue;
+    }
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    const unsigned* mask = m.dof_premask + k * m.nmaskword;
+    FOR_MASK_BITS(j, mask, m.nmaskword, { const double v = qvel[j]; for (int c = 0; c < 6; c++) s[c] += cdof[6 * j + c] * v; })
+    crossMotion(cdof_dot + 6 * k, s, cdof + 6 * k);
+  }
+  WSYNC();
 }
 
 // Jacobian-transpose application of a force/torque at a point of a body: one lane per dof.
 // qfrc[k] += jacp[:,k].force + jacr[:,k].torque for dofs on the body's chain.
-__device__ void applyFT_warp(const Env& e, const double* force, const double* torque, const double* point, int body,
+__device__ void applyFT_warp(const Env e, const double* force, const double* torque, const double* point, int body,
                              double* qfrc) {
-  const DevModel& m = e.m;
+  const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* com = e.D(B2MJ_F_SUBTREE_COM);
   double off[3];
@@ -412,8 +496,8 @@ __device__ void applyFT_warp(const Env& e, const double* force, const double* to
 }
 
 // mj_passive (springs, dampers, gravity compensation); the host passive hook is a split-step feature
-__device__ void stage_passive(const Env& e) {
-  const DevModel& m = e.m;
+__device__ void stage_passive(const Env e) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* qpos = e.D(B2MJ_F_QPOS);
   const double* qvel = e.D(B2MJ_F_QVEL);
@@ -473,55 +557,47 @@ __device__ void stage_passive(const Env& e) {
   }
 }
 
-// mj_rne(flg_acc = 0): bias forces.  Uses the cacc / cfrc_int fields as scratch.
-__device__ void stage_rne_bias(const Env& e) {
-  const DevModel& m = e.m;
+// mj_rne(flg_acc = 0): bias forces, without the tree recursions: cacc of a body is the sum of
+// cdof_dot*qvel over its chain, the backward force accumulation is folded into the projection
+// bias[k] = cdof[k] . sum_{i in subtree(body(k))} f_i.
+__device__ void stage_rne_bias(const Env e) {
+  const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
   const double* cvel = e.D(B2MJ_F_CVEL);
   const double* cinert = e.D(B2MJ_F_CINERT);
   const double* qvel = e.D(B2MJ_F_QVEL);
-  double* cacc = e.D(B2MJ_F_CACC);
-  double* cfrc = e.D(B2MJ_F_CFRC_INT);
+  double* fb = e.X(XF_BODYBUF);
   double* bias = e.D(B2MJ_F_QFRC_BIAS);
-  if (e.lane < 6) {
-    double g = 0;
-    if (e.lane >= 3 && !(m.opt.disableflags & B2MJ_DSBL_GRAVITY)) g = -m.opt.gravity[e.lane - 3];
-    cacc[e.lane] = g;
-    cfrc[e.lane] = 0;
-  }
-  WSYNC();
-  for (int l = 1; l < m.nlevel; l++) {
-    const int ladr = m.level_bodyadr[l], lnum = m.level_bodynum[l];
-    FORL(k, lnum) {
-      const int i = m.level_body[ladr + k];
-      const int bda = m.body_dofadr[i];
-      double tmp[6], tmp1[6], acc[6], f[6];
-      mulDofVec(tmp, cdof_dot + 6 * bda, qvel + bda, m.body_dofnum[i]);
-      for (int c = 0; c < 6; c++) acc[c] = cacc[6 * m.body_parentid[i] + c] + tmp[c];
-      for (int c = 0; c < 6; c++) cacc[6 * i + c] = acc[c];
-      mulInertVec(f, cinert + 10 * i, acc);
-      mulInertVec(tmp, cinert + 10 * i, cvel + 6 * i);
-      crossForce(tmp1, cvel + 6 * i, tmp);
-      for (int c = 0; c < 6; c++) cfrc[6 * i + c] = f[c] + tmp1[c];
-    }
-    WSYNC();
-  }
-  if (e.lane < 6) {
-    const int c = e.lane;
-    for (int i = m.nbody - 1; i > 0; i--) {
-      const int p = m.body_parentid[i];
-      if (p) cfrc[6 * p + c] += cfrc[6 * i + c];
+  const bool grav = !(m.opt.disableflags & B2MJ_DSBL_GRAVITY);
+  FORL(b, m.nbody) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (grav) { acc[3] = -m.opt.gravity[0]; acc[4] = -m.opt.gravity[1]; acc[5] = -m.opt.gravity[2]; }
+    const unsigned* mask = m.body_dofmask + b * m.nmaskword;
+    FOR_MASK_BITS(k, mask, m.nmaskword, { const double v = qvel[k]; for (int c = 0; c < 6; c++) acc[c] += cdof_dot[6 * k + c] * v; })
+    double f[6], tmp[6], tmp1[6];
+    if (b) {
+      mulInertVec(f, cinert + 10 * b, acc);
+      mulInertVec(tmp, cinert + 10 * b, cvel + 6 * b);
+      crossForce(tmp1, cvel + 6 * b, tmp);
+      for (int c = 0; c < 6; c++) fb[6 * b + c] = f[c] + tmp1[c];
+    } else {
+      for (int c = 0; c < 6; c++) fb[c] = 0;
     }
   }
   WSYNC();
-  FORL(i, m.nv) bias[i] = dot6(cdof + 6 * i, cfrc + 6 * m.dof_bodyid[i]);
+  FORL(k, m.nv) {
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    const unsigned* mask = m.body_submask + m.dof_bodyid[k] * m.nbodyword;
+    FOR_MASK_BITS(i, mask, m.nbodyword, { for (int c = 0; c < 6; c++) s[c] += fb[6 * i + c]; })
+    bias[k] = dot6(cdof + 6 * k, s);
+  }
   WSYNC();
 }
 
 // tendon / actuator velocities (head of mj_fwdVelocity)
-__device__ void stage_velocity_head(const Env& e) {
-  const DevModel& m = e.m;
+__device__ void stage_velocity_head(const Env e) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* qvel = e.D(B2MJ_F_QVEL);
   if (m.ntendon) {
@@ -546,8 +622,8 @@ __device__ void stage_velocity_head(const Env& e) {
 }
 
 // mj_fwdActuation
-__device__ void stage_actuation(const Env& e, int* warning) {
-  const DevModel& m = e.m;
+__device__ void stage_actuation(const Env e, int* warning) {
+  const DevModel& m = c_dm;
   const int nv = m.nv, nu = m.nu;
   double* qa = e.D(B2MJ_F_QFRC_ACTUATOR);
   if (!nu || (m.opt.disableflags & B2MJ_DSBL_ACTUATION)) {
@@ -603,8 +679,8 @@ __device__ void stage_actuation(const Env& e, int* warning) {
 }
 
 // mj_fwdAcceleration
-__device__ void stage_acceleration(const Env& e, const double* xfrc) {
-  const DevModel& m = e.m;
+__device__ void stage_acceleration(const Env e, const double* xfrc) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
   double* qas = e.D(B2MJ_F_QACC_SMOOTH);
@@ -629,13 +705,12 @@ __device__ void stage_acceleration(const Env& e, const double* xfrc) {
   }
   FORL(i, nv) qas[i] = qs[i];
   WSYNC();
-  if (e.lane == 0) solveLD_lane(m, qas, e.D(B2MJ_F_QLD), e.D(B2MJ_F_QLDIAGINV));
-  WSYNC();
+  solveW_warp(e, qas, e.X(XF_QW), e.D(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
 }
 
 // mj_integratePos for the joints handled by this lane
-__device__ void integratePos_warp(const Env& e, double* qpos, const double* qvel, double dt) {
-  const DevModel& m = e.m;
+__device__ void integratePos_warp(const Env e, double* qpos, const double* qvel, double dt) {
+  const DevModel& m = c_dm;
   FORL(j, m.njnt) {
     int padr = m.jnt_qposadr[j], vadr = m.jnt_dofadr[j];
     const int jt = m.jnt_type[j];
@@ -650,8 +725,8 @@ __device__ void integratePos_warp(const Env& e, double* qpos, const double* qvel
 }
 
 // mj_advance
-__device__ void advance_warp(const Env& e, const double* act_dot, const double* qacc, const double* qvel_for_pos) {
-  const DevModel& m = e.m;
+__device__ void advance_warp(const Env e, const double* act_dot, const double* qacc, const double* qvel_for_pos) {
+  const DevModel& m = c_dm;
   const double h = m.opt.timestep;
   double* qvel = e.D(B2MJ_F_QVEL);
   if (m.na) {
@@ -672,27 +747,21 @@ __device__ void advance_warp(const Env& e, const double* act_dot, const double* 
 }
 
 // mj_Euler: semi-implicit Euler, implicit in joint damping
-__device__ void stage_euler(const Env& e) {
-  const DevModel& m = e.m;
+__device__ void stage_euler(const Env e) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* act_dot = m.na ? e.D(B2MJ_F_ACT_DOT) : nullptr;
   if (!m.any_damping || (m.opt.disableflags & B2MJ_DSBL_EULERDAMP)) {
     advance_warp(e, act_dot, e.D(B2MJ_F_QACC), nullptr);
     return;
   }
-  double* qH = e.X(XF_QH);
-  double* qHd = e.X(XF_QHDIAGINV);
   double* acc = e.X(XF_VEC0);
-  const double* qM = e.D(B2MJ_F_QM);
   const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
   const double* qc = e.D(B2MJ_F_QFRC_CONSTRAINT);
-  FORL(k, m.nM) qH[k] = qM[k];
+  FORL(i, nv) acc[i] = qs[i] + qc[i];
   WSYNC();
-  FORL(i, nv) { qH[m.dof_Madr[i]] += m.opt.timestep * m.dof_damping[i]; acc[i] = qs[i] + qc[i]; }
-  WSYNC();
-  factorLD(e, qH, qHd, nullptr);
-  if (e.lane == 0) solveLD_lane(m, acc, qH, qHd);
-  WSYNC();
+  // qH = qM + h diag(damping) was factored (and inverted) next to qM in stage_crb_factor
+  solveW_warp(e, acc, e.X(XF_QHW), e.X(XF_QHDIAGINV), e.X(XF_VEC1));
   advance_warp(e, act_dot, acc, nullptr);
 }
 

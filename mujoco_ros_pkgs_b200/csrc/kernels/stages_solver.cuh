@@ -3,13 +3,12 @@
 // Replaces mj_projectConstraint + mj_solPGS / mj_solNewton inside the reference's mj_step call
 // (mujoco_env.cpp:498; rows M6/M9 of SURVEY 8a).
 //
-// PGS is run matrix-free: instead of the nefc x nefc matrix AR = J inv(M) J' + R (MuJoCo's efc_AR)
-// the warp keeps the nefc x nv factor B = (inv(M) J')' and the running vector a = inv(M) J' f, so a row
-// residual is b_i + J_i.a + R_i f_i (one nv-long dot product done with a warp shuffle reduction) and a
-// force change costs one nv-long axpy.  Same fixed point and same sweep order as the dense form;
-// memory per env drops from nefc^2 to nefc*nv doubles, which is what lets the arena stay in shared
-// memory.  Projections: equality free, friction loss box, limits / frictionless / pyramidal rows f>=0,
-// elliptic contacts as a block (ray update, then QCQP over the friction dims with the normal fixed).
+// PGS works on the explicit dual matrix AR = J inv(M) J' + R (MuJoCo's efc_AR), built wide-parallel from
+// G = J W with W = inv(L) of the L'DL factor: AR = G diag(1/D) G' + R.  The sweep itself keeps the row
+// residuals r = b + AR f distributed over the lanes' registers (lane j owns rows j, j+32): a row update
+// is one shuffle to fetch r_i, a handful of scalar flops executed redundantly by every lane, and one
+// FMA per lane to push the force change into the residuals -- no per-row reductions.  Same sweep order,
+// projections and cost guard as mj_solPGS.  Rows beyond 64 fall back to the matrix-free form.
 #pragma once
 #include "env_ctx.cuh"
 #include "stages_constraint.cuh"
@@ -17,30 +16,56 @@
 
 namespace b2k {
 
-// rows of B = inv(M) J' (row i = inv(M) J_i') and the diagonal of AR
-__device__ void stage_projectConstraint(const Env& e, int nefc) {
+#define B2K_PGS_REGROWS 64
+
+// AR lives in shared memory when it fits the small buffer, else in the env's HBM/L2 arena
+__device__ __forceinline__ double* arPtr(const Env e, int nefc) {
+  return nefc * nefc <= c_dm.xsize[XF_EFC_AR_S] ? e.X(XF_EFC_AR_S) : e.XG(XF_EFC_AR);
+}
+
+// G = J W (rows of J pushed through inv(L)) and AR = G diag(1/D) G' + R
+__device__ void stage_projectConstraint(const Env e, int nefc) {
   if (!nefc) return;
-  const DevModel& m = e.m;
+  const DevModel& m = c_dm;
   const int nv = m.nv;
-  const double* J = e.D(B2MJ_F_EFC_J);
+  const double* J = e.DG(B2MJ_F_EFC_J);
   const double* R = e.D(B2MJ_F_EFC_R);
-  double* B = e.X(XF_EFC_MINVJT);
-  double* ard = e.X(XF_EFC_ARDIAG);
-  const double* qLD = e.D(B2MJ_F_QLD);
+  const double* W = e.X(XF_QW);
   const double* dinv = e.D(B2MJ_F_QLDIAGINV);
-  FORL(i, nefc) {
-    double* b = B + i * nv;
-    for (int k = 0; k < nv; k++) b[k] = J[i * nv + k];
-    solveLD_lane(m, b, qLD, dinv);
-    double s = 0;
-    for (int k = 0; k < nv; k++) s += J[i * nv + k] * b[k];
-    ard[i] = s + R[i];
+  double* G = e.XG(XF_EFC_MINVJT);
+  FORL(item, nefc * nv) {
+    const int i = item / nv, k = item - i * nv;
+    const double* Ji = J + i * nv;
+    double s = Ji[k];
+    for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * Ji[m.dof_desc_dof[p]];
+    G[item] = s;
+  }
+  WSYNC();
+  double* ard = e.X(XF_EFC_ARDIAG);
+  if (nefc <= B2K_PGS_REGROWS) {
+    double* AR = arPtr(e, nefc);
+    // lower triangle incl. diagonal, mirrored
+    for (int item = e.lane; item < nefc * nefc; item += 32) {
+      const int i = item / nefc, j = item - i * nefc;
+      if (j > i) continue;
+      double s = 0;
+      for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[j * nv + k] * dinv[k];
+      if (i == j) { s += R[i]; ard[i] = s; }
+      AR[i * nefc + j] = s;
+      AR[j * nefc + i] = s;
+    }
+  } else {
+    FORL(i, nefc) {
+      double s = 0;
+      for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[i * nv + k] * dinv[k];
+      ard[i] = s + R[i];
+    }
   }
   WSYNC();
 }
 
 // dot of a constraint row with an nv-vector, result identical on all lanes
-__device__ __forceinline__ double rowDot(const Env& e, const double* row, const double* vec, int nv) {
+__device__ __forceinline__ double rowDot(const Env e, const double* row, const double* vec, int nv) {
   double s = 0;
   FORL(k, nv) s += row[k] * vec[k];
   return warpSum(s);
@@ -105,104 +130,128 @@ __device__ int QCQP(double* res, const double* Ain, const double* bin, const dou
   return la != 0;
 }
 
-// mj_solPGS (matrix-free).  force holds the warm start on entry.  Returns iterations used.
-__device__ int solvePGS(const Env& e, int nefc, double* avec) {
-  const DevModel& m = e.m;
-  const int nv = m.nv;
-  EfcPtrs P = efcPtrs(e);
-  const double* B = e.X(XF_EFC_MINVJT);
-  const double* ard = e.X(XF_EFC_ARDIAG);
-  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
-  const double* c_fri = e.D(B2MJ_F_CONTACT_FRICTION);
-  const double scale = 1 / (m.meaninertia * max(1, nv));
-  // a = inv(M) J' f
-  FORL(k, nv) {
-    double s = 0;
-    for (int i = 0; i < nefc; i++) s += B[i * nv + k] * P.force[i];
-    avec[k] = s;
+// weighted row product sum_k a[k] b[k] w[k], identical on all lanes
+__device__ __forceinline__ double rowDotW(const Env e, const double* a, const double* b, const double* w, int nv) {
+  double s = 0;
+  FORL(k, nv) s += a[k] * b[k] * w[k];
+  return warpSum(s);
+}
+
+// elliptic-cone block update shared by both PGS forms: given the dim x dim block Athis of AR, the block
+// residual res and the old forces, produce the new forces f (ray update, then QCQP on the friction dims)
+__device__ void pgsConeBlock(int dim, const double* Athis, const double* res, const double* oldf, const double* fri, double* f) {
+  for (int j = 0; j < dim; j++) f[j] = oldf[j];
+  if (f[0] < B2K_MINVAL) {
+    f[0] -= res[0] / Athis[0];
+    if (f[0] < 0) f[0] = 0;
+    for (int j = 1; j < dim; j++) f[j] = 0;
+  } else {
+    double v[6], v1[6];
+    for (int j = 0; j < dim; j++) v[j] = f[j];
+    double denom = 0, num = 0;
+    for (int j = 0; j < dim; j++) {
+      double s = 0;
+      for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * v[k];
+      v1[j] = s;
+    }
+    for (int j = 0; j < dim; j++) { denom += v[j] * v1[j]; num += v[j] * res[j]; }
+    if (denom >= B2K_MINVAL) {
+      double x = -num / denom;
+      if (f[0] + x * v[0] < 0) x = -v[0] / f[0];
+      for (int j = 0; j < dim; j++) f[j] += x * v[j];
+    }
   }
-  WSYNC();
+  if (f[0] < B2K_MINVAL) {
+    for (int j = 1; j < dim; j++) f[j] = 0;
+  } else {
+    double Ac[25], bc[5], v[5];
+    for (int j = 0; j < dim - 1; j++) {
+      for (int k = 0; k < dim - 1; k++) Ac[j * (dim - 1) + k] = Athis[(j + 1) * dim + k + 1];
+      double t = res[j + 1];
+      for (int k = 0; k < dim; k++) t -= Athis[(j + 1) * dim + k] * oldf[k];
+      t += Athis[(j + 1) * dim] * f[0];
+      bc[j] = t;
+    }
+    const int active = QCQP(v, Ac, bc, fri, f[0], dim - 1);
+    if (active) {
+      double s = 0;
+      for (int j = 0; j < dim - 1; j++) s += (v[j] / fri[j]) * (v[j] / fri[j]);
+      s = sqrt(f[0] * f[0] / fmax(B2K_MINVAL, s));
+      for (int j = 0; j < dim - 1; j++) v[j] *= s;
+    }
+    for (int j = 0; j < dim - 1; j++) f[1 + j] = v[j];
+  }
+}
+
+// mj_solPGS on the explicit AR with register-resident residuals (nefc <= 64).  force holds the
+// (already accepted) warm start on entry.  Returns iterations used.
+__device__ int solvePGS_reg(const Env e, int nefc) {
+  const DevModel& m = c_dm;
+  EfcPtrs P = efcPtrs(e);
+  const double* AR = arPtr(e, nefc);
+  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
+  const double scale = 1 / (m.meaninertia * max(1, m.nv));
+  const int lane = e.lane;
+  const bool two = nefc > 32;
+  // per-lane rows j0 = lane, j1 = lane + 32: residual r = b + AR f, force, row constants
+  const int j0 = lane, j1 = lane + 32;
+  double r0 = 0, r1 = 0, f0 = 0, f1 = 0, a0 = 1, a1 = 1, fl0 = 0, fl1 = 0;
+  int t0 = -1, t1 = -1;
+  if (j0 < nefc) {
+    f0 = P.force[j0]; a0 = AR[j0 * nefc + j0]; fl0 = P.floss[j0]; t0 = P.type[j0];
+    double s = P.b[j0];
+    for (int k = 0; k < nefc; k++) s += AR[j0 * nefc + k] * P.force[k];
+    r0 = s;
+  }
+  if (j1 < nefc) {
+    f1 = P.force[j1]; a1 = AR[j1 * nefc + j1]; fl1 = P.floss[j1]; t1 = P.type[j1];
+    double s = P.b[j1];
+    for (int k = 0; k < nefc; k++) s += AR[j1 * nefc + k] * P.force[k];
+    r1 = s;
+  }
+  const double ia0 = 1.0 / a0, ia1 = 1.0 / a1;
   int iter = 0;
   while (iter < m.opt.iterations) {
     double improvement = 0;
     for (int i = 0; i < nefc;) {
-      const int type = P.type[i];
+      const int src = i & 31;
+      const bool hi = i >= 32;
+      const int type = __shfl_sync(0xffffffffu, hi ? t1 : t0, src);
       if (type != B2MJ_CNSTR_CONTACT_ELLIPTIC) {
-        const double fold = P.force[i];
-        const double Aii = ard[i];
-        const double res = P.b[i] + rowDot(e, P.J + i * nv, avec, nv) + P.R[i] * fold;
-        double f = fold - res / Aii;
+        const double arow0 = AR[i * nefc + (j0 < nefc ? j0 : 0)];
+        const double arow1 = two ? AR[i * nefc + (j1 < nefc ? j1 : 0)] : 0.0;
+        const double fold = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
+        const double Aii = __shfl_sync(0xffffffffu, hi ? a1 : a0, src);
+        const double iA = __shfl_sync(0xffffffffu, hi ? ia1 : ia0, src);
+        const double res = __shfl_sync(0xffffffffu, hi ? r1 : r0, src);
+        double f = fold - res * iA;
         if (type == B2MJ_CNSTR_FRICTION_DOF || type == B2MJ_CNSTR_FRICTION_TENDON) {
-          const double fl = P.floss[i];
+          const double fl = __shfl_sync(0xffffffffu, hi ? fl1 : fl0, src);
           f = clampd(f, -fl, fl);
         } else if (type != B2MJ_CNSTR_EQUALITY) {
           if (f < 0) f = 0;
         }
         double delta = f - fold;
-        double change = 0.5 * delta * delta * Aii + delta * res;
+        double change = delta * (0.5 * delta * Aii + res);
         if (change > 1e-10) { delta = 0; change = 0; f = fold; }
         improvement -= change;
-        if (delta != 0) {
-          FORL(k, nv) avec[k] += delta * B[i * nv + k];
-          if (e.lane == 0) P.force[i] = f;
-          WSYNC();
-        }
+        r0 += arow0 * delta;
+        if (two) r1 += arow1 * delta;
+        if (lane == src) { if (hi) f1 = f; else f0 = f; }
         i += 1;
       } else {
         const int c = P.id[i], dim = c_dim[c];
         const double* fri = c_fri + 5 * c;
-        // dim x dim block of AR: J_(i+j) . B_(i+k) (+R on the diagonal)
         double Athis[36], res[6], oldf[6], f[6];
         for (int j = 0; j < dim; j++) {
-          for (int k = 0; k < dim; k++) {
-            double v = rowDot(e, P.J + (i + j) * nv, B + (i + k) * nv, nv);
-            if (j == k) v += P.R[i + j];
-            Athis[j * dim + k] = v;
-          }
-          oldf[j] = P.force[i + j];
-          f[j] = oldf[j];
-          res[j] = P.b[i + j] + rowDot(e, P.J + (i + j) * nv, avec, nv) + P.R[i + j] * oldf[j];
+          const int row = i + j, rs = row & 31;
+          const bool rh = row >= 32;
+          for (int k = 0; k < dim; k++) Athis[j * dim + k] = AR[row * nefc + i + k];
+          oldf[j] = __shfl_sync(0xffffffffu, rh ? f1 : f0, rs);
+          res[j] = __shfl_sync(0xffffffffu, rh ? r1 : r0, rs);
         }
-        if (f[0] < B2K_MINVAL) {
-          f[0] -= res[0] / Athis[0];
-          if (f[0] < 0) f[0] = 0;
-          for (int j = 1; j < dim; j++) f[j] = 0;
-        } else {
-          double v[6], v1[6];
-          for (int j = 0; j < dim; j++) v[j] = f[j];
-          double denom = 0, num = 0;
-          for (int j = 0; j < dim; j++) {
-            double s = 0;
-            for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * v[k];
-            v1[j] = s;
-          }
-          for (int j = 0; j < dim; j++) { denom += v[j] * v1[j]; num += v[j] * res[j]; }
-          if (denom >= B2K_MINVAL) {
-            double x = -num / denom;
-            if (f[0] + x * v[0] < 0) x = -v[0] / f[0];
-            for (int j = 0; j < dim; j++) f[j] += x * v[j];
-          }
-        }
-        if (f[0] < B2K_MINVAL) {
-          for (int j = 1; j < dim; j++) f[j] = 0;
-        } else {
-          double Ac[25], bc[5], v[5];
-          for (int j = 0; j < dim - 1; j++) {
-            for (int k = 0; k < dim - 1; k++) Ac[j * (dim - 1) + k] = Athis[(j + 1) * dim + k + 1];
-            double t = res[j + 1];
-            for (int k = 0; k < dim; k++) t -= Athis[(j + 1) * dim + k] * oldf[k];
-            t += Athis[(j + 1) * dim] * f[0];
-            bc[j] = t;
-          }
-          const int active = QCQP(v, Ac, bc, fri, f[0], dim - 1);
-          if (active) {
-            double s = 0;
-            for (int j = 0; j < dim - 1; j++) s += (v[j] / fri[j]) * (v[j] / fri[j]);
-            s = sqrt(f[0] * f[0] / fmax(B2K_MINVAL, s));
-            for (int j = 0; j < dim - 1; j++) v[j] *= s;
-          }
-          for (int j = 0; j < dim - 1; j++) f[1 + j] = v[j];
-        }
+        pgsConeBlock(dim, Athis, res, oldf, fri, f);
         double change = 0, delta[6];
         for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
         for (int j = 0; j < dim; j++) {
@@ -216,7 +265,96 @@ __device__ int solvePGS(const Env& e, int nefc, double* avec) {
         }
         improvement -= change;
         for (int j = 0; j < dim; j++) {
-          if (delta[j] != 0) FORL(k, nv) avec[k] += delta[j] * B[(i + j) * nv + k];
+          const int row = i + j;
+          if (j0 < nefc) r0 += AR[row * nefc + j0] * delta[j];
+          if (j1 < nefc) r1 += AR[row * nefc + j1] * delta[j];
+          if (lane == (row & 31)) { if (row >= 32) f1 = f[j]; else f0 = f[j]; }
+        }
+        i += dim;
+      }
+    }
+    improvement *= scale;
+    iter++;
+    if (improvement < m.opt.tolerance) break;
+  }
+  if (j0 < nefc) P.force[j0] = f0;
+  if (j1 < nefc) P.force[j1] = f1;
+  WSYNC();
+  return iter;
+}
+
+// mj_solPGS, matrix-free form for large nefc: rows of G = J inv(L) and the running vector
+// a = diag(1/D) G' f, so (AR f)_i = G_i . a + R_i f_i.  Returns iterations used.
+__device__ int solvePGS_free(const Env e, int nefc, double* avec) {
+  const DevModel& m = c_dm;
+  const int nv = m.nv;
+  EfcPtrs P = efcPtrs(e);
+  const double* G = e.XG(XF_EFC_MINVJT);
+  const double* ard = e.X(XF_EFC_ARDIAG);
+  const double* dinv = e.D(B2MJ_F_QLDIAGINV);
+  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
+  const double scale = 1 / (m.meaninertia * max(1, nv));
+  FORL(k, nv) {
+    double s = 0;
+    for (int i = 0; i < nefc; i++) s += G[i * nv + k] * P.force[i];
+    avec[k] = s * dinv[k];
+  }
+  WSYNC();
+  int iter = 0;
+  while (iter < m.opt.iterations) {
+    double improvement = 0;
+    for (int i = 0; i < nefc;) {
+      const int type = P.type[i];
+      if (type != B2MJ_CNSTR_CONTACT_ELLIPTIC) {
+        const double fold = P.force[i];
+        const double Aii = ard[i];
+        const double res = P.b[i] + rowDot(e, G + i * nv, avec, nv) + P.R[i] * fold;
+        double f = fold - res / Aii;
+        if (type == B2MJ_CNSTR_FRICTION_DOF || type == B2MJ_CNSTR_FRICTION_TENDON) {
+          const double fl = P.floss[i];
+          f = clampd(f, -fl, fl);
+        } else if (type != B2MJ_CNSTR_EQUALITY) {
+          if (f < 0) f = 0;
+        }
+        double delta = f - fold;
+        double change = 0.5 * delta * delta * Aii + delta * res;
+        if (change > 1e-10) { delta = 0; change = 0; f = fold; }
+        improvement -= change;
+        if (delta != 0) {
+          FORL(k, nv) avec[k] += delta * G[i * nv + k] * dinv[k];
+          if (e.lane == 0) P.force[i] = f;
+          WSYNC();
+        }
+        i += 1;
+      } else {
+        const int c = P.id[i], dim = c_dim[c];
+        const double* fri = c_fri + 5 * c;
+        double Athis[36], res[6], oldf[6], f[6];
+        for (int j = 0; j < dim; j++) {
+          for (int k = 0; k < dim; k++) {
+            double v = rowDotW(e, G + (i + j) * nv, G + (i + k) * nv, dinv, nv);
+            if (j == k) v += P.R[i + j];
+            Athis[j * dim + k] = v;
+          }
+          oldf[j] = P.force[i + j];
+          res[j] = P.b[i + j] + rowDot(e, G + (i + j) * nv, avec, nv) + P.R[i + j] * oldf[j];
+        }
+        pgsConeBlock(dim, Athis, res, oldf, fri, f);
+        double change = 0, delta[6];
+        for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
+        for (int j = 0; j < dim; j++) {
+          double s = 0;
+          for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * delta[k];
+          change += 0.5 * delta[j] * s + delta[j] * res[j];
+        }
+        if (change > 1e-10) {
+          change = 0;
+          for (int j = 0; j < dim; j++) { delta[j] = 0; f[j] = oldf[j]; }
+        }
+        improvement -= change;
+        for (int j = 0; j < dim; j++) {
+          if (delta[j] != 0) FORL(k, nv) avec[k] += delta[j] * G[(i + j) * nv + k] * dinv[k];
         }
         if (e.lane < dim) P.force[i + e.lane] = f[e.lane];
         WSYNC();
@@ -231,8 +369,8 @@ __device__ int solvePGS(const Env& e, int nefc, double* avec) {
 }
 
 // mj_fwdConstraint.  Returns solver iterations.
-__device__ int stage_fwdConstraint(const Env& e, int nefc, int ncon) {
-  const DevModel& m = e.m;
+__device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
+  const DevModel& m = c_dm;
   const int nv = m.nv;
   double* qacc = e.D(B2MJ_F_QACC);
   double* warm = e.D(B2MJ_F_QACC_WARMSTART);
@@ -256,7 +394,9 @@ __device__ int stage_fwdConstraint(const Env& e, int nefc, int ncon) {
   if (m.opt.solver == B2MJ_SOL_PGS) {
     double* jar = e.X(XF_EFC_JAREF);
     double* avec = e.X(XF_VEC1);
-    const double* B = e.X(XF_EFC_MINVJT);
+    const double* G = e.XG(XF_EFC_MINVJT);
+    const double* dinv = e.D(B2MJ_F_QLDIAGINV);
+    const bool reg = nefc <= B2K_PGS_REGROWS;
     if (warmstart) {
       FORL(i, nefc) {
         double s = 0;
@@ -265,34 +405,43 @@ __device__ int stage_fwdConstraint(const Env& e, int nefc, int ncon) {
       }
       WSYNC();
       constraintUpdate_warp(e, nefc, ncon, jar, false);
-      // dual cost 0.5 f'ARf + f'b with AR f = J (inv(M) J' f) + R f
-      FORL(k, nv) {
-        double s = 0;
-        for (int i = 0; i < nefc; i++) s += B[i * nv + k] * P.force[i];
-        avec[k] = s;
-      }
-      WSYNC();
+      // dual cost 0.5 f'ARf + f'b
       double cost = 0;
-      FORL(i, nefc) {
-        double s = 0;
-        for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * avec[k];
-        cost += P.force[i] * (0.5 * (s + P.R[i] * P.force[i]) + P.b[i]);
+      if (reg) {
+        const double* AR = arPtr(e, nefc);
+        FORL(i, nefc) {
+          double s = 0;
+          for (int k = 0; k < nefc; k++) s += AR[i * nefc + k] * P.force[k];
+          cost += P.force[i] * (0.5 * s + P.b[i]);
+        }
+      } else {
+        FORL(k, nv) {
+          double s = 0;
+          for (int i = 0; i < nefc; i++) s += G[i * nv + k] * P.force[i];
+          avec[k] = s * dinv[k];
+        }
+        WSYNC();
+        FORL(i, nefc) {
+          double s = 0;
+          for (int k = 0; k < nv; k++) s += G[i * nv + k] * avec[k];
+          cost += P.force[i] * (0.5 * (s + P.R[i] * P.force[i]) + P.b[i]);
+        }
       }
       cost = warpSum(cost);
+      WSYNC();
       if (cost > 0) { FORL(i, nefc) P.force[i] = 0; }
       WSYNC();
     } else {
       FORL(i, nefc) P.force[i] = 0;
       WSYNC();
     }
-    iters = solvePGS(e, nefc, avec);
+    iters = reg ? solvePGS_reg(e, nefc) : solvePGS_free(e, nefc, avec);
     // dual finish: qfrc_constraint = J' f ; qacc = qacc_smooth + inv(M) qfrc_constraint
     mulJacTVec_warp(e, nefc, qfc, P.force);
     double* tmp = e.X(XF_VEC2);
     FORL(i, nv) tmp[i] = qfc[i];
     WSYNC();
-    if (e.lane == 0) solveLD_lane(m, tmp, e.D(B2MJ_F_QLD), e.D(B2MJ_F_QLDIAGINV));
-    WSYNC();
+    solveW_warp(e, tmp, e.X(XF_QW), dinv, e.X(XF_VEC3));
     FORL(i, nv) { const double a = qas[i] + tmp[i]; qacc[i] = a; warm[i] = a; }
     WSYNC();
   }

@@ -6,6 +6,7 @@
 // mj_forward (:329,:621) and the two halves around the control hook (mjcb_control placement,
 // mujoco_env.h:242-246).  Pipeline order follows SURVEY.md Appendix A.
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "dev_model.h"
 #include "env_ctx.cuh"
@@ -21,8 +22,8 @@ namespace b2k {
 __device__ __forceinline__ bool isBad(double x) { return isnan(x) || x > B2MJ_MAXVAL || x < -B2MJ_MAXVAL; }
 
 // mj_resetData on the resident state of one env
-__device__ void resetEnv(const Env& e, int* warning, int which) {
-  const DevModel& m = e.m;
+__device__ void resetEnv(const Env e, int* warning, int which) {
+  const DevModel& m = c_dm;
   double* qpos = e.D(B2MJ_F_QPOS);
   FORL(i, m.nq) qpos[i] = m.qpos0[i];
   double* qvel = e.D(B2MJ_F_QVEL);
@@ -55,9 +56,9 @@ struct StepCtx {
   }
 
 // mj_forwardSkip split at the control hook
-__device__ void forwardPass(const Env& e, const LaunchArgs& a, int env, StepCtx& sc, bool skipsensor, bool first_half,
+__device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int env, StepCtx& sc, bool skipsensor, bool first_half,
                             bool second_half) {
-  const DevModel& m = e.m;
+  const DevModel& m = c_dm;
   int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
   const double* xfrc = (m.has_xfrc && a.xfrc) ? a.xfrc + (size_t)env * 6 * m.nbody : nullptr;
   if (first_half) {
@@ -89,8 +90,8 @@ __device__ void forwardPass(const Env& e, const LaunchArgs& a, int env, StepCtx&
 }
 
 // mj_RungeKutta(4)
-__device__ void stage_rk4(const Env& e, const LaunchArgs& a, int env, StepCtx& sc) {
-  const DevModel& m = e.m;
+__device__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
+  const DevModel& m = c_dm;
   const int nq = m.nq, nv = m.nv, na = m.na;
   const double h = m.opt.timestep;
   double* qpos = e.D(B2MJ_F_QPOS);
@@ -161,8 +162,9 @@ __device__ void stage_rk4(const Env& e, const LaunchArgs& a, int env, StepCtx& s
   advance_warp(e, dX + 2 * nv, dX + nv, dX);
 }
 
-__global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_constant__ DevModel m, const LaunchArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const LaunchArgs a) {
+  const DevModel& m = c_dm;
+  unsigned char* const smem_raw = b2k_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int env = blockIdx.x * nwarp + warp;
   if (env >= a.nenv) return;  // whole warp exits; no CTA-wide barrier is used below
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_
   int* si = reinterpret_cast<int*>(base + (size_t)m.arena_s_doubles * 8);
   double* gd = a.garena_d + (size_t)env * m.arena_g_doubles;
   int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
-  Env e{m, sd, si, gd, gi, lane};
+  Env e{(unsigned)(base - smem_raw), (unsigned)(base - smem_raw) + 8u * (unsigned)m.arena_s_doubles, gd, gi, lane};
   int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
   double* rec = a.rec + (size_t)env * m.rec_pitch;
 
@@ -290,18 +292,32 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const __grid_
 
 using namespace b2k;
 
+// host shadow of what c_dm currently holds (per device), so the constant is re-uploaded only when a
+// different handle / an edited model launches
+static DevModel g_shadow[16];
+static bool g_shadow_valid[16];
+
 extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps_per_cta, size_t smem_bytes,
                                cudaStream_t stream) {
-  static bool attr_set = false;
-  static size_t attr_bytes = 0;
-  if (!attr_set || smem_bytes > attr_bytes) {
+  static size_t attr_bytes[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (smem_bytes > attr_bytes[dev]) {
     cudaError_t err = cudaFuncSetAttribute(b2k_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return (int)err;
-    attr_set = true;
-    attr_bytes = smem_bytes;
+    attr_bytes[dev] = smem_bytes;
+  }
+  if (!g_shadow_valid[dev] || memcmp(&g_shadow[dev], m, sizeof(DevModel)) != 0) {
+    // kernels of another handle may still be reading the constant: drain the device first
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_dm, m, sizeof(DevModel));
+    if (err != cudaSuccess) return (int)err;
+    memcpy(&g_shadow[dev], m, sizeof(DevModel));
+    g_shadow_valid[dev] = true;
   }
   const int ctas = (a->nenv + warps_per_cta - 1) / warps_per_cta;
-  b2k_step_kernel<<<ctas, warps_per_cta * 32, smem_bytes, stream>>>(*m, *a);
+  b2k_step_kernel<<<ctas, warps_per_cta * 32, smem_bytes, stream>>>(*a);
   return (int)cudaGetLastError();
 }
 
