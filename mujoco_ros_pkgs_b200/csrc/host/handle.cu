@@ -214,10 +214,11 @@ static int check_supported(const b2mjModel* m) {
     const int t1 = m->geom_type[m->collpair_geom1[p]], t2 = m->geom_type[m->collpair_geom2[p]];
     const bool ok = (t1 == B2MJ_GEOM_PLANE && (t2 == B2MJ_GEOM_SPHERE || t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
                     (t1 == B2MJ_GEOM_SPHERE && (t2 == B2MJ_GEOM_SPHERE || t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
-                    (t1 == B2MJ_GEOM_CAPSULE && (t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX));
+                    (t1 == B2MJ_GEOM_CAPSULE && (t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
+                    (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX);
     if (!ok) {
       set_error("collision between geom types " + std::to_string(t1) + " and " + std::to_string(t2) +
-                " is not implemented in the CUDA narrowphase (cylinder/ellipsoid/box-box)");
+                " is not implemented in the CUDA narrowphase (cylinder / ellipsoid / mesh / hfield)");
       return B2MJ_EUNSUPPORTED;
     }
   }
@@ -300,6 +301,7 @@ static int make_layout(Handle* h) {
   xs[XF_QHW] = m->nM;
   xs[XF_DOFBUF] = 6 * nv;
   xs[XF_BODYBUF] = 6 * m->nbody;
+  xs[XF_PRIMAL] = pgs ? 0 : 8 * nv;
   xs[XF_EFC_AR] = pgs ? m->njmax * m->njmax : 0;
   xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * m->njmax, 400) : 0;
   // xfrc_applied / mocap live in their own HBM arrays (read only when the surface is enabled)

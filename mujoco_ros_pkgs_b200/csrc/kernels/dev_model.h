@@ -44,6 +44,7 @@ enum XField {
   XF_DOFBUF,        // 6*nv  crb * cdof per dof
   XF_BODYBUF,       // 6*nbody  per-body RNE force before the subtree sum
   XF_EFC_AR,        // njmax*njmax  dense AR = J inv(M) J' + R (PGS); always in the HBM/L2 arena
+  XF_PRIMAL,        // 8*nv  Newton / CG work vectors (Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
   XF_EFC_AR_S,      // shared-memory home of AR when nefc*nefc fits (the common case)
   XF_COUNT
 };

@@ -439,12 +439,15 @@ __device__ void mulJacTVec_warp(const Env e, int nefc, double* res, const double
 
 // mj_constraintUpdate: force / state / cost for jar = J qacc - aref; returns the constraint cost
 // (identical on all lanes).  Does NOT compute qfrc_constraint (callers do, when they need it).
-__device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const double* jar, bool coneHessian) {
+__device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const double* jar, bool coneHessian,
+                                        int* changed = nullptr) {
   const DevModel& m = c_dm;
   EfcPtrs P = efcPtrs(e);
   double s = 0;
+  int ch = 0;
   FORL(i, nefc) {
     const double D = P.D[i], R = P.R[i], x = jar[i];
+    const int oldstate = P.state[i];
     switch (P.type[i]) {
       case B2MJ_CNSTR_EQUALITY:
         P.force[i] = -D * x; P.state[i] = B2MJ_CSTATE_QUADRATIC; s += 0.5 * D * x * x;
@@ -462,6 +465,7 @@ __device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const d
         if (x >= 0) { P.force[i] = 0; P.state[i] = B2MJ_CSTATE_SATISFIED; }
         else { P.force[i] = -D * x; P.state[i] = B2MJ_CSTATE_QUADRATIC; s += 0.5 * D * x * x; }
     }
+    if (P.type[i] != B2MJ_CNSTR_CONTACT_ELLIPTIC) ch |= (P.state[i] != oldstate);
   }
   if (m.opt.cone == B2MJ_CONE_ELLIPTIC && ncon > 0) {
     const int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
@@ -516,6 +520,7 @@ __device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const d
     }
   }
   WSYNC();
+  if (changed) *changed = __any_sync(0xffffffffu, ch);
   return warpSum(s);
 }
 

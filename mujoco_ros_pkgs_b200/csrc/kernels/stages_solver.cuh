@@ -368,6 +368,356 @@ __device__ int solvePGS_free(const Env e, int nefc, double* avec) {
   return iter;
 }
 
+// ------------------------------------------------------------------------------------------------
+// primal solvers (mj_solNewton / mj_solCG), warp-cooperative
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void mulJacVec_warp(const Env e, int nefc, double* res, const double* vec) {
+  const int nv = c_dm.nv;
+  const double* J = e.DG(B2MJ_F_EFC_J);
+  FORL(i, nefc) {
+    double s = 0;
+    for (int k = 0; k < nv; k++) s += J[i * nv + k] * vec[k];
+    res[i] = s;
+  }
+  WSYNC();
+}
+
+__device__ __forceinline__ double dot_warp(const Env e, const double* a, const double* b, int n) {
+  double s = 0;
+  FORL(k, n) s += a[k] * b[k];
+  return warpSum(s);
+}
+
+// in-place dense Cholesky (lower) of the nv x nv Hessian; invd[j] = 1 / L[j][j]
+__device__ void cholFactor_warp(const Env e, double* A, double* invd, int n, double mindiag) {
+  for (int j = 0; j < n; j++) {
+    double s = A[j * n + j];
+    for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
+    if (s < mindiag) s = mindiag;
+    const double ljj = sqrt(s), inv = 1 / ljj;
+    for (int i = j + 1 + e.lane; i < n; i += 32) {
+      double t = A[i * n + j];
+      for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = t * inv;
+    }
+    WSYNC();
+    if (e.lane == 0) { A[j * n + j] = ljj; invd[j] = inv; }
+  }
+  WSYNC();
+}
+
+// x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+32, k+64, k+96
+#define B2K_CHOL_SLOTS 4
+__device__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n) {
+  double t[B2K_CHOL_SLOTS];
+#pragma unroll
+  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + 32 * s; t[s] = k < n ? b[k] : 0.0; }
+  for (int i = 0; i < n; i++) {  // L y = b
+    double ti = 0;
+#pragma unroll
+    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i >> 5) == s) ti = __shfl_sync(0xffffffffu, t[s], i & 31);
+    const double yi = ti * invd[i];
+#pragma unroll
+    for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
+      const int k = e.lane + 32 * s;
+      if (k == i) t[s] = yi;
+      else if (k > i && k < n) t[s] -= L[k * n + i] * yi;
+    }
+  }
+  for (int i = n - 1; i >= 0; i--) {  // L' x = y
+    double ti = 0;
+#pragma unroll
+    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i >> 5) == s) ti = __shfl_sync(0xffffffffu, t[s], i & 31);
+    const double xi = ti * invd[i];
+#pragma unroll
+    for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
+      const int k = e.lane + 32 * s;
+      if (k == i) t[s] = xi;
+      else if (k < i) t[s] -= L[i * n + k] * xi;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + 32 * s; if (k < n) x[k] = t[s]; }
+  WSYNC();
+}
+
+struct PrimalCtx {
+  int nv, nefc, ncon;
+  bool newton, cone;
+  double *Jaref, *Jv, *quad, *Ma, *Mv, *grad, *Mgrad, *search, *gradold, *Mgradold, *invd, *H;
+  double quadGauss[3];
+  double cost, gauss, scale;
+};
+
+struct LSPoint {
+  double alpha, cost, d0, d1;
+};
+
+// constraint update at the current qacc + Gauss term (primalUpdateConstraint)
+__device__ void primalUpdate(const Env e, PrimalCtx& c, int* changed) {
+  const double* qacc = e.D(B2MJ_F_QACC);
+  const double* qas = e.D(B2MJ_F_QACC_SMOOTH);
+  const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
+  c.cost = constraintUpdate_warp(e, c.nefc, c.ncon, c.Jaref, c.newton && c.cone, changed);
+  EfcPtrs P = efcPtrs(e);
+  mulJacTVec_warp(e, c.nefc, e.D(B2MJ_F_QFRC_CONSTRAINT), P.force);
+  double g = 0;
+  FORL(i, c.nv) g += (c.Ma[i] - qs[i]) * (qacc[i] - qas[i]);
+  c.gauss = 0.5 * warpSum(g);
+  c.cost += c.gauss;
+}
+
+// H = M + J' diag(D_active) J (+ cone blocks), then Cholesky
+__device__ void primalHessian(const Env e, PrimalCtx& c) {
+  const DevModel& m = c_dm;
+  const int nv = c.nv, nefc = c.nefc;
+  EfcPtrs P = efcPtrs(e);
+  const double* qM = e.D(B2MJ_F_QM);
+  double* H = c.H;
+  FORL(k, nv * nv) H[k] = 0;
+  WSYNC();
+  FORL(t, m.nM) {
+    const int i = m.M_row[t], j = m.M_col[t];
+    H[i * nv + j] = qM[t];
+    H[j * nv + i] = qM[t];
+  }
+  WSYNC();
+  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const double* cH = c.cone ? e.XG(XF_CONTACT_H) : nullptr;
+  // one lane per lower-triangle entry (i, j <= i)
+  for (int item = e.lane; item < nv * nv; item += 32) {
+    const int i = item / nv, j = item - i * nv;
+    if (j > i) continue;
+    double s = H[item];
+    for (int r = 0; r < nefc; r++) {
+      const int st = P.state[r];
+      if (st == B2MJ_CSTATE_QUADRATIC) {
+        s += P.D[r] * P.J[r * nv + i] * P.J[r * nv + j];
+      } else if (st == B2MJ_CSTATE_CONE) {
+        const int con = P.id[r], dim = c_dim[con];
+        const double* Hc = cH + 36 * con;
+        for (int a = 0; a < dim; a++) {
+          const double Ja = P.J[(r + a) * nv + i];
+          if (Ja == 0) continue;
+          double u = 0;
+          for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + j];
+          s += Ja * u;
+        }
+        r += dim - 1;
+      }
+    }
+    H[item] = s;
+  }
+  WSYNC();
+  cholFactor_warp(e, H, c.invd, nv, B2K_MINVAL);
+}
+
+__device__ void primalGradient(const Env e, PrimalCtx& c) {
+  const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
+  const double* qc = e.D(B2MJ_F_QFRC_CONSTRAINT);
+  FORL(i, c.nv) c.grad[i] = c.Ma[i] - qs[i] - qc[i];
+  WSYNC();
+  if (c.newton) {
+    cholSolve_warp(e, c.Mgrad, c.H, c.invd, c.grad, c.nv);
+  } else {
+    FORL(i, c.nv) c.Mgrad[i] = c.grad[i];
+    WSYNC();
+    solveW_warp(e, c.Mgrad, e.X(XF_QW), e.D(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
+  }
+}
+
+__device__ void primalPrepare(const Env e, PrimalCtx& c) {
+  EfcPtrs P = efcPtrs(e);
+  const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
+  mulM_warp(e, c.Mv, c.search);
+  mulJacVec_warp(e, c.nefc, c.Jv, c.search);
+  c.quadGauss[0] = c.gauss;
+  c.quadGauss[1] = dot_warp(e, c.search, c.Ma, c.nv) - dot_warp(e, qs, c.search, c.nv);
+  c.quadGauss[2] = 0.5 * dot_warp(e, c.search, c.Mv, c.nv);
+  FORL(i, c.nefc) {
+    const double D = P.D[i];
+    c.quad[3 * i] = 0.5 * D * c.Jaref[i] * c.Jaref[i];
+    c.quad[3 * i + 1] = D * c.Jaref[i] * c.Jv[i];
+    c.quad[3 * i + 2] = 0.5 * D * c.Jv[i] * c.Jv[i];
+  }
+  WSYNC();
+}
+
+__device__ LSPoint primalEval(const Env e, const PrimalCtx& c, double alpha) {
+  EfcPtrs P = efcPtrs(e);
+  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
+  const double* c_mu = e.D(B2MJ_F_CONTACT_MU);
+  const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
+  double q0 = 0, q1 = 0, q2 = 0, cost = 0, deriv0 = 0, deriv1 = 0;
+  FORL(i, c.nefc) {
+    const double x = c.Jaref[i] + alpha * c.Jv[i];
+    const double* qi = c.quad + 3 * i;
+    const int type = P.type[i];
+    if (type == B2MJ_CNSTR_EQUALITY) {
+      q0 += qi[0]; q1 += qi[1]; q2 += qi[2];
+    } else if (type == B2MJ_CNSTR_FRICTION_DOF || type == B2MJ_CNSTR_FRICTION_TENDON) {
+      const double f = P.floss[i], Rf = P.R[i] * f;
+      if (x <= -Rf) { q0 += f * (-0.5 * Rf - c.Jaref[i]); q1 += -f * c.Jv[i]; }
+      else if (x >= Rf) { q0 += f * (-0.5 * Rf + c.Jaref[i]); q1 += f * c.Jv[i]; }
+      else { q0 += qi[0]; q1 += qi[1]; q2 += qi[2]; }
+    } else if (type == B2MJ_CNSTR_CONTACT_ELLIPTIC) {
+      const int con = P.id[i];
+      if (c_adr[con] != i) continue;  // the contact's first row handles the whole cone
+      const int dim = c_dim[con];
+      const double mu = c_mu[con];
+      const double* fri = c_fri + 5 * con;
+      const double U0 = c.Jaref[i] * mu, V0 = c.Jv[i] * mu;
+      double UU = 0, UV = 0, VV = 0;
+      for (int j = 1; j < dim; j++) {
+        const double U = c.Jaref[i + j] * fri[j - 1], V = c.Jv[i + j] * fri[j - 1];
+        UU += U * U; UV += U * V; VV += V * V;
+      }
+      const double N = U0 + alpha * V0, Tsqr = UU + alpha * (2 * UV + alpha * VV);
+      bool bottom = false;
+      if (Tsqr <= 0) {
+        if (N < 0) bottom = true;
+      } else {
+        const double T = sqrt(Tsqr);
+        if (N >= mu * T) {
+        } else if (mu * N + T <= 0) {
+          bottom = true;
+        } else {
+          const double Dm = P.D[i] / (mu * mu * (1 + mu * mu));
+          const double N1 = V0, T1 = (UV + alpha * VV) / T, T2 = VV / T - (UV + alpha * VV) * T1 / (T * T);
+          const double NmT = N - mu * T;
+          cost += 0.5 * Dm * NmT * NmT;
+          deriv0 += Dm * NmT * (N1 - mu * T1);
+          deriv1 += Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NmT * (-mu * T2));
+        }
+      }
+      if (bottom)
+        for (int j = 0; j < dim; j++) { q0 += qi[3 * j]; q1 += qi[3 * j + 1]; q2 += qi[3 * j + 2]; }
+    } else {
+      if (x < 0) { q0 += qi[0]; q1 += qi[1]; q2 += qi[2]; }
+    }
+  }
+  q0 = warpSum(q0) + c.quadGauss[0];
+  q1 = warpSum(q1) + c.quadGauss[1];
+  q2 = warpSum(q2) + c.quadGauss[2];
+  cost = warpSum(cost);
+  deriv0 = warpSum(deriv0);
+  deriv1 = warpSum(deriv1);
+  LSPoint p;
+  p.alpha = alpha;
+  p.cost = cost + alpha * alpha * q2 + alpha * q1 + q0;
+  p.d0 = deriv0 + 2 * alpha * q2 + q1;
+  p.d1 = deriv1 + 2 * q2;
+  if (p.d1 < B2K_MINVAL) p.d1 = B2K_MINVAL;
+  return p;
+}
+
+// exact line search on the convex piecewise-quadratic restriction; returns the step (0 = no progress)
+__device__ double primalSearch(const Env e, PrimalCtx& c) {
+  const DevModel& m = c_dm;
+  const double snorm = sqrt(dot_warp(e, c.search, c.search, c.nv));
+  if (snorm < B2K_MINVAL) return 0;
+  const double gtol = m.opt.tolerance * m.opt.ls_tolerance * snorm / c.scale;
+  primalPrepare(e, c);
+  LSPoint p0 = primalEval(e, c, 0.0);
+  LSPoint p1 = primalEval(e, c, p0.alpha - p0.d0 / p0.d1);
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabs(p1.d0) < gtol) return p1.alpha;
+  const double dir = p1.d0 < 0 ? 1.0 : -1.0;
+  int iter = 0;
+  LSPoint p2 = p1;
+  while (p1.d0 * dir <= -gtol && iter < m.opt.ls_iterations) {
+    p2 = p1;
+    p1 = primalEval(e, c, p1.alpha - p1.d0 / p1.d1);
+    iter++;
+    if (fabs(p1.d0) < gtol) return p1.alpha;
+  }
+  if (iter >= m.opt.ls_iterations || p1.d0 * dir <= -gtol) return p1.cost < p0.cost ? p1.alpha : 0;
+  while (iter < m.opt.ls_iterations) {
+    const double lo = fmin(p1.alpha, p2.alpha), hi = fmax(p1.alpha, p2.alpha);
+    const double a1 = p1.alpha - p1.d0 / p1.d1, a2 = p2.alpha - p2.d0 / p2.d1;
+    double cand[3];
+    int nc = 0;
+    if (a1 > lo && a1 < hi) cand[nc++] = a1;
+    if (a2 > lo && a2 < hi) cand[nc++] = a2;
+    cand[nc++] = 0.5 * (lo + hi);
+    bool moved = false;
+    for (int k = 0; k < nc; k++) {
+      const LSPoint pc = primalEval(e, c, cand[k]);
+      if (fabs(pc.d0) < gtol) return pc.alpha;
+      if (pc.d0 * dir < 0) {
+        if (fabs(pc.alpha - p1.alpha) < fabs(p2.alpha - p1.alpha)) { p2 = pc; moved = true; }
+      } else {
+        if (fabs(pc.alpha - p2.alpha) < fabs(p1.alpha - p2.alpha)) { p1 = pc; moved = true; }
+      }
+    }
+    iter++;
+    if (!moved || fabs(p1.alpha - p2.alpha) < B2K_MINVAL) break;
+  }
+  const LSPoint best = p1.cost < p2.cost ? p1 : p2;
+  return best.cost < p0.cost ? best.alpha : 0;
+}
+
+// mj_solNewton / mj_solCG.  qacc holds the starting point.  Returns iterations used.
+__device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool newton) {
+  const DevModel& m = c_dm;
+  const int nv = m.nv;
+  PrimalCtx c;
+  c.nv = nv; c.nefc = nefc; c.ncon = ncon;
+  c.newton = newton;
+  c.cone = m.opt.cone == B2MJ_CONE_ELLIPTIC;
+  EfcPtrs P = efcPtrs(e);
+  double* w = e.X(XF_PRIMAL);
+  c.Ma = w; c.Mv = w + nv; c.grad = w + 2 * nv; c.Mgrad = w + 3 * nv; c.search = w + 4 * nv;
+  c.gradold = w + 5 * nv; c.Mgradold = w + 6 * nv; c.invd = w + 7 * nv;
+  c.Jaref = e.X(XF_EFC_JAREF); c.Jv = e.X(XF_EFC_JV); c.quad = e.XG(XF_EFC_QUAD);
+  c.H = newton ? e.XG(XF_NEWTON_H) : nullptr;
+  c.scale = 1 / (m.meaninertia * max(1, nv));
+  double* qacc = e.D(B2MJ_F_QACC);
+
+  mulM_warp(e, c.Ma, qacc);
+  mulJacVec_warp(e, nefc, c.Jaref, qacc);
+  FORL(i, nefc) c.Jaref[i] -= P.aref[i];
+  WSYNC();
+  primalUpdate(e, c, nullptr);
+  if (newton) primalHessian(e, c);
+  primalGradient(e, c);
+  FORL(i, nv) c.search[i] = -c.Mgrad[i];
+  WSYNC();
+  int iter = 0;
+  while (iter < m.opt.iterations) {
+    const double alpha = primalSearch(e, c);
+    if (alpha == 0) break;
+    FORL(i, nv) { qacc[i] += alpha * c.search[i]; c.Ma[i] += alpha * c.Mv[i]; }
+    FORL(i, nefc) c.Jaref[i] += alpha * c.Jv[i];
+    const double oldcost = c.cost;
+    FORL(i, nv) { c.gradold[i] = c.grad[i]; c.Mgradold[i] = c.Mgrad[i]; }
+    WSYNC();
+    int changed = 0;
+    primalUpdate(e, c, &changed);
+    if (newton && (c.cone || changed)) primalHessian(e, c);
+    primalGradient(e, c);
+    if (newton) {
+      FORL(i, nv) c.search[i] = -c.Mgrad[i];
+    } else {
+      double num = 0, den = 0;
+      FORL(i, nv) { num += c.grad[i] * (c.Mgrad[i] - c.Mgradold[i]); den += c.gradold[i] * c.Mgradold[i]; }
+      num = warpSum(num);
+      den = warpSum(den);
+      double beta = num / fmax(B2K_MINVAL, den);
+      if (beta < 0) beta = 0;
+      FORL(i, nv) c.search[i] = -c.Mgrad[i] + beta * c.search[i];
+    }
+    WSYNC();
+    const double improvement = c.scale * (oldcost - c.cost);
+    const double gradient = c.scale * sqrt(dot_warp(e, c.grad, c.grad, nv));
+    iter++;
+    if (improvement < m.opt.tolerance || gradient < m.opt.tolerance) break;
+  }
+  return iter;
+}
+
 // mj_fwdConstraint.  Returns solver iterations.
 __device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
   const DevModel& m = c_dm;
@@ -443,6 +793,31 @@ __device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
     WSYNC();
     solveW_warp(e, tmp, e.X(XF_QW), dinv, e.X(XF_VEC3));
     FORL(i, nv) { const double a = qas[i] + tmp[i]; qacc[i] = a; warm[i] = a; }
+    WSYNC();
+  } else {
+    const bool newton = m.opt.solver == B2MJ_SOL_NEWTON;
+    if (warmstart) {
+      // cost at the warm start vs at the unconstrained acceleration
+      double* jar = e.X(XF_EFC_JAREF);
+      double* Ma = e.X(XF_PRIMAL);
+      const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
+      mulJacVec_warp(e, nefc, jar, warm);
+      FORL(i, nefc) jar[i] -= P.aref[i];
+      WSYNC();
+      double cost_warm = constraintUpdate_warp(e, nefc, ncon, jar, false);
+      mulM_warp(e, Ma, warm);
+      double g = 0;
+      FORL(i, nv) g += (Ma[i] - qs[i]) * (warm[i] - qas[i]);
+      cost_warm += 0.5 * warpSum(g);
+      const double cost_smooth = constraintUpdate_warp(e, nefc, ncon, P.b, false);
+      if (cost_warm < cost_smooth) { FORL(i, nv) qacc[i] = warm[i]; }
+      else { FORL(i, nv) qacc[i] = qas[i]; }
+    } else {
+      FORL(i, nv) qacc[i] = qas[i];
+    }
+    WSYNC();
+    iters = solvePrimal(e, nefc, ncon, newton);
+    FORL(i, nv) warm[i] = qacc[i];
     WSYNC();
   }
   return iters;

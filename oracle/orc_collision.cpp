@@ -245,6 +245,149 @@ static int capsuleBox(Con* con, double margin, const double* pos1, const double*
 }
 
 // narrowphase dispatch; geoms already ordered so that type1 <= type2.  Returns -1 if unsupported.
+// box-box: separating-axis search over the 15 candidate axes, then either a face contact (incident
+// face clipped against the side planes of the reference face, up to 8 points) or a single edge-edge
+// contact.  A construction of our own, like the other box routines (MuJoCo's mjc_BoxBox is not
+// reproducible from memory; parity unpinned) — the CUDA narrowphase mirrors it step by step.
+static int boxBox(Con* con, double margin, const double* pos1, const double* mat1, const double* size1,
+                  const double* pos2, const double* mat2, const double* size2) {
+  double A[3][3], B[3][3], d[3], dA[3], dB[3], R[3][3], aR[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { A[i][k] = mat1[3 * k + i]; B[i][k] = mat2[3 * k + i]; }  // axes = matrix columns
+  sub3(d, pos2, pos1);
+  for (int i = 0; i < 3; i++) {
+    dA[i] = dot3(d, A[i]);
+    dB[i] = dot3(d, B[i]);
+    for (int j = 0; j < 3; j++) { R[i][j] = dot3(A[i], B[j]); aR[i][j] = std::fabs(R[i][j]) + 1e-12; }
+  }
+  double best = -1e30;
+  int code = -1;
+  for (int i = 0; i < 3; i++) {
+    const double s = std::fabs(dA[i]) - (size1[i] + size2[0] * aR[i][0] + size2[1] * aR[i][1] + size2[2] * aR[i][2]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = i; }
+  }
+  for (int j = 0; j < 3; j++) {
+    const double s = std::fabs(dB[j]) - (size2[j] + size1[0] * aR[0][j] + size1[1] * aR[1][j] + size1[2] * aR[2][j]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = 3 + j; }
+  }
+  double edgeN[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double L[3];
+      cross(L, A[i], B[j]);
+      const double l = norm3(L);
+      if (l < 1e-6) continue;
+      scl3(L, L, 1 / l);
+      double rA = 0, rB = 0;
+      for (int k = 0; k < 3; k++) {
+        if (k != i) rA += size1[k] * std::fabs(dot3(A[k], L));
+        if (k != j) rB += size2[k] * std::fabs(dot3(B[k], L));
+      }
+      const double dl = dot3(d, L);
+      const double s = std::fabs(dl) - (rA + rB);
+      if (s > margin) return 0;
+      if (s > best + 0.05 * std::fabs(best) + 1e-9) {
+        best = s;
+        code = 6 + 3 * i + j;
+        scl3(edgeN, L, dl < 0 ? -1.0 : 1.0);
+      }
+    }
+  if (code < 6) {
+    // face contact: reference box r (geom1 if code < 3), incident box c
+    const bool refA = code < 3;
+    const int r = refA ? code : code - 3;
+    const double (*Rf)[3] = refA ? A : B;
+    const double (*In)[3] = refA ? B : A;
+    const double* pr = refA ? pos1 : pos2;
+    const double* pi = refA ? pos2 : pos1;
+    const double* sr = refA ? size1 : size2;
+    const double* si = refA ? size2 : size1;
+    double n[3];
+    const double sgn = (refA ? dA[r] : -dB[r]) < 0 ? -1.0 : 1.0;
+    scl3(n, Rf[r], sgn);
+    int k = 0;
+    double bestdot = -1;
+    for (int q = 0; q < 3; q++) {
+      const double a = std::fabs(dot3(n, In[q]));
+      if (a > bestdot) { bestdot = a; k = q; }
+    }
+    const double fs = dot3(n, In[k]) > 0 ? -1.0 : 1.0;
+    const int ku = (k + 1) % 3, kv = (k + 2) % 3, ra = (r + 1) % 3, rb = (r + 2) % 3;
+    double poly[8][3], tmp[8][3];  // (x, y, h) in the reference-face frame
+    int np = 4;
+    const double su[4] = {1, -1, -1, 1}, sv[4] = {1, 1, -1, -1};
+    for (int v = 0; v < 4; v++) {
+      double w[3];
+      for (int c = 0; c < 3; c++)
+        w[c] = pi[c] + fs * si[k] * In[k][c] + su[v] * si[ku] * In[ku][c] + sv[v] * si[kv] * In[kv][c] - pr[c];
+      poly[v][0] = dot3(w, Rf[ra]);
+      poly[v][1] = dot3(w, Rf[rb]);
+      poly[v][2] = dot3(w, n) - sr[r];
+    }
+    for (int pl = 0; pl < 4; pl++) {  // clip against x <= sa, -x <= sa, y <= sb, -y <= sb
+      const int ax = pl >> 1;
+      const double sg = (pl & 1) ? -1.0 : 1.0, lim = ax == 0 ? sr[ra] : sr[rb];
+      int nq = 0;
+      for (int v = 0; v < np && nq < 8; v++) {
+        const double* p0 = poly[v];
+        const double* p1 = poly[(v + 1) % np];
+        const double e0 = sg * p0[ax] - lim, e1 = sg * p1[ax] - lim;
+        if (e0 <= 0) { for (int c = 0; c < 3; c++) tmp[nq][c] = p0[c]; nq++; }
+        if ((e0 < 0 && e1 > 0) || (e0 > 0 && e1 < 0)) {
+          if (nq < 8) {
+            const double t = e0 / (e0 - e1);
+            for (int c = 0; c < 3; c++) tmp[nq][c] = p0[c] + t * (p1[c] - p0[c]);
+            nq++;
+          }
+        }
+      }
+      np = nq;
+      for (int v = 0; v < np; v++) for (int c = 0; c < 3; c++) poly[v][c] = tmp[v][c];
+      if (np == 0) return 0;
+    }
+    int num = 0;
+    for (int v = 0; v < np && num < 8; v++) {
+      const double h = poly[v][2];
+      if (h >= margin) continue;
+      Con& cn = con[num++];
+      cn.dist = h;
+      for (int c = 0; c < 3; c++) {
+        cn.pos[c] = pr[c] + poly[v][0] * Rf[ra][c] + poly[v][1] * Rf[rb][c] + (sr[r] + 0.5 * h) * n[c];
+        cn.frame[c] = refA ? n[c] : -n[c];
+      }
+      for (int c = 3; c < 9; c++) cn.frame[c] = 0;
+    }
+    return num;
+  }
+  // edge-edge contact
+  const int i = (code - 6) / 3, j = (code - 6) % 3;
+  double pa[3], pb[3];
+  copy3(pa, pos1);
+  copy3(pb, pos2);
+  for (int k = 0; k < 3; k++) {
+    if (k != i) addToScl3(pa, A[k], (dot3(A[k], edgeN) > 0 ? 1.0 : -1.0) * size1[k]);
+    if (k != j) addToScl3(pb, B[k], (dot3(B[k], edgeN) > 0 ? -1.0 : 1.0) * size2[k]);
+  }
+  // closest points of the lines pa + al*A_i and pb + be*B_j
+  double w[3];
+  sub3(w, pb, pa);
+  const double uu = dot3(A[i], B[j]), wa = dot3(w, A[i]), wb = dot3(w, B[j]);
+  const double den = 1 - uu * uu;
+  double al = 0, be = 0;
+  if (den > 1e-12) { al = (wa - uu * wb) / den; be = (uu * wa - wb) / den; }
+  al = std::fmax(-size1[i], std::fmin(size1[i], al));
+  be = std::fmax(-size2[j], std::fmin(size2[j], be));
+  addToScl3(pa, A[i], al);
+  addToScl3(pb, B[j], be);
+  Con& cn = con[0];
+  cn.dist = best;
+  for (int c = 0; c < 3; c++) { cn.pos[c] = 0.5 * (pa[c] + pb[c]); cn.frame[c] = edgeN[c]; }
+  for (int c = 3; c < 9; c++) cn.frame[c] = 0;
+  return 1;
+}
+
 static int narrowphase(const b2mjModel* m, const OrcData* d, Con* con, int g1, int g2, double margin) {
   const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
   const double *pos1 = d->geom_xpos + 3 * g1, *mat1 = d->geom_xmat + 9 * g1, *size1 = m->geom_size + 3 * g1;
@@ -266,6 +409,7 @@ static int narrowphase(const b2mjModel* m, const OrcData* d, Con* con, int g1, i
     if (t2 == B2MJ_GEOM_BOX) return capsuleBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
     return -1;
   }
+  if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) return boxBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
   return -1;
 }
 

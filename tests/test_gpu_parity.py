@@ -53,7 +53,7 @@ def BatchSim():
     return B
 
 
-@pytest.mark.parametrize("name", ["panda_like.xml", "pendulum_scene.xml", "equality_scene.xml"])
+@pytest.mark.parametrize("name", ["panda_like.xml", "pendulum_scene.xml", "equality_scene.xml", "box_stack.xml"])
 def test_forward_fields_match_oracle(name, load_model, orc, capi, BatchSim):
     """Every mjData field after mj_forward, env by env (per-stage diff)."""
     model = load_model(name)
@@ -95,7 +95,8 @@ def test_forward_fields_match_oracle(name, load_model, orc, capi, BatchSim):
                 assert np.max(np.abs(gv - ov)) / scale < 1e-8 if ov.size else True, f"{name}:{fname} env {e}"
 
 
-@pytest.mark.parametrize("name,nsteps", [("panda_like.xml", 1000), ("pendulum_scene.xml", 300), ("equality_scene.xml", 300)])
+@pytest.mark.parametrize("name,nsteps", [("panda_like.xml", 1000), ("pendulum_scene.xml", 300), ("equality_scene.xml", 300),
+                                         ("box_stack.xml", 600)])
 def test_rollout_matches_oracle(name, nsteps, load_model, orc, BatchSim):
     """State divergence vs the oracle < 1e-5 per step and over the rollout; time bit-exact;
     contact-pair indices identical (checked at every 50th step)."""
@@ -140,7 +141,7 @@ def test_rollout_matches_oracle(name, nsteps, load_model, orc, BatchSim):
         np.testing.assert_array_equal(g2[e][:ncon[e]], o.get("contact_geom2")[:ncon[e]])
 
 
-@pytest.mark.parametrize("name", ["panda_like", "pendulum_scene", "equality_scene"])
+@pytest.mark.parametrize("name", ["panda_like", "pendulum_scene", "equality_scene", "box_stack"])
 def test_golden_trajectories(name, load_model, BatchSim):
     """Committed fixtures (tools/make_golden.py): same inputs in every env, same trajectory out."""
     g = np.load(os.path.join(GOLDEN, f"{name}.npz"))

@@ -276,7 +276,7 @@ def test_golden_trajectories(orc, load_model):
     """The oracle reproduces its own frozen trajectories (tests/golden/, tools/make_golden.py)."""
     import os
     from conftest import GOLDEN
-    for name in ("panda_like", "pendulum_scene", "equality_scene"):
+    for name in ("panda_like", "pendulum_scene", "equality_scene", "box_stack"):
         path = os.path.join(GOLDEN, f"{name}.npz")
         g = np.load(path)
         m = load_model(f"{name}.xml")
@@ -289,3 +289,15 @@ def test_golden_trajectories(orc, load_model):
             o.step(int(g["stride"]))
             np.testing.assert_allclose(o.get("qpos"), g["qpos"][k], rtol=1e-9, atol=1e-11)
             np.testing.assert_allclose(o.get("qvel"), g["qvel"][k], rtol=1e-8, atol=1e-10)
+
+
+def test_box_stack_rests(orc, load_model):
+    """box-box / plane-box face contacts: the slab rests on the table, the cube on the slab."""
+    m = load_model("box_stack.xml")
+    o = orc.Oracle(m)
+    o.step(2500)
+    q = o.get("qpos")
+    assert q[2] == pytest.approx(0.2 + 0.06, abs=2e-3)
+    assert q[9] == pytest.approx(0.2 + 0.12 + 0.05, abs=3e-3)
+    assert np.abs(o.get("qvel")).max() < 1e-3
+    assert o.get("ncon")[0] == 8

@@ -13,7 +13,7 @@ from oracle import binding as ob  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
-for name, nrec, stride in (("panda_like", 50, 10), ("pendulum_scene", 50, 10), ("equality_scene", 50, 10)):
+for name, nrec, stride in (("panda_like", 50, 10), ("pendulum_scene", 50, 10), ("equality_scene", 50, 10), ("box_stack", 60, 10)):
     m = _capi.Model.from_xml_file(os.path.join(ROOT, "mujoco_ros_pkgs_b200", "models", name + ".xml"))
     rng = np.random.default_rng(2024)
     qpos = m.qpos0.copy()
