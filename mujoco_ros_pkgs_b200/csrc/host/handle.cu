@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -198,6 +199,7 @@ static int upload_model(Handle* h) {
   d.meaninertia = m->stat.meaninertia;
   d.any_damping = 0;
   for (int i = 0; i < m->nv; i++) d.any_damping |= m->dof_damping[i] > 0;
+  d.dense_small = (m->nv > 0 && m->nv <= 16 && !getenv("B2MJ_NO_DENSE")) ? 1 : 0;
   d.need_rnepost = d.need_subtreevel = 0;
   for (int i = 0; i < m->nsensor; i++) {
     const int t = m->sensor_type[i];
@@ -301,9 +303,11 @@ static int make_layout(Handle* h) {
   xs[XF_QHW] = m->nM;
   xs[XF_DOFBUF] = 6 * nv;
   xs[XF_BODYBUF] = 6 * m->nbody;
+  xs[XF_MINV] = d.dense_small ? nv * nv : 0;
+  xs[XF_HINV] = (d.dense_small && d.any_damping && !rk4) ? nv * nv : 0;
   xs[XF_PRIMAL] = pgs ? 0 : 8 * nv;
-  xs[XF_EFC_AR] = pgs ? m->njmax * m->njmax : 0;
-  xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * m->njmax, 400) : 0;
+  xs[XF_EFC_AR] = pgs ? m->njmax * (m->njmax + 4) : 0;
+  xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * (m->njmax + 4), 384) : 0;  // nefc <= 17 stays on chip
   // xfrc_applied / mocap live in their own HBM arrays (read only when the surface is enabled)
   d.fsize[B2MJ_F_XFRC_APPLIED] = 0;
 
@@ -333,19 +337,28 @@ static int make_layout(Handle* h) {
     return ((dbl * 8 + ((ints + 1) & ~(size_t)1) * 4) + 15) & ~(size_t)15;
   };
   const size_t kSmPerSM = 228 * 1024, kCtaReserve = 1024, kMaxCta = 227 * 1024;
-  const size_t target = h->smem_target_bytes ? h->smem_target_bytes : 28 * 1024;  // ~8 envs per SM
-  struct Cand { int is_x, id; };
-  const Cand demote[] = {{1, XF_NEWTON_H}, {1, XF_EFC_MINVJT}, {0, B2MJ_F_EFC_J}, {1, XF_EFC_QUAD}, {1, XF_CONTACT_H},
-                         {0, B2MJ_F_CONTACT_FRAME}, {0, B2MJ_F_EFC_KBIP}, {0, B2MJ_F_CONTACT_SOLIMP},
-                         {0, B2MJ_F_CONTACT_FRICTION}, {0, B2MJ_F_CONTACT_POS}};
-  for (const Cand& c : demote) {
+  size_t target = h->smem_target_bytes ? h->smem_target_bytes : 16 * 1024;  // >= 14 envs per SM
+  if (const char* env = getenv("B2MJ_SMEM_TARGET_KB")) target = (size_t)atoi(env) * 1024;
+  // demotion candidates: everything sized by njmax / nconmax (the constraint / contact working set) plus
+  // the dense solver matrices, largest first.  The small AR window (XF_EFC_AR_S) and the per-env vectors
+  // always stay in shared memory.
+  struct Cand { int is_x, id; size_t bytes; };
+  std::vector<Cand> cands;
+  for (int f = 0; f < B2MJ_NFIELD; f++) {
+    const bool efc = f >= B2MJ_F_EFC_TYPE && f <= B2MJ_F_EFC_AR, con = f >= B2MJ_F_CONTACT_DIST && f <= B2MJ_F_CONTACT_EFC_ADDRESS;
+    if ((efc || con) && d.fsize[f]) cands.push_back({0, f, (size_t)d.fsize[f] * (d.fis_int[f] ? 4 : 8)});
+  }
+  for (int x : {XF_NEWTON_H, XF_EFC_MINVJT, XF_EFC_QUAD, XF_CONTACT_H, XF_EFC_ARDIAG, XF_EFC_JAREF, XF_EFC_JV})
+    if (xs[x]) cands.push_back({1, x, (size_t)xs[x] * 8});
+  std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.bytes > b.bytes; });
+  for (const Cand& c : cands) {
     if (smem_bytes_env() <= target) break;
     if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1;
   }
   if (smem_bytes_env() + 16 > kMaxCta - kCtaReserve) {
-    // last resort: everything except the record image goes global
-    for (int f = 0; f < B2MJ_NFIELD; f++) cold[f] = !is_record_field(f);
-    for (int i = 0; i < XF_COUNT; i++) xcold[i] = 1;
+    set_error("model does not fit the per-warp shared-memory arena (" + std::to_string(smem_bytes_env()) +
+              " bytes per env even with the constraint working set in HBM)");
+    return B2MJ_EUNSUPPORTED;
   }
   int sdo = d.rec_end, sio = 0;
   for (int f = 0; f < B2MJ_NFIELD; f++) d.off_s[f] = -1;
@@ -368,14 +381,16 @@ static int make_layout(Handle* h) {
   const size_t env_bytes = (((size_t)d.arena_s_doubles * 8 + (size_t)d.arena_s_ints * 4) + 15) & ~(size_t)15;
   // launch shape: warps per CTA maximising resident envs per SM
   int bestW = 1, bestEnv = 0;
-  const int tryW[] = {4, 8, 2, 1};
-  for (int W : tryW) {
-    if (h->force_warps_per_cta && W != h->force_warps_per_cta) continue;
+  // launch shape: as many resident envs per SM as shared memory and the 128-register build allow
+  // (16 warps per SM); among equals prefer the smallest CTA: a finished env frees its shared memory for
+  // the next one immediately instead of waiting for its CTA mates (measured, profiles/r1_sweeps.txt)
+  const int forceW = getenv("B2MJ_WARPS_PER_CTA") ? atoi(getenv("B2MJ_WARPS_PER_CTA")) : h->force_warps_per_cta;
+  for (int W = 1; W <= B2K_MAX_THREADS / 32; W++) {
+    if (forceW && W != forceW) continue;
     const size_t cta = (size_t)W * (env_bytes + 16);
     if (cta > kMaxCta) continue;
     int ctas = (int)(kSmPerSM / (cta + kCtaReserve));
-    ctas = std::min(ctas, 2048 / (W * 32));
-    ctas = std::min(ctas, 32);
+    ctas = std::min(ctas, 16 / W);
     const int envs = ctas * W;
     if (envs > bestEnv) { bestEnv = envs; bestW = W; }
   }
@@ -446,6 +461,7 @@ int handle_launch(Handle* h, int mode, int nsteps) {
   a.mode = mode;
   a.dump = h->keep_intermediates;
   a.prof = h->prof;
+  a.sync_stages = getenv("B2MJ_STAGE_SYNC") ? 1 : 0;  // measured: no gain on B200 (profiles/), off by default
   const int rc = b2k_launch_step(&h->dm, &a, h->warps_per_cta, h->smem_bytes, h->stream);
   if (rc != 0) {
     set_error(std::string("step kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));

@@ -44,6 +44,8 @@ enum XField {
   XF_DOFBUF,        // 6*nv  crb * cdof per dof
   XF_BODYBUF,       // 6*nbody  per-body RNE force before the subtree sum
   XF_EFC_AR,        // njmax*njmax  dense AR = J inv(M) J' + R (PGS); always in the HBM/L2 arena
+  XF_MINV,          // nv*nv  dense inv(qM) (small models: nv <= 16)
+  XF_HINV,          // nv*nv  dense inv(qM + h diag(damping))
   XF_PRIMAL,        // 8*nv  Newton / CG work vectors (Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
   XF_EFC_AR_S,      // shared-memory home of AR when nefc*nefc fits (the common case)
   XF_COUNT
@@ -96,6 +98,7 @@ struct DevModel {
   int need_rnepost;        // some sensor needs cacc / cfrc_int
   int need_subtreevel;
   int any_damping;         // Euler implicit damping active
+  int dense_small;         // nv <= 16: inertia handled as dense nv x nv matrices (explicit inverses, no index tables)
 };
 
 struct LaunchArgs {
@@ -110,6 +113,7 @@ struct LaunchArgs {
   int nsteps;
   int mode;                // 0 step, 1 forward only, 2 step_begin (to control hook), 3 step_end
   int dump;                // copy the shared arena to garena at the end
+  int sync_stages;         // CTA-wide lockstep at stage boundaries (instruction / constant cache locality)
   unsigned long long* prof; // [PROF_COUNT] per-stage SM-cycle totals over all envs, or null (b2mj_stage_profile)
 };
 

@@ -39,13 +39,19 @@ struct Env {
     const int o = c_dm.off_s[f];
     return o >= 0 ? sd() + o : gd + c_dm.off_g[f];
   }
+  __device__ __forceinline__ int* IG(int f) const {
+    const int o = c_dm.off_s[f];
+    return o >= 0 ? si() + o : gi + c_dm.off_g[f];
+  }
   __device__ __forceinline__ double* XG(int xf) const {
     const int o = c_dm.xoff_s[xf];
     return o >= 0 ? sd() + o : gd + c_dm.xoff_g[xf];
   }
 };
 
-#define FORL(i, n) for (int i = e.lane; i < (n); i += 32)
+// lane-strided loop; never unrolled: trip counts are 1-2 for the models this kernel targets and the
+// megakernel is instruction-cache bound, so code size matters more than loop overhead
+#define FORL(i, n) _Pragma("unroll 1") for (int i = e.lane; i < (n); i += 32)
 #define WSYNC() __syncwarp()
 
 // ---- TMA 1-D bulk copy + mbarrier wrappers (sm_90+/sm_100a PTX) ----

@@ -278,7 +278,7 @@ __device__ __forceinline__ double segmentBoxClosest(const double* c, const doubl
   return best_t;
 }
 
-__device__ int narrowphase(const double* gxpos, const double* gxmat, PairCon& o, int g1, int g2,
+__device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat, PairCon& o, int g1, int g2,
                            double margin) {
   const DevModel& m = c_dm;
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
@@ -393,7 +393,7 @@ __device__ int narrowphase(const double* gxpos, const double* gxmat, PairCon& o,
 }
 
 // mj_collision; returns ncon (also stored)
-__device__ int stage_collision(const Env e, int* warning) {
+__device__ __noinline__ int stage_collision(const Env e, int* warning) {
   const DevModel& m = c_dm;
   int* ncon_p = e.I(B2MJ_F_NCON);
   if ((m.opt.disableflags & (B2MJ_DSBL_CONSTRAINT | B2MJ_DSBL_CONTACT)) || m.nconmax == 0 || m.ncollpair == 0) {
@@ -403,19 +403,19 @@ __device__ int stage_collision(const Env e, int* warning) {
   }
   const double* gxpos = e.D(B2MJ_F_GEOM_XPOS);
   const double* gxmat = e.D(B2MJ_F_GEOM_XMAT);
-  double* c_dist = e.D(B2MJ_F_CONTACT_DIST);
+  double* c_dist = e.DG(B2MJ_F_CONTACT_DIST);
   double* c_pos = e.DG(B2MJ_F_CONTACT_POS);
   double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);
-  double* c_inc = e.D(B2MJ_F_CONTACT_INCLUDEMARGIN);
+  double* c_inc = e.DG(B2MJ_F_CONTACT_INCLUDEMARGIN);
   double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
-  double* c_solref = e.D(B2MJ_F_CONTACT_SOLREF);
+  double* c_solref = e.DG(B2MJ_F_CONTACT_SOLREF);
   double* c_solimp = e.DG(B2MJ_F_CONTACT_SOLIMP);
-  double* c_mu = e.D(B2MJ_F_CONTACT_MU);
-  int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
-  int* c_g1 = e.I(B2MJ_F_CONTACT_GEOM1);
-  int* c_g2 = e.I(B2MJ_F_CONTACT_GEOM2);
-  int* c_excl = e.I(B2MJ_F_CONTACT_EXCLUDE);
-  int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
+  double* c_mu = e.DG(B2MJ_F_CONTACT_MU);
+  int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+  int* c_g1 = e.IG(B2MJ_F_CONTACT_GEOM1);
+  int* c_g2 = e.IG(B2MJ_F_CONTACT_GEOM2);
+  int* c_excl = e.IG(B2MJ_F_CONTACT_EXCLUDE);
+  int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
   int carry = 0, overflow = 0;
   for (int base = 0; base < m.ncollpair; base += 32) {
     const int p = base + e.lane;

@@ -37,11 +37,11 @@ struct EfcPtrs {
 
 __device__ __forceinline__ EfcPtrs efcPtrs(const Env e) {
   EfcPtrs p;
-  p.J = e.DG(B2MJ_F_EFC_J); p.pos = e.D(B2MJ_F_EFC_POS); p.margin = e.D(B2MJ_F_EFC_MARGIN);
-  p.floss = e.D(B2MJ_F_EFC_FRICTIONLOSS); p.diag = e.D(B2MJ_F_EFC_DIAGAPPROX); p.KBIP = e.DG(B2MJ_F_EFC_KBIP);
-  p.D = e.D(B2MJ_F_EFC_D); p.R = e.D(B2MJ_F_EFC_R); p.vel = e.D(B2MJ_F_EFC_VEL); p.aref = e.D(B2MJ_F_EFC_AREF);
-  p.b = e.D(B2MJ_F_EFC_B); p.force = e.D(B2MJ_F_EFC_FORCE);
-  p.type = e.I(B2MJ_F_EFC_TYPE); p.id = e.I(B2MJ_F_EFC_ID); p.state = e.I(B2MJ_F_EFC_STATE);
+  p.J = e.DG(B2MJ_F_EFC_J); p.pos = e.DG(B2MJ_F_EFC_POS); p.margin = e.DG(B2MJ_F_EFC_MARGIN);
+  p.floss = e.DG(B2MJ_F_EFC_FRICTIONLOSS); p.diag = e.DG(B2MJ_F_EFC_DIAGAPPROX); p.KBIP = e.DG(B2MJ_F_EFC_KBIP);
+  p.D = e.DG(B2MJ_F_EFC_D); p.R = e.DG(B2MJ_F_EFC_R); p.vel = e.DG(B2MJ_F_EFC_VEL); p.aref = e.DG(B2MJ_F_EFC_AREF);
+  p.b = e.DG(B2MJ_F_EFC_B); p.force = e.DG(B2MJ_F_EFC_FORCE);
+  p.type = e.IG(B2MJ_F_EFC_TYPE); p.id = e.IG(B2MJ_F_EFC_ID); p.state = e.IG(B2MJ_F_EFC_STATE);
   return p;
 }
 
@@ -61,11 +61,11 @@ __device__ __forceinline__ double getImpedance(const double* solimp, double pos,
 }
 
 // mj_makeConstraint; returns nefc (also stored)
-__device__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
+__device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   int* nefc_p = e.I(B2MJ_F_NEFC);
-  int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
+  int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
   FORL(c, ncon) c_adr[c] = -1;
   if ((m.opt.disableflags & B2MJ_DSBL_CONSTRAINT) || m.njmax == 0 || nv == 0) {
     if (e.lane == 0) nefc_p[0] = 0;
@@ -260,12 +260,12 @@ __device__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
   // ---------------- contacts ----------------
   if (ncon > 0 && !(m.opt.disableflags & B2MJ_DSBL_CONTACT)) {
     const bool pyramid = m.opt.cone == B2MJ_CONE_PYRAMIDAL;
-    const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
-    const int* c_excl = e.I(B2MJ_F_CONTACT_EXCLUDE);
-    const int* c_g1 = e.I(B2MJ_F_CONTACT_GEOM1);
-    const int* c_g2 = e.I(B2MJ_F_CONTACT_GEOM2);
-    const double* c_dist = e.D(B2MJ_F_CONTACT_DIST);
-    const double* c_inc = e.D(B2MJ_F_CONTACT_INCLUDEMARGIN);
+    const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+    const int* c_excl = e.IG(B2MJ_F_CONTACT_EXCLUDE);
+    const int* c_g1 = e.IG(B2MJ_F_CONTACT_GEOM1);
+    const int* c_g2 = e.IG(B2MJ_F_CONTACT_GEOM2);
+    const double* c_dist = e.DG(B2MJ_F_CONTACT_DIST);
+    const double* c_inc = e.DG(B2MJ_F_CONTACT_INCLUDEMARGIN);
     const double* c_pos = e.DG(B2MJ_F_CONTACT_POS);
     const double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);
     const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
@@ -346,7 +346,7 @@ __device__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
 
   // ---------------- impedance: KBIP, R, D (mj_makeImpedance) ----------------
   const bool refsafe = !(m.opt.disableflags & B2MJ_DSBL_REFSAFE);
-  const double* c_solref = e.D(B2MJ_F_CONTACT_SOLREF);
+  const double* c_solref = e.DG(B2MJ_F_CONTACT_SOLREF);
   const double* c_solimp = e.DG(B2MJ_F_CONTACT_SOLIMP);
   FORL(i, nefc) {
     const int id = P.id[i], type = P.type[i];
@@ -381,9 +381,9 @@ __device__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
   }
   WSYNC();
   if (ncon > 0) {
-    const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+    const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
     const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
-    double* c_mu = e.D(B2MJ_F_CONTACT_MU);
+    double* c_mu = e.DG(B2MJ_F_CONTACT_MU);
     FORL(c, ncon) {
       const int adr = c_adr[c], dim = c_dim[c];
       if (adr < 0 || dim == 1) continue;
@@ -407,7 +407,7 @@ __device__ int stage_makeConstraint(const Env e, int ncon, int* warning) {
 }
 
 // mj_referenceConstraint: efc_vel = J qvel, aref = -B vel - K imp (pos - margin)
-__device__ void stage_referenceConstraint(const Env e, int nefc) {
+__device__ __noinline__ void stage_referenceConstraint(const Env e, int nefc) {
   if (!nefc) return;
   const DevModel& m = c_dm;
   const int nv = m.nv;
@@ -423,7 +423,7 @@ __device__ void stage_referenceConstraint(const Env e, int nefc) {
 }
 
 // res[k] = sum_i J[i][k] * f[i]   (J' f), one lane per dof
-__device__ void mulJacTVec_warp(const Env e, int nefc, double* res, const double* f) {
+__device__ __noinline__ void mulJacTVec_warp(const Env e, int nefc, double* res, const double* f) {
   const int nv = c_dm.nv;
   const double* J = e.DG(B2MJ_F_EFC_J);
   FORL(k, nv) {
@@ -439,7 +439,7 @@ __device__ void mulJacTVec_warp(const Env e, int nefc, double* res, const double
 
 // mj_constraintUpdate: force / state / cost for jar = J qacc - aref; returns the constraint cost
 // (identical on all lanes).  Does NOT compute qfrc_constraint (callers do, when they need it).
-__device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const double* jar, bool coneHessian,
+__device__ __noinline__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const double* jar, bool coneHessian,
                                         int* changed = nullptr) {
   const DevModel& m = c_dm;
   EfcPtrs P = efcPtrs(e);
@@ -468,9 +468,9 @@ __device__ double constraintUpdate_warp(const Env e, int nefc, int ncon, const d
     if (P.type[i] != B2MJ_CNSTR_CONTACT_ELLIPTIC) ch |= (P.state[i] != oldstate);
   }
   if (m.opt.cone == B2MJ_CONE_ELLIPTIC && ncon > 0) {
-    const int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
-    const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
-    const double* c_mu = e.D(B2MJ_F_CONTACT_MU);
+    const int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
+    const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+    const double* c_mu = e.DG(B2MJ_F_CONTACT_MU);
     const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
     double* cH = e.XG(XF_CONTACT_H);
     FORL(c, ncon) {

@@ -71,14 +71,14 @@ __device__ __forceinline__ void objAcceleration(const Env e, int type, int id, d
 }
 
 __device__ __forceinline__ int findLimitRow(const Env e, int nefc, int want, int id) {
-  const int* type = e.I(B2MJ_F_EFC_TYPE);
-  const int* eid = e.I(B2MJ_F_EFC_ID);
+  const int* type = e.IG(B2MJ_F_EFC_TYPE);
+  const int* eid = e.IG(B2MJ_F_EFC_ID);
   for (int r = 0; r < nefc; r++)
     if (type[r] == want && eid[r] == id) return r;
   return -1;
 }
 
-__device__ void stage_sensorPos(const Env e, int nefc) {
+__device__ __noinline__ void stage_sensorPos(const Env e, int nefc) {
   const DevModel& m = c_dm;
   if (!m.nsensor || (m.opt.disableflags & B2MJ_DSBL_SENSOR)) return;
   double* sd = e.D(B2MJ_F_SENSORDATA);
@@ -96,7 +96,7 @@ __device__ void stage_sensorPos(const Env e, int nefc) {
       case B2MJ_SENS_JOINTLIMITPOS:
       case B2MJ_SENS_TENDONLIMITPOS: {
         const int r = findLimitRow(e, nefc, type == B2MJ_SENS_JOINTLIMITPOS ? B2MJ_CNSTR_LIMIT_JOINT : B2MJ_CNSTR_LIMIT_TENDON, objid);
-        out[0] = r < 0 ? 0.0 : e.D(B2MJ_F_EFC_POS)[r] - e.D(B2MJ_F_EFC_MARGIN)[r];
+        out[0] = r < 0 ? 0.0 : e.DG(B2MJ_F_EFC_POS)[r] - e.DG(B2MJ_F_EFC_MARGIN)[r];
         break;
       }
       case B2MJ_SENS_FRAMEPOS:
@@ -134,7 +134,7 @@ __device__ void stage_sensorPos(const Env e, int nefc) {
 }
 
 // mj_subtreeVel (serial over bodies on lane 0; only runs when a subtree sensor exists)
-__device__ void subtreeVel_lane0(const Env e) {
+__device__ __noinline__ void subtreeVel_lane0(const Env e) {
   const DevModel& m = c_dm;
   if (e.lane == 0) {
     double* linvel = e.X(XF_SUBTREE_LINVEL);
@@ -175,7 +175,7 @@ __device__ void subtreeVel_lane0(const Env e) {
   WSYNC();
 }
 
-__device__ void stage_sensorVel(const Env e, int nefc) {
+__device__ __noinline__ void stage_sensorVel(const Env e, int nefc) {
   const DevModel& m = c_dm;
   if (!m.nsensor || (m.opt.disableflags & B2MJ_DSBL_SENSOR)) return;
   if (m.need_subtreevel) subtreeVel_lane0(e);
@@ -196,7 +196,7 @@ __device__ void stage_sensorVel(const Env e, int nefc) {
       case B2MJ_SENS_JOINTLIMITVEL:
       case B2MJ_SENS_TENDONLIMITVEL: {
         const int r = findLimitRow(e, nefc, type == B2MJ_SENS_JOINTLIMITVEL ? B2MJ_CNSTR_LIMIT_JOINT : B2MJ_CNSTR_LIMIT_TENDON, objid);
-        out[0] = r < 0 ? 0.0 : e.D(B2MJ_F_EFC_VEL)[r];
+        out[0] = r < 0 ? 0.0 : e.DG(B2MJ_F_EFC_VEL)[r];
         break;
       }
       case B2MJ_SENS_FRAMELINVEL:
@@ -235,12 +235,12 @@ __device__ void stage_sensorVel(const Env e, int nefc) {
 
 // local contact force [normal, tangents..., torques...] of contact c
 __device__ __forceinline__ void contactForce(const Env e, int c, double* lfrc) {
-  const int adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS)[c];
-  const int dim = e.I(B2MJ_F_CONTACT_DIM)[c];
-  const double* f = e.D(B2MJ_F_EFC_FORCE);
+  const int adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS)[c];
+  const int dim = e.IG(B2MJ_F_CONTACT_DIM)[c];
+  const double* f = e.DG(B2MJ_F_EFC_FORCE);
   for (int k = 0; k < 6; k++) lfrc[k] = 0;
   if (adr < 0) return;
-  if (e.I(B2MJ_F_EFC_TYPE)[adr] == B2MJ_CNSTR_CONTACT_PYRAMIDAL) {
+  if (e.IG(B2MJ_F_EFC_TYPE)[adr] == B2MJ_CNSTR_CONTACT_PYRAMIDAL) {
     const double* mu = e.DG(B2MJ_F_CONTACT_FRICTION) + 5 * c;
     for (int k = 0; k < 2 * (dim - 1); k++) lfrc[0] += f[adr + k];
     for (int k = 1; k < dim; k++) lfrc[k] = (f[adr + 2 * (k - 1)] - f[adr + 2 * (k - 1) + 1]) * mu[k - 1];
@@ -250,7 +250,7 @@ __device__ __forceinline__ void contactForce(const Env e, int c, double* lfrc) {
 }
 
 // mj_rnePostConstraint: cacc, cfrc_int, cfrc_ext
-__device__ void stage_rnePost(const Env e, int ncon, const double* xfrc) {
+__device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* xfrc) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
@@ -274,9 +274,9 @@ __device__ void stage_rnePost(const Env e, int ncon, const double* xfrc) {
           for (int k = 0; k < 6; k++) acc[k] += f[k];
         }
       }
-      const int* g1 = e.I(B2MJ_F_CONTACT_GEOM1);
-      const int* g2 = e.I(B2MJ_F_CONTACT_GEOM2);
-      const int* cadr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
+      const int* g1 = e.IG(B2MJ_F_CONTACT_GEOM1);
+      const int* g2 = e.IG(B2MJ_F_CONTACT_GEOM2);
+      const int* cadr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
       for (int c = 0; c < ncon; c++) {
         if (cadr[c] < 0) continue;
         const int b1 = m.geom_bodyid[g1[c]], b2 = m.geom_bodyid[g2[c]];
@@ -348,7 +348,7 @@ __device__ __forceinline__ bool pointInSite(const Env e, int site, const double*
   }
 }
 
-__device__ void stage_sensorAcc(const Env e, int nefc, int ncon, const double* xfrc) {
+__device__ __noinline__ void stage_sensorAcc(const Env e, int nefc, int ncon, const double* xfrc) {
   const DevModel& m = c_dm;
   if (!m.nsensor || (m.opt.disableflags & B2MJ_DSBL_SENSOR)) return;
   if (m.need_rnepost) stage_rnePost(e, ncon, xfrc);
@@ -362,10 +362,10 @@ __device__ void stage_sensorAcc(const Env e, int nefc, int ncon, const double* x
       case B2MJ_SENS_TOUCH: {
         double s = 0;
         const int body = m.site_bodyid[objid];
-        const int* g1 = e.I(B2MJ_F_CONTACT_GEOM1);
-        const int* g2 = e.I(B2MJ_F_CONTACT_GEOM2);
+        const int* g1 = e.IG(B2MJ_F_CONTACT_GEOM1);
+        const int* g2 = e.IG(B2MJ_F_CONTACT_GEOM2);
         for (int c = 0; c < ncon; c++) {
-          if (e.I(B2MJ_F_CONTACT_EFC_ADDRESS)[c] < 0) continue;
+          if (e.IG(B2MJ_F_CONTACT_EFC_ADDRESS)[c] < 0) continue;
           const int b1 = m.geom_bodyid[g1[c]], b2 = m.geom_bodyid[g2[c]];
           if (b1 != body && b2 != body) continue;
           double lfrc[6];
@@ -394,7 +394,7 @@ __device__ void stage_sensorAcc(const Env e, int nefc, int ncon, const double* x
       case B2MJ_SENS_JOINTLIMITFRC:
       case B2MJ_SENS_TENDONLIMITFRC: {
         const int r = findLimitRow(e, nefc, type == B2MJ_SENS_JOINTLIMITFRC ? B2MJ_CNSTR_LIMIT_JOINT : B2MJ_CNSTR_LIMIT_TENDON, objid);
-        out[0] = r < 0 ? 0.0 : e.D(B2MJ_F_EFC_FORCE)[r];
+        out[0] = r < 0 ? 0.0 : e.DG(B2MJ_F_EFC_FORCE)[r];
         break;
       }
       case B2MJ_SENS_FRAMELINACC:

@@ -37,7 +37,7 @@ B2K_DI void rotQ(double* r, const double* v, const double* q) {
 // mj_kinematics.  The tree recursion is replaced by (A) body-local transforms for all bodies at once,
 // (B) a pointer-jumping scan that composes them along the ancestor chains in ceil(log2(depth)) rounds,
 // (C) one parallel pass for matrices, inertial / joint / geom / site frames.
-__device__ void stage_kinematics(const Env e) {
+__device__ __noinline__ void stage_kinematics(const Env e) {
   const DevModel& m = c_dm;
   double* qpos = e.D(B2MJ_F_QPOS);
   double* xpos = e.D(B2MJ_F_XPOS);
@@ -181,7 +181,7 @@ __device__ void stage_kinematics(const Env e) {
 }
 
 // mj_comPos: subtree sums are gathers over the subtree bit masks (one lane per body)
-__device__ void stage_comPos(const Env e) {
+__device__ __noinline__ void stage_comPos(const Env e) {
   const DevModel& m = c_dm;
   const double* xipos = e.D(B2MJ_F_XIPOS);
   const double* ximat = e.D(B2MJ_F_XIMAT);
@@ -244,7 +244,7 @@ __device__ void stage_comPos(const Env e) {
 }
 
 // mj_tendon (fixed) + mj_transmission
-__device__ void stage_tendon_transmission(const Env e) {
+__device__ __noinline__ void stage_tendon_transmission(const Env e) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* qpos = e.D(B2MJ_F_QPOS);
@@ -291,7 +291,7 @@ __device__ void stage_tendon_transmission(const Env e) {
 // In-place sparse L'DL factorisation (mj_factorI) of up to two matrices with the same sparsity at once:
 // lanes 0-15 factor A, lanes 16-31 factor B (B = null: all 32 lanes on A).  Per pivot k the rank-1
 // update of the ancestor rows runs one lane per (ancestor row, column) pair.
-__device__ void factorLD2(const Env e, double* A, double* Bm, double* dinvA, double* sqrtinvA, double* dinvB) {
+__device__ __noinline__ void factorLD2(const Env e, double* A, double* Bm, double* dinvA, double* sqrtinvA, double* dinvB) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   const int half = Bm ? (e.lane >> 4) : 0, sub = Bm ? (e.lane & 15) : e.lane, stride = Bm ? 16 : 32;
@@ -323,7 +323,7 @@ __device__ void factorLD2(const Env e, double* A, double* Bm, double* dinvA, dou
 // W = inv(L) (unit lower triangular, same tree sparsity as L) for up to two factorisations at once.
 // Off-diagonals only, stored in the sparse layout of qM.  Rows depend on the rows of their ancestors,
 // so dofs are processed by depth level, one lane per (dof, ancestor) entry.
-__device__ void invL2(const Env e, const double* LA, double* WA, const double* LB, double* WB) {
+__device__ __noinline__ void invL2(const Env e, const double* LA, double* WA, const double* LB, double* WB) {
   const DevModel& m = c_dm;
   const int half = LB ? (e.lane >> 4) : 0, sub = LB ? (e.lane & 15) : e.lane, stride = LB ? 16 : 32;
   const double* LD = half ? LB : LA;
@@ -352,7 +352,7 @@ __device__ __forceinline__ void mulWT(const Env e, double* y, const double* W, c
 }
 
 // x <- inv(L'DL) x = W diag(dinv) W' x for one right-hand side, whole warp; tmp: nv scratch
-__device__ void solveW_warp(const Env e, double* x, const double* W, const double* dinv, double* tmp) {
+__device__ __noinline__ void solveW_warp(const Env e, double* x, const double* W, const double* dinv, double* tmp) {
   const DevModel& m = c_dm;
   FORL(k, m.nv) {
     double s = x[k];
@@ -389,7 +389,7 @@ __device__ __forceinline__ void solveLD_lane(double* x, const double* LD, const 
 }
 
 // res = M * vec: one lane per output row; row part over ancestors, column part over descendants
-__device__ void mulM_warp(const Env e, double* res, const double* vec) {
+__device__ __noinline__ void mulM_warp(const Env e, double* res, const double* vec) {
   const DevModel& m = c_dm;
   const double* qM = e.D(B2MJ_F_QM);
   FORL(i, m.nv) {
@@ -402,8 +402,43 @@ __device__ void mulM_warp(const Env e, double* res, const double* vec) {
   WSYNC();
 }
 
+// ---- dense small-model path (nv <= 16) ----------------------------------------------------------
+// In-place Gauss-Jordan inversion of up to two SPD nv x nv matrices at once (lanes 0..nv-1 own the rows
+// of A, lanes 16..16+nv-1 the rows of B): no index tables, no factor / triangular-solve chain; every
+// later solve is one dense mat-vec.
+__device__ __noinline__ void invertSPD2(const Env e, double* A, double* Bm, int n) {
+  const int half = e.lane >> 4, i = e.lane & 15;
+  double* Mx = half ? Bm : A;
+  const bool own = i < n && Mx != nullptr;
+  for (int k = 0; k < n; k++) {
+    if (own && i != k) {
+      const double p = 1.0 / Mx[k * n + k];
+      const double f = Mx[i * n + k] * p;
+      for (int j = 0; j < n; j++) Mx[i * n + j] -= f * Mx[k * n + j];
+      Mx[i * n + k] = -f;
+    }
+    WSYNC();
+    if (own && i == k) {
+      const double p = 1.0 / Mx[k * n + k];
+      for (int j = 0; j < n; j++) Mx[k * n + j] *= p;
+      Mx[k * n + k] = p;
+    }
+    WSYNC();
+  }
+}
+
+// out = Ainv * in for a dense nv x nv matrix (out != in)
+__device__ __forceinline__ void mulDense_warp(const Env e, double* out, const double* Ainv, const double* in, int n) {
+  FORL(i, n) {
+    double s = 0;
+    for (int j = 0; j < n; j++) s += Ainv[i * n + j] * in[j];
+    out[i] = s;
+  }
+  WSYNC();
+}
+
 // mj_crb + mj_factorM, plus the Euler-damping matrix qH = qM + h diag(damping) factored alongside
-__device__ void stage_crb_factor(const Env e) {
+__device__ __noinline__ void stage_crb_factor(const Env e, bool want_ld) {
   const DevModel& m = c_dm;
   const double* cinert = e.D(B2MJ_F_CINERT);
   const double* cdof = e.D(B2MJ_F_CDOF);
@@ -435,8 +470,48 @@ __device__ void stage_crb_factor(const Env e) {
     if (qH) qH[t] = hv;
   }
   WSYNC();
+  if (m.dense_small) {
+    // dense inverses; the sparse L'DL factor is only produced when someone will read it (arena dump)
+    const int nv = m.nv;
+    double* Minv = e.X(XF_MINV);
+    double* Hinv = qH ? e.X(XF_HINV) : nullptr;
+    FORL(t, m.nM) {
+      const int i = m.M_row[t], j = m.M_col[t];
+      const double v = qM[t];
+      Minv[i * nv + j] = v;
+      Minv[j * nv + i] = v;
+      if (Hinv) { const double hv = qH[t]; Hinv[i * nv + j] = hv; Hinv[j * nv + i] = hv; }
+    }
+    WSYNC();
+    // entries between dofs of different branches are structural zeros of M
+    FORL(item, nv * nv) {
+      const int i = item / nv, j = item - i * nv;
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      const unsigned* mask = m.body_dofmask + m.dof_bodyid[hi] * m.nmaskword;
+      if (!((mask[lo >> 5] >> (lo & 31)) & 1u)) { Minv[item] = 0; if (Hinv) Hinv[item] = 0; }
+    }
+    WSYNC();
+    invertSPD2(e, Minv, Hinv, nv);
+    if (!want_ld) return;
+  }
   factorLD2(e, qLD, qH, e.D(B2MJ_F_QLDIAGINV), e.D(B2MJ_F_QLDIAGSQRTINV), qH ? e.X(XF_QHDIAGINV) : nullptr);
   invL2(e, qLD, e.X(XF_QW), qH, qH ? e.X(XF_QHW) : nullptr);
+}
+
+// out = inv(M) in  /  out = inv(M + h diag(damping)) in   (out != in)
+__device__ __forceinline__ void solveM_warp(const Env e, double* out, const double* in) {
+  const DevModel& m = c_dm;
+  if (m.dense_small) { mulDense_warp(e, out, e.X(XF_MINV), in, m.nv); return; }
+  FORL(i, m.nv) out[i] = in[i];
+  WSYNC();
+  solveW_warp(e, out, e.X(XF_QW), e.D(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
+}
+__device__ __forceinline__ void solveH_warp(const Env e, double* out, const double* in) {
+  const DevModel& m = c_dm;
+  if (m.dense_small) { mulDense_warp(e, out, e.X(XF_HINV), in, m.nv); return; }
+  FORL(i, m.nv) out[i] = in[i];
+  WSYNC();
+  solveW_warp(e, out, e.X(XF_QHW), e.X(XF_QHDIAGINV), e.X(XF_VEC0));
 }
 
 __device__ __forceinline__ void mulDofVec(double* res, const double* dof, const double* vec, int n) {
@@ -447,7 +522,7 @@ __device__ __forceinline__ void mulDofVec(double* res, const double* dof, const 
 
 // mj_comVel: cvel of a body is the sum of cdof*qvel over the dofs of its chain (all cdof share the
 // subtree-com frame), so every body / dof is computed independently from the chain bit masks.
-__device__ void stage_comVel(const Env e) {
+__device__ __noinline__ void stage_comVel(const Env e) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* qvel = e.D(B2MJ_F_QVEL);
@@ -475,7 +550,7 @@ __device__ void stage_comVel(const Env e) {
 
 // Jacobian-transpose application of a force/torque at a point of a body: one lane per dof.
 // qfrc[k] += jacp[:,k].force + jacr[:,k].torque for dofs on the body's chain.
-__device__ void applyFT_warp(const Env e, const double* force, const double* torque, const double* point, int body,
+__device__ __noinline__ void applyFT_warp(const Env e, const double* force, const double* torque, const double* point, int body,
                              double* qfrc) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
@@ -496,7 +571,7 @@ __device__ void applyFT_warp(const Env e, const double* force, const double* tor
 }
 
 // mj_passive (springs, dampers, gravity compensation); the host passive hook is a split-step feature
-__device__ void stage_passive(const Env e) {
+__device__ __noinline__ void stage_passive(const Env e) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* qpos = e.D(B2MJ_F_QPOS);
@@ -560,7 +635,7 @@ __device__ void stage_passive(const Env e) {
 // mj_rne(flg_acc = 0): bias forces, without the tree recursions: cacc of a body is the sum of
 // cdof_dot*qvel over its chain, the backward force accumulation is folded into the projection
 // bias[k] = cdof[k] . sum_{i in subtree(body(k))} f_i.
-__device__ void stage_rne_bias(const Env e) {
+__device__ __noinline__ void stage_rne_bias(const Env e) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
@@ -596,7 +671,7 @@ __device__ void stage_rne_bias(const Env e) {
 }
 
 // tendon / actuator velocities (head of mj_fwdVelocity)
-__device__ void stage_velocity_head(const Env e) {
+__device__ __noinline__ void stage_velocity_head(const Env e) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* qvel = e.D(B2MJ_F_QVEL);
@@ -622,7 +697,7 @@ __device__ void stage_velocity_head(const Env e) {
 }
 
 // mj_fwdActuation
-__device__ void stage_actuation(const Env e, int* warning) {
+__device__ __noinline__ void stage_actuation(const Env e, int* warning) {
   const DevModel& m = c_dm;
   const int nv = m.nv, nu = m.nu;
   double* qa = e.D(B2MJ_F_QFRC_ACTUATOR);
@@ -679,7 +754,7 @@ __device__ void stage_actuation(const Env e, int* warning) {
 }
 
 // mj_fwdAcceleration
-__device__ void stage_acceleration(const Env e, const double* xfrc) {
+__device__ __noinline__ void stage_acceleration(const Env e, const double* xfrc) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
@@ -703,9 +778,7 @@ __device__ void stage_acceleration(const Env e, const double* xfrc) {
       applyFT_warp(e, x, x + 3, xipos + 3 * i, i, qs);
     }
   }
-  FORL(i, nv) qas[i] = qs[i];
-  WSYNC();
-  solveW_warp(e, qas, e.X(XF_QW), e.D(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
+  solveM_warp(e, qas, qs);
 }
 
 // mj_integratePos for the joints handled by this lane
@@ -747,7 +820,7 @@ __device__ void advance_warp(const Env e, const double* act_dot, const double* q
 }
 
 // mj_Euler: semi-implicit Euler, implicit in joint damping
-__device__ void stage_euler(const Env e) {
+__device__ __noinline__ void stage_euler(const Env e) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* act_dot = m.na ? e.D(B2MJ_F_ACT_DOT) : nullptr;
@@ -755,13 +828,14 @@ __device__ void stage_euler(const Env e) {
     advance_warp(e, act_dot, e.D(B2MJ_F_QACC), nullptr);
     return;
   }
-  double* acc = e.X(XF_VEC0);
+  double* rhs = e.X(XF_VEC1);
+  double* acc = e.X(XF_VEC2);
   const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
   const double* qc = e.D(B2MJ_F_QFRC_CONSTRAINT);
-  FORL(i, nv) acc[i] = qs[i] + qc[i];
+  FORL(i, nv) rhs[i] = qs[i] + qc[i];
   WSYNC();
-  // qH = qM + h diag(damping) was factored (and inverted) next to qM in stage_crb_factor
-  solveW_warp(e, acc, e.X(XF_QHW), e.X(XF_QHDIAGINV), e.X(XF_VEC1));
+  // qH = qM + h diag(damping) was factored / inverted next to qM in stage_crb_factor
+  solveH_warp(e, acc, rhs);
   advance_warp(e, act_dot, acc, nullptr);
 }
 

@@ -10,6 +10,8 @@
 // FMA per lane to push the force change into the residuals -- no per-row reductions.  Same sweep order,
 // projections and cost guard as mj_solPGS.  Rows beyond 64 fall back to the matrix-free form.
 #pragma once
+#include <math_constants.h>
+
 #include "env_ctx.cuh"
 #include "stages_constraint.cuh"
 #include "stages_smooth.cuh"
@@ -20,28 +22,41 @@ namespace b2k {
 
 // AR lives in shared memory when it fits the small buffer, else in the env's HBM/L2 arena
 __device__ __forceinline__ double* arPtr(const Env e, int nefc) {
-  return nefc * nefc <= c_dm.xsize[XF_EFC_AR_S] ? e.X(XF_EFC_AR_S) : e.XG(XF_EFC_AR);
+  return nefc * nefc <= c_dm.xsize[XF_EFC_AR_S] ? e.XG(XF_EFC_AR_S) : e.XG(XF_EFC_AR);
 }
 
 // G = J W (rows of J pushed through inv(L)) and AR = G diag(1/D) G' + R
-__device__ void stage_projectConstraint(const Env e, int nefc) {
+__device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
   if (!nefc) return;
   const DevModel& m = c_dm;
   const int nv = m.nv;
   const double* J = e.DG(B2MJ_F_EFC_J);
-  const double* R = e.D(B2MJ_F_EFC_R);
+  const double* R = e.DG(B2MJ_F_EFC_R);
   const double* W = e.X(XF_QW);
   const double* dinv = e.D(B2MJ_F_QLDIAGINV);
   double* G = e.XG(XF_EFC_MINVJT);
-  FORL(item, nefc * nv) {
-    const int i = item / nv, k = item - i * nv;
-    const double* Ji = J + i * nv;
-    double s = Ji[k];
-    for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * Ji[m.dof_desc_dof[p]];
-    G[item] = s;
+  const bool dense = m.dense_small;
+  if (dense) {
+    // G = J inv(M) (dense), AR = G J' + R
+    const double* Minv = e.X(XF_MINV);
+    FORL(item, nefc * nv) {
+      const int i = item / nv, k = item - i * nv;
+      const double* Ji = J + i * nv;
+      double s = 0;
+      for (int j = 0; j < nv; j++) s += Ji[j] * Minv[j * nv + k];
+      G[item] = s;
+    }
+  } else {
+    FORL(item, nefc * nv) {
+      const int i = item / nv, k = item - i * nv;
+      const double* Ji = J + i * nv;
+      double s = Ji[k];
+      for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * Ji[m.dof_desc_dof[p]];
+      G[item] = s;
+    }
   }
   WSYNC();
-  double* ard = e.X(XF_EFC_ARDIAG);
+  double* ard = e.XG(XF_EFC_ARDIAG);
   if (nefc <= B2K_PGS_REGROWS) {
     double* AR = arPtr(e, nefc);
     // lower triangle incl. diagonal, mirrored
@@ -49,15 +64,33 @@ __device__ void stage_projectConstraint(const Env e, int nefc) {
       const int i = item / nefc, j = item - i * nefc;
       if (j > i) continue;
       double s = 0;
-      for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[j * nv + k] * dinv[k];
+      if (dense) { for (int k = 0; k < nv; k++) s += G[i * nv + k] * J[j * nv + k]; }
+      else { for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[j * nv + k] * dinv[k]; }
       if (i == j) { s += R[i]; ard[i] = s; }
       AR[i * nefc + j] = s;
       AR[j * nefc + i] = s;
     }
+    WSYNC();
+    // row constants of the PGS sweep: {1/A_ii (negated on elliptic-cone rows), A_ii, lo, hi}
+    const int* type = e.IG(B2MJ_F_EFC_TYPE);
+    const double* floss = e.DG(B2MJ_F_EFC_FRICTIONLOSS);
+    double* rowc = AR + nefc * nefc;
+    FORL(i, nefc) {
+      const int t = type[i];
+      const double Aii = AR[i * nefc + i];
+      double lo = 0, up = CUDART_INF;
+      if (t == B2MJ_CNSTR_EQUALITY) lo = -CUDART_INF;
+      else if (t == B2MJ_CNSTR_FRICTION_DOF || t == B2MJ_CNSTR_FRICTION_TENDON) { lo = -floss[i]; up = floss[i]; }
+      rowc[4 * i] = t == B2MJ_CNSTR_CONTACT_ELLIPTIC ? -1.0 / Aii : 1.0 / Aii;
+      rowc[4 * i + 1] = Aii;
+      rowc[4 * i + 2] = lo;
+      rowc[4 * i + 3] = up;
+    }
   } else {
     FORL(i, nefc) {
       double s = 0;
-      for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[i * nv + k] * dinv[k];
+      if (dense) { for (int k = 0; k < nv; k++) s += G[i * nv + k] * J[i * nv + k]; }
+      else { for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[i * nv + k] * dinv[k]; }
       ard[i] = s + R[i];
     }
   }
@@ -101,7 +134,7 @@ __device__ __forceinline__ void cholSolveSmall(double* x, const double* L, const
     x[i] = t / L[i * n + i];
   }
 }
-__device__ int QCQP(double* res, const double* Ain, const double* bin, const double* d, double r, int n) {
+__device__ __noinline__ int QCQP(double* res, const double* Ain, const double* bin, const double* d, double r, int n) {
   double A[25], b[5], P[25], y[5], z[5], nb[5];
   for (int i = 0; i < n; i++) {
     b[i] = bin[i] * d[i];
@@ -133,13 +166,14 @@ __device__ int QCQP(double* res, const double* Ain, const double* bin, const dou
 // weighted row product sum_k a[k] b[k] w[k], identical on all lanes
 __device__ __forceinline__ double rowDotW(const Env e, const double* a, const double* b, const double* w, int nv) {
   double s = 0;
-  FORL(k, nv) s += a[k] * b[k] * w[k];
+  if (w) { FORL(k, nv) s += a[k] * b[k] * w[k]; }
+  else { FORL(k, nv) s += a[k] * b[k]; }
   return warpSum(s);
 }
 
 // elliptic-cone block update shared by both PGS forms: given the dim x dim block Athis of AR, the block
 // residual res and the old forces, produce the new forces f (ray update, then QCQP on the friction dims)
-__device__ void pgsConeBlock(int dim, const double* Athis, const double* res, const double* oldf, const double* fri, double* f) {
+__device__ __noinline__ void pgsConeBlock(int dim, const double* Athis, const double* res, const double* oldf, const double* fri, double* f) {
   for (int j = 0; j < dim; j++) f[j] = oldf[j];
   if (f[0] < B2K_MINVAL) {
     f[0] -= res[0] / Athis[0];
@@ -183,61 +217,54 @@ __device__ void pgsConeBlock(int dim, const double* Athis, const double* res, co
   }
 }
 
-// mj_solPGS on the explicit AR with register-resident residuals (nefc <= 64).  force holds the
-// (already accepted) warm start on entry.  Returns iterations used.
-__device__ int solvePGS_reg(const Env e, int nefc) {
+// mj_solPGS on the explicit AR with register-resident residuals (nefc <= 32, or <= 64 with TWO).
+// force holds the (already accepted) warm start on entry.  Per row: the row constants {1/A_ii, A_ii, lo,
+// hi} come from one broadcast shared-memory read, the residual and the old force from two shuffles, the
+// projection is a branch-free clamp, and every lane folds the force change into its own residual with
+// one FMA.  Returns iterations used.
+template <bool TWO>
+__device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* AR, const double* rowc) {
   const DevModel& m = c_dm;
   EfcPtrs P = efcPtrs(e);
-  const double* AR = arPtr(e, nefc);
-  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
   const double scale = 1 / (m.meaninertia * max(1, m.nv));
   const int lane = e.lane;
-  const bool two = nefc > 32;
-  // per-lane rows j0 = lane, j1 = lane + 32: residual r = b + AR f, force, row constants
   const int j0 = lane, j1 = lane + 32;
-  double r0 = 0, r1 = 0, f0 = 0, f1 = 0, a0 = 1, a1 = 1, fl0 = 0, fl1 = 0;
-  int t0 = -1, t1 = -1;
+  const int c0 = min(j0, nefc - 1), c1 = min(j1, nefc - 1);  // clamped column indices for AR row reads
+  double r0 = 0, r1 = 0, f0 = 0, f1 = 0;
   if (j0 < nefc) {
-    f0 = P.force[j0]; a0 = AR[j0 * nefc + j0]; fl0 = P.floss[j0]; t0 = P.type[j0];
+    f0 = P.force[j0];
     double s = P.b[j0];
     for (int k = 0; k < nefc; k++) s += AR[j0 * nefc + k] * P.force[k];
     r0 = s;
   }
-  if (j1 < nefc) {
-    f1 = P.force[j1]; a1 = AR[j1 * nefc + j1]; fl1 = P.floss[j1]; t1 = P.type[j1];
+  if (TWO && j1 < nefc) {
+    f1 = P.force[j1];
     double s = P.b[j1];
     for (int k = 0; k < nefc; k++) s += AR[j1 * nefc + k] * P.force[k];
     r1 = s;
   }
-  const double ia0 = 1.0 / a0, ia1 = 1.0 / a1;
   int iter = 0;
   while (iter < m.opt.iterations) {
     double improvement = 0;
     for (int i = 0; i < nefc;) {
       const int src = i & 31;
-      const bool hi = i >= 32;
-      const int type = __shfl_sync(0xffffffffu, hi ? t1 : t0, src);
-      if (type != B2MJ_CNSTR_CONTACT_ELLIPTIC) {
-        const double arow0 = AR[i * nefc + (j0 < nefc ? j0 : 0)];
-        const double arow1 = two ? AR[i * nefc + (j1 < nefc ? j1 : 0)] : 0.0;
-        const double fold = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
-        const double Aii = __shfl_sync(0xffffffffu, hi ? a1 : a0, src);
-        const double iA = __shfl_sync(0xffffffffu, hi ? ia1 : ia0, src);
+      const bool hi = TWO && i >= 32;
+      const double iA = rowc[4 * i];
+      if (iA >= 0) {  // scalar row (1/A_ii is stored negated for the rows of an elliptic cone)
+        const double Aii = rowc[4 * i + 1], lo = rowc[4 * i + 2], up = rowc[4 * i + 3];
+        const double arow0 = AR[i * nefc + c0];
+        const double arow1 = TWO ? AR[i * nefc + c1] : 0.0;
         const double res = __shfl_sync(0xffffffffu, hi ? r1 : r0, src);
-        double f = fold - res * iA;
-        if (type == B2MJ_CNSTR_FRICTION_DOF || type == B2MJ_CNSTR_FRICTION_TENDON) {
-          const double fl = __shfl_sync(0xffffffffu, hi ? fl1 : fl0, src);
-          f = clampd(f, -fl, fl);
-        } else if (type != B2MJ_CNSTR_EQUALITY) {
-          if (f < 0) f = 0;
-        }
+        const double fold = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
+        double f = fmin(fmax(fold - res * iA, lo), up);
         double delta = f - fold;
         double change = delta * (0.5 * delta * Aii + res);
         if (change > 1e-10) { delta = 0; change = 0; f = fold; }
         improvement -= change;
         r0 += arow0 * delta;
-        if (two) r1 += arow1 * delta;
+        if (TWO) r1 += arow1 * delta;
         if (lane == src) { if (hi) f1 = f; else f0 = f; }
         i += 1;
       } else {
@@ -246,7 +273,7 @@ __device__ int solvePGS_reg(const Env e, int nefc) {
         double Athis[36], res[6], oldf[6], f[6];
         for (int j = 0; j < dim; j++) {
           const int row = i + j, rs = row & 31;
-          const bool rh = row >= 32;
+          const bool rh = TWO && row >= 32;
           for (int k = 0; k < dim; k++) Athis[j * dim + k] = AR[row * nefc + i + k];
           oldf[j] = __shfl_sync(0xffffffffu, rh ? f1 : f0, rs);
           res[j] = __shfl_sync(0xffffffffu, rh ? r1 : r0, rs);
@@ -266,9 +293,9 @@ __device__ int solvePGS_reg(const Env e, int nefc) {
         improvement -= change;
         for (int j = 0; j < dim; j++) {
           const int row = i + j;
-          if (j0 < nefc) r0 += AR[row * nefc + j0] * delta[j];
-          if (j1 < nefc) r1 += AR[row * nefc + j1] * delta[j];
-          if (lane == (row & 31)) { if (row >= 32) f1 = f[j]; else f0 = f[j]; }
+          r0 += AR[row * nefc + c0] * delta[j];
+          if (TWO) r1 += AR[row * nefc + c1] * delta[j];
+          if (lane == (row & 31)) { if (TWO && row >= 32) f1 = f[j]; else f0 = f[j]; }
         }
         i += dim;
       }
@@ -278,27 +305,30 @@ __device__ int solvePGS_reg(const Env e, int nefc) {
     if (improvement < m.opt.tolerance) break;
   }
   if (j0 < nefc) P.force[j0] = f0;
-  if (j1 < nefc) P.force[j1] = f1;
+  if (TWO && j1 < nefc) P.force[j1] = f1;
   WSYNC();
   return iter;
 }
 
 // mj_solPGS, matrix-free form for large nefc: rows of G = J inv(L) and the running vector
 // a = diag(1/D) G' f, so (AR f)_i = G_i . a + R_i f_i.  Returns iterations used.
-__device__ int solvePGS_free(const Env e, int nefc, double* avec) {
+__device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   EfcPtrs P = efcPtrs(e);
   const double* G = e.XG(XF_EFC_MINVJT);
-  const double* ard = e.X(XF_EFC_ARDIAG);
-  const double* dinv = e.D(B2MJ_F_QLDIAGINV);
-  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const double* ard = e.XG(XF_EFC_ARDIAG);
+  // sparse models: AR = G diag(1/D) G' (G = J inv(L));  dense small models: AR = G J' (G = J inv(M))
+  const bool dense = m.dense_small;
+  const double* U = dense ? P.J : G;
+  const double* dinv = dense ? nullptr : e.D(B2MJ_F_QLDIAGINV);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
   const double scale = 1 / (m.meaninertia * max(1, nv));
   FORL(k, nv) {
     double s = 0;
-    for (int i = 0; i < nefc; i++) s += G[i * nv + k] * P.force[i];
-    avec[k] = s * dinv[k];
+    for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
+    avec[k] = dinv ? s * dinv[k] : s;
   }
   WSYNC();
   int iter = 0;
@@ -322,7 +352,7 @@ __device__ int solvePGS_free(const Env e, int nefc, double* avec) {
         if (change > 1e-10) { delta = 0; change = 0; f = fold; }
         improvement -= change;
         if (delta != 0) {
-          FORL(k, nv) avec[k] += delta * G[i * nv + k] * dinv[k];
+          FORL(k, nv) avec[k] += delta * U[i * nv + k] * (dinv ? dinv[k] : 1.0);
           if (e.lane == 0) P.force[i] = f;
           WSYNC();
         }
@@ -333,7 +363,7 @@ __device__ int solvePGS_free(const Env e, int nefc, double* avec) {
         double Athis[36], res[6], oldf[6], f[6];
         for (int j = 0; j < dim; j++) {
           for (int k = 0; k < dim; k++) {
-            double v = rowDotW(e, G + (i + j) * nv, G + (i + k) * nv, dinv, nv);
+            double v = rowDotW(e, G + (i + j) * nv, U + (i + k) * nv, dinv, nv);
             if (j == k) v += P.R[i + j];
             Athis[j * dim + k] = v;
           }
@@ -354,7 +384,7 @@ __device__ int solvePGS_free(const Env e, int nefc, double* avec) {
         }
         improvement -= change;
         for (int j = 0; j < dim; j++) {
-          if (delta[j] != 0) FORL(k, nv) avec[k] += delta[j] * G[(i + j) * nv + k] * dinv[k];
+          if (delta[j] != 0) FORL(k, nv) avec[k] += delta[j] * U[(i + j) * nv + k] * (dinv ? dinv[k] : 1.0);
         }
         if (e.lane < dim) P.force[i + e.lane] = f[e.lane];
         WSYNC();
@@ -390,7 +420,7 @@ __device__ __forceinline__ double dot_warp(const Env e, const double* a, const d
 }
 
 // in-place dense Cholesky (lower) of the nv x nv Hessian; invd[j] = 1 / L[j][j]
-__device__ void cholFactor_warp(const Env e, double* A, double* invd, int n, double mindiag) {
+__device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* invd, int n, double mindiag) {
   for (int j = 0; j < n; j++) {
     double s = A[j * n + j];
     for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
@@ -409,7 +439,7 @@ __device__ void cholFactor_warp(const Env e, double* A, double* invd, int n, dou
 
 // x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+32, k+64, k+96
 #define B2K_CHOL_SLOTS 4
-__device__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n) {
+__device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n) {
   double t[B2K_CHOL_SLOTS];
 #pragma unroll
   for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + 32 * s; t[s] = k < n ? b[k] : 0.0; }
@@ -455,7 +485,7 @@ struct LSPoint {
 };
 
 // constraint update at the current qacc + Gauss term (primalUpdateConstraint)
-__device__ void primalUpdate(const Env e, PrimalCtx& c, int* changed) {
+__device__ __noinline__ void primalUpdate(const Env e, PrimalCtx& c, int* changed) {
   const double* qacc = e.D(B2MJ_F_QACC);
   const double* qas = e.D(B2MJ_F_QACC_SMOOTH);
   const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
@@ -469,7 +499,7 @@ __device__ void primalUpdate(const Env e, PrimalCtx& c, int* changed) {
 }
 
 // H = M + J' diag(D_active) J (+ cone blocks), then Cholesky
-__device__ void primalHessian(const Env e, PrimalCtx& c) {
+__device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
   const DevModel& m = c_dm;
   const int nv = c.nv, nefc = c.nefc;
   EfcPtrs P = efcPtrs(e);
@@ -483,7 +513,7 @@ __device__ void primalHessian(const Env e, PrimalCtx& c) {
     H[j * nv + i] = qM[t];
   }
   WSYNC();
-  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* cH = c.cone ? e.XG(XF_CONTACT_H) : nullptr;
   // one lane per lower-triangle entry (i, j <= i)
   for (int item = e.lane; item < nv * nv; item += 32) {
@@ -521,9 +551,7 @@ __device__ void primalGradient(const Env e, PrimalCtx& c) {
   if (c.newton) {
     cholSolve_warp(e, c.Mgrad, c.H, c.invd, c.grad, c.nv);
   } else {
-    FORL(i, c.nv) c.Mgrad[i] = c.grad[i];
-    WSYNC();
-    solveW_warp(e, c.Mgrad, e.X(XF_QW), e.D(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
+    solveM_warp(e, c.Mgrad, c.grad);
   }
 }
 
@@ -544,11 +572,11 @@ __device__ void primalPrepare(const Env e, PrimalCtx& c) {
   WSYNC();
 }
 
-__device__ LSPoint primalEval(const Env e, const PrimalCtx& c, double alpha) {
+__device__ __noinline__ LSPoint primalEval(const Env e, const PrimalCtx& c, double alpha) {
   EfcPtrs P = efcPtrs(e);
-  const int* c_dim = e.I(B2MJ_F_CONTACT_DIM);
-  const int* c_adr = e.I(B2MJ_F_CONTACT_EFC_ADDRESS);
-  const double* c_mu = e.D(B2MJ_F_CONTACT_MU);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+  const int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
+  const double* c_mu = e.DG(B2MJ_F_CONTACT_MU);
   const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
   double q0 = 0, q1 = 0, q2 = 0, cost = 0, deriv0 = 0, deriv1 = 0;
   FORL(i, c.nefc) {
@@ -614,7 +642,7 @@ __device__ LSPoint primalEval(const Env e, const PrimalCtx& c, double alpha) {
 }
 
 // exact line search on the convex piecewise-quadratic restriction; returns the step (0 = no progress)
-__device__ double primalSearch(const Env e, PrimalCtx& c) {
+__device__ __noinline__ double primalSearch(const Env e, PrimalCtx& c) {
   const DevModel& m = c_dm;
   const double snorm = sqrt(dot_warp(e, c.search, c.search, c.nv));
   if (snorm < B2K_MINVAL) return 0;
@@ -671,7 +699,7 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
   double* w = e.X(XF_PRIMAL);
   c.Ma = w; c.Mv = w + nv; c.grad = w + 2 * nv; c.Mgrad = w + 3 * nv; c.search = w + 4 * nv;
   c.gradold = w + 5 * nv; c.Mgradold = w + 6 * nv; c.invd = w + 7 * nv;
-  c.Jaref = e.X(XF_EFC_JAREF); c.Jv = e.X(XF_EFC_JV); c.quad = e.XG(XF_EFC_QUAD);
+  c.Jaref = e.XG(XF_EFC_JAREF); c.Jv = e.XG(XF_EFC_JV); c.quad = e.XG(XF_EFC_QUAD);
   c.H = newton ? e.XG(XF_NEWTON_H) : nullptr;
   c.scale = 1 / (m.meaninertia * max(1, nv));
   double* qacc = e.D(B2MJ_F_QACC);
@@ -719,7 +747,7 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
 }
 
 // mj_fwdConstraint.  Returns solver iterations.
-__device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
+__device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
   double* qacc = e.D(B2MJ_F_QACC);
@@ -742,7 +770,7 @@ __device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
   const bool warmstart = !(m.opt.disableflags & B2MJ_DSBL_WARMSTART);
   int iters = 0;
   if (m.opt.solver == B2MJ_SOL_PGS) {
-    double* jar = e.X(XF_EFC_JAREF);
+    double* jar = e.XG(XF_EFC_JAREF);
     double* avec = e.X(XF_VEC1);
     const double* G = e.XG(XF_EFC_MINVJT);
     const double* dinv = e.D(B2MJ_F_QLDIAGINV);
@@ -765,10 +793,11 @@ __device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
           cost += P.force[i] * (0.5 * s + P.b[i]);
         }
       } else {
+        const double* U = m.dense_small ? P.J : G;
         FORL(k, nv) {
           double s = 0;
-          for (int i = 0; i < nefc; i++) s += G[i * nv + k] * P.force[i];
-          avec[k] = s * dinv[k];
+          for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
+          avec[k] = m.dense_small ? s : s * dinv[k];
         }
         WSYNC();
         FORL(i, nefc) {
@@ -785,20 +814,23 @@ __device__ int stage_fwdConstraint(const Env e, int nefc, int ncon) {
       FORL(i, nefc) P.force[i] = 0;
       WSYNC();
     }
-    iters = reg ? solvePGS_reg(e, nefc) : solvePGS_free(e, nefc, avec);
+    if (reg) {
+      const double* AR = arPtr(e, nefc);
+      iters = nefc <= 32 ? solvePGS_regT<false>(e, nefc, AR, AR + nefc * nefc) : solvePGS_regT<true>(e, nefc, AR, AR + nefc * nefc);
+    } else {
+      iters = solvePGS_free(e, nefc, avec);
+    }
     // dual finish: qfrc_constraint = J' f ; qacc = qacc_smooth + inv(M) qfrc_constraint
     mulJacTVec_warp(e, nefc, qfc, P.force);
     double* tmp = e.X(XF_VEC2);
-    FORL(i, nv) tmp[i] = qfc[i];
-    WSYNC();
-    solveW_warp(e, tmp, e.X(XF_QW), dinv, e.X(XF_VEC3));
+    solveM_warp(e, tmp, qfc);
     FORL(i, nv) { const double a = qas[i] + tmp[i]; qacc[i] = a; warm[i] = a; }
     WSYNC();
   } else {
     const bool newton = m.opt.solver == B2MJ_SOL_NEWTON;
     if (warmstart) {
       // cost at the warm start vs at the unconstrained acceleration
-      double* jar = e.X(XF_EFC_JAREF);
+      double* jar = e.XG(XF_EFC_JAREF);
       double* Ma = e.X(XF_PRIMAL);
       const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
       mulJacVec_warp(e, nefc, jar, warm);

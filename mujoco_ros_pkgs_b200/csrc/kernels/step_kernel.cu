@@ -22,7 +22,7 @@ namespace b2k {
 __device__ __forceinline__ bool isBad(double x) { return isnan(x) || x > B2MJ_MAXVAL || x < -B2MJ_MAXVAL; }
 
 // mj_resetData on the resident state of one env
-__device__ void resetEnv(const Env e, int* warning, int which) {
+__device__ __noinline__ void resetEnv(const Env e, int* warning, int which) {
   const DevModel& m = c_dm;
   double* qpos = e.D(B2MJ_F_QPOS);
   FORL(i, m.nq) qpos[i] = m.qpos0[i];
@@ -45,10 +45,19 @@ __device__ void resetEnv(const Env e, int* warning, int which) {
 
 struct StepCtx {
   int ncon, nefc, iters;
+  int nsync;         // threads taking part in the stage barriers (0 = no barriers in this pass)
   long long t_prev;  // stage profile (only touched when LaunchArgs::prof is set)
 };
 
+// Stage boundary.  All warps of the CTA run the same model, so keeping them in lockstep at stage
+// granularity makes them share instruction-cache lines and model-constant cache lines (the megakernel is
+// fetch-latency bound, not issue bound).  The barrier is a locality device, not a correctness one; it
+// counts only the warps that own an env (the last CTA may be partial).
+#define STAGE_SYNC() \
+  if (sc.nsync) asm volatile("bar.sync 1, %0;" ::"r"(sc.nsync) : "memory")
+
 #define PROF_MARK(id)                                                              \
+  STAGE_SYNC();                                                                    \
   if (a.prof) {                                                                    \
     const long long _now = clock64();                                              \
     if (e.lane == 0) atomicAdd(a.prof + (id), (unsigned long long)(_now - sc.t_prev)); \
@@ -65,7 +74,7 @@ __device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int e
     stage_kinematics(e); PROF_MARK(PROF_KINEMATICS)
     stage_comPos(e); PROF_MARK(PROF_COMPOS)
     stage_tendon_transmission(e); PROF_MARK(PROF_TENDON)
-    stage_crb_factor(e); PROF_MARK(PROF_CRB_FACTOR)
+    stage_crb_factor(e, a.dump != 0 || a.mode == MODE_STEP_BEGIN); PROF_MARK(PROF_CRB_FACTOR)
     sc.ncon = stage_collision(e, warning); PROF_MARK(PROF_COLLISION)
     sc.nefc = stage_makeConstraint(e, sc.ncon, warning); PROF_MARK(PROF_MAKECONSTRAINT)
     if (m.opt.solver == B2MJ_SOL_PGS) stage_projectConstraint(e, sc.nefc);
@@ -90,7 +99,7 @@ __device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int e
 }
 
 // mj_RungeKutta(4)
-__device__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
+__device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
   const DevModel& m = c_dm;
   const int nq = m.nq, nv = m.nv, na = m.na;
   const double h = m.opt.timestep;
@@ -183,6 +192,9 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const LaunchA
   StepCtx sc;
   sc.ncon = 0; sc.nefc = 0; sc.iters = 0;
   sc.t_prev = a.prof ? clock64() : 0;
+  const int cta_envs = min(nwarp, a.nenv - (int)blockIdx.x * nwarp);
+  const int nsync_main = (nwarp > 1 && a.sync_stages) ? cta_envs * 32 : 0;
+  sc.nsync = 0;
 
   // ---- resume a split step: bring the arena back from HBM ----
   if (a.mode == MODE_STEP_END) {
@@ -240,7 +252,9 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const LaunchA
       if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
     }
     const bool first = a.mode != MODE_STEP_END, second = a.mode != MODE_STEP_BEGIN;
+    sc.nsync = nsync_main;
     forwardPass(e, a, env, sc, false, first, second);
+    sc.nsync = 0;
     if (a.mode == MODE_FORWARD || a.mode == MODE_STEP_BEGIN) break;
     // mj_checkAcc
     {

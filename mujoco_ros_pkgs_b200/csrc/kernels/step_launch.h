@@ -5,7 +5,7 @@
 
 #include "dev_model.h"
 
-#define B2K_MAX_THREADS 256
+#define B2K_MAX_THREADS 128
 
 extern "C" {
 int b2k_launch_step(const b2k::DevModel* m, const b2k::LaunchArgs* a, int warps_per_cta, size_t smem_bytes,

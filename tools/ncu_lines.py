@@ -75,3 +75,30 @@ for (fn, ln), c in sorted(per.items(), key=lambda kv: -kv[1]["# Samples"])[:top]
     text = srccache[fn][ln - 1].strip()[:90] if 0 < ln <= len(srccache[fn]) else ""
     print(f"{100 * c['# Samples'] / tot['# Samples']:5.1f}% inst {c['Instructions Executed']:8.0f} lsb {c['stall_long_sb']:5.0f} noi {c['stall_no_inst']:5.0f} "
           f"wait {c['stall_wait']:5.0f} ssb {c['stall_short_sb']:5.0f} loc {c['L2 Theoretical Sectors Local']:7.0f} | {fn}:{ln} {text}")
+
+# ---- per-function aggregation (function = nearest preceding "__device__ ... name(" line in the file)
+import bisect
+funcs = {}
+for fn in set(k[0] for k in per):
+    p = glob.glob(os.path.join(ROOT, "mujoco_ros_pkgs_b200/csrc/*", fn))
+    if not p:
+        continue
+    starts = []
+    for i, l in enumerate(open(p[0]).read().splitlines(), 1):
+        mm = re.match(r"\s*(?:B2K_DI|__device__|__global__)[^;(]*?\b(\w+)\s*\(", l)
+        if mm:
+            starts.append((i, mm.group(1)))
+    funcs[fn] = starts
+agg = collections.defaultdict(collections.Counter)
+for (fn, ln), c in per.items():
+    name = "?"
+    if fn in funcs and funcs[fn]:
+        idx = bisect.bisect_right([s[0] for s in funcs[fn]], ln) - 1
+        if idx >= 0:
+            name = funcs[fn][idx][1]
+    agg[(fn, name)].update(c)
+print("\nper function (inlined code is attributed to the function it was written in):")
+nenv_steps = 4096.0
+for (fn, name), c in sorted(agg.items(), key=lambda kv: -kv[1]["# Samples"])[:45]:
+    print(f"  {100 * c['# Samples'] / tot['# Samples']:5.1f}% samples  {c['Instructions Executed'] / nenv_steps:7.0f} inst/env  "
+          f"lsb {c['stall_long_sb']:5.0f} noi {c['stall_no_inst']:5.0f} wait {c['stall_wait']:5.0f} ssb {c['stall_short_sb']:5.0f}  {fn}:{name}")
