@@ -103,3 +103,30 @@ def test_robot_hw_position_pid_tracks_target(load_model, BatchSim, capi):
     assert np.all(np.abs(sim.get("qfrc_applied")[:, model.jnt_dofadr[jid]]) <= 50.0 + 1e-12)
     # position servo on joint1 (ctrl=0) fights the PID; it must at least move toward the target
     assert np.all(sim.get("qpos")[:, model.jnt_qposadr[jid]] > 0.05)
+
+
+def test_robot_hw_on_hand_effort_and_pid(load_model, BatchSim, capi, orc):
+    """C3 path: the hand driven through robot_hw_write (EFFORT + POSITION_PID) under RK4; the effort part
+    is checked against the oracle stepping with the same qfrc_applied."""
+    model = load_model("hand_like.xml")
+    nenv = 8
+    names = ["FFJ2", "MFJ2", "RFJ2", "WRJ0"]
+    jids = [model.name2id(capi.OBJ_JOINT, n) for n in names]
+    sim = BatchSim(model, nenv)
+    sim.robot_hw_configure(jids, [0, 0, 0, 0], effort_limit=[2.0] * 4, pid=np.zeros((4, 5)),
+                           lower=[0, 0, 0, -0.7], upper=[1.57, 1.57, 1.57, 0.49], kind=[0, 0, 0, 0])
+    rng = np.random.default_rng(3)
+    cmd = rng.uniform(-0.2, 0.2, (nenv, 4))
+    oracles = [orc.Oracle(model) for _ in range(nenv)]
+    for _ in range(40):
+        sim.robot_hw_write(cmd)
+        sim.step(1)
+        for e, o in enumerate(oracles):
+            qf = np.zeros(model.nv)
+            for k, j in enumerate(jids):
+                qf[model.jnt_dofadr[j]] = cmd[e, k]
+            o.set("qfrc_applied", qf)
+            o.step(1)
+    gq = sim.get("qpos")
+    oq = np.stack([o.get("qpos") for o in oracles])
+    assert np.max(np.abs(gq - oq) / (1 + np.abs(oq))) < 1e-5

@@ -276,7 +276,7 @@ def test_golden_trajectories(orc, load_model):
     """The oracle reproduces its own frozen trajectories (tests/golden/, tools/make_golden.py)."""
     import os
     from conftest import GOLDEN
-    for name in ("panda_like", "pendulum_scene", "equality_scene", "box_stack"):
+    for name in ("panda_like", "pendulum_scene", "equality_scene", "box_stack", "hand_like", "humanoid_like", "bin"):
         path = os.path.join(GOLDEN, f"{name}.npz")
         g = np.load(path)
         m = load_model(f"{name}.xml")

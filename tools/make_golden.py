@@ -13,16 +13,18 @@ from oracle import binding as ob  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
-for name, nrec, stride in (("panda_like", 50, 10), ("pendulum_scene", 50, 10), ("equality_scene", 50, 10), ("box_stack", 60, 10)):
+for name, nrec, stride in (("panda_like", 50, 10), ("pendulum_scene", 50, 10), ("equality_scene", 50, 10), ("box_stack", 60, 10), ("hand_like", 30, 10),
+                           ("humanoid_like", 12, 5), ("bin", 15, 10)):
     m = _capi.Model.from_xml_file(os.path.join(ROOT, "mujoco_ros_pkgs_b200", "models", name + ".xml"))
     rng = np.random.default_rng(2024)
     qpos = m.qpos0.copy()
     qvel = np.zeros(m.nv)
     for j in range(m.njnt):
         t, qa, da = m.jnt_type[j], m.jnt_qposadr[j], m.jnt_dofadr[j]
+        amp = 0.02 if name in ("hand_like", "humanoid_like", "bin") else 0.1
         if t >= 2:
-            qpos[qa] += rng.uniform(-0.1, 0.1)
-            qvel[da] = rng.uniform(-0.5, 0.5)
+            qpos[qa] += rng.uniform(-amp, amp)
+            qvel[da] = rng.uniform(-5 * amp, 5 * amp)
         elif t == 1:
             q = qpos[qa:qa + 4] + rng.uniform(-0.1, 0.1, 4)
             qpos[qa:qa + 4] = q / np.linalg.norm(q)
