@@ -3,10 +3,12 @@
 
 Workload (config C2 of BASELINE.json / SURVEY.md 8d): Panda-like 7+2-DoF arm, 4096 envs PER GPU,
 Euler integrator, PGS solver, fresh random ctrl ~ U(ctrlrange) for every env at every step.
-A "step" is one b2mj_step(h, 1) over the whole batch preceded by the device-side ctrl write.
+A "step" is one mj_step of every env of the batch with fresh controls.
 
-  value      env-steps/s with inputs resident in HBM (ctrl for all steps pre-generated on the device),
-             CUDA events on the stepping stream around every step, L2 flushed between steps.
+  value      env-steps/s with inputs resident in HBM: one fused b2mj_rollout launch advances all envs K steps
+             reading the device-resident ctrl stream and writing the per-step trajectory (CUDA events on the
+             stepping stream).  per_step_launch reports the same K steps as K separate launches
+             (b2mj_set_device + b2mj_step, L2 flushed between steps) -- the closed-loop usage.
   e2e        same metric through the C-ABI with HOST buffers: per step b2mj_set(ctrl) from pinned host
              memory -> b2mj_step -> b2mj_get(qpos, qvel, sensordata) into pinned host memory.
   roofline   algorithmic state bytes per env-step x envs / kernel time, against the
@@ -176,7 +178,11 @@ def main():
         "workload": f"C2: {args.model} (nq={model.nq} nv={model.nv} nu={model.nu} nbody={model.nbody}), "
                     f"{args.nenv} envs per GPU, {integ}, {solver}, dt={model.opt.timestep}, random ctrl every step",
         "nenv_per_gpu": args.nenv, "global_envs": args.nenv * args.gpus, "parallelism": f"env-shard x{args.gpus}",
-        "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "NOT flushed (diagnostic)",
+        "launch_mode": "fused open-loop rollout: ONE b2mj_rollout launch advances every env --steps steps; ctrl stream "
+                       "[steps][nenv][nu] resident in HBM, per-step qpos/qvel/sensordata trajectory written to HBM",
+        "l2": ("inputs larger than L2 (ctrl stream + trajectory, %.0f MB); L2 flushed before the timed launch"
+               % ((args.steps * args.nenv * (model.nu + model.nq + model.nv + model.nsensordata) * 8) / 1e6))
+        if not args.no_flush else "NOT flushed (diagnostic)",
     }
     if args.impl == "reference":
         run_reference(args, model, workload)
@@ -221,16 +227,14 @@ def main():
         sim.step(1)
 
     launches_per_step = 2 if nu else 1
-    # ---------------- device-resident leg ----------------
+    ns = model.nsensordata
+    # ---------------- device-resident leg A: per-step launches (what a closed-loop user does) ----------------
     with torch.cuda.stream(stream):
         for k in range(W):
             one_step(k)
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        wall0 = time.perf_counter()
         for k in range(K):
             if not args.no_flush:
                 flush_buf.fill_(k)  # evict the state / model from L2 (buffer > 126 MB L2)
@@ -242,21 +246,49 @@ def main():
             kev[k][1].record(stream)
             evs[k][1].record(stream)
         barrier()
+    ps_step_ms = sum(a.elapsed_time(b) for a, b in evs)
+    ps_kern_ms = sum(a.elapsed_time(b) for a, b in kev)
+    stats = {k: sim.get(k)[:, 0] for k in ("ncon", "nefc", "solver_iter")}
+
+    # ---------------- device-resident leg B (headline): fused open-loop rollout ----------------
+    # One b2mj_rollout launch advances every env K steps; the ctrl stream for all steps is resident in HBM
+    # (K*nenv*nu*8 bytes, larger than L2 at the default K) and the per-step qpos/qvel/sensordata trajectory
+    # is written back to HBM, so every step's result stays observable.
+    sim.reset()
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    tq = torch.empty(K, nenv, model.nq, dtype=torch.float64, device=dev)
+    tv = torch.empty(K, nenv, model.nv, dtype=torch.float64, device=dev)
+    ts = torch.empty(K, nenv, max(ns, 1), dtype=torch.float64, device=dev) if ns else None
+    cptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
+    with torch.cuda.stream(stream):
+        sim.rollout(W, cptr(ctrl_dev[:W]) if nu else 0, tq.data_ptr(), tv.data_ptr(), cptr(ts))
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        if not args.no_flush:
+            flush_buf.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        e0.record(stream)
+        sim.rollout(K, cptr(ctrl_dev[W:]) if nu else 0, tq.data_ptr(), tv.data_ptr(), cptr(ts))
+        e1.record(stream)
+        barrier()
         wall = time.perf_counter() - wall0
         clocks = sampler.stop()
-    step_ms = sum(a.elapsed_time(b) for a, b in evs)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev)
-    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
+    step_ms = e0.elapsed_time(e1)
+    kern_ms = step_ms
+    t = torch.tensor([step_ms, kern_ms, ps_step_ms, ps_kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms = float(t[0]), float(t[1])
+    step_ms, kern_ms, ps_step_ms, ps_kern_ms = (float(x) for x in t)
     value = nenv * world * K / (step_ms * 1e-3)
+    ps_value = nenv * world * K / (ps_step_ms * 1e-3)
     warn = sim.get("warning").sum(0).tolist()
-    stats = {k: sim.get(k)[:, 0] for k in ("ncon", "nefc", "solver_iter")}
+    traj_ok = bool(torch.isfinite(tq[-1]).all().item())
 
     # ---------------- end-to-end leg: host buffers through the C-ABI ----------------
     KE = args.e2e_steps or K
-    ns = model.nsensordata
     pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()  # noqa: E731
     h_ctrl = pin(nenv, nu) if nu else None
     h_qpos, h_qvel, h_sens = pin(nenv, model.nq), pin(nenv, model.nv), pin(nenv, max(ns, 1))
@@ -293,8 +325,8 @@ def main():
     if rank == 0:
         peak, peak_src = load_peaks()
         bstate = state_bytes(model)
-        kernel_s = kern_ms * 1e-3 / K
-        achieved = bstate * nenv / kernel_s / 1e9
+        kernel_s = kern_ms * 1e-3          # one launch = nenv * K env-steps
+        achieved = bstate * nenv * K / kernel_s / 1e9
         info = sim.launch_info()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -302,13 +334,19 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": KE, "timing": "wall clock, sync both sides, pinned host buffers"},
-            "gpu_launches": launches_per_step * K,
+            "gpu_launches": 1,
+            "per_step_launch": {"value": ps_value, "unit": UNIT, "ms_per_step": ps_step_ms / K,
+                                "kernel_ms_per_launch": ps_kern_ms / K, "gpu_launches": launches_per_step * K,
+                                "note": "K launches of b2mj_set_device(ctrl) + b2mj_step(1), CUDA events per step, "
+                                        "L2 flushed between steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "b2k_step_kernel",
-                         "algorithmic_bytes_per_env_step": bstate, "kernel_ms_per_launch": kern_ms / K,
+                         "algorithmic_bytes_per_env_step": bstate, "env_steps_per_launch": nenv * K,
+                         "kernel_ms_per_launch": kern_ms,
                          "note": "latency/FP64-bound path: see DESIGN.md 'Roofline'"},
             "kernel": {k: info[k] for k in ("warps_per_cta", "ctas", "smem_bytes_per_cta", "regs_per_thread",
                                             "arena_in_smem", "state_record_bytes")},
+            "trajectory_finite": traj_ok,
             "workload_stats": {"warnings": warn, "ncon_mean": float(stats["ncon"].mean()),
                                "nefc_mean": float(stats["nefc"].mean()), "nefc_max": int(stats["nefc"].max()),
                                "solver_iter_mean": float(stats["solver_iter"].mean())},

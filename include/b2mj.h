@@ -293,6 +293,13 @@ int b2mj_forward(b2mj_handle* h);
 /* nsteps x mj_step on all envs, asynchronous on the handle's stream; no host callbacks inside
  * (mujoco_env.cpp:498,552,593).  ctrl/qfrc_applied/xfrc_applied are read as currently set. */
 int b2mj_step(b2mj_handle* h, int nsteps);
+/* fused open-loop rollout: nsteps x mj_step in ONE launch, every env advancing at its own pace with its
+ * state resident on chip.  dev_ctrl (DEVICE, [nsteps][nenv][nu], may be NULL = keep current ctrl) supplies
+ * fresh controls for every env at every step; the optional DEVICE outputs receive the per-step trajectory
+ * ([nsteps][nenv][nq] / [nv] / [nsensordata]) -- what the reference's lastStageCallback consumers would
+ * have read after each step (mujoco_env.cpp:500,554,595).  Same arithmetic as nsteps calls of b2mj_step. */
+int b2mj_rollout(b2mj_handle* h, int nsteps, const double* dev_ctrl, double* dev_qpos_out, double* dev_qvel_out,
+                 double* dev_sensor_out);
 /* split step around the control hook (mjcb_control fires between the velocity stage and actuation:
  * mujoco_env.h:242-246).  step_begin: checks + position + velocity stages (+pos/vel sensors);
  * step_end: actuation, acceleration, constraint solve, acc sensors, check, integrate. Euler only. */
@@ -380,6 +387,9 @@ int b2mj_launch_info(b2mj_handle* h, b2mjLaunchInfo* out);
  * envs, one entry per stage (b2mj_stage_name).  Returns the number of stages. */
 int b2mj_stage_profile(b2mj_handle* h, int enable, uint64_t* cycles, int ncycles);
 const char* b2mj_stage_name(int stage);
+/* diagnostic: SM residency of each env's last work item (last launch, or last rollout chunk), in units of
+ * 1024 cycles; host_kcycles: HOST int32 [nenv].  Shows the load imbalance between envs. */
+int b2mj_env_cycles(b2mj_handle* h, int* host_kcycles);
 
 const char* b2mj_last_error(void);
 int b2mj_version(void);

@@ -21,6 +21,7 @@ lib.b2mj_set_stream.argtypes = [_vp, _vp]
 lib.b2mj_reset.argtypes = [_vp, _vp]
 lib.b2mj_forward.argtypes = [_vp]
 lib.b2mj_step.argtypes = [_vp, C.c_int]
+lib.b2mj_rollout.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
 lib.b2mj_step_begin.argtypes = [_vp]
 lib.b2mj_step_end.argtypes = [_vp]
 lib.b2mj_sync.argtypes = [_vp]
@@ -29,6 +30,7 @@ lib.b2mj_get.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
 lib.b2mj_set.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
 lib.b2mj_set_device.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
 lib.b2mj_stage_profile.argtypes = [_vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
+lib.b2mj_env_cycles.argtypes = [_vp, _vp]
 lib.b2mj_stage_name.argtypes = [C.c_int]
 lib.b2mj_stage_name.restype = C.c_char_p
 lib.b2mj_device_ptr.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t)]
@@ -80,6 +82,11 @@ class BatchSim:
 
     def step(self, n: int = 1):
         check(lib.b2mj_step(self._h, n), "step")
+
+    def rollout(self, nsteps: int, ctrl_ptr: int = 0, qpos_ptr: int = 0, qvel_ptr: int = 0, sensor_ptr: int = 0):
+        """Fused open-loop rollout; all pointers are DEVICE addresses (0 = not used)."""
+        check(lib.b2mj_rollout(self._h, nsteps, _vp(ctrl_ptr or None), _vp(qpos_ptr or None), _vp(qvel_ptr or None),
+                               _vp(sensor_ptr or None)), "rollout")
 
     def step_begin(self):
         check(lib.b2mj_step_begin(self._h), "step_begin")
@@ -136,6 +143,11 @@ class BatchSim:
         buf = (C.c_uint64 * 64)()
         n = check(lib.b2mj_stage_profile(self._h, int(enable), buf, 64), "stage_profile")
         return {lib.b2mj_stage_name(i).decode(): int(buf[i]) for i in range(n)}
+
+    def env_cycles(self) -> np.ndarray:
+        out = np.zeros(self.nenv, dtype=np.int32)
+        check(lib.b2mj_env_cycles(self._h, out.ctypes.data), "env_cycles")
+        return out.astype(np.int64) * 1024
 
     # ---- plugin data paths ----
     def robot_hw_configure(self, joint_ids, modes, effort_limit=None, pid=None, lower=None, upper=None, kind=None):

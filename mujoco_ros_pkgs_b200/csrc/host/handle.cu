@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -280,7 +281,7 @@ static int make_layout(Handle* h) {
   const bool rk4 = m->opt.integrator == B2MJ_INT_RK4;
   int* xs = d.xsize;
   for (int i = 0; i < XF_COUNT; i++) xs[i] = 0;
-  xs[XF_QLOC] = 4 * m->njnt;
+  xs[XF_QLOC] = 0;
   xs[XF_QH] = m->nM;
   xs[XF_QHDIAGINV] = nv;
   xs[XF_EFC_MINVJT] = pgs ? m->njmax * nv : 0;
@@ -298,11 +299,9 @@ static int make_layout(Handle* h) {
   xs[XF_RK_XF] = rk4 ? 4 * nv : 0;
   xs[XF_RK_F] = rk4 ? 4 * (nv + na) : 0;
   xs[XF_RK_DX] = rk4 ? 2 * nv + na : 0;
-  xs[XF_TLOC] = 14 * m->nbody;
+  xs[XF_SCRATCH] = std::max(14 * m->nbody, 6 * nv);
   xs[XF_QW] = m->nM;
   xs[XF_QHW] = m->nM;
-  xs[XF_DOFBUF] = 6 * nv;
-  xs[XF_BODYBUF] = 6 * m->nbody;
   xs[XF_MINV] = d.dense_small ? nv * nv : 0;
   xs[XF_HINV] = (d.dense_small && d.any_damping && !rk4) ? nv * nv : 0;
   xs[XF_PRIMAL] = pgs ? 0 : 8 * nv;
@@ -325,6 +324,13 @@ static int make_layout(Handle* h) {
   // global arena (L2) when the per-env footprint would starve occupancy
   std::vector<char> cold(B2MJ_NFIELD, 0), xcold(XF_COUNT, 0);
   xcold[XF_EFC_AR] = 1;
+  // API-only fields (read back only through an arena dump) never occupy shared memory
+  cold[B2MJ_F_XIMAT] = 1;
+  if (!d.need_rnepost) cold[B2MJ_F_CACC] = cold[B2MJ_F_CFRC_INT] = cold[B2MJ_F_CFRC_EXT] = 1;
+  if (d.dense_small) {
+    cold[B2MJ_F_QLD] = cold[B2MJ_F_QLDIAGINV] = cold[B2MJ_F_QLDIAGSQRTINV] = 1;
+    xcold[XF_QH] = xcold[XF_QHDIAGINV] = xcold[XF_QW] = xcold[XF_QHW] = 1;
+  }
   auto smem_bytes_env = [&]() {
     size_t dbl = d.rec_end, ints = 0;
     for (int f = 0; f < B2MJ_NFIELD; f++) {
@@ -378,6 +384,20 @@ static int make_layout(Handle* h) {
   }
   d.arena_s_doubles = even(sdo);
   d.arena_s_ints = even(sio);
+  if (getenv("B2MJ_PRINT_LAYOUT")) {
+    static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
+                                   "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",
+                                   "SUBTREE_ANGMOM", "BODYVEL", "RK_X0", "RK_XF", "RK_F", "RK_DX", "SCRATCH", "QW", "QHW",
+                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S"};
+    fprintf(stderr, "[b2mj layout] record %d doubles; shared arena %d doubles + %d ints per env\n", d.rec_end, d.arena_s_doubles,
+            d.arena_s_ints);
+    for (int f = 0; f < B2MJ_NFIELD; f++)
+      if (d.fsize[f] && !is_record_field(f))
+        fprintf(stderr, "  %-24s %6d %s %s\n", b2mj_field_name((b2mj_field)f), d.fsize[f], d.fis_int[f] ? "i32" : "f64",
+                d.off_s[f] >= 0 ? "smem" : "HBM");
+    for (int i = 0; i < XF_COUNT; i++)
+      if (xs[i]) fprintf(stderr, "  x:%-22s %6d f64 %s\n", xnames[i], xs[i], d.xoff_s[i] >= 0 ? "smem" : "HBM");
+  }
   const size_t env_bytes = (((size_t)d.arena_s_doubles * 8 + (size_t)d.arena_s_ints * 4) + 15) & ~(size_t)15;
   // launch shape: warps per CTA maximising resident envs per SM
   int bestW = 1, bestEnv = 0;
@@ -447,7 +467,8 @@ static int upload_init_templates(Handle* h) {
   return 0;
 }
 
-int handle_launch(Handle* h, int mode, int nsteps) {
+int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, double* traj_qpos, double* traj_qvel,
+                  double* traj_sensor, int chunk) {
   LaunchArgs a;
   a.rec = h->rec;
   a.garena_d = h->garena_d;
@@ -461,6 +482,18 @@ int handle_launch(Handle* h, int mode, int nsteps) {
   a.mode = mode;
   a.dump = h->keep_intermediates;
   a.prof = h->prof;
+  a.ctrl_seq = ctrl_seq;
+  a.traj_qpos = traj_qpos;
+  a.traj_qvel = traj_qvel;
+  a.traj_sensor = traj_sensor;
+  a.sched = nullptr;
+  a.chunk = 0;
+  if (chunk > 0 && nsteps > chunk && !h->keep_intermediates) {
+    if (!h->sched) CUDA_OK(cudaMalloc(&h->sched, (size_t)(1 + h->nenv) * sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(h->sched, 0, (size_t)(1 + h->nenv) * sizeof(int), h->stream));
+    a.sched = h->sched;
+    a.chunk = chunk;
+  }
   a.sync_stages = getenv("B2MJ_STAGE_SYNC") ? 1 : 0;  // measured: no gain on B200 (profiles/), off by default
   const int rc = b2k_launch_step(&h->dm, &a, h->warps_per_cta, h->smem_bytes, h->stream);
   if (rc != 0) {
@@ -527,6 +560,7 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->warning); cudaFree(h->stats); cudaFree(h->xfrc); cudaFree(h->mocap); cudaFree(h->mocap_init);
   cudaFree(h->mask_dev);
   cudaFree(h->prof);
+  cudaFree(h->sched);
   handle_free_plugins(h);
   b2mj_model_free(h->model);
   delete h;
@@ -578,6 +612,23 @@ int b2mj_step(b2mj_handle* hh, int nsteps) {
   CUDA_OK(cudaSetDevice(h->device));
   h->in_split_step = 0;
   return handle_launch(h, MODE_STEP, nsteps);
+}
+
+int b2mj_rollout(b2mj_handle* hh, int nsteps, const double* dev_ctrl, double* dev_qpos_out, double* dev_qvel_out,
+                 double* dev_sensor_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  if (nsteps <= 0) {
+    set_error("b2mj_rollout: nsteps must be positive");
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  h->in_split_step = 0;
+  // long rollouts are scheduled as (env, chunk) tickets over a persistent grid: load balance across envs
+  // whose solver effort differs (B2MJ_ROLLOUT_CHUNK overrides the chunk length, 0 = one env per warp)
+  int chunk = 16;
+  if (const char* env = getenv("B2MJ_ROLLOUT_CHUNK")) chunk = atoi(env);
+  return handle_launch(h, MODE_STEP, nsteps, dev_ctrl, dev_qpos_out, dev_qvel_out, dev_sensor_out, chunk);
 }
 
 int b2mj_step_begin(b2mj_handle* hh) {
@@ -775,6 +826,15 @@ int b2mj_stage_profile(b2mj_handle* hh, int enable, uint64_t* cycles, int ncycle
   if (enable) CUDA_OK(cudaMemset(h->prof, 0, PROF_COUNT * sizeof(unsigned long long)));
   if (!enable && h->prof) { cudaFree(h->prof); h->prof = nullptr; }
   return PROF_COUNT;
+}
+
+int b2mj_env_cycles(b2mj_handle* hh, int* host_kcycles) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !host_kcycles) return B2MJ_EINVAL;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy2D(host_kcycles, sizeof(int), h->stats + 3, 4 * sizeof(int), sizeof(int), h->nenv, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 const char* b2mj_stage_name(int stage) {

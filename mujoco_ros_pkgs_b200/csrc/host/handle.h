@@ -30,6 +30,7 @@ struct Handle {
   double* mocap = nullptr;        // [nenv][7*nmocap]
   double* mocap_init = nullptr;
   unsigned char* mask_dev = nullptr;
+  int* sched = nullptr;                // [1 + nenv] ticket counter + per-env chunk progress (persistent rollout)
   unsigned long long* prof = nullptr;  // [PROF_COUNT] stage cycle totals (b2mj_stage_profile), null = off
 
   int warps_per_cta = 4;
@@ -46,7 +47,8 @@ struct Handle {
   SensorReadoutState* sensor_ro = nullptr;
 };
 
-int handle_launch(Handle* h, int mode, int nsteps);
+int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq = nullptr, double* traj_qpos = nullptr,
+                  double* traj_qvel = nullptr, double* traj_sensor = nullptr, int chunk = 0);
 void handle_free_plugins(Handle* h);
 void handle_reset_plugins(Handle* h, const uint8_t* env_mask);
 

@@ -38,11 +38,9 @@ enum XField {
   XF_RK_XF,         // 4*nv       RK4 stage velocities
   XF_RK_F,          // 4*(nv+na)  RK4 stage accelerations / act_dot
   XF_RK_DX,         // 2*nv+na
-  XF_TLOC,          // 14*nbody  ping-pong buffers of the kinematic scan (pos 3 + quat 4 per body)
+  XF_SCRATCH,       // stage-local scratch: max(14*nbody kinematic scan ping-pong, 6*nv crb*cdof, 6*nbody RNE forces)
   XF_QW,            // nM   off-diagonal entries of inv(L) for qLD (sparse layout of qM)
   XF_QHW,           // nM   same for qH
-  XF_DOFBUF,        // 6*nv  crb * cdof per dof
-  XF_BODYBUF,       // 6*nbody  per-body RNE force before the subtree sum
   XF_EFC_AR,        // njmax*njmax  dense AR = J inv(M) J' + R (PGS); always in the HBM/L2 arena
   XF_MINV,          // nv*nv  dense inv(qM) (small models: nv <= 16)
   XF_HINV,          // nv*nv  dense inv(qM + h diag(damping))
@@ -113,6 +111,16 @@ struct LaunchArgs {
   int nsteps;
   int mode;                // 0 step, 1 forward only, 2 step_begin (to control hook), 3 step_end
   int dump;                // copy the shared arena to garena at the end
+  // fused rollout (b2mj_rollout): per-step control stream in, per-step trajectory out (all optional)
+  const double* ctrl_seq;  // [nsteps][nenv][nu]
+  double* traj_qpos;       // [nsteps][nenv][nq]
+  double* traj_qvel;       // [nsteps][nenv][nv]
+  double* traj_sensor;     // [nsteps][nenv][nsensordata]
+  // persistent rollout scheduling: warps draw (env, chunk-of-steps) tickets from a global counter so that
+  // slow envs (long solver runs) do not leave the rest of the GPU idle; sched[0] = next ticket,
+  // sched[1 + env] = chunks of that env already completed.  null = one env per warp, all steps.
+  int* sched;
+  int chunk;               // steps per ticket
   int sync_stages;         // CTA-wide lockstep at stage boundaries (instruction / constant cache locality)
   unsigned long long* prof; // [PROF_COUNT] per-stage SM-cycle totals over all envs, or null (b2mj_stage_profile)
 };

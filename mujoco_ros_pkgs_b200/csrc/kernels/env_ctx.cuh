@@ -21,6 +21,7 @@ struct Env {
   double* gd;    // this env's HBM/L2 arena (doubles)
   int* gi;       // this env's HBM/L2 arena (ints)
   int lane;
+  int dump;      // the arena will be read back (keep_intermediates / split step): also produce API-only fields
 
   __device__ __forceinline__ double* sd() const { return reinterpret_cast<double*>(b2k_smem + sbd); }
   __device__ __forceinline__ int* si() const { return reinterpret_cast<int*>(b2k_smem + sbi); }
@@ -48,6 +49,10 @@ struct Env {
     return o >= 0 ? sd() + o : gd + c_dm.xoff_g[xf];
   }
 };
+
+// The megakernel is instruction-fetch bound (profiles/): run-time-bounded loops stay rolled so their bodies are
+// re-executed from the instruction cache instead of being fetched as straight-line copies.
+#define B2K_NOUNROLL _Pragma("unroll 1")
 
 // lane-strided loop; never unrolled: trip counts are 1-2 for the models this kernel targets and the
 // megakernel is instruction-cache bound, so code size matters more than loop overhead
@@ -83,6 +88,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes
 __device__ __forceinline__ void bulk_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {  // waits for the global writes themselves
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -173,7 +173,7 @@ __device__ __noinline__ int c_boxBox(PairCon& o, double margin, const double* po
       const int ax = pl >> 1;
       const double sg = (pl & 1) ? -1.0 : 1.0, lim = ax == 0 ? sr[ra] : sr[rb];
       int nq = 0;
-      for (int v = 0; v < np && nq < 8; v++) {
+      B2K_NOUNROLL for (int v = 0; v < np && nq < 8; v++) {
         const double* p0 = poly[v];
         const double* p1 = poly[(v + 1) % np];
         const double e0 = sg * p0[ax] - lim, e1 = sg * p1[ax] - lim;
@@ -187,12 +187,12 @@ __device__ __noinline__ int c_boxBox(PairCon& o, double margin, const double* po
         }
       }
       np = nq;
-      for (int v = 0; v < np; v++) for (int c = 0; c < 3; c++) poly[v][c] = tmp[v][c];
+      B2K_NOUNROLL for (int v = 0; v < np; v++) for (int c = 0; c < 3; c++) poly[v][c] = tmp[v][c];
       if (np == 0) return 0;
     }
     int num = 0;
     for (int c = 0; c < 3; c++) o.frame[c] = refA ? n[c] : -n[c];
-    for (int v = 0; v < np && num < 8; v++) {
+    B2K_NOUNROLL for (int v = 0; v < np && num < 8; v++) {
       const double h = poly[v][2];
       if (h >= margin) continue;
       o.dist[num] = h;
@@ -238,7 +238,7 @@ __device__ __forceinline__ double segmentBoxClosest(const double* c, const doubl
     if (t1 > -h && t1 < h) bp[nbp++] = t1;
     if (t2 > -h && t2 < h) bp[nbp++] = t2;
   }
-  for (int i = 1; i < nbp; i++) {  // insertion sort
+  B2K_NOUNROLL for (int i = 1; i < nbp; i++) {  // insertion sort
     const double v = bp[i];
     int j = i - 1;
     while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; j--; }
@@ -270,7 +270,7 @@ __device__ __forceinline__ double segmentBoxClosest(const double* c, const doubl
     double cand[2] = {hi, hi};
     int nc = 1;
     if (A > B2K_MINVAL) { cand[0] = clampd(-B / A, lo, hi); cand[1] = hi; nc = 2; }
-    for (int q = 0; q < nc; q++) {
+    B2K_NOUNROLL for (int q = 0; q < nc; q++) {
       const double v = d2(cand[q]);
       if (v < best) { best = v; best_t = cand[q]; }
     }
@@ -294,7 +294,7 @@ __device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat
       n += c_planeSphere(o, n, margin, pos1, mat1, p, size2[0]);
       sub3(p, pos2, seg);
       n += c_planeSphere(o, n, margin, pos1, mat1, p, size2[0]);
-      for (int i = 0; i < n; i++) copy3(o.frame + 6 * i + 3, axis);
+      B2K_NOUNROLL for (int i = 0; i < n; i++) copy3(o.frame + 6 * i + 3, axis);
       return n;
     }
     if (t2 == B2MJ_GEOM_BOX) {
@@ -417,7 +417,7 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
   int* c_excl = e.IG(B2MJ_F_CONTACT_EXCLUDE);
   int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
   int carry = 0, overflow = 0;
-  for (int base = 0; base < m.ncollpair; base += 32) {
+  B2K_NOUNROLL for (int base = 0; base < m.ncollpair; base += 32) {
     const int p = base + e.lane;
     PairCon pc;
     pc.shared_frame = 0;
@@ -469,7 +469,7 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
         for (int i = 0; i < 3; i++) fri[i] = fmax(m.geom_friction[3 * g1 + i], m.geom_friction[3 * g2 + i]);
       }
       const int first = carry + incl - num;
-      for (int i = 0; i < num; i++) {
+      B2K_NOUNROLL for (int i = 0; i < num; i++) {
         const int c = first + i;
         if (c >= m.nconmax) { overflow = 1; break; }
         c_dist[c] = pc.dist[i];

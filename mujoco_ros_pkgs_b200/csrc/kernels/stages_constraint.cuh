@@ -83,7 +83,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
     const double* xpos = e.D(B2MJ_F_XPOS);
     const double* xmat = e.D(B2MJ_F_XMAT);
     const double* xquat = e.D(B2MJ_F_XQUAT);
-    for (int q = 0; q < m.neq; q++) {
+    B2K_NOUNROLL for (int q = 0; q < m.neq; q++) {
       if (!m.eq_active[q]) continue;
       const int et = m.eq_type[q], id0 = m.eq_obj1id[q], id1 = m.eq_obj2id[q];
       const double* data = m.eq_data + B2MJ_NEQDATA * q;
@@ -122,7 +122,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
         if (e.lane == 0) {
           const double tran = m.body_invweight0[2 * id0] + m.body_invweight0[2 * id1];
           const double rot = m.body_invweight0[2 * id0 + 1] + m.body_invweight0[2 * id1 + 1];
-          for (int r = 0; r < size; r++) P.diag[row + r] = r < 3 ? tran : rot;
+          B2K_NOUNROLL for (int r = 0; r < size; r++) P.diag[row + r] = r < 3 ? tran : rot;
         }
       } else {
         const bool isj = et == B2MJ_EQ_JOINT;
@@ -170,7 +170,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
   }
   // ---------------- friction loss ----------------
   if (!(m.opt.disableflags & B2MJ_DSBL_FRICTIONLOSS)) {
-    for (int i = 0; i < nv; i++) {
+    B2K_NOUNROLL for (int i = 0; i < nv; i++) {
       const double fl = m.dof_frictionloss[i];
       if (fl <= 0) continue;
       if (row + 1 > m.njmax) { full = 1; continue; }
@@ -181,7 +181,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
       }
       row++;
     }
-    for (int i = 0; i < m.ntendon; i++) {
+    B2K_NOUNROLL for (int i = 0; i < m.ntendon; i++) {
       const double fl = m.tendon_frictionloss[i];
       if (fl <= 0) continue;
       if (row + 1 > m.njmax) { full = 1; continue; }
@@ -196,7 +196,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
   }
   // ---------------- limits ----------------
   if (!(m.opt.disableflags & B2MJ_DSBL_LIMIT)) {
-    for (int base = 0; base < m.njnt; base += 32) {
+    B2K_NOUNROLL for (int base = 0; base < m.njnt; base += 32) {
       const int j = base + e.lane;
       int cnt = 0;
       double dist[2], sgn[2], axis[3];
@@ -223,11 +223,11 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
       const int incl = warpInclusiveScan(cnt, e.lane);
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       int r0 = row + incl - cnt;
-      for (int s = 0; s < cnt; s++) {
+      B2K_NOUNROLL for (int s = 0; s < cnt; s++) {
         const int r = r0 + s;
         if (r >= m.njmax) { full = 1; break; }
         const int da = m.jnt_dofadr[j];
-        for (int k = 0; k < nv; k++) P.J[r * nv + k] = 0;
+        B2K_NOUNROLL for (int k = 0; k < nv; k++) P.J[r * nv + k] = 0;
         if (ball) for (int k = 0; k < 3; k++) P.J[r * nv + da + k] = -axis[k];
         else P.J[r * nv + da] = sgn[s];
         P.pos[r] = dist[s]; P.margin[r] = m.jnt_margin[j]; P.floss[r] = 0;
@@ -239,7 +239,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
     if (m.ntendon) {
       const double* tl = e.D(B2MJ_F_TEN_LENGTH);
       const double* tJ = e.D(B2MJ_F_TEN_J);
-      for (int i = 0; i < m.ntendon; i++) {
+      B2K_NOUNROLL for (int i = 0; i < m.ntendon; i++) {
         if (!m.tendon_limited[i]) continue;
         const double value = tl[i], margin = m.tendon_margin[i];
         for (int side = -1; side <= 1; side += 2) {
@@ -270,7 +270,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
     const double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);
     const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
     bool contacts_full = false;  // uniform: once a contact does not fit, all later ones are dropped
-    for (int base = 0; base < ncon && !contacts_full; base += 32) {
+    B2K_NOUNROLL for (int base = 0; base < ncon && !contacts_full; base += 32) {
       const int c = base + e.lane;
       int cnt = 0, dim = 0;
       if (c < ncon && !c_excl[c]) {
@@ -292,7 +292,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
           const double tran = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
           const double rot = m.body_invweight0[2 * b1 + 1] + m.body_invweight0[2 * b2 + 1];
           const double* fri = c_fri + 5 * c;
-          for (int r = 0; r < cnt; r++) {
+          B2K_NOUNROLL for (int r = 0; r < cnt; r++) {
             const bool first_or_pyr = (r == 0) || type != B2MJ_CNSTR_CONTACT_ELLIPTIC;
             P.pos[adr + r] = first_or_pyr ? c_dist[c] : 0.0;
             P.margin[adr + r] = first_or_pyr ? c_inc[c] : 0.0;
@@ -328,12 +328,12 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
         P.J[adr * nv + k] = v[0];
       } else if (pyramid) {
         const double* fri = c_fri + 5 * c;
-        for (int kk = 1; kk < dim; kk++) {
+        B2K_NOUNROLL for (int kk = 1; kk < dim; kk++) {
           P.J[(adr + 2 * (kk - 1)) * nv + k] = v[0] + fri[kk - 1] * v[kk];
           P.J[(adr + 2 * (kk - 1) + 1) * nv + k] = v[0] - fri[kk - 1] * v[kk];
         }
       } else {
-        for (int r = 0; r < dim; r++) P.J[(adr + r) * nv + k] = v[r];
+        B2K_NOUNROLL for (int r = 0; r < dim; r++) P.J[(adr + r) * nv + k] = v[r];
       }
     }
   }
@@ -391,12 +391,12 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
       if (m.opt.cone == B2MJ_CONE_ELLIPTIC) {
         P.R[adr + 1] = P.R[adr] / fmax(B2K_MINVAL, m.opt.impratio);
         c_mu[c] = fri[0] * sqrt(P.R[adr + 1] / P.R[adr]);
-        for (int j = 2; j < dim; j++) P.R[adr + j] = P.R[adr + 1] * fri[0] * fri[0] / (fri[j - 1] * fri[j - 1]);
+        B2K_NOUNROLL for (int j = 2; j < dim; j++) P.R[adr + j] = P.R[adr + 1] * fri[0] * fri[0] / (fri[j - 1] * fri[j - 1]);
       } else {
         const double mu = fri[0] * sqrt(1 / fmax(B2K_MINVAL, m.opt.impratio));
         c_mu[c] = mu;
         const double Rpy = 2 * mu * mu * P.R[adr];
-        for (int j = 0; j < 2 * (dim - 1); j++) P.R[adr + j] = Rpy;
+        B2K_NOUNROLL for (int j = 0; j < 2 * (dim - 1); j++) P.R[adr + j] = Rpy;
       }
     }
     WSYNC();
@@ -415,7 +415,7 @@ __device__ __noinline__ void stage_referenceConstraint(const Env e, int nefc) {
   const double* qvel = e.D(B2MJ_F_QVEL);
   FORL(i, nefc) {
     double s = 0;
-    for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qvel[k];
+    B2K_NOUNROLL for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qvel[k];
     P.vel[i] = s;
     P.aref[i] = -P.KBIP[4 * i + 1] * s - P.KBIP[4 * i] * P.KBIP[4 * i + 2] * (P.pos[i] - P.margin[i]);
   }
@@ -428,7 +428,7 @@ __device__ __noinline__ void mulJacTVec_warp(const Env e, int nefc, double* res,
   const double* J = e.DG(B2MJ_F_EFC_J);
   FORL(k, nv) {
     double s = 0;
-    for (int i = 0; i < nefc; i++) {
+    B2K_NOUNROLL for (int i = 0; i < nefc; i++) {
       const double fi = f[i];
       if (fi != 0) s += J[i * nv + k] * fi;
     }
@@ -481,12 +481,12 @@ __device__ __noinline__ double constraintUpdate_warp(const Env e, int nefc, int 
       double U[6];
       U[0] = jar[i] * mu;
       double TT = 0;
-      for (int j = 1; j < dim; j++) { U[j] = jar[i + j] * fri[j - 1]; TT += U[j] * U[j]; }
+      B2K_NOUNROLL for (int j = 1; j < dim; j++) { U[j] = jar[i + j] * fri[j - 1]; TT += U[j] * U[j]; }
       const double N = U[0], T = sqrt(TT);
       if ((N >= mu * T) || (T <= 0 && N >= 0)) {
-        for (int j = 0; j < dim; j++) { P.force[i + j] = 0; P.state[i + j] = B2MJ_CSTATE_SATISFIED; }
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) { P.force[i + j] = 0; P.state[i + j] = B2MJ_CSTATE_SATISFIED; }
       } else if ((mu * N + T <= 0) || (T <= 0 && N < 0)) {
-        for (int j = 0; j < dim; j++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
           const double x = jar[i + j];
           P.force[i + j] = -P.D[i + j] * x;
           P.state[i + j] = B2MJ_CSTATE_QUADRATIC;
@@ -498,15 +498,15 @@ __device__ __noinline__ double constraintUpdate_warp(const Env e, int nefc, int 
         s += 0.5 * Dm * NmT * NmT;
         const double f0 = -Dm * NmT * mu;
         P.force[i] = f0;
-        for (int j = 1; j < dim; j++) P.force[i + j] = -f0 / T * U[j] * fri[j - 1];
-        for (int j = 0; j < dim; j++) P.state[i + j] = B2MJ_CSTATE_CONE;
+        B2K_NOUNROLL for (int j = 1; j < dim; j++) P.force[i + j] = -f0 / T * U[j] * fri[j - 1];
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) P.state[i + j] = B2MJ_CSTATE_CONE;
         if (coneHessian) {
           double* H = cH + 36 * c;
           double g[6];
           g[0] = 0;
-          for (int j = 1; j < dim; j++) g[j] = U[j] * fri[j - 1] / T;
-          for (int a = 0; a < dim; a++)
-            for (int b = 0; b < dim; b++) {
+          B2K_NOUNROLL for (int j = 1; j < dim; j++) g[j] = U[j] * fri[j - 1] / T;
+          B2K_NOUNROLL for (int a = 0; a < dim; a++)
+            B2K_NOUNROLL for (int b = 0; b < dim; b++) {
               const double da = (a == 0 ? mu : -mu * g[a]), db = (b == 0 ? mu : -mu * g[b]);
               double h = Dm * da * db;
               if (a > 0 && b > 0) {

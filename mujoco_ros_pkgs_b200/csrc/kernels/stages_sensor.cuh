@@ -14,7 +14,7 @@ __device__ __forceinline__ void sens_cutoff(int i, double* out) {
   const double cutoff = m.sensor_cutoff[i];
   if (cutoff <= 0) return;
   const int dt = m.sensor_datatype[i];
-  for (int k = 0; k < m.sensor_dim[i]; k++) {
+  B2K_NOUNROLL for (int k = 0; k < m.sensor_dim[i]; k++) {
     if (dt == B2MJ_DATATYPE_REAL) out[k] = clampd(out[k], -cutoff, cutoff);
     else if (dt == B2MJ_DATATYPE_POSITIVE) out[k] = fmin(cutoff, out[k]);
   }
@@ -26,7 +26,7 @@ __device__ __forceinline__ void sens_frame(const Env e, int type, int id, const 
   const double* xquat = e.D(B2MJ_F_XQUAT);
   switch (type) {
     case B2MJ_OBJ_BODY:
-      *pos = e.D(B2MJ_F_XIPOS) + 3 * id; *mat = e.D(B2MJ_F_XIMAT) + 9 * id;
+      *pos = e.D(B2MJ_F_XIPOS) + 3 * id; *mat = e.DG(B2MJ_F_XIMAT) + 9 * id;
       mulQuat(quat, xquat + 4 * id, m.body_iquat + 4 * id);
       break;
     case B2MJ_OBJ_GEOM:
@@ -64,7 +64,7 @@ __device__ __forceinline__ void objAcceleration(const Env e, int type, int id, d
   sens_frame(e, type, id, &pos, &mat, q);
   const int b = sens_body(type, id);
   const double* com = e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b];
-  transformSpatial(res, e.D(B2MJ_F_CACC) + 6 * b, 0, pos, com, local ? mat : nullptr);
+  transformSpatial(res, e.DG(B2MJ_F_CACC) + 6 * b, 0, pos, com, local ? mat : nullptr);
   transformSpatial(vel, e.D(B2MJ_F_CVEL) + 6 * b, 0, pos, com, local ? mat : nullptr);
   cross(corr, vel, vel + 3);
   addTo3(res + 3, corr);
@@ -73,7 +73,7 @@ __device__ __forceinline__ void objAcceleration(const Env e, int type, int id, d
 __device__ __forceinline__ int findLimitRow(const Env e, int nefc, int want, int id) {
   const int* type = e.IG(B2MJ_F_EFC_TYPE);
   const int* eid = e.IG(B2MJ_F_EFC_ID);
-  for (int r = 0; r < nefc; r++)
+  B2K_NOUNROLL for (int r = 0; r < nefc; r++)
     if (type[r] == want && eid[r] == id) return r;
   return -1;
 }
@@ -140,11 +140,11 @@ __device__ __noinline__ void subtreeVel_lane0(const Env e) {
     double* linvel = e.X(XF_SUBTREE_LINVEL);
     double* angmom = e.X(XF_SUBTREE_ANGMOM);
     double* bodyvel = e.X(XF_BODYVEL);
-    const double* ximat = e.D(B2MJ_F_XIMAT);
+    const double* ximat = e.DG(B2MJ_F_XIMAT);
     const double* xipos = e.D(B2MJ_F_XIPOS);
     const double* com = e.D(B2MJ_F_SUBTREE_COM);
     const int nb = m.nbody;
-    for (int i = 0; i < nb; i++) {
+    B2K_NOUNROLL for (int i = 0; i < nb; i++) {
       objVelocity(e, B2MJ_OBJ_BODY, i, bodyvel + 6 * i, 0);
       scl3(linvel + 3 * i, bodyvel + 6 * i + 3, m.body_mass[i]);
       double dv[3];
@@ -242,10 +242,10 @@ __device__ __forceinline__ void contactForce(const Env e, int c, double* lfrc) {
   if (adr < 0) return;
   if (e.IG(B2MJ_F_EFC_TYPE)[adr] == B2MJ_CNSTR_CONTACT_PYRAMIDAL) {
     const double* mu = e.DG(B2MJ_F_CONTACT_FRICTION) + 5 * c;
-    for (int k = 0; k < 2 * (dim - 1); k++) lfrc[0] += f[adr + k];
-    for (int k = 1; k < dim; k++) lfrc[k] = (f[adr + 2 * (k - 1)] - f[adr + 2 * (k - 1) + 1]) * mu[k - 1];
+    B2K_NOUNROLL for (int k = 0; k < 2 * (dim - 1); k++) lfrc[0] += f[adr + k];
+    B2K_NOUNROLL for (int k = 1; k < dim; k++) lfrc[k] = (f[adr + 2 * (k - 1)] - f[adr + 2 * (k - 1) + 1]) * mu[k - 1];
   } else {
-    for (int k = 0; k < dim; k++) lfrc[k] = f[adr + k];
+    B2K_NOUNROLL for (int k = 0; k < dim; k++) lfrc[k] = f[adr + k];
   }
 }
 
@@ -259,9 +259,9 @@ __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* 
   const double* qvel = e.D(B2MJ_F_QVEL);
   const double* qacc = e.D(B2MJ_F_QACC);
   const double* com = e.D(B2MJ_F_SUBTREE_COM);
-  double* cacc = e.D(B2MJ_F_CACC);
-  double* cint = e.D(B2MJ_F_CFRC_INT);
-  double* cext = e.D(B2MJ_F_CFRC_EXT);
+  double* cacc = e.DG(B2MJ_F_CACC);
+  double* cint = e.DG(B2MJ_F_CFRC_INT);
+  double* cext = e.DG(B2MJ_F_CFRC_EXT);
   // external forces, one lane per body (contacts scanned in order => deterministic sums)
   FORL(b, m.nbody) {
     double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -277,7 +277,7 @@ __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* 
       const int* g1 = e.IG(B2MJ_F_CONTACT_GEOM1);
       const int* g2 = e.IG(B2MJ_F_CONTACT_GEOM2);
       const int* cadr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
-      for (int c = 0; c < ncon; c++) {
+      B2K_NOUNROLL for (int c = 0; c < ncon; c++) {
         if (cadr[c] < 0) continue;
         const int b1 = m.geom_bodyid[g1[c]], b2 = m.geom_bodyid[g2[c]];
         if (b1 != b && b2 != b) continue;
@@ -300,7 +300,7 @@ __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* 
     cint[e.lane] = 0;
   }
   WSYNC();
-  for (int l = 1; l < m.nlevel; l++) {
+  B2K_NOUNROLL for (int l = 1; l < m.nlevel; l++) {
     const int ladr = m.level_bodyadr[l], lnum = m.level_bodynum[l];
     FORL(k, lnum) {
       const int i = m.level_body[ladr + k];
@@ -364,7 +364,7 @@ __device__ __noinline__ void stage_sensorAcc(const Env e, int nefc, int ncon, co
         const int body = m.site_bodyid[objid];
         const int* g1 = e.IG(B2MJ_F_CONTACT_GEOM1);
         const int* g2 = e.IG(B2MJ_F_CONTACT_GEOM2);
-        for (int c = 0; c < ncon; c++) {
+        B2K_NOUNROLL for (int c = 0; c < ncon; c++) {
           if (e.IG(B2MJ_F_CONTACT_EFC_ADDRESS)[c] < 0) continue;
           const int b1 = m.geom_bodyid[g1[c]], b2 = m.geom_bodyid[g2[c]];
           if (b1 != body && b2 != body) continue;
@@ -381,7 +381,7 @@ __device__ __noinline__ void stage_sensorAcc(const Env e, int nefc, int ncon, co
       case B2MJ_SENS_TORQUE: {
         const int body = m.site_bodyid[objid];
         double f[6], dif[3], cr[3];
-        const double* w = e.D(B2MJ_F_CFRC_INT) + 6 * body;
+        const double* w = e.DG(B2MJ_F_CFRC_INT) + 6 * body;
         sub3(dif, e.D(B2MJ_F_SITE_XPOS) + 3 * objid, e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[body]);
         cross(cr, dif, w + 3);
         sub3(f, w, cr);

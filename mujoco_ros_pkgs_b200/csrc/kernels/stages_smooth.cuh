@@ -25,7 +25,7 @@ B2K_DI void rotQ(double* r, const double* v, const double* q) {
 
 // iterate the set bits of a multi-word mask: BODY is executed with `IDX` = bit index
 #define FOR_MASK_BITS(IDX, MASKPTR, NWORD, BODY)                \
-  for (int _w = 0; _w < (NWORD); _w++) {                        \
+  B2K_NOUNROLL for (int _w = 0; _w < (NWORD); _w++) {                        \
     unsigned _bits = (MASKPTR)[_w];                             \
     while (_bits) {                                             \
       const int IDX = (_w << 5) + __ffs(_bits) - 1;             \
@@ -44,10 +44,10 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
   double* xquat = e.D(B2MJ_F_XQUAT);
   double* xmat = e.D(B2MJ_F_XMAT);
   double* xipos = e.D(B2MJ_F_XIPOS);
-  double* ximat = e.D(B2MJ_F_XIMAT);
+  double* ximat = e.DG(B2MJ_F_XIMAT);
   double* xanchor = e.D(B2MJ_F_XANCHOR);
   double* xaxis = e.D(B2MJ_F_XAXIS);
-  double* T0 = e.X(XF_TLOC);
+  double* T0 = e.X(XF_SCRATCH);
   double* T1 = T0 + 7 * m.nbody;
   double* mocap_pos = m.nmocap ? e.D(B2MJ_F_MOCAP_POS) : nullptr;
   double* mocap_quat = m.nmocap ? e.D(B2MJ_F_MOCAP_QUAT) : nullptr;
@@ -74,7 +74,7 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
           copy3(p, m.body_pos + 3 * i);
           copy4(q, m.body_quat + 4 * i);
         }
-        for (int j = 0; j < jntnum; j++) {
+        B2K_NOUNROLL for (int j = 0; j < jntnum; j++) {
           const int jid = jntadr + j, jt = m.jnt_type[jid], qa = m.jnt_qposadr[jid];
           double anchor[3], axis[3];
           rotQ(axis, m.jnt_axis + 3 * jid, q);
@@ -103,7 +103,7 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
   // (B) pointer jumping: after round r, T[i] maps body i to the frame of its ancestor 2^(r+1) levels up
   double* src = T0;
   double* dst = T1;
-  for (int r = 0; r < m.njump; r++) {
+  B2K_NOUNROLL for (int r = 0; r < m.njump; r++) {
     const int* jump = m.body_jump + r * m.nbody;
     FORL(i, m.nbody) {
       const int a = jump[i];
@@ -136,11 +136,13 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
       double v[3], qi[4];
       rotVecMat(v, m.body_ipos + 3 * i, mat);
       add3(xipos + 3 * i, v, p);
-      mulQuat(qi, q, m.body_iquat + 4 * i);
-      quat2Mat(ximat + 9 * i, qi);
+      if (e.dump) {
+        mulQuat(qi, q, m.body_iquat + 4 * i);
+        quat2Mat(ximat + 9 * i, qi);
+      }
     } else {
       zero3(xipos);
-      for (int k = 0; k < 9; k++) ximat[k] = (k % 4 == 0) ? 1.0 : 0.0;
+      if (e.dump) for (int k = 0; k < 9; k++) ximat[k] = (k % 4 == 0) ? 1.0 : 0.0;
     }
   }
   WSYNC();
@@ -184,7 +186,7 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
 __device__ __noinline__ void stage_comPos(const Env e) {
   const DevModel& m = c_dm;
   const double* xipos = e.D(B2MJ_F_XIPOS);
-  const double* ximat = e.D(B2MJ_F_XIMAT);
+  const double* xquat = e.D(B2MJ_F_XQUAT);
   const double* xmat = e.D(B2MJ_F_XMAT);
   const double* xanchor = e.D(B2MJ_F_XANCHOR);
   const double* xaxis = e.D(B2MJ_F_XAXIS);
@@ -209,9 +211,11 @@ __device__ __noinline__ void stage_comPos(const Env e) {
   WSYNC();
   FORL(i, m.nbody) {
     if (i == 0) { for (int k = 0; k < 10; k++) cinert[k] = 0; continue; }
-    double off[3];
+    double off[3], qi[4], imat[9];
     sub3(off, xipos + 3 * i, com + 3 * m.body_rootid[i]);
-    inertCom(cinert + 10 * i, m.body_inertia + 3 * i, ximat + 9 * i, off, m.body_mass[i]);
+    mulQuat(qi, xquat + 4 * i, m.body_iquat + 4 * i);   // inertial frame recomputed: ximat is not kept on chip
+    quat2Mat(imat, qi);
+    inertCom(cinert + 10 * i, m.body_inertia + 3 * i, imat, off, m.body_mass[i]);
   }
   FORL(j, m.njnt) {
     const int da = 6 * m.jnt_dofadr[j], bi = m.jnt_bodyid[j];
@@ -255,7 +259,7 @@ __device__ __noinline__ void stage_tendon_transmission(const Env e) {
     WSYNC();
     FORL(i, m.ntendon) {
       double len = 0;
-      for (int w = m.tendon_adr[i]; w < m.tendon_adr[i] + m.tendon_num[i]; w++) {
+      B2K_NOUNROLL for (int w = m.tendon_adr[i]; w < m.tendon_adr[i] + m.tendon_num[i]; w++) {
         const int jid = m.wrap_objid[w];
         len += m.wrap_prm[w] * qpos[m.jnt_qposadr[jid]];
         tJ[i * nv + m.jnt_dofadr[jid]] = m.wrap_prm[w];
@@ -301,15 +305,15 @@ __device__ __noinline__ void factorLD2(const Env e, double* A, double* Bm, doubl
     if (d == 0) continue;
     const int Mkk = m.dof_Madr[k];
     const double inv = 1.0 / LD[Mkk];
-    for (int idx = sub; idx < d * d; idx += stride) {
+    B2K_NOUNROLL for (int idx = sub; idx < d * d; idx += stride) {
       const int a = idx / d, c = idx - a * d;
       if (c < d - a) LD[m.M_ancadr[Mkk + 1 + a] + c] -= LD[Mkk + 1 + a] * LD[Mkk + 1 + a + c] * inv;
     }
     WSYNC();
-    for (int c = sub; c < d; c += stride) LD[Mkk + 1 + c] *= inv;
+    B2K_NOUNROLL for (int c = sub; c < d; c += stride) LD[Mkk + 1 + c] *= inv;
     WSYNC();
   }
-  for (int i = sub; i < nv; i += stride) {
+  B2K_NOUNROLL for (int i = sub; i < nv; i += stride) {
     const double Dv = LD[m.dof_Madr[i]];
     if (half) dinvB[i] = 1.0 / Dv;
     else {
@@ -328,13 +332,13 @@ __device__ __noinline__ void invL2(const Env e, const double* LA, double* WA, co
   const int half = LB ? (e.lane >> 4) : 0, sub = LB ? (e.lane & 15) : e.lane, stride = LB ? 16 : 32;
   const double* LD = half ? LB : LA;
   double* W = half ? WB : WA;
-  for (int l = 1; l < m.ndoflevel; l++) {
+  B2K_NOUNROLL for (int l = 1; l < m.ndoflevel; l++) {
     const int adr0 = m.doflevel_adr[l], cnt = m.doflevel_adr[l + 1] - adr0;
-    for (int item = sub; item < cnt * l; item += stride) {
+    B2K_NOUNROLL for (int item = sub; item < cnt * l; item += stride) {
       const int i = m.doflevel_dof[adr0 + item / l], a = item % l;
       const int row = m.dof_Madr[i] + 1;
       double s = -LD[row + a];
-      for (int b = 0; b < a; b++) s -= LD[row + b] * W[m.M_ancadr[row + b] + (a - b)];
+      B2K_NOUNROLL for (int b = 0; b < a; b++) s -= LD[row + b] * W[m.M_ancadr[row + b] + (a - b)];
       W[row + a] = s;
     }
     WSYNC();
@@ -346,7 +350,7 @@ __device__ __forceinline__ void mulWT(const Env e, double* y, const double* W, c
   const DevModel& m = c_dm;
   FORL(k, m.nv) {
     double s = x[k];
-    for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
+    B2K_NOUNROLL for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
     y[k] = s;
   }
 }
@@ -356,14 +360,14 @@ __device__ __noinline__ void solveW_warp(const Env e, double* x, const double* W
   const DevModel& m = c_dm;
   FORL(k, m.nv) {
     double s = x[k];
-    for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
+    B2K_NOUNROLL for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
     tmp[k] = s * dinv[k];
   }
   WSYNC();
   FORL(i, m.nv) {
     const int row = m.dof_Madr[i] + 1, d = m.dof_nanc[i];
     double s = tmp[i];
-    for (int a = 0; a < d; a++) s += W[row + a] * tmp[m.M_col[row + a]];
+    B2K_NOUNROLL for (int a = 0; a < d; a++) s += W[row + a] * tmp[m.M_col[row + a]];
     x[i] = s;
   }
   WSYNC();
@@ -379,8 +383,8 @@ __device__ __forceinline__ void solveLD_lane(double* x, const double* LD, const 
     int adr = m.dof_Madr[i] + 1;
     for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) x[j] -= LD[adr++] * t;
   }
-  for (int i = 0; i < nv; i++) x[i] *= diaginv[i];
-  for (int i = 0; i < nv; i++) {
+  B2K_NOUNROLL for (int i = 0; i < nv; i++) x[i] *= diaginv[i];
+  B2K_NOUNROLL for (int i = 0; i < nv; i++) {
     int adr = m.dof_Madr[i] + 1;
     double xi = x[i];
     for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) xi -= LD[adr++] * x[j];
@@ -395,8 +399,8 @@ __device__ __noinline__ void mulM_warp(const Env e, double* res, const double* v
   FORL(i, m.nv) {
     const int row = m.dof_Madr[i], d = m.dof_nanc[i];
     double s = qM[row] * vec[i];
-    for (int a = 0; a < d; a++) s += qM[row + 1 + a] * vec[m.M_col[row + 1 + a]];
-    for (int p = m.dof_descadr[i]; p < m.dof_descadr[i + 1]; p++) s += qM[m.dof_desc_adr[p]] * vec[m.dof_desc_dof[p]];
+    B2K_NOUNROLL for (int a = 0; a < d; a++) s += qM[row + 1 + a] * vec[m.M_col[row + 1 + a]];
+    B2K_NOUNROLL for (int p = m.dof_descadr[i]; p < m.dof_descadr[i + 1]; p++) s += qM[m.dof_desc_adr[p]] * vec[m.dof_desc_dof[p]];
     res[i] = s;
   }
   WSYNC();
@@ -410,17 +414,17 @@ __device__ __noinline__ void invertSPD2(const Env e, double* A, double* Bm, int 
   const int half = e.lane >> 4, i = e.lane & 15;
   double* Mx = half ? Bm : A;
   const bool own = i < n && Mx != nullptr;
-  for (int k = 0; k < n; k++) {
+  B2K_NOUNROLL for (int k = 0; k < n; k++) {
     if (own && i != k) {
       const double p = 1.0 / Mx[k * n + k];
       const double f = Mx[i * n + k] * p;
-      for (int j = 0; j < n; j++) Mx[i * n + j] -= f * Mx[k * n + j];
+      B2K_NOUNROLL for (int j = 0; j < n; j++) Mx[i * n + j] -= f * Mx[k * n + j];
       Mx[i * n + k] = -f;
     }
     WSYNC();
     if (own && i == k) {
       const double p = 1.0 / Mx[k * n + k];
-      for (int j = 0; j < n; j++) Mx[k * n + j] *= p;
+      B2K_NOUNROLL for (int j = 0; j < n; j++) Mx[k * n + j] *= p;
       Mx[k * n + k] = p;
     }
     WSYNC();
@@ -431,7 +435,7 @@ __device__ __noinline__ void invertSPD2(const Env e, double* A, double* Bm, int 
 __device__ __forceinline__ void mulDense_warp(const Env e, double* out, const double* Ainv, const double* in, int n) {
   FORL(i, n) {
     double s = 0;
-    for (int j = 0; j < n; j++) s += Ainv[i * n + j] * in[j];
+    B2K_NOUNROLL for (int j = 0; j < n; j++) s += Ainv[i * n + j] * in[j];
     out[i] = s;
   }
   WSYNC();
@@ -444,10 +448,14 @@ __device__ __noinline__ void stage_crb_factor(const Env e, bool want_ld) {
   const double* cdof = e.D(B2MJ_F_CDOF);
   double* crb = e.D(B2MJ_F_CRB);
   double* qM = e.D(B2MJ_F_QM);
-  double* qLD = e.D(B2MJ_F_QLD);
-  double* buf = e.X(XF_DOFBUF);
+  double* qLD = e.DG(B2MJ_F_QLD);
+  double* buf = e.X(XF_SCRATCH) + 10 * 0;
   const bool damped = m.any_damping && !(m.opt.disableflags & B2MJ_DSBL_EULERDAMP) && m.opt.integrator == B2MJ_INT_EULER;
-  double* qH = damped ? e.X(XF_QH) : nullptr;
+  const bool dense = m.dense_small;
+  double* qH = (damped && (!dense || want_ld)) ? e.XG(XF_QH) : nullptr;
+  double* Minv = dense ? e.X(XF_MINV) : nullptr;
+  double* Hinv = (dense && damped) ? e.X(XF_HINV) : nullptr;
+  const int nvv = m.nv;
   FORL(b, m.nbody) {
     double s[10];
     for (int k = 0; k < 10; k++) s[k] = 0;
@@ -466,23 +474,18 @@ __device__ __noinline__ void stage_crb_factor(const Env e, bool want_ld) {
     double hv = v;
     if (i == j) { v += m.dof_armature[i]; hv = v + m.opt.timestep * m.dof_damping[i]; }
     qM[t] = v;
-    qLD[t] = v;
+    if (!dense || want_ld) qLD[t] = v;
     if (qH) qH[t] = hv;
+    if (dense) {
+      Minv[i * nvv + j] = v;
+      Minv[j * nvv + i] = v;
+      if (Hinv) { Hinv[i * nvv + j] = hv; Hinv[j * nvv + i] = hv; }
+    }
   }
   WSYNC();
-  if (m.dense_small) {
+  if (dense) {
     // dense inverses; the sparse L'DL factor is only produced when someone will read it (arena dump)
     const int nv = m.nv;
-    double* Minv = e.X(XF_MINV);
-    double* Hinv = qH ? e.X(XF_HINV) : nullptr;
-    FORL(t, m.nM) {
-      const int i = m.M_row[t], j = m.M_col[t];
-      const double v = qM[t];
-      Minv[i * nv + j] = v;
-      Minv[j * nv + i] = v;
-      if (Hinv) { const double hv = qH[t]; Hinv[i * nv + j] = hv; Hinv[j * nv + i] = hv; }
-    }
-    WSYNC();
     // entries between dofs of different branches are structural zeros of M
     FORL(item, nv * nv) {
       const int i = item / nv, j = item - i * nv;
@@ -494,8 +497,8 @@ __device__ __noinline__ void stage_crb_factor(const Env e, bool want_ld) {
     invertSPD2(e, Minv, Hinv, nv);
     if (!want_ld) return;
   }
-  factorLD2(e, qLD, qH, e.D(B2MJ_F_QLDIAGINV), e.D(B2MJ_F_QLDIAGSQRTINV), qH ? e.X(XF_QHDIAGINV) : nullptr);
-  invL2(e, qLD, e.X(XF_QW), qH, qH ? e.X(XF_QHW) : nullptr);
+  factorLD2(e, qLD, qH, e.DG(B2MJ_F_QLDIAGINV), e.DG(B2MJ_F_QLDIAGSQRTINV), qH ? e.XG(XF_QHDIAGINV) : nullptr);
+  invL2(e, qLD, e.XG(XF_QW), qH, qH ? e.XG(XF_QHW) : nullptr);
 }
 
 // out = inv(M) in  /  out = inv(M + h diag(damping)) in   (out != in)
@@ -504,19 +507,19 @@ __device__ __forceinline__ void solveM_warp(const Env e, double* out, const doub
   if (m.dense_small) { mulDense_warp(e, out, e.X(XF_MINV), in, m.nv); return; }
   FORL(i, m.nv) out[i] = in[i];
   WSYNC();
-  solveW_warp(e, out, e.X(XF_QW), e.D(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
+  solveW_warp(e, out, e.XG(XF_QW), e.DG(B2MJ_F_QLDIAGINV), e.X(XF_VEC0));
 }
 __device__ __forceinline__ void solveH_warp(const Env e, double* out, const double* in) {
   const DevModel& m = c_dm;
   if (m.dense_small) { mulDense_warp(e, out, e.X(XF_HINV), in, m.nv); return; }
   FORL(i, m.nv) out[i] = in[i];
   WSYNC();
-  solveW_warp(e, out, e.X(XF_QHW), e.X(XF_QHDIAGINV), e.X(XF_VEC0));
+  solveW_warp(e, out, e.XG(XF_QHW), e.XG(XF_QHDIAGINV), e.X(XF_VEC0));
 }
 
 __device__ __forceinline__ void mulDofVec(double* res, const double* dof, const double* vec, int n) {
   for (int k = 0; k < 6; k++) res[k] = 0;
-  for (int i = 0; i < n; i++)
+  B2K_NOUNROLL for (int i = 0; i < n; i++)
     for (int k = 0; k < 6; k++) res[k] += dof[6 * i + k] * vec[i];
 }
 
@@ -608,7 +611,7 @@ __device__ __noinline__ void stage_passive(const Env e) {
     const double* tl = e.D(B2MJ_F_TEN_LENGTH);
     const double* tv = e.D(B2MJ_F_TEN_VELOCITY);
     const double* tJ = e.D(B2MJ_F_TEN_J);
-    for (int i = 0; i < m.ntendon; i++) {
+    B2K_NOUNROLL for (int i = 0; i < m.ntendon; i++) {
       const double st = m.tendon_stiffness[i], dm = m.tendon_damping[i];
       if (st == 0 && dm == 0) continue;
       double frc = 0;
@@ -622,7 +625,7 @@ __device__ __noinline__ void stage_passive(const Env e) {
   }
   if (!(m.opt.disableflags & B2MJ_DSBL_GRAVITY)) {
     const double* xipos = e.D(B2MJ_F_XIPOS);
-    for (int i = 1; i < m.nbody; i++) {
+    B2K_NOUNROLL for (int i = 1; i < m.nbody; i++) {
       const double gc = m.body_gravcomp[i];
       if (gc == 0) continue;
       double force[3], torque[3] = {0, 0, 0};
@@ -642,7 +645,7 @@ __device__ __noinline__ void stage_rne_bias(const Env e) {
   const double* cvel = e.D(B2MJ_F_CVEL);
   const double* cinert = e.D(B2MJ_F_CINERT);
   const double* qvel = e.D(B2MJ_F_QVEL);
-  double* fb = e.X(XF_BODYBUF);
+  double* fb = e.X(XF_SCRATCH);
   double* bias = e.D(B2MJ_F_QFRC_BIAS);
   const bool grav = !(m.opt.disableflags & B2MJ_DSBL_GRAVITY);
   FORL(b, m.nbody) {
@@ -680,7 +683,7 @@ __device__ __noinline__ void stage_velocity_head(const Env e) {
     double* tv = e.D(B2MJ_F_TEN_VELOCITY);
     FORL(i, m.ntendon) {
       double s = 0;
-      for (int k = 0; k < nv; k++) s += tJ[i * nv + k] * qvel[k];
+      B2K_NOUNROLL for (int k = 0; k < nv; k++) s += tJ[i * nv + k] * qvel[k];
       tv[i] = s;
     }
   }
@@ -689,7 +692,7 @@ __device__ __noinline__ void stage_velocity_head(const Env e) {
     double* av = e.D(B2MJ_F_ACTUATOR_VELOCITY);
     FORL(i, m.nu) {
       double s = 0;
-      for (int k = 0; k < nv; k++) s += am[i * nv + k] * qvel[k];
+      B2K_NOUNROLL for (int k = 0; k < nv; k++) s += am[i * nv + k] * qvel[k];
       av[i] = s;
     }
   }
@@ -747,7 +750,7 @@ __device__ __noinline__ void stage_actuation(const Env e, int* warning) {
   WSYNC();
   FORL(k, nv) {
     double s = 0;
-    for (int i = 0; i < nu; i++) s += am[i * nv + k] * af[i];
+    B2K_NOUNROLL for (int i = 0; i < nu; i++) s += am[i * nv + k] * af[i];
     qa[k] = s;
   }
   WSYNC();
@@ -772,7 +775,7 @@ __device__ __noinline__ void stage_acceleration(const Env e, const double* xfrc)
   WSYNC();
   if (xfrc) {
     const double* xipos = e.D(B2MJ_F_XIPOS);
-    for (int i = 1; i < m.nbody; i++) {
+    B2K_NOUNROLL for (int i = 1; i < m.nbody; i++) {
       const double* x = xfrc + 6 * i;
       if (x[0] == 0 && x[1] == 0 && x[2] == 0 && x[3] == 0 && x[4] == 0 && x[5] == 0) continue;
       applyFT_warp(e, x, x + 3, xipos + 3 * i, i, qs);

@@ -32,8 +32,8 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
   const int nv = m.nv;
   const double* J = e.DG(B2MJ_F_EFC_J);
   const double* R = e.DG(B2MJ_F_EFC_R);
-  const double* W = e.X(XF_QW);
-  const double* dinv = e.D(B2MJ_F_QLDIAGINV);
+  const double* W = e.XG(XF_QW);
+  const double* dinv = e.DG(B2MJ_F_QLDIAGINV);
   double* G = e.XG(XF_EFC_MINVJT);
   const bool dense = m.dense_small;
   if (dense) {
@@ -43,7 +43,7 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
       const int i = item / nv, k = item - i * nv;
       const double* Ji = J + i * nv;
       double s = 0;
-      for (int j = 0; j < nv; j++) s += Ji[j] * Minv[j * nv + k];
+      B2K_NOUNROLL for (int j = 0; j < nv; j++) s += Ji[j] * Minv[j * nv + k];
       G[item] = s;
     }
   } else {
@@ -51,7 +51,7 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
       const int i = item / nv, k = item - i * nv;
       const double* Ji = J + i * nv;
       double s = Ji[k];
-      for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * Ji[m.dof_desc_dof[p]];
+      B2K_NOUNROLL for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * Ji[m.dof_desc_dof[p]];
       G[item] = s;
     }
   }
@@ -60,12 +60,12 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
   if (nefc <= B2K_PGS_REGROWS) {
     double* AR = arPtr(e, nefc);
     // lower triangle incl. diagonal, mirrored
-    for (int item = e.lane; item < nefc * nefc; item += 32) {
+    B2K_NOUNROLL for (int item = e.lane; item < nefc * nefc; item += 32) {
       const int i = item / nefc, j = item - i * nefc;
       if (j > i) continue;
       double s = 0;
-      if (dense) { for (int k = 0; k < nv; k++) s += G[i * nv + k] * J[j * nv + k]; }
-      else { for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[j * nv + k] * dinv[k]; }
+      if (dense) { B2K_NOUNROLL for (int k = 0; k < nv; k++) s += G[i * nv + k] * J[j * nv + k]; }
+      else { B2K_NOUNROLL for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[j * nv + k] * dinv[k]; }
       if (i == j) { s += R[i]; ard[i] = s; }
       AR[i * nefc + j] = s;
       AR[j * nefc + i] = s;
@@ -89,8 +89,8 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
   } else {
     FORL(i, nefc) {
       double s = 0;
-      if (dense) { for (int k = 0; k < nv; k++) s += G[i * nv + k] * J[i * nv + k]; }
-      else { for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[i * nv + k] * dinv[k]; }
+      if (dense) { B2K_NOUNROLL for (int k = 0; k < nv; k++) s += G[i * nv + k] * J[i * nv + k]; }
+      else { B2K_NOUNROLL for (int k = 0; k < nv; k++) s += G[i * nv + k] * G[i * nv + k] * dinv[k]; }
       ard[i] = s + R[i];
     }
   }
@@ -107,59 +107,59 @@ __device__ __forceinline__ double rowDot(const Env e, const double* row, const d
 // small SPD solve helpers for the elliptic QCQP (n <= 5), executed redundantly by every lane
 __device__ __forceinline__ int cholFactorSmall(double* A, int n, double mindiag) {
   int bad = 0;
-  for (int j = 0; j < n; j++) {
+  B2K_NOUNROLL for (int j = 0; j < n; j++) {
     double s = A[j * n + j];
-    for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
+    B2K_NOUNROLL for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
     if (s < mindiag) { s = mindiag; bad++; }
     const double ljj = sqrt(s);
     A[j * n + j] = ljj;
     const double inv = 1 / ljj;
-    for (int i = j + 1; i < n; i++) {
+    B2K_NOUNROLL for (int i = j + 1; i < n; i++) {
       double t = A[i * n + j];
-      for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
+      B2K_NOUNROLL for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
       A[i * n + j] = t * inv;
     }
   }
   return bad;
 }
 __device__ __forceinline__ void cholSolveSmall(double* x, const double* L, const double* b, int n) {
-  for (int i = 0; i < n; i++) {
+  B2K_NOUNROLL for (int i = 0; i < n; i++) {
     double t = b[i];
-    for (int k = 0; k < i; k++) t -= L[i * n + k] * x[k];
+    B2K_NOUNROLL for (int k = 0; k < i; k++) t -= L[i * n + k] * x[k];
     x[i] = t / L[i * n + i];
   }
   for (int i = n - 1; i >= 0; i--) {
     double t = x[i];
-    for (int k = i + 1; k < n; k++) t -= L[k * n + i] * x[k];
+    B2K_NOUNROLL for (int k = i + 1; k < n; k++) t -= L[k * n + i] * x[k];
     x[i] = t / L[i * n + i];
   }
 }
 __device__ __noinline__ int QCQP(double* res, const double* Ain, const double* bin, const double* d, double r, int n) {
   double A[25], b[5], P[25], y[5], z[5], nb[5];
-  for (int i = 0; i < n; i++) {
+  B2K_NOUNROLL for (int i = 0; i < n; i++) {
     b[i] = bin[i] * d[i];
     y[i] = 0;
-    for (int j = 0; j < n; j++) A[i * n + j] = Ain[i * n + j] * d[i] * d[j];
+    B2K_NOUNROLL for (int j = 0; j < n; j++) A[i * n + j] = Ain[i * n + j] * d[i] * d[j];
   }
   double la = 0;
   const double r2 = r * r;
   for (int iter = 0; iter < 20; iter++) {
-    for (int i = 0; i < n * n; i++) P[i] = A[i];
-    for (int i = 0; i < n; i++) P[i * n + i] += la;
-    if (cholFactorSmall(P, n, 1e-10)) { la = 0; for (int i = 0; i < n; i++) y[i] = 0; break; }
-    for (int i = 0; i < n; i++) nb[i] = -b[i];
+    B2K_NOUNROLL for (int i = 0; i < n * n; i++) P[i] = A[i];
+    B2K_NOUNROLL for (int i = 0; i < n; i++) P[i * n + i] += la;
+    if (cholFactorSmall(P, n, 1e-10)) { la = 0; B2K_NOUNROLL for (int i = 0; i < n; i++) y[i] = 0; break; }
+    B2K_NOUNROLL for (int i = 0; i < n; i++) nb[i] = -b[i];
     cholSolveSmall(y, P, nb, n);
     double val = -r2;
-    for (int i = 0; i < n; i++) val += y[i] * y[i];
+    B2K_NOUNROLL for (int i = 0; i < n; i++) val += y[i] * y[i];
     if (val < 1e-10) break;
     cholSolveSmall(z, P, y, n);
     double deriv = 0;
-    for (int i = 0; i < n; i++) deriv += -2 * y[i] * z[i];
+    B2K_NOUNROLL for (int i = 0; i < n; i++) deriv += -2 * y[i] * z[i];
     const double delta = -val / deriv;
     if (delta < 1e-10) break;
     la += delta;
   }
-  for (int i = 0; i < n; i++) res[i] = y[i] * d[i];
+  B2K_NOUNROLL for (int i = 0; i < n; i++) res[i] = y[i] * d[i];
   return la != 0;
 }
 
@@ -174,61 +174,64 @@ __device__ __forceinline__ double rowDotW(const Env e, const double* a, const do
 // elliptic-cone block update shared by both PGS forms: given the dim x dim block Athis of AR, the block
 // residual res and the old forces, produce the new forces f (ray update, then QCQP on the friction dims)
 __device__ __noinline__ void pgsConeBlock(int dim, const double* Athis, const double* res, const double* oldf, const double* fri, double* f) {
-  for (int j = 0; j < dim; j++) f[j] = oldf[j];
+  B2K_NOUNROLL for (int j = 0; j < dim; j++) f[j] = oldf[j];
   if (f[0] < B2K_MINVAL) {
     f[0] -= res[0] / Athis[0];
     if (f[0] < 0) f[0] = 0;
-    for (int j = 1; j < dim; j++) f[j] = 0;
+    B2K_NOUNROLL for (int j = 1; j < dim; j++) f[j] = 0;
   } else {
     double v[6], v1[6];
-    for (int j = 0; j < dim; j++) v[j] = f[j];
+    B2K_NOUNROLL for (int j = 0; j < dim; j++) v[j] = f[j];
     double denom = 0, num = 0;
-    for (int j = 0; j < dim; j++) {
+    B2K_NOUNROLL for (int j = 0; j < dim; j++) {
       double s = 0;
-      for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * v[k];
+      B2K_NOUNROLL for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * v[k];
       v1[j] = s;
     }
-    for (int j = 0; j < dim; j++) { denom += v[j] * v1[j]; num += v[j] * res[j]; }
+    B2K_NOUNROLL for (int j = 0; j < dim; j++) { denom += v[j] * v1[j]; num += v[j] * res[j]; }
     if (denom >= B2K_MINVAL) {
       double x = -num / denom;
       if (f[0] + x * v[0] < 0) x = -v[0] / f[0];
-      for (int j = 0; j < dim; j++) f[j] += x * v[j];
+      B2K_NOUNROLL for (int j = 0; j < dim; j++) f[j] += x * v[j];
     }
   }
   if (f[0] < B2K_MINVAL) {
-    for (int j = 1; j < dim; j++) f[j] = 0;
+    B2K_NOUNROLL for (int j = 1; j < dim; j++) f[j] = 0;
   } else {
     double Ac[25], bc[5], v[5];
-    for (int j = 0; j < dim - 1; j++) {
-      for (int k = 0; k < dim - 1; k++) Ac[j * (dim - 1) + k] = Athis[(j + 1) * dim + k + 1];
+    B2K_NOUNROLL for (int j = 0; j < dim - 1; j++) {
+      B2K_NOUNROLL for (int k = 0; k < dim - 1; k++) Ac[j * (dim - 1) + k] = Athis[(j + 1) * dim + k + 1];
       double t = res[j + 1];
-      for (int k = 0; k < dim; k++) t -= Athis[(j + 1) * dim + k] * oldf[k];
+      B2K_NOUNROLL for (int k = 0; k < dim; k++) t -= Athis[(j + 1) * dim + k] * oldf[k];
       t += Athis[(j + 1) * dim] * f[0];
       bc[j] = t;
     }
     const int active = QCQP(v, Ac, bc, fri, f[0], dim - 1);
     if (active) {
       double s = 0;
-      for (int j = 0; j < dim - 1; j++) s += (v[j] / fri[j]) * (v[j] / fri[j]);
+      B2K_NOUNROLL for (int j = 0; j < dim - 1; j++) s += (v[j] / fri[j]) * (v[j] / fri[j]);
       s = sqrt(f[0] * f[0] / fmax(B2K_MINVAL, s));
-      for (int j = 0; j < dim - 1; j++) v[j] *= s;
+      B2K_NOUNROLL for (int j = 0; j < dim - 1; j++) v[j] *= s;
     }
-    for (int j = 0; j < dim - 1; j++) f[1 + j] = v[j];
+    B2K_NOUNROLL for (int j = 0; j < dim - 1; j++) f[1 + j] = v[j];
   }
 }
 
 // mj_solPGS on the explicit AR with register-resident residuals (nefc <= 32, or <= 64 with TWO).
 // force holds the (already accepted) warm start on entry.  Per row: the row constants {1/A_ii, A_ii, lo,
-// hi} come from one broadcast shared-memory read, the residual and the old force from two shuffles, the
-// projection is a branch-free clamp, and every lane folds the force change into its own residual with
-// one FMA.  Returns iterations used.
-template <bool TWO>
-__device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* AR, const double* rowc) {
+// hi} come from one broadcast read, the residual and the old force from two shuffles, the projection is a
+// clamp, and every lane folds the force change into its own residual with one FMA.  SM = AR and the row
+// constants live in the shared-memory window (addresses formed from the shared symbol -> LDS), else in the
+// env's HBM/L2 arena.  Returns iterations used.
+template <bool TWO, bool SM>
+__device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* ARg, unsigned ARs) {
   const DevModel& m = c_dm;
+  const double* AR = SM ? reinterpret_cast<const double*>(b2k_smem + ARs) : ARg;
+  const double* rowc = AR + nefc * nefc;
   EfcPtrs P = efcPtrs(e);
-  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
-  const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
   const double scale = 1 / (m.meaninertia * max(1, m.nv));
+  const double tol = m.opt.tolerance;
+  const int maxiter = m.opt.iterations;
   const int lane = e.lane;
   const int j0 = lane, j1 = lane + 32;
   const int c0 = min(j0, nefc - 1), c1 = min(j1, nefc - 1);  // clamped column indices for AR row reads
@@ -236,73 +239,87 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
   if (j0 < nefc) {
     f0 = P.force[j0];
     double s = P.b[j0];
-    for (int k = 0; k < nefc; k++) s += AR[j0 * nefc + k] * P.force[k];
+    B2K_NOUNROLL for (int k = 0; k < nefc; k++) s += AR[j0 * nefc + k] * P.force[k];
     r0 = s;
   }
   if (TWO && j1 < nefc) {
     f1 = P.force[j1];
     double s = P.b[j1];
-    for (int k = 0; k < nefc; k++) s += AR[j1 * nefc + k] * P.force[k];
+    B2K_NOUNROLL for (int k = 0; k < nefc; k++) s += AR[j1 * nefc + k] * P.force[k];
     r1 = s;
   }
   int iter = 0;
-  while (iter < m.opt.iterations) {
+  while (iter < maxiter) {
     double improvement = 0;
+    const double* rc = rowc;
+    const double* arow = AR;
     for (int i = 0; i < nefc;) {
-      const int src = i & 31;
-      const bool hi = TWO && i >= 32;
-      const double iA = rowc[4 * i];
-      if (iA >= 0) {  // scalar row (1/A_ii is stored negated for the rows of an elliptic cone)
-        const double Aii = rowc[4 * i + 1], lo = rowc[4 * i + 2], up = rowc[4 * i + 3];
-        const double arow0 = AR[i * nefc + c0];
-        const double arow1 = TWO ? AR[i * nefc + c1] : 0.0;
-        const double res = __shfl_sync(0xffffffffu, hi ? r1 : r0, src);
-        const double fold = __shfl_sync(0xffffffffu, hi ? f1 : f0, src);
-        double f = fmin(fmax(fold - res * iA, lo), up);
+      const double iA = rc[0];
+      if (!(iA < 0)) {  // scalar row (1/A_ii is stored negated for the rows of an elliptic cone; NaN stays here)
+        const double Aii = rc[1], lo = rc[2], up = rc[3];
+        const double a0 = arow[c0];
+        const double a1 = TWO ? arow[c1] : 0.0;
+        double res, fold;
+        if (TWO && i >= 32) {
+          res = __shfl_sync(0xffffffffu, r1, i - 32);
+          fold = __shfl_sync(0xffffffffu, f1, i - 32);
+        } else {
+          res = __shfl_sync(0xffffffffu, r0, i);
+          fold = __shfl_sync(0xffffffffu, f0, i);
+        }
+        double f = fold - res * iA;
+        f = f < lo ? lo : f;
+        f = f > up ? up : f;
         double delta = f - fold;
         double change = delta * (0.5 * delta * Aii + res);
-        if (change > 1e-10) { delta = 0; change = 0; f = fold; }
+        if (change > 1e-10) { delta = 0; change = 0; f = fold; }  // cost guard of mj_solPGS (uniform branch)
         improvement -= change;
-        r0 += arow0 * delta;
-        if (TWO) r1 += arow1 * delta;
-        if (lane == src) { if (hi) f1 = f; else f0 = f; }
+        r0 += a0 * delta;
+        if (TWO) r1 += a1 * delta;
+        if (TWO && i >= 32) { if (lane == i - 32) f1 = f; }
+        else if (lane == i) f0 = f;
         i += 1;
+        rc += 4;
+        arow += nefc;
       } else {
-        const int c = P.id[i], dim = c_dim[c];
+        const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+        const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
+        const int c = P.id[i], dim = min(max(c_dim[c], 1), 6);
         const double* fri = c_fri + 5 * c;
         double Athis[36], res[6], oldf[6], f[6];
-        for (int j = 0; j < dim; j++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
           const int row = i + j, rs = row & 31;
           const bool rh = TWO && row >= 32;
-          for (int k = 0; k < dim; k++) Athis[j * dim + k] = AR[row * nefc + i + k];
+          B2K_NOUNROLL for (int k = 0; k < dim; k++) Athis[j * dim + k] = AR[row * nefc + i + k];
           oldf[j] = __shfl_sync(0xffffffffu, rh ? f1 : f0, rs);
           res[j] = __shfl_sync(0xffffffffu, rh ? r1 : r0, rs);
         }
         pgsConeBlock(dim, Athis, res, oldf, fri, f);
         double change = 0, delta[6];
-        for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
-        for (int j = 0; j < dim; j++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
           double s = 0;
-          for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * delta[k];
+          B2K_NOUNROLL for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * delta[k];
           change += 0.5 * delta[j] * s + delta[j] * res[j];
         }
         if (change > 1e-10) {
           change = 0;
-          for (int j = 0; j < dim; j++) { delta[j] = 0; f[j] = oldf[j]; }
+          B2K_NOUNROLL for (int j = 0; j < dim; j++) { delta[j] = 0; f[j] = oldf[j]; }
         }
         improvement -= change;
-        for (int j = 0; j < dim; j++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
           const int row = i + j;
           r0 += AR[row * nefc + c0] * delta[j];
           if (TWO) r1 += AR[row * nefc + c1] * delta[j];
           if (lane == (row & 31)) { if (TWO && row >= 32) f1 = f[j]; else f0 = f[j]; }
         }
         i += dim;
+        rc += 4 * dim;
+        arow += nefc * dim;
       }
     }
-    improvement *= scale;
     iter++;
-    if (improvement < m.opt.tolerance) break;
+    if (improvement * scale < tol) break;
   }
   if (j0 < nefc) P.force[j0] = f0;
   if (TWO && j1 < nefc) P.force[j1] = f1;
@@ -321,13 +338,13 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
   // sparse models: AR = G diag(1/D) G' (G = J inv(L));  dense small models: AR = G J' (G = J inv(M))
   const bool dense = m.dense_small;
   const double* U = dense ? P.J : G;
-  const double* dinv = dense ? nullptr : e.D(B2MJ_F_QLDIAGINV);
+  const double* dinv = dense ? nullptr : e.DG(B2MJ_F_QLDIAGINV);
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
   const double scale = 1 / (m.meaninertia * max(1, nv));
   FORL(k, nv) {
     double s = 0;
-    for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
+    B2K_NOUNROLL for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
     avec[k] = dinv ? s * dinv[k] : s;
   }
   WSYNC();
@@ -361,8 +378,8 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
         const int c = P.id[i], dim = c_dim[c];
         const double* fri = c_fri + 5 * c;
         double Athis[36], res[6], oldf[6], f[6];
-        for (int j = 0; j < dim; j++) {
-          for (int k = 0; k < dim; k++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
+          B2K_NOUNROLL for (int k = 0; k < dim; k++) {
             double v = rowDotW(e, G + (i + j) * nv, U + (i + k) * nv, dinv, nv);
             if (j == k) v += P.R[i + j];
             Athis[j * dim + k] = v;
@@ -372,18 +389,18 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
         }
         pgsConeBlock(dim, Athis, res, oldf, fri, f);
         double change = 0, delta[6];
-        for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
-        for (int j = 0; j < dim; j++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
           double s = 0;
-          for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * delta[k];
+          B2K_NOUNROLL for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * delta[k];
           change += 0.5 * delta[j] * s + delta[j] * res[j];
         }
         if (change > 1e-10) {
           change = 0;
-          for (int j = 0; j < dim; j++) { delta[j] = 0; f[j] = oldf[j]; }
+          B2K_NOUNROLL for (int j = 0; j < dim; j++) { delta[j] = 0; f[j] = oldf[j]; }
         }
         improvement -= change;
-        for (int j = 0; j < dim; j++) {
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
           if (delta[j] != 0) FORL(k, nv) avec[k] += delta[j] * U[(i + j) * nv + k] * (dinv ? dinv[k] : 1.0);
         }
         if (e.lane < dim) P.force[i + e.lane] = f[e.lane];
@@ -407,7 +424,7 @@ __device__ __forceinline__ void mulJacVec_warp(const Env e, int nefc, double* re
   const double* J = e.DG(B2MJ_F_EFC_J);
   FORL(i, nefc) {
     double s = 0;
-    for (int k = 0; k < nv; k++) s += J[i * nv + k] * vec[k];
+    B2K_NOUNROLL for (int k = 0; k < nv; k++) s += J[i * nv + k] * vec[k];
     res[i] = s;
   }
   WSYNC();
@@ -421,14 +438,14 @@ __device__ __forceinline__ double dot_warp(const Env e, const double* a, const d
 
 // in-place dense Cholesky (lower) of the nv x nv Hessian; invd[j] = 1 / L[j][j]
 __device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* invd, int n, double mindiag) {
-  for (int j = 0; j < n; j++) {
+  B2K_NOUNROLL for (int j = 0; j < n; j++) {
     double s = A[j * n + j];
-    for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
+    B2K_NOUNROLL for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
     if (s < mindiag) s = mindiag;
     const double ljj = sqrt(s), inv = 1 / ljj;
-    for (int i = j + 1 + e.lane; i < n; i += 32) {
+    B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += 32) {
       double t = A[i * n + j];
-      for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
+      B2K_NOUNROLL for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
       A[i * n + j] = t * inv;
     }
     WSYNC();
@@ -443,7 +460,7 @@ __device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double
   double t[B2K_CHOL_SLOTS];
 #pragma unroll
   for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + 32 * s; t[s] = k < n ? b[k] : 0.0; }
-  for (int i = 0; i < n; i++) {  // L y = b
+  B2K_NOUNROLL for (int i = 0; i < n; i++) {  // L y = b
     double ti = 0;
 #pragma unroll
     for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i >> 5) == s) ti = __shfl_sync(0xffffffffu, t[s], i & 31);
@@ -516,22 +533,22 @@ __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* cH = c.cone ? e.XG(XF_CONTACT_H) : nullptr;
   // one lane per lower-triangle entry (i, j <= i)
-  for (int item = e.lane; item < nv * nv; item += 32) {
+  B2K_NOUNROLL for (int item = e.lane; item < nv * nv; item += 32) {
     const int i = item / nv, j = item - i * nv;
     if (j > i) continue;
     double s = H[item];
-    for (int r = 0; r < nefc; r++) {
+    B2K_NOUNROLL for (int r = 0; r < nefc; r++) {
       const int st = P.state[r];
       if (st == B2MJ_CSTATE_QUADRATIC) {
         s += P.D[r] * P.J[r * nv + i] * P.J[r * nv + j];
       } else if (st == B2MJ_CSTATE_CONE) {
         const int con = P.id[r], dim = c_dim[con];
         const double* Hc = cH + 36 * con;
-        for (int a = 0; a < dim; a++) {
+        B2K_NOUNROLL for (int a = 0; a < dim; a++) {
           const double Ja = P.J[(r + a) * nv + i];
           if (Ja == 0) continue;
           double u = 0;
-          for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + j];
+          B2K_NOUNROLL for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + j];
           s += Ja * u;
         }
         r += dim - 1;
@@ -598,7 +615,7 @@ __device__ __noinline__ LSPoint primalEval(const Env e, const PrimalCtx& c, doub
       const double* fri = c_fri + 5 * con;
       const double U0 = c.Jaref[i] * mu, V0 = c.Jv[i] * mu;
       double UU = 0, UV = 0, VV = 0;
-      for (int j = 1; j < dim; j++) {
+      B2K_NOUNROLL for (int j = 1; j < dim; j++) {
         const double U = c.Jaref[i + j] * fri[j - 1], V = c.Jv[i + j] * fri[j - 1];
         UU += U * U; UV += U * V; VV += V * V;
       }
@@ -621,7 +638,7 @@ __device__ __noinline__ LSPoint primalEval(const Env e, const PrimalCtx& c, doub
         }
       }
       if (bottom)
-        for (int j = 0; j < dim; j++) { q0 += qi[3 * j]; q1 += qi[3 * j + 1]; q2 += qi[3 * j + 2]; }
+        B2K_NOUNROLL for (int j = 0; j < dim; j++) { q0 += qi[3 * j]; q1 += qi[3 * j + 1]; q2 += qi[3 * j + 2]; }
     } else {
       if (x < 0) { q0 += qi[0]; q1 += qi[1]; q2 += qi[2]; }
     }
@@ -671,7 +688,7 @@ __device__ __noinline__ double primalSearch(const Env e, PrimalCtx& c) {
     if (a2 > lo && a2 < hi) cand[nc++] = a2;
     cand[nc++] = 0.5 * (lo + hi);
     bool moved = false;
-    for (int k = 0; k < nc; k++) {
+    B2K_NOUNROLL for (int k = 0; k < nc; k++) {
       const LSPoint pc = primalEval(e, c, cand[k]);
       if (fabs(pc.d0) < gtol) return pc.alpha;
       if (pc.d0 * dir < 0) {
@@ -763,7 +780,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
   // efc_b = J qacc_smooth - aref
   FORL(i, nefc) {
     double s = 0;
-    for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qas[k];
+    B2K_NOUNROLL for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qas[k];
     P.b[i] = s - P.aref[i];
   }
   WSYNC();
@@ -773,12 +790,12 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
     double* jar = e.XG(XF_EFC_JAREF);
     double* avec = e.X(XF_VEC1);
     const double* G = e.XG(XF_EFC_MINVJT);
-    const double* dinv = e.D(B2MJ_F_QLDIAGINV);
+    const double* dinv = e.DG(B2MJ_F_QLDIAGINV);
     const bool reg = nefc <= B2K_PGS_REGROWS;
     if (warmstart) {
       FORL(i, nefc) {
         double s = 0;
-        for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * warm[k];
+        B2K_NOUNROLL for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * warm[k];
         jar[i] = s - P.aref[i];
       }
       WSYNC();
@@ -789,20 +806,20 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
         const double* AR = arPtr(e, nefc);
         FORL(i, nefc) {
           double s = 0;
-          for (int k = 0; k < nefc; k++) s += AR[i * nefc + k] * P.force[k];
+          B2K_NOUNROLL for (int k = 0; k < nefc; k++) s += AR[i * nefc + k] * P.force[k];
           cost += P.force[i] * (0.5 * s + P.b[i]);
         }
       } else {
         const double* U = m.dense_small ? P.J : G;
         FORL(k, nv) {
           double s = 0;
-          for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
+          B2K_NOUNROLL for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
           avec[k] = m.dense_small ? s : s * dinv[k];
         }
         WSYNC();
         FORL(i, nefc) {
           double s = 0;
-          for (int k = 0; k < nv; k++) s += G[i * nv + k] * avec[k];
+          B2K_NOUNROLL for (int k = 0; k < nv; k++) s += G[i * nv + k] * avec[k];
           cost += P.force[i] * (0.5 * (s + P.R[i] * P.force[i]) + P.b[i]);
         }
       }
@@ -815,8 +832,12 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
       WSYNC();
     }
     if (reg) {
-      const double* AR = arPtr(e, nefc);
-      iters = nefc <= 32 ? solvePGS_regT<false>(e, nefc, AR, AR + nefc * nefc) : solvePGS_regT<true>(e, nefc, AR, AR + nefc * nefc);
+      const bool sm = nefc * (nefc + 4) <= m.xsize[XF_EFC_AR_S];
+      const unsigned soff = e.sbd + 8u * (unsigned)m.xoff_s[XF_EFC_AR_S];
+      const double* ARg = e.XG(XF_EFC_AR);
+      if (sm) iters = solvePGS_regT<false, true>(e, nefc, nullptr, soff);   // window holds <= 17 rows
+      else if (nefc <= 32) iters = solvePGS_regT<false, false>(e, nefc, ARg, 0);
+      else iters = solvePGS_regT<true, false>(e, nefc, ARg, 0);
     } else {
       iters = solvePGS_free(e, nefc, avec);
     }

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "dev_model.h"
 #include "env_ctx.cuh"
 #include "stages_collision.cuh"
@@ -74,7 +76,7 @@ __device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int e
     stage_kinematics(e); PROF_MARK(PROF_KINEMATICS)
     stage_comPos(e); PROF_MARK(PROF_COMPOS)
     stage_tendon_transmission(e); PROF_MARK(PROF_TENDON)
-    stage_crb_factor(e, a.dump != 0 || a.mode == MODE_STEP_BEGIN); PROF_MARK(PROF_CRB_FACTOR)
+    stage_crb_factor(e, e.dump != 0); PROF_MARK(PROF_CRB_FACTOR)
     sc.ncon = stage_collision(e, warning); PROF_MARK(PROF_COLLISION)
     sc.nefc = stage_makeConstraint(e, sc.ncon, warning); PROF_MARK(PROF_MAKECONSTRAINT)
     if (m.opt.solver == B2MJ_SOL_PGS) stage_projectConstraint(e, sc.nefc);
@@ -171,135 +173,197 @@ __device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env
   advance_warp(e, dX + 2 * nv, dX + nv, dX);
 }
 
-__global__ void __launch_bounds__(B2K_MAX_THREADS) b2k_step_kernel(const LaunchArgs a) {
+__global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel(const LaunchArgs a) {
   const DevModel& m = c_dm;
   unsigned char* const smem_raw = b2k_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int env = blockIdx.x * nwarp + warp;
-  if (env >= a.nenv) return;  // whole warp exits; no CTA-wide barrier is used below
 
   // shared layout: [nwarp mbarriers, 16B each][nwarp env blocks: doubles | ints]
   const size_t env_bytes = (((size_t)m.arena_s_doubles * 8 + (size_t)m.arena_s_ints * 4) + 15) & ~(size_t)15;
   unsigned char* base = smem_raw + 16 * nwarp + (size_t)warp * env_bytes;
   double* sd = reinterpret_cast<double*>(base);
   int* si = reinterpret_cast<int*>(base + (size_t)m.arena_s_doubles * 8);
-  double* gd = a.garena_d + (size_t)env * m.arena_g_doubles;
-  int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
-  Env e{(unsigned)(base - smem_raw), (unsigned)(base - smem_raw) + 8u * (unsigned)m.arena_s_doubles, gd, gi, lane};
-  int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
-  double* rec = a.rec + (size_t)env * m.rec_pitch;
+  const unsigned bar = smem_u32(smem_raw + 16 * warp);
+  unsigned parity = 0;
+  bool bar_ready = false;
+  const int nchunks = a.sched ? (a.nsteps + a.chunk - 1) / a.chunk : 1;
 
-  StepCtx sc;
-  sc.ncon = 0; sc.nefc = 0; sc.iters = 0;
-  sc.t_prev = a.prof ? clock64() : 0;
-  const int cta_envs = min(nwarp, a.nenv - (int)blockIdx.x * nwarp);
-  const int nsync_main = (nwarp > 1 && a.sync_stages) ? cta_envs * 32 : 0;
-  sc.nsync = 0;
-
-  // ---- resume a split step: bring the arena back from HBM ----
-  if (a.mode == MODE_STEP_END) {
-    for (int f = 0; f < B2MJ_NFIELD; f++) {
-      const int os = m.off_s[f];
-      if (os < 0) continue;
-      if (m.fis_int[f]) { FORL(k, m.fsize[f]) si[os + k] = gi[m.off_g[f] + k]; }
-      else { FORL(k, m.fsize[f]) sd[os + k] = gd[m.off_g[f] + k]; }
+  for (;;) {
+    // ---- pick the work item: (env, [step0, step1)) ----
+    int env, step0, step1, chunk_id = 0;
+    if (a.sched) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(a.sched, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= a.nenv * nchunks) break;
+      chunk_id = t / a.nenv;           // chunk-major: all envs advance together
+      env = t - chunk_id * a.nenv;
+      step0 = chunk_id * a.chunk;
+      step1 = min(step0 + a.chunk, a.nsteps);
+      if (lane == 0) {
+        const volatile int* done = a.sched + 1 + env;
+        while (*done < chunk_id) __nanosleep(256);
+        __threadfence();
+      }
+      WSYNC();
+    } else {
+      env = blockIdx.x * nwarp + warp;
+      if (env >= a.nenv) return;  // whole warp exits; no CTA-wide barrier is used below
+      step0 = 0;
+      step1 = (a.mode == MODE_STEP) ? a.nsteps : 1;
     }
-    for (int f = 0; f < XF_COUNT; f++) {
-      const int os = m.xoff_s[f];
-      if (os < 0) continue;
-      FORL(k, m.xsize[f]) sd[os + k] = gd[m.xoff_g[f] + k];
+    double* gd = a.garena_d + (size_t)env * m.arena_g_doubles;
+    int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
+    Env e{(unsigned)(base - smem_raw), (unsigned)(base - smem_raw) + 8u * (unsigned)m.arena_s_doubles, gd, gi, lane,
+          (a.dump != 0 || a.mode == MODE_STEP_BEGIN || a.mode == MODE_STEP_END) ? 1 : 0};
+    int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
+    double* rec = a.rec + (size_t)env * m.rec_pitch;
+
+    StepCtx sc;
+    sc.ncon = 0; sc.nefc = 0; sc.iters = 0;
+    sc.t_prev = a.prof ? clock64() : 0;
+    const long long t_item0 = clock64();
+    const int cta_envs = min(nwarp, a.nenv - (int)blockIdx.x * nwarp);
+    const int nsync_main = (nwarp > 1 && a.sync_stages && !a.sched) ? cta_envs * 32 : 0;
+    sc.nsync = 0;
+
+    // ---- resume a split step: bring the arena back from HBM ----
+    if (a.mode == MODE_STEP_END) {
+      for (int f = 0; f < B2MJ_NFIELD; f++) {
+        const int os = m.off_s[f];
+        if (os < 0) continue;
+        if (m.fis_int[f]) { FORL(k, m.fsize[f]) si[os + k] = gi[m.off_g[f] + k]; }
+        else { FORL(k, m.fsize[f]) sd[os + k] = gd[m.off_g[f] + k]; }
+      }
+      for (int f = 0; f < XF_COUNT; f++) {
+        const int os = m.xoff_s[f];
+        if (os < 0) continue;
+        FORL(k, m.xsize[f]) sd[os + k] = gd[m.xoff_g[f] + k];
+      }
+      WSYNC();
+    }
+
+    // ---- state record: HBM -> SMEM with one TMA bulk copy (segments A+B are contiguous) ----
+    const unsigned load_bytes = (unsigned)(m.rec_C_begin - m.rec_A_begin) * 8u;
+    if (!bar_ready) {
+      if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      bar_ready = true;
+      WSYNC();
+    }
+    if (lane == 0) {
+      mbar_expect_tx(bar, load_bytes);
+      bulk_g2s(smem_u32(sd + m.rec_A_begin), rec + m.rec_A_begin, load_bytes, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    if (m.nmocap && a.mocap) {
+      const double* src = a.mocap + (size_t)env * 7 * m.nmocap;
+      double* mp = e.D(B2MJ_F_MOCAP_POS);
+      double* mq = e.D(B2MJ_F_MOCAP_QUAT);
+      FORL(k, 3 * m.nmocap) mp[k] = src[k];
+      FORL(k, 4 * m.nmocap) mq[k] = src[3 * m.nmocap + k];
     }
     WSYNC();
-  }
 
-  // ---- state record: HBM -> SMEM with one TMA bulk copy (segments A+B are contiguous) ----
-  const unsigned bar = smem_u32(smem_raw + 16 * warp);
-  const unsigned load_bytes = (unsigned)(m.rec_C_begin - m.rec_A_begin) * 8u;
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  WSYNC();
-  if (lane == 0) {
-    mbar_expect_tx(bar, load_bytes);
-    bulk_g2s(smem_u32(sd + m.rec_A_begin), rec + m.rec_A_begin, load_bytes, bar);
-  }
-  mbar_wait(bar, 0);
-  if (m.nmocap && a.mocap) {
-    const double* src = a.mocap + (size_t)env * 7 * m.nmocap;
-    double* mp = e.D(B2MJ_F_MOCAP_POS);
-    double* mq = e.D(B2MJ_F_MOCAP_QUAT);
-    FORL(k, 3 * m.nmocap) mp[k] = src[k];
-    FORL(k, 4 * m.nmocap) mq[k] = src[3 * m.nmocap + k];
-  }
-  WSYNC();
-
-  PROF_MARK(PROF_LOAD)
-  if (a.mode == MODE_STEP_END) {
-    sc.ncon = e.I(B2MJ_F_NCON)[0];
-    sc.nefc = e.I(B2MJ_F_NEFC)[0];
-  }
-
-  const int nsteps = (a.mode == MODE_STEP) ? a.nsteps : 1;
-  for (int step = 0; step < nsteps; step++) {
-    if (a.mode != MODE_STEP_END && a.mode != MODE_FORWARD) {
-      // mj_checkPos / mj_checkVel
-      int bad = 0;
-      { const double* q = e.D(B2MJ_F_QPOS); FORL(i, m.nq) bad |= isBad(q[i]); }
-      if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQPOS);
-      bad = 0;
-      { const double* v = e.D(B2MJ_F_QVEL); FORL(i, m.nv) bad |= isBad(v[i]); }
-      if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
+    PROF_MARK(PROF_LOAD)
+    if (a.mode == MODE_STEP_END) {
+      sc.ncon = e.I(B2MJ_F_NCON)[0];
+      sc.nefc = e.I(B2MJ_F_NEFC)[0];
     }
-    const bool first = a.mode != MODE_STEP_END, second = a.mode != MODE_STEP_BEGIN;
-    sc.nsync = nsync_main;
-    forwardPass(e, a, env, sc, false, first, second);
-    sc.nsync = 0;
-    if (a.mode == MODE_FORWARD || a.mode == MODE_STEP_BEGIN) break;
-    // mj_checkAcc
-    {
-      int bad = 0;
-      const double* qa = e.D(B2MJ_F_QACC);
-      FORL(i, m.nv) bad |= isBad(qa[i]);
-      if (__any_sync(0xffffffffu, bad)) {
-        resetEnv(e, warning, B2MJ_WARN_BADQACC);
-        forwardPass(e, a, env, sc, false, true, true);
+
+    B2K_NOUNROLL for (int step = step0; step < step1; step++) {
+      if (a.ctrl_seq) {  // fused rollout: this step's controls straight from the device-resident stream
+        const double* src = a.ctrl_seq + ((size_t)step * a.nenv + env) * m.nu;
+        double* ctrl = e.D(B2MJ_F_CTRL);
+        FORL(i, m.nu) ctrl[i] = src[i];
+        WSYNC();
+      }
+      if (a.mode != MODE_STEP_END && a.mode != MODE_FORWARD) {
+        // mj_checkPos / mj_checkVel
+        int bad = 0;
+        { const double* q = e.D(B2MJ_F_QPOS); FORL(i, m.nq) bad |= isBad(q[i]); }
+        if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQPOS);
+        bad = 0;
+        { const double* v = e.D(B2MJ_F_QVEL); FORL(i, m.nv) bad |= isBad(v[i]); }
+        if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
+      }
+      const bool first = a.mode != MODE_STEP_END, second = a.mode != MODE_STEP_BEGIN;
+      sc.nsync = nsync_main;
+      forwardPass(e, a, env, sc, false, first, second);
+      sc.nsync = 0;
+      if (a.mode == MODE_FORWARD || a.mode == MODE_STEP_BEGIN) break;
+      // mj_checkAcc
+      {
+        int bad = 0;
+        const double* qa = e.D(B2MJ_F_QACC);
+        FORL(i, m.nv) bad |= isBad(qa[i]);
+        if (__any_sync(0xffffffffu, bad)) {
+          resetEnv(e, warning, B2MJ_WARN_BADQACC);
+          forwardPass(e, a, env, sc, false, true, true);
+        }
+      }
+      if (m.opt.integrator == B2MJ_INT_RK4 && a.mode == MODE_STEP) stage_rk4(e, a, env, sc);
+      else stage_euler(e);
+      PROF_MARK(PROF_INTEGRATE)
+      if (a.traj_qpos) {
+        double* dst = a.traj_qpos + ((size_t)step * a.nenv + env) * m.nq;
+        const double* q = e.D(B2MJ_F_QPOS);
+        FORL(i, m.nq) dst[i] = q[i];
+      }
+      if (a.traj_qvel) {
+        double* dst = a.traj_qvel + ((size_t)step * a.nenv + env) * m.nv;
+        const double* v = e.D(B2MJ_F_QVEL);
+        FORL(i, m.nv) dst[i] = v[i];
+      }
+      if (a.traj_sensor && m.nsensordata) {
+        double* dst = a.traj_sensor + ((size_t)step * a.nenv + env) * m.nsensordata;
+        const double* sdat = e.D(B2MJ_F_SENSORDATA);
+        FORL(i, m.nsensordata) dst[i] = sdat[i];
       }
     }
-    if (m.opt.integrator == B2MJ_INT_RK4 && a.mode == MODE_STEP) stage_rk4(e, a, env, sc);
-    else stage_euler(e);
-    PROF_MARK(PROF_INTEGRATE)
-  }
 
-  // ---- results: counters, state record SMEM -> HBM (segments B+C contiguous), optional arena dump ----
-  if (lane == 0) {
-    int* st = a.stats + (size_t)env * 4;
-    st[0] = sc.ncon; st[1] = sc.nefc; st[2] = sc.iters; st[3] = 0;
-    e.I(B2MJ_F_SOLVER_ITER)[0] = sc.iters;
-    for (int k = 0; k < B2MJ_NWARNING; k++) e.I(B2MJ_F_WARNING)[k] = warning[k];
-  }
-  fence_async_smem();
-  WSYNC();
-  if (lane == 0) {
-    // MODE_STEP_BEGIN keeps qpos (normalised quaternions) consistent too: store B+C in every mode
-    bulk_s2g(rec + m.rec_B_begin, smem_u32(sd + m.rec_B_begin), (unsigned)(m.rec_end - m.rec_B_begin) * 8u);
-    bulk_commit_wait();
-  }
-  if (a.dump || a.mode == MODE_STEP_BEGIN) {
-    for (int f = 0; f < B2MJ_NFIELD; f++) {
-      const int os = m.off_s[f];
-      if (os < 0) continue;
-      if (m.fis_int[f]) { FORL(k, m.fsize[f]) gi[m.off_g[f] + k] = si[os + k]; }
-      else { FORL(k, m.fsize[f]) gd[m.off_g[f] + k] = sd[os + k]; }
+    // ---- results: counters, state record SMEM -> HBM (segments B+C contiguous), optional arena dump ----
+    if (lane == 0) {
+      int* st = a.stats + (size_t)env * 4;
+      st[0] = sc.ncon; st[1] = sc.nefc; st[2] = sc.iters;
+      st[3] = (int)((clock64() - t_item0) >> 10);  // this work item's residency in 1024-cycle units (diagnostic)
+      e.I(B2MJ_F_SOLVER_ITER)[0] = sc.iters;
+      for (int k = 0; k < B2MJ_NWARNING; k++) e.I(B2MJ_F_WARNING)[k] = warning[k];
     }
-    for (int f = 0; f < XF_COUNT; f++) {
-      const int os = m.xoff_s[f];
-      if (os < 0) continue;
-      FORL(k, m.xsize[f]) gd[m.xoff_g[f] + k] = sd[os + k];
+    fence_async_smem();
+    WSYNC();
+    if (lane == 0) {
+      // MODE_STEP_BEGIN keeps qpos (normalised quaternions) consistent too: store B+C in every mode
+      bulk_s2g(rec + m.rec_B_begin, smem_u32(sd + m.rec_B_begin), (unsigned)(m.rec_end - m.rec_B_begin) * 8u);
+      if (a.sched) {
+        // the next chunk of this env may be picked up by any warp on any SM: publish after the writes land
+        bulk_commit_wait_all();
+        __threadfence();
+        *((volatile int*)(a.sched + 1 + env)) = chunk_id + 1;
+      } else {
+        bulk_commit_wait();
+      }
     }
+    if (a.dump || a.mode == MODE_STEP_BEGIN) {
+      for (int f = 0; f < B2MJ_NFIELD; f++) {
+        const int os = m.off_s[f];
+        if (os < 0) continue;
+        if (m.fis_int[f]) { FORL(k, m.fsize[f]) gi[m.off_g[f] + k] = si[os + k]; }
+        else { FORL(k, m.fsize[f]) gd[m.off_g[f] + k] = sd[os + k]; }
+      }
+      for (int f = 0; f < XF_COUNT; f++) {
+        const int os = m.xoff_s[f];
+        if (os < 0) continue;
+        FORL(k, m.xsize[f]) gd[m.xoff_g[f] + k] = sd[os + k];
+      }
+    }
+    WSYNC();
+    PROF_MARK(PROF_STORE)
+    if (!a.sched) break;
   }
-  WSYNC();
-  PROF_MARK(PROF_STORE)
 }
 
 }  // namespace b2k
@@ -316,6 +380,7 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
   static size_t attr_bytes[16];
   int dev = 0;
   cudaGetDevice(&dev);
+  const int dev_id = dev;
   dev &= 15;
   if (smem_bytes > attr_bytes[dev]) {
     cudaError_t err = cudaFuncSetAttribute(b2k_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -330,7 +395,14 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
     memcpy(&g_shadow[dev], m, sizeof(DevModel));
     g_shadow_valid[dev] = true;
   }
-  const int ctas = (a->nenv + warps_per_cta - 1) / warps_per_cta;
+  int ctas = (a->nenv + warps_per_cta - 1) / warps_per_cta;
+  if (a->sched) {
+    // persistent grid: exactly the CTAs that are co-resident (spinning on a ticket needs its producer running)
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2k_step_kernel, warps_per_cta * 32, smem_bytes);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    ctas = std::max(1, std::min(ctas, per_sm * sms));
+  }
   b2k_step_kernel<<<ctas, warps_per_cta * 32, smem_bytes, stream>>>(*a);
   return (int)cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 #include "dev_model.h"
 
 #define B2K_MAX_THREADS 128
+#define B2K_MIN_CTAS 4   /* 4 x 128 threads = 16 warps per SM -> at most 128 registers per thread */
 
 extern "C" {
 int b2k_launch_step(const b2k::DevModel* m, const b2k::LaunchArgs* a, int warps_per_cta, size_t smem_bytes,

@@ -306,3 +306,32 @@ def test_full_batch_properties(load_model, BatchSim):
     np.testing.assert_array_equal(q, np.broadcast_to(q[0], q.shape))
     np.testing.assert_array_equal(q[0], small.get("qpos"))
     assert big.get("warning").sum() == 0
+
+
+def test_rollout_equals_stepping(load_model, BatchSim):
+    """b2mj_rollout (one launch, device ctrl stream, trajectory out) == nsteps x (set ctrl; b2mj_step)."""
+    import torch
+
+    model = load_model("panda_like.xml")
+    nenv, K = 64, 30
+    qpos, qvel = perturbed(model, nenv, 12)
+    rng = np.random.default_rng(4)
+    ctrl = np.stack([ctrl_sample(model, rng, nenv) for _ in range(K)])
+    a, b = BatchSim(model, nenv), BatchSim(model, nenv)
+    for s in (a, b):
+        s.set("qpos", qpos)
+        s.set("qvel", qvel)
+    cdev = torch.from_numpy(ctrl).cuda()
+    tq = torch.zeros(K, nenv, model.nq, dtype=torch.float64, device="cuda")
+    tv = torch.zeros(K, nenv, model.nv, dtype=torch.float64, device="cuda")
+    ts = torch.zeros(K, nenv, model.nsensordata, dtype=torch.float64, device="cuda")
+    a.rollout(K, cdev.data_ptr(), tq.data_ptr(), tv.data_ptr(), ts.data_ptr())
+    a.sync()
+    for k in range(K):
+        b.set("ctrl", ctrl[k])
+        b.step(1)
+        np.testing.assert_array_equal(tq[k].cpu().numpy(), b.get("qpos"))
+        np.testing.assert_array_equal(tv[k].cpu().numpy(), b.get("qvel"))
+        np.testing.assert_array_equal(ts[k].cpu().numpy(), b.get("sensordata"))
+    np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
+    np.testing.assert_array_equal(a.get("time"), b.get("time"))
