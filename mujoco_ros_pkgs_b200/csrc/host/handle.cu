@@ -405,12 +405,15 @@ static int make_layout(Handle* h) {
   // (16 warps per SM); among equals prefer the smallest CTA: a finished env frees its shared memory for
   // the next one immediately instead of waiting for its CTA mates (measured, profiles/r1_sweeps.txt)
   const int forceW = getenv("B2MJ_WARPS_PER_CTA") ? atoi(getenv("B2MJ_WARPS_PER_CTA")) : h->force_warps_per_cta;
-  for (int W = 1; W <= B2K_MAX_THREADS / 32; W++) {
+  // W = envs per CTA (each env is served by B2K_G lanes; CTAs hold whole warps)
+  const int wstep = 32 / B2K_G;
+  for (int W = wstep; W <= B2K_MAX_THREADS / B2K_G; W += wstep) {
     if (forceW && W != forceW) continue;
     const size_t cta = (size_t)W * (env_bytes + 16);
     if (cta > kMaxCta) continue;
     int ctas = (int)(kSmPerSM / (cta + kCtaReserve));
-    ctas = std::min(ctas, 16 / W);
+    ctas = std::min(ctas, (512 / B2K_G) / W);   // 128 registers per thread -> 512 threads per SM
+    ctas = std::min(ctas, 32);
     const int envs = ctas * W;
     if (envs > bestEnv) { bestEnv = envs; bestW = W; }
   }

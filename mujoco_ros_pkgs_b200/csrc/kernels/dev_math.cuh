@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "dev_model.h"
+
 namespace b2k {
 
 #define B2K_MINVAL 1E-15
@@ -188,21 +190,23 @@ B2K_DI void transformSpatial(double* res, const double* vec, int flg_force, cons
   else { for (int k = 0; k < 6; k++) res[k] = tran[k]; }
 }
 
-// warp reductions
-B2K_DI double warpSum(double v) {
+// ---- env-group collectives.  An env is served by a group of B2K_G consecutive lanes (32: one env per warp; 16: two envs per
+// warp, each SIMT instruction doing the work of two envs -- see dev_model.h for the measured trade-off).
+// `mask` names the lanes of the caller's group; the halves of a warp may diverge and reconverge freely.
+B2K_DI double warpSum(unsigned mask, double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = B2K_G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, B2K_G);
   return v;
 }
-B2K_DI int warpMaxInt(int v) {
+B2K_DI int warpMaxInt(unsigned mask, int v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = B2K_G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(mask, v, o, B2K_G));
   return v;
 }
-B2K_DI int warpInclusiveScan(int v, int lane) {
+B2K_DI int warpInclusiveScan(unsigned mask, int v, int lane) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, v, o);
+  for (int o = 1; o < B2K_G; o <<= 1) {
+    int t = __shfl_up_sync(mask, v, o, B2K_G);
     if (lane >= o) v += t;
   }
   return v;

@@ -15,6 +15,13 @@
 
 #include "b2mj.h"
 
+// lanes per env (see dev_math.cuh "env-group collectives"): 32 = one env per warp (default), 16 = two envs per
+// warp.  Measured on B200 (profiles/r1_experiments.txt): 16 is ~17% slower on the C2 workload -- the kernel needs the
+// warps for latency hiding more than it gains from halving the instruction stream per env.
+#ifndef B2K_G
+#define B2K_G 32
+#endif
+
 namespace b2k {
 
 // extra per-env scratch arrays that are not b2mj_field entries

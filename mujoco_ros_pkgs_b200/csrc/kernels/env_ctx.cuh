@@ -20,7 +20,8 @@ struct Env {
   unsigned sbi;  // byte offset of the int part
   double* gd;    // this env's HBM/L2 arena (doubles)
   int* gi;       // this env's HBM/L2 arena (ints)
-  int lane;
+  int lane;      // lane within the env's group: 0 .. B2K_G-1
+  unsigned mask; // the group's lanes within the warp (operand of every *_sync collective)
   int dump;      // the arena will be read back (keep_intermediates / split step): also produce API-only fields
 
   __device__ __forceinline__ double* sd() const { return reinterpret_cast<double*>(b2k_smem + sbd); }
@@ -56,8 +57,8 @@ struct Env {
 
 // lane-strided loop; never unrolled: trip counts are 1-2 for the models this kernel targets and the
 // megakernel is instruction-cache bound, so code size matters more than loop overhead
-#define FORL(i, n) _Pragma("unroll 1") for (int i = e.lane; i < (n); i += 32)
-#define WSYNC() __syncwarp()
+#define FORL(i, n) _Pragma("unroll 1") for (int i = e.lane; i < (n); i += B2K_G)
+#define WSYNC() __syncwarp(e.mask)
 
 // ---- TMA 1-D bulk copy + mbarrier wrappers (sm_90+/sm_100a PTX) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -417,7 +417,7 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
   int* c_excl = e.IG(B2MJ_F_CONTACT_EXCLUDE);
   int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
   int carry = 0, overflow = 0;
-  B2K_NOUNROLL for (int base = 0; base < m.ncollpair; base += 32) {
+  B2K_NOUNROLL for (int base = 0; base < m.ncollpair; base += B2K_G) {
     const int p = base + e.lane;
     PairCon pc;
     pc.shared_frame = 0;
@@ -443,8 +443,8 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
       }
       if (!cull) num = narrowphase(gxpos, gxmat, pc, g1, g2, margin);
     }
-    const int incl = warpInclusiveScan(num, e.lane);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int incl = warpInclusiveScan(e.mask, num, e.lane);
+    const int total = __shfl_sync(e.mask, incl, B2K_G - 1, B2K_G);
     if (num > 0) {
       int condim;
       double solref[2], solimp[5], fri[3];
@@ -497,7 +497,7 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
     }
     carry += total;
   }
-  if (__any_sync(0xffffffffu, overflow) || carry > m.nconmax) {
+  if (__any_sync(e.mask, overflow) || carry > m.nconmax) {
     if (e.lane == 0) warning[B2MJ_WARN_CONTACTFULL]++;
     carry = min(carry, m.nconmax);
   }

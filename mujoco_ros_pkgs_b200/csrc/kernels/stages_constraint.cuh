@@ -196,7 +196,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
   }
   // ---------------- limits ----------------
   if (!(m.opt.disableflags & B2MJ_DSBL_LIMIT)) {
-    B2K_NOUNROLL for (int base = 0; base < m.njnt; base += 32) {
+    B2K_NOUNROLL for (int base = 0; base < m.njnt; base += B2K_G) {
       const int j = base + e.lane;
       int cnt = 0;
       double dist[2], sgn[2], axis[3];
@@ -220,8 +220,8 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
           if (d < margin) { dist[0] = d; cnt = 1; ball = true; }
         }
       }
-      const int incl = warpInclusiveScan(cnt, e.lane);
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const int incl = warpInclusiveScan(e.mask, cnt, e.lane);
+      const int total = __shfl_sync(e.mask, incl, B2K_G - 1, B2K_G);
       int r0 = row + incl - cnt;
       B2K_NOUNROLL for (int s = 0; s < cnt; s++) {
         const int r = r0 + s;
@@ -270,14 +270,14 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
     const double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);
     const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
     bool contacts_full = false;  // uniform: once a contact does not fit, all later ones are dropped
-    B2K_NOUNROLL for (int base = 0; base < ncon && !contacts_full; base += 32) {
+    B2K_NOUNROLL for (int base = 0; base < ncon && !contacts_full; base += B2K_G) {
       const int c = base + e.lane;
       int cnt = 0, dim = 0;
       if (c < ncon && !c_excl[c]) {
         dim = c_dim[c];
         cnt = dim == 1 ? 1 : (pyramid ? 2 * (dim - 1) : dim);
       }
-      const int incl = warpInclusiveScan(cnt, e.lane);
+      const int incl = warpInclusiveScan(e.mask, cnt, e.lane);
       int endrow = row;
       if (cnt > 0) {
         const int adr = row + incl - cnt;
@@ -306,8 +306,8 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
           }
         }
       }
-      contacts_full = __any_sync(0xffffffffu, full);
-      row = warpMaxInt(endrow);
+      contacts_full = __any_sync(e.mask, full);
+      row = warpMaxInt(e.mask, endrow);
     }
     WSYNC();
     // Jacobian entries: one (contact, dof) column per lane
@@ -337,7 +337,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
       }
     }
   }
-  if (__any_sync(0xffffffffu, full)) {
+  if (__any_sync(e.mask, full)) {
     if (e.lane == 0) warning[B2MJ_WARN_CNSTRFULL]++;
   }
   const int nefc = row;
@@ -520,8 +520,8 @@ __device__ __noinline__ double constraintUpdate_warp(const Env e, int nefc, int 
     }
   }
   WSYNC();
-  if (changed) *changed = __any_sync(0xffffffffu, ch);
-  return warpSum(s);
+  if (changed) *changed = __any_sync(e.mask, ch);
+  return warpSum(e.mask, s);
 }
 
 }  // namespace b2k

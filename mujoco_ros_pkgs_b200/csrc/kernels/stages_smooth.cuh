@@ -298,7 +298,7 @@ __device__ __noinline__ void stage_tendon_transmission(const Env e) {
 __device__ __noinline__ void factorLD2(const Env e, double* A, double* Bm, double* dinvA, double* sqrtinvA, double* dinvB) {
   const DevModel& m = c_dm;
   const int nv = m.nv;
-  const int half = Bm ? (e.lane >> 4) : 0, sub = Bm ? (e.lane & 15) : e.lane, stride = Bm ? 16 : 32;
+  const int half = Bm ? (e.lane / (B2K_G / 2)) : 0, sub = Bm ? (e.lane % (B2K_G / 2)) : e.lane, stride = Bm ? B2K_G / 2 : B2K_G;
   double* LD = half ? Bm : A;
   for (int k = nv - 1; k >= 0; k--) {
     const int d = m.dof_nanc[k];
@@ -329,7 +329,7 @@ __device__ __noinline__ void factorLD2(const Env e, double* A, double* Bm, doubl
 // so dofs are processed by depth level, one lane per (dof, ancestor) entry.
 __device__ __noinline__ void invL2(const Env e, const double* LA, double* WA, const double* LB, double* WB) {
   const DevModel& m = c_dm;
-  const int half = LB ? (e.lane >> 4) : 0, sub = LB ? (e.lane & 15) : e.lane, stride = LB ? 16 : 32;
+  const int half = LB ? (e.lane / (B2K_G / 2)) : 0, sub = LB ? (e.lane % (B2K_G / 2)) : e.lane, stride = LB ? B2K_G / 2 : B2K_G;
   const double* LD = half ? LB : LA;
   double* W = half ? WB : WA;
   B2K_NOUNROLL for (int l = 1; l < m.ndoflevel; l++) {
@@ -407,27 +407,30 @@ __device__ __noinline__ void mulM_warp(const Env e, double* res, const double* v
 }
 
 // ---- dense small-model path (nv <= 16) ----------------------------------------------------------
-// In-place Gauss-Jordan inversion of up to two SPD nv x nv matrices at once (lanes 0..nv-1 own the rows
-// of A, lanes 16..16+nv-1 the rows of B): no index tables, no factor / triangular-solve chain; every
-// later solve is one dense mat-vec.
+// In-place Gauss-Jordan inversion of up to two SPD nv x nv matrices (lane i owns row i): no index
+// tables, no factor / triangular-solve chain; every later solve is one dense mat-vec.
 __device__ __noinline__ void invertSPD2(const Env e, double* A, double* Bm, int n) {
-  const int half = e.lane >> 4, i = e.lane & 15;
-  double* Mx = half ? Bm : A;
-  const bool own = i < n && Mx != nullptr;
-  B2K_NOUNROLL for (int k = 0; k < n; k++) {
-    if (own && i != k) {
-      const double p = 1.0 / Mx[k * n + k];
-      const double f = Mx[i * n + k] * p;
-      B2K_NOUNROLL for (int j = 0; j < n; j++) Mx[i * n + j] -= f * Mx[k * n + j];
-      Mx[i * n + k] = -f;
+  // lane i owns row i (n <= 16 <= B2K_G); the two matrices are inverted one after the other
+  B2K_NOUNROLL for (int mat = 0; mat < 2; mat++) {
+    double* Mx = mat ? Bm : A;
+    if (!Mx) continue;
+    const int i = e.lane;
+    const bool own = i < n;
+    B2K_NOUNROLL for (int k = 0; k < n; k++) {
+      if (own && i != k) {
+        const double p = 1.0 / Mx[k * n + k];
+        const double f = Mx[i * n + k] * p;
+        B2K_NOUNROLL for (int j = 0; j < n; j++) Mx[i * n + j] -= f * Mx[k * n + j];
+        Mx[i * n + k] = -f;
+      }
+      WSYNC();
+      if (own && i == k) {
+        const double p = 1.0 / Mx[k * n + k];
+        B2K_NOUNROLL for (int j = 0; j < n; j++) Mx[k * n + j] *= p;
+        Mx[k * n + k] = p;
+      }
+      WSYNC();
     }
-    WSYNC();
-    if (own && i == k) {
-      const double p = 1.0 / Mx[k * n + k];
-      B2K_NOUNROLL for (int j = 0; j < n; j++) Mx[k * n + j] *= p;
-      Mx[k * n + k] = p;
-    }
-    WSYNC();
   }
 }
 
@@ -723,7 +726,7 @@ __device__ __noinline__ void stage_actuation(const Env e, int* warning) {
     const double c = ctrl[i];
     if (isnan(c) || c > B2MJ_MAXVAL || c < -B2MJ_MAXVAL) badc = 1;
   }
-  if (__any_sync(0xffffffffu, badc)) {
+  if (__any_sync(e.mask, badc)) {
     FORL(i, nu) ctrl[i] = 0;
     if (e.lane == 0) warning[B2MJ_WARN_BADCTRL]++;
     WSYNC();

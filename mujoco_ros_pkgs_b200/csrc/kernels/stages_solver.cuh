@@ -60,7 +60,7 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
   if (nefc <= B2K_PGS_REGROWS) {
     double* AR = arPtr(e, nefc);
     // lower triangle incl. diagonal, mirrored
-    B2K_NOUNROLL for (int item = e.lane; item < nefc * nefc; item += 32) {
+    B2K_NOUNROLL for (int item = e.lane; item < nefc * nefc; item += B2K_G) {
       const int i = item / nefc, j = item - i * nefc;
       if (j > i) continue;
       double s = 0;
@@ -101,7 +101,7 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
 __device__ __forceinline__ double rowDot(const Env e, const double* row, const double* vec, int nv) {
   double s = 0;
   FORL(k, nv) s += row[k] * vec[k];
-  return warpSum(s);
+  return warpSum(e.mask, s);
 }
 
 // small SPD solve helpers for the elliptic QCQP (n <= 5), executed redundantly by every lane
@@ -168,7 +168,7 @@ __device__ __forceinline__ double rowDotW(const Env e, const double* a, const do
   double s = 0;
   if (w) { FORL(k, nv) s += a[k] * b[k] * w[k]; }
   else { FORL(k, nv) s += a[k] * b[k]; }
-  return warpSum(s);
+  return warpSum(e.mask, s);
 }
 
 // elliptic-cone block update shared by both PGS forms: given the dim x dim block Athis of AR, the block
@@ -223,7 +223,7 @@ __device__ __noinline__ void pgsConeBlock(int dim, const double* Athis, const do
 // clamp, and every lane folds the force change into its own residual with one FMA.  SM = AR and the row
 // constants live in the shared-memory window (addresses formed from the shared symbol -> LDS), else in the
 // env's HBM/L2 arena.  Returns iterations used.
-template <bool TWO, bool SM>
+template <int NS, bool SM>
 __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* ARg, unsigned ARs) {
   const DevModel& m = c_dm;
   const double* AR = SM ? reinterpret_cast<const double*>(b2k_smem + ARs) : ARg;
@@ -233,20 +233,20 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
   const double tol = m.opt.tolerance;
   const int maxiter = m.opt.iterations;
   const int lane = e.lane;
-  const int j0 = lane, j1 = lane + 32;
-  const int c0 = min(j0, nefc - 1), c1 = min(j1, nefc - 1);  // clamped column indices for AR row reads
-  double r0 = 0, r1 = 0, f0 = 0, f1 = 0;
-  if (j0 < nefc) {
-    f0 = P.force[j0];
-    double s = P.b[j0];
-    B2K_NOUNROLL for (int k = 0; k < nefc; k++) s += AR[j0 * nefc + k] * P.force[k];
-    r0 = s;
-  }
-  if (TWO && j1 < nefc) {
-    f1 = P.force[j1];
-    double s = P.b[j1];
-    B2K_NOUNROLL for (int k = 0; k < nefc; k++) s += AR[j1 * nefc + k] * P.force[k];
-    r1 = s;
+  // lane j owns rows j, j+G, ... (NS slots): residual r = b + AR f and force f live in registers
+  double r[NS], f[NS];
+  int col[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int j = lane + B2K_G * s;
+    col[s] = min(j, nefc - 1);  // clamped column index for AR row reads
+    r[s] = 0; f[s] = 0;
+    if (j < nefc) {
+      f[s] = P.force[j];
+      double acc = P.b[j];
+      B2K_NOUNROLL for (int k = 0; k < nefc; k++) acc += AR[j * nefc + k] * P.force[k];
+      r[s] = acc;
+    }
   }
   int iter = 0;
   while (iter < maxiter) {
@@ -257,27 +257,29 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
       const double iA = rc[0];
       if (!(iA < 0)) {  // scalar row (1/A_ii is stored negated for the rows of an elliptic cone; NaN stays here)
         const double Aii = rc[1], lo = rc[2], up = rc[3];
-        const double a0 = arow[c0];
-        const double a1 = TWO ? arow[c1] : 0.0;
-        double res, fold;
-        if (TWO && i >= 32) {
-          res = __shfl_sync(0xffffffffu, r1, i - 32);
-          fold = __shfl_sync(0xffffffffu, f1, i - 32);
-        } else {
-          res = __shfl_sync(0xffffffffu, r0, i);
-          fold = __shfl_sync(0xffffffffu, f0, i);
-        }
-        double f = fold - res * iA;
-        f = f < lo ? lo : f;
-        f = f > up ? up : f;
-        double delta = f - fold;
+        double a[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) a[s] = arow[col[s]];
+        const int src = i % B2K_G, slot = i / B2K_G;
+        double res = 0, fold = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+          if (NS == 1 || slot == s) {
+            res = __shfl_sync(e.mask, r[s], src, B2K_G);
+            fold = __shfl_sync(e.mask, f[s], src, B2K_G);
+          }
+        double fn = fold - res * iA;
+        fn = fn < lo ? lo : fn;
+        fn = fn > up ? up : fn;
+        double delta = fn - fold;
         double change = delta * (0.5 * delta * Aii + res);
-        if (change > 1e-10) { delta = 0; change = 0; f = fold; }  // cost guard of mj_solPGS (uniform branch)
+        if (change > 1e-10) { delta = 0; change = 0; fn = fold; }  // cost guard of mj_solPGS (uniform branch)
         improvement -= change;
-        r0 += a0 * delta;
-        if (TWO) r1 += a1 * delta;
-        if (TWO && i >= 32) { if (lane == i - 32) f1 = f; }
-        else if (lane == i) f0 = f;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+          r[s] += a[s] * delta;
+          if ((NS == 1 || slot == s) && lane == src) f[s] = fn;
+        }
         i += 1;
         rc += 4;
         arow += nefc;
@@ -286,32 +288,40 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
         const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
         const int c = P.id[i], dim = min(max(c_dim[c], 1), 6);
         const double* fri = c_fri + 5 * c;
-        double Athis[36], res[6], oldf[6], f[6];
-        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
-          const int row = i + j, rs = row & 31;
-          const bool rh = TWO && row >= 32;
-          B2K_NOUNROLL for (int k = 0; k < dim; k++) Athis[j * dim + k] = AR[row * nefc + i + k];
-          oldf[j] = __shfl_sync(0xffffffffu, rh ? f1 : f0, rs);
-          res[j] = __shfl_sync(0xffffffffu, rh ? r1 : r0, rs);
+        double Athis[36], res[6], oldf[6], fb[6];
+        for (int j = 0; j < dim; j++) {
+          const int row = i + j, rs = row % B2K_G, slot = row / B2K_G;
+          for (int k = 0; k < dim; k++) Athis[j * dim + k] = AR[row * nefc + i + k];
+          double rr = 0, ff = 0;
+#pragma unroll
+          for (int s = 0; s < NS; s++)
+            if (NS == 1 || slot == s) {
+              ff = __shfl_sync(e.mask, f[s], rs, B2K_G);
+              rr = __shfl_sync(e.mask, r[s], rs, B2K_G);
+            }
+          oldf[j] = ff;
+          res[j] = rr;
         }
-        pgsConeBlock(dim, Athis, res, oldf, fri, f);
+        pgsConeBlock(dim, Athis, res, oldf, fri, fb);
         double change = 0, delta[6];
-        B2K_NOUNROLL for (int j = 0; j < dim; j++) delta[j] = f[j] - oldf[j];
-        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
-          double s = 0;
-          B2K_NOUNROLL for (int k = 0; k < dim; k++) s += Athis[j * dim + k] * delta[k];
-          change += 0.5 * delta[j] * s + delta[j] * res[j];
+        for (int j = 0; j < dim; j++) delta[j] = fb[j] - oldf[j];
+        for (int j = 0; j < dim; j++) {
+          double acc = 0;
+          for (int k = 0; k < dim; k++) acc += Athis[j * dim + k] * delta[k];
+          change += 0.5 * delta[j] * acc + delta[j] * res[j];
         }
         if (change > 1e-10) {
           change = 0;
-          B2K_NOUNROLL for (int j = 0; j < dim; j++) { delta[j] = 0; f[j] = oldf[j]; }
+          for (int j = 0; j < dim; j++) { delta[j] = 0; fb[j] = oldf[j]; }
         }
         improvement -= change;
-        B2K_NOUNROLL for (int j = 0; j < dim; j++) {
-          const int row = i + j;
-          r0 += AR[row * nefc + c0] * delta[j];
-          if (TWO) r1 += AR[row * nefc + c1] * delta[j];
-          if (lane == (row & 31)) { if (TWO && row >= 32) f1 = f[j]; else f0 = f[j]; }
+        for (int j = 0; j < dim; j++) {
+          const int row = i + j, rs = row % B2K_G, slot = row / B2K_G;
+#pragma unroll
+          for (int s = 0; s < NS; s++) {
+            r[s] += AR[row * nefc + col[s]] * delta[j];
+            if ((NS == 1 || slot == s) && lane == rs) f[s] = fb[j];
+          }
         }
         i += dim;
         rc += 4 * dim;
@@ -321,8 +331,11 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
     iter++;
     if (improvement * scale < tol) break;
   }
-  if (j0 < nefc) P.force[j0] = f0;
-  if (TWO && j1 < nefc) P.force[j1] = f1;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int j = lane + B2K_G * s;
+    if (j < nefc) P.force[j] = f[s];
+  }
   WSYNC();
   return iter;
 }
@@ -433,7 +446,7 @@ __device__ __forceinline__ void mulJacVec_warp(const Env e, int nefc, double* re
 __device__ __forceinline__ double dot_warp(const Env e, const double* a, const double* b, int n) {
   double s = 0;
   FORL(k, n) s += a[k] * b[k];
-  return warpSum(s);
+  return warpSum(e.mask, s);
 }
 
 // in-place dense Cholesky (lower) of the nv x nv Hessian; invd[j] = 1 / L[j][j]
@@ -443,7 +456,7 @@ __device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* inv
     B2K_NOUNROLL for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
     if (s < mindiag) s = mindiag;
     const double ljj = sqrt(s), inv = 1 / ljj;
-    B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += 32) {
+    B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += B2K_G) {
       double t = A[i * n + j];
       B2K_NOUNROLL for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
       A[i * n + j] = t * inv;
@@ -454,20 +467,20 @@ __device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* inv
   WSYNC();
 }
 
-// x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+32, k+64, k+96
-#define B2K_CHOL_SLOTS 4
+// x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+G, k+2G, ...
+#define B2K_CHOL_SLOTS (128 / B2K_G)
 __device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n) {
   double t[B2K_CHOL_SLOTS];
 #pragma unroll
-  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + 32 * s; t[s] = k < n ? b[k] : 0.0; }
+  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + B2K_G * s; t[s] = k < n ? b[k] : 0.0; }
   B2K_NOUNROLL for (int i = 0; i < n; i++) {  // L y = b
     double ti = 0;
 #pragma unroll
-    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i >> 5) == s) ti = __shfl_sync(0xffffffffu, t[s], i & 31);
+    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i / B2K_G) == s) ti = __shfl_sync(e.mask, t[s], i % B2K_G, B2K_G);
     const double yi = ti * invd[i];
 #pragma unroll
     for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
-      const int k = e.lane + 32 * s;
+      const int k = e.lane + B2K_G * s;
       if (k == i) t[s] = yi;
       else if (k > i && k < n) t[s] -= L[k * n + i] * yi;
     }
@@ -475,17 +488,17 @@ __device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double
   for (int i = n - 1; i >= 0; i--) {  // L' x = y
     double ti = 0;
 #pragma unroll
-    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i >> 5) == s) ti = __shfl_sync(0xffffffffu, t[s], i & 31);
+    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i / B2K_G) == s) ti = __shfl_sync(e.mask, t[s], i % B2K_G, B2K_G);
     const double xi = ti * invd[i];
 #pragma unroll
     for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
-      const int k = e.lane + 32 * s;
+      const int k = e.lane + B2K_G * s;
       if (k == i) t[s] = xi;
       else if (k < i) t[s] -= L[i * n + k] * xi;
     }
   }
 #pragma unroll
-  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + 32 * s; if (k < n) x[k] = t[s]; }
+  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + B2K_G * s; if (k < n) x[k] = t[s]; }
   WSYNC();
 }
 
@@ -511,7 +524,7 @@ __device__ __noinline__ void primalUpdate(const Env e, PrimalCtx& c, int* change
   mulJacTVec_warp(e, c.nefc, e.D(B2MJ_F_QFRC_CONSTRAINT), P.force);
   double g = 0;
   FORL(i, c.nv) g += (c.Ma[i] - qs[i]) * (qacc[i] - qas[i]);
-  c.gauss = 0.5 * warpSum(g);
+  c.gauss = 0.5 * warpSum(e.mask, g);
   c.cost += c.gauss;
 }
 
@@ -533,7 +546,7 @@ __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* cH = c.cone ? e.XG(XF_CONTACT_H) : nullptr;
   // one lane per lower-triangle entry (i, j <= i)
-  B2K_NOUNROLL for (int item = e.lane; item < nv * nv; item += 32) {
+  B2K_NOUNROLL for (int item = e.lane; item < nv * nv; item += B2K_G) {
     const int i = item / nv, j = item - i * nv;
     if (j > i) continue;
     double s = H[item];
@@ -643,12 +656,12 @@ __device__ __noinline__ LSPoint primalEval(const Env e, const PrimalCtx& c, doub
       if (x < 0) { q0 += qi[0]; q1 += qi[1]; q2 += qi[2]; }
     }
   }
-  q0 = warpSum(q0) + c.quadGauss[0];
-  q1 = warpSum(q1) + c.quadGauss[1];
-  q2 = warpSum(q2) + c.quadGauss[2];
-  cost = warpSum(cost);
-  deriv0 = warpSum(deriv0);
-  deriv1 = warpSum(deriv1);
+  q0 = warpSum(e.mask, q0) + c.quadGauss[0];
+  q1 = warpSum(e.mask, q1) + c.quadGauss[1];
+  q2 = warpSum(e.mask, q2) + c.quadGauss[2];
+  cost = warpSum(e.mask, cost);
+  deriv0 = warpSum(e.mask, deriv0);
+  deriv1 = warpSum(e.mask, deriv1);
   LSPoint p;
   p.alpha = alpha;
   p.cost = cost + alpha * alpha * q2 + alpha * q1 + q0;
@@ -748,8 +761,8 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
     } else {
       double num = 0, den = 0;
       FORL(i, nv) { num += c.grad[i] * (c.Mgrad[i] - c.Mgradold[i]); den += c.gradold[i] * c.Mgradold[i]; }
-      num = warpSum(num);
-      den = warpSum(den);
+      num = warpSum(e.mask, num);
+      den = warpSum(e.mask, den);
       double beta = num / fmax(B2K_MINVAL, den);
       if (beta < 0) beta = 0;
       FORL(i, nv) c.search[i] = -c.Mgrad[i] + beta * c.search[i];
@@ -823,7 +836,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
           cost += P.force[i] * (0.5 * (s + P.R[i] * P.force[i]) + P.b[i]);
         }
       }
-      cost = warpSum(cost);
+      cost = warpSum(e.mask, cost);
       WSYNC();
       if (cost > 0) { FORL(i, nefc) P.force[i] = 0; }
       WSYNC();
@@ -835,9 +848,11 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
       const bool sm = nefc * (nefc + 4) <= m.xsize[XF_EFC_AR_S];
       const unsigned soff = e.sbd + 8u * (unsigned)m.xoff_s[XF_EFC_AR_S];
       const double* ARg = e.XG(XF_EFC_AR);
-      if (sm) iters = solvePGS_regT<false, true>(e, nefc, nullptr, soff);   // window holds <= 17 rows
-      else if (nefc <= 32) iters = solvePGS_regT<false, false>(e, nefc, ARg, 0);
-      else iters = solvePGS_regT<true, false>(e, nefc, ARg, 0);
+      if (sm && nefc <= B2K_G) iters = solvePGS_regT<1, true>(e, nefc, nullptr, soff);
+      else if (sm) iters = solvePGS_regT<2, true>(e, nefc, nullptr, soff);   // window holds <= 17 rows
+      else if (nefc <= B2K_G) iters = solvePGS_regT<1, false>(e, nefc, ARg, 0);
+      else if (nefc <= 2 * B2K_G) iters = solvePGS_regT<2, false>(e, nefc, ARg, 0);
+      else iters = solvePGS_regT<(64 / B2K_G > 2 ? 64 / B2K_G : 2), false>(e, nefc, ARg, 0);
     } else {
       iters = solvePGS_free(e, nefc, avec);
     }
@@ -861,7 +876,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
       mulM_warp(e, Ma, warm);
       double g = 0;
       FORL(i, nv) g += (Ma[i] - qs[i]) * (warm[i] - qas[i]);
-      cost_warm += 0.5 * warpSum(g);
+      cost_warm += 0.5 * warpSum(e.mask, g);
       const double cost_smooth = constraintUpdate_warp(e, nefc, ncon, P.b, false);
       if (cost_warm < cost_smooth) { FORL(i, nv) qacc[i] = warm[i]; }
       else { FORL(i, nv) qacc[i] = qas[i]; }

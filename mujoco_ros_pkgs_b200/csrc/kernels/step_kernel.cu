@@ -6,6 +6,7 @@
 // mj_forward (:329,:621) and the two halves around the control hook (mjcb_control placement,
 // mujoco_env.h:242-246).  Pipeline order follows SURVEY.md Appendix A.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -176,7 +177,9 @@ __device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env
 __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel(const LaunchArgs a) {
   const DevModel& m = c_dm;
   unsigned char* const smem_raw = b2k_smem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  // "warp" below = env group of B2K_G lanes (a half-warp when B2K_G == 16)
+  const int warp = threadIdx.x / B2K_G, lane = threadIdx.x % B2K_G, nwarp = blockDim.x / B2K_G;
+  const unsigned gmask = B2K_G == 32 ? 0xffffffffu : (((1u << B2K_G) - 1u) << (threadIdx.x & 31 & ~(B2K_G - 1)));
 
   // shared layout: [nwarp mbarriers, 16B each][nwarp env blocks: doubles | ints]
   const size_t env_bytes = (((size_t)m.arena_s_doubles * 8 + (size_t)m.arena_s_ints * 4) + 15) & ~(size_t)15;
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     if (a.sched) {
       int t = 0;
       if (lane == 0) t = atomicAdd(a.sched, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
+      t = __shfl_sync(gmask, t, 0, B2K_G);
       if (t >= a.nenv * nchunks) break;
       chunk_id = t / a.nenv;           // chunk-major: all envs advance together
       env = t - chunk_id * a.nenv;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         while (*done < chunk_id) __nanosleep(256);
         __threadfence();
       }
-      WSYNC();
+      __syncwarp(gmask);
     } else {
       env = blockIdx.x * nwarp + warp;
       if (env >= a.nenv) return;  // whole warp exits; no CTA-wide barrier is used below
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     double* gd = a.garena_d + (size_t)env * m.arena_g_doubles;
     int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
     Env e{(unsigned)(base - smem_raw), (unsigned)(base - smem_raw) + 8u * (unsigned)m.arena_s_doubles, gd, gi, lane,
-          (a.dump != 0 || a.mode == MODE_STEP_BEGIN || a.mode == MODE_STEP_END) ? 1 : 0};
+          gmask, (a.dump != 0 || a.mode == MODE_STEP_BEGIN || a.mode == MODE_STEP_END) ? 1 : 0};
     int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
     double* rec = a.rec + (size_t)env * m.rec_pitch;
 
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     sc.t_prev = a.prof ? clock64() : 0;
     const long long t_item0 = clock64();
     const int cta_envs = min(nwarp, a.nenv - (int)blockIdx.x * nwarp);
-    const int nsync_main = (nwarp > 1 && a.sync_stages && !a.sched) ? cta_envs * 32 : 0;
+    const int nsync_main = (nwarp > 1 && a.sync_stages && !a.sched) ? cta_envs * B2K_G : 0;
     sc.nsync = 0;
 
     // ---- resume a split step: bring the arena back from HBM ----
@@ -285,10 +288,10 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         // mj_checkPos / mj_checkVel
         int bad = 0;
         { const double* q = e.D(B2MJ_F_QPOS); FORL(i, m.nq) bad |= isBad(q[i]); }
-        if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQPOS);
+        if (__any_sync(e.mask, bad)) resetEnv(e, warning, B2MJ_WARN_BADQPOS);
         bad = 0;
         { const double* v = e.D(B2MJ_F_QVEL); FORL(i, m.nv) bad |= isBad(v[i]); }
-        if (__any_sync(0xffffffffu, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
+        if (__any_sync(e.mask, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
       }
       const bool first = a.mode != MODE_STEP_END, second = a.mode != MODE_STEP_BEGIN;
       sc.nsync = nsync_main;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         int bad = 0;
         const double* qa = e.D(B2MJ_F_QACC);
         FORL(i, m.nv) bad |= isBad(qa[i]);
-        if (__any_sync(0xffffffffu, bad)) {
+        if (__any_sync(e.mask, bad)) {
           resetEnv(e, warning, B2MJ_WARN_BADQACC);
           forwardPass(e, a, env, sc, false, true, true);
         }
@@ -387,6 +390,13 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
     if (err != cudaSuccess) return (int)err;
     attr_bytes[dev] = smem_bytes;
   }
+  if (const char* cv = getenv("B2MJ_CARVEOUT")) {  // experiment: shared-memory carveout in percent (more L1 for tables)
+    static int applied = -1;
+    if (applied != atoi(cv)) {
+      cudaFuncSetAttribute(b2k_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+      applied = atoi(cv);
+    }
+  }
   if (!g_shadow_valid[dev] || memcmp(&g_shadow[dev], m, sizeof(DevModel)) != 0) {
     // kernels of another handle may still be reading the constant: drain the device first
     cudaError_t err = cudaDeviceSynchronize();
@@ -399,11 +409,11 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
   if (a->sched) {
     // persistent grid: exactly the CTAs that are co-resident (spinning on a ticket needs its producer running)
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2k_step_kernel, warps_per_cta * 32, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2k_step_kernel, warps_per_cta * B2K_G, smem_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     ctas = std::max(1, std::min(ctas, per_sm * sms));
   }
-  b2k_step_kernel<<<ctas, warps_per_cta * 32, smem_bytes, stream>>>(*a);
+  b2k_step_kernel<<<ctas, warps_per_cta * B2K_G, smem_bytes, stream>>>(*a);
   return (int)cudaGetLastError();
 }
 
