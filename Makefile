@@ -3,18 +3,19 @@
 #   make lib / make oracle
 ROOT    := $(abspath $(dir $(lastword $(MAKEFILE_LIST))))
 CSRC    := $(ROOT)/mujoco_ros_pkgs_b200/csrc
-BUILD   := $(ROOT)/build
+BUILD   ?= $(ROOT)/build
+EXTRA   ?=
 NVCC    ?= /usr/local/cuda/bin/nvcc
 CXX     ?= g++
 CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wextra -I$(ROOT)/include -I$(CSRC)
 NVFLAGS := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
-           -I$(ROOT)/include -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v
+           -I$(ROOT)/include -I$(CSRC) --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
 
 HOST_SRCS := $(wildcard $(CSRC)/model/*.cpp) $(wildcard $(CSRC)/host/*.cpp)
 CUDA_SRCS := $(wildcard $(CSRC)/kernels/*.cu) $(wildcard $(CSRC)/host/*.cu)
 HOST_OBJS := $(patsubst $(CSRC)/%.cpp,$(BUILD)/%.o,$(HOST_SRCS))
 CUDA_OBJS := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.cu.o,$(CUDA_SRCS))
-LIB := $(ROOT)/mujoco_ros_pkgs_b200/libb2mj.so
+LIB ?= $(ROOT)/mujoco_ros_pkgs_b200/libb2mj.so
 
 all: lib oracle
 lib: $(LIB)

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2mj.so")
+# B2MJ_LIB: developer override to load an experimental build of the same library (tools/ sweeps)
+LIB_PATH = os.environ.get("B2MJ_LIB") or os.path.join(_HERE, "libb2mj.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -361,6 +361,57 @@ static int make_layout(Handle* h) {
     if (smem_bytes_env() <= target) break;
     if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1;
   }
+  // Occupancy-driven second tier.  The fused step is latency bound (one dependent chain per env), so what
+  // matters most is that the WHOLE batch is resident at once (one wave): resident envs per SM are limited by
+  // the per-env shared arena.  Fields that are written once and read once by parallel lanes cost one L2
+  // round trip per stage when they live in the env's global arena instead, so they are demoted -- cheapest
+  // first -- until ceil(nenv / #SM) envs fit on an SM (or the register file is the limit).
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int reg_envs = 512 / B2K_G;  // 128 registers per thread
+  // Measured (profiles/r1_layout_sweep.txt): when the whole batch could be resident at once the step is bound by
+  // the slowest env's dependent chain and keeping hot fields on chip wins; once the batch exceeds what the SMs
+  // can hold even fully demoted, resident envs per SM is what buys throughput (18M -> 26M env-steps/s at 16k envs).
+  int goal = h->nenv > sms * reg_envs ? reg_envs : 0;
+  if (const char* env = getenv("B2MJ_ENVS_PER_SM")) goal = std::min(reg_envs, std::max(1, atoi(env)));
+  auto envs_per_sm = [&](int* bestW_out) {
+    const size_t eb = smem_bytes_env();
+    int bestW = 0, bestEnv = 0;
+    const int forceW = getenv("B2MJ_WARPS_PER_CTA") ? atoi(getenv("B2MJ_WARPS_PER_CTA")) : h->force_warps_per_cta;
+    const int wstep = 32 / B2K_G;  // W = envs per CTA (each env is served by B2K_G lanes; CTAs hold whole warps)
+    for (int W = wstep; W <= B2K_MAX_THREADS / B2K_G; W += wstep) {
+      if (forceW && W != forceW) continue;
+      const size_t cta = (size_t)W * (eb + 16);
+      if (cta > kMaxCta) continue;
+      int ctas = (int)(kSmPerSM / (cta + kCtaReserve));
+      ctas = std::min(ctas, reg_envs / W);
+      ctas = std::min(ctas, 32);
+      // among equals prefer the smallest CTA: a finished env frees its shared memory for the next one
+      // immediately instead of waiting for its CTA mates
+      if (ctas * W > bestEnv) { bestEnv = ctas * W; bestW = W; }
+    }
+    if (bestW_out) *bestW_out = bestW;
+    return bestEnv;
+  };
+  {
+    const std::initializer_list<int> tier2 = {
+        B2MJ_F_GEOM_XMAT, B2MJ_F_GEOM_XPOS, B2MJ_F_CRB, B2MJ_F_XQUAT, B2MJ_F_XIPOS, B2MJ_F_XANCHOR, B2MJ_F_XAXIS,
+        B2MJ_F_SITE_XPOS, B2MJ_F_SITE_XMAT, B2MJ_F_ACTUATOR_MOMENT, B2MJ_F_ACTUATOR_LENGTH, B2MJ_F_ACTUATOR_VELOCITY,
+        B2MJ_F_ACTUATOR_FORCE, B2MJ_F_CDOF_DOT, B2MJ_F_CINERT, B2MJ_F_CVEL, B2MJ_F_SUBTREE_COM};
+    const int level = getenv("B2MJ_DEMOTE_LEVEL") ? atoi(getenv("B2MJ_DEMOTE_LEVEL")) : -1;  // experiments: force the first N
+    int n = 0;
+    for (int f : tier2) {
+      if (level >= 0 ? n >= level : envs_per_sm(nullptr) >= goal) break;
+      if (d.fsize[f] && !cold[f]) cold[f] = 1;
+      n++;
+    }
+    // last resort: a smaller on-chip window for the PGS matrix (rows beyond it run from the L2-resident copy)
+    for (int win : {192, 96}) {
+      if (level >= 0 ? n >= level : envs_per_sm(nullptr) >= goal) break;
+      if (xs[XF_EFC_AR_S] > win) xs[XF_EFC_AR_S] = win;
+      n++;
+    }
+  }
   if (smem_bytes_env() + 16 > kMaxCta - kCtaReserve) {
     set_error("model does not fit the per-warp shared-memory arena (" + std::to_string(smem_bytes_env()) +
               " bytes per env even with the constraint working set in HBM)");
@@ -399,24 +450,8 @@ static int make_layout(Handle* h) {
       if (xs[i]) fprintf(stderr, "  x:%-22s %6d f64 %s\n", xnames[i], xs[i], d.xoff_s[i] >= 0 ? "smem" : "HBM");
   }
   const size_t env_bytes = (((size_t)d.arena_s_doubles * 8 + (size_t)d.arena_s_ints * 4) + 15) & ~(size_t)15;
-  // launch shape: warps per CTA maximising resident envs per SM
-  int bestW = 1, bestEnv = 0;
-  // launch shape: as many resident envs per SM as shared memory and the 128-register build allow
-  // (16 warps per SM); among equals prefer the smallest CTA: a finished env frees its shared memory for
-  // the next one immediately instead of waiting for its CTA mates (measured, profiles/r1_sweeps.txt)
-  const int forceW = getenv("B2MJ_WARPS_PER_CTA") ? atoi(getenv("B2MJ_WARPS_PER_CTA")) : h->force_warps_per_cta;
-  // W = envs per CTA (each env is served by B2K_G lanes; CTAs hold whole warps)
-  const int wstep = 32 / B2K_G;
-  for (int W = wstep; W <= B2K_MAX_THREADS / B2K_G; W += wstep) {
-    if (forceW && W != forceW) continue;
-    const size_t cta = (size_t)W * (env_bytes + 16);
-    if (cta > kMaxCta) continue;
-    int ctas = (int)(kSmPerSM / (cta + kCtaReserve));
-    ctas = std::min(ctas, (512 / B2K_G) / W);   // 128 registers per thread -> 512 threads per SM
-    ctas = std::min(ctas, 32);
-    const int envs = ctas * W;
-    if (envs > bestEnv) { bestEnv = envs; bestW = W; }
-  }
+  int bestW = 1;
+  const int bestEnv = envs_per_sm(&bestW);
   if (bestEnv == 0) {
     set_error("model does not fit the shared-memory arena even with all optional arrays in HBM");
     return B2MJ_EUNSUPPORTED;

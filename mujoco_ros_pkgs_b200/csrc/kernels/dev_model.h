@@ -15,11 +15,12 @@
 
 #include "b2mj.h"
 
-// lanes per env (see dev_math.cuh "env-group collectives"): 32 = one env per warp (default), 16 = two envs per
-// warp.  Measured on B200 (profiles/r1_experiments.txt): 16 is ~17% slower on the C2 workload -- the kernel needs the
-// warps for latency hiding more than it gains from halving the instruction stream per env.
+// lanes per env (see dev_math.cuh "env-group collectives"): 32 = one env per warp, 16 = two envs per warp (default).
+// Measured on B200 (profiles/r1_layout_sweep.txt): the step is latency bound per env, so throughput follows the
+// number of resident envs; with 16 lanes the same register file and issue slots carry twice the envs
+// (C2, 4096 envs: 8.8M -> 12.4M env-steps/s; saturated: 18M -> 26M with the occupancy-driven arena layout).
 #ifndef B2K_G
-#define B2K_G 32
+#define B2K_G 16
 #endif
 
 namespace b2k {
