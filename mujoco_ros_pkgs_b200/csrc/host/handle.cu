@@ -357,23 +357,9 @@ static int make_layout(Handle* h) {
   for (int x : {XF_NEWTON_H, XF_EFC_MINVJT, XF_EFC_QUAD, XF_CONTACT_H, XF_EFC_ARDIAG, XF_EFC_JAREF, XF_EFC_JV})
     if (xs[x]) cands.push_back({1, x, (size_t)xs[x] * 8});
   std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.bytes > b.bytes; });
-  for (const Cand& c : cands) {
-    if (smem_bytes_env() <= target) break;
-    if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1;
-  }
-  // Occupancy-driven second tier.  The fused step is latency bound (one dependent chain per env), so what
-  // matters most is that the WHOLE batch is resident at once (one wave): resident envs per SM are limited by
-  // the per-env shared arena.  Fields that are written once and read once by parallel lanes cost one L2
-  // round trip per stage when they live in the env's global arena instead, so they are demoted -- cheapest
-  // first -- until ceil(nenv / #SM) envs fit on an SM (or the register file is the limit).
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const int reg_envs = 512 / B2K_G;  // 128 registers per thread
-  // Measured (profiles/r1_layout_sweep.txt): when the whole batch could be resident at once the step is bound by
-  // the slowest env's dependent chain and keeping hot fields on chip wins; once the batch exceeds what the SMs
-  // can hold even fully demoted, resident envs per SM is what buys throughput (18M -> 26M env-steps/s at 16k envs).
-  int goal = h->nenv > sms * reg_envs ? reg_envs : 0;
-  if (const char* env = getenv("B2MJ_ENVS_PER_SM")) goal = std::min(reg_envs, std::max(1, atoi(env)));
   auto envs_per_sm = [&](int* bestW_out) {
     const size_t eb = smem_bytes_env();
     int bestW = 0, bestEnv = 0;
@@ -393,6 +379,38 @@ static int make_layout(Handle* h) {
     if (bestW_out) *bestW_out = bestW;
     return bestEnv;
   };
+  // Tier 1: demote the constraint / contact working set until the arena meets the target, then keep going only
+  // while that removes a whole WAVE of a per-step launch (waves = ceil(nenv / resident envs); e.g. C2 at 4096
+  // envs: 16.0 KB -> 13 envs/SM -> 3 waves, 15.2 KB -> 14 envs/SM -> 2 waves, +14% end to end).
+  {
+    auto waves = [&]() {
+      const int eps = envs_per_sm(nullptr);
+      return eps > 0 ? (h->nenv + eps * sms - 1) / (eps * sms) : 1 << 30;
+    };
+    size_t k = 0;
+    for (; k < cands.size() && smem_bytes_env() > target; k++) {
+      if (cands[k].is_x) xcold[cands[k].id] = 1; else cold[cands[k].id] = 1;
+    }
+    std::vector<char> best_cold = cold, best_xcold = xcold;
+    int best_waves = waves();
+    for (; k < cands.size() && best_waves > 1; k++) {
+      if (cands[k].is_x) xcold[cands[k].id] = 1; else cold[cands[k].id] = 1;
+      const int w = waves();
+      if (w < best_waves) { best_waves = w; best_cold = cold; best_xcold = xcold; }
+    }
+    cold = best_cold;
+    xcold = best_xcold;
+  }
+  // Occupancy-driven second tier.  The fused step is latency bound (one dependent chain per env), so what
+  // matters most is that the WHOLE batch is resident at once (one wave): resident envs per SM are limited by
+  // the per-env shared arena.  Fields that are written once and read once by parallel lanes cost one L2
+  // round trip per stage when they live in the env's global arena instead, so they are demoted -- cheapest
+  // first -- until ceil(nenv / #SM) envs fit on an SM (or the register file is the limit).
+  // Measured (profiles/r1_layout_sweep.txt): when the whole batch could be resident at once the step is bound by
+  // the slowest env's dependent chain and keeping hot fields on chip wins; once the batch exceeds what the SMs
+  // can hold even fully demoted, resident envs per SM is what buys throughput (18M -> 26M env-steps/s at 16k envs).
+  int goal = h->nenv > sms * reg_envs ? reg_envs : 0;
+  if (const char* env = getenv("B2MJ_ENVS_PER_SM")) goal = std::min(reg_envs, std::max(1, atoi(env)));
   {
     const std::initializer_list<int> tier2 = {
         B2MJ_F_GEOM_XMAT, B2MJ_F_GEOM_XPOS, B2MJ_F_CRB, B2MJ_F_XQUAT, B2MJ_F_XIPOS, B2MJ_F_XANCHOR, B2MJ_F_XAXIS,
@@ -739,6 +757,13 @@ static int locate(Handle* h, int f, bool for_write, unsigned char** base, size_t
   if (f == B2MJ_F_XFRC_APPLIED) { *base = (unsigned char*)h->xfrc; *pitch = (size_t)6 * m->nbody * sizeof(double); return 0; }
   if (f == B2MJ_F_MOCAP_POS) { *base = (unsigned char*)h->mocap; *pitch = (size_t)7 * m->nmocap * sizeof(double); return 0; }
   if (f == B2MJ_F_MOCAP_QUAT) { *base = (unsigned char*)(h->mocap + 3 * m->nmocap); *pitch = (size_t)7 * m->nmocap * sizeof(double); return 0; }
+  if (for_write && f == B2MJ_F_QFRC_PASSIVE && h->in_split_step) {
+    // passive hook of a split step (mjcb_passive, mujoco_env.h:247-251): plugins ADD to qfrc_passive; the arena
+    // image written by step_begin is what step_end reloads
+    *base = (unsigned char*)(h->garena_d + d.off_g[f]);
+    *pitch = (size_t)d.arena_g_doubles * sizeof(double);
+    return 0;
+  }
   if (for_write) { set_error(std::string("field '") + b2mj_field_name((b2mj_field)f) + "' is computed, not settable"); return B2MJ_EINVAL; }
   if (f == B2MJ_F_NCON || f == B2MJ_F_NEFC || f == B2MJ_F_SOLVER_ITER) {
     *base = (unsigned char*)(h->stats + (f == B2MJ_F_NCON ? 0 : f == B2MJ_F_NEFC ? 1 : 2));
