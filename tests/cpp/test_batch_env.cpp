@@ -3,6 +3,8 @@
 //                                               StepUnblocked :229-260, num_steps exit :395-424, reset :480-530)
 //   mujoco_ros/test/mujoco_ros_plugin_test.cpp (Control/Passive/LastCallback :97-121, failing load :141-170, reset)
 //   mujoco_ros/test/ros_interface_test.cpp     (initial joint states :300-351)
+//   mujoco_ros_sensors/test/mujoco_sensors_test.cpp (GT == sensordata/cutoff :326-328, noise :335-391)
+//   mujoco_ros_control: control_period gating + writeSim modes (mujoco_ros_control_plugin.cpp:153-194)
 // No gtest in the image: a tiny EXPECT macro set; exit code = number of failed expectations.
 // Usage: test_batch_env <models_dir> [nenv]
 #include <cmath>
@@ -10,6 +12,7 @@
 #include <cstdlib>
 
 #include "b2mj_env.hpp"
+#include "b2mj_plugins.hpp"
 
 using namespace b2mj_ros;
 
@@ -295,6 +298,126 @@ static void test_load_errors() {
   EXPECT_NEAR(env.getDataPtr()->time(0), 0.02, 1e-12);
 }
 
+
+// mujoco_ros_sensors as a BatchPlugin: the lastStage readout publishes float(sensordata / cutoff); registered
+// noise shifts only the flagged dimensions (mujoco_sensors_test.cpp:326-328, 335-391)
+static void test_sensors_plugin() {
+  BatchEnv env(g_nenv);
+  auto* sp = new BatchSensorsPlugin(/*seed=*/7);
+  env.registerPlugin(BatchPluginPtr(sp), {{"type", "mujoco_ros_sensors/MujocoRosSensorsPlugin"}});
+  EXPECT_TRUE(env.load(g_models + "/pendulum_scene.xml"));
+  const b2mjModel* m = env.getModelPtr();
+  EXPECT_TRUE((int)sp->records().size() == m->nsensor);
+  int s_pos = -1, s_quat = -1, s_vel = -1, s_jv = -1;
+  for (int i = 0; i < m->nsensor; i++) {
+    const auto& r = sp->records()[i];
+    if (r.name == "immovable_pos") s_pos = i;
+    if (r.name == "immovable_quat") s_quat = i;
+    if (r.name == "vel_EE") s_vel = i;
+    if (r.name == "vel_joint2") s_jv = i;
+  }
+  EXPECT_TRUE(s_pos >= 0 && s_quat >= 0 && s_vel >= 0 && s_jv >= 0);
+  EXPECT_TRUE(sp->records()[s_pos].msg == BatchSensorsPlugin::POINT_STAMPED && sp->records()[s_pos].frame_id == "world");
+  EXPECT_TRUE(sp->records()[s_quat].msg == BatchSensorsPlugin::QUATERNION_STAMPED);
+  EXPECT_TRUE(sp->records()[s_vel].msg == BatchSensorsPlugin::VECTOR3_STAMPED && sp->records()[s_vel].frame_id == "joint2_site");
+  EXPECT_TRUE(sp->records()[s_jv].msg == BatchSensorsPlugin::SCALAR_STAMPED);
+  // give joint2 a velocity so the velocimeter reads something
+  {
+    BatchData* d = env.getDataPtr();
+    const int dof = m->jnt_dofadr[b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint2")];
+    for (int e = 0; e < g_nenv; e++) d->row(B2MJ_F_QVEL, e)[dof] = 0.5 + 0.01 * e;
+    EXPECT_TRUE(d->commit(B2MJ_F_QVEL));
+  }
+  EXPECT_TRUE(env.step(5));
+  EXPECT_TRUE(sp->readouts() == 5);
+  BatchData* d = env.getDataPtr();
+  d->invalidate();
+  for (int e = 0; e < g_nenv; e++) {
+    const double* sd = d->row(B2MJ_F_SENSORDATA, e);
+    for (int i = 0; i < m->nsensor; i++) {
+      const double cutoff = m->sensor_cutoff[i] > 0 ? m->sensor_cutoff[i] : 1.0;
+      for (int k = 0; k < m->sensor_dim[i]; k++) {
+        const double expect = (double)(float)(sd[m->sensor_adr[i] + k] / cutoff);
+        EXPECT_DOUBLE_EQ(sp->value(e, i)[k], expect);
+        EXPECT_DOUBLE_EQ(sp->groundTruth(e, i)[k], expect);
+      }
+    }
+  }
+  EXPECT_TRUE(std::fabs(sp->value(0, s_jv)[0]) > 1e-3);
+  // noise on dims x (sigma only) and y (mean only) of vel_EE; z untouched
+  BatchSensorsPlugin::NoiseModel nm;
+  nm.sensor_name = "vel_EE"; nm.set_flag = 0x03; nm.mean[0] = 0.0; nm.std[0] = 0.025; nm.mean[1] = 1.0; nm.std[1] = 0.0;
+  BatchSensorsPlugin::NoiseModel unknown;
+  unknown.sensor_name = "no_such_sensor"; unknown.set_flag = 1;
+  EXPECT_TRUE(sp->registerNoiseModels({nm, unknown}));
+  EXPECT_TRUE(env.step(1));
+  double sx = 0, sxx = 0;
+  for (int e = 0; e < g_nenv; e++) {
+    const double* v = sp->value(e, s_vel);
+    const double* g = sp->groundTruth(e, s_vel);
+    EXPECT_NEAR(v[1] - g[1], 1.0, 1e-6);
+    EXPECT_DOUBLE_EQ(v[2], g[2]);
+    sx += v[0] - g[0]; sxx += (v[0] - g[0]) * (v[0] - g[0]);
+    EXPECT_DOUBLE_EQ(sp->value(e, s_pos)[0], sp->groundTruth(e, s_pos)[0]);  // other sensors stay noise-free
+  }
+  if (g_nenv >= 32) { EXPECT_TRUE(std::fabs(sx / g_nenv) < 0.02); EXPECT_TRUE(sxx / g_nenv > 1e-5 && sxx / g_nenv < 0.003); }
+}
+
+// mujoco_ros_control as a BatchPlugin: update gated to control_period, write every step, e-stop zeroes efforts
+static void test_control_plugin() {
+  BatchEnv env(g_nenv);
+  std::vector<BatchRosControlPlugin::Joint> joints(2);
+  joints[0].name = "joint1"; joints[0].control_mode = B2MJ_CTRL_EFFORT; joints[0].effort_limit = 87; joints[0].lower = -2.8973; joints[0].upper = 2.8973;
+  joints[1].name = "joint4"; joints[1].control_mode = B2MJ_CTRL_POSITION_PID; joints[1].effort_limit = 87;
+  joints[1].pid[0] = 300; joints[1].pid[2] = 30; joints[1].lower = -3.0718; joints[1].upper = -0.0698;
+  int n_calls = 0; bool saw_reset = false; double last_period = -1;
+  auto controller = [&](double /*time*/, double period, bool reset_ctrls, int nenv, int nj, const double* pos, const double* /*vel*/,
+                        const double* /*eff*/, double* cmd) {
+    n_calls++; saw_reset |= reset_ctrls; last_period = period;
+    for (int e = 0; e < nenv; e++) { cmd[e * nj + 0] = 2.5; cmd[e * nj + 1] = -1.2; }
+    (void)pos;
+  };
+  auto* cp = new BatchRosControlPlugin(joints, controller, /*control_period=*/0.01);
+  env.registerPlugin(BatchPluginPtr(cp), {{"type", "mujoco_ros_control/MujocoRosControlPlugin"}});
+  auto* missing = new BatchRosControlPlugin({{"no_such_joint", B2MJ_CTRL_EFFORT}}, controller);
+  env.registerPlugin(BatchPluginPtr(missing));
+  EXPECT_TRUE(env.load(g_models + "/panda_like.xml"));
+  EXPECT_TRUE(cp->loaded());
+  EXPECT_FALSE(missing->loaded());
+  const b2mjModel* m = env.getModelPtr();
+  const double dt = m->opt.timestep;  // 0.002
+  EXPECT_TRUE(env.step(1));           // t = 0 inside the hook: no update, no write (ros::Time zero)
+  EXPECT_TRUE(cp->updates() == 0 && cp->writes() == 0);
+  EXPECT_TRUE(env.step(1));           // t = dt: first update (reset_ctrls) + first write
+  EXPECT_TRUE(cp->updates() == 1 && cp->writes() == 1 && saw_reset);
+  EXPECT_NEAR(last_period, dt, 1e-12);
+  EXPECT_TRUE(env.step(20));
+  EXPECT_TRUE(cp->writes() == 21);                       // writeSim every step
+  EXPECT_TRUE(cp->updates() >= 4 && cp->updates() <= 5);  // controller only every control_period (5 steps)
+  EXPECT_TRUE(n_calls == cp->updates());
+  BatchData* d = env.getDataPtr();
+  d->invalidate();
+  const int d1 = m->jnt_dofadr[b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint1")], j4 = b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint4");
+  for (int e = 0; e < g_nenv; e++) EXPECT_DOUBLE_EQ(d->row(B2MJ_F_QFRC_APPLIED, e)[d1], 2.5);  // EFFORT: qfrc_applied = cmd
+  // POSITION_PID pulls joint4 from qpos0 towards the target (the model's own position actuator holds against it)
+  const double q4_0 = m->qpos0[m->jnt_qposadr[j4]];
+  EXPECT_TRUE(env.step(600));
+  d->invalidate();
+  const double q4 = d->row(B2MJ_F_QPOS, g_nenv - 1)[m->jnt_qposadr[j4]];
+  EXPECT_TRUE(std::fabs(q4 - (-1.2)) < 0.8 * std::fabs(q4_0 - (-1.2)));
+  // e-stop: efforts go to zero on the next write (default_robot_hw_sim.cpp:271-275)
+  cp->eStopActive(true);
+  EXPECT_TRUE(env.step(6));  // spans a controller update, where the e-stop is latched (:177-179)
+  d->invalidate();
+  EXPECT_DOUBLE_EQ(d->row(B2MJ_F_QFRC_APPLIED, 0)[d1], 0.0);
+  cp->eStopActive(false);
+  saw_reset = false;
+  EXPECT_TRUE(env.step(6));
+  EXPECT_TRUE(saw_reset);  // controllers are reset after an e-stop release (:181-184)
+  d->invalidate();
+  EXPECT_DOUBLE_EQ(d->row(B2MJ_F_QFRC_APPLIED, 0)[d1], 2.5);
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { std::printf("usage: %s <models_dir> [nenv]\n", argv[0]); return 2; }
   g_models = argv[1];
@@ -314,6 +437,8 @@ int main(int argc, char** argv) {
   test_hook_semantics();
   test_initial_joint_states();
   test_load_errors();
+  test_sensors_plugin();
+  test_control_plugin();
   std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "OK", g_checks, g_fail);
   return g_fail ? 1 : 0;
 }

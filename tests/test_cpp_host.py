@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "mujoco_ros_pkgs_b200")
 BIN = os.path.join(ROOT, "build", "tests", "test_batch_env")
 SRC = os.path.join(ROOT, "tests", "cpp", "test_batch_env.cpp")
-HDRS = [os.path.join(ROOT, "include", h) for h in ("b2mj.h", "b2mj_env.hpp")]
+HDRS = [os.path.join(ROOT, "include", h) for h in ("b2mj.h", "b2mj_env.hpp", "b2mj_plugins.hpp")]
 
 
 def build_binary():
