@@ -393,7 +393,7 @@ static int make_layout(Handle* h) {
     }
     std::vector<char> best_cold = cold, best_xcold = xcold;
     int best_waves = waves();
-    for (; k < cands.size() && best_waves > 1; k++) {
+    for (; k < cands.size() && best_waves > 1 && !getenv("B2MJ_NO_WAVE_FIT"); k++) {
       if (cands[k].is_x) xcold[cands[k].id] = 1; else cold[cands[k].id] = 1;
       const int w = waves();
       if (w < best_waves) { best_waves = w; best_cold = cold; best_xcold = xcold; }
@@ -401,35 +401,10 @@ static int make_layout(Handle* h) {
     cold = best_cold;
     xcold = best_xcold;
   }
-  // Occupancy-driven second tier.  The fused step is latency bound (one dependent chain per env), so what
-  // matters most is that the WHOLE batch is resident at once (one wave): resident envs per SM are limited by
-  // the per-env shared arena.  Fields that are written once and read once by parallel lanes cost one L2
-  // round trip per stage when they live in the env's global arena instead, so they are demoted -- cheapest
-  // first -- until ceil(nenv / #SM) envs fit on an SM (or the register file is the limit).
-  // Measured (profiles/r1_layout_sweep.txt): when the whole batch could be resident at once the step is bound by
-  // the slowest env's dependent chain and keeping hot fields on chip wins; once the batch exceeds what the SMs
-  // can hold even fully demoted, resident envs per SM is what buys throughput (18M -> 26M env-steps/s at 16k envs).
-  int goal = h->nenv > sms * reg_envs ? reg_envs : 0;
-  if (const char* env = getenv("B2MJ_ENVS_PER_SM")) goal = std::min(reg_envs, std::max(1, atoi(env)));
-  {
-    const std::initializer_list<int> tier2 = {
-        B2MJ_F_GEOM_XMAT, B2MJ_F_GEOM_XPOS, B2MJ_F_CRB, B2MJ_F_XQUAT, B2MJ_F_XIPOS, B2MJ_F_XANCHOR, B2MJ_F_XAXIS,
-        B2MJ_F_SITE_XPOS, B2MJ_F_SITE_XMAT, B2MJ_F_ACTUATOR_MOMENT, B2MJ_F_ACTUATOR_LENGTH, B2MJ_F_ACTUATOR_VELOCITY,
-        B2MJ_F_ACTUATOR_FORCE, B2MJ_F_CDOF_DOT, B2MJ_F_CINERT, B2MJ_F_CVEL, B2MJ_F_SUBTREE_COM};
-    const int level = getenv("B2MJ_DEMOTE_LEVEL") ? atoi(getenv("B2MJ_DEMOTE_LEVEL")) : -1;  // experiments: force the first N
-    int n = 0;
-    for (int f : tier2) {
-      if (level >= 0 ? n >= level : envs_per_sm(nullptr) >= goal) break;
-      if (d.fsize[f] && !cold[f]) cold[f] = 1;
-      n++;
-    }
-    // last resort: a smaller on-chip window for the PGS matrix (rows beyond it run from the L2-resident copy)
-    for (int win : {192, 96}) {
-      if (level >= 0 ? n >= level : envs_per_sm(nullptr) >= goal) break;
-      if (xs[XF_EFC_AR_S] > win) xs[XF_EFC_AR_S] = win;
-      n++;
-    }
-  }
+  // A second tier that also demoted write-once/read-once kinematic fields (geom frames, crb, cinert, cvel, ...)
+  // was measured and dropped (profiles/r1_layout_sweep.txt): it buys throughput only for contact-free batches far
+  // beyond one wave (18M -> 26M env-steps/s at 16k envs) and costs ~8% at the BASELINE batch because every access
+  // to a demotable field goes through a generic pointer instead of an LDS address.
   if (smem_bytes_env() + 16 > kMaxCta - kCtaReserve) {
     set_error("model does not fit the per-warp shared-memory arena (" + std::to_string(smem_bytes_env()) +
               " bytes per env even with the constraint working set in HBM)");

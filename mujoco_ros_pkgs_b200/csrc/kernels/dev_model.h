@@ -15,12 +15,14 @@
 
 #include "b2mj.h"
 
-// lanes per env (see dev_math.cuh "env-group collectives"): 32 = one env per warp, 16 = two envs per warp (default).
-// Measured on B200 (profiles/r1_layout_sweep.txt): the step is latency bound per env, so throughput follows the
-// number of resident envs; with 16 lanes the same register file and issue slots carry twice the envs
-// (C2, 4096 envs: 8.8M -> 12.4M env-steps/s; saturated: 18M -> 26M with the occupancy-driven arena layout).
+// lanes per env (see dev_math.cuh "env-group collectives"): 32 = one env per warp (default), 16 = two envs per warp.
+// Measured on B200 at the BASELINE config (C2, 4096 envs, 100 + 1000 steps of random control, profiles/
+// r1_layout_sweep.txt): 16 lanes win only while the batch is contact free (12.4M vs 8.8M env-steps/s over the
+// first 300 steps); once contacts appear the two envs of a warp serialise each other's solver iterations and the
+// partial-mask collectives cost extra instructions: 32 lanes give 9.0M / 6.2M / 5.4M (rollout / per-step / end to
+// end) against 8.3M / 5.2M / 4.7M.
 #ifndef B2K_G
-#define B2K_G 16
+#define B2K_G 32
 #endif
 
 namespace b2k {

@@ -401,8 +401,8 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
     WSYNC();
     return 0;
   }
-  const double* gxpos = e.DG(B2MJ_F_GEOM_XPOS);
-  const double* gxmat = e.DG(B2MJ_F_GEOM_XMAT);
+  const double* gxpos = e.D(B2MJ_F_GEOM_XPOS);
+  const double* gxmat = e.D(B2MJ_F_GEOM_XMAT);
   double* c_dist = e.DG(B2MJ_F_CONTACT_DIST);
   double* c_pos = e.DG(B2MJ_F_CONTACT_POS);
   double* c_frame = e.DG(B2MJ_F_CONTACT_FRAME);

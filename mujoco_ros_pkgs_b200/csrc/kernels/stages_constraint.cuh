@@ -74,7 +74,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
   }
   EfcPtrs P = efcPtrs(e);
   const double* cdof = e.D(B2MJ_F_CDOF);
-  const double* com = e.DG(B2MJ_F_SUBTREE_COM);
+  const double* com = e.D(B2MJ_F_SUBTREE_COM);
   const double* qpos = e.D(B2MJ_F_QPOS);
   int row = 0, full = 0;
 
@@ -82,7 +82,7 @@ __device__ __noinline__ int stage_makeConstraint(const Env e, int ncon, int* war
   if (m.neq && !(m.opt.disableflags & B2MJ_DSBL_EQUALITY)) {
     const double* xpos = e.D(B2MJ_F_XPOS);
     const double* xmat = e.D(B2MJ_F_XMAT);
-    const double* xquat = e.DG(B2MJ_F_XQUAT);
+    const double* xquat = e.D(B2MJ_F_XQUAT);
     B2K_NOUNROLL for (int q = 0; q < m.neq; q++) {
       if (!m.eq_active[q]) continue;
       const int et = m.eq_type[q], id0 = m.eq_obj1id[q], id1 = m.eq_obj2id[q];

@@ -23,18 +23,18 @@ __device__ __forceinline__ void sens_cutoff(int i, double* out) {
 __device__ __forceinline__ void sens_frame(const Env e, int type, int id, const double** pos, const double** mat,
                                            double* quat) {
   const DevModel& m = c_dm;
-  const double* xquat = e.DG(B2MJ_F_XQUAT);
+  const double* xquat = e.D(B2MJ_F_XQUAT);
   switch (type) {
     case B2MJ_OBJ_BODY:
-      *pos = e.DG(B2MJ_F_XIPOS) + 3 * id; *mat = e.DG(B2MJ_F_XIMAT) + 9 * id;
+      *pos = e.D(B2MJ_F_XIPOS) + 3 * id; *mat = e.DG(B2MJ_F_XIMAT) + 9 * id;
       mulQuat(quat, xquat + 4 * id, m.body_iquat + 4 * id);
       break;
     case B2MJ_OBJ_GEOM:
-      *pos = e.DG(B2MJ_F_GEOM_XPOS) + 3 * id; *mat = e.DG(B2MJ_F_GEOM_XMAT) + 9 * id;
+      *pos = e.D(B2MJ_F_GEOM_XPOS) + 3 * id; *mat = e.D(B2MJ_F_GEOM_XMAT) + 9 * id;
       mulQuat(quat, xquat + 4 * m.geom_bodyid[id], m.geom_quat + 4 * id);
       break;
     case B2MJ_OBJ_SITE:
-      *pos = e.DG(B2MJ_F_SITE_XPOS) + 3 * id; *mat = e.DG(B2MJ_F_SITE_XMAT) + 9 * id;
+      *pos = e.D(B2MJ_F_SITE_XPOS) + 3 * id; *mat = e.D(B2MJ_F_SITE_XMAT) + 9 * id;
       mulQuat(quat, xquat + 4 * m.site_bodyid[id], m.site_quat + 4 * id);
       break;
     default:
@@ -55,7 +55,7 @@ __device__ __forceinline__ void objVelocity(const Env e, int type, int id, doubl
   double q[4];
   sens_frame(e, type, id, &pos, &mat, q);
   const int b = sens_body(type, id);
-  transformSpatial(res, e.DG(B2MJ_F_CVEL) + 6 * b, 0, pos, e.DG(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b], local ? mat : nullptr);
+  transformSpatial(res, e.D(B2MJ_F_CVEL) + 6 * b, 0, pos, e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b], local ? mat : nullptr);
 }
 __device__ __forceinline__ void objAcceleration(const Env e, int type, int id, double* res, int local) {
   const DevModel& m = c_dm;
@@ -63,9 +63,9 @@ __device__ __forceinline__ void objAcceleration(const Env e, int type, int id, d
   double q[4], vel[6], corr[3];
   sens_frame(e, type, id, &pos, &mat, q);
   const int b = sens_body(type, id);
-  const double* com = e.DG(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b];
+  const double* com = e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[b];
   transformSpatial(res, e.DG(B2MJ_F_CACC) + 6 * b, 0, pos, com, local ? mat : nullptr);
-  transformSpatial(vel, e.DG(B2MJ_F_CVEL) + 6 * b, 0, pos, com, local ? mat : nullptr);
+  transformSpatial(vel, e.D(B2MJ_F_CVEL) + 6 * b, 0, pos, com, local ? mat : nullptr);
   cross(corr, vel, vel + 3);
   addTo3(res + 3, corr);
 }
@@ -88,10 +88,10 @@ __device__ __noinline__ void stage_sensorPos(const Env e, int nefc) {
     const int type = m.sensor_type[i], objid = m.sensor_objid[i];
     double* out = sd + m.sensor_adr[i];
     switch (type) {
-      case B2MJ_SENS_MAGNETOMETER: rotVecMatT(out, m.opt.magnetic, e.DG(B2MJ_F_SITE_XMAT) + 9 * objid); break;
+      case B2MJ_SENS_MAGNETOMETER: rotVecMatT(out, m.opt.magnetic, e.D(B2MJ_F_SITE_XMAT) + 9 * objid); break;
       case B2MJ_SENS_JOINTPOS: out[0] = qpos[m.jnt_qposadr[objid]]; break;
       case B2MJ_SENS_TENDONPOS: out[0] = e.D(B2MJ_F_TEN_LENGTH)[objid]; break;
-      case B2MJ_SENS_ACTUATORPOS: out[0] = e.DG(B2MJ_F_ACTUATOR_LENGTH)[objid]; break;
+      case B2MJ_SENS_ACTUATORPOS: out[0] = e.D(B2MJ_F_ACTUATOR_LENGTH)[objid]; break;
       case B2MJ_SENS_BALLQUAT: copy4(out, qpos + m.jnt_qposadr[objid]); normalize4(out); break;
       case B2MJ_SENS_JOINTLIMITPOS:
       case B2MJ_SENS_TENDONLIMITPOS: {
@@ -124,7 +124,7 @@ __device__ __noinline__ void stage_sensorPos(const Env e, int nefc) {
         }
         break;
       }
-      case B2MJ_SENS_SUBTREECOM: copy3(out, e.DG(B2MJ_F_SUBTREE_COM) + 3 * objid); break;
+      case B2MJ_SENS_SUBTREECOM: copy3(out, e.D(B2MJ_F_SUBTREE_COM) + 3 * objid); break;
       case B2MJ_SENS_CLOCK: out[0] = e.D(B2MJ_F_TIME)[0]; break;
       default: break;
     }
@@ -141,8 +141,8 @@ __device__ __noinline__ void subtreeVel_lane0(const Env e) {
     double* angmom = e.X(XF_SUBTREE_ANGMOM);
     double* bodyvel = e.X(XF_BODYVEL);
     const double* ximat = e.DG(B2MJ_F_XIMAT);
-    const double* xipos = e.DG(B2MJ_F_XIPOS);
-    const double* com = e.DG(B2MJ_F_SUBTREE_COM);
+    const double* xipos = e.D(B2MJ_F_XIPOS);
+    const double* com = e.D(B2MJ_F_SUBTREE_COM);
     const int nb = m.nbody;
     B2K_NOUNROLL for (int i = 0; i < nb; i++) {
       objVelocity(e, B2MJ_OBJ_BODY, i, bodyvel + 6 * i, 0);
@@ -191,7 +191,7 @@ __device__ __noinline__ void stage_sensorVel(const Env e, int nefc) {
       case B2MJ_SENS_GYRO: objVelocity(e, B2MJ_OBJ_SITE, objid, tmp, 1); copy3(out, tmp); break;
       case B2MJ_SENS_JOINTVEL: out[0] = qvel[m.jnt_dofadr[objid]]; break;
       case B2MJ_SENS_TENDONVEL: out[0] = e.D(B2MJ_F_TEN_VELOCITY)[objid]; break;
-      case B2MJ_SENS_ACTUATORVEL: out[0] = e.DG(B2MJ_F_ACTUATOR_VELOCITY)[objid]; break;
+      case B2MJ_SENS_ACTUATORVEL: out[0] = e.D(B2MJ_F_ACTUATOR_VELOCITY)[objid]; break;
       case B2MJ_SENS_BALLANGVEL: copy3(out, qvel + m.jnt_dofadr[objid]); break;
       case B2MJ_SENS_JOINTLIMITVEL:
       case B2MJ_SENS_TENDONLIMITVEL: {
@@ -253,12 +253,12 @@ __device__ __forceinline__ void contactForce(const Env e, int c, double* lfrc) {
 __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* xfrc) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
-  const double* cdof_dot = e.DG(B2MJ_F_CDOF_DOT);
-  const double* cvel = e.DG(B2MJ_F_CVEL);
-  const double* cinert = e.DG(B2MJ_F_CINERT);
+  const double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
+  const double* cvel = e.D(B2MJ_F_CVEL);
+  const double* cinert = e.D(B2MJ_F_CINERT);
   const double* qvel = e.D(B2MJ_F_QVEL);
   const double* qacc = e.D(B2MJ_F_QACC);
-  const double* com = e.DG(B2MJ_F_SUBTREE_COM);
+  const double* com = e.D(B2MJ_F_SUBTREE_COM);
   double* cacc = e.DG(B2MJ_F_CACC);
   double* cint = e.DG(B2MJ_F_CFRC_INT);
   double* cext = e.DG(B2MJ_F_CFRC_EXT);
@@ -270,7 +270,7 @@ __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* 
         const double* x = xfrc + 6 * b;
         if (!(x[0] == 0 && x[1] == 0 && x[2] == 0 && x[3] == 0 && x[4] == 0 && x[5] == 0)) {
           double corr[6] = {x[3], x[4], x[5], x[0], x[1], x[2]}, f[6];
-          transformSpatial(f, corr, 1, com + 3 * m.body_rootid[b], e.DG(B2MJ_F_XIPOS) + 3 * b, nullptr);
+          transformSpatial(f, corr, 1, com + 3 * m.body_rootid[b], e.D(B2MJ_F_XIPOS) + 3 * b, nullptr);
           for (int k = 0; k < 6; k++) acc[k] += f[k];
         }
       }
@@ -331,8 +331,8 @@ __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* 
 __device__ __forceinline__ bool pointInSite(const Env e, int site, const double* p) {
   const DevModel& m = c_dm;
   double dif[3], loc[3];
-  sub3(dif, p, e.DG(B2MJ_F_SITE_XPOS) + 3 * site);
-  rotVecMatT(loc, dif, e.DG(B2MJ_F_SITE_XMAT) + 9 * site);
+  sub3(dif, p, e.D(B2MJ_F_SITE_XPOS) + 3 * site);
+  rotVecMatT(loc, dif, e.D(B2MJ_F_SITE_XMAT) + 9 * site);
   const double* s = m.site_size + 3 * site;
   switch (m.site_type[site]) {
     case B2MJ_GEOM_SPHERE: return dot3(loc, loc) <= s[0] * s[0];
@@ -382,14 +382,14 @@ __device__ __noinline__ void stage_sensorAcc(const Env e, int nefc, int ncon, co
         const int body = m.site_bodyid[objid];
         double f[6], dif[3], cr[3];
         const double* w = e.DG(B2MJ_F_CFRC_INT) + 6 * body;
-        sub3(dif, e.DG(B2MJ_F_SITE_XPOS) + 3 * objid, e.DG(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[body]);
+        sub3(dif, e.D(B2MJ_F_SITE_XPOS) + 3 * objid, e.D(B2MJ_F_SUBTREE_COM) + 3 * m.body_rootid[body]);
         cross(cr, dif, w + 3);
         sub3(f, w, cr);
         copy3(f + 3, w + 3);
-        rotVecMatT(out, type == B2MJ_SENS_FORCE ? f + 3 : f, e.DG(B2MJ_F_SITE_XMAT) + 9 * objid);
+        rotVecMatT(out, type == B2MJ_SENS_FORCE ? f + 3 : f, e.D(B2MJ_F_SITE_XMAT) + 9 * objid);
         break;
       }
-      case B2MJ_SENS_ACTUATORFRC: out[0] = e.DG(B2MJ_F_ACTUATOR_FORCE)[objid]; break;
+      case B2MJ_SENS_ACTUATORFRC: out[0] = e.D(B2MJ_F_ACTUATOR_FORCE)[objid]; break;
       case B2MJ_SENS_JOINTACTFRC: out[0] = e.D(B2MJ_F_QFRC_ACTUATOR)[m.jnt_dofadr[objid]]; break;
       case B2MJ_SENS_JOINTLIMITFRC:
       case B2MJ_SENS_TENDONLIMITFRC: {

@@ -41,12 +41,12 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
   const DevModel& m = c_dm;
   double* qpos = e.D(B2MJ_F_QPOS);
   double* xpos = e.D(B2MJ_F_XPOS);
-  double* xquat = e.DG(B2MJ_F_XQUAT);
+  double* xquat = e.D(B2MJ_F_XQUAT);
   double* xmat = e.D(B2MJ_F_XMAT);
-  double* xipos = e.DG(B2MJ_F_XIPOS);
+  double* xipos = e.D(B2MJ_F_XIPOS);
   double* ximat = e.DG(B2MJ_F_XIMAT);
-  double* xanchor = e.DG(B2MJ_F_XANCHOR);
-  double* xaxis = e.DG(B2MJ_F_XAXIS);
+  double* xanchor = e.D(B2MJ_F_XANCHOR);
+  double* xaxis = e.D(B2MJ_F_XAXIS);
   double* T0 = e.X(XF_SCRATCH);
   double* T1 = T0 + 7 * m.nbody;
   double* mocap_pos = m.nmocap ? e.D(B2MJ_F_MOCAP_POS) : nullptr;
@@ -157,8 +157,8 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
       copy3(xaxis + 3 * j, x);
     }
   }
-  double* gxpos = e.DG(B2MJ_F_GEOM_XPOS);
-  double* gxmat = e.DG(B2MJ_F_GEOM_XMAT);
+  double* gxpos = e.D(B2MJ_F_GEOM_XPOS);
+  double* gxmat = e.D(B2MJ_F_GEOM_XMAT);
   FORL(i, m.ngeom) {
     const int b = m.geom_bodyid[i];
     double v[3], q[4];
@@ -168,8 +168,8 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
     quat2Mat(gxmat + 9 * i, q);
   }
   if (m.nsite) {
-    double* sxpos = e.DG(B2MJ_F_SITE_XPOS);
-    double* sxmat = e.DG(B2MJ_F_SITE_XMAT);
+    double* sxpos = e.D(B2MJ_F_SITE_XPOS);
+    double* sxmat = e.D(B2MJ_F_SITE_XMAT);
     FORL(i, m.nsite) {
       const int b = m.site_bodyid[i];
       double v[3], q[4];
@@ -185,13 +185,13 @@ __device__ __noinline__ void stage_kinematics(const Env e) {
 // mj_comPos: subtree sums are gathers over the subtree bit masks (one lane per body)
 __device__ __noinline__ void stage_comPos(const Env e) {
   const DevModel& m = c_dm;
-  const double* xipos = e.DG(B2MJ_F_XIPOS);
-  const double* xquat = e.DG(B2MJ_F_XQUAT);
+  const double* xipos = e.D(B2MJ_F_XIPOS);
+  const double* xquat = e.D(B2MJ_F_XQUAT);
   const double* xmat = e.D(B2MJ_F_XMAT);
-  const double* xanchor = e.DG(B2MJ_F_XANCHOR);
-  const double* xaxis = e.DG(B2MJ_F_XAXIS);
-  double* com = e.DG(B2MJ_F_SUBTREE_COM);
-  double* cinert = e.DG(B2MJ_F_CINERT);
+  const double* xanchor = e.D(B2MJ_F_XANCHOR);
+  const double* xaxis = e.D(B2MJ_F_XAXIS);
+  double* com = e.D(B2MJ_F_SUBTREE_COM);
+  double* cinert = e.D(B2MJ_F_CINERT);
   double* cdof = e.D(B2MJ_F_CDOF);
   FORL(b, m.nbody) {
     const double sm = m.body_subtreemass[b];
@@ -269,8 +269,8 @@ __device__ __noinline__ void stage_tendon_transmission(const Env e) {
     WSYNC();
   }
   if (m.nu) {
-    double* al = e.DG(B2MJ_F_ACTUATOR_LENGTH);
-    double* am = e.DG(B2MJ_F_ACTUATOR_MOMENT);
+    double* al = e.D(B2MJ_F_ACTUATOR_LENGTH);
+    double* am = e.D(B2MJ_F_ACTUATOR_MOMENT);
     const double* tl = m.ntendon ? e.D(B2MJ_F_TEN_LENGTH) : nullptr;
     const double* tJ = m.ntendon ? e.D(B2MJ_F_TEN_J) : nullptr;
     // one lane per (actuator, dof) entry of the moment matrix
@@ -412,17 +412,13 @@ __device__ __noinline__ void mulM_warp(const Env e, double* res, const double* v
 // matrices IN REGISTERS; per pivot the pivot row travels by shuffles, so the dependent chain per pivot is
 // shuffle -> reciprocal -> FMA instead of a shared-memory round trip per element (the shared-memory version
 // was 20% of the step's instructions).  Same operation order as the row-by-row elimination it replaces.
-template <int NV, bool TWO>
-__device__ __forceinline__ void invertSPD2_regT(const Env e, double* A, double* Bm, int n) {
-  const int i = e.lane;
-  const bool own = i < n;
-  double a[NV], b[NV];
+template <int NV>
+__device__ __forceinline__ void invertSPD_regT(const Env e, double* Mx, int n, int i) {
+  // i = row owned by this lane (0..15 within its 16-lane segment); Mx = the matrix this segment inverts
+  const bool own = Mx != nullptr && i < n;
+  double a[NV];
 #pragma unroll
-  for (int j = 0; j < NV; j++) {
-    const bool in = own && j < n;
-    a[j] = in ? A[i * n + j] : (i == j ? 1.0 : 0.0);
-    if (TWO) b[j] = in ? Bm[i * n + j] : (i == j ? 1.0 : 0.0);
-  }
+  for (int j = 0; j < NV; j++) a[j] = (own && j < n) ? Mx[i * n + j] : (i == j ? 1.0 : 0.0);
   // Rolled pivot loop (the megakernel is instruction-fetch bound: straight-line code measured slower in the
   // desynchronised rollout).  The row is rotated left by one column per pivot, so the pivot column is always
   // register 0 and the finished column re-enters at register NV-1: static register indices in a rolled loop.
@@ -430,47 +426,39 @@ __device__ __forceinline__ void invertSPD2_regT(const Env e, double* A, double* 
   // and complete the NV rotations that bring the columns back in place.
   B2K_NOUNROLL for (int k = 0; k < NV; k++) {
     const bool piv = i == k;
-    {
-      const double ia = 1.0 / __shfl_sync(e.mask, a[0], k, B2K_G);
-      const double fa = a[0] * ia;
+    const double ia = 1.0 / __shfl_sync(e.mask, a[0], k, 16);
+    const double fa = a[0] * ia;
 #pragma unroll
-      for (int j = 1; j < NV; j++) {
-        const double pj = __shfl_sync(e.mask, a[j], k, B2K_G);
-        a[j - 1] = piv ? pj * ia : a[j] - fa * pj;
-      }
-      a[NV - 1] = piv ? ia : -fa;
+    for (int j = 1; j < NV; j++) {
+      const double pj = __shfl_sync(e.mask, a[j], k, 16);
+      a[j - 1] = piv ? pj * ia : a[j] - fa * pj;
     }
-    if (TWO) {
-      const double ib = 1.0 / __shfl_sync(e.mask, b[0], k, B2K_G);
-      const double fb = b[0] * ib;
-#pragma unroll
-      for (int j = 1; j < NV; j++) {
-        const double pj = __shfl_sync(e.mask, b[j], k, B2K_G);
-        b[j - 1] = piv ? pj * ib : b[j] - fb * pj;
-      }
-      b[NV - 1] = piv ? ib : -fb;
-    }
+    a[NV - 1] = piv ? ia : -fa;
   }
 #pragma unroll
-  for (int j = 0; j < NV; j++) {
-    if (own && j < n) {
-      A[i * n + j] = a[j];
-      if (TWO) Bm[i * n + j] = b[j];
-    }
-  }
-  WSYNC();
+  for (int j = 0; j < NV; j++)
+    if (own && j < n) Mx[i * n + j] = a[j];
 }
 
+// Inverts A and (optionally) Bm in place.  One env per warp (B2K_G == 32): the two 16-lane segments invert the
+// two matrices side by side; two envs per warp (B2K_G == 16): one after the other.
 __device__ __noinline__ void invertSPD2(const Env e, double* A, double* Bm, int n) {
-  if (Bm) {
-    if (n <= 8) invertSPD2_regT<8, true>(e, A, Bm, n);
-    else if (n <= 12) invertSPD2_regT<12, true>(e, A, Bm, n);
-    else invertSPD2_regT<16, true>(e, A, Bm, n);
-  } else {
-    if (n <= 8) invertSPD2_regT<8, false>(e, A, nullptr, n);
-    else if (n <= 12) invertSPD2_regT<12, false>(e, A, nullptr, n);
-    else invertSPD2_regT<16, false>(e, A, nullptr, n);
+  const int i = e.lane & 15;
+#if B2K_G == 32
+  double* Mx = (e.lane >> 4) ? Bm : A;
+  if (n <= 8) invertSPD_regT<8>(e, Mx, n, i);
+  else if (n <= 12) invertSPD_regT<12>(e, Mx, n, i);
+  else invertSPD_regT<16>(e, Mx, n, i);
+#else
+  B2K_NOUNROLL for (int mat = 0; mat < 2; mat++) {
+    double* Mx = mat ? Bm : A;
+    if (!Mx) continue;
+    if (n <= 8) invertSPD_regT<8>(e, Mx, n, i);
+    else if (n <= 12) invertSPD_regT<12>(e, Mx, n, i);
+    else invertSPD_regT<16>(e, Mx, n, i);
   }
+#endif
+  WSYNC();
 }
 
 // out = Ainv * in for a dense nv x nv matrix (out != in)
@@ -486,9 +474,9 @@ __device__ __forceinline__ void mulDense_warp(const Env e, double* out, const do
 // mj_crb + mj_factorM, plus the Euler-damping matrix qH = qM + h diag(damping) factored alongside
 __device__ __noinline__ void stage_crb_factor(const Env e, bool want_ld) {
   const DevModel& m = c_dm;
-  const double* cinert = e.DG(B2MJ_F_CINERT);
+  const double* cinert = e.D(B2MJ_F_CINERT);
   const double* cdof = e.D(B2MJ_F_CDOF);
-  double* crb = e.DG(B2MJ_F_CRB);
+  double* crb = e.D(B2MJ_F_CRB);
   double* qM = e.D(B2MJ_F_QM);
   double* qLD = e.DG(B2MJ_F_QLD);
   double* buf = e.X(XF_SCRATCH) + 10 * 0;
@@ -571,8 +559,8 @@ __device__ __noinline__ void stage_comVel(const Env e) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
   const double* qvel = e.D(B2MJ_F_QVEL);
-  double* cvelA = e.DG(B2MJ_F_CVEL);
-  double* cdof_dot = e.DG(B2MJ_F_CDOF_DOT);
+  double* cvelA = e.D(B2MJ_F_CVEL);
+  double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
   FORL(b, m.nbody) {
     double s[6] = {0, 0, 0, 0, 0, 0};
     const unsigned* mask = m.body_dofmask + b * m.nmaskword;
@@ -599,7 +587,7 @@ __device__ __noinline__ void applyFT_warp(const Env e, const double* force, cons
                              double* qfrc) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
-  const double* com = e.DG(B2MJ_F_SUBTREE_COM);
+  const double* com = e.D(B2MJ_F_SUBTREE_COM);
   double off[3];
   sub3(off, point, com + 3 * m.body_rootid[body]);
   const unsigned* mask = m.body_dofmask + body * m.nmaskword;
@@ -666,7 +654,7 @@ __device__ __noinline__ void stage_passive(const Env e) {
     WSYNC();
   }
   if (!(m.opt.disableflags & B2MJ_DSBL_GRAVITY)) {
-    const double* xipos = e.DG(B2MJ_F_XIPOS);
+    const double* xipos = e.D(B2MJ_F_XIPOS);
     B2K_NOUNROLL for (int i = 1; i < m.nbody; i++) {
       const double gc = m.body_gravcomp[i];
       if (gc == 0) continue;
@@ -683,9 +671,9 @@ __device__ __noinline__ void stage_passive(const Env e) {
 __device__ __noinline__ void stage_rne_bias(const Env e) {
   const DevModel& m = c_dm;
   const double* cdof = e.D(B2MJ_F_CDOF);
-  const double* cdof_dot = e.DG(B2MJ_F_CDOF_DOT);
-  const double* cvel = e.DG(B2MJ_F_CVEL);
-  const double* cinert = e.DG(B2MJ_F_CINERT);
+  const double* cdof_dot = e.D(B2MJ_F_CDOF_DOT);
+  const double* cvel = e.D(B2MJ_F_CVEL);
+  const double* cinert = e.D(B2MJ_F_CINERT);
   const double* qvel = e.D(B2MJ_F_QVEL);
   double* fb = e.X(XF_SCRATCH);
   double* bias = e.D(B2MJ_F_QFRC_BIAS);
@@ -730,8 +718,8 @@ __device__ __noinline__ void stage_velocity_head(const Env e) {
     }
   }
   if (m.nu) {
-    const double* am = e.DG(B2MJ_F_ACTUATOR_MOMENT);
-    double* av = e.DG(B2MJ_F_ACTUATOR_VELOCITY);
+    const double* am = e.D(B2MJ_F_ACTUATOR_MOMENT);
+    double* av = e.D(B2MJ_F_ACTUATOR_VELOCITY);
     FORL(i, m.nu) {
       double s = 0;
       B2K_NOUNROLL for (int k = 0; k < nv; k++) s += am[i * nv + k] * qvel[k];
@@ -748,15 +736,15 @@ __device__ __noinline__ void stage_actuation(const Env e, int* warning) {
   double* qa = e.D(B2MJ_F_QFRC_ACTUATOR);
   if (!nu || (m.opt.disableflags & B2MJ_DSBL_ACTUATION)) {
     FORL(i, nv) qa[i] = 0;
-    if (nu) { double* af = e.DG(B2MJ_F_ACTUATOR_FORCE); FORL(i, nu) af[i] = 0; }
+    if (nu) { double* af = e.D(B2MJ_F_ACTUATOR_FORCE); FORL(i, nu) af[i] = 0; }
     WSYNC();
     return;
   }
   double* ctrl = e.D(B2MJ_F_CTRL);
-  double* af = e.DG(B2MJ_F_ACTUATOR_FORCE);
-  const double* al = e.DG(B2MJ_F_ACTUATOR_LENGTH);
-  const double* av = e.DG(B2MJ_F_ACTUATOR_VELOCITY);
-  const double* am = e.DG(B2MJ_F_ACTUATOR_MOMENT);
+  double* af = e.D(B2MJ_F_ACTUATOR_FORCE);
+  const double* al = e.D(B2MJ_F_ACTUATOR_LENGTH);
+  const double* av = e.D(B2MJ_F_ACTUATOR_VELOCITY);
+  const double* am = e.D(B2MJ_F_ACTUATOR_MOMENT);
   const double* act = m.na ? e.D(B2MJ_F_ACT) : nullptr;
   double* act_dot = m.na ? e.D(B2MJ_F_ACT_DOT) : nullptr;
   // bad controls: warn and zero all of them
@@ -816,7 +804,7 @@ __device__ __noinline__ void stage_acceleration(const Env e, const double* xfrc)
   }
   WSYNC();
   if (xfrc) {
-    const double* xipos = e.DG(B2MJ_F_XIPOS);
+    const double* xipos = e.D(B2MJ_F_XIPOS);
     B2K_NOUNROLL for (int i = 1; i < m.nbody; i++) {
       const double* x = xfrc + 6 * i;
       if (x[0] == 0 && x[1] == 0 && x[2] == 0 && x[3] == 0 && x[4] == 0 && x[5] == 0) continue;
