@@ -22,7 +22,8 @@ namespace b2k {
 
 // AR lives in shared memory when it fits the small buffer, else in the env's HBM/L2 arena
 __device__ __forceinline__ double* arPtr(const Env e, int nefc) {
-  return nefc * nefc <= c_dm.xsize[XF_EFC_AR_S] ? e.XG(XF_EFC_AR_S) : e.XG(XF_EFC_AR);
+  // the window also holds the 4 row constants per row that stage_projectConstraint appends after the matrix
+  return nefc * (nefc + 4) <= c_dm.xsize[XF_EFC_AR_S] ? e.XG(XF_EFC_AR_S) : e.XG(XF_EFC_AR);
 }
 
 // G = J W (rows of J pushed through inv(L)) and AR = G diag(1/D) G' + R
@@ -336,6 +337,70 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
     const int j = lane + B2K_G * s;
     if (j < nefc) P.force[j] = f[s];
   }
+  WSYNC();
+  return iter;
+}
+
+// mj_solPGS for scalar rows only (no elliptic-cone blocks), nefc <= lanes per env: OWNER COMPUTES.
+// Lane i owns row i: its residual, force and row constants {1/A_ii, A_ii, lo, hi} stay in registers.  A row update
+// is: the owner clamps its own force (no operand shuffles, no row-constant loads), one shuffle broadcasts the
+// force change, every lane folds it into its residual with one FMA.  The only memory operand, AR[i][lane], does
+// not depend on the chain: it is fetched FOUR ROWS AHEAD into a register ring, so neither an L1 hit (41 cycles) nor
+// an L2 hit (392 cycles, the common case once the 28 KB of L1 left beside the arenas thrashes) is ever waited
+// for.  The dependent chain per row is FMA -> clamp -> shuffle -> FMA; the shuffle-operand version it replaces
+// waited for a row-constant load every row and dominated the slowest envs (21 rows x 100 iterations: 1.34M ->
+// 0.85M cycles for the slowest env of a step).  The row loop stays rolled: a fully unrolled sweep measured 30%
+// SLOWER in the desynchronised rollout (instruction fetch).  Same arithmetic and order as solvePGS_regT.
+// Returns iterations used, or -1 if a cone row is present (caller falls back to solvePGS_regT).
+__device__ __noinline__ int solvePGS_own(const Env e, int nefc, const double* AR) {
+  const DevModel& m = c_dm;
+  const double* rowc = AR + nefc * nefc;
+  EfcPtrs P = efcPtrs(e);
+  const double scale = 1 / (m.meaninertia * max(1, m.nv));
+  const double tol = m.opt.tolerance;
+  const int maxiter = m.opt.iterations;
+  const int lane = e.lane;
+  const bool own = lane < nefc;
+  const int me = own ? lane : nefc - 1;
+  const double iA = rowc[4 * me];
+  if (__any_sync(e.mask, iA < 0)) return -1;
+  const double Aii = rowc[4 * me + 1], lo = rowc[4 * me + 2], up = rowc[4 * me + 3];
+  double f = 0, r = 0;
+  if (own) {
+    f = P.force[lane];
+    double acc = P.b[lane];
+    B2K_NOUNROLL for (int k = 0; k < nefc; k++) acc += AR[lane * nefc + k] * P.force[k];
+    r = acc;
+  }
+  // register ring: AR[row][me] for the rows the sweep reaches next (rows cycle modulo nefc across iterations)
+  const double* col = AR + me;
+  double p0 = col[0], p1 = col[(1 % nefc) * nefc], p2 = col[(2 % nefc) * nefc], p3 = col[(3 % nefc) * nefc];
+  int nxt = 4 % nefc;
+  int iter = 0;
+  while (iter < maxiter) {
+    double improvement = 0;
+    B2K_NOUNROLL for (int i = 0; i < nefc; i++) {
+      const double ai = p0;
+      p0 = p1; p1 = p2; p2 = p3;
+      p3 = col[nxt * nefc];
+      nxt = nxt + 1 == nefc ? 0 : nxt + 1;
+      double fn = f - r * iA;
+      fn = fn < lo ? lo : fn;
+      fn = fn > up ? up : fn;
+      double delta = fn - f;
+      double change = delta * (0.5 * delta * Aii + r);
+      const bool reject = change > 1e-10;  // cost guard of mj_solPGS
+      delta = reject ? 0.0 : delta;
+      change = reject ? 0.0 : change;
+      const double d = __shfl_sync(e.mask, delta, i, B2K_G);
+      improvement -= __shfl_sync(e.mask, change, i, B2K_G);
+      r += ai * d;
+      if (lane == i) f = reject ? f : fn;
+    }
+    iter++;
+    if (improvement * scale < tol) break;
+  }
+  if (own) P.force[lane] = f;
   WSYNC();
   return iter;
 }
@@ -844,7 +909,13 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
       FORL(i, nefc) P.force[i] = 0;
       WSYNC();
     }
-    if (reg) {
+    bool done = false;
+    if (reg && nefc <= B2K_G) {
+      const int it = solvePGS_own(e, nefc, arPtr(e, nefc));
+      if (it >= 0) { iters = it; done = true; }
+    }
+    if (done) {
+    } else if (reg) {
       const bool sm = nefc * (nefc + 4) <= m.xsize[XF_EFC_AR_S];
       const unsigned soff = e.sbd + 8u * (unsigned)m.xoff_s[XF_EFC_AR_S];
       const double* ARg = e.XG(XF_EFC_AR);

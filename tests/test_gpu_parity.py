@@ -335,3 +335,52 @@ def test_rollout_equals_stepping(load_model, BatchSim):
         np.testing.assert_array_equal(ts[k].cpu().numpy(), b.get("sensordata"))
     np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
     np.testing.assert_array_equal(a.get("time"), b.get("time"))
+
+
+def test_contact_rich_single_steps_match_oracle_across_nefc(load_model, orc, BatchSim):
+    """PGS parity for every constraint count the C2 workload produces, not just the typical few rows: the batch
+    is driven into contact with random controls, then envs are picked so that each nefc value seen (in particular
+    17..25: past the one-row-per-lane half, and 18/19 where AR plus its row constants no longer fit the on-chip
+    window) gets a state-injected single step on the oracle.  Tolerance 1e-5 relative on qacc / qvel / qpos."""
+    model = load_model("panda_like.xml")
+    nenv = 2048
+    rng = np.random.default_rng(5)
+    qpos, qvel = perturbed(model, nenv, 77, 0.1)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    picked = {}
+    for block in range(12):
+        for _ in range(100):
+            sim.set("ctrl", ctrl_sample(model, rng, nenv))
+            sim.step(1)
+        # state BEFORE the probe step
+        st = {k: sim.get(k) for k in ("qpos", "qvel", "qacc_warmstart", "time")}
+        ctrl = ctrl_sample(model, rng, nenv)
+        sim.set("ctrl", ctrl)
+        sim.step(1)
+        nefc = sim.get("nefc")[:, 0]
+        out = {k: sim.get(k) for k in ("qpos", "qvel", "qacc")}
+        iters = sim.get("solver_iter")[:, 0]
+        for e in range(nenv):
+            n = int(nefc[e])
+            if n >= 6 and len(picked.get(n, [])) < 2:
+                picked.setdefault(n, []).append((e, {k: v[e].copy() for k, v in st.items()}, ctrl[e].copy(),
+                                                 {k: v[e].copy() for k, v in out.items()}, int(iters[e])))
+    assert picked, "the workload produced no contact-rich env"
+    seen = sorted(picked)
+    assert seen[-1] >= 17, f"expected constraint counts beyond 16 rows, saw {seen}"
+    worst = 0.0
+    for n in seen:
+        for e, st, ctrl, out, it in picked[n]:
+            o = orc.Oracle(model)
+            o.set("qpos", st["qpos"])
+            o.set("qvel", st["qvel"])
+            o.set("qacc_warmstart", st["qacc_warmstart"])
+            o.set("ctrl", ctrl)
+            o.step(1)
+            assert o.get("nefc")[0] == n
+            err = max(rel(out["qacc"], o.get("qacc")), rel(out["qvel"], o.get("qvel")), rel(out["qpos"], o.get("qpos")))
+            worst = max(worst, err)
+            assert err < TOL, f"nefc={n} env={e} iters={it}: single-step mismatch {err:.3e}"
+    print(f"contact-rich single steps: nefc values {seen}, worst rel err {worst:.2e}")
