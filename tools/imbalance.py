@@ -22,6 +22,11 @@ for k in range(3):
     it = sim.get("solver_iter")[:, 0]; ne = sim.get("nefc")[:, 0]; c = sim.env_cycles()
     idx = np.argsort(c)[-5:]
     print("   slowest envs: cycles", c[idx].tolist(), "nefc", ne[idx].tolist(), "iters", it[idx].tolist())
+    b, a = np.polyfit((ne * it).astype(float), c.astype(float), 1)
+    print(f"   fit cycles = {a:.0f} + {b:.1f} x (nefc x iters)   [cycles per PGS row update in situ = {b:.1f}]")
+    big = ne * it >= 1000
+    if big.any():
+        print(f"   envs with nefc x iters >= 1000: {int(big.sum())}, (cycles - {a:.0f}) / rows: median {np.median((c[big] - a) / (ne * it)[big]):.1f}")
     print("   corr(cycles, nefc*iters) =", np.corrcoef(c, ne * it)[0, 1], " base (nefc==0):", c[ne == 0].mean() if (ne == 0).any() else None,
           " nefc<=1:", c[ne <= 1].mean())
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
