@@ -46,6 +46,19 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(model_name, env_steps_per_launch):
+    """DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of the same launch
+    shape (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the fused rollout launch,
+    recorded per env-step so it can be scaled to this run's launch size).  None if no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        per = t["rollout_dram_bytes_per_env_step"].get(model_name)
+        return None if per is None else float(per) * env_steps_per_launch
+    except Exception:
+        return None
+
+
 def state_bytes(model):
     """Algorithmic bytes per env-step (SURVEY 8d / DESIGN.md): state + inputs read, state + outputs written."""
     nq, nv, na, nu, ns = model.nq, model.nv, model.na, model.nu, model.nsensordata
@@ -340,7 +353,8 @@ def main():
                                 "note": "K launches of b2mj_set_device(ctrl) + b2mj_step(1), CUDA events per step, "
                                         "L2 flushed between steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "b2k_step_kernel",
+                         "traffic": load_traffic(args.model, nenv * K), "peak_source": peak_src, "kernel": "b2k_step_kernel",
+                         "traffic_source": "profiles/r1_traffic.json (ncu --set full of the rollout launch, scaled per env-step)",
                          "algorithmic_bytes_per_env_step": bstate, "env_steps_per_launch": nenv * K,
                          "kernel_ms_per_launch": kern_ms,
                          "note": "latency/FP64-bound path: see DESIGN.md 'Roofline'"},

@@ -308,9 +308,13 @@ def test_full_batch_properties(load_model, BatchSim):
     assert big.get("warning").sum() == 0
 
 
-def test_rollout_equals_stepping(load_model, BatchSim):
-    """b2mj_rollout (one launch, device ctrl stream, trajectory out) == nsteps x (set ctrl; b2mj_step)."""
+@pytest.mark.parametrize("chunk", ["0", "7"])
+def test_rollout_equals_stepping(chunk, load_model, BatchSim, monkeypatch):
+    """b2mj_rollout (one launch, device ctrl stream, trajectory out) == nsteps x (set ctrl; b2mj_step), for both
+    schedules: static one-env-per-warp (chunk 0) and the ticketed persistent grid (chunks of 7 steps)."""
     import torch
+
+    monkeypatch.setenv("B2MJ_ROLLOUT_CHUNK", chunk)
 
     model = load_model("panda_like.xml")
     nenv, K = 64, 30
