@@ -366,7 +366,7 @@ def main():
                                "solver_iter_mean": float(stats["solver_iter"].mean())},
             "wall_s_timed_region": wall,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # CPU baseline: rank 0 at N=1 only (bounded sample)
             cores = os.cpu_count() or 1
             csteps = 50
             secs = cpu_rollout(model, nenv, csteps, args.seed, cores)
