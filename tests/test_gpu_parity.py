@@ -388,3 +388,54 @@ def test_contact_rich_single_steps_match_oracle_across_nefc(load_model, orc, Bat
             worst = max(worst, err)
             assert err < TOL, f"nefc={n} env={e} iters={it}: single-step mismatch {err:.3e}"
     print(f"contact-rich single steps: nefc values {seen}, worst rel err {worst:.2e}")
+
+
+def test_runtime_model_mutation_matches_oracle(capi, orc, BatchSim):
+    """The reference's mutating services (callbacks.cpp:462-738: set_gravity, set_body_state mass, set_geom_properties
+    friction / size -> mj_setConst, equality parameters) as host-side model edits + b2mj_model_set_const +
+    b2mj_model_update on a live handle: the batch must then step exactly like an oracle created from the edited model."""
+    from conftest import model_path
+
+    model = capi.Model.from_xml_file(model_path("pendulum_scene.xml"))
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 3, 0.2)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    sim.step(50)
+    # ---- edit: gravity (set_gravity), a body mass + inertia (set_body_state), geom friction / size (set_geom_properties)
+    model.opt.gravity[0] = 1.5
+    model.opt.gravity[2] = -4.0
+    b = model.name2id(capi.OBJ_BODY, "end_link")
+    model.body_mass[b] *= 2.0
+    model.body_inertia[b] *= 2.0
+    g = model.name2id(capi.OBJ_GEOM, "ball")
+    model.geom_friction[g, 0] = 0.3
+    model.geom_size[g, 0] = 0.06
+    model.geom_rbound[g] = 0.06
+    model.set_const()              # mj_setConst: subtree masses, dof_M0, invweights
+    sim.model_update(model)
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "qacc_warmstart", "time")}
+    sim.step(100)
+    gq, gv = sim.get("qpos"), sim.get("qvel")
+    worst = 0.0
+    for e in range(nenv):
+        o = orc.Oracle(model)
+        for k in ("qpos", "qvel", "qacc_warmstart", "time"):
+            o.set(k, st[k][e])
+        o.step(100)
+        worst = max(worst, rel(gq[e], o.get("qpos")), rel(gv[e], o.get("qvel")))
+    assert worst < TOL, worst
+    # and it differs from the un-edited dynamics (the update really took effect)
+    ref = capi.Model.from_xml_file(model_path("pendulum_scene.xml"))
+    o = orc.Oracle(ref)
+    for k in ("qpos", "qvel", "qacc_warmstart", "time"):
+        o.set(k, st[k][0])
+    o.step(100)
+    assert rel(gq[0], o.get("qpos")) > 1e-3
+    # size fields cannot change on a live handle
+    import ctypes
+
+    bad = capi.Model.from_xml_file(model_path("panda_like.xml"))
+    with pytest.raises(Exception):
+        sim.model_update(bad)
