@@ -383,7 +383,6 @@ __device__ __noinline__ int solvePGS_own(const Env e, int nefc, const double* AR
 #define B2K_PGS_OWN_ROW(SLOT)                                                       \
   {                                                                                 \
     const double ai = SLOT;                                                         \
-    SLOT = col[min(i + 2, last) * nefc];                                            \
     double fn = f - r * iA;                                                         \
     fn = fn < lo ? lo : fn;                                                         \
     fn = fn > up ? up : fn;                                                         \
@@ -395,6 +394,8 @@ __device__ __noinline__ int solvePGS_own(const Env e, int nefc, const double* AR
     const double d = __shfl_sync(e.mask, delta, i, B2K_G);                          \
     improvement -= __shfl_sync(e.mask, change, i, B2K_G);                           \
     r += ai * d;                                                                    \
+    /* refill after the last use of ai: the load then targets the slot register itself (no later move) */ \
+    SLOT = col[min(i + 2, last) * nefc];                                            \
     if (lane == i) f = reject ? f : fn;                                             \
     i++;                                                                            \
   }
