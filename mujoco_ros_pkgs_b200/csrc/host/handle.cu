@@ -366,7 +366,7 @@ static int make_layout(Handle* h) {
     int bestW = 0, bestEnv = 0;
     const int forceW = getenv("B2MJ_WARPS_PER_CTA") ? atoi(getenv("B2MJ_WARPS_PER_CTA")) : h->force_warps_per_cta;
     const int wstep = 32 / B2K_G;  // W = envs per CTA (each env is served by B2K_G lanes; CTAs hold whole warps)
-    for (int W = wstep; W <= B2K_MAX_THREADS / B2K_G; W += wstep) {
+    for (int W = wstep; W <= B2K_STEP_THREADS / B2K_G; W += wstep) {
       if (forceW && W != forceW) continue;
       const size_t cta = (size_t)W * (eb + 16);
       if (cta > kMaxCta) continue;
@@ -452,6 +452,19 @@ static int make_layout(Handle* h) {
   }
   h->warps_per_cta = bestW;
   h->smem_bytes = (size_t)bestW * (env_bytes + 16);
+  // Rollout shape: half of an SM's resident envs per CTA, stages lock-stepped with a CTA barrier.  Warps that
+  // run the same stage together share instruction fetches -- the fused rollout is fetch bound (ncu: 12.7
+  // no-instruction stall cycles per issue when the warps drift apart).  Measured on C2 at 4096 envs (CTA width x
+  // stage barrier): 2 -> 11.6M, 5 -> 12.3M, 6 -> 11.2M, 7 -> 13.6M, 8 -> 9.4M, 14 -> 12.2M env-steps/s.
+  h->rollout_warps_per_cta = 0;
+  {
+    const int Wr = bestEnv / 2;
+    const size_t cta = (size_t)Wr * (env_bytes + 16);
+    if (Wr > bestW && Wr * B2K_G <= B2K_MAX_THREADS && (Wr * B2K_G) % 32 == 0 && cta <= kMaxCta &&
+        (int)(kSmPerSM / (cta + kCtaReserve)) * Wr >= bestEnv)
+      h->rollout_warps_per_cta = Wr;
+  }
+  if (const char* env = getenv("B2MJ_ROLLOUT_WARPS_PER_CTA")) h->rollout_warps_per_cta = atoi(env);
   h->arena_in_smem = 1;
   for (int f = 0; f < B2MJ_NFIELD; f++) if (!is_record_field(f) && d.fsize[f] && d.off_s[f] < 0) h->arena_in_smem = 0;
   for (int i = 0; i < XF_COUNT; i++) if (xs[i] && d.xoff_s[i] < 0) h->arena_in_smem = 0;
@@ -526,8 +539,17 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
     a.sched = h->sched;
     a.chunk = chunk;
   }
-  a.sync_stages = getenv("B2MJ_STAGE_SYNC") ? 1 : 0;  // measured: no gain on B200 (profiles/), off by default
-  const int rc = b2k_launch_step(&h->dm, &a, h->warps_per_cta, h->smem_bytes, h->stream);
+  // per-step launches start every warp in step anyway (stage barriers measured no gain there); the static fused
+  // rollout uses its wide lock-stepped shape
+  int W = h->warps_per_cta;
+  a.sync_stages = 0;
+  if (mode == MODE_STEP && nsteps > 1 && !a.sched && !h->keep_intermediates && h->rollout_warps_per_cta > 0) {
+    W = h->rollout_warps_per_cta;
+    a.sync_stages = 1;
+  }
+  if (const char* env = getenv("B2MJ_STAGE_SYNC")) a.sync_stages = atoi(env) ? 1 : 0;
+  const size_t smem = h->smem_bytes / h->warps_per_cta * W;
+  const int rc = b2k_launch_step(&h->dm, &a, W, smem, h->stream);
   if (rc != 0) {
     set_error(std::string("step kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return B2MJ_ECUDA;

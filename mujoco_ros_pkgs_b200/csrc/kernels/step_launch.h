@@ -5,8 +5,9 @@
 
 #include "dev_model.h"
 
-#define B2K_MAX_THREADS 128
-#define B2K_MIN_CTAS 4   /* 4 x 128 threads = 16 warps per SM -> at most 128 registers per thread */
+#define B2K_MAX_THREADS 512 /* widest CTA: the lock-stepped rollout shape (half of an SM's resident envs per CTA) */
+#define B2K_MIN_CTAS 1      /* 512 threads x 128 registers = the whole register file */
+#define B2K_STEP_THREADS 128 /* widest CTA of a per-step launch (small CTAs free their slots as envs finish) */
 
 extern "C" {
 int b2k_launch_step(const b2k::DevModel* m, const b2k::LaunchArgs* a, int warps_per_cta, size_t smem_bytes,
