@@ -239,13 +239,13 @@ def main():
             sim.set_device("ctrl", ctrl_dev[k].data_ptr(), nu)
         sim.step(1)
 
-    launches_per_step = 2 if nu else 1
     ns = model.nsensordata
     # ---------------- device-resident leg A: per-step launches (what a closed-loop user does) ----------------
     with torch.cuda.stream(stream):
         for k in range(W):
             one_step(k)
         barrier()
+        launches0 = sim.launch_info()["launches"]
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         for k in range(K):
@@ -259,6 +259,7 @@ def main():
             kev[k][1].record(stream)
             evs[k][1].record(stream)
         barrier()
+    ps_launches = sim.launch_info()["launches"] - launches0  # the handle's own count of kernels it launched
     ps_step_ms = sum(a.elapsed_time(b) for a, b in evs)
     ps_kern_ms = sum(a.elapsed_time(b) for a, b in kev)
     stats = {k: sim.get(k)[:, 0] for k in ("ncon", "nefc", "solver_iter")}
@@ -283,9 +284,11 @@ def main():
             flush_buf.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wall0 = time.perf_counter()
+        launches1 = sim.launch_info()["launches"]
         e0.record(stream)
         sim.rollout(K, cptr(ctrl_dev[W:]) if nu else 0, tq.data_ptr(), tv.data_ptr(), cptr(ts))
         e1.record(stream)
+        rollout_launches = sim.launch_info()["launches"] - launches1
         barrier()
         wall = time.perf_counter() - wall0
         clocks = sampler.stop()
@@ -347,10 +350,10 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": KE, "timing": "wall clock, sync both sides, pinned host buffers"},
-            "gpu_launches": 1,
+            "gpu_launches": rollout_launches,
             "per_step_launch": {"value": ps_value, "unit": UNIT, "ms_per_step": ps_step_ms / K,
-                                "kernel_ms_per_launch": ps_kern_ms / K, "gpu_launches": launches_per_step * K,
-                                "note": "K launches of b2mj_set_device(ctrl) + b2mj_step(1), CUDA events per step, "
+                                "kernel_ms_per_launch": ps_kern_ms / K, "gpu_launches": ps_launches,
+                                "note": "K x (b2mj_set_device(ctrl) + b2mj_step(1) + launch-order refresh), CUDA events per step, "
                                         "L2 flushed between steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(args.model, nenv * K), "peak_source": peak_src, "kernel": "b2k_step_kernel",

@@ -549,12 +549,26 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
   }
   if (const char* env = getenv("B2MJ_STAGE_SYNC")) a.sync_stages = atoi(env) ? 1 : 0;
   const size_t smem = h->smem_bytes / h->warps_per_cta * W;
+  static const bool reorder = !getenv("B2MJ_NO_REORDER");
+  a.perm = (reorder && h->perm_valid && !a.sched) ? h->perm : nullptr;
   const int rc = b2k_launch_step(&h->dm, &a, W, smem, h->stream);
   if (rc != 0) {
     set_error(std::string("step kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return B2MJ_ECUDA;
   }
   h->launches++;
+  // heaviest-first launch order for the next launch, from the solver work this one recorded (only worth a kernel
+  // when the batch spans more than one wave)
+  if (reorder && mode != MODE_FORWARD && mode != MODE_STEP_BEGIN && h->nenv >= 1024) {
+    if (!h->perm) CUDA_OK(cudaMalloc(&h->perm, (size_t)h->nenv * sizeof(int)));
+    const int orc = b2k_launch_order(h->stats, h->nenv, h->perm, h->stream);
+    if (orc != 0) {
+      set_error(std::string("order kernel launch failed: ") + cudaGetErrorString((cudaError_t)orc));
+      return B2MJ_ECUDA;
+    }
+    h->perm_valid = 1;
+    h->launches++;
+  }
   h->dump_valid = (h->keep_intermediates || mode == MODE_STEP_BEGIN);
   return 0;
 }
@@ -615,6 +629,7 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->mask_dev);
   cudaFree(h->prof);
   cudaFree(h->sched);
+  cudaFree(h->perm);
   handle_free_plugins(h);
   b2mj_model_free(h->model);
   delete h;

@@ -30,6 +30,8 @@ struct Handle {
   double* mocap = nullptr;        // [nenv][7*nmocap]
   double* mocap_init = nullptr;
   unsigned char* mask_dev = nullptr;
+  int* perm = nullptr;                 // [nenv] launch slot -> env, heaviest first (refreshed after every step launch)
+  int perm_valid = 0;
   int* sched = nullptr;                // [1 + nenv] ticket counter + per-env chunk progress (persistent rollout)
   unsigned long long* prof = nullptr;  // [PROF_COUNT] stage cycle totals (b2mj_stage_profile), null = off
 

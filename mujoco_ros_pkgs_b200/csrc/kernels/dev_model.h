@@ -132,6 +132,7 @@ struct LaunchArgs {
   int* sched;
   int chunk;               // steps per ticket
   int sync_stages;         // CTA-wide lockstep at stage boundaries (instruction / constant cache locality)
+  const int* perm;         // [nenv] launch slot -> env, heaviest envs first (b2k_order_kernel), or null = identity
   unsigned long long* prof; // [PROF_COUNT] per-stage SM-cycle totals over all envs, or null (b2mj_stage_profile)
 };
 

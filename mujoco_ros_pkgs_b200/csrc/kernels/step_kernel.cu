@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     } else {
       env = blockIdx.x * nwarp + warp;
       if (env >= a.nenv) return;  // whole warp exits; no CTA-wide barrier is used below
+      if (a.perm) env = a.perm[env];  // heaviest envs occupy the first launch slots
       step0 = 0;
       step1 = (a.mode == MODE_STEP) ? a.nsteps : 1;
     }
@@ -414,6 +415,34 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
     ctas = std::max(1, std::min(ctas, per_sm * sms));
   }
   b2k_step_kernel<<<ctas, warps_per_cta * B2K_G, smem_bytes, stream>>>(*a);
+  return (int)cudaGetLastError();
+}
+
+// Launch order for the next launch: envs sorted into weight classes by the solver work of their last step
+// (constraint rows x iterations), heaviest first.  A launch ends when its slowest env does; an env with 21 rows at the
+// 100-iteration PGS cap takes 4x the median step, and if it starts in the second wave its whole run is added to the
+// launch.  Contact states persist from step to step, so last step's work predicts this step's.  One CTA.
+#define B2K_ORDER_CLASSES 4
+__global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* __restrict__ perm) {
+  __shared__ int count[B2K_ORDER_CLASSES], cursor[B2K_ORDER_CLASSES];
+  if (threadIdx.x < B2K_ORDER_CLASSES) count[threadIdx.x] = 0;
+  __syncthreads();
+  auto cls = [&](int e) {
+    const int w = stats[4 * e + 1] * stats[4 * e + 2];
+    return w >= 1200 ? 0 : w >= 400 ? 1 : w >= 100 ? 2 : 3;
+  };
+  for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&count[cls(e)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < B2K_ORDER_CLASSES; c++) { cursor[c] = acc; acc += count[c]; }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nenv; e += blockDim.x) perm[atomicAdd(&cursor[cls(e)], 1)] = e;
+}
+
+extern "C" int b2k_launch_order(const int* stats, int nenv, int* perm, cudaStream_t stream) {
+  b2k_order_kernel<<<1, 1024, 0, stream>>>(stats, nenv, perm);
   return (int)cudaGetLastError();
 }
 
