@@ -10,7 +10,8 @@ A "step" is one mj_step of every env of the batch with fresh controls.
              stepping stream).  per_step_launch reports the same K steps as K separate launches
              (b2mj_set_device + b2mj_step, L2 flushed between steps) -- the closed-loop usage.
   e2e        same metric through the C-ABI with HOST buffers: per step b2mj_set(ctrl) from pinned host
-             memory -> b2mj_step -> b2mj_get(qpos, qvel, sensordata) into pinned host memory.
+             memory -> b2mj_step -> b2mj_get(qpos, qvel, sensordata) into pinned host memory (b2mj_step_host:
+             the same four transfers and the launch queued in one call, one synchronisation).
   roofline   algorithmic state bytes per env-step x envs / kernel time, against the
              measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline / --impl reference: the CPU oracle (restatement of the reference's mj_step loop; the
@@ -316,12 +317,8 @@ def main():
     def e2e_step(k):
         if nu:
             np.copyto(h_ctrl, ctrl_e2e[k])  # the producer's write into the pinned staging buffer
-            sim.set_from("ctrl", h_ctrl)
-        sim.step(1)
-        sim.get_into("qpos", h_qpos)
-        sim.get_into("qvel", h_qvel)
-        if ns:
-            sim.get_into("sensordata", h_sens)
+        # one C-ABI call: ctrl H2D -> step -> qpos / qvel / sensordata D2H -> one synchronisation
+        sim.step_host(1, h_ctrl if nu else None, h_qpos, h_qvel, h_sens if ns else None)
 
     for k in range(min(W, KE)):
         e2e_step(k)
@@ -349,7 +346,7 @@ def main():
             "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": KE, "timing": "wall clock, sync both sides, pinned host buffers"},
+                    "steps": KE, "timing": "wall clock, sync both sides, pinned host buffers, one b2mj_step_host call per step"},
             "gpu_launches": rollout_launches,
             "per_step_launch": {"value": ps_value, "unit": UNIT, "ms_per_step": ps_step_ms / K,
                                 "kernel_ms_per_launch": ps_kern_ms / K, "gpu_launches": ps_launches,

@@ -305,6 +305,13 @@ int b2mj_rollout(b2mj_handle* h, int nsteps, const double* dev_ctrl, double* dev
  * step_end: actuation, acceleration, constraint solve, acc sensors, check, integrate. Euler only. */
 int b2mj_step_begin(b2mj_handle* h);
 int b2mj_step_end(b2mj_handle* h);
+/* one closed-loop exchange with HOST buffers in a single call: upload ctrl ([nenv][nu], may be NULL = keep), run
+ * nsteps steps, download qpos / qvel / sensordata ([nenv][nq|nv|nsensordata], any may be NULL), synchronise once.
+ * The reference does exactly this around every mj_step -- control plugins write d->ctrl, the step runs, lastStage
+ * plugins read the state out (mujoco_env.cpp:593-595) -- as separate accesses to host memory; here the four
+ * transfers and the launch are queued back to back on the handle's stream (use pinned buffers for full-speed DMA). */
+int b2mj_step_host(b2mj_handle* h, int nsteps, const double* host_ctrl, double* host_qpos, double* host_qvel,
+                   double* host_sensordata);
 /* block until all queued work on the handle's stream has finished */
 int b2mj_sync(b2mj_handle* h);
 

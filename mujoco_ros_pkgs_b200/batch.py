@@ -22,6 +22,7 @@ lib.b2mj_reset.argtypes = [_vp, _vp]
 lib.b2mj_forward.argtypes = [_vp]
 lib.b2mj_step.argtypes = [_vp, C.c_int]
 lib.b2mj_rollout.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
+lib.b2mj_step_host.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
 lib.b2mj_step_begin.argtypes = [_vp]
 lib.b2mj_step_end.argtypes = [_vp]
 lib.b2mj_sync.argtypes = [_vp]
@@ -93,6 +94,19 @@ class BatchSim:
 
     def step_end(self):
         check(lib.b2mj_step_end(self._h), "step_end")
+
+    def step_host(self, nsteps: int, ctrl: np.ndarray = None, qpos: np.ndarray = None, qvel: np.ndarray = None,
+                  sensordata: np.ndarray = None):
+        """b2mj_step_host: ctrl up, nsteps steps, qpos / qvel / sensordata down, one synchronisation.  Arrays are
+        C-contiguous float64 [nenv][n] host buffers (pinned for full-speed DMA); None skips that transfer."""
+        def ptr(a, n):
+            if a is None:
+                return None
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.nenv * n, (a.shape, n)
+            return _vp(a.ctypes.data)
+        m = self.model
+        check(lib.b2mj_step_host(self._h, nsteps, ptr(ctrl, m.nu), ptr(qpos, m.nq), ptr(qvel, m.nv),
+                                 ptr(sensordata, m.nsensordata)), "step_host")
 
     def sync(self):
         check(lib.b2mj_sync(self._h), "sync")

@@ -835,6 +835,35 @@ int b2mj_set(b2mj_handle* hh, b2mj_field f, const void* host_src, size_t bytes) 
   return 0;
 }
 
+int b2mj_step_host(b2mj_handle* hh, int nsteps, const double* host_ctrl, double* host_qpos, double* host_qvel,
+                   double* host_sensordata) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  if (nsteps <= 0) {
+    set_error("b2mj_step_host: nsteps must be positive");
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  const b2mjModel* m = h->model;
+  unsigned char* base; size_t pitch, es; int n;
+  if (host_ctrl && m->nu) {
+    if (int rc = locate(h, B2MJ_F_CTRL, true, &base, &pitch, &es, &n)) return rc;
+    CUDA_OK(cudaMemcpy2DAsync(base, pitch, host_ctrl, n * es, n * es, h->nenv, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->in_split_step = 0;
+  if (int rc = handle_launch(h, MODE_STEP, nsteps)) return rc;
+  const struct { b2mj_field f; double* dst; } outs[3] = {
+      {B2MJ_F_QPOS, host_qpos}, {B2MJ_F_QVEL, host_qvel}, {B2MJ_F_SENSORDATA, host_sensordata}};
+  for (const auto& o : outs) {
+    if (!o.dst) continue;
+    if (int rc = locate(h, o.f, false, &base, &pitch, &es, &n)) return rc;
+    if (n == 0) continue;
+    CUDA_OK(cudaMemcpy2DAsync(o.dst, n * es, base, pitch, n * es, h->nenv, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int b2mj_set_device(b2mj_handle* hh, b2mj_field f, const void* dev_src, size_t src_pitch_elems) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !dev_src) return B2MJ_EINVAL;

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -439,3 +439,62 @@ def test_runtime_model_mutation_matches_oracle(capi, orc, BatchSim):
     bad = capi.Model.from_xml_file(model_path("panda_like.xml"))
     with pytest.raises(Exception):
         sim.model_update(bad)
+
+
+def test_step_host_equals_set_step_get(load_model, BatchSim):
+    """b2mj_step_host (one call: ctrl up, step, state down, one sync) == b2mj_set + b2mj_step + b2mj_get, bitwise."""
+    model = load_model("pendulum_scene.xml" if False else "panda_like.xml")
+    nenv = 96
+    qpos, qvel = perturbed(model, nenv, 31)
+    rng = np.random.default_rng(8)
+    a, b = BatchSim(model, nenv), BatchSim(model, nenv)
+    for s_ in (a, b):
+        s_.set("qpos", qpos)
+        s_.set("qvel", qvel)
+    hq = np.empty((nenv, model.nq)); hv = np.empty((nenv, model.nv)); hs = np.empty((nenv, model.nsensordata))
+    for k in range(25):
+        ctrl = np.ascontiguousarray(ctrl_sample(model, rng, nenv))
+        a.step_host(1, ctrl, hq, hv, hs)
+        b.set("ctrl", ctrl)
+        b.step(1)
+        np.testing.assert_array_equal(hq, b.get("qpos"))
+        np.testing.assert_array_equal(hv, b.get("qvel"))
+        np.testing.assert_array_equal(hs, b.get("sensordata"))
+    a.step_host(3)   # no transfers at all: keeps ctrl
+    b.step(3)
+    np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
+    with pytest.raises(Exception):
+        a.step_host(0)
+
+
+def test_launch_order_does_not_change_results(tmp_path):
+    """The heaviest-first launch order (b2k_order_kernel) only permutes which warp runs which env: a contact-rich
+    2048-env run must be bitwise identical with the reordering disabled (B2MJ_NO_REORDER=1, separate process)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from mujoco_ros_pkgs_b200 import _capi\n"
+        "from mujoco_ros_pkgs_b200.batch import BatchSim\n"
+        "m = _capi.Model.from_xml_file(%r)\n"
+        "rng = np.random.default_rng(2)\n"
+        "n = 2048\n"
+        "sim = BatchSim(m, n)\n"
+        "sim.set('qpos', np.tile(m.qpos0, (n, 1)) + rng.uniform(-0.3, 0.3, (n, m.nq)))\n"
+        "lo, hi = m.actuator_ctrlrange[:, 0], m.actuator_ctrlrange[:, 1]\n"
+        "for k in range(700):\n"
+        "    if k %% 50 == 0: sim.set('ctrl', rng.uniform(lo, hi, (n, m.nu)))\n"
+        "    sim.step(1)\n"
+        "sim.step(40)\n"
+        "np.save(sys.argv[1], np.concatenate([sim.get('qpos'), sim.get('qvel'), sim.get('nefc').astype(float)], axis=1))\n"
+    ) % (ROOT, os.path.join(ROOT, "mujoco_ros_pkgs_b200", "models", "panda_like.xml"))
+    outs = []
+    for tag, extra in (("on", {}), ("off", {"B2MJ_NO_REORDER": "1"})):
+        out = str(tmp_path / f"state_{tag}.npy")
+        env = dict(os.environ, **extra)
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=600)
+        outs.append(np.load(out))
+    assert outs[0][:, -1].max() >= 8, "the run should reach contact-rich states"
+    np.testing.assert_array_equal(outs[0], outs[1])
