@@ -5,7 +5,7 @@ Workload (config C2 of BASELINE.json / SURVEY.md 8d): Panda-like 7+2-DoF arm, 40
 Euler integrator, PGS solver, fresh random ctrl ~ U(ctrlrange) for every env at every step.
 A "step" is one mj_step of every env of the batch with fresh controls.
 
-  value      env-steps/s with inputs resident in HBM: one fused b2mj_rollout launch advances all envs K steps
+  value      env-steps/s with inputs resident in HBM: one fused b2mj_rollout call advances all envs K steps
              reading the device-resident ctrl stream and writing the per-step trajectory (CUDA events on the
              stepping stream).  per_step_launch reports the same K steps as K separate launches
              (b2mj_set_device + b2mj_step, L2 flushed between steps) -- the closed-loop usage.
@@ -192,8 +192,9 @@ def main():
         "workload": f"C2: {args.model} (nq={model.nq} nv={model.nv} nu={model.nu} nbody={model.nbody}), "
                     f"{args.nenv} envs per GPU, {integ}, {solver}, dt={model.opt.timestep}, random ctrl every step",
         "nenv_per_gpu": args.nenv, "global_envs": args.nenv * args.gpus, "parallelism": f"env-shard x{args.gpus}",
-        "launch_mode": "fused open-loop rollout: ONE b2mj_rollout launch advances every env --steps steps; ctrl stream "
-                       "[steps][nenv][nu] resident in HBM, per-step qpos/qvel/sensordata trajectory written to HBM",
+        "launch_mode": "fused open-loop rollout: ONE b2mj_rollout call = one b2k_step_kernel launch that advances every env "
+                       "--steps steps (+ the one-CTA launch-order kernel); ctrl stream [steps][nenv][nu] resident in HBM, "
+                       "per-step qpos/qvel/sensordata trajectory written to HBM",
         "l2": ("inputs larger than L2 (ctrl stream + trajectory, %.0f MB); L2 flushed before the timed launch"
                % ((args.steps * args.nenv * (model.nu + model.nq + model.nv + model.nsensordata) * 8) / 1e6))
         if not args.no_flush else "NOT flushed (diagnostic)",
