@@ -19,6 +19,7 @@
 namespace b2k {
 
 #define B2K_PGS_REGROWS 64
+#define B2K_SPARSE_H_MIN_NV 48  // models wider than this build the Newton Hessian row-sparse
 
 // AR lives in shared memory when it fits the small buffer, else in the env's HBM/L2 arena
 __device__ __forceinline__ double* arPtr(const Env e, int nefc) {
@@ -622,6 +623,57 @@ __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
   WSYNC();
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* cH = c.cone ? e.XG(XF_CONTACT_H) : nullptr;
+#if B2K_G == 32
+  if (nv > B2K_SPARSE_H_MIN_NV) {
+    // Row-sparse J' D J for large models (C5: nv 120, a contact row touches the <= 12 dofs of two free bodies).
+    // Rows are visited in order; per row (or elliptic-cone block) the non-zero columns are compacted with a ballot
+    // and every lane adds one (column, column) pair of the lower triangle.  Each H entry still accumulates its rows
+    // in increasing order with the same expression as the dense loop below, which only adds exact zeros elsewhere:
+    // the result is bitwise the same, at nnz^2 / 2 instead of nv^2 / 2 multiply-adds per row.
+    int* cols = reinterpret_cast<int*>(e.X(XF_SCRATCH));
+    B2K_NOUNROLL for (int r = 0; r < nefc; r++) {
+      const int st = P.state[r];
+      int dim = 1;
+      if (st == B2MJ_CSTATE_CONE) dim = c_dim[P.id[r]];
+      else if (st != B2MJ_CSTATE_QUADRATIC) continue;
+      int nnz = 0;
+      B2K_NOUNROLL for (int k0 = 0; k0 < nv; k0 += 32) {
+        const int k = k0 + e.lane;
+        bool nz = false;
+        if (k < nv) { B2K_NOUNROLL for (int a = 0; a < dim; a++) nz |= P.J[(r + a) * nv + k] != 0; }
+        const unsigned b = __ballot_sync(e.mask, nz);
+        if (nz) cols[nnz + __popc(b & ((1u << e.lane) - 1u))] = k;
+        nnz += __popc(b);
+      }
+      WSYNC();
+      const int npair = nnz * (nnz + 1) / 2;
+      B2K_NOUNROLL for (int idx = e.lane; idx < npair; idx += 32) {
+        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while (a * (a + 1) / 2 > idx) a--;
+        while ((a + 1) * (a + 2) / 2 <= idx) a++;
+        const int i = cols[a], j = cols[idx - a * (a + 1) / 2];  // cols ascending: i >= j
+        double s = H[i * nv + j];
+        if (st == B2MJ_CSTATE_QUADRATIC) {
+          s += P.D[r] * P.J[r * nv + i] * P.J[r * nv + j];
+        } else {
+          const double* Hc = cH + 36 * P.id[r];
+          B2K_NOUNROLL for (int p = 0; p < dim; p++) {
+            const double Ja = P.J[(r + p) * nv + i];
+            if (Ja == 0) continue;
+            double u = 0;
+            B2K_NOUNROLL for (int q = 0; q < dim; q++) u += Hc[p * dim + q] * P.J[(r + q) * nv + j];
+            s += Ja * u;
+          }
+        }
+        H[i * nv + j] = s;
+      }
+      WSYNC();
+      r += dim - 1;
+    }
+    cholFactor_warp(e, H, c.invd, nv, B2K_MINVAL);
+    return;
+  }
+#endif
   // one lane per lower-triangle entry (i, j <= i)
   B2K_NOUNROLL for (int item = e.lane; item < nv * nv; item += B2K_G) {
     const int i = item / nv, j = item - i * nv;
