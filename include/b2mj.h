@@ -293,11 +293,13 @@ int b2mj_forward(b2mj_handle* h);
 /* nsteps x mj_step on all envs, asynchronous on the handle's stream; no host callbacks inside
  * (mujoco_env.cpp:498,552,593).  ctrl/qfrc_applied/xfrc_applied are read as currently set. */
 int b2mj_step(b2mj_handle* h, int nsteps);
-/* fused open-loop rollout: nsteps x mj_step in ONE launch, every env advancing at its own pace with its
- * state resident on chip.  dev_ctrl (DEVICE, [nsteps][nenv][nu], may be NULL = keep current ctrl) supplies
- * fresh controls for every env at every step; the optional DEVICE outputs receive the per-step trajectory
- * ([nsteps][nenv][nq] / [nv] / [nsensordata]) -- what the reference's lastStageCallback consumers would
- * have read after each step (mujoco_env.cpp:500,554,595).  Same arithmetic as nsteps calls of b2mj_step. */
+/* fused open-loop rollout: nsteps x mj_step in ONE step-kernel launch, every env's state resident on chip for the
+ * whole rollout (static schedule: one env per warp, stages lock-stepped within a CTA; a ticketed persistent grid is
+ * used instead when the batch would leave the last wave mostly empty).  dev_ctrl (DEVICE, [nsteps][nenv][nu], may be
+ * NULL = keep current ctrl) supplies fresh controls for every env at every step; the optional DEVICE outputs receive
+ * the per-step trajectory ([nsteps][nenv][nq] / [nv] / [nsensordata]) -- what the reference's lastStageCallback
+ * consumers would have read after each step (mujoco_env.cpp:500,554,595).  Same arithmetic, bit for bit, as nsteps
+ * calls of b2mj_step (tests/test_gpu_parity.py::test_rollout_equals_stepping). */
 int b2mj_rollout(b2mj_handle* h, int nsteps, const double* dev_ctrl, double* dev_qpos_out, double* dev_qvel_out,
                  double* dev_sensor_out);
 /* split step around the control hook (mjcb_control fires between the velocity stage and actuation:
