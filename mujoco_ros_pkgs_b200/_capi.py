@@ -187,6 +187,9 @@ class Model:
         n = check(lib.b2mj_field_size(self._ptr, field, C.byref(is_int)), "field_size")
         return n, bool(is_int.value)
 
+    def field_size_by_name(self, name: str) -> int:
+        return self.field_size(field_id(name))[0]
+
     def __del__(self):
         try:
             if self._ptr:

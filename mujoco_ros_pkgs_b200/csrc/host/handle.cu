@@ -243,6 +243,16 @@ static int check_supported(const b2mjModel* m) {
     set_error("noslip post-solver is not implemented");
     return B2MJ_EUNSUPPORTED;
   }
+  if (m->opt.density != 0 || m->opt.viscosity != 0 || m->opt.wind[0] != 0 || m->opt.wind[1] != 0 || m->opt.wind[2] != 0) {
+    set_error("fluid forces (option density / viscosity / wind) are not implemented in the passive stage");
+    return B2MJ_EUNSUPPORTED;
+  }
+  if (m->opt.solver != B2MJ_SOL_PGS && m->nv > B2K_NEWTON_MAX_NV) {
+    // the Newton / CG triangular solves keep the solution vector in a 4-register-per-lane window (cholSolve_warp)
+    set_error("Newton / CG solvers support at most " + std::to_string(B2K_NEWTON_MAX_NV) + " dofs per env (model has " +
+              std::to_string(m->nv) + ")");
+    return B2MJ_EUNSUPPORTED;
+  }
   return 0;
 }
 
@@ -304,7 +314,9 @@ static int make_layout(Handle* h) {
   xs[XF_QW] = m->nM;
   xs[XF_QHW] = m->nM;
   xs[XF_MINV] = d.dense_small ? nv * nv : 0;
-  xs[XF_HINV] = (d.dense_small && d.any_damping && !rk4) ? nv * nv : 0;
+  // reserved whether or not the model has damping now: b2mj_model_update may switch damping on later and the arena
+  // layout of a live handle cannot change
+  xs[XF_HINV] = (d.dense_small && !rk4) ? nv * nv : 0;
   xs[XF_PRIMAL] = pgs ? 0 : 8 * nv;
   xs[XF_EFC_AR] = pgs ? m->njmax * (m->njmax + 4) : 0;
   xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * (m->njmax + 4), 384) : 0;  // nefc <= 17 stays on chip
@@ -630,6 +642,7 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->prof);
   cudaFree(h->sched);
   cudaFree(h->perm);
+  cudaFree(h->publish_slab);
   handle_free_plugins(h);
   b2mj_model_free(h->model);
   delete h;
@@ -659,6 +672,7 @@ int b2mj_reset(b2mj_handle* hh, const uint8_t* env_mask) {
   CUDA_OK(cudaGetLastError());
   h->launches++;
   h->dump_valid = 0;
+  h->in_split_step = 0;  // a reset between step_begin and step_end abandons the split step
   if (!env_mask) h->dm.has_xfrc = 0;
   handle_reset_plugins(h, env_mask);
   return 0;
@@ -922,8 +936,13 @@ int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
   b2mj_model_free(h->model);
   h->model = clone;
   const int has_xfrc = h->dm.has_xfrc;
+  const int was_rnepost = h->dm.need_rnepost, was_subtreevel = h->dm.need_subtreevel, was_dense = h->dm.dense_small;
   if (int rc = upload_model(h)) return rc;
   h->dm.has_xfrc = has_xfrc;
+  if (h->dm.need_rnepost != was_rnepost || h->dm.need_subtreevel != was_subtreevel || h->dm.dense_small != was_dense) {
+    set_error("b2mj_model_update: the edit changes which per-env arrays exist (sensor types); create a new handle");
+    return B2MJ_EINVAL;
+  }
   return upload_init_templates(h);
 }
 

@@ -46,6 +46,9 @@ struct Handle {
   int in_split_step = 0;
   uint64_t launches = 0;
 
+  double* publish_slab = nullptr;       // staging of b2mj_allgather_publish (per handle: device- and stream-local)
+  size_t publish_slab_n = 0;
+
   RobotHWState* robot_hw = nullptr;
   SensorReadoutState* sensor_ro = nullptr;
 };

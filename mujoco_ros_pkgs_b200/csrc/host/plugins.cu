@@ -434,14 +434,16 @@ int b2mj_allgather_publish(b2mj_handle* hh, b2mj_field f, void* nccl_comm, void*
   CUDA_OK(cudaSetDevice(h->device));
   // pack the strided field into a contiguous slab at this rank's slot, then gather in place
   // (rank slot unknown here: use a private staging slab and an out-of-place gather)
-  static thread_local double* slab = nullptr;
-  static thread_local size_t slab_n = 0;
   const size_t cnt = (size_t)h->nenv * n;
-  if (slab_n < cnt) {
-    cudaFree(slab);
-    CUDA_OK(cudaMalloc(&slab, cnt * sizeof(double)));
-    slab_n = cnt;
+  if (h->publish_slab_n < cnt) {
+    CUDA_OK(cudaStreamSynchronize(h->stream));  // an earlier gather may still read the old slab
+    cudaFree(h->publish_slab);
+    h->publish_slab = nullptr;
+    h->publish_slab_n = 0;
+    CUDA_OK(cudaMalloc(&h->publish_slab, cnt * sizeof(double)));
+    h->publish_slab_n = cnt;
   }
+  double* slab = h->publish_slab;
   CUDA_OK(cudaMemcpy2DAsync(slab, n * sizeof(double), ptr, pitch * sizeof(double), n * sizeof(double), h->nenv,
                             cudaMemcpyDeviceToDevice, h->stream));
   const int rc = fn(slab, dev_dst_all, cnt, /*ncclDouble*/ 8, nccl_comm, h->stream);

@@ -15,18 +15,14 @@
 
 #include "b2mj.h"
 
-// lanes per env (see dev_math.cuh "env-group collectives"): 32 = one env per warp (default), 16 = two envs per warp.
-// Measured on B200 at the BASELINE config (C2, 4096 envs, 100 + 1000 steps of random control, profiles/
-// r1_layout_sweep.txt): 16 lanes win only while the batch is contact free (12.4M vs 8.8M env-steps/s over the
-// first 300 steps); once contacts appear the two envs of a warp serialise each other's solver iterations and the
-// partial-mask collectives cost extra instructions: 32 lanes give 9.0M / 6.2M / 5.4M (rollout / per-step / end to
-// end) against 8.3M / 5.2M / 4.7M.
-// NOTE: only B2K_G == 32 is validated in the r1 final build (all GPU tests).  The 16-lane build was parity green up
-// to the owner-computes PGS change and currently faults in the golden-trajectory test (illegal instruction); it is kept
-// as an experiment knob, not a supported configuration.
-#ifndef B2K_G
-#define B2K_G 32
+// lanes per env: one env per warp.  A 16-lane variant (two envs per warp) was measured in round 1 (profiles/
+// r1_layout_sweep.txt): it wins only while the batch is contact free and loses 8-13 % on the BASELINE workload because
+// the two envs of a warp serialise each other's solver iterations.  It is not a supported configuration: the
+// owner-computes PGS, the register Gauss-Jordan and the Cholesky register windows assume 32 lanes.
+#ifdef B2K_G
+#error "B2K_G is not a build knob any more: the step kernel is written for one env per 32-lane warp"
 #endif
+#define B2K_G 32
 
 namespace b2k {
 

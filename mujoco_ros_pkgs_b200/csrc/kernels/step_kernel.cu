@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "dev_model.h"
 #include "env_ctx.cuh"
@@ -378,6 +379,9 @@ using namespace b2k;
 // different handle / an edited model launches
 static DevModel g_shadow[16];
 static bool g_shadow_valid[16];
+// one lock per device covers compare + upload + launch, so two host threads driving different handles on the same
+// GPU cannot launch with each other's model (the constant is process-global per device)
+static std::mutex g_launch_mutex[16];
 
 extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps_per_cta, size_t smem_bytes,
                                cudaStream_t stream) {
@@ -386,6 +390,7 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
   cudaGetDevice(&dev);
   const int dev_id = dev;
   dev &= 15;
+  std::lock_guard<std::mutex> lock(g_launch_mutex[dev]);
   if (smem_bytes > attr_bytes[dev]) {
     cudaError_t err = cudaFuncSetAttribute(b2k_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return (int)err;
@@ -423,22 +428,48 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
 // 100-iteration PGS cap takes 4x the median step, and if it starts in the second wave its whole run is added to the
 // launch.  Contact states persist from step to step, so last step's work predicts this step's.  One CTA.
 #define B2K_ORDER_CLASSES 4
+// Stable counting sort (deterministic launch order: within a class envs keep their index order).
 __global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* __restrict__ perm) {
   __shared__ int count[B2K_ORDER_CLASSES], cursor[B2K_ORDER_CLASSES];
+  __shared__ int wtot[32][B2K_ORDER_CLASSES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x < B2K_ORDER_CLASSES) count[threadIdx.x] = 0;
   __syncthreads();
   auto cls = [&](int e) {
     const int w = stats[4 * e + 1] * stats[4 * e + 2];
     return w >= 1200 ? 0 : w >= 400 ? 1 : w >= 100 ? 2 : 3;
   };
-  for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&count[cls(e)], 1);
+  for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&count[cls(e)], 1);  // integer totals: order-free
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int c = 0; c < B2K_ORDER_CLASSES; c++) { cursor[c] = acc; acc += count[c]; }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nenv; e += blockDim.x) perm[atomicAdd(&cursor[cls(e)], 1)] = e;
+  for (int base = 0; base < nenv; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    const int c = e < nenv ? cls(e) : -1;
+    int rank = 0;
+#pragma unroll
+    for (int k = 0; k < B2K_ORDER_CLASSES; k++) {
+      const unsigned b = __ballot_sync(0xffffffffu, c == k);
+      if (c == k) rank = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) wtot[warp][k] = __popc(b);
+    }
+    __syncthreads();
+    if (c >= 0) {
+      int off = cursor[c];
+      for (int w = 0; w < warp; w++) off += wtot[w][c];
+      perm[off + rank] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x < B2K_ORDER_CLASSES) {
+      int t = 0;
+      for (int w = 0; w < nwarp; w++) t += wtot[w][threadIdx.x];
+      cursor[threadIdx.x] += t;
+    }
+    __syncthreads();
+  }
 }
 
 extern "C" int b2k_launch_order(const int* stats, int nenv, int* perm, cudaStream_t stream) {

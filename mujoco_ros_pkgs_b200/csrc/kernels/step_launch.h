@@ -7,6 +7,7 @@
 
 #define B2K_MAX_THREADS 512 /* widest CTA: the lock-stepped rollout shape (half of an SM's resident envs per CTA) */
 #define B2K_MIN_CTAS 1      /* 512 threads x 128 registers = the whole register file */
+#define B2K_NEWTON_MAX_NV 128 /* Newton / CG: cholSolve_warp keeps x in B2K_CHOL_SLOTS = 128 / 32 registers per lane */
 #define B2K_STEP_THREADS 128 /* widest CTA of a per-step launch (small CTAs free their slots as envs finish) */
 
 extern "C" {

@@ -1,0 +1,368 @@
+"""GPU parity for the device code paths round 1 left untested (VERDICT r1 "What's weak" 3, 4): every solver x cone x
+integrator combination the reference exposes (viewer.cpp:579-609) on models that reach each PGS size class (<= 32 rows
+owner-computes, 33..64 two-slot register form, > 64 matrix-free), the CG solver, elliptic cones under PGS (QCQP block
+updates), RK4 with PGS, activation dynamics (na > 0), xfrc_applied, mocap bodies, the BADQVEL / BADQACC resets,
+efc_state, and the reference's own five MJCF files compiled verbatim.  All through the C-ABI against the CPU oracle;
+tolerance 1e-5 relative per step (BASELINE.json north_star), integer fields exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from parity_util import (TOL, compare_forward_fields, ctrl_sample, injected_steps, make_oracles, perturbed, rel)
+
+pytestmark = pytest.mark.gpu
+
+PGS, CG, NEWTON = 0, 1, 2
+PYR, ELL = 0, 1
+EULER, RK4 = 0, 1
+
+
+@pytest.fixture(scope="module")
+def BatchSim():
+    from mujoco_ros_pkgs_b200.batch import BatchSim as B
+
+    return B
+
+
+def variant(capi, name, solver=None, cone=None, integrator=None):
+    from conftest import model_path
+
+    m = capi.Model.from_xml_file(model_path(name))
+    if solver is not None:
+        m.opt.solver = solver
+    if cone is not None:
+        m.opt.cone = cone
+    if integrator is not None:
+        m.opt.integrator = integrator
+    return m
+
+
+# (model, solver, cone, integrator, settle steps, checked steps, perturbation, envs)
+MATRIX = [
+    ("panda_like.xml", PGS, ELL, None, 450, 40, 0.1, 16),          # PGS + elliptic cones, <= 32 rows (regT<1> cone path)
+    ("panda_like.xml", CG, None, None, 450, 40, 0.1, 16),          # CG
+    ("panda_like.xml", NEWTON, ELL, None, 450, 40, 0.1, 16),
+    ("box_stack.xml", PGS, ELL, None, 150, 40, 0.1, 8),            # stacked boxes: 24 cone rows
+    ("box_stack.xml", PGS, PYR, None, 150, 40, 0.1, 8),            # pyramidal: 33..64 rows -> regT<2>
+    ("box_stack.xml", CG, None, None, 150, 40, 0.1, 8),
+    ("equality_scene.xml", PGS, None, None, 50, 40, 0.1, 8),       # equality rows (lo = -inf) under PGS
+    ("equality_scene.xml", CG, None, None, 50, 40, 0.1, 8),
+    ("humanoid_like.xml", PGS, PYR, None, 120, 30, 0.02, 8),       # 33..64 rows
+    ("humanoid_like.xml", PGS, ELL, None, 120, 30, 0.02, 8),
+    ("humanoid_like.xml", CG, None, None, 120, 30, 0.02, 8),
+    ("hand_like.xml", PGS, PYR, RK4, 100, 20, 0.02, 8),            # RK4 + PGS, 33..64 rows
+    ("hand_like.xml", PGS, ELL, RK4, 100, 20, 0.02, 8),            # RK4 + PGS + elliptic
+    ("hand_like.xml", CG, None, RK4, 100, 20, 0.02, 8),
+    ("hand_like.xml", NEWTON, PYR, EULER, 100, 20, 0.02, 8),
+    ("bin.xml", PGS, ELL, None, 100, 10, 0.02, 4),                 # > 64 rows: matrix-free PGS with cone blocks
+    ("bin.xml", PGS, PYR, None, 100, 10, 0.02, 4),                 # > 64 scalar rows
+    ("bin.xml", CG, None, None, 100, 10, 0.02, 4),
+    ("bin.xml", NEWTON, PYR, None, 100, 10, 0.02, 4),
+]
+
+
+@pytest.mark.parametrize("name,solver,cone,integ,settle,nchk,amp,nenv", MATRIX)
+def test_solver_cone_integrator_matrix(name, solver, cone, integ, settle, nchk, amp, nenv, capi, orc, BatchSim):
+    model = variant(capi, name, solver, cone, integ)
+    tag = f"{name}[sol{model.opt.solver} cone{model.opt.cone} int{model.opt.integrator}]"
+    qpos, qvel = perturbed(model, nenv, 41, amp)
+    rng = np.random.default_rng(17)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    # drive the batch into its contact regime with piecewise-constant random controls
+    for s in range(settle):
+        if model.nu and s % 25 == 0:
+            sim.set("ctrl", ctrl_sample(model, rng, nenv))
+        sim.step(1)
+    assert np.all(np.isfinite(sim.get("qpos")))
+    oracles = make_oracles(orc, model, sim.get("qpos"), sim.get("qvel"))
+    worst, max_nefc = injected_steps(model, sim, oracles, nchk, rng, tag=tag)
+    # all fields after a forward pass from the state the batch has reached
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "act", "qacc_warmstart", "time", "ctrl") if model.field_size_by_name(k) > 0}
+    sim.keep_intermediates(True)
+    sim.forward()
+    for e, o in enumerate(oracles):
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.forward()
+    wf = compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag=tag)
+    print(f"{tag}: injected-step worst {worst:.2e}, forward fields worst {wf:.2e}, max nefc {max_nefc}")
+
+
+@pytest.mark.parametrize("integ", [EULER, RK4])
+def test_activation_dynamics(integ, capi, orc, BatchSim):
+    """na > 0: integrator / filter activation dynamics, actlimited clamp, affine gain + bias, forcerange, tendon
+    transmission -- act and act_dot against the oracle, free-running for 400 steps (smooth dynamics, no chaos)."""
+    model = variant(capi, "actuated_arm.xml", integrator=integ)
+    assert model.na == 4
+    nenv = 16
+    qpos, qvel = perturbed(model, nenv, 5, 0.2)
+    rng = np.random.default_rng(3)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    act0 = rng.uniform(-0.3, 0.3, (nenv, model.na))
+    sim.set("act", act0)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    for e, o in enumerate(oracles):
+        o.set("act", act0[e])
+    worst = 0.0
+    for s in range(400):
+        if s % 10 == 0:
+            ctrl = ctrl_sample(model, rng, nenv) * 1.5   # beyond ctrlrange: exercises the ctrl clamp
+        sim.set("ctrl", ctrl)
+        sim.step(1)
+        for e, o in enumerate(oracles):
+            o.set("ctrl", ctrl[e])
+            o.step(1)
+        if s % 20 == 19:
+            for k in ("qpos", "qvel", "act", "act_dot", "sensordata"):
+                g = sim.get(k)
+                for e, o in enumerate(oracles):
+                    worst = max(worst, rel(g[e], o.get(k)))
+            assert worst < TOL, (s, worst)
+    assert np.abs(sim.get("act")).max() > 0.05
+    # forward fields incl. actuator_force / qfrc_actuator / actuator_moment
+    sim.keep_intermediates(True)
+    sim.forward()
+    for o in oracles:
+        o.forward()
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag=f"actuated_arm int{integ}")
+
+
+def test_xfrc_applied_matches_oracle(capi, orc, BatchSim):
+    """Cartesian wrenches on bodies (mjData.xfrc_applied, written by plugins inside controlCallback,
+    plugin_utils.h:89-95) enter qfrc_smooth through J'; also the accelerometer path of the sensors."""
+    model = variant(capi, "humanoid_like.xml")
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 9, 0.02)
+    rng = np.random.default_rng(12)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+
+    def wrench(s):
+        return {"xfrc_applied": rng.uniform(-20, 20, (nenv, 6 * model.nbody))}
+
+    worst, _ = injected_steps(model, sim, oracles, 40, rng, tag="humanoid xfrc", extra_inputs=wrench)
+    x = rng.uniform(-20, 20, (nenv, 6 * model.nbody))
+    sim.set("xfrc_applied", x)
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "qacc_warmstart", "time", "ctrl")}
+    sim.keep_intermediates(True)
+    sim.forward()
+    for e, o in enumerate(oracles):
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.set("xfrc_applied", x[e])
+        o.forward()
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag="humanoid xfrc")
+    # and the wrench really acts: qacc differs from the wrench-free forward pass
+    qa = sim.get("qacc")
+    sim.set("xfrc_applied", np.zeros_like(x))
+    sim.forward()
+    assert rel(qa, sim.get("qacc")) > 1e-3
+    print(f"xfrc injected-step worst {worst:.2e}")
+
+
+def ref_fixture():
+    return np.load(os.path.join(GOLDEN, "ref_models.npz"))
+
+
+@pytest.mark.parametrize("name", ["pendulum_world", "empty_world", "equality_world", "mocap_world", "sensors_world"])
+def test_reference_xml_verbatim(name, capi, orc, BatchSim):
+    """The reference's own MJCF files (bytes frozen by tools/make_ref_model_fixtures.py), compiled verbatim: forward
+    fields at qpos0 against a live oracle and the 200-step trajectory against the frozen one."""
+    g = ref_fixture()
+    model = capi.Model.from_xml_string(bytes(g[f"{name}__xml"]).decode())
+    nenv = 3
+    sim = BatchSim(model, nenv)
+    sim.keep_intermediates(True)
+    sim.forward()
+    oracles = [orc.Oracle(model) for _ in range(nenv)]
+    for o in oracles:
+        o.forward()
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag=name)
+    sim.keep_intermediates(False)
+    tq, tv = g[f"{name}__qpos"], g[f"{name}__qvel"]
+    for k in range(tq.shape[0]):
+        sim.step(1)
+        if k % 20 == 19 or k == 0:
+            assert rel(sim.get("qpos"), np.tile(tq[k], (nenv, 1))) < TOL, (name, k)
+            assert rel(sim.get("qvel"), np.tile(tv[k], (nenv, 1))) < TOL, (name, k)
+    np.testing.assert_array_equal(sim.get("time")[:, 0], g[f"{name}__time"][0])
+
+
+def test_mocap_bodies_drag_welded_box(capi, orc, BatchSim):
+    """mocap_world.xml (mujoco_ros_mocap_plugin/assets): the plugin writes d->mocap_pos / mocap_quat every control
+    callback (mocap_plugin.cpp); a weld ties a free box to mocap2.  Per-env mocap trajectories, injected-step parity."""
+    g = ref_fixture()
+    model = capi.Model.from_xml_string(bytes(g["mocap_world__xml"]).decode())
+    assert model.nmocap == 2
+    nenv = 6
+    sim = BatchSim(model, nenv)
+    oracles = [orc.Oracle(model) for _ in range(nenv)]
+    rng = np.random.default_rng(4)
+    base_pos = sim.get("mocap_pos").copy()
+    phase = rng.uniform(0, 6.28, (nenv, 1))
+
+    def move(s):
+        p = base_pos.copy()
+        p[:, 3:4] += 0.2 * np.sin(0.02 * s + phase)        # mocap2 x
+        p[:, 5:6] += 0.1 * (1 - np.cos(0.015 * s + phase))  # mocap2 z
+        q = np.tile([1.0, 0, 0, 0, 1.0, 0, 0, 0], (nenv, 1))
+        ang = 0.3 * np.sin(0.01 * s + phase[:, 0])
+        q[:, 4], q[:, 7] = np.cos(ang / 2), np.sin(ang / 2)
+        return {"mocap_pos": p, "mocap_quat": q}
+
+    worst, max_nefc = injected_steps(model, sim, oracles, 150, rng, tag="mocap_world", extra_inputs=move, check_every=3)
+    q = sim.get("qpos")
+    assert np.abs(q[:, 0] - 0.3).max() > 0.02, "the welded box should have been dragged"
+    assert max_nefc >= 6
+    print(f"mocap injected-step worst {worst:.2e}, max nefc {max_nefc}")
+
+
+def test_bad_qvel_and_qacc_trigger_reset(capi, BatchSim):
+    """mj_checkVel / mj_checkAcc: a non-finite or huge value resets THAT env (mj_resetData) and bumps its warning
+    counter; the others are untouched."""
+    model = variant(capi, "pendulum_scene.xml")
+    nenv = 5
+    sim = BatchSim(model, nenv)
+    v = np.zeros((nenv, model.nv))
+    v[1, 2] = np.inf
+    v[3, 0] = 2e10          # > mjMAXVAL
+    sim.set("qvel", v)
+    sim.step(1)
+    w = sim.get("warning")
+    assert w[1, 5] == 1 and w[3, 5] == 1 and w[[0, 2, 4]].sum() == 0   # B2MJ_WARN_BADQVEL = 5
+    assert np.all(np.isfinite(sim.get("qvel")))
+    # BADQACC: an absurd applied force makes qacc exceed mjMAXVAL on one env
+    sim.reset()
+    f = np.zeros((nenv, model.nv))
+    f[2, 5] = 1e14
+    sim.set("qfrc_applied", f)
+    sim.step(1)
+    w = sim.get("warning")
+    assert w[2, 6] == 1 and w[[0, 1, 3, 4]].sum() == 0                  # B2MJ_WARN_BADQACC = 6
+    t = sim.get("time")[:, 0]
+    assert t[2] == model.opt.timestep   # reset to t = 0, then the step is taken from the reset state
+    q = sim.get("qpos")
+    assert np.all(np.isfinite(q)) and np.all(np.isfinite(sim.get("qacc")))
+
+
+@pytest.mark.parametrize("name,solver", [("panda_like.xml", PGS), ("panda_like.xml", NEWTON), ("humanoid_like.xml", NEWTON),
+                                         ("humanoid_like.xml", CG), ("box_stack.xml", PGS), ("bin.xml", NEWTON)])
+def test_efc_state_matches_oracle(name, solver, capi, orc, BatchSim):
+    """efc_state (satisfied / quadratic / linear / cone per row) after the solve, integer-exact."""
+    model = variant(capi, name, solver)
+    nenv = 8 if name != "bin.xml" else 4
+    qpos, qvel = perturbed(model, nenv, 23, 0.02 if name != "panda_like.xml" else 0.1)
+    rng = np.random.default_rng(8)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    for s in range(200 if name != "bin.xml" else 100):
+        if model.nu and s % 25 == 0:
+            sim.set("ctrl", ctrl_sample(model, rng, nenv))
+        sim.step(1)
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "qacc_warmstart", "time", "ctrl") if model.field_size_by_name(k) > 0}
+    sim.keep_intermediates(True)
+    sim.forward()
+    nefc = sim.get("nefc")[:, 0]
+    gs = sim.get("efc_state")
+    total = 0
+    for e in range(nenv):
+        o = orc.Oracle(model)
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.forward()
+        assert o.get("nefc")[0] == nefc[e]
+        np.testing.assert_array_equal(gs[e][:nefc[e]], o.get("efc_state")[:nefc[e]], err_msg=f"{name} env {e}")
+        total += int(nefc[e])
+    assert total > 0
+
+
+def test_damping_switched_on_by_model_update(capi, orc, BatchSim):
+    """a handle created with zero joint damping must step correctly after b2mj_model_update turns damping
+    on (the implicit-damping inverse needs arena space that is reserved at create time)."""
+    from conftest import model_path
+
+    model = capi.Model.from_xml_file(model_path("panda_like.xml"))
+    model.dof_damping[:] = 0
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 2, 0.1)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    sim.step(20)
+    model.dof_damping[:] = 2.0
+    sim.model_update(model)
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "qacc_warmstart", "time")}
+    sim.step(50)
+    gq, gv = sim.get("qpos"), sim.get("qvel")
+    for e in range(nenv):
+        o = orc.Oracle(model)
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.step(50)
+        assert rel(gq[e], o.get("qpos")) < TOL and rel(gv[e], o.get("qvel")) < TOL
+
+
+def test_reset_abandons_split_step(capi, BatchSim):
+    model = variant(capi, "pendulum_scene.xml")
+    sim = BatchSim(model, 2)
+    sim.step_begin()
+    sim.reset()
+    with pytest.raises(capi.B2mjError):
+        sim.step_end()
+
+
+def test_unsupported_options_are_rejected(capi, BatchSim):
+    """Fluid forces are not implemented: nonzero density / viscosity / wind must be refused, not ignored."""
+    for attr, val in (("density", 1.2), ("viscosity", 0.01)):
+        m = variant(capi, "pendulum_scene.xml")
+        setattr(m.opt, attr, val)
+        with pytest.raises(capi.B2mjError):
+            BatchSim(m, 2)
+    m = variant(capi, "pendulum_scene.xml")
+    m.opt.wind[0] = 1.0
+    with pytest.raises(capi.B2mjError):
+        BatchSim(m, 2)
+
+
+@pytest.mark.parametrize("name,nenv,amp", [("humanoid_like.xml", 6, 0.02), ("hand_like.xml", 6, 0.02), ("bin.xml", 3, 0.02)])
+def test_thousand_step_per_step_parity(name, nenv, amp, capi, orc, BatchSim):
+    """North star: "<1e-5 rel per step ... over 1000 steps".  The contact-rich configs are chaotic (a free-running
+    1e-13 difference grows past 1e-5 within a few hundred steps on either side), so the 1000-step claim is checked the
+    way the north star words it -- per step: every step starts from the batch's own state on both sides.  The
+    free-running divergence of a second, never-corrected set of oracles is printed for the record."""
+    model = variant(capi, name)
+    qpos, qvel = perturbed(model, nenv, 61, amp)
+    rng = np.random.default_rng(29)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    free = make_oracles(orc, model, qpos, qvel)
+    worst, max_nefc, div = 0.0, 0, []
+    rng_free = np.random.default_rng(29)
+    for block in range(10):
+        # identical control streams for the injected and the free-running oracles
+        state = rng.bit_generator.state
+        w, mn = injected_steps(model, sim, oracles, 100, rng, tag=name)
+        rng_free.bit_generator.state = state
+        for s in range(100):
+            ctrl = ctrl_sample(model, rng_free, nenv)
+            for e, o in enumerate(free):
+                if model.nu:
+                    o.set("ctrl", ctrl[e])
+                o.step(1)
+        worst, max_nefc = max(worst, w), max(max_nefc, mn)
+        gq = sim.get("qpos")
+        div.append(max(rel(gq[e], o.get("qpos")) for e, o in enumerate(free)))
+    np.testing.assert_array_equal(sim.get("time")[:, 0], [o.time for o in free])
+    print(f"{name}: 1000 injected steps worst {worst:.2e}, max nefc {max_nefc}; free-running divergence per 100 steps "
+          + " ".join(f"{d:.1e}" for d in div))
