@@ -343,21 +343,39 @@ int b2mj_model_update(b2mj_handle* h, const b2mjModel* m);
  *  sensor_readout — MujocoRosSensorsPlugin::lastStageCallback arithmetic (mujoco_sensor_handler_plugin.cpp:175-437) */
 enum { B2MJ_CTRL_EFFORT = 0, B2MJ_CTRL_POSITION = 1, B2MJ_CTRL_POSITION_PID = 2, B2MJ_CTRL_VELOCITY = 3,
        B2MJ_CTRL_VELOCITY_PID = 4 };
+/* joint_limits_interface::JointLimits + SoftJointLimits of one joint (what registerJointLimits reads from the URDF
+ * and the parameter server, default_robot_hw_sim.cpp:340-446).  A joint with limits gets the saturation handle of its
+ * hardware interface, or the soft-limits handle when has_soft_limits is set; enforced on the command before every
+ * write (:262-267). */
+typedef struct b2mjJointLimits {
+  int has_position_limits, has_velocity_limits, has_acceleration_limits, has_effort_limits;
+  int has_soft_limits, angle_wraparound;
+  double min_position, max_position, max_velocity, max_acceleration, max_effort;
+  double soft_min_position, soft_max_position, k_position, k_velocity;
+} b2mjJointLimits;
 typedef struct b2mjRobotHW {
-  int njoint;                /* controlled joints */
+  int njoint;                /* controlled joints (transmissions) */
   const int* joint_id;       /* [njoint] model joint ids (hinge/slide) */
   const int* control_mode;   /* [njoint] B2MJ_CTRL_* */
-  const double* effort_limit;/* [njoint] */
-  const double* pid_gains;   /* [njoint][5] p,i,d,i_max,i_min */
-  const double* lower_limit; /* [njoint] joint limits (for limit-aware position error) */
+  const double* effort_limit;/* [njoint] or NULL (limits' max_effort, else none) */
+  const double* pid_gains;   /* [njoint][5] p,i,d,i_max,i_min (control_toolbox::Pid) or NULL */
+  const double* lower_limit; /* [njoint] joint limits for the limit-aware position error, or NULL (limits / jnt_range) */
   const double* upper_limit; /* [njoint] */
-  const int* joint_kind;     /* [njoint] 0 revolute (limited), 1 continuous, 2 prismatic */
+  const int* joint_kind;     /* [njoint] 0 revolute (limited), 1 continuous, 2 prismatic; NULL = from the model */
+  const b2mjJointLimits* limits; /* [njoint] or NULL = no joint_limits_interface handles */
+  const int* pid_antiwindup; /* [njoint] or NULL (0) */
 } b2mjRobotHW;
+/* Joint state starts as DefaultRobotHWSim::initSim leaves it (position 1.0, effort 1.0, :132-137). */
 int b2mj_robot_hw_configure(b2mj_handle* h, const b2mjRobotHW* cfg);
-/* cmd: DEVICE or HOST pointer [nenv][njoint] (is_device flag); e_stop: 0/1; period: control dt for PID */
+/* DefaultRobotHWSim::writeSim (:248-326): e-stop hold, enforceLimits, mode switch.  Uses the joint state of the LAST
+ * b2mj_robot_hw_read (the reference reads once per control period and writes every step).
+ * cmd: DEVICE or HOST pointer [nenv][njoint] (is_device flag); e_stop: 0/1; period: time since the last write */
 int b2mj_robot_hw_write(b2mj_handle* h, const double* cmd, int is_device, int e_stop, double period);
-/* pos/vel/eff: HOST [nenv][njoint] each (any may be NULL) — DefaultRobotHWSim::readSim (:230-246) */
+/* DefaultRobotHWSim::readSim (:230-246): refresh position (revolute: unwrapped) / velocity / effort from the state,
+ * then copy them to HOST [nenv][njoint] arrays (any may be NULL; all NULL = device-side refresh only, asynchronous) */
 int b2mj_robot_hw_read(b2mj_handle* h, double* pos, double* vel, double* eff);
+/* DEVICE pointers ([nenv][njoint]) of the joint-state interface values, for device-resident controllers */
+int b2mj_robot_hw_state_ptrs(b2mj_handle* h, double** dev_pos, double** dev_vel, double** dev_eff);
 
 typedef struct b2mjSensorNoise {
   int sensor_id;

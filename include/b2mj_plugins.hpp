@@ -39,6 +39,12 @@ class BatchRosControlPlugin : public BatchPlugin {
     double pid[5] = {0, 0, 0, 0, 0};  // p, i, d, i_max, i_min (gazebo_ros_control/pid_gains)
     int joint_kind = 0;          // 0 revolute (limited), 1 continuous, 2 prismatic
     double lower = 0, upper = 0;
+    // joint_limits_interface data of the joint (URDF <limit>/<safety_controller> + joint_limits rosparams,
+    // default_robot_hw_sim.cpp:340-446).  With has_limits the joint gets the saturation handle of its hardware interface,
+    // or the soft-limits handle when limits.has_soft_limits is set; enforced before every write (:262-267).
+    bool has_limits = false;
+    b2mjJointLimits limits{};
+    bool pid_antiwindup = false;
   };
 
   BatchRosControlPlugin(std::vector<Joint> joints, BatchController controller, double control_period = 0.0)
@@ -77,8 +83,10 @@ class BatchRosControlPlugin : public BatchPlugin {
  protected:
   bool load(const b2mjModel* m, BatchData* d) override {
     const int n = njoint();
-    std::vector<int> ids(n), modes(n), kinds(n);
+    std::vector<int> ids(n), modes(n), kinds(n), aw(n);
     std::vector<double> elim(n), pid(5 * n), lo(n), hi(n);
+    std::vector<b2mjJointLimits> lims(n);
+    bool any_limits = false;
     for (int j = 0; j < n; j++) {
       ids[j] = b2mj_name2id(m, B2MJ_OBJ_JOINT, joints_[j].name.c_str());
       if (ids[j] < 0) return false;  // "This transmission has no associated joints" -> plugin quarantined
@@ -88,8 +96,22 @@ class BatchRosControlPlugin : public BatchPlugin {
       for (int k = 0; k < 5; k++) pid[5 * j + k] = joints_[j].pid[k];
       lo[j] = joints_[j].lower;
       hi[j] = joints_[j].upper;
+      aw[j] = joints_[j].pid_antiwindup ? 1 : 0;
+      lims[j] = joints_[j].limits;
+      any_limits |= joints_[j].has_limits;
     }
-    b2mjRobotHW cfg{n, ids.data(), modes.data(), elim.data(), pid.data(), lo.data(), hi.data(), kinds.data()};
+    if (any_limits) {
+      // the C-ABI takes limits for all joints or none: a joint without limits gets a handle that cannot bind
+      // (no position / acceleration limits, infinite velocity / effort bounds)
+      for (int j = 0; j < n; j++)
+        if (!joints_[j].has_limits) {
+          lims[j] = b2mjJointLimits{};
+          lims[j].has_velocity_limits = lims[j].has_effort_limits = 1;
+          lims[j].max_velocity = lims[j].max_effort = 1.7976931348623157e308;
+        }
+    }
+    b2mjRobotHW cfg{n, ids.data(), modes.data(), elim.data(), pid.data(), lo.data(), hi.data(), kinds.data(),
+                    any_limits ? lims.data() : nullptr, aw.data()};
     if (b2mj_robot_hw_configure(d->handle(), &cfg) != B2MJ_OK) return false;
     const size_t sz = (size_t)d->nenv() * n;
     pos_.assign(sz, 0); vel_.assign(sz, 0); eff_.assign(sz, 0); cmd_.assign(sz, 0);

@@ -48,11 +48,22 @@ class B2mjLaunchInfo(C.Structure):
                 ("state_record_bytes", C.c_int), ("regs_per_thread", C.c_int), ("launches", C.c_uint64)]
 
 
+class B2mjJointLimits(C.Structure):
+    _fields_ = [("has_position_limits", C.c_int), ("has_velocity_limits", C.c_int),
+                ("has_acceleration_limits", C.c_int), ("has_effort_limits", C.c_int),
+                ("has_soft_limits", C.c_int), ("angle_wraparound", C.c_int),
+                ("min_position", C.c_double), ("max_position", C.c_double), ("max_velocity", C.c_double),
+                ("max_acceleration", C.c_double), ("max_effort", C.c_double),
+                ("soft_min_position", C.c_double), ("soft_max_position", C.c_double),
+                ("k_position", C.c_double), ("k_velocity", C.c_double)]
+
+
 class B2mjRobotHW(C.Structure):
     _fields_ = [("njoint", C.c_int), ("joint_id", C.POINTER(C.c_int)), ("control_mode", C.POINTER(C.c_int)),
                 ("effort_limit", C.POINTER(C.c_double)), ("pid_gains", C.POINTER(C.c_double)),
                 ("lower_limit", C.POINTER(C.c_double)), ("upper_limit", C.POINTER(C.c_double)),
-                ("joint_kind", C.POINTER(C.c_int))]
+                ("joint_kind", C.POINTER(C.c_int)), ("limits", C.POINTER(B2mjJointLimits)),
+                ("pid_antiwindup", C.POINTER(C.c_int))]
 
 
 class B2mjSensorNoise(C.Structure):
@@ -68,7 +79,7 @@ EXPORTS = [
     "b2mj_create", "b2mj_destroy", "b2mj_nenv", "b2mj_model", "b2mj_set_stream", "b2mj_reset",
     "b2mj_forward", "b2mj_step", "b2mj_rollout", "b2mj_step_begin", "b2mj_step_end", "b2mj_step_host", "b2mj_sync",
     "b2mj_set_keep_intermediates", "b2mj_get", "b2mj_set", "b2mj_set_device", "b2mj_device_ptr", "b2mj_model_update",
-    "b2mj_robot_hw_configure", "b2mj_robot_hw_write", "b2mj_robot_hw_read", "b2mj_sensor_configure_noise",
+    "b2mj_robot_hw_configure", "b2mj_robot_hw_write", "b2mj_robot_hw_read", "b2mj_robot_hw_state_ptrs", "b2mj_sensor_configure_noise",
     "b2mj_sensor_readout", "b2mj_allgather_publish", "b2mj_launch_info", "b2mj_stage_profile", "b2mj_stage_name", "b2mj_env_cycles", "b2mj_last_error", "b2mj_version",
     "b2mj_device_count",
 ]

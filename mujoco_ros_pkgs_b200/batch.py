@@ -164,7 +164,9 @@ class BatchSim:
         return out.astype(np.int64) * 1024
 
     # ---- plugin data paths ----
-    def robot_hw_configure(self, joint_ids, modes, effort_limit=None, pid=None, lower=None, upper=None, kind=None):
+    def robot_hw_configure(self, joint_ids, modes, effort_limit=None, pid=None, lower=None, upper=None, kind=None,
+                           limits=None, antiwindup=None):
+        """limits: list of dicts with b2mjJointLimits field names (missing fields 0), one per joint, or None."""
         nj = len(joint_ids)
         self._hw_keep = []
 
@@ -174,8 +176,17 @@ class BatchSim:
             a = np.ascontiguousarray(x, dtype=dt)
             self._hw_keep.append(a)
             return a.ctypes.data_as(C.POINTER(C.c_int if dt == np.int32 else C.c_double))
+        lim = None
+        if limits is not None:
+            assert len(limits) == nj
+            lim = (_capi.B2mjJointLimits * nj)()
+            for k, d in enumerate(limits):
+                for name, val in d.items():
+                    setattr(lim[k], name, val)
+            self._hw_keep.append(lim)
         cfg = _capi.B2mjRobotHW(nj, arr(joint_ids, np.int32), arr(modes, np.int32), arr(effort_limit, np.float64),
-                                arr(pid, np.float64), arr(lower, np.float64), arr(upper, np.float64), arr(kind, np.int32))
+                                arr(pid, np.float64), arr(lower, np.float64), arr(upper, np.float64), arr(kind, np.int32),
+                                lim, arr(antiwindup, np.int32))
         check(lib.b2mj_robot_hw_configure(self._h, C.byref(cfg)), "robot_hw_configure")
         self._hw_nj = nj
 

@@ -39,8 +39,10 @@ struct RobotHWState {
   int njoint = 0;
   int *joint_id = nullptr, *mode = nullptr, *kind = nullptr, *qposadr = nullptr, *dofadr = nullptr;
   double *effort_limit = nullptr, *pid = nullptr, *lower = nullptr, *upper = nullptr;
+  b2mjJointLimits* limits = nullptr;  // [njoint] or null: no joint_limits_interface handle registered
   // per (env, joint) state
-  double *pos = nullptr, *vel = nullptr, *eff = nullptr, *i_error = nullptr, *last_error = nullptr, *hold_cmd = nullptr;
+  double *pos = nullptr, *vel = nullptr, *eff = nullptr, *i_error = nullptr, *last_error = nullptr, *d_error = nullptr,
+         *hold_cmd = nullptr, *prev_cmd = nullptr;
   double* cmd = nullptr;  // staging for host commands
   int last_e_stop = 0;
 };
@@ -56,39 +58,177 @@ struct SensorReadoutState {
 };
 
 // ---------------------------------------------------------------- robot hw kernels
-__device__ __forceinline__ double normalize_angle(double a) {
-  const double two_pi = 6.283185307179586476925286766559;
-  a = fmod(a + 3.14159265358979323846, two_pi);
-  if (a < 0) a += two_pi;
-  return a - 3.14159265358979323846;
+// ros/angles 1.9.13 (angles.h), the functions writeSim / readSim call (default_robot_hw_sim.cpp:242,287-295)
+#define B2MJ_PI 3.14159265358979323846
+__device__ __forceinline__ double normalize_angle(double angle) {
+  const double result = fmod(angle + B2MJ_PI, 2.0 * B2MJ_PI);
+  if (result <= 0.0) return result + B2MJ_PI;
+  return result - B2MJ_PI;
 }
 __device__ __forceinline__ double shortest_angular_distance(double from, double to) { return normalize_angle(to - from); }
+__device__ __forceinline__ double two_pi_complement(double angle) {
+  if (angle > 2 * B2MJ_PI || angle < -2.0 * B2MJ_PI) angle = fmod(angle, 2.0 * B2MJ_PI);
+  if (angle < 0) return 2 * B2MJ_PI + angle;
+  else if (angle > 0) return -2 * B2MJ_PI + angle;
+  return 2 * B2MJ_PI;
+}
+__device__ bool find_min_max_delta(double from, double left_limit, double right_limit, double& result_min_delta,
+                                   double& result_max_delta) {
+  double delta[4];
+  delta[0] = shortest_angular_distance(from, left_limit);
+  delta[1] = shortest_angular_distance(from, right_limit);
+  delta[2] = two_pi_complement(delta[0]);
+  delta[3] = two_pi_complement(delta[1]);
+  if (delta[0] == 0) {
+    result_min_delta = delta[0];
+    result_max_delta = fmax(delta[1], delta[3]);
+    return true;
+  }
+  if (delta[1] == 0) {
+    result_max_delta = delta[1];
+    result_min_delta = fmin(delta[0], delta[2]);
+    return true;
+  }
+  double delta_min = delta[0], delta_min_2pi = delta[2];
+  if (delta[2] < delta_min) { delta_min = delta[2]; delta_min_2pi = delta[0]; }
+  double delta_max = delta[1], delta_max_2pi = delta[3];
+  if (delta[3] > delta_max) { delta_max = delta[3]; delta_max_2pi = delta[1]; }
+  if ((delta_min <= delta_max_2pi) || (delta_max >= delta_min_2pi)) {
+    result_min_delta = delta_max_2pi;
+    result_max_delta = delta_min_2pi;
+    return left_limit == -B2MJ_PI && right_limit == B2MJ_PI;
+  }
+  result_min_delta = delta_min;
+  result_max_delta = delta_max;
+  return true;
+}
+__device__ double shortest_angular_distance_with_limits(double from, double to, double left_limit, double right_limit) {
+  double min_delta = -2 * B2MJ_PI, max_delta = 2 * B2MJ_PI, min_delta_to = -2 * B2MJ_PI, max_delta_to = 2 * B2MJ_PI;
+  const bool flag = find_min_max_delta(from, left_limit, right_limit, min_delta, max_delta);
+  const double delta = shortest_angular_distance(from, to);
+  const double delta_mod_2pi = two_pi_complement(delta);
+  if (flag) {  // from position is within the limits
+    if (delta >= min_delta && delta <= max_delta) return delta;
+    if (delta_mod_2pi >= min_delta && delta_mod_2pi <= max_delta) return delta_mod_2pi;
+    find_min_max_delta(to, left_limit, right_limit, min_delta_to, max_delta_to);
+    if (fabs(min_delta_to) < fabs(max_delta_to)) return fmax(delta, delta_mod_2pi);
+    if (fabs(min_delta_to) > fabs(max_delta_to)) return fmin(delta, delta_mod_2pi);
+    return fabs(delta) < fabs(delta_mod_2pi) ? delta : delta_mod_2pi;
+  }
+  find_min_max_delta(to, left_limit, right_limit, min_delta_to, max_delta_to);
+  if (fabs(min_delta) < fabs(max_delta)) return fmin(delta, delta_mod_2pi);
+  if (fabs(min_delta) > fabs(max_delta)) return fmax(delta, delta_mod_2pi);
+  return fabs(delta) < fabs(delta_mod_2pi) ? delta : delta_mod_2pi;
+}
+__device__ __forceinline__ double saturate_d(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
+// joint_limits_interface (ros_control 0.19): the one handle a joint owns, chosen by its hardware interface
+// (default_robot_hw_sim.cpp:411-445); enforced on the command before writeSim's mode switch (:262-267)
+__device__ double enforce_limits(const b2mjJointLimits& L, int iface, double c, double pos, double vel, double period,
+                                 double* prev_cmd) {
+  if (iface == B2MJ_CTRL_POSITION) {
+    double prev = *prev_cmd;
+    if (isnan(prev)) prev = pos;
+    if (!L.has_soft_limits) {  // PositionJointSaturationHandle
+      const double lo_lim = L.has_position_limits ? L.min_position : -1.7976931348623157e308;
+      const double hi_lim = L.has_position_limits ? L.max_position : 1.7976931348623157e308;
+      double min_pos = lo_lim, max_pos = hi_lim;
+      if (L.has_velocity_limits) {
+        const double delta_pos = L.max_velocity * period;
+        min_pos = fmax(prev - delta_pos, lo_lim);
+        max_pos = fmin(prev + delta_pos, hi_lim);
+      }
+      c = saturate_d(c, min_pos, max_pos);
+    } else {  // PositionJointSoftLimitsHandle
+      double soft_min_vel = -L.max_velocity, soft_max_vel = L.max_velocity;
+      if (L.has_position_limits) {
+        soft_min_vel = saturate_d(-L.k_position * (prev - L.soft_min_position), -L.max_velocity, L.max_velocity);
+        soft_max_vel = saturate_d(-L.k_position * (prev - L.soft_max_position), -L.max_velocity, L.max_velocity);
+      }
+      double pos_low = prev + soft_min_vel * period, pos_high = prev + soft_max_vel * period;
+      if (L.has_position_limits) {
+        pos_low = fmax(pos_low, L.min_position);
+        pos_high = fmin(pos_high, L.max_position);
+      }
+      c = saturate_d(c, pos_low, pos_high);
+    }
+    *prev_cmd = c;
+  } else if (iface == B2MJ_CTRL_VELOCITY) {
+    if (!L.has_soft_limits) {  // VelocityJointSaturationHandle
+      double vel_low = -L.max_velocity, vel_high = L.max_velocity;
+      if (L.has_acceleration_limits) {
+        const double prev = isnan(*prev_cmd) ? 0.0 : *prev_cmd;  // prev_cmd_ starts at 0
+        vel_low = fmax(prev - L.max_acceleration * period, -L.max_velocity);
+        vel_high = fmin(prev + L.max_acceleration * period, L.max_velocity);
+      }
+      c = saturate_d(c, vel_low, vel_high);
+      *prev_cmd = c;
+    } else {  // VelocityJointSoftLimitsHandle
+      double min_vel = -L.max_velocity, max_vel = L.max_velocity;
+      if (L.has_position_limits) {
+        min_vel = saturate_d(-L.k_position * (pos - L.soft_min_position), -L.max_velocity, L.max_velocity);
+        max_vel = saturate_d(-L.k_position * (pos - L.soft_max_position), -L.max_velocity, L.max_velocity);
+      }
+      if (L.has_acceleration_limits) {
+        min_vel = fmax(vel - L.max_acceleration * period, min_vel);
+        max_vel = fmin(vel + L.max_acceleration * period, max_vel);
+      }
+      c = saturate_d(c, min_vel, max_vel);
+    }
+  } else {
+    if (!L.has_soft_limits) {  // EffortJointSaturationHandle
+      double min_eff = -L.max_effort, max_eff = L.max_effort;
+      if (L.has_position_limits) {
+        if (pos < L.min_position) min_eff = 0.0;
+        else if (pos > L.max_position) max_eff = 0.0;
+      }
+      if (vel < -L.max_velocity) min_eff = 0.0;
+      else if (vel > L.max_velocity) max_eff = 0.0;
+      c = saturate_d(c, min_eff, max_eff);
+    } else {  // EffortJointSoftLimitsHandle
+      double soft_min_vel = -L.max_velocity, soft_max_vel = L.max_velocity;
+      if (L.has_position_limits) {
+        soft_min_vel = saturate_d(-L.k_position * (pos - L.soft_min_position), -L.max_velocity, L.max_velocity);
+        soft_max_vel = saturate_d(-L.k_position * (pos - L.soft_max_position), -L.max_velocity, L.max_velocity);
+      }
+      const double soft_min_eff = saturate_d(-L.k_velocity * (vel - soft_min_vel), -L.max_effort, L.max_effort);
+      const double soft_max_eff = saturate_d(-L.k_velocity * (vel - soft_max_vel), -L.max_effort, L.max_effort);
+      c = saturate_d(c, soft_min_eff, soft_max_eff);
+    }
+  }
+  return c;
+}
+
+// One thread per (env, joint).  do_read: readSim (:230-246) refreshes the joint-state interface values from the state
+// record; do_write: writeSim (:248-326) consumes them.  The reference reads only when a control period has elapsed but
+// writes every step (mujoco_ros_control_plugin.cpp:176-193), so between updates the PID runs on the state of the last
+// read -- the two halves are therefore separate launches, not one fused read-modify-write.
 __global__ void robot_hw_kernel(double* rec, int pitch, int rec_qpos, int rec_qvel, int rec_qfrc, int nenv, int nj,
                                 const int* mode, const int* kind, const int* qposadr, const int* dofadr,
                                 const double* effort_limit, const double* pid, const double* lower, const double* upper,
-                                double* pos, double* vel, double* eff, double* i_error, double* last_error, double* hold_cmd,
-                                const double* cmd, int e_stop, int e_stop_rising, double period, int do_write) {
+                                const b2mjJointLimits* limits, double* pos, double* vel, double* eff, double* i_error,
+                                double* last_error, double* d_error, double* hold_cmd, double* prev_cmd, const double* cmd,
+                                int e_stop, int e_stop_rising, double period, int do_read, int do_write) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nenv * nj) return;
   const int env = idx / nj, j = idx - env * nj;
   double* r = rec + (size_t)env * pitch;
-  // readSim
-  const double position = r[rec_qpos + qposadr[j]], velocity = r[rec_qvel + dofadr[j]], effort = r[rec_qfrc + dofadr[j]];
-  if (kind[j] == 2) pos[idx] = position;
-  else pos[idx] += shortest_angular_distance(pos[idx], position);
-  vel[idx] = velocity;
-  eff[idx] = effort;
+  if (do_read) {
+    const double position = r[rec_qpos + qposadr[j]], velocity = r[rec_qvel + dofadr[j]], effort = r[rec_qfrc + dofadr[j]];
+    if (kind[j] == 2) pos[idx] = position;
+    else pos[idx] += shortest_angular_distance(pos[idx], position);
+    vel[idx] = velocity;
+    eff[idx] = effort;
+  }
   if (!do_write) return;
-  // writeSim
   double c = cmd[idx];
   const int md = mode[j];
-  if (md == B2MJ_CTRL_POSITION || md == B2MJ_CTRL_POSITION_PID) {
-    if (e_stop) {
-      if (e_stop_rising) hold_cmd[idx] = c;
-      c = hold_cmd[idx];
-    }
+  const int iface = md == B2MJ_CTRL_POSITION_PID ? B2MJ_CTRL_POSITION : md == B2MJ_CTRL_VELOCITY_PID ? B2MJ_CTRL_VELOCITY : md;
+  if (iface == B2MJ_CTRL_POSITION && e_stop) {
+    if (e_stop_rising) hold_cmd[idx] = c;
+    c = hold_cmd[idx];
   }
+  if (limits) c = enforce_limits(limits[j], iface, c, pos[idx], vel[idx], period, prev_cmd + idx);
   switch (md) {
     case B2MJ_CTRL_EFFORT: r[rec_qfrc + dofadr[j]] = e_stop ? 0.0 : c; break;
     case B2MJ_CTRL_POSITION:
@@ -104,38 +244,46 @@ __global__ void robot_hw_kernel(double* rec, int pitch, int rec_qpos, int rec_qv
     case B2MJ_CTRL_VELOCITY_PID: {
       double error;
       if (md == B2MJ_CTRL_POSITION_PID) {
-        if (kind[j] == 0) {
-          // revolute with limits: shortest distance that stays inside [lower, upper] when possible
-          const double d1 = shortest_angular_distance(pos[idx], c);
-          const double d2 = d1 > 0 ? d1 - 6.283185307179586476925286766559 : d1 + 6.283185307179586476925286766559;
-          const double t1 = pos[idx] + d1, t2 = pos[idx] + d2;
-          if (t1 >= lower[j] && t1 <= upper[j]) error = d1;
-          else if (t2 >= lower[j] && t2 <= upper[j]) error = d2;
-          else error = d1;
-        } else if (kind[j] == 1) {
-          error = shortest_angular_distance(pos[idx], c);
-        } else {
-          error = c - pos[idx];
-        }
+        if (kind[j] == 0) error = shortest_angular_distance_with_limits(pos[idx], c, lower[j], upper[j]);
+        else if (kind[j] == 1) error = shortest_angular_distance(pos[idx], c);
+        else error = c - pos[idx];
       } else {
         error = e_stop ? -vel[idx] : c - vel[idx];
       }
-      // control_toolbox::Pid::computeCommand(error, dt)
-      const double* g = pid + 5 * j;
+      // control_toolbox::Pid::computeCommand(error, dt) (1.19.0); gains: p, i, d, i_max, i_min, antiwindup
+      const double* g = pid + 6 * j;
       double out = 0;
-      if (period > 0 && !isnan(error) && !isinf(error)) {
-        const double error_dot = (error - last_error[idx]) / period;
-        last_error[idx] = error;
-        i_error[idx] += period * error;
-        double i_term = g[1] * i_error[idx];
-        i_term = fmax(g[4], fmin(i_term, g[3]));
-        out = g[0] * error + i_term + g[2] * error_dot;
+      if (!(period == 0.0 || isnan(error) || isinf(error))) {
+        double error_dot = d_error[idx];
+        if (period > 0.0) {
+          error_dot = (error - last_error[idx]) / period;
+          last_error[idx] = error;
+        }
+        d_error[idx] = error_dot;
+        if (!(isnan(error_dot) || isinf(error_dot))) {
+          const double p_term = g[0] * error;
+          double ie = i_error[idx] + period * error;
+          const bool antiwindup = g[5] != 0;
+          if (antiwindup && g[1] != 0) {
+            const double a = g[4] / g[1], b = g[3] / g[1];
+            ie = saturate_d(ie, fmin(a, b), fmax(a, b));
+          }
+          i_error[idx] = ie;
+          double i_term = g[1] * ie;
+          if (!antiwindup) i_term = saturate_d(i_term, g[4], g[3]);
+          const double d_term = g[2] * error_dot;
+          out = p_term + i_term + d_term;
+        }
       }
       const double lim = effort_limit[j];
-      r[rec_qfrc + dofadr[j]] = fmax(-lim, fmin(out, lim));
+      r[rec_qfrc + dofadr[j]] = saturate_d(out, -lim, lim);
       break;
     }
   }
+}
+
+__global__ void fill_kernel(double* p, double v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ---------------------------------------------------------------- sensor readout kernels
@@ -180,33 +328,40 @@ __global__ void sensor_readout_kernel(const double* rec, int pitch, int rec_sd, 
   }
   if (!fl) return;
   const bool quat = (type == B2MJ_SENS_BALLQUAT || type == B2MJ_SENS_FRAMEQUAT);
+  if (!quat && dim == 1) {
+    // scalar sensors draw once whichever flag bit is set and use mean[0] / sigma[0] (:369-371)
+    const double noise = philox_normal(seed, (unsigned)env, (unsigned)n, 0u, count) * sigma[3 * n] + mean[3 * n];
+    v[0] = (double)(float)(sd[adr] + noise / cutoff);
+    return;
+  }
   double noise[3] = {0, 0, 0};
   int ni = 0;
   for (int k = 0; k < 3; k++) {
     if (fl & (1 << k)) {
       noise[k] = philox_normal(seed, (unsigned)env, (unsigned)n, (unsigned)k, count) * sigma[3 * n + ni] + mean[3 * n + ni];
-      ni++;
+      if (k < 2) ni++;
     }
   }
   if (!quat) {
     for (int k = 0; k < dim && k < 3; k++) v[k] = (double)(float)(sd[adr + k] + noise[k] / cutoff);
   } else {
-    // q = (setRPY(noise) * normalize(q_msg)).normalize(), sensor order (w,x,y,z)
+    // q = (setRPY(noise) * normalize(q_msg)).normalize(), sensor order (w,x,y,z); tf2 normalises by multiplying with
+    // the reciprocal length and composes the product in this term order (tf2/LinearMath/Quaternion.h)
     double w = v[0], x = v[1], y = v[2], z = v[3];
-    double nrm = sqrt(w * w + x * x + y * y + z * z);
-    if (nrm > 0) { w /= nrm; x /= nrm; y /= nrm; z /= nrm; }
+    double inv = 1.0 / sqrt(x * x + y * y + z * z + w * w);
+    x *= inv; y *= inv; z *= inv; w *= inv;
     const double hr = noise[0] * 0.5, hp = noise[1] * 0.5, hy = noise[2] * 0.5;
     const double cr = cos(hr), sr = sin(hr), cp = cos(hp), sp = sin(hp), cy = cos(hy), sy = sin(hy);
     double rx = sr * cp * cy - cr * sp * sy, ry = cr * sp * cy + sr * cp * sy, rz = cr * cp * sy - sr * sp * cy,
            rw = cr * cp * cy + sr * sp * sy;
-    nrm = sqrt(rw * rw + rx * rx + ry * ry + rz * rz);
-    rw /= nrm; rx /= nrm; ry /= nrm; rz /= nrm;
-    double ow = rw * w - rx * x - ry * y - rz * z;
-    double ox = rw * x + rx * w + ry * z - rz * y;
-    double oy = rw * y - rx * z + ry * w + rz * x;
-    double oz = rw * z + rx * y - ry * x + rz * w;
-    nrm = sqrt(ow * ow + ox * ox + oy * oy + oz * oz);
-    v[0] = ow / nrm; v[1] = ox / nrm; v[2] = oy / nrm; v[3] = oz / nrm;
+    inv = 1.0 / sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+    rx *= inv; ry *= inv; rz *= inv; rw *= inv;
+    const double ox = rw * x + rx * w + ry * z - rz * y;
+    const double oy = rw * y + ry * w + rz * x - rx * z;
+    const double oz = rw * z + rz * w + rx * y - ry * x;
+    const double ow = rw * w - rx * x - ry * y - rz * z;
+    inv = 1.0 / sqrt(ox * ox + oy * oy + oz * oz + ow * ow);
+    v[0] = ow * inv; v[1] = ox * inv; v[2] = oy * inv; v[3] = oz * inv;
   }
 }
 
@@ -214,9 +369,9 @@ void handle_free_plugins(Handle* h) {
   if (h->robot_hw) {
     RobotHWState* s = h->robot_hw;
     cudaFree(s->joint_id); cudaFree(s->mode); cudaFree(s->kind); cudaFree(s->qposadr); cudaFree(s->dofadr);
-    cudaFree(s->effort_limit); cudaFree(s->pid); cudaFree(s->lower); cudaFree(s->upper);
+    cudaFree(s->effort_limit); cudaFree(s->pid); cudaFree(s->lower); cudaFree(s->upper); cudaFree(s->limits);
     cudaFree(s->pos); cudaFree(s->vel); cudaFree(s->eff); cudaFree(s->i_error); cudaFree(s->last_error);
-    cudaFree(s->hold_cmd); cudaFree(s->cmd);
+    cudaFree(s->d_error); cudaFree(s->hold_cmd); cudaFree(s->prev_cmd); cudaFree(s->cmd);
     delete s;
     h->robot_hw = nullptr;
   }
@@ -228,17 +383,31 @@ void handle_free_plugins(Handle* h) {
   }
 }
 
+// joint-state interface values and controller state as DefaultRobotHWSim::initSim leaves them
+// (default_robot_hw_sim.cpp:132-137: position 1.0, velocity 0, effort 1.0; Pid zeroed; limit handles fresh:
+// position handles start with prev_cmd = NaN "take the current position", velocity handles with 0)
+static void robot_hw_init_state(Handle* h) {
+  RobotHWState* s = h->robot_hw;
+  const size_t n = (size_t)h->nenv * s->njoint;
+  const size_t bytes = n * sizeof(double);
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 1184);
+  fill_kernel<<<blocks, 256, 0, h->stream>>>(s->pos, 1.0, n);
+  fill_kernel<<<blocks, 256, 0, h->stream>>>(s->eff, 1.0, n);
+  cudaMemsetAsync(s->vel, 0, bytes, h->stream);
+  cudaMemsetAsync(s->i_error, 0, bytes, h->stream);
+  cudaMemsetAsync(s->last_error, 0, bytes, h->stream);
+  cudaMemsetAsync(s->d_error, 0, bytes, h->stream);
+  cudaMemsetAsync(s->hold_cmd, 0, bytes, h->stream);
+  // prev_cmd: NaN = "unset" (position handles then take the current position, velocity handles 0)
+  fill_kernel<<<blocks, 256, 0, h->stream>>>(s->prev_cmd, nan(""), n);
+  s->last_e_stop = 0;
+}
+
 void handle_reset_plugins(Handle* h, const uint8_t* env_mask) {
-  // DefaultRobotHWSim has no reset hook of its own; PID integrators restart with the plugin reload.
-  // Here a full reset clears the controller state so that rollouts are reproducible.
+  // DefaultRobotHWSim has no reset hook of its own; its state restarts when the plugin is reloaded with the env.
+  // Here a full reset puts the controller state back to its post-initSim values so that rollouts are reproducible.
   if (h->robot_hw && !env_mask) {
-    RobotHWState* s = h->robot_hw;
-    const size_t n = (size_t)h->nenv * s->njoint * sizeof(double);
-    cudaMemsetAsync(s->pos, 0, n, h->stream);
-    cudaMemsetAsync(s->i_error, 0, n, h->stream);
-    cudaMemsetAsync(s->last_error, 0, n, h->stream);
-    cudaMemsetAsync(s->hold_cmd, 0, n, h->stream);
-    s->last_e_stop = 0;
+    robot_hw_init_state(h);
   }
   if (h->sensor_ro && !env_mask) h->sensor_ro->count = 0;
 }
@@ -265,24 +434,39 @@ int b2mj_robot_hw_configure(b2mj_handle* hh, const b2mjRobotHW* cfg) {
   const b2mjModel* m = h->model;
   const int nj = cfg->njoint;
   std::vector<int> qa(nj), da(nj), kind(nj);
-  std::vector<double> lim(nj), pid(5 * nj, 0.0), lo(nj), hi(nj);
+  std::vector<double> lim(nj), pid(6 * nj, 0.0), lo(nj), hi(nj);
   for (int j = 0; j < nj; j++) {
     const int id = cfg->joint_id[j];
     if (id < 0 || id >= m->njnt || (m->jnt_type[id] != B2MJ_JNT_HINGE && m->jnt_type[id] != B2MJ_JNT_SLIDE)) {
       set_error("b2mj_robot_hw_configure: joint " + std::to_string(j) + " is not a hinge/slide joint of the model");
       return B2MJ_EINVAL;
     }
-    if (cfg->control_mode[j] < B2MJ_CTRL_EFFORT || cfg->control_mode[j] > B2MJ_CTRL_VELOCITY_PID) {
+    const int md = cfg->control_mode[j];
+    if (md < B2MJ_CTRL_EFFORT || md > B2MJ_CTRL_VELOCITY_PID) {
       set_error("b2mj_robot_hw_configure: unknown control mode");
       return B2MJ_EINVAL;
+    }
+    const b2mjJointLimits* L = cfg->limits ? cfg->limits + j : nullptr;
+    if (L) {
+      // the joint_limits_interface handle constructors throw on these (ros_control joint_limits_interface.h), which
+      // makes the reference's plugin fail to load
+      const int iface = md == B2MJ_CTRL_POSITION_PID ? B2MJ_CTRL_POSITION : md == B2MJ_CTRL_VELOCITY_PID ? B2MJ_CTRL_VELOCITY : md;
+      const bool need_vel = iface != B2MJ_CTRL_POSITION || L->has_soft_limits;
+      if ((need_vel && !L->has_velocity_limits) || (iface == B2MJ_CTRL_EFFORT && !L->has_effort_limits)) {
+        set_error("b2mj_robot_hw_configure: joint " + std::to_string(j) +
+                  " lacks the velocity / effort limits its limit handle requires");
+        return B2MJ_EINVAL;
+      }
     }
     qa[j] = m->jnt_qposadr[id];
     da[j] = m->jnt_dofadr[id];
     kind[j] = cfg->joint_kind ? cfg->joint_kind[j] : (m->jnt_type[id] == B2MJ_JNT_SLIDE ? 2 : (m->jnt_limited[id] ? 0 : 1));
-    lim[j] = cfg->effort_limit ? cfg->effort_limit[j] : 1e300;
-    if (cfg->pid_gains) std::memcpy(&pid[5 * j], cfg->pid_gains + 5 * j, 5 * sizeof(double));
-    lo[j] = cfg->lower_limit ? cfg->lower_limit[j] : m->jnt_range[2 * id];
-    hi[j] = cfg->upper_limit ? cfg->upper_limit[j] : m->jnt_range[2 * id + 1];
+    // registerJointLimits (:340-446): effort / position limits default to "none" = +-max double
+    lim[j] = cfg->effort_limit ? cfg->effort_limit[j] : (L && L->has_effort_limits ? L->max_effort : 1.7976931348623157e308);
+    if (cfg->pid_gains) std::memcpy(&pid[6 * j], cfg->pid_gains + 5 * j, 5 * sizeof(double));
+    pid[6 * j + 5] = cfg->pid_antiwindup ? (double)cfg->pid_antiwindup[j] : 0.0;
+    lo[j] = cfg->lower_limit ? cfg->lower_limit[j] : (L && L->has_position_limits ? L->min_position : m->jnt_range[2 * id]);
+    hi[j] = cfg->upper_limit ? cfg->upper_limit[j] : (L && L->has_position_limits ? L->max_position : m->jnt_range[2 * id + 1]);
   }
   CUDA_OK(cudaSetDevice(h->device));
   if (h->robot_hw) {
@@ -301,29 +485,33 @@ int b2mj_robot_hw_configure(b2mj_handle* hh, const b2mjRobotHW* cfg) {
   rc |= upload(&s->qposadr, qa.data(), nj);
   rc |= upload(&s->dofadr, da.data(), nj);
   rc |= upload(&s->effort_limit, lim.data(), nj);
-  rc |= upload(&s->pid, pid.data(), 5 * nj);
+  rc |= upload(&s->pid, pid.data(), 6 * nj);
   rc |= upload(&s->lower, lo.data(), nj);
   rc |= upload(&s->upper, hi.data(), nj);
+  if (cfg->limits) rc |= upload(&s->limits, cfg->limits, nj);
   if (rc) return B2MJ_ECUDA;
   const size_t n = (size_t)h->nenv * nj;
-  double** per[] = {&s->pos, &s->vel, &s->eff, &s->i_error, &s->last_error, &s->hold_cmd, &s->cmd};
+  double** per[] = {&s->pos, &s->vel, &s->eff, &s->i_error, &s->last_error, &s->d_error, &s->hold_cmd, &s->prev_cmd, &s->cmd};
   for (double** p : per) {
     CUDA_OK(cudaMalloc(p, n * sizeof(double)));
     CUDA_OK(cudaMemset(*p, 0, n * sizeof(double)));
   }
+  robot_hw_init_state(h);
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-static int robot_hw_run(Handle* h, const double* cmd_dev, int e_stop, double period, int do_write) {
+static int robot_hw_run(Handle* h, const double* cmd_dev, int e_stop, double period, int do_read, int do_write) {
   RobotHWState* s = h->robot_hw;
   const b2k::DevModel& d = h->dm;
   const int n = h->nenv * s->njoint;
-  const int rising = (e_stop && !s->last_e_stop) ? 1 : 0;
+  const int rising = (do_write && e_stop && !s->last_e_stop) ? 1 : 0;
   robot_hw_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->rec, d.rec_pitch, d.rec_qpos, d.rec_qvel, d.rec_qfrc_applied,
                                                           h->nenv, s->njoint, s->mode, s->kind, s->qposadr, s->dofadr,
-                                                          s->effort_limit, s->pid, s->lower, s->upper, s->pos, s->vel, s->eff,
-                                                          s->i_error, s->last_error, s->hold_cmd, cmd_dev, e_stop, rising,
-                                                          period, do_write);
+                                                          s->effort_limit, s->pid, s->lower, s->upper, s->limits, s->pos,
+                                                          s->vel, s->eff, s->i_error, s->last_error, s->d_error,
+                                                          s->hold_cmd, s->prev_cmd, cmd_dev, e_stop, rising, period,
+                                                          do_read, do_write);
   CUDA_OK(cudaGetLastError());
   if (do_write) s->last_e_stop = e_stop ? 1 : 0;
   h->launches++;
@@ -341,7 +529,7 @@ int b2mj_robot_hw_write(b2mj_handle* hh, const double* cmd, int is_device, int e
                             cudaMemcpyHostToDevice, h->stream));
     src = h->robot_hw->cmd;
   }
-  return robot_hw_run(h, src, e_stop, period, 1);
+  return robot_hw_run(h, src, e_stop, period, 0, 1);
 }
 
 int b2mj_robot_hw_read(b2mj_handle* hh, double* pos, double* vel, double* eff) {
@@ -349,12 +537,23 @@ int b2mj_robot_hw_read(b2mj_handle* hh, double* pos, double* vel, double* eff) {
   if (!h) return B2MJ_EINVAL;
   if (!h->robot_hw) { set_error("b2mj_robot_hw_read: call b2mj_robot_hw_configure first"); return B2MJ_ESTATE; }
   CUDA_OK(cudaSetDevice(h->device));
-  if (int rc = robot_hw_run(h, nullptr, 0, 0, 0)) return rc;
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (int rc = robot_hw_run(h, nullptr, 0, 0, 1, 0)) return rc;
+  if (!pos && !vel && !eff) return 0;  // device-resident controllers: state refreshed, nothing copied, no sync
   const size_t bytes = (size_t)h->nenv * h->robot_hw->njoint * sizeof(double);
-  if (pos) CUDA_OK(cudaMemcpy(pos, h->robot_hw->pos, bytes, cudaMemcpyDeviceToHost));
-  if (vel) CUDA_OK(cudaMemcpy(vel, h->robot_hw->vel, bytes, cudaMemcpyDeviceToHost));
-  if (eff) CUDA_OK(cudaMemcpy(eff, h->robot_hw->eff, bytes, cudaMemcpyDeviceToHost));
+  if (pos) CUDA_OK(cudaMemcpyAsync(pos, h->robot_hw->pos, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (vel) CUDA_OK(cudaMemcpyAsync(vel, h->robot_hw->vel, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (eff) CUDA_OK(cudaMemcpyAsync(eff, h->robot_hw->eff, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b2mj_robot_hw_state_ptrs(b2mj_handle* hh, double** dev_pos, double** dev_vel, double** dev_eff) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  if (!h->robot_hw) { set_error("b2mj_robot_hw_state_ptrs: call b2mj_robot_hw_configure first"); return B2MJ_ESTATE; }
+  if (dev_pos) *dev_pos = h->robot_hw->pos;
+  if (dev_vel) *dev_vel = h->robot_hw->vel;
+  if (dev_eff) *dev_eff = h->robot_hw->eff;
   return 0;
 }
 

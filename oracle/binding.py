@@ -122,3 +122,79 @@ def rollout(model, qpos, qvel, nsteps, ctrl=None, nthreads=1, want_sensors=False
     secs = lib.orc_rollout(model.ptr, nenv, nsteps, qpos.ctypes.data, qvel.ctypes.data, cptr, nthreads,
                            sens.ctypes.data if sens is not None else None)
     return secs, qpos, qvel, sens
+
+
+# ---- plugin data paths restated from the reference sources (oracle/orc_plugins.cpp) ----
+lib.orc_hw_create.restype = _vp
+lib.orc_hw_create.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]
+lib.orc_hw_free.argtypes = [_vp]
+lib.orc_hw_read.argtypes = [_vp, _vp, _vp]
+lib.orc_hw_write.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_double]
+lib.orc_hw_state.argtypes = [_vp, _vp, _vp, _vp]
+lib.orc_sensor_readout.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+
+
+class RobotHW:
+    """DefaultRobotHWSim (default_robot_hw_sim.cpp) for ONE env of an Oracle.  pid rows: p, i, d, i_max, i_min,
+    antiwindup; limits: list of dicts with b2mjJointLimits field names, or None."""
+
+    def __init__(self, oracle: Oracle, joint_ids, modes, kinds, lower=None, upper=None, effort_limit=None, pid=None,
+                 limits=None, literal_indexing=False):
+        from mujoco_ros_pkgs_b200 import _capi
+
+        self.o = oracle
+        nj = len(joint_ids)
+        self.nj = nj
+
+        def arr(x, dt):
+            return None if x is None else np.ascontiguousarray(x, dtype=dt)
+
+        a = [arr(joint_ids, np.int32), arr(modes, np.int32), arr(kinds, np.int32), arr(lower, np.float64),
+             arr(upper, np.float64), arr(effort_limit, np.float64), arr(pid, np.float64)]
+        if a[6] is not None:
+            assert a[6].shape == (nj, 6)
+        lim = None
+        if limits is not None:
+            lim = (_capi.B2mjJointLimits * nj)()
+            for k, d in enumerate(limits):
+                for name, val in d.items():
+                    setattr(lim[k], name, val)
+        ptr = lambda x: None if x is None else x.ctypes.data
+        self._h = _vp(lib.orc_hw_create(oracle.model.ptr, nj, *[ptr(x) for x in a],
+                                        C.cast(lim, _vp) if lim is not None else None, int(literal_indexing)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.orc_hw_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def read(self):
+        lib.orc_hw_read(self._h, self.o.model.ptr, self.o._d)
+
+    def write(self, cmd, e_stop=False, period=0.001):
+        c = np.ascontiguousarray(cmd, dtype=np.float64)
+        assert c.size == self.nj
+        lib.orc_hw_write(self._h, self.o.model.ptr, self.o._d, c.ctypes.data, int(e_stop), float(period))
+
+    def state(self):
+        outs = [np.zeros(self.nj) for _ in range(3)]
+        lib.orc_hw_state(self._h, *[x.ctypes.data for x in outs])
+        return outs
+
+
+def sensor_readout(oracle: Oracle, flag=None, mean=None, sigma=None, normals=None):
+    """MujocoRosSensorsPlugin::lastStageCallback arithmetic for one env: returns (values, gt) [nsensordata]."""
+    m = oracle.model
+    ns = max(m.nsensor, 1)
+    flag = np.ascontiguousarray(flag if flag is not None else np.zeros(ns), dtype=np.int32)
+    mean = np.ascontiguousarray(mean if mean is not None else np.zeros((ns, 3)), dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma if sigma is not None else np.zeros((ns, 3)), dtype=np.float64)
+    normals = np.ascontiguousarray(normals if normals is not None else np.zeros(3 * ns), dtype=np.float64)
+    v = np.zeros(max(m.nsensordata, 1))
+    g = np.zeros(max(m.nsensordata, 1))
+    lib.orc_sensor_readout(m.ptr, oracle._d, flag.ctypes.data, mean.ctypes.data, sigma.ctypes.data,
+                           normals.ctypes.data, v.ctypes.data, g.ctypes.data)
+    return v[:m.nsensordata], g[:m.nsensordata]
