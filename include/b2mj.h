@@ -389,11 +389,21 @@ int b2mj_sensor_configure_noise(b2mj_handle* h, const b2mjSensorNoise* models, i
  * (noisy quaternions stay float64, as tf2 composes them); gt is the noise-free value.
  * gt may be NULL (eval mode publishes no ground truth: mujoco_sensor_handler_plugin.cpp:65-67). */
 int b2mj_sensor_readout(b2mj_handle* h, double* values, double* gt);
+/* device-resident form: same kernel, no copy, no synchronisation; returns DEVICE pointers ([nenv][nsensordata]) that
+ * stay valid until destroy (dev_gt may be NULL) */
+int b2mj_sensor_readout_device(b2mj_handle* h, double** dev_values, double** dev_gt);
 
 /* multi-GPU publish: gather this rank's [nenv][count] slab of field f into dev_dst_all
  * ([world][nenv][count], device pointer) using the NCCL communicator passed as void* (ncclComm_t).
  * Only exchange step on the path. */
 int b2mj_allgather_publish(b2mj_handle* h, b2mj_field f, void* nccl_comm, void* dev_dst_all);
+/* same for several float64 fields packed per env ([nenv][sum of counts], fields in the order given) and gathered with
+ * ONE collective: the aggregated state + sensor publish of a step (what the reference's lastStage consumers read after
+ * mj_step, mujoco_env.cpp:593-595).  dev_dst_all: [world][nenv][sum of counts]. */
+int b2mj_allgather_publish_multi(b2mj_handle* h, const b2mj_field* fields, int nfields, void* nccl_comm, void* dev_dst_all);
+/* the packing step alone (no collective): this rank's slab, DEVICE pointer valid until the next publish call;
+ * *count_per_env = sum of the field counts */
+int b2mj_publish_pack(b2mj_handle* h, const b2mj_field* fields, int nfields, double** dev_slab, int* count_per_env);
 
 /* introspection for the benchmark / roofline */
 typedef struct b2mjLaunchInfo {
@@ -417,6 +427,10 @@ const char* b2mj_stage_name(int stage);
 /* diagnostic: SM residency of each env's last work item (last launch, or last rollout chunk), in units of
  * 1024 cycles; host_kcycles: HOST int32 [nenv].  Shows the load imbalance between envs. */
 int b2mj_env_cycles(b2mj_handle* h, int* host_kcycles);
+
+/* measured FP64 peak of a device (dependent-free DFMA chains on every SM): the denominator of the FP64 roofline
+ * bench.py reports beside the HBM one */
+int b2mj_ubench_dfma(int device, double* tflops, double* dfma_per_clk_per_sm);
 
 const char* b2mj_last_error(void);
 int b2mj_version(void);

@@ -43,6 +43,11 @@ lib.b2mj_robot_hw_read.argtypes = [_vp, _vp, _vp, _vp]
 lib.b2mj_sensor_configure_noise.argtypes = [_vp, C.POINTER(_capi.B2mjSensorNoise), C.c_int, C.c_uint64]
 lib.b2mj_sensor_readout.argtypes = [_vp, _vp, _vp]
 lib.b2mj_allgather_publish.argtypes = [_vp, C.c_int, _vp, _vp]
+lib.b2mj_allgather_publish_multi.argtypes = [_vp, C.POINTER(C.c_int), C.c_int, _vp, _vp]
+lib.b2mj_publish_pack.argtypes = [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp), C.POINTER(C.c_int)]
+lib.b2mj_sensor_readout_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
+lib.b2mj_robot_hw_state_ptrs.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
+lib.b2mj_ubench_dfma.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
 
 
 class BatchSim:
@@ -199,6 +204,33 @@ class BatchSim:
         outs = [np.zeros((self.nenv, self._hw_nj)) for _ in range(3)]
         check(lib.b2mj_robot_hw_read(self._h, *[o.ctypes.data for o in outs]), "robot_hw_read")
         return outs
+
+    def robot_hw_write_device(self, cmd_dev_ptr: int, e_stop=False, period=0.001):
+        """cmd already on the device ([nenv][njoint] float64): no copy, asynchronous."""
+        check(lib.b2mj_robot_hw_write(self._h, _vp(cmd_dev_ptr), 1, int(e_stop), float(period)), "robot_hw_write")
+
+    def robot_hw_refresh(self):
+        """readSim on the device only (no copies, no synchronisation)."""
+        check(lib.b2mj_robot_hw_read(self._h, None, None, None), "robot_hw_read")
+
+    def sensor_readout_device(self, want_gt=False):
+        v, g = _vp(), _vp()
+        check(lib.b2mj_sensor_readout_device(self._h, C.byref(v), C.byref(g) if want_gt else None), "sensor_readout_device")
+        return v.value, g.value
+
+    def publish_fields(self, names):
+        ids = (C.c_int * len(names))(*[_capi.field_id(n) for n in names])
+        return ids, len(names)
+
+    def allgather_publish_multi(self, names, comm_ptr, dst_dev_ptr: int):
+        ids, n = self.publish_fields(names)
+        check(lib.b2mj_allgather_publish_multi(self._h, ids, n, comm_ptr, _vp(dst_dev_ptr)), "allgather_publish_multi")
+
+    def publish_pack(self, names):
+        ids, n = self.publish_fields(names)
+        slab, row = _vp(), C.c_int()
+        check(lib.b2mj_publish_pack(self._h, ids, n, C.byref(slab), C.byref(row)), "publish_pack")
+        return slab.value, row.value
 
     def sensor_configure_noise(self, models, seed=0):
         arr = (_capi.B2mjSensorNoise * max(1, len(models)))()

@@ -583,12 +583,8 @@ int b2mj_sensor_configure_noise(b2mj_handle* hh, const b2mjSensorNoise* models, 
   return 0;
 }
 
-int b2mj_sensor_readout(b2mj_handle* hh, double* values, double* gt) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
-  if (!h || !values) return B2MJ_EINVAL;
+static int sensor_readout_launch(Handle* h, bool want_gt) {
   const b2mjModel* m = h->model;
-  if (m->nsensordata == 0) return 0;
-  CUDA_OK(cudaSetDevice(h->device));
   if (!h->sensor_ro) h->sensor_ro = new SensorReadoutState();
   SensorReadoutState* s = h->sensor_ro;
   const size_t n = (size_t)h->nenv * m->nsensordata;
@@ -601,39 +597,91 @@ int b2mj_sensor_readout(b2mj_handle* hh, double* values, double* gt) {
   sensor_readout_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(
       h->rec, d.rec_pitch, d.rec_sensordata, h->nenv, m->nsensor, m->nsensordata, d.sensor_type, d.sensor_adr, d.sensor_dim,
       d.sensor_cutoff, s->mean, s->sigma, s->flag, (unsigned long long)s->seed, (unsigned long long)s->count, s->values,
-      gt ? s->gt : nullptr);
+      want_gt ? s->gt : nullptr);
   CUDA_OK(cudaGetLastError());
   h->launches++;
   s->count++;
+  return 0;
+}
+
+int b2mj_sensor_readout(b2mj_handle* hh, double* values, double* gt) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !values) return B2MJ_EINVAL;
+  const b2mjModel* m = h->model;
+  if (m->nsensordata == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (int rc = sensor_readout_launch(h, gt != nullptr)) return rc;
+  SensorReadoutState* s = h->sensor_ro;
+  const size_t n = (size_t)h->nenv * m->nsensordata;
+  CUDA_OK(cudaMemcpyAsync(values, s->values, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (gt) CUDA_OK(cudaMemcpyAsync(gt, s->gt, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
-  CUDA_OK(cudaMemcpy(values, s->values, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (gt) CUDA_OK(cudaMemcpy(gt, s->gt, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b2mj_sensor_readout_device(b2mj_handle* hh, double** dev_values, double** dev_gt) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !dev_values) return B2MJ_EINVAL;
+  if (h->model->nsensordata == 0) { *dev_values = nullptr; if (dev_gt) *dev_gt = nullptr; return 0; }
+  CUDA_OK(cudaSetDevice(h->device));
+  if (int rc = sensor_readout_launch(h, dev_gt != nullptr)) return rc;
+  *dev_values = h->sensor_ro->values;
+  if (dev_gt) *dev_gt = h->sensor_ro->gt;
   return 0;
 }
 
 // NCCL is resolved at run time from the process (torch ships libnccl); no link-time dependency.
-int b2mj_allgather_publish(b2mj_handle* hh, b2mj_field f, void* nccl_comm, void* dev_dst_all) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
-  if (!h || !nccl_comm || !dev_dst_all) return B2MJ_EINVAL;
-  typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
-  static allgather_fn fn = nullptr;
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+static nccl_allgather_fn resolve_allgather() {
+  static nccl_allgather_fn fn = nullptr;
   if (!fn) {
-    fn = (allgather_fn)dlsym(RTLD_DEFAULT, "ncclAllGather");
+    fn = (nccl_allgather_fn)dlsym(RTLD_DEFAULT, "ncclAllGather");
     if (!fn) {
       void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-      if (lib) fn = (allgather_fn)dlsym(lib, "ncclAllGather");
+      if (lib) fn = (nccl_allgather_fn)dlsym(lib, "ncclAllGather");
     }
-    if (!fn) { set_error("b2mj_allgather_publish: ncclAllGather not found in the process"); return B2MJ_EUNSUPPORTED; }
   }
-  void* ptr; size_t pitch;
-  if (int rc = b2mj_device_ptr(hh, f, &ptr, &pitch)) return rc;
-  int is_int = 0;
-  const int n = b2mj_field_size(h->model, f, &is_int);
-  if (is_int) { set_error("b2mj_allgather_publish: float64 fields only"); return B2MJ_EINVAL; }
+  return fn;
+}
+
+// one thread per (env, element of the packed row): rows gathered from the strided record / side arrays
+struct PackSrc { const double* base; int pitch, count, dst_off; };
+#define B2MJ_MAX_PUBLISH_FIELDS 8
+struct PackArgs { PackSrc src[B2MJ_MAX_PUBLISH_FIELDS]; int nsrc, row, nenv; };
+__global__ void publish_pack_kernel(PackArgs a, double* __restrict__ slab) {
+  const long long total = (long long)a.nenv * a.row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int env = (int)(i / a.row), k = (int)(i - (long long)env * a.row);
+    int s = 0;
+    while (s + 1 < a.nsrc && k >= a.src[s + 1].dst_off) s++;
+    slab[i] = a.src[s].base[(size_t)env * a.src[s].pitch + (k - a.src[s].dst_off)];
+  }
+}
+
+int b2mj_publish_pack(b2mj_handle* hh, const b2mj_field* fields, int nfields, double** dev_slab, int* count_per_env) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !fields || nfields <= 0 || nfields > B2MJ_MAX_PUBLISH_FIELDS || !dev_slab) {
+    set_error("b2mj_publish_pack: bad argument (1.." + std::to_string(B2MJ_MAX_PUBLISH_FIELDS) + " fields)");
+    return B2MJ_EINVAL;
+  }
+  PackArgs a{};
+  int row = 0;
+  for (int i = 0; i < nfields; i++) {
+    void* ptr; size_t pitch;
+    if (int rc = b2mj_device_ptr(hh, fields[i], &ptr, &pitch)) return rc;
+    int is_int = 0;
+    const int n = b2mj_field_size(h->model, fields[i], &is_int);
+    if (is_int) { set_error("b2mj_publish_pack: float64 fields only"); return B2MJ_EINVAL; }
+    if (n == 0) continue;
+    a.src[a.nsrc++] = PackSrc{(const double*)ptr, (int)pitch, n, row};
+    row += n;
+  }
+  if (count_per_env) *count_per_env = row;
+  if (row == 0) { *dev_slab = nullptr; return 0; }
+  a.row = row;
+  a.nenv = h->nenv;
   CUDA_OK(cudaSetDevice(h->device));
-  // pack the strided field into a contiguous slab at this rank's slot, then gather in place
-  // (rank slot unknown here: use a private staging slab and an out-of-place gather)
-  const size_t cnt = (size_t)h->nenv * n;
+  const size_t cnt = (size_t)h->nenv * row;
   if (h->publish_slab_n < cnt) {
     CUDA_OK(cudaStreamSynchronize(h->stream));  // an earlier gather may still read the old slab
     cudaFree(h->publish_slab);
@@ -642,13 +690,31 @@ int b2mj_allgather_publish(b2mj_handle* hh, b2mj_field f, void* nccl_comm, void*
     CUDA_OK(cudaMalloc(&h->publish_slab, cnt * sizeof(double)));
     h->publish_slab_n = cnt;
   }
-  double* slab = h->publish_slab;
-  CUDA_OK(cudaMemcpy2DAsync(slab, n * sizeof(double), ptr, pitch * sizeof(double), n * sizeof(double), h->nenv,
-                            cudaMemcpyDeviceToDevice, h->stream));
-  const int rc = fn(slab, dev_dst_all, cnt, /*ncclDouble*/ 8, nccl_comm, h->stream);
+  const int blocks = (int)std::min<size_t>((cnt + 255) / 256, 148 * 8);
+  publish_pack_kernel<<<blocks, 256, 0, h->stream>>>(a, h->publish_slab);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  *dev_slab = h->publish_slab;
+  return 0;
+}
+
+int b2mj_allgather_publish_multi(b2mj_handle* hh, const b2mj_field* fields, int nfields, void* nccl_comm, void* dev_dst_all) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !nccl_comm || !dev_dst_all) return B2MJ_EINVAL;
+  nccl_allgather_fn fn = resolve_allgather();
+  if (!fn) { set_error("b2mj_allgather_publish: ncclAllGather not found in the process"); return B2MJ_EUNSUPPORTED; }
+  double* slab = nullptr;
+  int row = 0;
+  if (int rc = b2mj_publish_pack(hh, fields, nfields, &slab, &row)) return rc;
+  if (row == 0) return 0;
+  const int rc = fn(slab, dev_dst_all, (size_t)h->nenv * row, /*ncclDouble*/ 8, nccl_comm, h->stream);
   if (rc != 0) { set_error("ncclAllGather failed with code " + std::to_string(rc)); return B2MJ_ECUDA; }
   h->launches++;
   return 0;
+}
+
+int b2mj_allgather_publish(b2mj_handle* hh, b2mj_field f, void* nccl_comm, void* dev_dst_all) {
+  return b2mj_allgather_publish_multi(hh, &f, 1, nccl_comm, dev_dst_all);
 }
 
 }  // extern "C"

@@ -198,3 +198,55 @@ def sensor_readout(oracle: Oracle, flag=None, mean=None, sigma=None, normals=Non
     lib.orc_sensor_readout(m.ptr, oracle._d, flag.ctypes.data, mean.ctypes.data, sigma.ctypes.data,
                            normals.ctypes.data, v.ctypes.data, g.ctypes.data)
     return v[:m.nsensordata], g[:m.nsensordata]
+
+
+class _RolloutArgs(C.Structure):
+    _fields_ = [("nenv", C.c_int), ("nsteps", C.c_int), ("nthreads", C.c_int),
+                ("qpos", _vp), ("qvel", _vp), ("act", _vp), ("warm", _vp), ("time", _vp),
+                ("ctrl", _vp), ("sensor_out", _vp),
+                ("hw_njoint", C.c_int), ("hw_joint_id", _vp), ("hw_mode", _vp), ("hw_kind", _vp),
+                ("hw_lower", _vp), ("hw_upper", _vp), ("hw_effort", _vp), ("hw_pid6", _vp), ("hw_limits", _vp),
+                ("hw_cmd", _vp), ("hw_control_every", C.c_int)]
+
+
+lib.orc_rollout_ex.restype = C.c_double
+lib.orc_rollout_ex.argtypes = [_vp, C.POINTER(_RolloutArgs)]
+
+
+def rollout_ex(model, state, nsteps, ctrl=None, nthreads=1, want_sensors=False, hw=None, hw_cmd=None,
+               hw_control_every=1):
+    """CPU baseline driver from a full state snapshot.  state: dict with qpos, qvel and optionally act,
+    qacc_warmstart, time ([nenv][...]); updated copies are returned.  hw: dict(joint_ids, modes, kinds, lower, upper,
+    effort, pid6) enables the actuator-write path with hw_cmd [nsteps][nenv][nj].  Returns (seconds, state, sensors)."""
+    c64 = lambda x: np.ascontiguousarray(x, dtype=np.float64).copy()  # noqa: E731
+    st = {k: c64(v) for k, v in state.items() if v is not None and np.size(v)}
+    nenv = st["qpos"].shape[0]
+    a = _RolloutArgs()
+    a.nenv, a.nsteps, a.nthreads = nenv, nsteps, nthreads
+    a.qpos, a.qvel = st["qpos"].ctypes.data, st["qvel"].ctypes.data
+    a.act = st["act"].ctypes.data if "act" in st else None
+    a.warm = st["qacc_warmstart"].ctypes.data if "qacc_warmstart" in st else None
+    a.time = st["time"].ctypes.data if "time" in st else None
+    keep = []
+    if ctrl is not None and model.nu:
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        assert ctrl.shape == (nsteps, nenv, model.nu), ctrl.shape
+        a.ctrl = ctrl.ctypes.data
+    sens = np.zeros((nenv, max(model.nsensordata, 1)), dtype=np.float32) if want_sensors else None
+    a.sensor_out = sens.ctypes.data if sens is not None else None
+    if hw is not None:
+        nj = len(hw["joint_ids"])
+        a.hw_njoint = nj
+        for name, key, dt in (("hw_joint_id", "joint_ids", np.int32), ("hw_mode", "modes", np.int32),
+                              ("hw_kind", "kinds", np.int32), ("hw_lower", "lower", np.float64),
+                              ("hw_upper", "upper", np.float64), ("hw_effort", "effort", np.float64),
+                              ("hw_pid6", "pid6", np.float64)):
+            arr = np.ascontiguousarray(hw[key], dtype=dt)
+            keep.append(arr)
+            setattr(a, name, arr.ctypes.data)
+        hw_cmd = np.ascontiguousarray(hw_cmd, dtype=np.float64)
+        assert hw_cmd.shape == (nsteps, nenv, nj)
+        a.hw_cmd = hw_cmd.ctypes.data
+        a.hw_control_every = hw_control_every
+    secs = lib.orc_rollout_ex(model.ptr, C.byref(a))
+    return secs, st, sens

@@ -47,6 +47,32 @@ void* orc_field_ptr(OrcData* d, int field);
 double orc_rollout(const b2mjModel* m, int nenv, int nsteps, double* qpos, double* qvel, const double* ctrl,
                    int nthreads, float* sensor_out /* [nenv][nsensordata] or NULL */);
 
+/* ---- plugin data paths restated from the reference's own sources (orc_plugins.cpp) ---- */
+typedef struct OrcRobotHW OrcRobotHW;
+OrcRobotHW* orc_hw_create(const b2mjModel* m, int nj, const int* joint_id, const int* method, const int* type,
+                          const double* lower, const double* upper, const double* effort_limit, const double* pid6,
+                          const b2mjJointLimits* limits, int literal_indexing);
+void orc_hw_free(OrcRobotHW* hw);
+void orc_hw_read(OrcRobotHW* hw, const b2mjModel* m, const OrcData* d);   /* DefaultRobotHWSim::readSim */
+void orc_hw_write(OrcRobotHW* hw, const b2mjModel* m, OrcData* d, const double* cmd, int e_stop, double period);
+void orc_hw_state(const OrcRobotHW* hw, double* pos, double* vel, double* eff);
+void orc_sensor_readout(const b2mjModel* m, const OrcData* d, const int* flag, const double* mean, const double* sigma,
+                        const double* normals, double* values, double* gt);   /* lastStageCallback arithmetic */
+
+typedef struct OrcRolloutArgs {
+  int nenv, nsteps, nthreads;
+  double *qpos, *qvel, *act, *warm, *time; /* in/out, [nenv][nq|nv|na|nv|1]; act / warm / time may be NULL */
+  const double* ctrl;                      /* [nsteps][nenv][nu] or NULL */
+  float* sensor_out;                       /* [nenv][nsensordata] or NULL */
+  int hw_njoint;                           /* 0 = no actuator-write path */
+  const int *hw_joint_id, *hw_mode, *hw_kind;
+  const double *hw_lower, *hw_upper, *hw_effort, *hw_pid6;
+  const b2mjJointLimits* hw_limits;
+  const double* hw_cmd;                    /* [nsteps][nenv][hw_njoint] */
+  int hw_control_every;
+} OrcRolloutArgs;
+double orc_rollout_ex(const b2mjModel* m, const OrcRolloutArgs* a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,9 +22,11 @@
 // same dof address (:273-321); reads use the MuJoCo joint id (:237).  `literal_indexing` reproduces that; the default
 // (0) uses the joint id for writes as well.  The two agree whenever transmissions are listed in MuJoCo joint order
 // over a hinge/slide-only prefix (every model the reference ships; tests/test_gpu_plugins.py checks it on hand_like).
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "orc_types.h"
@@ -455,6 +457,62 @@ void orc_sensor_readout(const b2mjModel* m, const OrcData* d, const int* flag, c
       values[adr + k] = (double)static_cast<float>(d->sensordata[adr + k] + noise / cutoff);
     }
   }
+}
+
+// CPU baseline driver with the full state record and the actuator-write path (bench.py cpu_baseline / --impl reference
+// for the configs that go through mujoco_ros_control): per env and step, readSim every `hw_control_every` steps, writeSim
+// every step (mujoco_ros_control_plugin.cpp:176-193), mj_step, last-stage sensor readout.  Threads over envs.
+double orc_rollout_ex(const b2mjModel* m, const OrcRolloutArgs* a) {
+  const int nthreads = a->nthreads < 1 ? 1 : a->nthreads;
+  std::vector<OrcData*> datas(nthreads);
+  for (auto& p : datas) p = orc_make_data(m);
+  const int nj = a->hw_njoint;
+  auto worker = [&](int tid) {
+    OrcData* d = datas[tid];
+    std::vector<double> vals(m->nsensordata > 0 ? m->nsensordata : 1), gt(vals.size());
+    std::vector<int> zflag(m->nsensor > 0 ? m->nsensor : 1, 0);
+    std::vector<double> zms(3 * zflag.size(), 0.0);
+    for (int e = tid; e < a->nenv; e += nthreads) {
+      orc_reset_data(m, d);
+      std::memcpy(d->qpos, a->qpos + (size_t)e * m->nq, sizeof(double) * m->nq);
+      std::memcpy(d->qvel, a->qvel + (size_t)e * m->nv, sizeof(double) * m->nv);
+      if (a->act && m->na) std::memcpy(d->act, a->act + (size_t)e * m->na, sizeof(double) * m->na);
+      if (a->warm) std::memcpy(d->qacc_warmstart, a->warm + (size_t)e * m->nv, sizeof(double) * m->nv);
+      if (a->time) d->time[0] = a->time[e];
+      OrcRobotHW* hw = nj ? orc_hw_create(m, nj, a->hw_joint_id, a->hw_mode, a->hw_kind, a->hw_lower, a->hw_upper,
+                                           a->hw_effort, a->hw_pid6, a->hw_limits, 0)
+                          : nullptr;
+      for (int s = 0; s < a->nsteps; s++) {
+        if (a->ctrl && m->nu) std::memcpy(d->ctrl, a->ctrl + ((size_t)s * a->nenv + e) * m->nu, sizeof(double) * m->nu);
+        if (hw) {
+          if (s % (a->hw_control_every > 0 ? a->hw_control_every : 1) == 0) orc_hw_read(hw, m, d);
+          orc_hw_write(hw, m, d, a->hw_cmd + ((size_t)s * a->nenv + e) * nj, 0, m->opt.timestep);
+        }
+        orc_step(m, d);
+        if (a->sensor_out && m->nsensordata) {
+          orc_sensor_readout(m, d, zflag.data(), zms.data(), zms.data(), zms.data(), vals.data(), gt.data());
+          for (int k = 0; k < m->nsensordata; k++) a->sensor_out[(size_t)e * m->nsensordata + k] = (float)vals[k];
+        }
+      }
+      if (hw) orc_hw_free(hw);
+      std::memcpy(a->qpos + (size_t)e * m->nq, d->qpos, sizeof(double) * m->nq);
+      std::memcpy(a->qvel + (size_t)e * m->nv, d->qvel, sizeof(double) * m->nv);
+      if (a->act && m->na) std::memcpy(a->act + (size_t)e * m->na, d->act, sizeof(double) * m->na);
+      if (a->warm) std::memcpy(a->warm + (size_t)e * m->nv, d->qacc_warmstart, sizeof(double) * m->nv);
+      if (a->time) a->time[e] = d->time[0];
+    }
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  if (nthreads == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(worker, t);
+    for (auto& t : th) t.join();
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (auto p : datas) orc_free_data(p);
+  return secs;
 }
 
 }  // extern "C"
