@@ -28,11 +28,11 @@ $(BUILD)/%.o: $(CSRC)/%.cpp $(ROOT)/include/b2mj.h $(wildcard $(CSRC)/*/*.h)
 
 $(BUILD)/%.cu.o: $(CSRC)/%.cu $(ROOT)/include/b2mj.h $(wildcard $(CSRC)/*/*.h) $(wildcard $(CSRC)/*/*.cuh)
 	@mkdir -p $(dir $@)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) $(NVFLAGS_$(notdir $<)) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
 
 # The plugin data paths (robot_hw, sensor readout) are compared BITWISE against oracle/orc_plugins.cpp, which follows the
 # reference's C++ line by line (plain IEEE double arithmetic): no FMA contraction in that file.
-$(BUILD)/host/plugins.cu.o: EXTRA += -fmad=false
+NVFLAGS_plugins.cu := -fmad=false
 
 $(LIB): $(HOST_OBJS) $(CUDA_OBJS)
 	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $^ -cudart static

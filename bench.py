@@ -333,7 +333,7 @@ def parity_gate(model, snap, ctrl_seq, nsteps, nsub=64):
 def time_fused(C, sim, snap, ctrl_dev, W, K, traj=True):
     """restore -> warm-up rollout (W steps) -> L2 flush -> ONE timed rollout launch of K steps.  Returns
     (ms, launches, trajectory-finite flag)."""
-    torch, model, stream, nenv = C.torch, C.model, C.stream, sim.nenv
+    torch, model, stream, nenv = C.torch, sim.model, C.stream, sim.nenv
     restore(sim, snap)
     nu, ns = model.nu, model.nsensordata
     n = max(K, W)

@@ -392,27 +392,58 @@ static int make_layout(Handle* h) {
     if (bestW_out) *bestW_out = bestW;
     return bestEnv;
   };
-  // Tier 1: demote the constraint / contact working set until the arena meets the target, then keep going only
-  // while that removes a whole WAVE of a per-step launch (waves = ceil(nenv / resident envs); e.g. C2 at 4096
-  // envs: 16.0 KB -> 13 envs/SM -> 3 waves, 15.2 KB -> 14 envs/SM -> 2 waves, +14% end to end).
+  // Placement policy (round 2).  All candidates start in the HBM/L2 arena; they are promoted to shared memory hottest
+  // first while the batch keeps its residency.  Residency target: with only the fixed fields on chip an SM holds E0
+  // envs, the batch then needs w = ceil(nenv / (E0 * SMs)) waves; E = ceil(nenv / (w * SMs)) <= E0 is the SMALLEST
+  // residency that still runs in w waves, and every byte of shared memory beyond E envs per SM is free to hold solver
+  // state.  For the BASELINE batch sizes: C2 (4096 envs) E0 = E = 14 -> the round-1 layout; C3 (1024 envs) E0 = 6,
+  // w = 2, E = 4 -> 57 KB per env; C4 (2048 envs) E0 = E = 4 -> 57 KB.  In round 1 every solver array of the Newton
+  // configs (H, Jaref, Jv, quad, D, state, ... even the 4.6 KB Hessian of the hand) lived in L2: each dependent access
+  // in the Cholesky / line search paid ~400 cycles (solve = 69 % of a C3 / C4 step, 94 % of C5).
   {
-    auto waves = [&]() {
-      const int eps = envs_per_sm(nullptr);
-      return eps > 0 ? (h->nenv + eps * sms - 1) / (eps * sms) : 1 << 30;
-    };
-    size_t k = 0;
-    for (; k < cands.size() && smem_bytes_env() > target; k++) {
-      if (cands[k].is_x) xcold[cands[k].id] = 1; else cold[cands[k].id] = 1;
+    (void)target;
+    for (const Cand& c : cands) { if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1; }
+    int E = 1;
+    {
+      const int E0 = std::max(1, envs_per_sm(nullptr));
+      const int w = (h->nenv + E0 * sms - 1) / (E0 * sms);
+      E = std::max(1, std::min(E0, (h->nenv + w * sms - 1) / (w * sms)));
+      if (const char* env = getenv("B2MJ_ENVS_PER_SM")) E = std::max(1, atoi(env));
     }
-    std::vector<char> best_cold = cold, best_xcold = xcold;
-    int best_waves = waves();
-    for (; k < cands.size() && best_waves > 1 && !getenv("B2MJ_NO_WAVE_FIT"); k++) {
-      if (cands[k].is_x) xcold[cands[k].id] = 1; else cold[cands[k].id] = 1;
-      const int w = waves();
-      if (w < best_waves) { best_waves = w; best_cold = cold; best_xcold = xcold; }
+    // hottest first: what the solver touches in every iteration, then once-per-step arrays, largest last
+    std::vector<std::pair<int, int>> order;  // (is_x, id)
+    if (newton || m->opt.solver == B2MJ_SOL_CG) {
+      for (int x : {XF_NEWTON_H, XF_EFC_JAREF, XF_EFC_JV, XF_EFC_QUAD}) order.push_back({1, x});
+      for (int f : {B2MJ_F_EFC_D, B2MJ_F_EFC_STATE, B2MJ_F_EFC_FORCE, B2MJ_F_EFC_AREF, B2MJ_F_EFC_TYPE, B2MJ_F_EFC_ID,
+                    B2MJ_F_EFC_R, B2MJ_F_EFC_FRICTIONLOSS, B2MJ_F_CONTACT_DIM, B2MJ_F_CONTACT_EFC_ADDRESS,
+                    B2MJ_F_CONTACT_MU, B2MJ_F_CONTACT_FRICTION})
+        order.push_back({0, f});
+      order.push_back({1, XF_CONTACT_H});
+      for (int f : {B2MJ_F_EFC_B, B2MJ_F_EFC_J, B2MJ_F_EFC_VEL, B2MJ_F_EFC_POS, B2MJ_F_EFC_MARGIN}) order.push_back({0, f});
+    } else {
+      for (int f : {B2MJ_F_EFC_FORCE, B2MJ_F_EFC_B, B2MJ_F_EFC_TYPE, B2MJ_F_EFC_ID}) order.push_back({0, f});
+      order.push_back({1, XF_EFC_ARDIAG});
+      for (int f : {B2MJ_F_CONTACT_DIM, B2MJ_F_CONTACT_EFC_ADDRESS, B2MJ_F_CONTACT_GEOM1, B2MJ_F_CONTACT_GEOM2,
+                    B2MJ_F_CONTACT_EXCLUDE, B2MJ_F_EFC_R, B2MJ_F_EFC_D, B2MJ_F_EFC_AREF, B2MJ_F_EFC_FRICTIONLOSS,
+                    B2MJ_F_CONTACT_FRICTION})
+        order.push_back({0, f});
+      order.push_back({1, XF_EFC_JAREF});
+      order.push_back({0, B2MJ_F_EFC_J});
+      order.push_back({1, XF_EFC_MINVJT});
     }
-    cold = best_cold;
-    xcold = best_xcold;
+    // the rest, smallest first
+    std::vector<Cand> rest(cands.begin(), cands.end());
+    std::stable_sort(rest.begin(), rest.end(), [](const Cand& a, const Cand& b) { return a.bytes < b.bytes; });
+    for (const Cand& c : rest) order.push_back({c.is_x, c.id});
+    const bool no_promote = getenv("B2MJ_NO_PROMOTE") != nullptr;
+    for (const auto& o : order) {
+      char& flag = o.first ? xcold[o.second] : cold[o.second];
+      const int sz = o.first ? xs[o.second] : d.fsize[o.second];
+      if (!flag || !sz || no_promote) continue;
+      if (o.first && o.second == XF_EFC_AR) continue;  // the full AR always stays in the L2 arena
+      flag = 0;
+      if (envs_per_sm(nullptr) < E) flag = 1;  // does not fit at this residency: stays in L2
+    }
   }
   // A second tier that also demoted write-once/read-once kinematic fields (geom frames, crb, cinert, cvel, ...)
   // was measured and dropped (profiles/r1_layout_sweep.txt): it buys throughput only for contact-free batches far
@@ -441,6 +472,30 @@ static int make_layout(Handle* h) {
   }
   d.arena_s_doubles = even(sdo);
   d.arena_s_ints = even(sio);
+  // PGS AR overlay (stages_solver.cuh::arPtr): the contiguous run of kinematic frame fields xpos .. crb, allowed when no
+  // acc-stage sensor reads frames after the solve (touch, accelerometer, force, torque, frame accelerations do)
+  d.ar_ovl_off = 0;
+  d.ar_ovl_doubles = 0;
+  if (pgs && !getenv("B2MJ_NO_AR_OVERLAY")) {
+    bool ok = true;
+    for (int i = 0; i < m->nsensor && ok; i++) {
+      const int t = m->sensor_type[i];
+      if (m->sensor_needstage[i] == B2MJ_STAGE_ACC && t != B2MJ_SENS_ACTUATORFRC && t != B2MJ_SENS_JOINTACTFRC &&
+          t != B2MJ_SENS_JOINTLIMITFRC && t != B2MJ_SENS_TENDONLIMITFRC)
+        ok = false;
+    }
+    // longest run of consecutively placed hot fields starting at xpos
+    int begin = d.off_s[B2MJ_F_XPOS], end = begin;
+    for (int f = B2MJ_F_XPOS; ok && begin >= 0 && f <= B2MJ_F_CRB; f++) {
+      if (d.off_s[f] < 0 || d.fis_int[f] || !d.fsize[f]) continue;
+      if (d.off_s[f] != end) break;
+      end += d.fsize[f];
+    }
+    if (ok && begin >= 0 && end > begin) {
+      d.ar_ovl_off = begin;
+      d.ar_ovl_doubles = end - begin;
+    }
+  }
   if (getenv("B2MJ_PRINT_LAYOUT")) {
     static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
                                    "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",

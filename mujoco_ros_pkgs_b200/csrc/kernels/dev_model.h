@@ -94,6 +94,7 @@ struct DevModel {
   int fsize[B2MJ_NFIELD];   // per-env element count of each field
   unsigned char fis_int[B2MJ_NFIELD];
   int xsize[XF_COUNT];
+  int ar_ovl_off, ar_ovl_doubles;     // PGS: AR may overlay [xpos .. crb] of the shared arena (0 doubles = not allowed)
   int arena_g_doubles, arena_g_ints;  // full arena sizes per env
   int arena_s_doubles, arena_s_ints;  // shared-memory resident sizes per env
   // ---- state record layout (doubles) ----

@@ -21,10 +21,26 @@ namespace b2k {
 #define B2K_PGS_REGROWS 64
 #define B2K_SPARSE_H_MIN_NV 48  // models wider than this build the Newton Hessian row-sparse
 
-// AR lives in shared memory when it fits the small buffer, else in the env's HBM/L2 arena
+// Where AR (+ the 4 row constants per row that stage_projectConstraint appends after the matrix) lives:
+//  1. the small shared-memory window XF_EFC_AR_S (nefc <= 17 for the C2 model: the common case);
+//  2. else an OVERLAY on the kinematic frames [xpos .. crb] of the env's own arena: by the time the constraint solve
+//     runs (AR is built at the head of stage_fwdConstraint, not in the position stage) nothing reads those fields any
+//     more in a plain step (host-side rule in make_layout: no acc-stage sensor that needs frames; never when the arena
+//     will be dumped).  Round 1 fetched AR from the L2 arena for 18..25 rows -- exactly the envs whose 100-iteration
+//     Gauss-Seidel chains end every per-step launch -- at ~270 cycles per row update against ~140 from shared memory;
+//  3. else the env's HBM / L2 arena.
 __device__ __forceinline__ double* arPtr(const Env e, int nefc) {
-  // the window also holds the 4 row constants per row that stage_projectConstraint appends after the matrix
-  return nefc * (nefc + 4) <= c_dm.xsize[XF_EFC_AR_S] ? e.XG(XF_EFC_AR_S) : e.XG(XF_EFC_AR);
+  const int need = nefc * (nefc + 4);
+  if (need <= c_dm.xsize[XF_EFC_AR_S]) return e.XG(XF_EFC_AR_S);
+  if (!e.dump && need <= c_dm.ar_ovl_doubles) return e.sd() + c_dm.ar_ovl_off;
+  return e.XG(XF_EFC_AR);
+}
+// shared-memory byte offset of AR if it is on chip (cases 1, 2), else 0xffffffff
+__device__ __forceinline__ unsigned arSmemOffset(const Env e, int nefc) {
+  const int need = nefc * (nefc + 4);
+  if (need <= c_dm.xsize[XF_EFC_AR_S]) return e.sbd + 8u * (unsigned)c_dm.xoff_s[XF_EFC_AR_S];
+  if (!e.dump && need <= c_dm.ar_ovl_doubles) return e.sbd + 8u * (unsigned)c_dm.ar_ovl_off;
+  return 0xffffffffu;
 }
 
 // G = J W (rows of J pushed through inv(L)) and AR = G diag(1/D) G' + R
@@ -942,6 +958,8 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
   const bool warmstart = !(m.opt.disableflags & B2MJ_DSBL_WARMSTART);
   int iters = 0;
   if (m.opt.solver == B2MJ_SOL_PGS) {
+    // mj_projectConstraint, deferred from the position stage so that AR may overlay fields that are dead by now
+    stage_projectConstraint(e, nefc);
     double* jar = e.XG(XF_EFC_JAREF);
     double* avec = e.X(XF_VEC1);
     const double* G = e.XG(XF_EFC_MINVJT);
@@ -993,8 +1011,8 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
     }
     if (done) {
     } else if (reg) {
-      const bool sm = nefc * (nefc + 4) <= m.xsize[XF_EFC_AR_S];
-      const unsigned soff = e.sbd + 8u * (unsigned)m.xoff_s[XF_EFC_AR_S];
+      const unsigned soff = arSmemOffset(e, nefc);
+      const bool sm = soff != 0xffffffffu;
       const double* ARg = e.XG(XF_EFC_AR);
       if (sm && nefc <= B2K_G) iters = solvePGS_regT<1, true>(e, nefc, nullptr, soff);
       else if (sm) iters = solvePGS_regT<2, true>(e, nefc, nullptr, soff);   // window holds <= 17 rows

@@ -81,8 +81,7 @@ __device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int e
     stage_crb_factor(e, e.dump != 0); PROF_MARK(PROF_CRB_FACTOR)
     sc.ncon = stage_collision(e, warning); PROF_MARK(PROF_COLLISION)
     sc.nefc = stage_makeConstraint(e, sc.ncon, warning); PROF_MARK(PROF_MAKECONSTRAINT)
-    if (m.opt.solver == B2MJ_SOL_PGS) stage_projectConstraint(e, sc.nefc);
-    PROF_MARK(PROF_PROJECT)
+    PROF_MARK(PROF_PROJECT)  // mj_projectConstraint runs at the head of the solve stage (stage_fwdConstraint)
     if (!skipsensor) stage_sensorPos(e, sc.nefc);
     PROF_MARK(PROF_SENSORPOS)
     stage_velocity_head(e); PROF_MARK(PROF_VELHEAD)

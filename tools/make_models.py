@@ -15,7 +15,7 @@ def hand():
     A('     4 fixed tendons coupling the two distal joints of the four fingers, capsule links, RK4 + Newton + elliptic. -->')
     A('<mujoco model="hand_like">')
     A('  <compiler angle="radian" autolimits="true"/>')
-    A('  <size nconmax="48" njmax="192"/>')
+    A('  <size nconmax="32" njmax="96"/>')
     A('  <option timestep="0.002" integrator="RK4" solver="Newton" cone="elliptic" gravity="0 0 -9.81"/>')
     A('  <default>')
     A('    <joint type="hinge" damping="0.05" armature="0.0002" limited="true"/>')
@@ -117,7 +117,7 @@ def humanoid():
      subtreecom, 21 jointpos, 21 jointvel, 2 touch; nsensordata = 63).  Euler, Newton, pyramidal. -->
 <mujoco model="humanoid_like">
   <compiler angle="degree" autolimits="true"/>
-  <size nconmax="48" njmax="256"/>
+  <size nconmax="32" njmax="128"/>
   <option timestep="0.005" integrator="Euler" solver="Newton" cone="pyramidal"/>
   <default>
     <joint type="hinge" damping="0.2" stiffness="1" armature="0.01" limited="true" solimplimit="0 0.99 0.01"/>
