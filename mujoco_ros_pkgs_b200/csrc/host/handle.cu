@@ -373,25 +373,33 @@ static int make_layout(Handle* h) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const int reg_envs = 512 / B2K_G;  // 128 registers per thread
+  // envs an SM keeps resident when CTAs hold W envs each: asked of the occupancy calculator (registers, allocation
+  // granularity, per-CTA reserve), not estimated
+  auto resident = [&](int W) -> int {
+    const size_t cta = (size_t)W * (smem_bytes_env() + 16);
+    if (W < 1 || W * B2K_G > B2K_MAX_THREADS || cta > kMaxCta - kCtaReserve) return 0;
+    int ctas = 0;
+    if (b2k_occupancy(W * B2K_G, cta, &ctas) != 0) {
+      ctas = (int)(kSmPerSM / (cta + kCtaReserve));
+      ctas = std::min(ctas, reg_envs / W);
+    }
+    return std::min(ctas, 32) * W;
+  };
   auto envs_per_sm = [&](int* bestW_out) {
-    const size_t eb = smem_bytes_env();
     int bestW = 0, bestEnv = 0;
     const int forceW = getenv("B2MJ_WARPS_PER_CTA") ? atoi(getenv("B2MJ_WARPS_PER_CTA")) : h->force_warps_per_cta;
-    const int wstep = 32 / B2K_G;  // W = envs per CTA (each env is served by B2K_G lanes; CTAs hold whole warps)
-    for (int W = wstep; W <= B2K_STEP_THREADS / B2K_G; W += wstep) {
+    for (int W = 1; W <= B2K_STEP_THREADS / B2K_G; W++) {
       if (forceW && W != forceW) continue;
-      const size_t cta = (size_t)W * (eb + 16);
-      if (cta > kMaxCta) continue;
-      int ctas = (int)(kSmPerSM / (cta + kCtaReserve));
-      ctas = std::min(ctas, reg_envs / W);
-      ctas = std::min(ctas, 32);
       // among equals prefer the smallest CTA: a finished env frees its shared memory for the next one
       // immediately instead of waiting for its CTA mates
-      if (ctas * W > bestEnv) { bestEnv = ctas * W; bestW = W; }
+      const int n = resident(W);
+      if (n > bestEnv) { bestEnv = n; bestW = W; }
     }
     if (bestW_out) *bestW_out = bestW;
     return bestEnv;
   };
+  // the lock-stepped rollout CTA (half of an SM's envs) must stay resident twice per SM as well
+  auto rollout_shape_ok = [&](int E) { return E < 4 || (E % 2) || resident(E / 2) >= E; };
   // Placement policy (round 2).  All candidates start in the HBM/L2 arena; they are promoted to shared memory hottest
   // first while the batch keeps its residency.  Residency target: with only the fixed fields on chip an SM holds E0
   // envs, the batch then needs w = ceil(nenv / (E0 * SMs)) waves; E = ceil(nenv / (w * SMs)) <= E0 is the SMALLEST
@@ -436,13 +444,16 @@ static int make_layout(Handle* h) {
     std::stable_sort(rest.begin(), rest.end(), [](const Cand& a, const Cand& b) { return a.bytes < b.bytes; });
     for (const Cand& c : rest) order.push_back({c.is_x, c.id});
     const bool no_promote = getenv("B2MJ_NO_PROMOTE") != nullptr;
+    int promote_left = getenv("B2MJ_PROMOTE_MAX") ? atoi(getenv("B2MJ_PROMOTE_MAX")) : 1 << 30;  // experiment knob
     for (const auto& o : order) {
       char& flag = o.first ? xcold[o.second] : cold[o.second];
       const int sz = o.first ? xs[o.second] : d.fsize[o.second];
       if (!flag || !sz || no_promote) continue;
       if (o.first && o.second == XF_EFC_AR) continue;  // the full AR always stays in the L2 arena
+      if (promote_left <= 0) break;
       flag = 0;
-      if (envs_per_sm(nullptr) < E) flag = 1;  // does not fit at this residency: stays in L2
+      if (envs_per_sm(nullptr) < E || !rollout_shape_ok(E)) flag = 1;  // does not fit at this residency: stays in L2
+      else promote_left--;
     }
   }
   // A second tier that also demoted write-once/read-once kinematic fields (geom frames, crb, cinert, cvel, ...)
@@ -526,10 +537,7 @@ static int make_layout(Handle* h) {
   h->rollout_warps_per_cta = 0;
   {
     const int Wr = bestEnv / 2;
-    const size_t cta = (size_t)Wr * (env_bytes + 16);
-    if (Wr > bestW && Wr * B2K_G <= B2K_MAX_THREADS && (Wr * B2K_G) % 32 == 0 && cta <= kMaxCta &&
-        (int)(kSmPerSM / (cta + kCtaReserve)) * Wr >= bestEnv)
-      h->rollout_warps_per_cta = Wr;
+    if (Wr > bestW && Wr * B2K_G <= B2K_MAX_THREADS && resident(Wr) >= bestEnv) h->rollout_warps_per_cta = Wr;
   }
   if (const char* env = getenv("B2MJ_ROLLOUT_WARPS_PER_CTA")) h->rollout_warps_per_cta = atoi(env);
   h->arena_in_smem = 1;

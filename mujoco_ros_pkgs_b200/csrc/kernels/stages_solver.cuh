@@ -362,20 +362,82 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
 // Lane i owns row i: its residual, force and row constants {1/A_ii, A_ii, lo, hi} stay in registers.  A row update
 // is: the owner clamps its own force (no operand shuffles, no row-constant loads), one shuffle broadcasts the
 // force change, every lane folds it into its residual with one FMA.  The only memory operand, AR[i][lane], does
-// not depend on the chain: it is fetched FOUR ROWS AHEAD into a register ring, so neither an L1 hit (41 cycles) nor
-// an L2 hit (392 cycles, the common case once the 28 KB of L1 left beside the arenas thrashes) is ever waited
-// for.  The dependent chain per row is FMA -> clamp -> shuffle -> FMA; the shuffle-operand version it replaces
-// waited for a row-constant load every row and dominated the slowest envs (21 rows x 100 iterations: 1.34M ->
-// 0.85M cycles for the slowest env of a step).  The row loop stays rolled: a fully unrolled sweep measured 30%
-// SLOWER in the desynchronised rollout (instruction fetch).  Same arithmetic and order as solvePGS_regT.
-// Returns iterations used, or -1 if a cone row is present (caller falls back to solvePGS_regT).
-__device__ __noinline__ int solvePGS_own(const Env e, int nefc, const double* AR) {
+// not depend on the chain: it is fetched two rows ahead into a register ring.  The row loop stays rolled: a fully
+// unrolled sweep measured 30% SLOWER in the desynchronised rollout (instruction fetch).
+//
+// Round 2: the Gauss-Seidel sweep of the heaviest env ends every per-step launch (21-25 rows x 70-100 iterations =
+// 2/3 of the launch).  Measured in situ, a row costs (instructions per row) x ~5.2 cycles -- the warp shares its
+// scheduler and the instruction caches with warps running other stages, so the row is ISSUE bound, not bound by its
+// dependent chain (a variant that shortened the chain by speculating the cost guard but added six instructions per
+// row ran 13 % slower: 261 vs 231 cycles per row).  Hence the row is written for instruction count (44 -> 24):
+//  * the guard value is not broadcast: the owner zeroes its own force change before the one shuffle, and each lane
+//    accumulates the improvement of its own row; one butterfly sum per SWEEP replaces two shuffles + an add per ROW
+//    (the sum is taken in a different order than mj_solPGS takes it: it only feeds the convergence test);
+//  * the next AR operand is fetched through a running pointer (the two rows read past the matrix fall into the row
+//    constants stored behind it), no index clamp / multiply per row;
+//  * 0.5 * A_ii is folded into one constant (exact), so the guard is one FMA and one multiply;
+//  * when every row is an equality (no clamp) or a unilateral row (lo = 0, hi = inf) the clamp is a sign test on the
+//    high word plus a select (SIMPLE = true; friction-loss rows take the generic two-sided form).
+// Forces and residuals are bitwise those of the round-1 form.  Returns iterations used.
+template <bool SIMPLE>
+__device__ __forceinline__ int solvePGS_own_T(const Env e, int nefc, const double* AR, double iA, double Aii, double lo,
+                                              double up, double f, double r, double* f_out) {
   const DevModel& m = c_dm;
-  const double* rowc = AR + nefc * nefc;
-  EfcPtrs P = efcPtrs(e);
   const double scale = 1 / (m.meaninertia * max(1, m.nv));
   const double tol = m.opt.tolerance;
   const int maxiter = m.opt.iterations;
+  const int lane = e.lane;
+  const int me = lane < nefc ? lane : nefc - 1;
+  const bool pos = !(lo < 0);  // unilateral row (lo == 0); equality rows have lo = -inf
+  const double hA = 0.5 * Aii;
+  // register ring: slot k holds AR[row][me] of the next row with row % 2 == k; refilled right after its row consumed
+  // it, two rows ahead.  Rows 0,1 open every sweep and stay in q0,q1.
+  const double* col = AR + me;
+  const double q0 = col[0], q1 = col[nefc];
+  int iter = 0;
+#define B2K_PGS_OWN_ROW(SLOT)                                                  \
+  {                                                                            \
+    const double ai = SLOT;                                                    \
+    const double x = f - r * iA;                                               \
+    double fn;                                                                 \
+    if (SIMPLE) {                                                              \
+      fn = (pos && __double2hiint(x) < 0) ? 0.0 : x;                           \
+    } else {                                                                   \
+      fn = x < lo ? lo : x;                                                    \
+      fn = fn > up ? up : fn;                                                  \
+    }                                                                          \
+    double delta = fn - f;                                                     \
+    const double change = delta * (hA * delta + r);                            \
+    const bool ok = !(change > 1e-10); /* cost guard of mj_solPGS */           \
+    delta = ok ? delta : 0.0;                                                  \
+    const double d = __shfl_sync(e.mask, delta, i, B2K_G);                     \
+    r += ai * d;                                                               \
+    if (ok && lane == i) { f = fn; improvement -= change; }                    \
+    SLOT = *pcol;                                                              \
+    pcol += nefc;                                                              \
+    i++;                                                                       \
+  }
+  while (iter < maxiter) {
+    double improvement = 0;  // this lane's own row only; summed over the warp once per sweep
+    double p0 = q0, p1 = q1;
+    const double* pcol = col + 2 * nefc;
+    int i = 0;
+    B2K_NOUNROLL while (i + 2 <= nefc) {
+      B2K_PGS_OWN_ROW(p0)
+      B2K_PGS_OWN_ROW(p1)
+    }
+    if (i < nefc) B2K_PGS_OWN_ROW(p0)
+    iter++;
+    if (warpSum(e.mask, improvement) * scale < tol) break;
+  }
+#undef B2K_PGS_OWN_ROW
+  *f_out = f;
+  return iter;
+}
+
+__device__ __noinline__ int solvePGS_own(const Env e, int nefc, const double* AR) {
+  const double* rowc = AR + nefc * nefc;
+  EfcPtrs P = efcPtrs(e);
   const int lane = e.lane;
   const bool own = lane < nefc;
   const int me = own ? lane : nefc - 1;
@@ -389,49 +451,14 @@ __device__ __noinline__ int solvePGS_own(const Env e, int nefc, const double* AR
     B2K_NOUNROLL for (int k = 0; k < nefc; k++) acc += AR[lane * nefc + k] * P.force[k];
     r = acc;
   }
-  // register ring: slot k holds AR[row][me] of the next row with row % 2 == k.  A slot is refilled right after its
-  // row consumed it and is not touched again until two rows (~300 cycles) later: the warp issues in order, so even
-  // a register move of a freshly loaded value waits for the load.  Rows 0,1 open every sweep and stay in q0,q1.
-  // (Four slots measured +5% per-step but -9% in the fetch-bound rollout: code size.)
-  const double* col = AR + me;
-  const int last = nefc - 1;
-  const double q0 = col[0], q1 = col[min(1, last) * nefc];
-  int iter = 0;
-#define B2K_PGS_OWN_ROW(SLOT)                                                       \
-  {                                                                                 \
-    const double ai = SLOT;                                                         \
-    double fn = f - r * iA;                                                         \
-    fn = fn < lo ? lo : fn;                                                         \
-    fn = fn > up ? up : fn;                                                         \
-    double delta = fn - f;                                                          \
-    double change = delta * (0.5 * delta * Aii + r);                                \
-    const bool reject = change > 1e-10; /* cost guard of mj_solPGS */               \
-    delta = reject ? 0.0 : delta;                                                   \
-    change = reject ? 0.0 : change;                                                 \
-    const double d = __shfl_sync(e.mask, delta, i, B2K_G);                          \
-    improvement -= __shfl_sync(e.mask, change, i, B2K_G);                           \
-    r += ai * d;                                                                    \
-    /* refill after the last use of ai: the load then targets the slot register itself (no later move) */ \
-    SLOT = col[min(i + 2, last) * nefc];                                            \
-    if (lane == i) f = reject ? f : fn;                                             \
-    i++;                                                                            \
-  }
-  while (iter < maxiter) {
-    double improvement = 0;
-    double p0 = q0, p1 = q1;
-    int i = 0;
-    B2K_NOUNROLL while (i + 2 <= nefc) {
-      B2K_PGS_OWN_ROW(p0)
-      B2K_PGS_OWN_ROW(p1)
-    }
-    if (i < nefc) B2K_PGS_OWN_ROW(p0)
-    iter++;
-    if (improvement * scale < tol) break;
-  }
-#undef B2K_PGS_OWN_ROW
+  // simple rows: (-inf, +inf) or (0, +inf)
+  const bool simple_row = (up == CUDART_INF) && (lo == 0 || lo == -CUDART_INF);
+  int iters;
+  if (__all_sync(e.mask, simple_row)) iters = solvePGS_own_T<true>(e, nefc, AR, iA, Aii, lo, up, f, r, &f);
+  else iters = solvePGS_own_T<false>(e, nefc, AR, iA, Aii, lo, up, f, r, &f);
   if (own) P.force[lane] = f;
   WSYNC();
-  return iter;
+  return iters;
 }
 
 // mj_solPGS, matrix-free form for large nefc: rows of G = J inv(L) and the running vector
