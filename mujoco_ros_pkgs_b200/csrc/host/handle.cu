@@ -301,7 +301,11 @@ static int make_layout(Handle* h) {
   xs[XF_EFC_JAREF] = m->njmax;
   xs[XF_EFC_JV] = pgs ? 0 : m->njmax;
   xs[XF_EFC_QUAD] = pgs ? 0 : 3 * m->njmax;
-  xs[XF_NEWTON_H] = newton ? nv * nv : 0;
+  // team mode (kernels/team.cuh): wide Newton models get one env per CTA and 8 warps; H then has an odd leading dimension
+  d.team_warps = (newton && nv >= B2K_TEAM_MIN_NV && !getenv("B2MJ_NO_TEAM")) ? B2K_TEAM_WARPS : 1;
+  d.ldh = d.team_warps > 1 ? (nv | 1) : nv;
+  xs[XF_NEWTON_H] = newton ? nv * d.ldh : 0;
+  xs[XF_JCOLS] = d.team_warps > 1 ? (m->njmax * 17 + 7) / 8 : 0;
   xs[XF_CONTACT_H] = (newton && m->opt.cone == B2MJ_CONE_ELLIPTIC) ? 36 * m->nconmax : 0;
   xs[XF_SUBTREE_LINVEL] = d.need_subtreevel ? 3 * m->nbody : 0;
   xs[XF_SUBTREE_ANGMOM] = d.need_subtreevel ? 3 * m->nbody : 0;
@@ -368,7 +372,8 @@ static int make_layout(Handle* h) {
     if ((efc || con) && d.fsize[f]) cands.push_back({0, f, (size_t)d.fsize[f] * (d.fis_int[f] ? 4 : 8)});
   }
   for (int x : {XF_NEWTON_H, XF_EFC_MINVJT, XF_EFC_QUAD, XF_CONTACT_H, XF_EFC_ARDIAG, XF_EFC_JAREF, XF_EFC_JV})
-    if (xs[x]) cands.push_back({1, x, (size_t)xs[x] * 8});
+    if (xs[x] && !(x == XF_NEWTON_H && d.team_warps > 1))  // the team factorises H in shared memory: never demoted
+      cands.push_back({1, x, (size_t)xs[x] * 8});
   std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.bytes > b.bytes; });
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -376,10 +381,11 @@ static int make_layout(Handle* h) {
   // envs an SM keeps resident when CTAs hold W envs each: asked of the occupancy calculator (registers, allocation
   // granularity, per-CTA reserve), not estimated
   auto resident = [&](int W) -> int {
-    const size_t cta = (size_t)W * (smem_bytes_env() + 16);
-    if (W < 1 || W * B2K_G > B2K_MAX_THREADS || cta > kMaxCta - kCtaReserve) return 0;
+    const int tw = d.team_warps;
+    const size_t cta = (size_t)W * (smem_bytes_env() + (tw > 1 ? 64 : 16));
+    if (W < 1 || (tw > 1 && W > 1) || W * B2K_G * tw > B2K_MAX_THREADS || cta > kMaxCta - kCtaReserve) return 0;
     int ctas = 0;
-    if (b2k_occupancy(W * B2K_G, cta, &ctas) != 0) {
+    if (b2k_occupancy(W * B2K_G * tw, cta, &ctas) != 0) {
       ctas = (int)(kSmPerSM / (cta + kCtaReserve));
       ctas = std::min(ctas, reg_envs / W);
     }
@@ -511,7 +517,7 @@ static int make_layout(Handle* h) {
     static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
                                    "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",
                                    "SUBTREE_ANGMOM", "BODYVEL", "RK_X0", "RK_XF", "RK_F", "RK_DX", "SCRATCH", "QW", "QHW",
-                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S"};
+                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JCOLS"};
     fprintf(stderr, "[b2mj layout] record %d doubles; shared arena %d doubles + %d ints per env\n", d.rec_end, d.arena_s_doubles,
             d.arena_s_ints);
     for (int f = 0; f < B2MJ_NFIELD; f++)
@@ -529,7 +535,7 @@ static int make_layout(Handle* h) {
     return B2MJ_EUNSUPPORTED;
   }
   h->warps_per_cta = bestW;
-  h->smem_bytes = (size_t)bestW * (env_bytes + 16);
+  h->smem_bytes = (size_t)bestW * (env_bytes + (d.team_warps > 1 ? 64 : 16));
   // Rollout shape: half of an SM's resident envs per CTA, stages lock-stepped with a CTA barrier.  Warps that
   // run the same stage together share instruction fetches -- the fused rollout is fetch bound (ncu: 12.7
   // no-instruction stall cycles per issue when the warps drift apart).  Measured on C2 at 4096 envs (CTA width x
@@ -537,7 +543,8 @@ static int make_layout(Handle* h) {
   h->rollout_warps_per_cta = 0;
   {
     const int Wr = bestEnv / 2;
-    if (Wr > bestW && Wr * B2K_G <= B2K_MAX_THREADS && resident(Wr) >= bestEnv) h->rollout_warps_per_cta = Wr;
+    if (d.team_warps == 1 && Wr > bestW && Wr * B2K_G <= B2K_MAX_THREADS && resident(Wr) >= bestEnv)
+      h->rollout_warps_per_cta = Wr;
   }
   if (const char* env = getenv("B2MJ_ROLLOUT_WARPS_PER_CTA")) h->rollout_warps_per_cta = atoi(env);
   h->arena_in_smem = 1;
@@ -778,7 +785,7 @@ int b2mj_rollout(b2mj_handle* hh, int nsteps, const double* dev_ctrl, double* de
   {
     int per_sm = 0, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    if (b2k_occupancy(h->warps_per_cta * B2K_G, h->smem_bytes, &per_sm) == 0 && per_sm > 0) {
+    if (h->dm.team_warps == 1 && b2k_occupancy(h->warps_per_cta * B2K_G, h->smem_bytes, &per_sm) == 0 && per_sm > 0) {
       const double slots = (double)per_sm * h->warps_per_cta * sms;
       const double waves = h->nenv / slots;
       const double idle = std::ceil(waves) - waves;  // empty fraction of the last wave

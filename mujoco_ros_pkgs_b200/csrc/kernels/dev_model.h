@@ -55,6 +55,7 @@ enum XField {
   XF_HINV,          // nv*nv  dense inv(qM + h diag(damping))
   XF_PRIMAL,        // 8*nv  Newton / CG work vectors (Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
   XF_EFC_AR_S,      // shared-memory home of AR when nefc*nefc fits (the common case)
+  XF_JCOLS,         // team mode: per constraint row {nnz, columns} bytes (team.cuh), njmax * 17 bytes
   XF_COUNT
 };
 
@@ -107,6 +108,8 @@ struct DevModel {
   int need_subtreevel;
   int any_damping;         // Euler implicit damping active
   int dense_small;         // nv <= 16: inertia handled as dense nv x nv matrices (explicit inverses, no index tables)
+  int team_warps;          // warps per env: 1, or 8 for wide Newton models (team.cuh): one env per CTA, helpers on call
+  int ldh;                 // leading dimension of the Newton Hessian (odd in team mode: conflict-free column walks)
 };
 
 struct LaunchArgs {

@@ -15,6 +15,7 @@
 #include "env_ctx.cuh"
 #include "stages_constraint.cuh"
 #include "stages_smooth.cuh"
+#include "team.cuh"
 
 namespace b2k {
 
@@ -554,6 +555,7 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
 // ------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void mulJacVec_warp(const Env e, int nefc, double* res, const double* vec) {
+  if (c_dm.team_warps > 1) { mulJacVec_sparse(e, nefc, res, vec); return; }  // column lists of this pass (TEAM_JCOLS)
   const int nv = c_dm.nv;
   const double* J = e.DG(B2MJ_F_EFC_J);
   FORL(i, nefc) {
@@ -603,7 +605,7 @@ __device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* inv
 
 // x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+G, k+2G, ...
 #define B2K_CHOL_SLOTS (128 / B2K_G)
-__device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n) {
+__device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n, int ld) {
   double t[B2K_CHOL_SLOTS];
 #pragma unroll
   for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + B2K_G * s; t[s] = k < n ? b[k] : 0.0; }
@@ -616,7 +618,7 @@ __device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double
     for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
       const int k = e.lane + B2K_G * s;
       if (k == i) t[s] = yi;
-      else if (k > i && k < n) t[s] -= L[k * n + i] * yi;
+      else if (k > i && k < n) t[s] -= L[k * ld + i] * yi;
     }
   }
   for (int i = n - 1; i >= 0; i--) {  // L' x = y
@@ -628,7 +630,7 @@ __device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double
     for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
       const int k = e.lane + B2K_G * s;
       if (k == i) t[s] = xi;
-      else if (k < i) t[s] -= L[i * n + k] * xi;
+      else if (k < i) t[s] -= L[i * ld + k] * xi;
     }
   }
 #pragma unroll
@@ -655,7 +657,8 @@ __device__ __noinline__ void primalUpdate(const Env e, PrimalCtx& c, int* change
   const double* qs = e.D(B2MJ_F_QFRC_SMOOTH);
   c.cost = constraintUpdate_warp(e, c.nefc, c.ncon, c.Jaref, c.newton && c.cone, changed);
   EfcPtrs P = efcPtrs(e);
-  mulJacTVec_warp(e, c.nefc, e.D(B2MJ_F_QFRC_CONSTRAINT), P.force);
+  if (c_dm.team_warps > 1) mulJacTVec_sparse(e, c.nefc, e.D(B2MJ_F_QFRC_CONSTRAINT), P.force);
+  else mulJacTVec_warp(e, c.nefc, e.D(B2MJ_F_QFRC_CONSTRAINT), P.force);
   double g = 0;
   FORL(i, c.nv) g += (c.Ma[i] - qs[i]) * (qacc[i] - qas[i]);
   c.gauss = 0.5 * warpSum(e.mask, g);
@@ -665,6 +668,10 @@ __device__ __noinline__ void primalUpdate(const Env e, PrimalCtx& c, int* change
 // H = M + J' diag(D_active) J (+ cone blocks), then Cholesky
 __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
   const DevModel& m = c_dm;
+  if (m.team_warps > 1) {  // wide models: the whole team builds and factorises H in shared memory (team.cuh)
+    team_call(e, TEAM_HESSIAN_CHOL, c.nefc, c.cone ? 1 : 0);
+    return;
+  }
   const int nv = c.nv, nefc = c.nefc;
   EfcPtrs P = efcPtrs(e);
   const double* qM = e.D(B2MJ_F_QM);
@@ -764,7 +771,7 @@ __device__ void primalGradient(const Env e, PrimalCtx& c) {
   FORL(i, c.nv) c.grad[i] = c.Ma[i] - qs[i] - qc[i];
   WSYNC();
   if (c.newton) {
-    cholSolve_warp(e, c.Mgrad, c.H, c.invd, c.grad, c.nv);
+    cholSolve_warp(e, c.Mgrad, c.H, c.invd, c.grad, c.nv, c_dm.ldh);
   } else {
     solveM_warp(e, c.Mgrad, c.grad);
   }
@@ -1057,6 +1064,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
     WSYNC();
   } else {
     const bool newton = m.opt.solver == B2MJ_SOL_NEWTON;
+    if (m.team_warps > 1) team_call(e, TEAM_JCOLS, nefc, 0);  // column lists of J for this forward pass
     if (warmstart) {
       // cost at the warm start vs at the unconstrained acceleration
       double* jar = e.XG(XF_EFC_JAREF);

@@ -177,16 +177,20 @@ __device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env
 __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel(const LaunchArgs a) {
   const DevModel& m = c_dm;
   unsigned char* const smem_raw = b2k_smem;
-  // "warp" below = env group of B2K_G lanes (a half-warp when B2K_G == 16)
-  const int warp = threadIdx.x / B2K_G, lane = threadIdx.x % B2K_G, nwarp = blockDim.x / B2K_G;
-  const unsigned gmask = B2K_G == 32 ? 0xffffffffu : (((1u << B2K_G) - 1u) << (threadIdx.x & 31 & ~(B2K_G - 1)));
+  // "warp" below = env slot of the CTA.  Normally one warp per env; in team mode (team.cuh) team_warps warps share a
+  // slot: warp 0 of the team runs the step, the others serve team calls.
+  const int tw = m.team_warps;
+  const int warp = (threadIdx.x / B2K_G) / tw, lane = threadIdx.x % B2K_G, nwarp = (blockDim.x / B2K_G) / tw;
+  const bool team_helper = ((threadIdx.x / B2K_G) % tw) != 0;
+  const unsigned gmask = 0xffffffffu;
 
-  // shared layout: [nwarp mbarriers, 16B each][nwarp env blocks: doubles | ints]
+  // shared layout: [nwarp slot headers (mbarrier; + team control block in team mode)][nwarp env blocks: doubles | ints]
   const size_t env_bytes = (((size_t)m.arena_s_doubles * 8 + (size_t)m.arena_s_ints * 4) + 15) & ~(size_t)15;
-  unsigned char* base = smem_raw + 16 * nwarp + (size_t)warp * env_bytes;
+  const int hdr = tw > 1 ? B2K_TEAM_HDR : 16;
+  unsigned char* base = smem_raw + hdr * nwarp + (size_t)warp * env_bytes;
   double* sd = reinterpret_cast<double*>(base);
   int* si = reinterpret_cast<int*>(base + (size_t)m.arena_s_doubles * 8);
-  const unsigned bar = smem_u32(smem_raw + 16 * warp);
+  const unsigned bar = smem_u32(smem_raw + hdr * warp);
   unsigned parity = 0;
   bool bar_ready = false;
   const int nchunks = a.sched ? (a.nsteps + a.chunk - 1) / a.chunk : 1;
@@ -220,6 +224,10 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
     Env e{(unsigned)(base - smem_raw), (unsigned)(base - smem_raw) + 8u * (unsigned)m.arena_s_doubles, gd, gi, lane,
           gmask, (a.dump != 0 || a.mode == MODE_STEP_BEGIN || a.mode == MODE_STEP_END) ? 1 : 0};
+    if (team_helper) {  // team mode: this warp only serves the main warp's team calls for this env
+      team_worker(e);
+      return;
+    }
     int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
     double* rec = a.rec + (size_t)env * m.rec_pitch;
 
@@ -366,6 +374,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     }
     WSYNC();
     PROF_MARK(PROF_STORE)
+    if (tw > 1) team_release(e);  // retire the helpers of this env slot
     if (!a.sched) break;
   }
 }
@@ -414,11 +423,12 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
   if (a->sched) {
     // persistent grid: exactly the CTAs that are co-resident (spinning on a ticket needs its producer running)
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2k_step_kernel, warps_per_cta * B2K_G, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b2k_step_kernel, warps_per_cta * B2K_G * m->team_warps, smem_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
     ctas = std::max(1, std::min(ctas, per_sm * sms));
   }
-  b2k_step_kernel<<<ctas, warps_per_cta * B2K_G, smem_bytes, stream>>>(*a);
+  // warps_per_cta counts env slots; in team mode every slot is team_warps warps wide
+  b2k_step_kernel<<<ctas, warps_per_cta * B2K_G * m->team_warps, smem_bytes, stream>>>(*a);
   return (int)cudaGetLastError();
 }
 

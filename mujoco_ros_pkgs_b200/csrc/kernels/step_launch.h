@@ -8,6 +8,8 @@
 #define B2K_MAX_THREADS 512 /* widest CTA: the lock-stepped rollout shape (half of an SM's resident envs per CTA) */
 #define B2K_MIN_CTAS 1      /* 512 threads x 128 registers = the whole register file */
 #define B2K_NEWTON_MAX_NV 128 /* Newton / CG: cholSolve_warp keeps x in B2K_CHOL_SLOTS = 128 / 32 registers per lane */
+#define B2K_TEAM_MIN_NV 64   /* Newton models at least this wide run in team mode (kernels/team.cuh) */
+#define B2K_TEAM_WARPS 8     /* warps per env in team mode */
 #define B2K_STEP_THREADS 128 /* widest CTA of a per-step launch (small CTAs free their slots as envs finish) */
 
 extern "C" {

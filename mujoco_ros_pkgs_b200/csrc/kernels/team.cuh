@@ -1,0 +1,243 @@
+// team.cuh — several warps working on ONE env for the stages that dominate wide models.
+//
+// The step kernel gives every env one warp.  That is the right grain for the Panda (nv = 9), but the collision-heavy
+// BASELINE config C5 (20 free boxes, nv = 120, Newton, elliptic cones, ~230 constraint rows) spent 94 % of its step in
+// the Newton solve: a dense 120 x 120 Hessian built and factorised three to four times per step by 32 lanes out of an L2
+// resident matrix (2.9 M cycles per factorisation, profiles/r2_*).  With 512 envs per GPU there are only 3.5 envs per SM,
+// so the SM's other schedulers idle.  For such models (DevModel::team_warps > 1) a CTA carries ONE env and team_warps
+// warps: warp 0 runs the step as before, the others park on a named barrier and are called in -- a command word in
+// shared memory, two barrier crossings -- for the team stages:
+//   TEAM_JCOLS         compact non-zero column lists of the constraint Jacobian rows (a contact row of C5 touches the
+//                      12 dofs of two free bodies, not 120 columns)
+//   TEAM_HESSIAN_CHOL  H = M + J' D J (+ elliptic cone blocks) accumulated row-sparse with every H row owned by one warp
+//                      (deterministic: each entry adds its constraint rows in increasing order), then a right-looking
+//                      Cholesky with the trailing update spread over all threads; H lives in shared memory with an odd
+//                      leading dimension so column walks are bank-conflict free
+// Reference semantics: mj_solNewton's Hessian / factor (the test oracle restates it); same matrix, different
+// summation order in the factorisation (right-looking), within the solver's own tolerance.
+#pragma once
+#include "env_ctx.cuh"
+#include "stages_constraint.cuh"
+
+namespace b2k {
+
+#define B2K_JCOLS_K 16                       /* stored non-zero columns per Jacobian row; 255 in nnz = "dense row" */
+#define B2K_JCOLS_STRIDE (B2K_JCOLS_K + 1)   /* bytes per row: nnz, then the columns */
+#define B2K_TEAM_HDR 64                      /* bytes of per-env-slot header in team mode: mbarrier + control block */
+
+enum { TEAM_EXIT = 0, TEAM_JCOLS = 1, TEAM_HESSIAN_CHOL = 2 };
+
+struct TeamCtl {
+  int cmd, nefc, ncon, newton_cone;
+};
+
+__device__ __forceinline__ int team_T() { return c_dm.team_warps * 32; }
+__device__ __forceinline__ int team_tid() { return (int)threadIdx.x % (c_dm.team_warps * 32); }
+// team mode runs ONE env slot per CTA (make_layout enforces it), so the slot is 0 and the team barrier is a fixed id:
+// a run-time id would make ptxas reserve all 16 named barriers for every CTA of every model
+__device__ __forceinline__ int team_slot() { return 0; }
+__device__ __forceinline__ void team_bar() { asm volatile("bar.sync 2, %0;" ::"r"(team_T()) : "memory"); }
+__device__ __forceinline__ TeamCtl* team_ctl() {
+  return reinterpret_cast<TeamCtl*>(b2k_smem + (size_t)team_slot() * B2K_TEAM_HDR + 16);
+}
+__device__ __forceinline__ unsigned char* team_jcols(const Env e) { return reinterpret_cast<unsigned char*>(e.X(XF_JCOLS)); }
+
+// ---- TEAM_JCOLS: per constraint row the sorted list of columns where the row (or, for a row of an elliptic contact,
+// any row of that contact) is non-zero.  One warp per row, ballot compaction over 32-column chunks.
+__device__ void team_build_jcols(const Env e, int nefc) {
+  const DevModel& m = c_dm;
+  const int nv = m.nv, w = team_tid() >> 5, lane = team_tid() & 31, TW = m.team_warps;
+  const double* J = e.DG(B2MJ_F_EFC_J);
+  const int* type = e.IG(B2MJ_F_EFC_TYPE);
+  const int* id = e.IG(B2MJ_F_EFC_ID);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+  const int* c_adr = e.IG(B2MJ_F_CONTACT_EFC_ADDRESS);
+  unsigned char* jc = team_jcols(e);
+  for (int r = w; r < nefc; r += TW) {
+    int r0 = r, dim = 1;
+    if (type[r] == B2MJ_CNSTR_CONTACT_ELLIPTIC) { r0 = c_adr[id[r]]; dim = c_dim[id[r]]; }
+    unsigned char* row = jc + (size_t)r * B2K_JCOLS_STRIDE;
+    int nnz = 0;
+    for (int k0 = 0; k0 < nv; k0 += 32) {
+      const int k = k0 + lane;
+      bool nz = false;
+      if (k < nv)
+        for (int a = 0; a < dim; a++) nz |= J[(size_t)(r0 + a) * nv + k] != 0;
+      const unsigned b = __ballot_sync(0xffffffffu, nz);
+      const int pos = nnz + __popc(b & ((1u << lane) - 1u));
+      if (nz && pos < B2K_JCOLS_K) row[1 + pos] = (unsigned char)k;
+      nnz += __popc(b);
+    }
+    if (lane == 0) row[0] = (unsigned char)(nnz > B2K_JCOLS_K ? 255 : nnz);
+  }
+}
+
+// ---- TEAM_HESSIAN_CHOL
+__device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
+  const DevModel& m = c_dm;
+  const int nv = m.nv, ld = m.ldh, T = team_T(), tid = team_tid(), w = tid >> 5, lane = tid & 31, TW = m.team_warps;
+  double* H = e.XG(XF_NEWTON_H);
+  double* invd = e.X(XF_PRIMAL) + 7 * nv;
+  const double* qM = e.D(B2MJ_F_QM);
+  EfcPtrs P = efcPtrs(e);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+  const double* cH = cone ? e.XG(XF_CONTACT_H) : nullptr;
+  const unsigned char* jc = team_jcols(e);
+  // H = M (lower triangle; everything else zero)
+  for (int k = tid; k < nv * ld; k += T) H[k] = 0;
+  team_bar();
+  for (int t = tid; t < m.nM; t += T) H[m.M_row[t] * ld + m.M_col[t]] = qM[t];
+  team_bar();
+  // H += J' D J: warp w owns the H rows i with i % TW == w and visits the constraint rows in order
+  for (int r = 0; r < nefc; r++) {
+    const int st = P.state[r];
+    int dim = 1;
+    if (st == B2MJ_CSTATE_CONE) dim = c_dim[P.id[r]];
+    else if (st != B2MJ_CSTATE_QUADRATIC) continue;
+    const unsigned char* row = jc + (size_t)r * B2K_JCOLS_STRIDE;
+    const int nnz = row[0];
+    const double* Jr = P.J + (size_t)r * nv;
+    if (nnz != 255) {
+      // sparse row / block: lane b holds column cols[b]
+      const int myc = lane < nnz ? row[1 + lane] : -1;
+      unsigned mine = __ballot_sync(0xffffffffu, myc >= 0 && (myc % TW) == w);
+      while (mine) {
+        const int a = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const int i = __shfl_sync(0xffffffffu, myc, a);
+        if (myc >= 0 && myc <= i) {
+          double s = H[i * ld + myc];
+          if (st == B2MJ_CSTATE_QUADRATIC) {
+            s += P.D[r] * Jr[i] * Jr[myc];
+          } else {
+            const double* Hc = cH + 36 * P.id[r];
+            for (int p = 0; p < dim; p++) {
+              const double Ja = Jr[p * nv + i];
+              if (Ja == 0) continue;
+              double u = 0;
+              for (int q = 0; q < dim; q++) u += Hc[p * dim + q] * Jr[q * nv + myc];
+              s += Ja * u;
+            }
+          }
+          H[i * ld + myc] = s;
+        }
+      }
+    } else {
+      // dense row / block: every owned H row i, lanes over the columns j <= i
+      for (int i = w; i < nv; i += TW) {
+        bool any = false;
+        for (int p = 0; p < dim; p++) any |= Jr[p * nv + i] != 0;
+        if (!any) continue;
+        for (int j = lane; j <= i; j += 32) {
+          double s = H[i * ld + j];
+          if (st == B2MJ_CSTATE_QUADRATIC) {
+            s += P.D[r] * Jr[i] * Jr[j];
+          } else {
+            const double* Hc = cH + 36 * P.id[r];
+            for (int p = 0; p < dim; p++) {
+              const double Ja = Jr[p * nv + i];
+              if (Ja == 0) continue;
+              double u = 0;
+              for (int q = 0; q < dim; q++) u += Hc[p * dim + q] * Jr[q * nv + j];
+              s += Ja * u;
+            }
+          }
+          H[i * ld + j] = s;
+        }
+      }
+    }
+    r += dim - 1;
+  }
+  team_bar();
+  // right-looking Cholesky, lower triangle in place; invd[j] = 1 / L[j][j]
+  for (int j = 0; j < nv; j++) {
+    double s = H[j * ld + j];
+    if (s < B2K_MINVAL) s = B2K_MINVAL;
+    const double ljj = sqrt(s), inv = 1 / ljj;
+    for (int i = j + 1 + tid; i < nv; i += T) H[i * ld + j] *= inv;
+    team_bar();
+    if (tid == 0) { H[j * ld + j] = ljj; invd[j] = inv; }
+    // trailing update: one warp per row i, lanes over the columns j < k <= i
+    for (int i = j + 1 + w; i < nv; i += TW) {
+      const double lij = H[i * ld + j];
+      if (lij == 0) continue;  // block structure: most of a contact-sparse factor is exact zeros
+      for (int k = j + 1 + lane; k <= i; k += 32) H[i * ld + k] -= lij * H[k * ld + j];
+    }
+    team_bar();
+  }
+}
+
+__device__ __noinline__ void team_exec(const Env e, int cmd, int nefc, int cone) {
+  if (cmd == TEAM_JCOLS) team_build_jcols(e, nefc);
+  else if (cmd == TEAM_HESSIAN_CHOL) team_hessian_chol(e, nefc, cone != 0);
+}
+
+// called by the env's main warp (warp 0 of the team)
+__device__ __noinline__ void team_call(const Env e, int cmd, int nefc, int cone) {
+  TeamCtl* c = team_ctl();
+  if (e.lane == 0) { c->cmd = cmd; c->nefc = nefc; c->newton_cone = cone; }
+  __syncwarp();
+  team_bar();  // the helpers wait here
+  team_exec(e, cmd, nefc, cone);
+  team_bar();
+}
+
+// helper warps: serve team calls until the main warp retires the env slot
+__device__ void team_worker(const Env e) {
+  TeamCtl* c = team_ctl();
+  for (;;) {
+    team_bar();
+    const int cmd = c->cmd;
+    if (cmd == TEAM_EXIT) return;
+    team_exec(e, cmd, c->nefc, c->newton_cone);
+    team_bar();
+  }
+}
+__device__ __forceinline__ void team_release(const Env e) {
+  TeamCtl* c = team_ctl();
+  if (e.lane == 0) c->cmd = TEAM_EXIT;
+  __syncwarp();
+  team_bar();
+}
+
+// ---- sparse Jacobian products for the main warp, on the column lists (res identical to the dense loops up to the
+// order in which exact zeros are skipped)
+__device__ __forceinline__ void mulJacVec_sparse(const Env e, int nefc, double* res, const double* vec) {
+  const int nv = c_dm.nv;
+  const double* J = e.DG(B2MJ_F_EFC_J);
+  const unsigned char* jc = team_jcols(e);
+  FORL(i, nefc) {
+    const unsigned char* row = jc + (size_t)i * B2K_JCOLS_STRIDE;
+    const double* Ji = J + (size_t)i * nv;
+    double s = 0;
+    if (row[0] != 255) {
+      for (int a = 0; a < row[0]; a++) { const int k = row[1 + a]; s += Ji[k] * vec[k]; }
+    } else {
+      for (int k = 0; k < nv; k++) s += Ji[k] * vec[k];
+    }
+    res[i] = s;
+  }
+  WSYNC();
+}
+__device__ __forceinline__ void mulJacTVec_sparse(const Env e, int nefc, double* res, const double* f) {
+  const int nv = c_dm.nv;
+  const double* J = e.DG(B2MJ_F_EFC_J);
+  const unsigned char* jc = team_jcols(e);
+  FORL(k, nv) res[k] = 0;
+  WSYNC();
+  // rows in order; within a row the columns are distinct, so the lanes never collide
+  for (int i = 0; i < nefc; i++) {
+    const double fi = f[i];
+    if (fi == 0) continue;
+    const unsigned char* row = jc + (size_t)i * B2K_JCOLS_STRIDE;
+    const double* Ji = J + (size_t)i * nv;
+    if (row[0] != 255) {
+      if (e.lane < row[0]) { const int k = row[1 + e.lane]; res[k] += Ji[k] * fi; }
+    } else {
+      FORL(k, nv) res[k] += Ji[k] * fi;
+    }
+    WSYNC();
+  }
+}
+
+}  // namespace b2k
