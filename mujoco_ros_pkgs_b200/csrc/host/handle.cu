@@ -303,6 +303,7 @@ static int make_layout(Handle* h) {
   xs[XF_EFC_QUAD] = pgs ? 0 : 3 * m->njmax;
   // team mode (kernels/team.cuh): wide Newton models get one env per CTA and 8 warps; H then has an odd leading dimension
   d.team_warps = (newton && nv >= B2K_TEAM_MIN_NV && !getenv("B2MJ_NO_TEAM")) ? B2K_TEAM_WARPS : 1;
+  if (d.team_warps > 1 && getenv("B2MJ_TEAM_WARPS")) d.team_warps = std::max(2, std::min(16, atoi(getenv("B2MJ_TEAM_WARPS"))));
   d.ldh = d.team_warps > 1 ? (nv | 1) : nv;
   xs[XF_NEWTON_H] = newton ? nv * d.ldh : 0;
   xs[XF_JCOLS] = d.team_warps > 1 ? (m->njmax * 17 + 7) / 8 : 0;

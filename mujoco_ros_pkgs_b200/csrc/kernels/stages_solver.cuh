@@ -15,6 +15,7 @@
 #include "env_ctx.cuh"
 #include "stages_constraint.cuh"
 #include "stages_smooth.cuh"
+#include "step_launch.h"
 #include "team.cuh"
 
 namespace b2k {
@@ -576,7 +577,16 @@ __device__ __forceinline__ double dot_warp(const Env e, const double* a, const d
 // Per column: the diagonal's dot product is split over the lanes (one butterfly sum instead of a j-long dependent
 // chain executed redundantly by every lane), and each lane's row update runs four independent accumulators so the
 // FMA chain does not wait on itself (the factorisation was 98% of a C5 step: nv 120, refactored every iteration).
-__device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* invd, int n, double mindiag) {
+// SM: the Hessian is in the shared arena -- its address is then formed from the shared symbol (LDS / STS, ~29 cycles);
+// through the generic pointer of a possibly demoted field every access is a generic load (~100 cycles in situ), and
+// the dependent chains of the factorisation / substitution multiply that.
+template <bool SM>
+__device__ __forceinline__ double* newtonH(const Env e) { return SM ? e.X(XF_NEWTON_H) : e.XG(XF_NEWTON_H); }
+
+template <bool SM>
+__device__ __noinline__ void cholFactor_warp(const Env e, int n, double mindiag) {
+  double* A = newtonH<SM>(e);
+  double* invd = e.X(XF_PRIMAL) + 7 * n;
   B2K_NOUNROLL for (int j = 0; j < n; j++) {
     const double* Aj = A + j * n;
     double p = 0;
@@ -603,40 +613,72 @@ __device__ __noinline__ void cholFactor_warp(const Env e, double* A, double* inv
   WSYNC();
 }
 
-// x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+G, k+2G, ...
-#define B2K_CHOL_SLOTS (128 / B2K_G)
-__device__ __noinline__ void cholSolve_warp(const Env e, double* x, const double* L, const double* invd, const double* b, int n, int ld) {
+// x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+32, k+64, k+96 (n <= 128).
+// Written block-wise -- the outer loop over the 32-entry blocks is unrolled so that every register slot is named
+// statically; the round-1 form indexed the slots through run-time predicates, which put the vector in LOCAL memory
+// with eight branches per step (800 cycles per substitution step, 194 k cycles per solve at nv = 120, ~38 k at nv = 24).
+#define B2K_CHOL_SLOTS (B2K_NEWTON_MAX_NV / 32)
+template <bool SM>
+__device__ __noinline__ void cholSolve_warp(const Env e, int n, int ld) {
+  // Mgrad = inv(H) grad on the solver's work vectors (XF_PRIMAL: Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
+  const double* L = newtonH<SM>(e);
+  double* wv = e.X(XF_PRIMAL);
+  const double* b = wv + 2 * n;
+  double* x = wv + 3 * n;
+  const double* invd = wv + 7 * n;
   double t[B2K_CHOL_SLOTS];
+  const int lane = e.lane;
 #pragma unroll
-  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + B2K_G * s; t[s] = k < n ? b[k] : 0.0; }
-  B2K_NOUNROLL for (int i = 0; i < n; i++) {  // L y = b
-    double ti = 0;
+  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = lane + 32 * s; t[s] = k < n ? b[k] : 0.0; }
+  // L y = b
 #pragma unroll
-    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i / B2K_G) == s) ti = __shfl_sync(e.mask, t[s], i % B2K_G, B2K_G);
-    const double yi = ti * invd[i];
+  for (int bi = 0; bi < B2K_CHOL_SLOTS; bi++) {
+    const int i0 = 32 * bi;
+    if (i0 < n) {
+      const int cnt = min(32, n - i0);
+      B2K_NOUNROLL for (int ii = 0; ii < cnt; ii++) {
+        const int i = i0 + ii;
+        const double yi = __shfl_sync(e.mask, t[bi], ii) * invd[i];
+        if (lane == ii) t[bi] = yi;
+        else if (lane > ii && lane + i0 < n) t[bi] -= L[(lane + i0) * ld + i] * yi;
 #pragma unroll
-    for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
-      const int k = e.lane + B2K_G * s;
-      if (k == i) t[s] = yi;
-      else if (k > i && k < n) t[s] -= L[k * ld + i] * yi;
+        for (int s = bi + 1; s < B2K_CHOL_SLOTS; s++) {
+          const int k = lane + 32 * s;
+          if (k < n) t[s] -= L[k * ld + i] * yi;
+        }
+      }
     }
   }
-  for (int i = n - 1; i >= 0; i--) {  // L' x = y
-    double ti = 0;
+  // L' x = y
 #pragma unroll
-    for (int s = 0; s < B2K_CHOL_SLOTS; s++) if ((i / B2K_G) == s) ti = __shfl_sync(e.mask, t[s], i % B2K_G, B2K_G);
-    const double xi = ti * invd[i];
+  for (int bi = B2K_CHOL_SLOTS - 1; bi >= 0; bi--) {
+    const int i0 = 32 * bi;
+    if (i0 < n) {
+      const int cnt = min(32, n - i0);
+      B2K_NOUNROLL for (int ii = cnt - 1; ii >= 0; ii--) {
+        const int i = i0 + ii;
+        const double xi = __shfl_sync(e.mask, t[bi], ii) * invd[i];
+        const double* Li = L + i * ld;
+        if (lane == ii) t[bi] = xi;
+        else if (lane < ii) t[bi] -= Li[lane + i0] * xi;
 #pragma unroll
-    for (int s = 0; s < B2K_CHOL_SLOTS; s++) {
-      const int k = e.lane + B2K_G * s;
-      if (k == i) t[s] = xi;
-      else if (k < i) t[s] -= L[i * ld + k] * xi;
+        for (int s = 0; s < bi; s++) t[s] -= Li[lane + 32 * s] * xi;
+      }
     }
   }
 #pragma unroll
-  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = e.lane + B2K_G * s; if (k < n) x[k] = t[s]; }
+  for (int s = 0; s < B2K_CHOL_SLOTS; s++) { const int k = lane + 32 * s; if (k < n) x[k] = t[s]; }
   WSYNC();
 }
+
+// developer build (-DB2K_SOLVE_PROF): cycle split of the primal solver, read with b2k_sprof_read (tools/solve_profile.py)
+#ifdef B2K_SOLVE_PROF  /* g_sprof lives in team.cuh */
+#define SPROF_DECL long long _sp_t = clock64();
+#define SPROF(id) { const long long _n = clock64(); if (e.lane == 0) atomicAdd(&g_sprof[id], (unsigned long long)(_n - _sp_t)); _sp_t = _n; }
+#else
+#define SPROF_DECL
+#define SPROF(id)
+#endif
 
 struct PrimalCtx {
   int nv, nefc, ncon;
@@ -666,7 +708,8 @@ __device__ __noinline__ void primalUpdate(const Env e, PrimalCtx& c, int* change
 }
 
 // H = M + J' diag(D_active) J (+ cone blocks), then Cholesky
-__device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
+template <bool SM>
+__device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
   const DevModel& m = c_dm;
   if (m.team_warps > 1) {  // wide models: the whole team builds and factorises H in shared memory (team.cuh)
     team_call(e, TEAM_HESSIAN_CHOL, c.nefc, c.cone ? 1 : 0);
@@ -675,7 +718,7 @@ __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
   const int nv = c.nv, nefc = c.nefc;
   EfcPtrs P = efcPtrs(e);
   const double* qM = e.D(B2MJ_F_QM);
-  double* H = c.H;
+  double* H = newtonH<SM>(e);
   FORL(k, nv * nv) H[k] = 0;
   WSYNC();
   FORL(t, m.nM) {
@@ -733,7 +776,7 @@ __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
       WSYNC();
       r += dim - 1;
     }
-    cholFactor_warp(e, H, c.invd, nv, B2K_MINVAL);
+    cholFactor_warp<SM>(e, nv, B2K_MINVAL);
     return;
   }
 #endif
@@ -762,7 +805,11 @@ __device__ __noinline__ void primalHessian(const Env e, PrimalCtx& c) {
     H[item] = s;
   }
   WSYNC();
-  cholFactor_warp(e, H, c.invd, nv, B2K_MINVAL);
+  cholFactor_warp<SM>(e, nv, B2K_MINVAL);
+}
+__device__ __forceinline__ void primalHessian(const Env e, PrimalCtx& c) {
+  if (c_dm.xoff_s[XF_NEWTON_H] >= 0) primalHessianT<true>(e, c);
+  else primalHessianT<false>(e, c);
 }
 
 __device__ void primalGradient(const Env e, PrimalCtx& c) {
@@ -771,7 +818,8 @@ __device__ void primalGradient(const Env e, PrimalCtx& c) {
   FORL(i, c.nv) c.grad[i] = c.Ma[i] - qs[i] - qc[i];
   WSYNC();
   if (c.newton) {
-    cholSolve_warp(e, c.Mgrad, c.H, c.invd, c.grad, c.nv, c_dm.ldh);
+    if (c_dm.xoff_s[XF_NEWTON_H] >= 0) cholSolve_warp<true>(e, c.nv, c_dm.ldh);
+    else cholSolve_warp<false>(e, c.nv, c_dm.ldh);
   } else {
     solveM_warp(e, c.Mgrad, c.grad);
   }
@@ -926,18 +974,24 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
   c.scale = 1 / (m.meaninertia * max(1, nv));
   double* qacc = e.D(B2MJ_F_QACC);
 
+  SPROF_DECL
   mulM_warp(e, c.Ma, qacc);
   mulJacVec_warp(e, nefc, c.Jaref, qacc);
   FORL(i, nefc) c.Jaref[i] -= P.aref[i];
   WSYNC();
+  SPROF(0)
   primalUpdate(e, c, nullptr);
+  SPROF(1)
   if (newton) primalHessian(e, c);
+  SPROF(2)
   primalGradient(e, c);
+  SPROF(3)
   FORL(i, nv) c.search[i] = -c.Mgrad[i];
   WSYNC();
   int iter = 0;
   while (iter < m.opt.iterations) {
     const double alpha = primalSearch(e, c);
+    SPROF(4)
     if (alpha == 0) break;
     FORL(i, nv) { qacc[i] += alpha * c.search[i]; c.Ma[i] += alpha * c.Mv[i]; }
     FORL(i, nefc) c.Jaref[i] += alpha * c.Jv[i];
@@ -946,8 +1000,11 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
     WSYNC();
     int changed = 0;
     primalUpdate(e, c, &changed);
+    SPROF(1)
     if (newton && (c.cone || changed)) primalHessian(e, c);
+    SPROF(2)
     primalGradient(e, c);
+    SPROF(3)
     if (newton) {
       FORL(i, nv) c.search[i] = -c.Mgrad[i];
     } else {

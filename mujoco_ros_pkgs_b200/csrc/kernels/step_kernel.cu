@@ -486,6 +486,15 @@ extern "C" int b2k_launch_order(const int* stats, int nenv, int* perm, cudaStrea
   return (int)cudaGetLastError();
 }
 
+#ifdef B2K_SOLVE_PROF
+extern "C" int b2k_sprof_read(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16) cudaMemcpyFromSymbol(out16, b2k::g_sprof, 16 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(b2k::g_sprof, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 extern "C" int b2k_step_kernel_attrs(int* regs, int* static_smem, int* max_threads) {
   cudaFuncAttributes at;
   cudaError_t err = cudaFuncGetAttributes(&at, b2k_step_kernel);

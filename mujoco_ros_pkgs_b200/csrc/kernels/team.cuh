@@ -21,6 +21,15 @@
 
 namespace b2k {
 
+#ifdef B2K_SOLVE_PROF
+__device__ unsigned long long g_sprof[16];  // cycle split of the primal solver (developer build only)
+#define TPROF_DECL long long _tp = clock64();
+#define TPROF(id) { const long long _n = clock64(); if (team_tid() == 0) atomicAdd(&g_sprof[id], (unsigned long long)(_n - _tp)); _tp = _n; }
+#else
+#define TPROF_DECL
+#define TPROF(id)
+#endif
+
 #define B2K_JCOLS_K 16                       /* stored non-zero columns per Jacobian row; 255 in nnz = "dense row" */
 #define B2K_JCOLS_STRIDE (B2K_JCOLS_K + 1)   /* bytes per row: nnz, then the columns */
 #define B2K_TEAM_HDR 64                      /* bytes of per-env-slot header in team mode: mbarrier + control block */
@@ -76,18 +85,20 @@ __device__ void team_build_jcols(const Env e, int nefc) {
 __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
   const DevModel& m = c_dm;
   const int nv = m.nv, ld = m.ldh, T = team_T(), tid = team_tid(), w = tid >> 5, lane = tid & 31, TW = m.team_warps;
-  double* H = e.XG(XF_NEWTON_H);
+  double* H = e.X(XF_NEWTON_H);  // team mode: always in the shared arena (make_layout), addressed as shared memory
   double* invd = e.X(XF_PRIMAL) + 7 * nv;
   const double* qM = e.D(B2MJ_F_QM);
   EfcPtrs P = efcPtrs(e);
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* cH = cone ? e.XG(XF_CONTACT_H) : nullptr;
   const unsigned char* jc = team_jcols(e);
+  TPROF_DECL
   // H = M (lower triangle; everything else zero)
   for (int k = tid; k < nv * ld; k += T) H[k] = 0;
   team_bar();
   for (int t = tid; t < m.nM; t += T) H[m.M_row[t] * ld + m.M_col[t]] = qM[t];
   team_bar();
+  TPROF(5)
   // H += J' D J: warp w owns the H rows i with i % TW == w and visits the constraint rows in order
   for (int r = 0; r < nefc; r++) {
     const int st = P.state[r];
@@ -98,29 +109,45 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
     const int nnz = row[0];
     const double* Jr = P.J + (size_t)r * nv;
     if (nnz != 255) {
-      // sparse row / block: lane b holds column cols[b]
+      // sparse row / block: lane b holds column cols[b].  All operands of the block are fetched up front in ONE L2
+      // round trip (this lane's column of J for every row of the block, the cone block of the contact); the row
+      // values J[.][i] of an owned H row i then come from the lane that holds column i, by shuffle.  Fetching them
+      // inside the accumulation loop made the build a chain of dependent L2 gathers (465 k cycles per build).
       const int myc = lane < nnz ? row[1 + lane] : -1;
+      double jv[6], wv[6];
+#pragma unroll
+      for (int p = 0; p < 6; p++) jv[p] = (p < dim && myc >= 0) ? Jr[p * nv + myc] : 0.0;
+      if (st == B2MJ_CSTATE_CONE) {
+        const double* Hc = cH + 36 * P.id[r];
+#pragma unroll
+        for (int p = 0; p < 6; p++) {
+          double u = 0;
+          if (p < dim) {
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q < dim) u += Hc[p * dim + q] * jv[q];
+          }
+          wv[p] = u;
+        }
+      } else {
+        const double Dr = P.D[r];
+#pragma unroll
+        for (int p = 0; p < 6; p++) wv[p] = Dr;
+      }
       unsigned mine = __ballot_sync(0xffffffffu, myc >= 0 && (myc % TW) == w);
       while (mine) {
         const int a = __ffs(mine) - 1;
         mine &= mine - 1;
         const int i = __shfl_sync(0xffffffffu, myc, a);
-        if (myc >= 0 && myc <= i) {
-          double s = H[i * ld + myc];
-          if (st == B2MJ_CSTATE_QUADRATIC) {
-            s += P.D[r] * Jr[i] * Jr[myc];
-          } else {
-            const double* Hc = cH + 36 * P.id[r];
-            for (int p = 0; p < dim; p++) {
-              const double Ja = Jr[p * nv + i];
-              if (Ja == 0) continue;
-              double u = 0;
-              for (int q = 0; q < dim; q++) u += Hc[p * dim + q] * Jr[q * nv + myc];
-              s += Ja * u;
-            }
-          }
-          H[i * ld + myc] = s;
+        double acc = 0;
+        if (st == B2MJ_CSTATE_QUADRATIC) {
+          acc = (wv[0] * __shfl_sync(0xffffffffu, jv[0], a)) * jv[0];
+        } else {
+#pragma unroll
+          for (int p = 0; p < 6; p++)
+            if (p < dim) acc += __shfl_sync(0xffffffffu, jv[p], a) * wv[p];
         }
+        if (myc >= 0 && myc <= i) H[i * ld + myc] += acc;
       }
     } else {
       // dense row / block: every owned H row i, lanes over the columns j <= i
@@ -149,6 +176,7 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
     r += dim - 1;
   }
   team_bar();
+  TPROF(6)
   // right-looking Cholesky, lower triangle in place; invd[j] = 1 / L[j][j]
   for (int j = 0; j < nv; j++) {
     double s = H[j * ld + j];
@@ -165,6 +193,7 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
     }
     team_bar();
   }
+  TPROF(7)
 }
 
 __device__ __noinline__ void team_exec(const Env e, int cmd, int nefc, int cone) {
