@@ -338,6 +338,14 @@ int b2mj_device_ptr(b2mj_handle* h, b2mj_field f, void** dev_ptr, size_t* pitch_
  * callbacks.cpp:462-738: gravity, body_mass, geom_*, eq_*) */
 int b2mj_model_update(b2mj_handle* h, const b2mjModel* m);
 
+/* per-env model variants: domain randomisation, and the reference's mutating services applied to ONE env rather than
+ * to all (set_body_state mass / inertia, set_geom_properties friction / size / -> mj_setConst, set_gravity,
+ * set_equality_constraint_parameters: callbacks.cpp:210-370, 462-592, 641-738).  models[0..nmodels) are edited copies of
+ * the handle's model -- same sizes, topology, qpos0, solver / integrator / cone / timestep; parameters, gravity and the
+ * constants b2mj_model_set_const derives may differ -- and env_model[e] (HOST, nenv ints) picks the variant of env e.
+ * nmodels = 0 returns to the one shared model.  Stepping then uses the per-env-model build of the step kernel. */
+int b2mj_set_env_models(b2mj_handle* h, const b2mjModel* const* models, int nmodels, const int* env_model);
+
 /* batched plugin data paths (device kernels):
  *  robot_hw_write — DefaultRobotHWSim::writeSim (default_robot_hw_sim.cpp:248-326)
  *  sensor_readout — MujocoRosSensorsPlugin::lastStageCallback arithmetic (mujoco_sensor_handler_plugin.cpp:175-437) */

@@ -36,6 +36,7 @@ lib.b2mj_stage_name.argtypes = [C.c_int]
 lib.b2mj_stage_name.restype = C.c_char_p
 lib.b2mj_device_ptr.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t)]
 lib.b2mj_model_update.argtypes = [_vp, _vp]
+lib.b2mj_set_env_models.argtypes = [_vp, C.POINTER(_vp), C.c_int, _vp]
 lib.b2mj_launch_info.argtypes = [_vp, C.POINTER(_capi.B2mjLaunchInfo)]
 lib.b2mj_robot_hw_configure.argtypes = [_vp, C.POINTER(_capi.B2mjRobotHW)]
 lib.b2mj_robot_hw_write.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_double]
@@ -151,6 +152,16 @@ class BatchSim:
 
     def model_update(self, model: Model = None):
         check(lib.b2mj_model_update(self._h, (model or self.model).ptr), "model_update")
+
+    def set_env_models(self, models, env_model):
+        """Per-env model variants: models = list of Model (edited copies), env_model = [nenv] variant index."""
+        if not models:
+            check(lib.b2mj_set_env_models(self._h, None, 0, None), "set_env_models")
+            return
+        ptrs = (_vp * len(models))(*[m.ptr for m in models])
+        idx = np.ascontiguousarray(env_model, dtype=np.int32)
+        assert idx.size == self.nenv
+        check(lib.b2mj_set_env_models(self._h, ptrs, len(models), idx.ctypes.data), "set_env_models")
 
     def launch_info(self) -> dict:
         li = _capi.B2mjLaunchInfo()

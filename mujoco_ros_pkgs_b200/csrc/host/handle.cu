@@ -73,15 +73,42 @@ static int field_count(const b2mjModel* m, int f, int* is_int) {
   return b2mj_field_size(m, (b2mj_field)f, is_int);
 }
 
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// bytes of the per-variant region of a model blob: every B2MJ_MODEL_ARRAYS array + gravity[3] + {meaninertia}
+static size_t variant_region_bytes(const b2mjModel* m) {
+  size_t total = 0;
+#define X(t, n, r, c) total += al256(sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c) + 16);
+  B2MJ_MODEL_ARRAYS(X)
+#undef X
+  total += al256(3 * sizeof(double) + 16) + al256(sizeof(double) + 16);
+  return total;
+}
+// pack one model's arrays at host (same order / offsets for every variant) and point d's arrays at dev_base
+static void pack_variant(const b2mjModel* m, unsigned char* host, DevModel* d, unsigned char* dev_base) {
+  size_t off = 0;
+#define X(t, n, r, c)                                                               \
+  {                                                                                 \
+    size_t bytes = sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c);             \
+    if (bytes) std::memcpy(host + off, m->n, bytes);                                \
+    if (d) d->n = reinterpret_cast<const t*>(dev_base + off);                       \
+    off += al256(bytes + 16);                                                       \
+  }
+  B2MJ_MODEL_ARRAYS(X)
+#undef X
+  std::memcpy(host + off, m->opt.gravity, 3 * sizeof(double));
+  if (d) d->env_gravity = reinterpret_cast<const double*>(dev_base + off);
+  off += al256(3 * sizeof(double) + 16);
+  std::memcpy(host + off, &m->stat.meaninertia, sizeof(double));
+  if (d) d->env_scalars = reinterpret_cast<const double*>(dev_base + off);
+}
+
 // upload model arrays into one device blob and fill the DevModel pointers
 static int upload_model(Handle* h) {
   const b2mjModel* m = h->model;
   DevModel& d = h->dm;
-  size_t total = 0;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-#define X(t, n, r, c) total += al(sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c) + 16);
-  B2MJ_MODEL_ARRAYS(X)
-#undef X
+  size_t total = variant_region_bytes(m);
   // ---- derived topology tables (dof-chain masks, subtree masks, scan jump tables, sparse-M indices) ----
   const int nbody = m->nbody, nv = m->nv, nM = m->nM;
   d.nmaskword = std::max(1, (nv + 31) / 32);
@@ -178,16 +205,9 @@ static int upload_model(Handle* h) {
     h->model_blob_bytes = total;
   }
   std::vector<unsigned char> host(total, 0);
-  size_t off = 0;
-#define X(t, n, r, c)                                                               \
-  {                                                                                 \
-    size_t bytes = sizeof(t) * (size_t)std::max(m->r, 0) * (size_t)(c);             \
-    if (bytes) std::memcpy(host.data() + off, m->n, bytes);                         \
-    d.n = reinterpret_cast<const t*>((unsigned char*)h->model_blob + off);          \
-    off += al(bytes + 16);                                                          \
-  }
-  B2MJ_MODEL_ARRAYS(X)
-#undef X
+  pack_variant(m, host.data(), &d, (unsigned char*)h->model_blob);
+  d.env_model_stride = 0;
+  size_t off = variant_region_bytes(m);
   for (const Extra& x : extras) {
     if (x.bytes) std::memcpy(host.data() + off, x.src, x.bytes);
     *x.slot = (unsigned char*)h->model_blob + off;
@@ -634,7 +654,15 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
   const size_t smem = h->smem_bytes / h->warps_per_cta * W;
   static const bool reorder = !getenv("B2MJ_NO_REORDER");
   a.perm = (reorder && h->perm_valid && !a.sched) ? h->perm : nullptr;
-  const int rc = b2k_launch_step(&h->dm, &a, W, smem, h->stream);
+  a.env_model = nullptr;
+  int rc;
+  if (h->n_env_models > 0) {  // per-env model variants: the kernel build that reads every model array per env
+    a.env_model = h->env_model_idx;
+    h->dm_env.has_xfrc = h->dm.has_xfrc;
+    rc = b2k_em_launch_step(&h->dm_env, &a, W, smem, h->stream);
+  } else {
+    rc = b2k_launch_step(&h->dm, &a, W, smem, h->stream);
+  }
   if (rc != 0) {
     set_error(std::string("step kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return B2MJ_ECUDA;
@@ -714,6 +742,8 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->sched);
   cudaFree(h->perm);
   cudaFree(h->publish_slab);
+  cudaFree(h->env_blob);
+  cudaFree(h->env_model_idx);
   handle_free_plugins(h);
   b2mj_model_free(h->model);
   delete h;
@@ -1003,6 +1033,7 @@ int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
   if (int rc = check_supported(m)) return rc;
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->n_env_models) b2mj_set_env_models(hh, nullptr, 0, nullptr);  // a broadcast update replaces per-env variants
   b2mjModel* clone = model_clone(m);
   b2mj_model_free(h->model);
   h->model = clone;
@@ -1015,6 +1046,69 @@ int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
     return B2MJ_EINVAL;
   }
   return upload_init_templates(h);
+}
+
+int b2mj_set_env_models(b2mj_handle* hh, const b2mjModel* const* models, int nmodels, const int* env_model) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || nmodels < 0 || (nmodels > 0 && (!models || !env_model))) {
+    set_error("b2mj_set_env_models: bad argument");
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->env_blob);
+  cudaFree(h->env_model_idx);
+  h->env_blob = nullptr;
+  h->env_model_idx = nullptr;
+  h->n_env_models = 0;
+  if (nmodels == 0) return 0;
+  const b2mjModel* o = h->model;
+  for (int v = 0; v < nmodels; v++) {
+    const b2mjModel* m = models[v];
+    if (!m) { set_error("b2mj_set_env_models: null model"); return B2MJ_EINVAL; }
+#define X(n) if (m->n != o->n) { set_error("b2mj_set_env_models: variant " + std::to_string(v) + " differs in size field '" #n "'"); return B2MJ_EINVAL; }
+    B2MJ_MODEL_SIZES(X)
+#undef X
+    if (m->opt.solver != o->opt.solver || m->opt.integrator != o->opt.integrator || m->opt.cone != o->opt.cone ||
+        m->opt.timestep != o->opt.timestep || m->opt.disableflags != o->opt.disableflags) {
+      set_error("b2mj_set_env_models: variants must share solver / integrator / cone / timestep / flags");
+      return B2MJ_EINVAL;
+    }
+    if (int rc = check_supported(m)) return rc;
+    // topology (parents, addresses, types, pair table) and the reset pose are shared: only parameters may differ
+    const bool same_topology =
+        !std::memcmp(m->body_parentid, o->body_parentid, sizeof(int) * o->nbody) &&
+        !std::memcmp(m->jnt_type, o->jnt_type, sizeof(int) * o->njnt) && !std::memcmp(m->dof_parentid, o->dof_parentid, sizeof(int) * o->nv) &&
+        !std::memcmp(m->geom_type, o->geom_type, sizeof(int) * o->ngeom) && !std::memcmp(m->geom_bodyid, o->geom_bodyid, sizeof(int) * o->ngeom) &&
+        !std::memcmp(m->collpair_geom1, o->collpair_geom1, sizeof(int) * o->ncollpair) &&
+        !std::memcmp(m->collpair_geom2, o->collpair_geom2, sizeof(int) * o->ncollpair) &&
+        !std::memcmp(m->qpos0, o->qpos0, sizeof(double) * o->nq);
+    if (!same_topology) {
+      set_error("b2mj_set_env_models: variant " + std::to_string(v) + " changes topology or qpos0; only parameters may differ");
+      return B2MJ_EINVAL;
+    }
+    int damp = 0;
+    for (int i = 0; i < m->nv; i++) damp |= m->dof_damping[i] > 0;
+    (void)damp;  // XF_HINV is reserved whether or not a variant has damping (make_layout)
+  }
+  std::vector<int> idx(env_model, env_model + h->nenv);
+  for (int e = 0; e < h->nenv; e++)
+    if (idx[e] < 0 || idx[e] >= nmodels) { set_error("b2mj_set_env_models: env_model index out of range"); return B2MJ_EINVAL; }
+  const size_t stride = variant_region_bytes(o);
+  std::vector<unsigned char> host(stride * nmodels, 0);
+  CUDA_OK(cudaMalloc(&h->env_blob, host.size()));
+  h->dm_env = h->dm;
+  for (int v = 0; v < nmodels; v++)
+    pack_variant(models[v], host.data() + stride * v, v == 0 ? &h->dm_env : nullptr, (unsigned char*)h->env_blob);
+  h->dm_env.env_model_stride = (long long)stride;
+  h->dm_env.any_damping = 0;
+  for (int v = 0; v < nmodels; v++)
+    for (int i = 0; i < o->nv; i++) h->dm_env.any_damping |= models[v]->dof_damping[i] > 0;
+  CUDA_OK(cudaMemcpy(h->env_blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&h->env_model_idx, sizeof(int) * h->nenv));
+  CUDA_OK(cudaMemcpy(h->env_model_idx, idx.data(), sizeof(int) * h->nenv, cudaMemcpyHostToDevice));
+  h->n_env_models = nmodels;
+  return 0;
 }
 
 int b2mj_stage_profile(b2mj_handle* hh, int enable, uint64_t* cycles, int ncycles) {

@@ -46,6 +46,12 @@ struct Handle {
   int in_split_step = 0;
   uint64_t launches = 0;
 
+  // per-env model variants (b2mj_set_env_models): variant blob, env -> variant index, device view pointing at variant 0
+  void* env_blob = nullptr;
+  int* env_model_idx = nullptr;
+  int n_env_models = 0;
+  b2k::DevModel dm_env{};
+
   double* publish_slab = nullptr;       // staging of b2mj_allgather_publish (per handle: device- and stream-local)
   size_t publish_slab_n = 0;
 

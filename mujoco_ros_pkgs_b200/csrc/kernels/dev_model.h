@@ -24,7 +24,42 @@
 #endif
 #define B2K_G 32
 
+// The step kernel translation unit is compiled twice: once as is (namespace b2k: every env shares one model) and once
+// with -DB2K_PER_ENV_MODEL (namespace b2k_em): there every model array is read through a per-env byte offset, so that
+// each env may run its own VARIANT of the model (domain randomisation / the reference's mutating services applied to
+// one env: set_body_state mass, set_geom_properties, set_gravity, set_equality_constraint_parameters --
+// mujoco_ros/src/callbacks.cpp:210-370, 462-738).  Same sizes and topology, different values.  The shared-model build
+// pays nothing for it: MArr below is then a bare pointer.
+#ifdef B2K_PER_ENV_MODEL
+#define b2k b2k_em
+#endif
+
 namespace b2k {
+
+#if defined(__CUDACC__) && defined(B2K_PER_ENV_MODEL)
+__device__ __forceinline__ long long env_model_offset();  // env_ctx.cuh: byte offset of this warp's model variant
+#endif
+
+// model array as the device sees it (pointer-sized in both builds, so DevModel has ONE layout for the host)
+template <class T>
+struct MArr {
+  const T* p;
+  __host__ __device__ MArr& operator=(const T* q) { p = q; return *this; }
+  __host__ __device__ __forceinline__ const T* get() const {
+#if defined(__CUDA_ARCH__) && defined(B2K_PER_ENV_MODEL)
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + env_model_offset());
+#else
+    return p;
+#endif
+  }
+  __host__ __device__ __forceinline__ operator const T*() const { return get(); }
+  __host__ __device__ __forceinline__ const T& operator[](int i) const { return get()[i]; }
+  __host__ __device__ __forceinline__ const T& operator[](unsigned i) const { return get()[i]; }
+  __host__ __device__ __forceinline__ const T& operator[](long long i) const { return get()[i]; }
+  __host__ __device__ __forceinline__ const T& operator[](size_t i) const { return get()[i]; }
+  __host__ __device__ __forceinline__ const T* operator+(int i) const { return get() + i; }
+  __host__ __device__ __forceinline__ const T* operator+(size_t i) const { return get() + i; }
+};
 
 // extra per-env scratch arrays that are not b2mj_field entries
 enum XField {
@@ -66,9 +101,12 @@ struct DevModel {
   int nmaskword;  // words per body of body_dofmask
   b2mjOption opt;
   double meaninertia;
-#define B2K_X_ARR(t, n, r, c) const t* n;
+#define B2K_X_ARR(t, n, r, c) MArr<t> n;
   B2MJ_MODEL_ARRAYS(B2K_X_ARR)
 #undef B2K_X_ARR
+  MArr<double> env_gravity;   // [3] opt.gravity of the model variant
+  MArr<double> env_scalars;   // [1] stat.meaninertia of the model variant
+  long long env_model_stride; // bytes between model variants in the blob, 0 = one shared model
   const unsigned* body_dofmask;  // [nbody][nmaskword]: bit k set if dof k is on the chain from the body to its root
   // ---- derived topology tables (host-built, handle.cu::upload_model) for the wide-parallel stages ----
   int nbodyword;                 // words per body of body_submask
@@ -136,6 +174,7 @@ struct LaunchArgs {
   int chunk;               // steps per ticket
   int sync_stages;         // CTA-wide lockstep at stage boundaries (instruction / constant cache locality)
   const int* perm;         // [nenv] launch slot -> env, heaviest envs first (b2k_order_kernel), or null = identity
+  const int* env_model;    // [nenv] model variant of each env (per-env-model build only), or null
   unsigned long long* prof; // [PROF_COUNT] per-stage SM-cycle totals over all envs, or null (b2mj_stage_profile)
 };
 

@@ -15,6 +15,16 @@ __constant__ DevModel c_dm;
 // the compiler emits LDS / STS (not generic LD / ST) for arena traffic.
 extern __shared__ __align__(16) unsigned char b2k_smem[];
 
+#ifdef B2K_PER_ENV_MODEL
+// byte offset of this warp's model variant: written by the env's main warp into the spare half of its 16-byte
+// mbarrier slot when the env is picked up (step_kernel.cu), read back by every model array access
+__device__ __forceinline__ long long env_model_offset() {
+  const int tw = c_dm.team_warps;
+  const int slot = ((int)threadIdx.x / 32) / tw;
+  return *reinterpret_cast<const long long*>(b2k_smem + (tw > 1 ? 64 : 16) * slot + 8);
+}
+#endif
+
 struct Env {
   unsigned sbd;  // byte offset in b2k_smem of this env's shared arena (doubles; starts with the record image)
   unsigned sbi;  // byte offset of the int part

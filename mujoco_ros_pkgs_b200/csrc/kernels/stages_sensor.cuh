@@ -295,7 +295,7 @@ __device__ __noinline__ void stage_rnePost(const Env e, int ncon, const double* 
   }
   if (e.lane < 6) {
     double g = 0;
-    if (e.lane >= 3 && !(m.opt.disableflags & B2MJ_DSBL_GRAVITY)) g = -m.opt.gravity[e.lane - 3];
+    if (e.lane >= 3 && !(m.opt.disableflags & B2MJ_DSBL_GRAVITY)) g = -m.env_gravity[e.lane - 3];
     cacc[e.lane] = g;
     cint[e.lane] = 0;
   }

@@ -659,7 +659,7 @@ __device__ __noinline__ void stage_passive(const Env e) {
       const double gc = m.body_gravcomp[i];
       if (gc == 0) continue;
       double force[3], torque[3] = {0, 0, 0};
-      scl3(force, m.opt.gravity, -(m.body_mass[i] * gc));
+      scl3(force, m.env_gravity + 0, -(m.body_mass[i] * gc));
       applyFT_warp(e, force, torque, xipos + 3 * i, i, qp);
     }
   }
@@ -680,7 +680,7 @@ __device__ __noinline__ void stage_rne_bias(const Env e) {
   const bool grav = !(m.opt.disableflags & B2MJ_DSBL_GRAVITY);
   FORL(b, m.nbody) {
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    if (grav) { acc[3] = -m.opt.gravity[0]; acc[4] = -m.opt.gravity[1]; acc[5] = -m.opt.gravity[2]; }
+    if (grav) { acc[3] = -m.env_gravity[0]; acc[4] = -m.env_gravity[1]; acc[5] = -m.env_gravity[2]; }
     const unsigned* mask = m.body_dofmask + b * m.nmaskword;
     FOR_MASK_BITS(k, mask, m.nmaskword, { const double v = qvel[k]; for (int c = 0; c < 6; c++) acc[c] += cdof_dot[6 * k + c] * v; })
     double f[6], tmp[6], tmp1[6];

@@ -249,7 +249,7 @@ __device__ __noinline__ int solvePGS_regT(const Env e, int nefc, const double* A
   const double* AR = SM ? reinterpret_cast<const double*>(b2k_smem + ARs) : ARg;
   const double* rowc = AR + nefc * nefc;
   EfcPtrs P = efcPtrs(e);
-  const double scale = 1 / (m.meaninertia * max(1, m.nv));
+  const double scale = 1 / (m.env_scalars[0] * max(1, m.nv));
   const double tol = m.opt.tolerance;
   const int maxiter = m.opt.iterations;
   const int lane = e.lane;
@@ -385,7 +385,7 @@ template <bool SIMPLE>
 __device__ __forceinline__ int solvePGS_own_T(const Env e, int nefc, const double* AR, double iA, double Aii, double lo,
                                               double up, double f, double r, double* f_out) {
   const DevModel& m = c_dm;
-  const double scale = 1 / (m.meaninertia * max(1, m.nv));
+  const double scale = 1 / (m.env_scalars[0] * max(1, m.nv));
   const double tol = m.opt.tolerance;
   const int maxiter = m.opt.iterations;
   const int lane = e.lane;
@@ -477,7 +477,7 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
   const double* dinv = dense ? nullptr : e.DG(B2MJ_F_QLDIAGINV);
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
   const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
-  const double scale = 1 / (m.meaninertia * max(1, nv));
+  const double scale = 1 / (m.env_scalars[0] * max(1, nv));
   FORL(k, nv) {
     double s = 0;
     B2K_NOUNROLL for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
@@ -971,7 +971,7 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
   c.gradold = w + 5 * nv; c.Mgradold = w + 6 * nv; c.invd = w + 7 * nv;
   c.Jaref = e.XG(XF_EFC_JAREF); c.Jv = e.XG(XF_EFC_JV); c.quad = e.XG(XF_EFC_QUAD);
   c.H = newton ? e.XG(XF_NEWTON_H) : nullptr;
-  c.scale = 1 / (m.meaninertia * max(1, nv));
+  c.scale = 1 / (m.env_scalars[0] * max(1, nv));
   double* qacc = e.D(B2MJ_F_QACC);
 
   SPROF_DECL

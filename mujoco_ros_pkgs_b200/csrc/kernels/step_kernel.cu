@@ -220,6 +220,12 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
       step0 = 0;
       step1 = (a.mode == MODE_STEP) ? a.nsteps : 1;
     }
+#ifdef B2K_PER_ENV_MODEL
+    // this env's model variant: byte offset into the variant blob, parked in the spare half of the mbarrier slot
+    if (lane == 0 && !team_helper)
+      *reinterpret_cast<long long*>(smem_raw + hdr * warp + 8) = a.env_model ? (long long)a.env_model[env] * m.env_model_stride : 0;
+    __syncwarp(gmask);
+#endif
     double* gd = a.garena_d + (size_t)env * m.arena_g_doubles;
     int* gi = a.garena_i + (size_t)env * m.arena_g_ints;
     Env e{(unsigned)(base - smem_raw), (unsigned)(base - smem_raw) + 8u * (unsigned)m.arena_s_doubles, gd, gi, lane,
@@ -383,6 +389,10 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
 
 using namespace b2k;
 
+#ifdef B2K_PER_ENV_MODEL
+#define b2k_launch_step b2k_em_launch_step
+#endif
+
 // host shadow of what c_dm currently holds (per device), so the constant is re-uploaded only when a
 // different handle / an edited model launches
 static DevModel g_shadow[16];
@@ -432,6 +442,7 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
   return (int)cudaGetLastError();
 }
 
+#ifndef B2K_PER_ENV_MODEL  /* launch order, attributes and occupancy are shared with the main build */
 // Launch order for the next launch: envs sorted into weight classes by the solver work of their last step
 // (constraint rows x iterations), heaviest first.  A launch ends when its slowest env does; an env with 21 rows at the
 // 100-iteration PGS cap takes 4x the median step, and if it starts in the second wave its whole run is added to the
@@ -513,3 +524,4 @@ extern "C" int b2k_occupancy(int threads, size_t smem_bytes, int* ctas_per_sm) {
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, b2k_step_kernel, threads, smem_bytes);
   return (int)err;
 }
+#endif  // !B2K_PER_ENV_MODEL

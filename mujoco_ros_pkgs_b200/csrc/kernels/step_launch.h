@@ -15,6 +15,12 @@
 extern "C" {
 int b2k_launch_step(const b2k::DevModel* m, const b2k::LaunchArgs* a, int warps_per_cta, size_t smem_bytes,
                     cudaStream_t stream);
+#ifndef B2K_PER_ENV_MODEL
+/* the same kernel compiled with per-env model variants (step_kernel.cu with -DB2K_PER_ENV_MODEL, namespace b2k_em);
+ * DevModel / LaunchArgs have one layout in both builds */
+int b2k_em_launch_step(const b2k::DevModel* m, const b2k::LaunchArgs* a, int warps_per_cta, size_t smem_bytes,
+                       cudaStream_t stream);
+#endif
 int b2k_step_kernel_attrs(int* regs, int* static_smem, int* max_threads);
 int b2k_occupancy(int threads, size_t smem_bytes, int* ctas_per_sm);
 int b2k_launch_order(const int* stats, int nenv, int* perm, cudaStream_t stream);
