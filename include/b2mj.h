@@ -94,7 +94,7 @@ enum {
 
 /* error codes */
 enum {
-  B2MJ_OK = 0, B2MJ_EINVAL = -1, B2MJ_ENOMEM = -2, B2MJ_ECUDA = -3, B2MJ_EPARSE = -4,
+  B2MJ_OK = 0, B2MJ_AGAIN = 1 /* b2mj_step_end: RK4 sub-step done, run the hooks and call it again */, B2MJ_EINVAL = -1, B2MJ_ENOMEM = -2, B2MJ_ECUDA = -3, B2MJ_EPARSE = -4,
   B2MJ_EUNSUPPORTED = -5, B2MJ_ESTATE = -6, B2MJ_ENODEVICE = -7
 };
 
@@ -304,7 +304,11 @@ int b2mj_rollout(b2mj_handle* h, int nsteps, const double* dev_ctrl, double* dev
                  double* dev_sensor_out);
 /* split step around the control hook (mjcb_control fires between the velocity stage and actuation:
  * mujoco_env.h:242-246).  step_begin: checks + position + velocity stages (+pos/vel sensors);
- * step_end: actuation, acceleration, constraint solve, acc sensors, check, integrate. Euler only. */
+ * step_end: actuation, acceleration, constraint solve, acc sensors, check, integrate.
+ * RK4 (mj_RungeKutta makes four forward passes and the callbacks fire in each, plugin_utils.h:89-105): b2mj_step_end
+ * returns B2MJ_AGAIN after each of the first three sub-steps -- the caller runs its passive / control hooks again and
+ * calls b2mj_step_end again; the fourth call integrates and returns 0:
+ *     b2mj_step_begin(h); hooks(); while (b2mj_step_end(h) == B2MJ_AGAIN) hooks();   */
 int b2mj_step_begin(b2mj_handle* h);
 int b2mj_step_end(b2mj_handle* h);
 /* one closed-loop exchange with HOST buffers in a single call: upload ctrl ([nenv][nu], may be NULL = keep), run

@@ -265,18 +265,21 @@ class BatchEnv {
   bool simStep() {
     bool ok;
     const bool hooks = !cb_ready_plugins_.empty();
-    if (hooks && model_->opt.integrator == B2MJ_INT_EULER) {
+    if (hooks) {
+      // split step: the hooks run between the velocity stage and actuation of EVERY forward pass -- once for Euler,
+      // four times for RK4 (b2mj_step_end returns B2MJ_AGAIN after each of the first three sub-steps), exactly where
+      // mj_step fires mjcb_passive / mjcb_control (plugin_utils.h:89-105)
       ok = b2mj_step_begin(handle_) == B2MJ_OK;
-      if (ok) {
+      while (ok) {
         data_->invalidate();
         runPassiveCbs();
         runControlCbs();
-        ok = b2mj_step_end(handle_) == B2MJ_OK;
+        const int rc = b2mj_step_end(handle_);
+        if (rc == B2MJ_AGAIN) continue;
+        ok = rc == B2MJ_OK;
+        break;
       }
     } else {
-      // RK4 re-enters the hooks in each of its 4 sub-steps inside mj_step; the fused RK4 step cannot yield to
-      // the host there, so controls are sampled once per step (zero-order hold) -- documented deviation
-      if (hooks) { data_->invalidate(); runPassiveCbs(); runControlCbs(); }
       ok = b2mj_step(handle_, 1) == B2MJ_OK;
     }
     if (!ok) { load_error_ = b2mj_last_error(); return false; }

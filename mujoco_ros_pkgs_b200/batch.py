@@ -98,8 +98,9 @@ class BatchSim:
     def step_begin(self):
         check(lib.b2mj_step_begin(self._h), "step_begin")
 
-    def step_end(self):
-        check(lib.b2mj_step_end(self._h), "step_end")
+    def step_end(self) -> int:
+        """Returns 0 when the step is complete, 1 (B2MJ_AGAIN) after an RK4 sub-step: run the hooks, call again."""
+        return check(lib.b2mj_step_end(self._h), "step_end")
 
     def step_host(self, nsteps: int, ctrl: np.ndarray = None, qpos: np.ndarray = None, qvel: np.ndarray = None,
                   sensordata: np.ndarray = None):

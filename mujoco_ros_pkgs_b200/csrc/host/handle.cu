@@ -331,7 +331,7 @@ static int make_layout(Handle* h) {
   xs[XF_SUBTREE_LINVEL] = d.need_subtreevel ? 3 * m->nbody : 0;
   xs[XF_SUBTREE_ANGMOM] = d.need_subtreevel ? 3 * m->nbody : 0;
   xs[XF_BODYVEL] = d.need_subtreevel ? 6 * m->nbody : 0;
-  xs[XF_RK_X0] = rk4 ? nq + nv + na : 0;
+  xs[XF_RK_X0] = rk4 ? nq + nv + na + 1 : 0;  // + the step's start time (split RK4 steps span several launches)
   xs[XF_RK_XF] = rk4 ? 4 * nv : 0;
   xs[XF_RK_F] = rk4 ? 4 * (nv + na) : 0;
   xs[XF_RK_DX] = rk4 ? 2 * nv + na : 0;
@@ -629,6 +629,7 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
   a.nsteps = nsteps;
   a.mode = mode;
   a.dump = h->keep_intermediates;
+  a.rk_stage = h->rk_stage;
   a.prof = h->prof;
   a.ctrl_seq = ctrl_seq;
   a.traj_qpos = traj_qpos;
@@ -681,6 +682,7 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
     h->launches++;
   }
   h->dump_valid = (h->keep_intermediates || mode == MODE_STEP_BEGIN);
+  if (mode != MODE_STEP_END) h->rk_stage = 0;
   return 0;
 }
 
@@ -830,11 +832,8 @@ int b2mj_rollout(b2mj_handle* hh, int nsteps, const double* dev_ctrl, double* de
 int b2mj_step_begin(b2mj_handle* hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return B2MJ_EINVAL;
-  if (h->model->opt.integrator != B2MJ_INT_EULER) {
-    set_error("split step needs the Euler integrator (RK4 re-enters the control hook 4x per step)");
-    return B2MJ_EUNSUPPORTED;
-  }
   CUDA_OK(cudaSetDevice(h->device));
+  h->rk_stage = 0;
   int rc = handle_launch(h, MODE_STEP_BEGIN, 1);
   if (!rc) h->in_split_step = 1;
   return rc;
@@ -848,6 +847,17 @@ int b2mj_step_end(b2mj_handle* hh) {
     return B2MJ_ESTATE;
   }
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->model->opt.integrator == B2MJ_INT_RK4) {
+    // mj_RungeKutta runs four forward passes and the hooks fire in each: one launch per sub-step, B2MJ_AGAIN until
+    // the fourth has been integrated
+    const int stage = h->rk_stage;
+    const int rc = handle_launch(h, MODE_STEP_END, 1);
+    if (rc) { h->in_split_step = 0; return rc; }
+    if (stage < 3) { h->rk_stage = stage + 1; h->dump_valid = 1; return B2MJ_AGAIN; }
+    h->rk_stage = 0;
+    h->in_split_step = 0;
+    return 0;
+  }
   h->in_split_step = 0;
   return handle_launch(h, MODE_STEP_END, 1);
 }

@@ -44,6 +44,7 @@ struct Handle {
   int keep_intermediates = 0;
   int dump_valid = 0;
   int in_split_step = 0;
+  int rk_stage = 0;               // split RK4 step: sub-step whose second half the next b2mj_step_end runs
   uint64_t launches = 0;
 
   // per-env model variants (b2mj_set_env_models): variant blob, env -> variant index, device view pointing at variant 0

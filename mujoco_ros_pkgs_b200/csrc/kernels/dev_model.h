@@ -162,6 +162,7 @@ struct LaunchArgs {
   int nsteps;
   int mode;                // 0 step, 1 forward only, 2 step_begin (to control hook), 3 step_end
   int dump;                // copy the shared arena to garena at the end
+  int rk_stage;            // MODE_STEP_END of an RK4 model: which sub-step's second half this launch runs (0..3)
   // fused rollout (b2mj_rollout): per-step control stream in, per-step trajectory out (all optional)
   const double* ctrl_seq;  // [nsteps][nenv][nu]
   double* traj_qpos;       // [nsteps][nenv][nq]

@@ -101,77 +101,112 @@ __device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int e
   }
 }
 
-// mj_RungeKutta(4)
-__device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
+// mj_RungeKutta(4), in resumable pieces: the fused step runs them back to back around full forward passes; the split
+// step (b2mj_step_begin / b2mj_step_end with the host's control hook in between) runs one piece per launch, so that
+// mjcb_control / mjcb_passive fire in EVERY forward pass of a step as they do in the reference (plugin_utils.h:89-105:
+// "called ... in every sub-step of RK4").  State that must survive between launches lives in the arena (XF_RK_*),
+// which the split modes dump to / reload from HBM; X0's last slot carries the step's start time.
+struct RkPtrs {
+  double *qpos, *qvel, *qacc, *act, *act_dot, *timep, *X0, *Xf, *F, *dX;
+  int nq, nv, na;
+};
+__device__ __forceinline__ RkPtrs rkPtrs(const Env e) {
   const DevModel& m = c_dm;
-  const int nq = m.nq, nv = m.nv, na = m.na;
-  const double h = m.opt.timestep;
-  double* qpos = e.D(B2MJ_F_QPOS);
-  double* qvel = e.D(B2MJ_F_QVEL);
-  double* qacc = e.D(B2MJ_F_QACC);
-  double* act = na ? e.D(B2MJ_F_ACT) : nullptr;
-  double* act_dot = na ? e.D(B2MJ_F_ACT_DOT) : nullptr;
-  double* timep = e.D(B2MJ_F_TIME);
-  double* X0 = e.X(XF_RK_X0);      // nq + nv + na
-  double* Xf = e.X(XF_RK_XF);      // 4 * nv   stage velocities
-  double* F = e.X(XF_RK_F);        // 4 * (nv + na) stage accelerations / act_dot
-  double* dX = e.X(XF_RK_DX);      // 2*nv + na
-  const double time0 = timep[0];
-  const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1};
-  const double Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
-  FORL(i, nq) X0[i] = qpos[i];
-  FORL(i, nv) { X0[nq + i] = qvel[i]; Xf[i] = qvel[i]; F[i] = qacc[i]; }
-  FORL(i, na) { X0[nq + nv + i] = act[i]; F[nv + i] = act_dot[i]; }
+  RkPtrs r;
+  r.nq = m.nq; r.nv = m.nv; r.na = m.na;
+  r.qpos = e.D(B2MJ_F_QPOS); r.qvel = e.D(B2MJ_F_QVEL); r.qacc = e.D(B2MJ_F_QACC);
+  r.act = m.na ? e.D(B2MJ_F_ACT) : nullptr;
+  r.act_dot = m.na ? e.D(B2MJ_F_ACT_DOT) : nullptr;
+  r.timep = e.D(B2MJ_F_TIME);
+  r.X0 = e.X(XF_RK_X0);   // nq + nv + na + 1 (start time)
+  r.Xf = e.X(XF_RK_XF);   // 4 * nv   stage velocities
+  r.F = e.X(XF_RK_F);     // 4 * (nv + na) stage accelerations / act_dot
+  r.dX = e.X(XF_RK_DX);   // 2*nv + na
+  return r;
+}
+// after the first forward pass: save the start state and stage 0
+__device__ __noinline__ void rk_init(const Env e) {
+  const RkPtrs r = rkPtrs(e);
+  const int nq = r.nq, nv = r.nv, na = r.na;
+  FORL(i, nq) r.X0[i] = r.qpos[i];
+  FORL(i, nv) { r.X0[nq + i] = r.qvel[i]; r.Xf[i] = r.qvel[i]; r.F[i] = r.qacc[i]; }
+  FORL(i, na) { r.X0[nq + nv + i] = r.act[i]; r.F[nv + i] = r.act_dot[i]; }
+  if (e.lane == 0) r.X0[nq + nv + na] = r.timep[0];
   WSYNC();
-  for (int s = 1; s < 4; s++) {
-    FORL(k, nv) {
-      double dv = 0, da = 0;
-      for (int j = 0; j < 3; j++) {
-        const double c = A[(s - 1) * 3 + j];
-        if (c == 0) continue;
-        dv += c * Xf[j * nv + k];
-        da += c * F[j * (nv + na) + k];
-      }
-      dX[k] = dv;
-      dX[nv + k] = da;
-    }
-    FORL(k, na) {
-      double d = 0;
-      for (int j = 0; j < 3; j++) {
-        const double c = A[(s - 1) * 3 + j];
-        if (c != 0) d += c * F[j * (nv + na) + nv + k];
-      }
-      dX[2 * nv + k] = d;
-    }
-    FORL(i, nq) qpos[i] = X0[i];
-    WSYNC();
-    integratePos_warp(e, qpos, dX, h);
-    FORL(k, nv) qvel[k] = X0[nq + k] + h * dX[nv + k];
-    FORL(k, na) act[k] = X0[nq + nv + k] + h * dX[2 * nv + k];
-    if (e.lane == 0) timep[0] = time0 + (s == 3 ? 1.0 : 0.5) * h;
-    WSYNC();
-    forwardPass(e, a, env, sc, true, true, true);
-    FORL(k, nv) { Xf[s * nv + k] = qvel[k]; F[s * (nv + na) + k] = qacc[k]; }
-    FORL(k, na) F[s * (nv + na) + nv + k] = act_dot[k];
-    WSYNC();
-  }
+}
+// state of stage s (1..3) from the start state and the stages recorded so far
+__device__ __noinline__ void rk_setup_stage(const Env e, int s) {
+  const RkPtrs r = rkPtrs(e);
+  const int nq = r.nq, nv = r.nv, na = r.na;
+  const double h = c_dm.opt.timestep;
+  const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1};
   FORL(k, nv) {
     double dv = 0, da = 0;
-    for (int j = 0; j < 4; j++) { dv += Bw[j] * Xf[j * nv + k]; da += Bw[j] * F[j * (nv + na) + k]; }
-    dX[k] = dv;
-    dX[nv + k] = da;
+    for (int j = 0; j < 3; j++) {
+      const double c = A[(s - 1) * 3 + j];
+      if (c == 0) continue;
+      dv += c * r.Xf[j * nv + k];
+      da += c * r.F[j * (nv + na) + k];
+    }
+    r.dX[k] = dv;
+    r.dX[nv + k] = da;
   }
   FORL(k, na) {
     double d = 0;
-    for (int j = 0; j < 4; j++) d += Bw[j] * F[j * (nv + na) + nv + k];
-    dX[2 * nv + k] = d;
+    for (int j = 0; j < 3; j++) {
+      const double c = A[(s - 1) * 3 + j];
+      if (c != 0) d += c * r.F[j * (nv + na) + nv + k];
+    }
+    r.dX[2 * nv + k] = d;
   }
-  FORL(i, nq) qpos[i] = X0[i];
-  FORL(i, nv) qvel[i] = X0[nq + i];
-  FORL(i, na) act[i] = X0[nq + nv + i];
-  if (e.lane == 0) timep[0] = time0;
+  FORL(i, nq) r.qpos[i] = r.X0[i];
   WSYNC();
-  advance_warp(e, dX + 2 * nv, dX + nv, dX);
+  integratePos_warp(e, r.qpos, r.dX, h);
+  FORL(k, nv) r.qvel[k] = r.X0[nq + k] + h * r.dX[nv + k];
+  FORL(k, na) r.act[k] = r.X0[nq + nv + k] + h * r.dX[2 * nv + k];
+  if (e.lane == 0) r.timep[0] = r.X0[nq + nv + na] + (s == 3 ? 1.0 : 0.5) * h;
+  WSYNC();
+}
+// after the forward pass of stage s: record its velocity / acceleration
+__device__ __noinline__ void rk_record(const Env e, int s) {
+  const RkPtrs r = rkPtrs(e);
+  const int nv = r.nv, na = r.na;
+  FORL(k, nv) { r.Xf[s * nv + k] = r.qvel[k]; r.F[s * (nv + na) + k] = r.qacc[k]; }
+  FORL(k, na) r.F[s * (nv + na) + nv + k] = r.act_dot[k];
+  WSYNC();
+}
+// Butcher combination and the final advance from the start state
+__device__ __noinline__ void rk_finish(const Env e) {
+  const RkPtrs r = rkPtrs(e);
+  const int nq = r.nq, nv = r.nv, na = r.na;
+  const double Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+  FORL(k, nv) {
+    double dv = 0, da = 0;
+    for (int j = 0; j < 4; j++) { dv += Bw[j] * r.Xf[j * nv + k]; da += Bw[j] * r.F[j * (nv + na) + k]; }
+    r.dX[k] = dv;
+    r.dX[nv + k] = da;
+  }
+  FORL(k, na) {
+    double d = 0;
+    for (int j = 0; j < 4; j++) d += Bw[j] * r.F[j * (nv + na) + nv + k];
+    r.dX[2 * nv + k] = d;
+  }
+  FORL(i, nq) r.qpos[i] = r.X0[i];
+  FORL(i, nv) r.qvel[i] = r.X0[nq + i];
+  FORL(i, na) r.act[i] = r.X0[nq + nv + i];
+  if (e.lane == 0) r.timep[0] = r.X0[nq + nv + na];
+  WSYNC();
+  advance_warp(e, r.dX + 2 * nv, r.dX + nv, r.dX);
+}
+
+__device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
+  rk_init(e);
+  for (int s = 1; s < 4; s++) {
+    rk_setup_stage(e, s);
+    forwardPass(e, a, env, sc, true, true, true);
+    rk_record(e, s);
+  }
+  rk_finish(e);
 }
 
 __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel(const LaunchArgs a) {
@@ -309,10 +344,24 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         if (__any_sync(e.mask, bad)) resetEnv(e, warning, B2MJ_WARN_BADQVEL);
       }
       const bool first = a.mode != MODE_STEP_END, second = a.mode != MODE_STEP_BEGIN;
+      const bool rk_split = a.mode == MODE_STEP_END && m.opt.integrator == B2MJ_INT_RK4;
       sc.nsync = nsync_main;
-      forwardPass(e, a, env, sc, false, first, second);
+      // (split RK4: stages 1..3 are sensor-free forward passes, like the fused mj_RungeKutta)
+      forwardPass(e, a, env, sc, rk_split && a.rk_stage > 0, first, second);
       sc.nsync = 0;
       if (a.mode == MODE_FORWARD || a.mode == MODE_STEP_BEGIN) break;
+      if (rk_split && a.rk_stage > 0) {
+        // second half of sub-step rk_stage done: record it, then either open the next sub-step (first half only: the
+        // host's hooks run before its second half) or finish the step
+        rk_record(e, a.rk_stage);
+        if (a.rk_stage < 3) {
+          rk_setup_stage(e, a.rk_stage + 1);
+          forwardPass(e, a, env, sc, true, true, false);
+        } else {
+          rk_finish(e);
+        }
+        break;
+      }
       // mj_checkAcc
       {
         int bad = 0;
@@ -322,6 +371,12 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
           resetEnv(e, warning, B2MJ_WARN_BADQACC);
           forwardPass(e, a, env, sc, false, true, true);
         }
+      }
+      if (rk_split) {  // sub-step 0 of a split RK4 step: open sub-step 1 and yield to the host
+        rk_init(e);
+        rk_setup_stage(e, 1);
+        forwardPass(e, a, env, sc, true, true, false);
+        break;
       }
       if (m.opt.integrator == B2MJ_INT_RK4 && a.mode == MODE_STEP) stage_rk4(e, a, env, sc);
       else stage_euler(e);
@@ -365,7 +420,8 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         bulk_commit_wait();
       }
     }
-    if (a.dump || a.mode == MODE_STEP_BEGIN) {
+    if (a.dump || a.mode == MODE_STEP_BEGIN ||
+        (a.mode == MODE_STEP_END && m.opt.integrator == B2MJ_INT_RK4 && a.rk_stage < 3)) {
       for (int f = 0; f < B2MJ_NFIELD; f++) {
         const int os = m.off_s[f];
         if (os < 0) continue;

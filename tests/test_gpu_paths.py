@@ -370,3 +370,61 @@ def test_thousand_step_per_step_parity(name, nenv, amp, capi, orc, BatchSim):
     np.testing.assert_array_equal(sim.get("time")[:, 0], [o.time for o in free])
     print(f"{name}: 1000 injected steps worst {worst:.2e}, max nefc {max_nefc}; free-running divergence per 100 steps "
           + " ".join(f"{d:.1e}" for d in div))
+
+
+def test_rk4_split_step_hooks_fire_in_every_substep(capi, orc, BatchSim):
+    """mj_RungeKutta makes four forward passes and mjcb_control fires in each (plugin_utils.h:89-97).  The split step
+    yields to the host four times per RK4 step (b2mj_step_end -> B2MJ_AGAIN); with a controller that reads the
+    sub-step state (time and qvel) the batch must follow an oracle whose control callback does the same, and with a
+    constant control the split step must equal the fused one bitwise."""
+    model = variant(capi, "actuated_arm.xml", integrator=RK4)
+    nenv = 6
+    qpos, qvel = perturbed(model, nenv, 15, 0.2)
+    a, b = BatchSim(model, nenv), BatchSim(model, nenv)
+    for s_ in (a, b):
+        s_.set("qpos", qpos)
+        s_.set("qvel", qvel)
+    ctrl = np.random.default_rng(1).uniform(-1, 1, (nenv, model.nu))
+    a.set("ctrl", ctrl)
+    b.set("ctrl", ctrl)
+    for _ in range(25):
+        a.step(1)
+        b.step_begin()
+        n = 1
+        while b.step_end() == 1:
+            n += 1
+        assert n == 4
+    np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
+    np.testing.assert_array_equal(a.get("act"), b.get("act"))
+    np.testing.assert_array_equal(a.get("time"), b.get("time"))
+
+    # state-dependent controller evaluated inside every sub-step
+    def controller(time, qv):
+        return np.stack([0.8 * np.sin(40.0 * time + k) - 0.5 * qv[:, k % qv.shape[1]] for k in range(model.nu)], axis=1)
+
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    calls = [0]
+
+    def cb(o):
+        calls[0] += 1
+        c = controller(np.array([o.time]), o.get("qvel")[None, :])[0]
+        o.set("ctrl", c)
+
+    for o in oracles:
+        o.set_callbacks(control=cb)
+    for _ in range(60):
+        sim.step_begin()
+        while True:
+            sim.set("ctrl", controller(sim.get("time")[:, 0], sim.get("qvel")))
+            if sim.step_end() != 1:
+                break
+        for o in oracles:
+            o.step(1)
+    assert calls[0] == 60 * 4 * nenv
+    gq, gv = sim.get("qpos"), sim.get("qvel")
+    for e, o in enumerate(oracles):
+        assert rel(gq[e], o.get("qpos")) < TOL and rel(gv[e], o.get("qvel")) < TOL, e
+    np.testing.assert_array_equal(sim.get("time")[:, 0], [o.time for o in oracles])
