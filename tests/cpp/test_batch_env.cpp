@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "b2mj_compat.hpp"
 #include "b2mj_env.hpp"
 #include "b2mj_plugins.hpp"
 
@@ -418,6 +419,63 @@ static void test_control_plugin() {
   EXPECT_DOUBLE_EQ(d->row(B2MJ_F_QFRC_APPLIED, 0)[d1], 2.5);
 }
 
+// A single-env callback body written against mjData member names (what the reference's plugins look like: they get
+// (const mjModel*, mjData*) of the one env, plugin_utils.h:97-135) hosted on the batch through the compat view.
+// The body below is a joint-space PD controller + a Cartesian push on a body + a passive damper, i.e. it touches
+// d->time, d->qpos, d->qvel, d->ctrl, d->xfrc_applied, d->xpos and d->qfrc_passive by name.
+static int g_body_calls = 0;
+static void single_env_control_body(const b2mjModel* m, EnvDataView* d) {
+  g_body_calls++;
+  const int j = b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint2");
+  const int qadr = m->jnt_qposadr[j], dadr = m->jnt_dofadr[j];
+  const double target = -0.3 + 0.05 * d->env;                       // each env its own target
+  d->ctrl[1] = target + 0.2 * (target - d->qpos[qadr]) - 0.01 * d->qvel[dadr];
+  const int b = b2mj_name2id(m, B2MJ_OBJ_BODY, "link7");
+  if (b > 0 && d->xpos) d->xfrc_applied[6 * b + 2] = d->xpos[3 * b + 2] > 0.2 ? -1.0 : 0.0;  // push down while above 20 cm
+}
+static void single_env_passive_body(const b2mjModel* m, EnvDataView* d) {
+  if (d->qfrc_passive) d->qfrc_passive[m->nv - 1] += -0.05 * d->qvel[m->nv - 1];
+}
+static void test_single_env_compat_view() {
+  BatchEnv env(g_nenv);
+  auto* ad = new SingleEnvPluginAdapter(SingleEnvPluginAdapter::ALL_ENVS);
+  double seen_time = -1;
+  int last_calls = 0;
+  ad->setControlCallback(single_env_control_body);
+  ad->setPassiveCallback(single_env_passive_body);
+  ad->setLastStageCallback([&](const b2mjModel*, EnvDataView* d) { seen_time = d->time; last_calls++; });
+  env.registerPlugin(BatchPluginPtr(ad), {{"type", "compat/SingleEnv"}});
+  EXPECT_TRUE(env.load(g_models + "/panda_like.xml"));
+  EXPECT_TRUE(ad->loaded());
+  const b2mjModel* m = env.getModelPtr();
+  g_body_calls = 0;
+  EXPECT_TRUE(env.step(200));
+  EXPECT_TRUE(g_body_calls == 200 * g_nenv);
+  EXPECT_TRUE(last_calls == 200 * g_nenv);
+  EXPECT_NEAR(seen_time, 200 * m->opt.timestep, 1e-9);
+  BatchData* d = env.getDataPtr();
+  d->invalidate();
+  const int j = b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint2");
+  for (int e = 0; e < g_nenv; e++) {
+    const double target = -0.3 + 0.05 * e;
+    // the position servo on joint2 follows the per-env target the body wrote into ITS env's ctrl row
+    EXPECT_NEAR(d->row(B2MJ_F_QPOS, e)[m->jnt_qposadr[j]], target, 0.08);
+    EXPECT_TRUE(std::fabs(d->row(B2MJ_F_CTRL, e)[1] - target) < 0.1);
+  }
+  if (g_nenv > 1) EXPECT_TRUE(std::fabs(d->row(B2MJ_F_QPOS, 0)[m->jnt_qposadr[j]] - d->row(B2MJ_F_QPOS, g_nenv - 1)[m->jnt_qposadr[j]]) > 1e-3);
+  // one env only: the others keep zero controls
+  BatchEnv env1(g_nenv);
+  auto* one = new SingleEnvPluginAdapter(0);
+  one->setControlCallback([](const b2mjModel*, EnvDataView* v) { v->ctrl[0] = 0.7; });
+  env1.registerPlugin(BatchPluginPtr(one));
+  EXPECT_TRUE(env1.load(g_models + "/panda_like.xml"));
+  EXPECT_TRUE(env1.step(3));
+  BatchData* d1 = env1.getDataPtr();
+  d1->invalidate();
+  EXPECT_DOUBLE_EQ(d1->row(B2MJ_F_CTRL, 0)[0], 0.7);
+  if (g_nenv > 1) EXPECT_DOUBLE_EQ(d1->row(B2MJ_F_CTRL, g_nenv - 1)[0], 0.0);
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { std::printf("usage: %s <models_dir> [nenv]\n", argv[0]); return 2; }
   g_models = argv[1];
@@ -439,6 +497,7 @@ int main(int argc, char** argv) {
   test_load_errors();
   test_sensors_plugin();
   test_control_plugin();
+  test_single_env_compat_view();
   std::printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "OK", g_checks, g_fail);
   return g_fail ? 1 : 0;
 }
