@@ -342,6 +342,18 @@ int b2mj_device_ptr(b2mj_handle* h, b2mj_field f, void** dev_ptr, size_t* pitch_
  * callbacks.cpp:462-738: gravity, body_mass, geom_*, eq_*) */
 int b2mj_model_update(b2mj_handle* h, const b2mjModel* m);
 
+/* narrowphase override per geom-type pair: the batched counterpart of MujocoEnv::registerCollisionFunction
+ * (mujoco_env.h:211, mujoco_env.cpp:163-176), which lets a plugin overwrite mjCOLLISIONFUNC[type1][type2] and restores
+ * the defaults on reload (:949-954).  The narrowphase is device code, so a host function pointer cannot be called from
+ * it; the table instead selects among functions the library provides:
+ *   B2MJ_COLLFN_DEFAULT           the built-in function of the pair
+ *   B2MJ_COLLFN_NONE              no contacts for this pair type (what registering a function that returns 0 does)
+ *   B2MJ_COLLFN_BOUNDING_SPHERES  both geoms collide as their bounding spheres (geom_rbound); planes stay planes
+ * type1 <= type2 (the table is upper triangular, like mjCOLLISIONFUNC).  Takes effect from the next step. */
+enum { B2MJ_COLLFN_DEFAULT = 0, B2MJ_COLLFN_NONE = 1, B2MJ_COLLFN_BOUNDING_SPHERES = 2 };
+int b2mj_register_collision_function(b2mj_handle* h, int geom_type1, int geom_type2, int collfn);
+int b2mj_reset_collision_functions(b2mj_handle* h); /* all pairs back to B2MJ_COLLFN_DEFAULT (prepareReload) */
+
 /* per-env model variants: domain randomisation, and the reference's mutating services applied to ONE env rather than
  * to all (set_body_state mass / inertia, set_geom_properties friction / size / -> mj_setConst, set_gravity,
  * set_equality_constraint_parameters: callbacks.cpp:210-370, 462-592, 641-738).  models[0..nmodels) are edited copies of

@@ -235,6 +235,15 @@ class BatchEnv {
   void setInitialJointPositions(const std::map<std::string, std::string>& m) { initial_joint_positions_ = m; }
   void setInitialJointVelocities(const std::map<std::string, std::string>& m) { initial_joint_velocities_ = m; }
 
+  // mujoco_env.h:211 / mujoco_env.cpp:163-176: overwrite the narrowphase of a geom-type pair; the defaults come back
+  // on the next load (prepareReload, :949-954).  collfn: B2MJ_COLLFN_* (device code cannot call a host function).
+  bool registerCollisionFunction(int geom_type1, int geom_type2, int collfn) {
+    if (!handle_) return false;  // like the reference: plugins register from load(), i.e. once a model is loaded
+    custom_collisions_.push_back({geom_type1, geom_type2, collfn});
+    return b2mj_register_collision_function(handle_, geom_type1, geom_type2, collfn) == B2MJ_OK;
+  }
+
+  size_t numCustomCollisions() const { return custom_collisions_.size(); }
   void setNumStepsUntilExit(int n) { num_steps_until_exit_ = n; }  // mujoco_env.h:271 (-1 = no limit)
 
   const b2mjModel* getModelPtr() const { return model_; }
@@ -417,6 +426,7 @@ class BatchEnv {
     return true;
   }
   void unload() {
+    custom_collisions_.clear();  // prepareReload: "Resetting collision cbs to default" (mujoco_env.cpp:949-954)
     cb_ready_plugins_.clear();
     data_.reset();
     if (handle_) { b2mj_destroy(handle_); handle_ = nullptr; }
@@ -430,6 +440,8 @@ class BatchEnv {
   std::vector<BatchPlugin*> cb_ready_plugins_;  // objects managed by plugins_ (mujoco_env.h:265)
   std::vector<BatchPluginPtr> plugins_;
   int num_steps_until_exit_ = -1;
+  struct CustomCollision { int t1, t2, fn; };
+  std::vector<CustomCollision> custom_collisions_;  // mujoco_env.h custom_collisions_ (cleared by every load)
   std::map<std::string, std::string> initial_joint_positions_, initial_joint_velocities_;
   std::thread physics_thread_handle_;
   std::atomic_int is_physics_running_ = {0};

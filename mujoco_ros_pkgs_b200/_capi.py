@@ -79,7 +79,7 @@ EXPORTS = [
     "b2mj_create", "b2mj_destroy", "b2mj_nenv", "b2mj_model", "b2mj_set_stream", "b2mj_reset",
     "b2mj_forward", "b2mj_step", "b2mj_rollout", "b2mj_step_begin", "b2mj_step_end", "b2mj_step_host", "b2mj_sync",
     "b2mj_set_keep_intermediates", "b2mj_get", "b2mj_set", "b2mj_set_device", "b2mj_device_ptr", "b2mj_model_update",
-    "b2mj_set_env_models",
+    "b2mj_set_env_models", "b2mj_register_collision_function", "b2mj_reset_collision_functions",
     "b2mj_robot_hw_configure", "b2mj_robot_hw_write", "b2mj_robot_hw_read", "b2mj_robot_hw_state_ptrs", "b2mj_sensor_configure_noise",
     "b2mj_sensor_readout", "b2mj_sensor_readout_device", "b2mj_allgather_publish", "b2mj_allgather_publish_multi",
     "b2mj_publish_pack", "b2mj_ubench_dfma", "b2mj_launch_info", "b2mj_stage_profile", "b2mj_stage_name", "b2mj_env_cycles", "b2mj_last_error", "b2mj_version",

@@ -36,6 +36,8 @@ lib.b2mj_stage_name.argtypes = [C.c_int]
 lib.b2mj_stage_name.restype = C.c_char_p
 lib.b2mj_device_ptr.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t)]
 lib.b2mj_model_update.argtypes = [_vp, _vp]
+lib.b2mj_register_collision_function.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+lib.b2mj_reset_collision_functions.argtypes = [_vp]
 lib.b2mj_set_env_models.argtypes = [_vp, C.POINTER(_vp), C.c_int, _vp]
 lib.b2mj_launch_info.argtypes = [_vp, C.POINTER(_capi.B2mjLaunchInfo)]
 lib.b2mj_robot_hw_configure.argtypes = [_vp, C.POINTER(_capi.B2mjRobotHW)]
@@ -153,6 +155,12 @@ class BatchSim:
 
     def model_update(self, model: Model = None):
         check(lib.b2mj_model_update(self._h, (model or self.model).ptr), "model_update")
+
+    def register_collision_function(self, type1: int, type2: int, collfn: int):
+        check(lib.b2mj_register_collision_function(self._h, type1, type2, collfn), "register_collision_function")
+
+    def reset_collision_functions(self):
+        check(lib.b2mj_reset_collision_functions(self._h), "reset_collision_functions")
 
     def set_env_models(self, models, env_model):
         """Per-env model variants: models = list of Model (edited copies), env_model = [nenv] variant index."""

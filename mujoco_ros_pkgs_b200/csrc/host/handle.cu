@@ -1058,6 +1058,30 @@ int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
   return upload_init_templates(h);
 }
 
+int b2mj_register_collision_function(b2mj_handle* hh, int t1, int t2, int collfn) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || t1 < 0 || t2 < 0 || t1 > 7 || t2 > 7 || collfn < B2MJ_COLLFN_DEFAULT || collfn > B2MJ_COLLFN_BOUNDING_SPHERES) {
+    set_error("b2mj_register_collision_function: bad geom type or function id");
+    return B2MJ_EINVAL;
+  }
+  if (t1 > t2) std::swap(t1, t2);
+  if (collfn == B2MJ_COLLFN_BOUNDING_SPHERES && t2 == B2MJ_GEOM_PLANE) {
+    set_error("b2mj_register_collision_function: a plane has no bounding sphere");
+    return B2MJ_EINVAL;
+  }
+  h->dm.collfunc[t1 * 8 + t2] = (unsigned char)collfn;
+  h->dm_env.collfunc[t1 * 8 + t2] = (unsigned char)collfn;
+  return 0;
+}
+
+int b2mj_reset_collision_functions(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  std::memset(h->dm.collfunc, 0, sizeof(h->dm.collfunc));
+  std::memset(h->dm_env.collfunc, 0, sizeof(h->dm_env.collfunc));
+  return 0;
+}
+
 int b2mj_set_env_models(b2mj_handle* hh, const b2mjModel* const* models, int nmodels, const int* env_model) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || nmodels < 0 || (nmodels > 0 && (!models || !env_model))) {

@@ -146,6 +146,7 @@ struct DevModel {
   int need_subtreevel;
   int any_damping;         // Euler implicit damping active
   int dense_small;         // nv <= 16: inertia handled as dense nv x nv matrices (explicit inverses, no index tables)
+  unsigned char collfunc[64];  // narrowphase override per geom-type pair [t1 * 8 + t2]: B2MJ_COLLFN_* (0 = built in)
   int team_warps;          // warps per env: 1, or 8 for wide Newton models (team.cuh): one env per CTA, helpers on call
   int ldh;                 // leading dimension of the Newton Hessian (odd in team mode: conflict-free column walks)
 };

@@ -284,6 +284,15 @@ __device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   const double *pos1 = gxpos + 3 * g1, *mat1 = gxmat + 9 * g1, *size1 = m.geom_size + 3 * g1;
   const double *pos2 = gxpos + 3 * g2, *mat2 = gxmat + 9 * g2, *size2 = m.geom_size + 3 * g2;
+  // narrowphase override table: the batched counterpart of MujocoEnv::registerCollisionFunction, which overwrites
+  // mjCOLLISIONFUNC[t1][t2] (mujoco_env.cpp:163-176).  Device code cannot call a host plugin's function pointer, so the
+  // table selects among functions the library provides (b2mj_register_collision_function).
+  const int fn = m.collfunc[(t1 & 7) * 8 + (t2 & 7)];
+  if (fn == B2MJ_COLLFN_NONE) return 0;
+  if (fn == B2MJ_COLLFN_BOUNDING_SPHERES) {
+    if (t1 == B2MJ_GEOM_PLANE) return c_planeSphere(o, 0, margin, pos1, mat1, pos2, m.geom_rbound[g2]);
+    return c_sphereSphere(o, 0, margin, pos1, m.geom_rbound[g1], pos2, m.geom_rbound[g2]);
+  }
   if (t1 == B2MJ_GEOM_PLANE) {
     if (t2 == B2MJ_GEOM_SPHERE) return c_planeSphere(o, 0, margin, pos1, mat1, pos2, size2[0]);
     if (t2 == B2MJ_GEOM_CAPSULE) {

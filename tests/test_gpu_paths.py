@@ -428,3 +428,41 @@ def test_rk4_split_step_hooks_fire_in_every_substep(capi, orc, BatchSim):
     for e, o in enumerate(oracles):
         assert rel(gq[e], o.get("qpos")) < TOL and rel(gv[e], o.get("qvel")) < TOL, e
     np.testing.assert_array_equal(sim.get("time")[:, 0], [o.time for o in oracles])
+
+
+def test_collision_function_override_table(capi, BatchSim):
+    """Batched counterpart of MujocoEnv::registerCollisionFunction (mujoco_env.cpp:163-176): overriding the narrowphase
+    of a geom-type pair.  NONE on (plane, sphere): the pendulum scene's ball falls through the floor in exact free
+    fall; BOUNDING_SPHERES on (plane, box): a box comes to rest one bounding radius above the plane instead of one
+    half-height; reset restores the built-in functions."""
+    PLANE, SPHERE, BOX = 0, 2, 6
+    model = variant(capi, "pendulum_scene.xml")
+    nenv = 3
+    a, b = BatchSim(model, nenv), BatchSim(model, nenv)
+    b.register_collision_function(PLANE, SPHERE, 1)   # B2MJ_COLLFN_NONE
+    for s_ in (a, b):
+        s_.step(400)
+    assert np.all(a.get("ncon")[:, 0] == 1) and np.all(b.get("ncon")[:, 0] == 0)
+    ball = model.jnt_qposadr[model.name2id(capi.OBJ_JOINT, "ball_freejoint")]
+    dof = model.jnt_dofadr[model.name2id(capi.OBJ_JOINT, "ball_freejoint")]
+    g, h, k = 9.81, model.opt.timestep, 400
+    np.testing.assert_allclose(b.get("qvel")[:, dof + 2], -g * h * k, rtol=1e-12)
+    np.testing.assert_allclose(b.get("qpos")[:, ball + 2], model.qpos0[ball + 2] - g * h * h * k * (k + 1) / 2, rtol=1e-12)
+    assert a.get("qpos")[0, ball + 2] > 0.04      # the unmodified batch rests on the floor
+    b.reset_collision_functions()
+    b.reset()
+    b.step(400)
+    np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
+    # bounding spheres for plane-box
+    xml = """<mujoco><option timestep="0.002"/><worldbody><geom type="plane" size="2 2 .1"/>
+      <body pos="0 0 0.5"><freejoint/><geom type="box" size="0.1 0.1 0.05" density="500"/></body></worldbody></mujoco>"""
+    m = capi.Model.from_xml_string(xml)
+    c, d = BatchSim(m, 2), BatchSim(m, 2)
+    d.register_collision_function(BOX, PLANE, 2)      # argument order does not matter; B2MJ_COLLFN_BOUNDING_SPHERES
+    for s_ in (c, d):
+        s_.step(1500)
+    rb = float(m.geom_rbound[1])
+    assert abs(c.get("qpos")[0, 2] - 0.05) < 2e-3
+    assert abs(d.get("qpos")[0, 2] - rb) < 2e-3 and rb > 0.14
+    with pytest.raises(capi.B2mjError):
+        d.register_collision_function(PLANE, PLANE, 2)
