@@ -428,7 +428,7 @@ static void single_env_control_body(const b2mjModel* m, EnvDataView* d) {
   g_body_calls++;
   const int j = b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint2");
   const int qadr = m->jnt_qposadr[j], dadr = m->jnt_dofadr[j];
-  const double target = -0.3 + 0.05 * d->env;                       // each env its own target
+  const double target = -0.3 + 0.02 * d->env;                      // each env its own target
   d->ctrl[1] = target + 0.2 * (target - d->qpos[qadr]) - 0.01 * d->qvel[dadr];
   const int b = b2mj_name2id(m, B2MJ_OBJ_BODY, "link7");
   if (b > 0 && d->xpos) d->xfrc_applied[6 * b + 2] = d->xpos[3 * b + 2] > 0.2 ? -1.0 : 0.0;  // push down while above 20 cm
@@ -457,7 +457,7 @@ static void test_single_env_compat_view() {
   d->invalidate();
   const int j = b2mj_name2id(m, B2MJ_OBJ_JOINT, "joint2");
   for (int e = 0; e < g_nenv; e++) {
-    const double target = -0.3 + 0.05 * e;
+    const double target = -0.3 + 0.02 * e;
     // the position servo on joint2 follows the per-env target the body wrote into ITS env's ctrl row
     EXPECT_NEAR(d->row(B2MJ_F_QPOS, e)[m->jnt_qposadr[j]], target, 0.08);
     EXPECT_TRUE(std::fabs(d->row(B2MJ_F_CTRL, e)[1] - target) < 0.1);
