@@ -348,15 +348,6 @@ static int make_layout(Handle* h) {
   // xfrc_applied / mocap live in their own HBM arrays (read only when the surface is enabled)
   d.fsize[B2MJ_F_XFRC_APPLIED] = 0;
 
-  // global (full) arena offsets
-  int gd = 0, gi = 0;
-  for (int f = 0; f < B2MJ_NFIELD; f++) {
-    if (d.fis_int[f]) { d.off_g[f] = gi; gi += d.fsize[f]; }
-    else { d.off_g[f] = gd; gd += d.fsize[f]; }
-  }
-  for (int i = 0; i < XF_COUNT; i++) { d.xoff_g[i] = gd; gd += xs[i]; }
-  d.arena_g_doubles = even(gd);
-  d.arena_g_ints = even(gi);
 
   // shared placement: record image first, then hot fields; big constraint arrays are demoted to the
   // global arena (L2) when the per-env footprint would starve occupancy
@@ -466,13 +457,10 @@ static int make_layout(Handle* h) {
       order.push_back({0, B2MJ_F_EFC_J});
       order.push_back({1, XF_EFC_MINVJT});
     }
-    // the rest, smallest first
-    std::vector<Cand> rest(cands.begin(), cands.end());
-    std::stable_sort(rest.begin(), rest.end(), [](const Cand& a, const Cand& b) { return a.bytes < b.bytes; });
-    for (const Cand& c : rest) order.push_back({c.is_x, c.id});
     const bool no_promote = getenv("B2MJ_NO_PROMOTE") != nullptr;
     int promote_left = getenv("B2MJ_PROMOTE_MAX") ? atoi(getenv("B2MJ_PROMOTE_MAX")) : 1 << 30;  // experiment knob
-    for (const auto& o : order) {
+    auto promote = [&](const std::vector<std::pair<int, int>>& list) {
+    for (const auto& o : list) {
       char& flag = o.first ? xcold[o.second] : cold[o.second];
       const int sz = o.first ? xs[o.second] : d.fsize[o.second];
       if (!flag || !sz || no_promote) continue;
@@ -482,7 +470,39 @@ static int make_layout(Handle* h) {
       if (envs_per_sm(nullptr) < E || !rollout_shape_ok(E)) flag = 1;  // does not fit at this residency: stays in L2
       else promote_left--;
     }
+    };
+    promote(order);
+    // primal solvers: whatever shared memory is still free at this residency becomes a window for the ACTIVE rows of
+    // efc_J (stages_constraint.cuh::solveJ), when the full njmax-row Jacobian itself stayed in L2
+    d.jwin_rows = 0;
+    if (!pgs && d.team_warps == 1 && cold[B2MJ_F_EFC_J] && !no_promote && !getenv("B2MJ_NO_JWIN")) {
+      int lo = 0, hi = std::min(m->njmax, 4096);
+      while (lo < hi) {  // largest row count that keeps the residency
+        const int mid = (lo + hi + 1) / 2;
+        xs[XF_JWIN] = 2 + mid * nv;
+        if (envs_per_sm(nullptr) >= E && rollout_shape_ok(E)) lo = mid; else hi = mid - 1;
+      }
+      // (rows beyond what a step ever uses would only crowd out the cold arrays below: cap at 64)
+      d.jwin_rows = lo >= 4 ? std::min(lo, 64) : 0;
+      xs[XF_JWIN] = d.jwin_rows ? 2 + d.jwin_rows * nv : 0;
+    }
+    // the rest, smallest first
+    std::vector<Cand> rest(cands.begin(), cands.end());
+    std::stable_sort(rest.begin(), rest.end(), [](const Cand& a, const Cand& b) { return a.bytes < b.bytes; });
+    std::vector<std::pair<int, int>> rest_order;
+    for (const Cand& c : rest) rest_order.push_back({c.is_x, c.id});
+    promote(rest_order);
   }
+  // global (full) arena offsets (after every size is final: the efc_J window above is sized last)
+  int gd = 0, gi = 0;
+  for (int f = 0; f < B2MJ_NFIELD; f++) {
+    if (d.fis_int[f]) { d.off_g[f] = gi; gi += d.fsize[f]; }
+    else { d.off_g[f] = gd; gd += d.fsize[f]; }
+  }
+  for (int i = 0; i < XF_COUNT; i++) { d.xoff_g[i] = gd; gd += xs[i]; }
+  d.arena_g_doubles = even(gd);
+  d.arena_g_ints = even(gi);
+
   // A second tier that also demoted write-once/read-once kinematic fields (geom frames, crb, cinert, cvel, ...)
   // was measured and dropped (profiles/r1_layout_sweep.txt): it buys throughput only for contact-free batches far
   // beyond one wave (18M -> 26M env-steps/s at 16k envs) and costs ~8% at the BASELINE batch because every access
@@ -538,7 +558,7 @@ static int make_layout(Handle* h) {
     static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
                                    "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",
                                    "SUBTREE_ANGMOM", "BODYVEL", "RK_X0", "RK_XF", "RK_F", "RK_DX", "SCRATCH", "QW", "QHW",
-                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JCOLS"};
+                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS"};
     fprintf(stderr, "[b2mj layout] record %d doubles; shared arena %d doubles + %d ints per env\n", d.rec_end, d.arena_s_doubles,
             d.arena_s_ints);
     for (int f = 0; f < B2MJ_NFIELD; f++)

@@ -90,6 +90,7 @@ enum XField {
   XF_HINV,          // nv*nv  dense inv(qM + h diag(damping))
   XF_PRIMAL,        // 8*nv  Newton / CG work vectors (Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
   XF_EFC_AR_S,      // shared-memory home of AR when nefc*nefc fits (the common case)
+  XF_JWIN,          // primal solvers: shared-memory window for the ACTIVE rows of efc_J: [0] = valid flag, rows from +2
   XF_JCOLS,         // team mode: per constraint row {nnz, columns} bytes (team.cuh), njmax * 17 bytes
   XF_COUNT
 };
@@ -148,6 +149,7 @@ struct DevModel {
   int dense_small;         // nv <= 16: inertia handled as dense nv x nv matrices (explicit inverses, no index tables)
   unsigned char collfunc[64];  // narrowphase override per geom-type pair [t1 * 8 + t2]: B2MJ_COLLFN_* (0 = built in)
   int team_warps;          // warps per env: 1, or 8 for wide Newton models (team.cuh): one env per CTA, helpers on call
+  int jwin_rows;           // rows the efc_J window holds (0 = no window)
   int ldh;                 // leading dimension of the Newton Hessian (odd in team mode: conflict-free column walks)
 };
 

@@ -30,6 +30,31 @@ __device__ __forceinline__ bool jacColumn(const double* cdof, const double* com,
   return true;
 }
 
+// efc_J as the SOLVE stage reads it.  The Jacobian is sized for njmax rows and lives in the env's L2 arena, but a step
+// uses a handful of rows (C3: ~9 of 96, C4: ~8 of 128): stage_fwdConstraint copies the active rows into a shared-memory
+// window when they fit (XF_JWIN, sized by make_layout from the shared memory left over at the chosen residency) and
+// every solver routine picks its base pointer here.  Round 2 profile: with J in L2 the Newton Hessian build was a
+// chain of dependent ~600-cycle gathers (93 k cycles per build at nv = 24).
+__device__ __forceinline__ const double* solveJ(const Env e) {
+  if (c_dm.jwin_rows > 0) {
+    const double* w = e.X(XF_JWIN);
+    if (w[0] != 0.0) return w + 2;
+  }
+  return e.DG(B2MJ_F_EFC_J);
+}
+__device__ __forceinline__ void stageJWindow(const Env e, int nefc) {
+  if (c_dm.jwin_rows <= 0) return;
+  double* w = e.X(XF_JWIN);
+  const bool fits = nefc <= c_dm.jwin_rows;
+  if (fits) {
+    const double* J = e.DG(B2MJ_F_EFC_J);
+    const int n = nefc * c_dm.nv;
+    FORL(k, n) w[2 + k] = J[k];
+  }
+  if (e.lane == 0) w[0] = fits ? 1.0 : 0.0;
+  WSYNC();
+}
+
 struct EfcPtrs {
   double *J, *pos, *margin, *floss, *diag, *KBIP, *D, *R, *vel, *aref, *b, *force;
   int *type, *id, *state;
@@ -425,7 +450,7 @@ __device__ __noinline__ void stage_referenceConstraint(const Env e, int nefc) {
 // res[k] = sum_i J[i][k] * f[i]   (J' f), one lane per dof
 __device__ __noinline__ void mulJacTVec_warp(const Env e, int nefc, double* res, const double* f) {
   const int nv = c_dm.nv;
-  const double* J = e.DG(B2MJ_F_EFC_J);
+  const double* J = solveJ(e);  // only called from the solve stage (window staged) or with the window invalid
   FORL(k, nv) {
     double s = 0;
     B2K_NOUNROLL for (int i = 0; i < nefc; i++) {

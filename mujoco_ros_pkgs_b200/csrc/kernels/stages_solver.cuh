@@ -558,7 +558,7 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
 __device__ __forceinline__ void mulJacVec_warp(const Env e, int nefc, double* res, const double* vec) {
   if (c_dm.team_warps > 1) { mulJacVec_sparse(e, nefc, res, vec); return; }  // column lists of this pass (TEAM_JCOLS)
   const int nv = c_dm.nv;
-  const double* J = e.DG(B2MJ_F_EFC_J);
+  const double* J = solveJ(e);
   FORL(i, nefc) {
     double s = 0;
     B2K_NOUNROLL for (int k = 0; k < nv; k++) s += J[i * nv + k] * vec[k];
@@ -717,6 +717,7 @@ __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
   }
   const int nv = c.nv, nefc = c.nefc;
   EfcPtrs P = efcPtrs(e);
+  P.J = const_cast<double*>(solveJ(e));  // active rows from the shared-memory window when staged
   const double* qM = e.D(B2MJ_F_QM);
   double* H = newtonH<SM>(e);
   FORL(k, nv * nv) H[k] = 0;
@@ -1122,6 +1123,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
   } else {
     const bool newton = m.opt.solver == B2MJ_SOL_NEWTON;
     if (m.team_warps > 1) team_call(e, TEAM_JCOLS, nefc, 0);  // column lists of J for this forward pass
+    stageJWindow(e, nefc);                                     // active rows of J into shared memory when they fit
     if (warmstart) {
       // cost at the warm start vs at the unconstrained acceleration
       double* jar = e.XG(XF_EFC_JAREF);

@@ -17,5 +17,5 @@ timeout 300 python tools/imbalance.py > gpurun_out/imbalance.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu --no-configs --no-parity --e2e-steps 5 > gpurun_out/b_ncu.log 2>&1
 # full capture of one per-step launch and of the fused rollout launch (the dominant kernel, both shapes)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:b2k_step -s 6 -c 1 -o gpurun_out/step_full -f python bench.py --steps 20 --warmup 3 --no-cpu --no-configs --no-parity --e2e-steps 5 > gpurun_out/ncu_full.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:b2k_step -s 26 -c 1 -o gpurun_out/rollout_full -f python bench.py --steps 20 --warmup 3 --no-cpu --no-configs --no-parity --e2e-steps 5 > gpurun_out/ncu_rollout.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:b2k_step -s 25 -c 1 -o gpurun_out/rollout_full -f python bench.py --steps 20 --warmup 3 --no-cpu --no-configs --no-parity --e2e-steps 5 > gpurun_out/ncu_rollout.log 2>&1
 ls -la gpurun_out
