@@ -67,11 +67,12 @@ def load_profile_constants(model_name):
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
             return {"dram": t.get("rollout_dram_bytes_per_env_step", {}).get(model_name),
-                    "fp64_inst": t.get("rollout_fp64_thread_inst_per_env_step", {}).get(model_name),
+                    "fp64_pipe_pct": t.get("rollout_fp64_pipe_active_pct_elapsed", {}).get(model_name),
+                    "warp_inst": t.get("rollout_warp_inst_per_env_step", {}).get(model_name),
                     "source": f"profiles/{name}"}
         except Exception:
             continue
-    return {"dram": None, "fp64_inst": None, "source": None}
+    return {"dram": None, "fp64_pipe_pct": None, "warp_inst": None, "source": None}
 
 
 def state_bytes(model):
@@ -738,12 +739,12 @@ def main():
         prof = load_profile_constants(args.model)
         fp64 = {"peak_measured_tflops": tf.value, "dfma_per_clk_per_sm": per_clk.value,
                 "peak_source": "b2mj_ubench_dfma, measured live on this GPU"}
-        if prof["fp64_inst"]:
-            ach = 2.0 * prof["fp64_inst"] * nenv * K / kernel_s / 1e12
-            fp64.update(achieved_tflops=ach, frac=ach / tf.value,
-                        fp64_thread_inst_per_env_step=prof["fp64_inst"],
-                        inst_source=f"PROFILE CONSTANT ({prof['source']}: ncu smsp__sass_thread_inst_executed_op_fp64 of the "
-                                    "rollout launch / env-steps), counted as 2 flop each")
+        if prof["fp64_pipe_pct"]:
+            fp64.update(frac=prof["fp64_pipe_pct"] / 100.0, achieved_tflops=tf.value * prof["fp64_pipe_pct"] / 100.0,
+                        warp_inst_per_env_step=prof["warp_inst"],
+                        frac_source=f"PROFILE CONSTANT ({prof['source']}: ncu sm__pipe_fp64_cycles_active, % of elapsed cycles, of "
+                                    "the rollout launch) -- the share of the FP64 pipe's issue capacity the kernel uses; "
+                                    "achieved_tflops = that share x the peak measured live")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
