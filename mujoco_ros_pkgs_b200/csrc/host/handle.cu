@@ -251,8 +251,9 @@ static int check_supported(const b2mjModel* m) {
       set_error("rangefinder sensors need a ray caster: not implemented");
       return B2MJ_EUNSUPPORTED;
     }
-  if (m->opt.integrator != B2MJ_INT_EULER && m->opt.integrator != B2MJ_INT_RK4) {
-    set_error("implicit / implicitfast integrators are not implemented (Euler and RK4 are)");
+  if (m->opt.integrator != B2MJ_INT_EULER && m->opt.integrator != B2MJ_INT_RK4 && m->opt.integrator != B2MJ_INT_IMPLICIT &&
+      m->opt.integrator != B2MJ_INT_IMPLICITFAST) {
+    set_error("unknown integrator");
     return B2MJ_EUNSUPPORTED;
   }
   if (m->opt.solver != B2MJ_SOL_PGS && m->opt.solver != B2MJ_SOL_NEWTON && m->opt.solver != B2MJ_SOL_CG) {
@@ -324,7 +325,7 @@ static int make_layout(Handle* h) {
   // team mode (kernels/team.cuh): wide Newton models get one env per CTA and 8 warps; H then has an odd leading dimension
   d.team_warps = (newton && nv >= B2K_TEAM_MIN_NV && !getenv("B2MJ_NO_TEAM")) ? B2K_TEAM_WARPS : 1;
   if (d.team_warps > 1 && getenv("B2MJ_TEAM_WARPS")) d.team_warps = std::max(2, std::min(16, atoi(getenv("B2MJ_TEAM_WARPS"))));
-  d.ldh = d.team_warps > 1 ? (nv | 1) : nv;
+  d.ldh = nv | 1;  // odd: lanes walking a column (or owning a row each) hit distinct shared-memory banks
   xs[XF_NEWTON_H] = newton ? nv * d.ldh : 0;
   xs[XF_JCOLS] = d.team_warps > 1 ? (m->njmax * 17 + 7) / 8 : 0;
   xs[XF_CONTACT_H] = (newton && m->opt.cone == B2MJ_CONE_ELLIPTIC) ? 36 * m->nconmax : 0;
@@ -345,6 +346,9 @@ static int make_layout(Handle* h) {
   xs[XF_PRIMAL] = pgs ? 0 : 8 * nv;
   xs[XF_EFC_AR] = pgs ? m->njmax * (m->njmax + 4) : 0;
   xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * (m->njmax + 4), 384) : 0;  // nefc <= 17 stays on chip
+  const bool implicit_full = m->opt.integrator == B2MJ_INT_IMPLICIT;
+  xs[XF_IMPL_LU] = implicit_full ? nv * nv : 0;
+  xs[XF_IMPL_D] = implicit_full ? 6 * m->nbody * nv : 0;
   // xfrc_applied / mocap live in their own HBM arrays (read only when the surface is enabled)
   d.fsize[B2MJ_F_XFRC_APPLIED] = 0;
 
@@ -353,6 +357,7 @@ static int make_layout(Handle* h) {
   // global arena (L2) when the per-env footprint would starve occupancy
   std::vector<char> cold(B2MJ_NFIELD, 0), xcold(XF_COUNT, 0);
   xcold[XF_EFC_AR] = 1;
+  xcold[XF_IMPL_LU] = xcold[XF_IMPL_D] = 1;  // once-per-step matrices of the implicit integrator
   // API-only fields (read back only through an arena dump) never occupy shared memory
   cold[B2MJ_F_XIMAT] = 1;
   if (!d.need_rnepost) cold[B2MJ_F_CACC] = cold[B2MJ_F_CFRC_INT] = cold[B2MJ_F_CFRC_EXT] = 1;
@@ -558,7 +563,7 @@ static int make_layout(Handle* h) {
     static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
                                    "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",
                                    "SUBTREE_ANGMOM", "BODYVEL", "RK_X0", "RK_XF", "RK_F", "RK_DX", "SCRATCH", "QW", "QHW",
-                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS"};
+                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS", "IMPL_LU", "IMPL_D"};
     fprintf(stderr, "[b2mj layout] record %d doubles; shared arena %d doubles + %d ints per env\n", d.rec_end, d.arena_s_doubles,
             d.arena_s_ints);
     for (int f = 0; f < B2MJ_NFIELD; f++)

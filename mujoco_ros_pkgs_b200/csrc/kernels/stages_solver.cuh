@@ -583,34 +583,37 @@ __device__ __forceinline__ double dot_warp(const Env e, const double* a, const d
 template <bool SM>
 __device__ __forceinline__ double* newtonH(const Env e) { return SM ? e.X(XF_NEWTON_H) : e.XG(XF_NEWTON_H); }
 
+// Right-looking Cholesky, lane i owns row i of the trailing block: per pivot the column is scaled, then every lane
+// updates its own row entries (j < k <= i) in a rolled loop whose iterations are independent -- one broadcast read of
+// L(k, j), one read-modify-write of A(i, k) -- so the only serial chain per pivot is pivot -> sqrt -> reciprocal ->
+// column.  The left-looking form it replaces paid a 5-round shuffle reduction plus a dependent dot product per pivot
+// (profiles/r2b_ncu_c4_lines.txt: 9 % of the C4 step).  ld is odd (handle.cu), so the lanes' rows fall in distinct banks.
 template <bool SM>
-__device__ __noinline__ void cholFactor_warp(const Env e, int n, double mindiag) {
+__device__ __noinline__ void cholFactor_warp(const Env e, int n, int ld, double mindiag) {
   double* A = newtonH<SM>(e);
   double* invd = e.X(XF_PRIMAL) + 7 * n;
   B2K_NOUNROLL for (int j = 0; j < n; j++) {
-    const double* Aj = A + j * n;
-    double p = 0;
-    B2K_NOUNROLL for (int k = e.lane; k < j; k += B2K_G) p += Aj[k] * Aj[k];
-    double s = Aj[j] - warpSum(e.mask, p);
+    double s = A[j * ld + j];
     if (s < mindiag) s = mindiag;
     const double ljj = sqrt(s), inv = 1 / ljj;
+    B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += B2K_G) A[i * ld + j] *= inv;
+    WSYNC();
+    if (e.lane == 0) { A[j * ld + j] = ljj; invd[j] = inv; }
+    const double* Lj = A + j;  // column j: L(k, j) = Lj[k * ld]
     B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += B2K_G) {
-      const double* Ai = A + i * n;
-      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-      int k = 0;
-      B2K_NOUNROLL for (; k + 4 <= j; k += 4) {
-        t0 += Ai[k] * Aj[k];
-        t1 += Ai[k + 1] * Aj[k + 1];
-        t2 += Ai[k + 2] * Aj[k + 2];
-        t3 += Ai[k + 3] * Aj[k + 3];
+      double* Ai = A + i * ld;
+      const double lij = Ai[j];
+      int k = j + 1;
+      B2K_NOUNROLL for (; k + 2 <= i + 1; k += 2) {
+        const double a0 = Ai[k] - lij * Lj[k * ld];
+        const double a1 = Ai[k + 1] - lij * Lj[(k + 1) * ld];
+        Ai[k] = a0;
+        Ai[k + 1] = a1;
       }
-      B2K_NOUNROLL for (; k < j; k++) t0 += Ai[k] * Aj[k];
-      A[i * n + j] = (Ai[j] - ((t0 + t1) + (t2 + t3))) * inv;
+      if (k <= i) Ai[k] -= lij * Lj[k * ld];
     }
     WSYNC();
-    if (e.lane == 0) { A[j * n + j] = ljj; invd[j] = inv; }
   }
-  WSYNC();
 }
 
 // x = inv(L L') b with the triangular sweeps held in registers: lane k owns entries k, k+32, k+64, k+96 (n <= 128).
@@ -707,6 +710,64 @@ __device__ __noinline__ void primalUpdate(const Env e, PrimalCtx& c, int* change
   c.cost += c.gauss;
 }
 
+// J' D J for models of up to 32 dofs: every lane keeps its share of the lower triangle (NI entries, lane-strided) in
+// registers and the constraint rows are visited ONCE, in order, by the whole warp.  Per row the lane issues the loads of
+// all its entries back to back, so the L2 / shared-memory latency of efc_J, efc_D and efc_state is paid once per row
+// instead of once per (entry, row) as in the entry-outer loop this replaces (profiles/r2b_ncu_c4_lines.txt: that loop was
+// 17.7 % of the C4 step, almost all of it long-scoreboard stalls).  Each entry still accumulates its rows in increasing
+// order with the same expression, so the result is bitwise unchanged.
+template <int NI>
+__device__ __forceinline__ void hessianJTDJ_reg(const Env e, const PrimalCtx& c, const EfcPtrs& P, double* H, int ld,
+                                                const int* c_dim, const double* cH) {
+  const int nv = c.nv, nefc = c.nefc;
+  const int ntri = nv * (nv + 1) / 2;
+  // passes of 32 * NI entries (one pass up to nv = 24, two up to nv = 34): bounded register use, no spills
+  B2K_NOUNROLL for (int base = 0; base < ntri; base += 32 * NI) {
+    double s[NI];
+    unsigned ij[NI];  // entry (i, j <= i) packed as i | j << 8
+#pragma unroll
+    for (int k = 0; k < NI; k++) {
+      const int idx = base + e.lane + 32 * k;
+      int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+      while (i * (i + 1) / 2 > idx) i--;
+      while ((i + 1) * (i + 2) / 2 <= idx) i++;
+      const int j = idx - i * (i + 1) / 2;
+      const bool ok = idx < ntri;
+      ij[k] = ok ? (unsigned)i | ((unsigned)j << 8) : 0u;
+      s[k] = ok ? H[i * ld + j] : 0.0;
+    }
+    B2K_NOUNROLL for (int r = 0; r < nefc; r++) {
+      const int st = P.state[r];
+      if (st == B2MJ_CSTATE_QUADRATIC) {
+        const double Dr = P.D[r];
+        const double* Jr = P.J + r * nv;
+#pragma unroll
+        for (int k = 0; k < NI; k++) s[k] += Dr * Jr[ij[k] & 255u] * Jr[ij[k] >> 8];
+      } else if (st == B2MJ_CSTATE_CONE) {
+        const int con = P.id[r], dim = c_dim[con];
+        const double* Hc = cH + 36 * con;
+#pragma unroll
+        for (int k = 0; k < NI; k++) {
+          double sk = s[k];
+          const int oi = (int)(ij[k] & 255u), oj = (int)(ij[k] >> 8);
+          B2K_NOUNROLL for (int a = 0; a < dim; a++) {
+            const double Ja = P.J[(r + a) * nv + oi];
+            if (Ja == 0) continue;
+            double u = 0;
+            B2K_NOUNROLL for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + oj];
+            sk += Ja * u;
+          }
+          s[k] = sk;
+        }
+        r += dim - 1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NI; k++)
+      if (base + e.lane + 32 * k < ntri) H[(ij[k] & 255u) * ld + (ij[k] >> 8)] = s[k];
+  }
+}
+
 // H = M + J' diag(D_active) J (+ cone blocks), then Cholesky
 template <bool SM>
 __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
@@ -715,17 +776,17 @@ __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
     team_call(e, TEAM_HESSIAN_CHOL, c.nefc, c.cone ? 1 : 0);
     return;
   }
-  const int nv = c.nv, nefc = c.nefc;
+  const int nv = c.nv, nefc = c.nefc, ld = m.ldh;
   EfcPtrs P = efcPtrs(e);
   P.J = const_cast<double*>(solveJ(e));  // active rows from the shared-memory window when staged
   const double* qM = e.D(B2MJ_F_QM);
   double* H = newtonH<SM>(e);
-  FORL(k, nv * nv) H[k] = 0;
+  FORL(k, nv * ld) H[k] = 0;
   WSYNC();
   FORL(t, m.nM) {
     const int i = m.M_row[t], j = m.M_col[t];
-    H[i * nv + j] = qM[t];
-    H[j * nv + i] = qM[t];
+    H[i * ld + j] = qM[t];
+    H[j * ld + i] = qM[t];
   }
   WSYNC();
   const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
@@ -759,7 +820,7 @@ __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
         while (a * (a + 1) / 2 > idx) a--;
         while ((a + 1) * (a + 2) / 2 <= idx) a++;
         const int i = cols[a], j = cols[idx - a * (a + 1) / 2];  // cols ascending: i >= j
-        double s = H[i * nv + j];
+        double s = H[i * ld + j];
         if (st == B2MJ_CSTATE_QUADRATIC) {
           s += P.D[r] * P.J[r * nv + i] * P.J[r * nv + j];
         } else {
@@ -772,41 +833,18 @@ __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
             s += Ja * u;
           }
         }
-        H[i * nv + j] = s;
+        H[i * ld + j] = s;
       }
       WSYNC();
       r += dim - 1;
     }
-    cholFactor_warp<SM>(e, nv, B2K_MINVAL);
+    cholFactor_warp<SM>(e, nv, ld, B2K_MINVAL);
     return;
   }
 #endif
-  // one lane per lower-triangle entry (i, j <= i)
-  B2K_NOUNROLL for (int item = e.lane; item < nv * nv; item += B2K_G) {
-    const int i = item / nv, j = item - i * nv;
-    if (j > i) continue;
-    double s = H[item];
-    B2K_NOUNROLL for (int r = 0; r < nefc; r++) {
-      const int st = P.state[r];
-      if (st == B2MJ_CSTATE_QUADRATIC) {
-        s += P.D[r] * P.J[r * nv + i] * P.J[r * nv + j];
-      } else if (st == B2MJ_CSTATE_CONE) {
-        const int con = P.id[r], dim = c_dim[con];
-        const double* Hc = cH + 36 * con;
-        B2K_NOUNROLL for (int a = 0; a < dim; a++) {
-          const double Ja = P.J[(r + a) * nv + i];
-          if (Ja == 0) continue;
-          double u = 0;
-          B2K_NOUNROLL for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + j];
-          s += Ja * u;
-        }
-        r += dim - 1;
-      }
-    }
-    H[item] = s;
-  }
+  hessianJTDJ_reg<10>(e, c, P, H, ld, c_dim, cH);
   WSYNC();
-  cholFactor_warp<SM>(e, nv, B2K_MINVAL);
+  cholFactor_warp<SM>(e, nv, ld, B2K_MINVAL);
 }
 __device__ __forceinline__ void primalHessian(const Env e, PrimalCtx& c) {
   if (c_dm.xoff_s[XF_NEWTON_H] >= 0) primalHessianT<true>(e, c);

@@ -250,3 +250,24 @@ def rollout_ex(model, state, nsteps, ctrl=None, nthreads=1, want_sensors=False, 
         a.hw_control_every = hw_control_every
     secs = lib.orc_rollout_ex(model.ptr, C.byref(a))
     return secs, st, sens
+
+
+# ---- implicit integrators: dense velocity derivatives after a forward pass (oracle/orc_implicit.cpp) ----
+lib.orc_rne_vel_derivative.argtypes = [_vp, _vp, _vp]
+lib.orc_smooth_vel_derivative.argtypes = [_vp, _vp, C.c_int, _vp]
+
+
+def rne_vel_derivative(oracle: Oracle) -> np.ndarray:
+    """d qfrc_bias / d qvel, dense [nv][nv], at the oracle's current state (call forward() first)."""
+    nv = oracle.model.nv
+    out = np.zeros((nv, nv))
+    lib.orc_rne_vel_derivative(oracle.model.ptr, oracle._d, out.ctypes.data)
+    return out
+
+
+def smooth_vel_derivative(oracle: Oracle, flg_bias: bool) -> np.ndarray:
+    """mjd_smooth_vel: qDeriv on MuJoCo's ancestor/descendant sparsity pattern, dense [nv][nv]."""
+    nv = oracle.model.nv
+    out = np.zeros((nv, nv))
+    lib.orc_smooth_vel_derivative(oracle.model.ptr, oracle._d, int(flg_bias), out.ctypes.data)
+    return out

@@ -35,6 +35,10 @@ void orc_step2(const b2mjModel* m, OrcData* d);        /* mj_step2: actuation ..
 void orc_set_callbacks(OrcData* d, orc_callback control, orc_callback passive, void* user);
 int orc_callback_counts(const OrcData* d, int* ncontrol, int* npassive);
 
+/* implicit integrators (orc_implicit.cpp): dense [nv][nv] velocity derivatives after a forward pass (test hooks) */
+void orc_rne_vel_derivative(const b2mjModel* m, const OrcData* d, double* dbias);
+void orc_smooth_vel_derivative(const b2mjModel* m, const OrcData* d, int flg_bias, double* qderiv);
+
 /* field access by b2mj_field id; count = number of elements copied; returns per-env element count */
 int orc_get(const b2mjModel* m, const OrcData* d, int field, void* dst, int max_elems);
 int orc_set(const b2mjModel* m, OrcData* d, int field, const void* src, int nelems);

@@ -439,6 +439,13 @@ static void euler(const b2mjModel* m, OrcData* d) {
   advance(m, d, d->act_dot, qacc.data(), nullptr);
 }
 
+// mj_implicit: (M - h qDeriv) qacc = qfrc_smooth + qfrc_constraint (orc_implicit.cpp), then mj_advance
+static void implicitIntegrate(const b2mjModel* m, OrcData* d) {
+  std::vector<double> qacc(m->nv);
+  implicitQacc(m, d, qacc.data());
+  advance(m, d, d->act_dot, qacc.data(), nullptr);
+}
+
 // mj_RungeKutta(4): classical RK4; stages 2-4 skip sensors; control callback fires in every stage
 static void rungeKutta4(const b2mjModel* m, OrcData* d) {
   const int nq = m->nq, nv = m->nv, na = m->na;
@@ -503,6 +510,7 @@ void orc_step(const b2mjModel* m, OrcData* d) {
   forwardSkip(m, d, false, false, false);
   checkAcc(m, d);
   if (m->opt.integrator == B2MJ_INT_RK4) rungeKutta4(m, d);
+  else if (m->opt.integrator == B2MJ_INT_IMPLICIT || m->opt.integrator == B2MJ_INT_IMPLICITFAST) implicitIntegrate(m, d);
   else euler(m, d);
 }
 
@@ -519,7 +527,9 @@ void orc_step2(const b2mjModel* m, OrcData* d) {
   forwardSkip(m, d, false, false, true);
   d->cb_control = saved;
   checkAcc(m, d);
-  euler(m, d);
+  // mj_step2: Euler or implicit; RK4 falls back to Euler
+  if (m->opt.integrator == B2MJ_INT_IMPLICIT || m->opt.integrator == B2MJ_INT_IMPLICITFAST) implicitIntegrate(m, d);
+  else euler(m, d);
 }
 
 double orc_rollout(const b2mjModel* m, int nenv, int nsteps, double* qpos, double* qvel, const double* ctrl,

@@ -127,4 +127,6 @@ void sensorPos(const b2mjModel* m, OrcData* d);
 void sensorVel(const b2mjModel* m, OrcData* d);
 void sensorAcc(const b2mjModel* m, OrcData* d);
 void integratePos(const b2mjModel* m, double* qpos, const double* qvel, double dt);
+// orc_implicit.cpp
+void implicitQacc(const b2mjModel* m, OrcData* d, double* qacc_out);
 }  // namespace orc

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 PGS, CG, NEWTON = 0, 1, 2
 PYR, ELL = 0, 1
-EULER, RK4 = 0, 1
+EULER, RK4, IMPLICIT, IMPLICITFAST = 0, 1, 2, 3
 
 
 @pytest.fixture(scope="module")
@@ -60,6 +60,16 @@ MATRIX = [
     ("bin.xml", PGS, PYR, None, 100, 10, 0.02, 4),                 # > 64 scalar rows
     ("bin.xml", CG, None, None, 100, 10, 0.02, 4),
     ("bin.xml", NEWTON, PYR, None, 100, 10, 0.02, 4),
+    # implicit-in-velocity integrators (stages_implicit.cuh): dense inverse path (nv <= 16), sparse L'DL path, dense LU
+    ("panda_like.xml", None, None, IMPLICITFAST, 450, 40, 0.1, 16),
+    ("panda_like.xml", None, None, IMPLICIT, 450, 40, 0.1, 16),
+    ("humanoid_like.xml", None, None, IMPLICITFAST, 120, 30, 0.02, 8),
+    ("humanoid_like.xml", None, None, IMPLICIT, 120, 30, 0.02, 8),
+    ("hand_like.xml", None, None, IMPLICITFAST, 100, 20, 0.02, 8),
+    ("hand_like.xml", None, None, IMPLICIT, 100, 20, 0.02, 8),
+    ("actuated_arm.xml", None, None, IMPLICITFAST, 50, 40, 0.2, 8),  # tendon transmission, affine gain / bias, na > 0
+    ("actuated_arm.xml", None, None, IMPLICIT, 50, 40, 0.2, 8),
+    ("bin.xml", None, None, IMPLICIT, 100, 6, 0.02, 2),              # 20 free bodies: nv = 120 dense LU
 ]
 
 
@@ -94,6 +104,77 @@ def test_solver_cone_integrator_matrix(name, solver, cone, integ, settle, nchk, 
         o.forward()
     wf = compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tol=1e-6 if cg else 1e-8, tag=tag)
     print(f"{tag}: injected-step worst {worst:.2e}, forward fields worst {wf:.2e}, max nefc {max_nefc}")
+
+
+IMPLICIT_ARM = """
+<mujoco>
+  <compiler angle="radian"/>
+  <option timestep="0.002" integrator="{integ}" gravity="0 0 -9.81"><flag contact="disable"/></option>
+  <worldbody>
+    <body pos="0 0 1">
+      <joint name="j1" type="hinge" axis="0 1 0" damping="0.7"/>
+      <geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.04" density="800"/>
+      <body pos="0.4 0 0">
+        <joint name="j2" type="hinge" axis="0 0 1" damping="0.3"/>
+        <geom type="capsule" fromto="0 0 0 0.3 0.1 0" size="0.03" density="800"/>
+        <body pos="0.3 0.1 0">
+          <joint name="j3" type="ball" damping="0.05"/>
+          <geom type="box" size="0.05 0.08 0.03" pos="0.05 0 0.02" density="900"/>
+        </body>
+      </body>
+    </body>
+    <body pos="0 1 1">
+      <freejoint/>
+      <geom type="box" size="0.1 0.2 0.05" density="500"/>
+      <body pos="0.2 0 0">
+        <joint name="k1" type="slide" axis="1 0 0" damping="0.2"/>
+        <geom type="sphere" size="0.05" pos="0.1 0.05 0" density="700"/>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <velocity joint="j1" kv="3.5"/>
+    <position joint="j2" kp="20" kv="1.5"/>
+    <general joint="k1" gaintype="affine" gainprm="2 0 -0.8" biastype="affine" biasprm="0 -1 -0.4"/>
+  </actuator>
+</mujoco>
+"""
+
+
+@pytest.mark.parametrize("integ", ["implicit", "implicitfast"])
+def test_implicit_integrators_free_running(integ, capi, orc, BatchSim):
+    """Ball + free + slide joints with velocity-dependent actuators (every term of mjd_smooth_vel), contact free, so a
+    300-step free-running comparison is meaningful; also through the split step (control hook between the halves)."""
+    model = capi.Model.from_xml_string(IMPLICIT_ARM.format(integ=integ))
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 9, 0.3)
+    qvel *= 10
+    rng = np.random.default_rng(2)
+    sim, split = BatchSim(model, nenv), BatchSim(model, nenv)
+    for s_ in (sim, split):
+        s_.set("qpos", qpos)
+        s_.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    worst = 0.0
+    for s in range(300):
+        if s % 20 == 0:
+            ctrl = rng.uniform(-1, 1, (nenv, model.nu))
+        sim.set("ctrl", ctrl)
+        sim.step(1)
+        split.step_begin()
+        split.set("ctrl", ctrl)
+        split.step_end()
+        for e, o in enumerate(oracles):
+            o.set("ctrl", ctrl[e])
+            o.step(1)
+        if s % 25 == 24:
+            for k in ("qpos", "qvel"):
+                g, g2 = sim.get(k), split.get(k)
+                np.testing.assert_array_equal(g, g2)
+                for e, o in enumerate(oracles):
+                    worst = max(worst, rel(g[e], o.get(k)))
+            assert worst < 1e-8, (s, worst)
+    print(f"{integ}: free-running 300 steps worst {worst:.2e}")
 
 
 @pytest.mark.parametrize("integ", [EULER, RK4])
