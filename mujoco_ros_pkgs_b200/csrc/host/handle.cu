@@ -264,8 +264,9 @@ static int check_supported(const b2mjModel* m) {
     set_error("noslip post-solver is not implemented");
     return B2MJ_EUNSUPPORTED;
   }
-  if (m->opt.density != 0 || m->opt.viscosity != 0 || m->opt.wind[0] != 0 || m->opt.wind[1] != 0 || m->opt.wind[2] != 0) {
-    set_error("fluid forces (option density / viscosity / wind) are not implemented in the passive stage");
+  if ((m->opt.density > 0 || m->opt.viscosity > 0) &&
+      (m->opt.integrator == B2MJ_INT_IMPLICIT || m->opt.integrator == B2MJ_INT_IMPLICITFAST)) {
+    set_error("fluid forces with an implicit integrator need the fluid velocity derivatives (mjd_inertiaBoxFluid): not implemented");
     return B2MJ_EUNSUPPORTED;
   }
   if (m->opt.solver != B2MJ_SOL_PGS && m->nv > B2K_NEWTON_MAX_NV) {
@@ -540,7 +541,8 @@ static int make_layout(Handle* h) {
   d.ar_ovl_off = 0;
   d.ar_ovl_doubles = 0;
   if (pgs && !getenv("B2MJ_NO_AR_OVERLAY")) {
-    bool ok = true;
+    // the implicit integrator differentiates the RNE pass after the solve: it reads cinert / cdof, which the overlay reuses
+    bool ok = m->opt.integrator != B2MJ_INT_IMPLICIT;
     for (int i = 0; i < m->nsensor && ok; i++) {
       const int t = m->sensor_type[i];
       if (m->sensor_needstage[i] == B2MJ_STAGE_ACC && t != B2MJ_SENS_ACTUATORFRC && t != B2MJ_SENS_JOINTACTFRC &&

@@ -663,6 +663,58 @@ __device__ __noinline__ void stage_passive(const Env e) {
       applyFT_warp(e, force, torque, xipos + 3 * i, i, qp);
     }
   }
+  // body-level viscosity, lift and drag (mj_inertiaBoxFluidModel; option density / viscosity / wind, which the reference
+  // exposes at mujoco_ros/src/viewer.cpp:597-600): one lane per body forms the world-frame wrench at the body's centre of
+  // mass, the warp then projects each wrench onto the body's dof chain
+  if (m.opt.viscosity > 0 || m.opt.density > 0) {
+    const double* xipos = e.D(B2MJ_F_XIPOS);
+    const double* xquat = e.D(B2MJ_F_XQUAT);
+    const double* cvel = e.D(B2MJ_F_CVEL);
+    const double* com = e.D(B2MJ_F_SUBTREE_COM);
+    double* buf = e.X(XF_SCRATCH);  // [nbody][6]: torque, force
+    const double rho = m.opt.density, mu = m.opt.viscosity, kPi = 3.14159265358979323846;
+    FORL(i, m.nbody) {
+      double lfrc[6] = {0, 0, 0, 0, 0, 0}, bfrc[6] = {0, 0, 0, 0, 0, 0};
+      const double mass = m.body_mass[i];
+      if (i && mass >= B2K_MINVAL) {
+        const double* inertia = m.body_inertia + 3 * i;
+        double box[3], qi[4], ximat[9], lvel[6], wind[6] = {0, 0, 0, 0, 0, 0}, lwind[6];
+        box[0] = sqrt(fmax(B2K_MINVAL, inertia[1] + inertia[2] - inertia[0]) / mass * 6.0);
+        box[1] = sqrt(fmax(B2K_MINVAL, inertia[0] + inertia[2] - inertia[1]) / mass * 6.0);
+        box[2] = sqrt(fmax(B2K_MINVAL, inertia[0] + inertia[1] - inertia[2]) / mass * 6.0);
+        mulQuat(qi, xquat + 4 * i, m.body_iquat + 4 * i);
+        quat2Mat(ximat, qi);
+        const double* c0 = com + 3 * m.body_rootid[i];
+        transformSpatial(lvel, cvel + 6 * i, 0, xipos + 3 * i, c0, ximat);
+        wind[3] = m.opt.wind[0]; wind[4] = m.opt.wind[1]; wind[5] = m.opt.wind[2];
+        transformSpatial(lwind, wind, 0, xipos + 3 * i, c0, ximat);
+        for (int k = 0; k < 3; k++) lvel[3 + k] -= lwind[3 + k];
+        if (mu > 0) {
+          const double diam = (box[0] + box[1] + box[2]) / 3.0;
+          scl3(lfrc, lvel, -kPi * diam * diam * diam * mu);
+          scl3(lfrc + 3, lvel + 3, -3.0 * kPi * diam * mu);
+        }
+        if (rho > 0) {
+          lfrc[3] -= 0.5 * rho * box[1] * box[2] * fabs(lvel[3]) * lvel[3];
+          lfrc[4] -= 0.5 * rho * box[0] * box[2] * fabs(lvel[4]) * lvel[4];
+          lfrc[5] -= 0.5 * rho * box[0] * box[1] * fabs(lvel[5]) * lvel[5];
+          const double b0 = box[0] * box[0] * box[0] * box[0], b1 = box[1] * box[1] * box[1] * box[1],
+                       b2 = box[2] * box[2] * box[2] * box[2];
+          lfrc[0] -= rho * box[0] * (b1 + b2) * fabs(lvel[0]) * lvel[0] / 64.0;
+          lfrc[1] -= rho * box[1] * (b0 + b2) * fabs(lvel[1]) * lvel[1] / 64.0;
+          lfrc[2] -= rho * box[2] * (b0 + b1) * fabs(lvel[2]) * lvel[2] / 64.0;
+        }
+        rotVecMat(bfrc, lfrc, ximat);
+        rotVecMat(bfrc + 3, lfrc + 3, ximat);
+      }
+      for (int k = 0; k < 6; k++) buf[6 * i + k] = bfrc[k];
+    }
+    WSYNC();
+    B2K_NOUNROLL for (int i = 1; i < m.nbody; i++) {
+      if (m.body_mass[i] < B2K_MINVAL) continue;
+      applyFT_warp(e, buf + 6 * i + 3, buf + 6 * i, xipos + 3 * i, i, qp);
+    }
+  }
 }
 
 // mj_rne(flg_acc = 0): bias forces, without the tree recursions: cacc of a body is the sum of

@@ -319,6 +319,8 @@ void comVel(const b2mjModel* m, OrcData* d) {
   }
 }
 
+static void inertiaBoxFluid(const b2mjModel* m, OrcData* d, int i);
+
 // mj_passive: springs, dampers, then the passive callback (mjcb_passive, reference mujoco_env.h:247-251)
 void passive(const b2mjModel* m, OrcData* d) {
   const int nv = m->nv;
@@ -365,6 +367,11 @@ void passive(const b2mjModel* m, OrcData* d) {
       applyFT(m, d, force, torque, d->xipos + 3 * i, i, d->qfrc_passive);
     }
   }
+  // body-level viscosity, lift and drag (inertia-box fluid model); the reference exposes density / viscosity / wind in
+  // its option panel (mujoco_ros/src/viewer.cpp:597-600)
+  if (m->opt.viscosity > 0 || m->opt.density > 0)
+    for (int i = 1; i < m->nbody; i++)
+      if (m->body_mass[i] >= MINVAL) inertiaBoxFluid(m, d, i);
   if (d->cb_passive) {
     d->n_passive_calls++;
     d->cb_passive(m, d, d->cb_user);
@@ -535,6 +542,39 @@ void objectVelocity(const b2mjModel* m, const OrcData* d, int objtype, int objid
   const double *pos, *rot;
   object_frame(m, d, objtype, objid, &bodyid, &pos, &rot);
   transformSpatial(res, d->cvel + 6 * bodyid, 0, pos, d->subtree_com + 3 * m->body_rootid[bodyid], flg_local ? rot : nullptr);
+}
+
+// mj_inertiaBoxFluidModel: viscous drag of the sphere equivalent to the body's inertia box, quadratic lift / drag on
+// the box faces, relative to the wind; applied at the body's centre of mass
+static void inertiaBoxFluid(const b2mjModel* m, OrcData* d, int i) {
+  const double* inertia = m->body_inertia + 3 * i;
+  const double mass = m->body_mass[i], rho = m->opt.density, mu = m->opt.viscosity, kPi = 3.14159265358979323846;
+  double box[3], lvel[6], wind[6] = {0, 0, 0, 0, 0, 0}, lwind[6], lfrc[6] = {0, 0, 0, 0, 0, 0}, bfrc[6];
+  box[0] = std::sqrt(std::fmax(MINVAL, inertia[1] + inertia[2] - inertia[0]) / mass * 6.0);
+  box[1] = std::sqrt(std::fmax(MINVAL, inertia[0] + inertia[2] - inertia[1]) / mass * 6.0);
+  box[2] = std::sqrt(std::fmax(MINVAL, inertia[0] + inertia[1] - inertia[2]) / mass * 6.0);
+  objectVelocity(m, d, B2MJ_OBJ_BODY, i, lvel, 1);
+  copy3(wind + 3, m->opt.wind);
+  transformSpatial(lwind, wind, 0, d->xipos + 3 * i, d->subtree_com + 3 * m->body_rootid[i], d->ximat + 9 * i);
+  for (int k = 0; k < 3; k++) lvel[3 + k] -= lwind[3 + k];
+  if (mu > 0) {
+    const double diam = (box[0] + box[1] + box[2]) / 3.0;
+    scl3(lfrc, lvel, -kPi * diam * diam * diam * mu);
+    scl3(lfrc + 3, lvel + 3, -3.0 * kPi * diam * mu);
+  }
+  if (rho > 0) {
+    lfrc[3] -= 0.5 * rho * box[1] * box[2] * std::fabs(lvel[3]) * lvel[3];
+    lfrc[4] -= 0.5 * rho * box[0] * box[2] * std::fabs(lvel[4]) * lvel[4];
+    lfrc[5] -= 0.5 * rho * box[0] * box[1] * std::fabs(lvel[5]) * lvel[5];
+    const double b0 = box[0] * box[0] * box[0] * box[0], b1 = box[1] * box[1] * box[1] * box[1],
+                 b2 = box[2] * box[2] * box[2] * box[2];
+    lfrc[0] -= rho * box[0] * (b1 + b2) * std::fabs(lvel[0]) * lvel[0] / 64.0;
+    lfrc[1] -= rho * box[1] * (b0 + b2) * std::fabs(lvel[1]) * lvel[1] / 64.0;
+    lfrc[2] -= rho * box[2] * (b0 + b1) * std::fabs(lvel[2]) * lvel[2] / 64.0;
+  }
+  rotVecMat(bfrc, lfrc, d->ximat + 9 * i);
+  rotVecMat(bfrc + 3, lfrc + 3, d->ximat + 9 * i);
+  applyFT(m, d, bfrc + 3, bfrc, d->xipos + 3 * i, i, d->qfrc_passive);
 }
 
 // mj_objectAcceleration (needs cacc from rnePostConstraint)

@@ -177,6 +177,32 @@ def test_implicit_integrators_free_running(integ, capi, orc, BatchSim):
     print(f"{integ}: free-running 300 steps worst {worst:.2e}")
 
 
+@pytest.mark.parametrize("name,integ", [("humanoid_like.xml", EULER), ("hand_like.xml", RK4), ("bin.xml", EULER)])
+def test_fluid_forces(name, integ, capi, orc, BatchSim):
+    """option density / viscosity / wind (viewer.cpp:597-600): inertia-box fluid model in the passive stage."""
+    model = variant(capi, name, integrator=integ)
+    model.opt.density, model.opt.viscosity = 40.0, 0.9
+    model.opt.wind[0], model.opt.wind[1], model.opt.wind[2] = 1.5, -0.7, 0.3
+    nenv = 4
+    qpos, qvel = perturbed(model, nenv, 11, 0.05)
+    qvel *= 20
+    sim = BatchSim(model, nenv)
+    sim.keep_intermediates(True)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    sim.forward()
+    for o in oracles:
+        o.forward()
+    gp = sim.get("qfrc_passive")
+    for e, o in enumerate(oracles):
+        assert np.max(np.abs(o.get("qfrc_passive"))) > 1e-3
+        assert rel(gp[e], o.get("qfrc_passive")) < 1e-11, (e, rel(gp[e], o.get("qfrc_passive")))
+    rng = np.random.default_rng(5)
+    worst, _ = injected_steps(model, sim, oracles, 30, rng, tag=f"fluid:{name}")
+    print(f"fluid {name}: injected-step worst {worst:.2e}")
+
+
 @pytest.mark.parametrize("integ", [EULER, RK4])
 def test_activation_dynamics(integ, capi, orc, BatchSim):
     """na > 0: integrator / filter activation dynamics, actlimited clamp, affine gain + bias, forcerange, tendon
