@@ -63,7 +63,7 @@ enum { B2MJ_GAIN_FIXED = 0, B2MJ_GAIN_AFFINE = 1 };
 enum { B2MJ_BIAS_NONE = 0, B2MJ_BIAS_AFFINE = 1 };
 enum { B2MJ_OBJ_UNKNOWN = 0, B2MJ_OBJ_BODY = 1, B2MJ_OBJ_XBODY = 2, B2MJ_OBJ_JOINT = 3, B2MJ_OBJ_DOF = 4,
        B2MJ_OBJ_GEOM = 5, B2MJ_OBJ_SITE = 6, B2MJ_OBJ_CAMERA = 7, B2MJ_OBJ_TENDON = 16,
-       B2MJ_OBJ_ACTUATOR = 17, B2MJ_OBJ_SENSOR = 18, B2MJ_OBJ_EQUALITY = 15 };
+       B2MJ_OBJ_ACTUATOR = 17, B2MJ_OBJ_SENSOR = 18, B2MJ_OBJ_EQUALITY = 15, B2MJ_OBJ_KEY = 21 };
 enum { B2MJ_STAGE_NONE = 0, B2MJ_STAGE_POS = 1, B2MJ_STAGE_VEL = 2, B2MJ_STAGE_ACC = 3 };
 enum { B2MJ_DATATYPE_REAL = 0, B2MJ_DATATYPE_POSITIVE = 1, B2MJ_DATATYPE_AXIS = 2, B2MJ_DATATYPE_QUATERNION = 3 };
 /* sensor enum: the 36 types the reference's sensor plugin names (mujoco_sensor_handler_plugin.cpp:70-105) */
@@ -140,7 +140,8 @@ typedef struct b2mjStatistic {
 #define B2MJ_MODEL_SIZES(X)                                                                       \
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(nwrap) X(neq)          \
   X(nsensor) X(nsensordata) X(nM) X(nmocap) X(nexclude) X(ncollpair) X(nconmax) X(njmax)          \
-  X(nnames) X(nlevel) X(ntree)
+  X(nnames) X(nlevel) X(ntree)                                                                    \
+  X(nkey) X(nkeyq) X(nkeyv) X(nkeya) X(nkeyu) X(nkeymp) X(nkeymq) /* keyframes; nkeyq = nkey*nq, ... (flat arrays) */
 
 /* X(ctype, name, rows(size field), cols) */
 #define B2MJ_MODEL_ARRAYS(X)                                                                      \
@@ -202,6 +203,9 @@ typedef struct b2mjStatistic {
   X(int, name_bodyadr, nbody, 1) X(int, name_jntadr, njnt, 1) X(int, name_geomadr, ngeom, 1)      \
   X(int, name_siteadr, nsite, 1) X(int, name_tendonadr, ntendon, 1)                               \
   X(int, name_actuatoradr, nu, 1) X(int, name_sensoradr, nsensor, 1) X(int, name_eqadr, neq, 1)   \
+  X(double, key_time, nkey, 1) X(double, key_qpos, nkeyq, 1) X(double, key_qvel, nkeyv, 1)        \
+  X(double, key_act, nkeya, 1) X(double, key_ctrl, nkeyu, 1) X(double, key_mpos, nkeymp, 1)       \
+  X(double, key_mquat, nkeymq, 1) X(int, name_keyadr, nkey, 1)                                    \
   X(char, names, nnames, 1)
 
 typedef struct b2mjModel {
@@ -260,6 +264,13 @@ int b2mj_field_by_name(const char* name); /* -1 if unknown */
 int b2mj_model_from_xml_file(const char* path, b2mjModel** out);
 int b2mj_model_from_xml_string(const char* xml, b2mjModel** out);
 void b2mj_model_free(b2mjModel* m);
+/* Binary model files: the counterpart of the reference's .mjb load path (mj_loadModel, mujoco_env.cpp:771-911 picks
+ * it by file extension).  The format is this library's own (header "B2MJB", version, size fields, option, statistic,
+ * then every array of B2MJ_MODEL_ARRAYS) -- NOT MuJoCo's .mjb layout, which only libmujoco can produce. */
+int b2mj_model_save_binary(const b2mjModel* m, const char* path);
+int b2mj_model_load_binary(const char* path, b2mjModel** out);
+/* file loader that dispatches on the extension like the reference: ".b2mjb" -> binary, anything else -> MJCF XML */
+int b2mj_model_from_file(const char* path, b2mjModel** out);
 /* re-derive qpos0-dependent constants after mass / geometry edits (replaces mj_setConst,
  * reference callbacks.cpp:254,582) */
 int b2mj_model_set_const(b2mjModel* m);
@@ -288,6 +299,10 @@ int b2mj_set_stream(b2mj_handle* h, void* cuda_stream);
 
 /* mj_resetData semantics per env (mujoco_env.cpp:252); env_mask NULL = all, else nenv bytes (host) */
 int b2mj_reset(b2mj_handle* h, const uint8_t* env_mask);
+/* mj_resetDataKeyframe per env: mj_resetData, then time / qpos / qvel / act / ctrl / mocap pose from keyframe `key`
+ * (<keyframe><key .../>) of the model.  The reference reaches keyframes through its viewer (viewer.cpp:1735-1751:
+ * "load key" copies key_qpos / key_qvel / key_act / key_mpos / key_mquat into mjData).  env_mask as in b2mj_reset. */
+int b2mj_reset_keyframe(b2mj_handle* h, int key, const uint8_t* env_mask);
 /* mj_forward on all envs (mujoco_env.cpp:329,621): all stages, no integration */
 int b2mj_forward(b2mj_handle* h);
 /* nsteps x mj_step on all envs, asynchronous on the handle's stream; no host callbacks inside

@@ -74,7 +74,8 @@ class B2mjSensorNoise(C.Structure):
 # every symbol include/b2mj.h declares (tests/test_capi_symbols.py checks the header against this list)
 EXPORTS = [
     "b2mj_field_size", "b2mj_field_name", "b2mj_field_by_name", "b2mj_model_from_xml_file",
-    "b2mj_model_from_xml_string", "b2mj_model_free", "b2mj_model_set_const", "b2mj_name2id", "b2mj_id2name",
+    "b2mj_model_from_xml_string", "b2mj_model_free", "b2mj_model_save_binary", "b2mj_model_load_binary",
+    "b2mj_model_from_file", "b2mj_reset_keyframe", "b2mj_model_set_const", "b2mj_name2id", "b2mj_id2name",
     "b2mj_model_narrays", "b2mj_model_array_info", "b2mj_model_nsizes", "b2mj_model_size_info",
     "b2mj_create", "b2mj_destroy", "b2mj_nenv", "b2mj_model", "b2mj_set_stream", "b2mj_reset",
     "b2mj_forward", "b2mj_step", "b2mj_rollout", "b2mj_step_begin", "b2mj_step_end", "b2mj_step_host", "b2mj_sync",
@@ -96,6 +97,9 @@ lib.b2mj_model_from_xml_file.argtypes = [C.c_char_p, C.POINTER(_vp)]
 lib.b2mj_model_from_xml_string.argtypes = [C.c_char_p, C.POINTER(_vp)]
 lib.b2mj_model_free.argtypes = [_vp]
 lib.b2mj_model_free.restype = None
+lib.b2mj_model_save_binary.argtypes = [_vp, C.c_char_p]
+lib.b2mj_model_load_binary.argtypes = [C.c_char_p, C.POINTER(_vp)]
+lib.b2mj_model_from_file.argtypes = [C.c_char_p, C.POINTER(_vp)]
 lib.b2mj_model_set_const.argtypes = [_vp]
 lib.b2mj_name2id.argtypes = [_vp, C.c_int, C.c_char_p]
 lib.b2mj_id2name.argtypes = [_vp, C.c_int, C.c_int]
@@ -121,7 +125,7 @@ def check(rc: int, what: str = "") -> int:
 
 # object types (b2mj.h)
 OBJ_BODY, OBJ_XBODY, OBJ_JOINT, OBJ_DOF, OBJ_GEOM, OBJ_SITE = 1, 2, 3, 4, 5, 6
-OBJ_EQUALITY, OBJ_TENDON, OBJ_ACTUATOR, OBJ_SENSOR = 15, 16, 17, 18
+OBJ_EQUALITY, OBJ_TENDON, OBJ_ACTUATOR, OBJ_SENSOR, OBJ_KEY = 15, 16, 17, 18, 21
 
 
 class Model:
@@ -171,6 +175,22 @@ class Model:
         out = _vp()
         check(lib.b2mj_model_from_xml_string(xml.encode(), C.byref(out)), "compile xml")
         return cls(out.value)
+
+    @classmethod
+    def from_file(cls, path: str) -> "Model":
+        """Extension dispatch like the reference's loader (mujoco_env.cpp:771-911): .b2mjb binary, else MJCF XML."""
+        out = _vp()
+        check(lib.b2mj_model_from_file(path.encode(), C.byref(out)), f"load {path}")
+        return cls(out.value)
+
+    @classmethod
+    def load_binary(cls, path: str) -> "Model":
+        out = _vp()
+        check(lib.b2mj_model_load_binary(path.encode(), C.byref(out)), f"load {path}")
+        return cls(out.value)
+
+    def save_binary(self, path: str):
+        check(lib.b2mj_model_save_binary(self._ptr, path.encode()), f"save {path}")
 
     def __getattr__(self, k):
         d = self.__dict__

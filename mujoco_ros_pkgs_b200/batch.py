@@ -19,6 +19,7 @@ lib.b2mj_destroy.restype = None
 lib.b2mj_nenv.argtypes = [_vp]
 lib.b2mj_set_stream.argtypes = [_vp, _vp]
 lib.b2mj_reset.argtypes = [_vp, _vp]
+lib.b2mj_reset_keyframe.argtypes = [_vp, C.c_int, _vp]
 lib.b2mj_forward.argtypes = [_vp]
 lib.b2mj_step.argtypes = [_vp, C.c_int]
 lib.b2mj_rollout.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
@@ -85,6 +86,15 @@ class BatchSim:
             m = np.ascontiguousarray(mask, dtype=np.uint8)
             assert m.size == self.nenv
             check(lib.b2mj_reset(self._h, m.ctypes.data), "reset")
+
+    def reset_keyframe(self, key: int, mask=None):
+        """mj_resetDataKeyframe on all (or the masked) envs."""
+        if mask is None:
+            check(lib.b2mj_reset_keyframe(self._h, int(key), None), "reset_keyframe")
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            assert m.size == self.nenv
+            check(lib.b2mj_reset_keyframe(self._h, int(key), m.ctypes.data), "reset_keyframe")
 
     def forward(self):
         check(lib.b2mj_forward(self._h), "forward")

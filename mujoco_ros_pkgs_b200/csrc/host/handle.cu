@@ -767,6 +767,7 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->model_blob); cudaFree(h->rec); cudaFree(h->rec_init); cudaFree(h->garena_d); cudaFree(h->garena_i);
   cudaFree(h->warning); cudaFree(h->stats); cudaFree(h->xfrc); cudaFree(h->mocap); cudaFree(h->mocap_init);
   cudaFree(h->mask_dev);
+  cudaFree(h->rec_key); cudaFree(h->mocap_key);
   cudaFree(h->prof);
   cudaFree(h->sched);
   cudaFree(h->perm);
@@ -803,6 +804,49 @@ int b2mj_reset(b2mj_handle* hh, const uint8_t* env_mask) {
   h->launches++;
   h->dump_valid = 0;
   h->in_split_step = 0;  // a reset between step_begin and step_end abandons the split step
+  if (!env_mask) h->dm.has_xfrc = 0;
+  handle_reset_plugins(h, env_mask);
+  return 0;
+}
+
+int b2mj_reset_keyframe(b2mj_handle* hh, int key, const uint8_t* env_mask) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return B2MJ_EINVAL;
+  const b2mjModel* m = h->model;
+  if (key < 0 || key >= m->nkey) {
+    set_error("b2mj_reset_keyframe: the model has " + std::to_string(m->nkey) + " keyframes, asked for " + std::to_string(key));
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  const DevModel& d = h->dm;
+  // same path as b2mj_reset with the keyframe as the template record (mj_resetData, then the key's state on top)
+  std::vector<double> rec(d.rec_pitch, 0.0);
+  for (int i = 0; i < m->nq; i++) rec[d.rec_qpos + i] = m->key_qpos[(size_t)key * m->nq + i];
+  for (int i = 0; i < m->nv; i++) rec[d.rec_qvel + i] = m->key_qvel[(size_t)key * m->nv + i];
+  for (int i = 0; i < m->na; i++) rec[d.rec_act + i] = m->key_act[(size_t)key * m->na + i];
+  for (int i = 0; i < m->nu; i++) rec[d.rec_ctrl + i] = m->key_ctrl[(size_t)key * m->nu + i];
+  rec[d.rec_time] = m->key_time[key];
+  if (!h->rec_key) CUDA_OK(cudaMalloc(&h->rec_key, (size_t)d.rec_pitch * sizeof(double)));
+  CUDA_OK(cudaMemcpyAsync(h->rec_key, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (m->nmocap) {
+    std::vector<double> mc(7 * m->nmocap);
+    for (int i = 0; i < 3 * m->nmocap; i++) mc[i] = m->key_mpos[(size_t)key * 3 * m->nmocap + i];
+    for (int i = 0; i < 4 * m->nmocap; i++) mc[3 * m->nmocap + i] = m->key_mquat[(size_t)key * 4 * m->nmocap + i];
+    if (!h->mocap_key) CUDA_OK(cudaMalloc(&h->mocap_key, mc.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(h->mocap_key, mc.data(), mc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));  // the staging vectors go out of scope
+  const unsigned char* dmask = nullptr;
+  if (env_mask) {
+    CUDA_OK(cudaMemcpyAsync(h->mask_dev, env_mask, h->nenv, cudaMemcpyHostToDevice, h->stream));
+    dmask = h->mask_dev;
+  }
+  reset_kernel<<<h->nenv, 64, 0, h->stream>>>(h->rec, h->rec_key, d.rec_pitch, h->nenv, dmask, h->warning, h->stats, h->xfrc,
+                                              6 * m->nbody, h->mocap, m->nmocap ? h->mocap_key : h->mocap_init, 7 * m->nmocap);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  h->dump_valid = 0;
+  h->in_split_step = 0;
   if (!env_mask) h->dm.has_xfrc = 0;
   handle_reset_plugins(h, env_mask);
   return 0;

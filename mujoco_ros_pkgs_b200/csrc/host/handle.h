@@ -29,6 +29,8 @@ struct Handle {
   double* xfrc = nullptr;         // [nenv][6*nbody]
   double* mocap = nullptr;        // [nenv][7*nmocap]
   double* mocap_init = nullptr;
+  double* rec_key = nullptr;      // keyframe reset templates (b2mj_reset_keyframe), allocated on first use
+  double* mocap_key = nullptr;
   unsigned char* mask_dev = nullptr;
   int* perm = nullptr;                 // [nenv] launch slot -> env, heaviest first (refreshed after every step launch)
   int perm_valid = 0;

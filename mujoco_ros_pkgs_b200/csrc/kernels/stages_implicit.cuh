@@ -2,7 +2,7 @@
 //
 // Replaces mj_implicit inside the reference's mj_step call (mujoco_ros/src/mujoco_env.cpp:498) for models that select
 // those integrators -- the reference exposes the choice in its option panel (mujoco_ros/src/viewer.cpp:579-582).
-// Row M11 of SURVEY 8(a).  Semantics restated in oracle/orc_implicit.cpp (mj_implicitSkip + mjd_smooth_vel):
+// Row M11 of SURVEY 8(a).  Semantics (mj_implicitSkip + mjd_smooth_vel of MuJoCo 2.3.7):
 //
 //   qDeriv = d(qfrc_actuator + qfrc_passive [- qfrc_bias]) / d qvel on MuJoCo's pattern "D" (dof pairs on one chain)
 //   implicitfast: (M - h qDeriv) symmetric  -> the same inverse / L'DL machinery as the Euler damping matrix qH

@@ -716,7 +716,7 @@ b2mjModel* compile(const XmlNode* root) {
   }
 
   // ---- tendons, actuators, equality, excludes, sensors: collected as nodes, resolved after ids exist
-  std::vector<const XmlNode*> tendon_nodes, act_nodes, eq_nodes, excl_nodes, sens_nodes;
+  std::vector<const XmlNode*> tendon_nodes, act_nodes, eq_nodes, excl_nodes, sens_nodes, key_nodes;
   for (auto& sec : root->children) {
     if (sec->tag == "tendon")
       for (auto& ch : sec->children) {
@@ -734,9 +734,14 @@ b2mjModel* compile(const XmlNode* root) {
       }
     else if (sec->tag == "sensor")
       for (auto& ch : sec->children) sens_nodes.push_back(ch.get());
+    else if (sec->tag == "keyframe")
+      for (auto& ch : sec->children) {
+        if (ch->tag != "key") fail(ch.get(), "only <key> is allowed inside <keyframe>");
+        key_nodes.push_back(ch.get());
+      }
     else if (sec->tag == "compiler" || sec->tag == "option" || sec->tag == "size" || sec->tag == "default" ||
              sec->tag == "worldbody" || sec->tag == "visual" || sec->tag == "asset" || sec->tag == "statistic" ||
-             sec->tag == "keyframe" || sec->tag == "custom") {
+             sec->tag == "custom") {
     } else {
       fail(sec.get(), "unsupported top-level section");
     }
@@ -756,6 +761,10 @@ b2mjModel* compile(const XmlNode* root) {
   m->ntendon = (int)tendon_nodes.size(); m->nwrap = nwrap; m->nu = (int)act_nodes.size();
   m->neq = (int)eq_nodes.size(); m->nexclude = (int)excl_nodes.size(); m->nsensor = (int)sens_nodes.size();
   m->nsensordata = nsensordata; m->nmocap = nmocap;
+  m->nkey = (int)key_nodes.size();
+  m->nkeyq = m->nkey * nq; m->nkeyv = m->nkey * nv; m->nkeyu = m->nkey * m->nu;
+  m->nkeymp = m->nkey * 3 * nmocap; m->nkeymq = m->nkey * 4 * nmocap;
+  m->nkeya = 0;  // set once the actuators are parsed (na)
 
   // nM and levels need the dof tree; names need everything: compute before allocating
   Names names;
@@ -789,7 +798,7 @@ b2mjModel* compile(const XmlNode* root) {
 
   // pre-build names so nnames is known
   std::vector<int> nb_adr(nbody), nj_adr(njnt), ng_adr(ngeom), ns_adr(nsite), nt_adr(m->ntendon), na_adr(m->nu),
-      nsn_adr(m->nsensor), ne_adr(m->neq);
+      nsn_adr(m->nsensor), ne_adr(m->neq), nk_adr(m->nkey);
   {
     int j = 0, g = 0, s = 0;
     for (int i = 0; i < nbody; i++) {
@@ -825,6 +834,8 @@ b2mjModel* compile(const XmlNode* root) {
       nsn_adr[i] = names.add(sens_nodes[i]->attr("name") ? *sens_nodes[i]->attr("name") : "");
     for (size_t i = 0; i < eq_nodes.size(); i++)
       ne_adr[i] = names.add(eq_nodes[i]->attr("name") ? *eq_nodes[i]->attr("name") : "");
+    for (size_t i = 0; i < key_nodes.size(); i++)
+      nk_adr[i] = names.add(key_nodes[i]->attr("name") ? *key_nodes[i]->attr("name") : "");
   }
   m->nnames = (int)names.buf.size();
   m->ntree = 0;
@@ -838,6 +849,7 @@ b2mjModel* compile(const XmlNode* root) {
   std::copy(na_adr.begin(), na_adr.end(), m->name_actuatoradr);
   std::copy(nsn_adr.begin(), nsn_adr.end(), m->name_sensoradr);
   std::copy(ne_adr.begin(), ne_adr.end(), m->name_eqadr);
+  std::copy(nk_adr.begin(), nk_adr.end(), m->name_keyadr);
 
   // ---- fill body / joint / dof / geom / site arrays
   {
@@ -1095,6 +1107,41 @@ b2mjModel* compile(const XmlNode* root) {
       m->actuator_actadr[i] = m->actuator_dyntype[i] == B2MJ_DYN_NONE ? -1 : na++;
     }
     m->na = na;
+  }
+
+  // ---- keyframes (mjModel key_*): unspecified parts default to the reference pose / zero, as in the MuJoCo compiler
+  if (m->nkey) {
+    m->nkeya = m->nkey * m->na;
+    std::free(m->key_act);
+    m->key_act = (double*)std::calloc(m->nkeya ? m->nkeya : 1, sizeof(double));
+    for (int k = 0; k < m->nkey; k++) {
+      const XmlNode* n = key_nodes[k];
+      AttrMap em;
+      for (auto& kv : n->attrs) em[kv.first] = kv.second;
+      A a{em, n};
+      m->key_time[k] = a.num("time", 0);
+      auto fill = [&](const char* attr, double* dst, int cnt) {
+        if (!a.has(attr)) return;
+        auto v = parse_nums(a.str(attr));
+        if ((int)v.size() != cnt)
+          fail(n, std::string("keyframe attribute '") + attr + "' needs " + std::to_string(cnt) + " numbers, got " +
+                      std::to_string(v.size()));
+        std::copy(v.begin(), v.end(), dst);
+      };
+      std::copy(m->qpos0, m->qpos0 + nq, m->key_qpos + (size_t)k * nq);
+      for (int b = 0; b < nbody; b++) {
+        const int id = m->body_mocapid[b];
+        if (id < 0) continue;
+        std::copy(m->body_pos + 3 * b, m->body_pos + 3 * b + 3, m->key_mpos + ((size_t)k * nmocap + id) * 3);
+        std::copy(m->body_quat + 4 * b, m->body_quat + 4 * b + 4, m->key_mquat + ((size_t)k * nmocap + id) * 4);
+      }
+      fill("qpos", m->key_qpos + (size_t)k * nq, nq);
+      fill("qvel", m->key_qvel + (size_t)k * nv, nv);
+      fill("act", m->key_act + (size_t)k * m->na, m->na);
+      fill("ctrl", m->key_ctrl + (size_t)k * m->nu, m->nu);
+      fill("mpos", m->key_mpos + (size_t)k * 3 * nmocap, 3 * nmocap);
+      fill("mquat", m->key_mquat + (size_t)k * 4 * nmocap, 4 * nmocap);
+    }
   }
 
   // ---- sensors

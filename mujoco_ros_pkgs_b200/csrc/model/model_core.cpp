@@ -1,6 +1,8 @@
 // model_core.cpp — b2mjModel ownership, reflection, names, field table.
 #include "model_core.h"
 
+#include <cstdio>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -191,6 +193,87 @@ void b2mj_model_free(b2mjModel* m) {
   std::free(m);
 }
 
+// ---- binary model files (the reference loads ".mjb" through mj_loadModel, mujoco_env.cpp:771-911) ----
+// layout: "B2MJB\0" | int32 version | int32 nsizes | int32 narrays | int32 sizeof(option) | int32 sizeof(statistic) |
+//         nsizes x int32 | option | statistic | per array: int64 byte count, bytes
+static const char kBinMagic[6] = {'B', '2', 'M', 'J', 'B', 0};
+
+int b2mj_model_save_binary(const b2mjModel* m, const char* path) {
+  if (!m || !path) { set_error("b2mj_model_save_binary: null argument"); return B2MJ_EINVAL; }
+  FILE* f = std::fopen(path, "wb");
+  if (!f) { set_error(std::string("cannot open '") + path + "' for writing"); return B2MJ_EINVAL; }
+  bool ok = std::fwrite(kBinMagic, 1, 6, f) == 6;
+  auto put32 = [&](int v) { ok = ok && std::fwrite(&v, sizeof(int), 1, f) == 1; };
+  put32(B2MJ_VERSION);
+  put32(b2mj_model_nsizes());
+  put32(b2mj_model_narrays());
+  put32((int)sizeof(b2mjOption));
+  put32((int)sizeof(b2mjStatistic));
+#define X(n) put32(m->n);
+  B2MJ_MODEL_SIZES(X)
+#undef X
+  ok = ok && std::fwrite(&m->opt, sizeof(b2mjOption), 1, f) == 1;
+  ok = ok && std::fwrite(&m->stat, sizeof(b2mjStatistic), 1, f) == 1;
+#define X(t, n, r, c)                                                                   \
+  {                                                                                     \
+    const long long bytes = (long long)sizeof(t) * std::max(m->r, 0) * (long long)(c);  \
+    ok = ok && std::fwrite(&bytes, sizeof(bytes), 1, f) == 1;                           \
+    if (bytes) ok = ok && std::fwrite(m->n, 1, (size_t)bytes, f) == (size_t)bytes;      \
+  }
+  B2MJ_MODEL_ARRAYS(X)
+#undef X
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) { set_error(std::string("write error on '") + path + "'"); return B2MJ_EINVAL; }
+  return 0;
+}
+
+int b2mj_model_load_binary(const char* path, b2mjModel** out) {
+  if (!path || !out) { set_error("b2mj_model_load_binary: null argument"); return B2MJ_EINVAL; }
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { set_error(std::string("cannot open '") + path + "'"); return B2MJ_EINVAL; }
+  auto bad = [&](const std::string& why, b2mjModel* m) {
+    std::fclose(f);
+    if (m) b2mj_model_free(m);
+    set_error(std::string("'") + path + "': " + why);
+    return B2MJ_EINVAL;
+  };
+  char magic[6];
+  int hdr[5];
+  if (std::fread(magic, 1, 6, f) != 6 || std::memcmp(magic, kBinMagic, 6)) return bad("not a b2mj binary model", nullptr);
+  if (std::fread(hdr, sizeof(int), 5, f) != 5) return bad("truncated header", nullptr);
+  if (hdr[0] != B2MJ_VERSION || hdr[1] != b2mj_model_nsizes() || hdr[2] != b2mj_model_narrays() ||
+      hdr[3] != (int)sizeof(b2mjOption) || hdr[4] != (int)sizeof(b2mjStatistic))
+    return bad("written by an incompatible library version (re-compile the model from its XML)", nullptr);
+  b2mjModel* m = model_new();
+  if (!m) return bad("out of memory", nullptr);
+#define X(n) if (std::fread(&m->n, sizeof(int), 1, f) != 1 || m->n < 0) return bad("bad size field '" #n "'", m);
+  B2MJ_MODEL_SIZES(X)
+#undef X
+  if (std::fread(&m->opt, sizeof(b2mjOption), 1, f) != 1 || std::fread(&m->stat, sizeof(b2mjStatistic), 1, f) != 1)
+    return bad("truncated option block", m);
+  model_alloc_arrays(m);
+#define X(t, n, r, c)                                                                                        \
+  {                                                                                                          \
+    long long bytes = -1;                                                                                    \
+    const long long want = (long long)sizeof(t) * m->r * (long long)(c);                                     \
+    if (std::fread(&bytes, sizeof(bytes), 1, f) != 1 || bytes != want) return bad("bad array '" #n "'", m);  \
+    if (bytes && std::fread(m->n, 1, (size_t)bytes, f) != (size_t)bytes) return bad("truncated array '" #n "'", m); \
+  }
+  B2MJ_MODEL_ARRAYS(X)
+#undef X
+  std::fclose(f);
+  *out = m;
+  return 0;
+}
+
+int b2mj_model_from_file(const char* path, b2mjModel** out) {
+  if (!path || !out) { set_error("b2mj_model_from_file: null argument"); return B2MJ_EINVAL; }
+  const std::string p(path);
+  const std::string ext = p.size() >= 6 ? p.substr(p.size() - 6) : "";
+  if (ext == ".b2mjb") return b2mj_model_load_binary(path, out);
+  return b2mj_model_from_xml_file(path, out);
+}
+
 static const int* name_adr_table(const b2mjModel* m, int objtype, int* count) {
   switch (objtype) {
     case B2MJ_OBJ_BODY: case B2MJ_OBJ_XBODY: *count = m->nbody; return m->name_bodyadr;
@@ -201,6 +284,7 @@ static const int* name_adr_table(const b2mjModel* m, int objtype, int* count) {
     case B2MJ_OBJ_ACTUATOR: *count = m->nu; return m->name_actuatoradr;
     case B2MJ_OBJ_SENSOR: *count = m->nsensor; return m->name_sensoradr;
     case B2MJ_OBJ_EQUALITY: *count = m->neq; return m->name_eqadr;
+    case B2MJ_OBJ_KEY: *count = m->nkey; return m->name_keyadr;
     default: *count = 0; return nullptr;
   }
 }

@@ -23,6 +23,7 @@ lib.orc_make_data.argtypes = [_vp]
 lib.orc_free_data.argtypes = [_vp]
 lib.orc_reset_data.argtypes = [_vp, _vp]
 lib.orc_forward.argtypes = [_vp, _vp]
+lib.orc_reset_keyframe.argtypes = [_vp, _vp, C.c_int]
 lib.orc_step.argtypes = [_vp, _vp]
 lib.orc_step1.argtypes = [_vp, _vp]
 lib.orc_step2.argtypes = [_vp, _vp]
@@ -55,6 +56,9 @@ class Oracle:
 
     def reset(self):
         lib.orc_reset_data(self.model.ptr, self._d)
+
+    def reset_keyframe(self, key: int):
+        lib.orc_reset_keyframe(self.model.ptr, self._d, int(key))
 
     def forward(self):
         lib.orc_forward(self.model.ptr, self._d)

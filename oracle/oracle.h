@@ -27,6 +27,7 @@ typedef void (*orc_callback)(const b2mjModel* m, OrcData* d, void* user);
 OrcData* orc_make_data(const b2mjModel* m);            /* mj_makeData + mj_resetData */
 void orc_free_data(OrcData* d);
 void orc_reset_data(const b2mjModel* m, OrcData* d);   /* mj_resetData */
+void orc_reset_keyframe(const b2mjModel* m, OrcData* d, int key); /* mj_resetDataKeyframe */
 void orc_forward(const b2mjModel* m, OrcData* d);      /* mj_forward */
 void orc_step(const b2mjModel* m, OrcData* d);         /* mj_step */
 void orc_step1(const b2mjModel* m, OrcData* d);        /* mj_step1: up to (excluding) the control callback */

@@ -502,6 +502,22 @@ void orc_reset_data(const b2mjModel* m, OrcData* d) {
   d->n_control_calls = d->n_passive_calls = 0;
 }
 
+// mj_resetDataKeyframe: mj_resetData, then the keyframe's time / qpos / qvel / act / ctrl / mocap pose
+void orc_reset_keyframe(const b2mjModel* m, OrcData* d, int key) {
+  resetData(m, d);
+  d->n_control_calls = d->n_passive_calls = 0;
+  if (key < 0 || key >= m->nkey) return;
+  d->time[0] = m->key_time[key];
+  copy(d->qpos, m->key_qpos + (size_t)key * m->nq, m->nq);
+  copy(d->qvel, m->key_qvel + (size_t)key * m->nv, m->nv);
+  if (m->na) copy(d->act, m->key_act + (size_t)key * m->na, m->na);
+  if (m->nu) copy(d->ctrl, m->key_ctrl + (size_t)key * m->nu, m->nu);
+  if (m->nmocap) {
+    copy(d->mocap_pos, m->key_mpos + (size_t)key * 3 * m->nmocap, 3 * m->nmocap);
+    copy(d->mocap_quat, m->key_mquat + (size_t)key * 4 * m->nmocap, 4 * m->nmocap);
+  }
+}
+
 void orc_forward(const b2mjModel* m, OrcData* d) { forwardSkip(m, d, false, false, false); }
 
 void orc_step(const b2mjModel* m, OrcData* d) {
