@@ -170,7 +170,7 @@ typedef struct b2mjStatistic {
   X(double, geom_solmix, ngeom, 1) X(double, geom_solref, ngeom, 2)                               \
   X(double, geom_solimp, ngeom, 5) X(double, geom_size, ngeom, 3) X(double, geom_rbound, ngeom, 1)\
   X(double, geom_pos, ngeom, 3) X(double, geom_quat, ngeom, 4) X(double, geom_friction, ngeom, 3) \
-  X(double, geom_margin, ngeom, 1) X(double, geom_gap, ngeom, 1)                                  \
+  X(double, geom_margin, ngeom, 1) X(double, geom_gap, ngeom, 1) X(double, geom_rgba, ngeom, 4)   \
   X(int, site_bodyid, nsite, 1) X(int, site_type, nsite, 1) X(double, site_size, nsite, 3)        \
   X(double, site_pos, nsite, 3) X(double, site_quat, nsite, 4)                                    \
   X(int, tendon_adr, ntendon, 1) X(int, tendon_num, ntendon, 1) X(int, tendon_limited, ntendon, 1)\

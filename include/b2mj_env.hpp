@@ -307,6 +307,14 @@ class BatchEnv {
     settings_.reset_request.store(0);
   }
 
+  // viewer.cpp:1735-1745 ("load key": mj_resetDataKeyframe-style copy of key_qpos / key_qvel / key_act / key_mpos /
+  // key_mquat into mjData), for the whole batch.  Returns false for a key the model does not have.
+  bool loadKeyframe(int key) {
+    if (!handle_ || b2mj_reset_keyframe(handle_, key, nullptr) != 0) return false;
+    data_->invalidate();
+    return true;
+  }
+
   // mujoco_env.cpp:266-402.  Values are broadcast to every env of the batch.
   void loadInitialJointStates() {
     auto parse = [](const std::string& s, std::vector<double>& out) {

@@ -246,11 +246,6 @@ static int check_supported(const b2mjModel* m) {
       return B2MJ_EUNSUPPORTED;
     }
   }
-  for (int i = 0; i < m->nsensor; i++)
-    if (m->sensor_type[i] == B2MJ_SENS_RANGEFINDER) {
-      set_error("rangefinder sensors need a ray caster: not implemented");
-      return B2MJ_EUNSUPPORTED;
-    }
   if (m->opt.integrator != B2MJ_INT_EULER && m->opt.integrator != B2MJ_INT_RK4 && m->opt.integrator != B2MJ_INT_IMPLICIT &&
       m->opt.integrator != B2MJ_INT_IMPLICITFAST) {
     set_error("unknown integrator");

@@ -2,7 +2,7 @@
 //
 // Replaces row M10 of SURVEY 8(a): the values the reference's sensor plugin reads from d->sensordata
 // (mujoco_ros_sensors/src/mujoco_sensor_handler_plugin.cpp:183-226).  Types: the 36 names that plugin
-// knows (:70-105) except rangefinder (needs a ray caster) — b2mj_create rejects models that use it.
+// knows (:70-105), rangefinder included (ray cast against the primitive geoms, mj_ray / mju_rayGeom).
 #pragma once
 #include "env_ctx.cuh"
 #include "stages_smooth.cuh"
@@ -41,6 +41,101 @@ __device__ __forceinline__ void sens_frame(const Env e, int type, int id, const 
       *pos = e.D(B2MJ_F_XPOS) + 3 * id; *mat = e.D(B2MJ_F_XMAT) + 9 * id;
       copy4(quat, xquat + 4 * id);
   }
+}
+
+// ---- mj_ray / mju_rayGeom for the rangefinder (plane, sphere, capsule, ellipsoid, cylinder, box) ----
+// smallest non-negative root of a x^2 + 2 b x + c = 0 (both roots in xx), -1 if none
+__device__ __forceinline__ double rayQuad(double a, double b, double c, double* xx) {
+  const double det0 = b * b - a * c;
+  if (det0 < B2K_MINVAL) { xx[0] = -1; xx[1] = -1; return -1; }
+  const double det = sqrt(det0);
+  xx[0] = (-b - det) / a;
+  xx[1] = (-b + det) / a;
+  return xx[0] >= 0 ? xx[0] : (xx[1] >= 0 ? xx[1] : -1.0);
+}
+__device__ __noinline__ double rayGeom(const double* pos, const double* mat, const double* size, const double* pnt,
+                                       const double* vec, int type) {
+  double dif[3], lpnt[3], lvec[3], xx[2], x = -1, sol;
+  sub3(dif, pnt, pos);
+  rotVecMatT(lpnt, dif, mat);
+  rotVecMatT(lvec, vec, mat);
+#define B2K_RAY_BETTER(S) { const double _s = (S); if (_s >= 0 && (x < 0 || _s < x)) x = _s; }
+  const double vv = dot3(lvec, lvec), vp = dot3(lvec, lpnt), pp = dot3(lpnt, lpnt);
+  if (type == B2MJ_GEOM_PLANE) {
+    if (lvec[2] > -B2K_MINVAL) return -1;
+    sol = -lpnt[2] / lvec[2];
+    if (sol < 0) return -1;
+    const double p0 = lpnt[0] + sol * lvec[0], p1 = lpnt[1] + sol * lvec[1];
+    return ((size[0] <= 0 || fabs(p0) <= size[0]) && (size[1] <= 0 || fabs(p1) <= size[1])) ? sol : -1.0;
+  }
+  if (type == B2MJ_GEOM_SPHERE) return rayQuad(vv, vp, pp - size[0] * size[0], xx);
+  if (type == B2MJ_GEOM_ELLIPSOID) {
+    const double s0 = 1 / (size[0] * size[0]), s1 = 1 / (size[1] * size[1]), s2 = 1 / (size[2] * size[2]);
+    return rayQuad(s0 * lvec[0] * lvec[0] + s1 * lvec[1] * lvec[1] + s2 * lvec[2] * lvec[2],
+                   s0 * lvec[0] * lpnt[0] + s1 * lvec[1] * lpnt[1] + s2 * lvec[2] * lpnt[2],
+                   s0 * lpnt[0] * lpnt[0] + s1 * lpnt[1] * lpnt[1] + s2 * lpnt[2] * lpnt[2] - 1, xx);
+  }
+  const double a2 = lvec[0] * lvec[0] + lvec[1] * lvec[1], b2 = lvec[0] * lpnt[0] + lvec[1] * lpnt[1],
+               c2 = lpnt[0] * lpnt[0] + lpnt[1] * lpnt[1] - size[0] * size[0];
+  if (type == B2MJ_GEOM_CAPSULE) {
+    const double ssz = size[0] + size[1];
+    if (rayQuad(vv, vp, pp - ssz * ssz, xx) < 0) return -1;
+    sol = rayQuad(a2, b2, c2, xx);
+    if (sol >= 0 && fabs(lpnt[2] + sol * lvec[2]) <= size[1]) B2K_RAY_BETTER(sol)
+    double ldif[3] = {lpnt[0], lpnt[1], lpnt[2] - size[1]};
+    rayQuad(vv, dot3(lvec, ldif), dot3(ldif, ldif) - size[0] * size[0], xx);
+    for (int i = 0; i < 2; i++)
+      if (xx[i] >= 0 && lpnt[2] + xx[i] * lvec[2] >= size[1]) B2K_RAY_BETTER(xx[i])
+    ldif[2] = lpnt[2] + size[1];
+    rayQuad(vv, dot3(lvec, ldif), dot3(ldif, ldif) - size[0] * size[0], xx);
+    for (int i = 0; i < 2; i++)
+      if (xx[i] >= 0 && lpnt[2] + xx[i] * lvec[2] <= -size[1]) B2K_RAY_BETTER(xx[i])
+    return x;
+  }
+  if (type == B2MJ_GEOM_CYLINDER) {
+    if (rayQuad(vv, vp, pp - (size[0] * size[0] + size[1] * size[1]), xx) < 0) return -1;
+    if (fabs(lvec[2]) > B2K_MINVAL)
+      for (int side = -1; side <= 1; side += 2) {
+        sol = (side * size[1] - lpnt[2]) / lvec[2];
+        if (sol >= 0) {
+          const double p0 = lpnt[0] + sol * lvec[0], p1 = lpnt[1] + sol * lvec[1];
+          if (p0 * p0 + p1 * p1 <= size[0] * size[0]) B2K_RAY_BETTER(sol)
+        }
+      }
+    sol = rayQuad(a2, b2, c2, xx);
+    if (sol >= 0 && fabs(lpnt[2] + sol * lvec[2]) <= size[1]) B2K_RAY_BETTER(sol)
+    return x;
+  }
+  if (type == B2MJ_GEOM_BOX) {
+    if (rayQuad(vv, vp, pp - dot3(size, size), xx) < 0) return -1;
+    B2K_NOUNROLL for (int i = 0; i < 3; i++) {
+      if (fabs(lvec[i]) <= B2K_MINVAL) continue;
+      const int i0 = (i + 1) % 3, i1 = (i + 2) % 3;
+      for (int side = -1; side <= 1; side += 2) {
+        sol = (side * size[i] - lpnt[i]) / lvec[i];
+        if (sol >= 0) {
+          const double p0 = lpnt[i0] + sol * lvec[i0], p1 = lpnt[i1] + sol * lvec[i1];
+          if (fabs(p0) <= size[i0] && fabs(p1) <= size[i1]) B2K_RAY_BETTER(sol)
+        }
+      }
+    }
+    return x;
+  }
+#undef B2K_RAY_BETTER
+  return -1;
+}
+// nearest hit over all geoms except those of bodyexclude and fully transparent ones; -1 if none (one lane, serial)
+__device__ __noinline__ double rayScene(const Env e, const double* pnt, const double* vec, int bodyexclude) {
+  const DevModel& m = c_dm;
+  const double* gx = e.D(B2MJ_F_GEOM_XPOS);
+  const double* gm = e.D(B2MJ_F_GEOM_XMAT);
+  double best = -1;
+  B2K_NOUNROLL for (int g = 0; g < m.ngeom; g++) {
+    if (m.geom_bodyid[g] == bodyexclude || m.geom_rgba[4 * g + 3] == 0) continue;
+    const double x = rayGeom(gx + 3 * g, gm + 9 * g, m.geom_size + 3 * g, pnt, vec, m.geom_type[g]);
+    if (x >= 0 && (best < 0 || x < best)) best = x;
+  }
+  return best;
 }
 
 __device__ __forceinline__ int sens_body(int type, int id) {
@@ -89,6 +184,12 @@ __device__ __noinline__ void stage_sensorPos(const Env e, int nefc) {
     double* out = sd + m.sensor_adr[i];
     switch (type) {
       case B2MJ_SENS_MAGNETOMETER: rotVecMatT(out, m.opt.magnetic, e.D(B2MJ_F_SITE_XMAT) + 9 * objid); break;
+      case B2MJ_SENS_RANGEFINDER: {  // ray along the site's z axis, the site's own body excluded
+        const double* sm = e.D(B2MJ_F_SITE_XMAT) + 9 * objid;
+        const double rvec[3] = {sm[2], sm[5], sm[8]};
+        out[0] = rayScene(e, e.D(B2MJ_F_SITE_XPOS) + 3 * objid, rvec, m.site_bodyid[objid]);
+        break;
+      }
       case B2MJ_SENS_JOINTPOS: out[0] = qpos[m.jnt_qposadr[objid]]; break;
       case B2MJ_SENS_TENDONPOS: out[0] = e.D(B2MJ_F_TEN_LENGTH)[objid]; break;
       case B2MJ_SENS_ACTUATORPOS: out[0] = e.D(B2MJ_F_ACTUATOR_LENGTH)[objid]; break;

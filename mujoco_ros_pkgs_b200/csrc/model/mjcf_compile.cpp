@@ -189,6 +189,7 @@ struct CGeom {
   double solref[2] = {0.02, 1}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2};
   double solmix = 1, margin = 0, gap = 0, mass = 0;
   double inertia[3] = {0, 0, 0};
+  double rgba[4] = {0.5, 0.5, 0.5, 1};
   int contype = 1, conaffinity = 1, condim = 3, priority = 0;
 };
 struct CSite {
@@ -407,6 +408,7 @@ struct Builder {
     g.solmix = a.num("solmix", 1);
     g.margin = a.num("margin", 0);
     g.gap = a.num("gap", 0);
+    a.vec("rgba", g.rgba, 4, 1);  // only alpha matters to the physics: mj_ray skips fully transparent geoms
     g.contype = a.integer("contype", 1);
     g.conaffinity = a.integer("conaffinity", 1);
     g.condim = a.integer("condim", 3);
@@ -562,6 +564,7 @@ const SensorSpec kSensors[] = {
     {"force", B2MJ_SENS_FORCE, 3, B2MJ_STAGE_ACC, 0, "site", B2MJ_OBJ_SITE},
     {"torque", B2MJ_SENS_TORQUE, 3, B2MJ_STAGE_ACC, 0, "site", B2MJ_OBJ_SITE},
     {"magnetometer", B2MJ_SENS_MAGNETOMETER, 3, B2MJ_STAGE_POS, 0, "site", B2MJ_OBJ_SITE},
+    {"rangefinder", B2MJ_SENS_RANGEFINDER, 1, B2MJ_STAGE_POS, B2MJ_DATATYPE_POSITIVE, "site", B2MJ_OBJ_SITE},
     {"jointpos", B2MJ_SENS_JOINTPOS, 1, B2MJ_STAGE_POS, 0, "joint", B2MJ_OBJ_JOINT},
     {"jointvel", B2MJ_SENS_JOINTVEL, 1, B2MJ_STAGE_VEL, 0, "joint", B2MJ_OBJ_JOINT},
     {"tendonpos", B2MJ_SENS_TENDONPOS, 1, B2MJ_STAGE_POS, 0, "tendon", B2MJ_OBJ_TENDON},
@@ -934,6 +937,7 @@ b2mjModel* compile(const XmlNode* root) {
         copy3(m->geom_friction + 3 * g, gm.friction);
         m->geom_margin[g] = gm.margin;
         m->geom_gap[g] = gm.gap;
+        for (int k = 0; k < 4; k++) m->geom_rgba[4 * g + k] = gm.rgba[k];
         double rb = 0;
         switch (gm.type) {
           case B2MJ_GEOM_SPHERE: rb = gm.size[0]; break;

@@ -165,7 +165,7 @@ int b2mj_field_size(const b2mjModel* m, b2mj_field f, int* is_int) {
     case B2MJ_F_EFC_STATE: return nj;
     case B2MJ_F_EFC_J: return nj * nv;
     case B2MJ_F_EFC_KBIP: return 4 * nj;
-    case B2MJ_F_EFC_AR: return (m->opt.solver == B2MJ_SOL_PGS) ? nj * nj : 0;
+    case B2MJ_F_EFC_AR: return (m->opt.solver == B2MJ_SOL_PGS || m->opt.noslip_iterations > 0) ? nj * nj : 0;
     case B2MJ_F_NCON: case B2MJ_F_NEFC: case B2MJ_F_SOLVER_ITER: return 1;
     case B2MJ_F_WARNING: return B2MJ_NWARNING;
     default: break;

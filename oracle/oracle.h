@@ -40,6 +40,9 @@ int orc_callback_counts(const OrcData* d, int* ncontrol, int* npassive);
 void orc_rne_vel_derivative(const b2mjModel* m, const OrcData* d, double* dbias);
 void orc_smooth_vel_derivative(const b2mjModel* m, const OrcData* d, int flg_bias, double* qderiv);
 
+/* mj_ray (geomgroup NULL, flg_static 1): distance to the nearest geom along vec, -1 if none (orc_ray.cpp) */
+double orc_ray(const b2mjModel* m, const OrcData* d, const double* pnt, const double* vec, int bodyexclude, int* geomid);
+
 /* field access by b2mj_field id; count = number of elements copied; returns per-env element count */
 int orc_get(const b2mjModel* m, const OrcData* d, int field, void* dst, int max_elems);
 int orc_set(const b2mjModel* m, OrcData* d, int field, const void* src, int nelems);

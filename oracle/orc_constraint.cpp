@@ -374,7 +374,7 @@ void mulJacTVec(const b2mjModel* m, const OrcData* d, double* res, const double*
 // mj_projectConstraint: AR = J inv(M) J' + diag(R) via JM2 = J inv(L) sqrt(inv(D))  (dual solvers)
 void projectConstraint(const b2mjModel* m, OrcData* d) {
   const int nv = m->nv, nefc = d->nefc();
-  if (nefc == 0 || m->opt.solver != B2MJ_SOL_PGS) return;
+  if (nefc == 0 || !(m->opt.solver == B2MJ_SOL_PGS || m->opt.noslip_iterations > 0)) return;  // mj_isDual
   std::vector<double> JM2((size_t)nefc * nv);
   for (int i = 0; i < nefc; i++) solveM2(m, d, &JM2[(size_t)i * nv], d->efc_J + i * nv);
   for (int i = 0; i < nefc; i++)

@@ -73,6 +73,12 @@ void sensorPos(const b2mjModel* m, OrcData* d) {
     double* out = d->sensordata + adr;
     switch (type) {
       case B2MJ_SENS_MAGNETOMETER: rotVecMatT(out, m->opt.magnetic, d->site_xmat + 9 * objid); break;
+      case B2MJ_SENS_RANGEFINDER: {  // ray along the site's z axis, the site's own body excluded
+        const double* sm = d->site_xmat + 9 * objid;
+        const double rvec[3] = {sm[2], sm[5], sm[8]};
+        out[0] = ray(m, d, d->site_xpos + 3 * objid, rvec, m->site_bodyid[objid], nullptr);
+        break;
+      }
       case B2MJ_SENS_JOINTPOS: out[0] = d->qpos[m->jnt_qposadr[objid]]; break;
       case B2MJ_SENS_TENDONPOS: out[0] = d->ten_length[objid]; break;
       case B2MJ_SENS_ACTUATORPOS: out[0] = d->actuator_length[objid]; break;

@@ -192,6 +192,102 @@ static void solPGS(const b2mjModel* m, OrcData* d, int maxiter) {
   for (int i = 0; i < m->nv; i++) d->qacc[i] += d->qacc_smooth[i];
 }
 
+// mj_solNoSlip: modified PGS over the friction-loss rows and the friction dimensions of contacts, on the dual problem
+// WITHOUT the regulariser R (so converged friction forces leave no residual slip); normal forces stay as the main
+// solver left them.  Runs after the main solver when opt.noslip_iterations > 0 -- the reference exposes both knobs in
+// its option panel (mujoco_ros/src/viewer.cpp:590-591 "Noslip Iter" / "Noslip Tol").
+static void solNoSlip(const b2mjModel* m, OrcData* d, int maxiter) {
+  const int nefc = d->nefc();
+  const double* AR = d->efc_AR;
+  const double* R = d->efc_R;
+  const double* b = d->efc_b;
+  double* force = d->efc_force;
+  const double scale = 1 / (m->stat.meaninertia * std::max(1, m->nv));
+  auto residual = [&](double* res, int i, int dim) {  // residual of the unregularised system
+    for (int j = 0; j < dim; j++) res[j] = b[i + j] + dot(AR + (i + j) * nefc, force, nefc) - R[i + j] * force[i + j];
+  };
+  auto block = [&](double* Ac, int i, int dim) {
+    for (int j = 0; j < dim; j++)
+      for (int k = 0; k < dim; k++) Ac[j * dim + k] = AR[(i + j) * nefc + i + k] - (j == k ? R[i + j] : 0.0);
+  };
+  int iter = 0;
+  while (iter < maxiter) {
+    double improvement = 0;
+    if (iter == 0)  // the cost drops by the regulariser's share when R is removed
+      for (int i = 0; i < nefc; i++) improvement += 0.5 * force[i] * force[i] * R[i];
+    for (int i = 0; i < nefc; i++) {
+      const int t = d->efc_type[i];
+      double res[6], oldforce[6], Ac[36];
+      if (t == B2MJ_CNSTR_FRICTION_DOF || t == B2MJ_CNSTR_FRICTION_TENDON) {
+        residual(res, i, 1);
+        oldforce[0] = force[i];
+        block(Ac, i, 1);
+        force[i] -= res[0] / Ac[0];
+        const double fl = d->efc_frictionloss[i];
+        force[i] = clampd(force[i], -fl, fl);
+        improvement -= costChange(Ac, force + i, oldforce, res, 1, 1);
+      } else if (t == B2MJ_CNSTR_CONTACT_PYRAMIDAL) {
+        const int dim = d->contact_dim[d->efc_id[i]];
+        // pairs of opposing pyramid edges: their sum (the normal load they carry) is kept, the split is re-optimised
+        for (int j = i; j < i + 2 * (dim - 1); j += 2) {
+          residual(res, j, 2);
+          oldforce[0] = force[j]; oldforce[1] = force[j + 1];
+          block(Ac, j, 2);
+          const double bc0 = res[0] - Ac[0] * oldforce[0] - Ac[1] * oldforce[1];
+          const double bc1 = res[1] - Ac[2] * oldforce[0] - Ac[3] * oldforce[1];
+          const double mid = 0.5 * (force[j] + force[j + 1]);
+          const double K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2], K0 = mid * (Ac[0] - Ac[3]) + bc0 - bc1;
+          if (K1 < MINVAL) {
+            force[j] = force[j + 1] = mid;
+          } else {
+            const double y = -K0 / K1;
+            if (y < -mid) { force[j] = 0; force[j + 1] = 2 * mid; }
+            else if (y > mid) { force[j] = 2 * mid; force[j + 1] = 0; }
+            else { force[j] = mid + y; force[j + 1] = mid - y; }
+          }
+          improvement -= costChange(Ac, force + j, oldforce, res, 2, 2);
+        }
+        i += 2 * (dim - 1) - 1;
+      } else if (t == B2MJ_CNSTR_CONTACT_ELLIPTIC) {
+        const int c = d->efc_id[i], dim = d->contact_dim[c];
+        const double* mu = d->contact_friction + 5 * c;
+        const int fd = dim - 1;
+        if (fd > 0) {
+          residual(res, i + 1, fd);
+          for (int j = 0; j < fd; j++) oldforce[j] = force[i + 1 + j];
+          block(Ac, i + 1, fd);
+          double bc[5], v[5];
+          for (int j = 0; j < fd; j++) {
+            bc[j] = res[j];
+            for (int k = 0; k < fd; k++) bc[j] -= Ac[j * fd + k] * oldforce[k];
+          }
+          if (force[i] < MINVAL) {
+            for (int j = 0; j < fd; j++) force[i + 1 + j] = 0;
+          } else {
+            const int active = QCQP(v, Ac, bc, mu, force[i], fd);
+            if (active) {
+              double s = 0;
+              for (int j = 0; j < fd; j++) s += (v[j] / mu[j]) * (v[j] / mu[j]);
+              s = std::sqrt(force[i] * force[i] / std::fmax(MINVAL, s));
+              for (int j = 0; j < fd; j++) v[j] *= s;
+            }
+            for (int j = 0; j < fd; j++) force[i + 1 + j] = v[j];
+          }
+          improvement -= costChange(Ac, force + i + 1, oldforce, res, fd, fd);
+        }
+        i += dim - 1;
+      }
+    }
+    improvement *= scale;
+    iter++;
+    if (improvement < m->opt.noslip_tolerance) break;
+  }
+  d->solver_iter_[0] += iter;
+  mulJacTVec(m, d, d->qfrc_constraint, force);
+  solveM(m, d, d->qacc, d->qfrc_constraint);
+  for (int i = 0; i < m->nv; i++) d->qacc[i] += d->qacc_smooth[i];
+}
+
 // ----------------------------------------------------------------------------------------------
 // primal solvers (CG, Newton)
 // ----------------------------------------------------------------------------------------------
@@ -504,7 +600,9 @@ void fwdConstraint(const b2mjModel* m, OrcData* d) {
     }
     solPrimal(m, d, m->opt.iterations, m->opt.solver == B2MJ_SOL_NEWTON);
   }
+  // the warm start of the next step is the main solver's result; the noslip pass runs after it is saved
   copy(d->qacc_warmstart, d->qacc, nv);
+  if (m->opt.noslip_iterations > 0) solNoSlip(m, d, m->opt.noslip_iterations);
 }
 
 }  // namespace orc

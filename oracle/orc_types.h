@@ -64,7 +64,7 @@
   X(B2MJ_F_EFC_R, efc_R, double, m->njmax) X(B2MJ_F_EFC_VEL, efc_vel, double, m->njmax)            \
   X(B2MJ_F_EFC_AREF, efc_aref, double, m->njmax) X(B2MJ_F_EFC_B, efc_b, double, m->njmax)          \
   X(B2MJ_F_EFC_FORCE, efc_force, double, m->njmax) X(B2MJ_F_EFC_STATE, efc_state, int, m->njmax)   \
-  X(B2MJ_F_EFC_AR, efc_AR, double, (m->opt.solver == B2MJ_SOL_PGS ? m->njmax * m->njmax : 0))      \
+  X(B2MJ_F_EFC_AR, efc_AR, double, ((m->opt.solver == B2MJ_SOL_PGS || m->opt.noslip_iterations > 0) ? m->njmax * m->njmax : 0))      \
   X(B2MJ_F_NCON, ncon_, int, 1) X(B2MJ_F_NEFC, nefc_, int, 1) X(B2MJ_F_SOLVER_ITER, solver_iter_, int, 1) \
   X(B2MJ_F_WARNING, warning, int, B2MJ_NWARNING)
 
@@ -127,6 +127,8 @@ void sensorPos(const b2mjModel* m, OrcData* d);
 void sensorVel(const b2mjModel* m, OrcData* d);
 void sensorAcc(const b2mjModel* m, OrcData* d);
 void integratePos(const b2mjModel* m, double* qpos, const double* qvel, double dt);
+// orc_ray.cpp
+double ray(const b2mjModel* m, const OrcData* d, const double* pnt, const double* vec, int bodyexclude, int* geomid);
 // orc_implicit.cpp
 void implicitQacc(const b2mjModel* m, OrcData* d, double* qacc_out);
 }  // namespace orc

@@ -203,6 +203,62 @@ def test_fluid_forces(name, integ, capi, orc, BatchSim):
     print(f"fluid {name}: injected-step worst {worst:.2e}")
 
 
+RANGE_SCENE = """
+<mujoco>
+  <option timestep="0.002"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1"/>
+    <geom type="sphere" size="0.25" pos="0.6 0 0.3"/>
+    <geom type="capsule" size="0.1 0.3" pos="0 0.7 0.4" euler="0 70 20"/>
+    <geom type="cylinder" size="0.2 0.4" pos="-0.7 0 0.4" euler="30 0 0" contype="0" conaffinity="0"/>
+    <geom type="ellipsoid" size="0.1 0.2 0.3" pos="0 -0.7 0.5" euler="0 40 0" contype="0" conaffinity="0"/>
+    <geom type="box" size="0.2 0.3 0.1" pos="0.5 0.5 0.8" euler="20 30 40"/>
+    <geom type="box" size="0.5 0.5 0.01" pos="0 0 0.2" rgba="1 0 0 0" contype="0" conaffinity="0"/>
+    <body name="probe" pos="0 0 1.2">
+      <freejoint/>
+      <geom type="sphere" size="0.08"/>
+      <site name="s0" pos="0 0 0" euler="180 0 0"/>
+      <site name="s1" pos="0.02 0 0" euler="120 0 0"/>
+      <site name="s2" pos="0 0.02 0" euler="0 120 0"/>
+      <site name="s3" pos="0 0 0.02" euler="200 30 0"/>
+      <site name="s4" pos="0 0 0" euler="0 0 0"/>
+      <site name="s5" pos="0 0 0" euler="150 40 10"/>
+    </body>
+  </worldbody>
+  <sensor>
+    <rangefinder site="s0"/><rangefinder site="s1"/><rangefinder site="s2"/><rangefinder site="s3" cutoff="0.9"/>
+    <rangefinder site="s4"/><rangefinder site="s5"/>
+  </sensor>
+</mujoco>
+"""
+
+
+def test_rangefinder(capi, orc, BatchSim):
+    """mjSENS_RANGEFINDER (the sensor plugin publishes it as a scalar, mujoco_sensor_handler_plugin.cpp:331): rays from a
+    tumbling free body against every primitive geom type, transparent geoms and the site's own body excluded."""
+    model = capi.Model.from_xml_string(RANGE_SCENE)
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 3, 0.3)
+    qvel *= 15
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    hits = 0
+    for s in range(150):
+        sim.step(1)
+        for o in oracles:
+            o.step(1)
+        if s % 10 == 9:
+            g = sim.get("sensordata")
+            for e, o in enumerate(oracles):
+                want = o.get("sensordata")
+                assert np.array_equal(g[e] < 0, want < 0), (s, e, g[e], want)
+                assert rel(g[e], want) < 1e-9, (s, e, g[e], want)
+                hits += int(np.sum(want >= 0))
+    assert hits > 100
+
+
 @pytest.mark.parametrize("integ", [EULER, RK4])
 def test_activation_dynamics(integ, capi, orc, BatchSim):
     """na > 0: integrator / filter activation dynamics, actlimited clamp, affine gain + bias, forcerange, tendon

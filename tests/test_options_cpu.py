@@ -63,3 +63,90 @@ def test_fluid_off_by_default(capi, orc):
     o.set("qvel", np.ones(6))
     o.forward()
     assert np.all(o.get("qfrc_passive") == 0)
+
+
+RANGE = """
+<mujoco>
+  <option gravity="0 0 0"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1"/>
+    <geom name="ball" type="sphere" size="0.25" pos="2 0 1"/>
+    <geom name="cap" type="capsule" size="0.1 0.3" pos="0 2 1" euler="0 90 0"/>
+    <geom name="cyl" type="cylinder" size="0.2 0.4" pos="-2 0 1"/>
+    <geom name="egg" type="ellipsoid" size="0.1 0.2 0.3" pos="0 -2 1"/>
+    <geom name="brick" type="box" size="0.2 0.3 0.1" pos="0 0 3"/>
+    <geom name="ghost" type="box" size="0.5 0.5 0.01" pos="0 0 0.5" rgba="1 0 0 0"/>
+    <body name="probe" pos="0 0 1">
+      <geom name="shell" type="sphere" size="0.05"/>
+      <site name="down" pos="0 0 0" euler="180 0 0"/>
+      <site name="up" pos="0 0 0"/>
+      <site name="xp" pos="0 0 0" euler="0 90 0"/>
+      <site name="xm" pos="0 0 0" euler="0 -90 0"/>
+      <site name="yp" pos="0 0 0" euler="-90 0 0"/>
+      <site name="ym" pos="0 0 0" euler="90 0 0"/>
+      <site name="far" pos="20 0 0" euler="0 0 0"/>
+    </body>
+  </worldbody>
+  <sensor>
+    <rangefinder site="down"/><rangefinder site="up"/><rangefinder site="xp"/><rangefinder site="xm"/>
+    <rangefinder site="yp"/><rangefinder site="ym"/><rangefinder site="far"/><rangefinder site="down" cutoff="0.4"/>
+  </sensor>
+</mujoco>
+"""
+
+
+def test_rangefinder_closed_forms(capi, orc):
+    m = capi.Model.from_xml_string(RANGE)
+    o = orc.Oracle(m)
+    o.forward()
+    s = o.get("sensordata")
+    # down: the transparent slab at z = 0.5 and the probe's own shell are skipped -> the floor, 1 m below
+    assert abs(s[0] - 1.0) < 1e-14
+    assert abs(s[1] - (3 - 0.1 - 1)) < 1e-14            # up: bottom face of the brick
+    assert abs(s[2] - (2 - 0.25)) < 1e-14               # +x: the ball
+    assert abs(s[3] - (2 - 0.2)) < 1e-14                # -x: round side of the cylinder
+    assert abs(s[4] - (2 - 0.1)) < 1e-14                # +y: round side of the capsule (axis along x)
+    assert abs(s[5] - (2 - 0.2)) < 1e-14                # -y: the ellipsoid's y semi-axis
+    assert s[6] == -1.0                                 # nothing above the far site
+    assert abs(s[7] - 0.4) < 1e-15                      # cutoff clamps the 1 m reading
+
+
+def test_ray_hits_caps_and_edges(capi, orc):
+    import ctypes as C
+    m = capi.Model.from_xml_string(RANGE)
+    o = orc.Oracle(m)
+    o.forward()
+    lib = orc.lib
+    lib.orc_ray.restype = C.c_double
+    lib.orc_ray.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+
+    def ray(p, v, exclude=-1):
+        p, v = np.asarray(p, float), np.asarray(v, float)
+        gid = C.c_int(-7)
+        x = lib.orc_ray(m.ptr, o._d, p.ctypes.data, v.ctypes.data, exclude, C.byref(gid))
+        return x, gid.value
+
+    gid = lambda n: m.name2id(capi.OBJ_GEOM, n)
+    # capsule end cap, from +x along its axis: centre (0,2,1), half-length 0.3 along x, radius 0.1
+    x, g = ray([1, 2, 1], [-1, 0, 0])
+    assert g == gid("cap") and abs(x - (1 - 0.4)) < 1e-14
+    # cylinder flat top from above
+    x, g = ray([-2, 0, 5], [0, 0, -1])
+    assert g == gid("cyl") and abs(x - (5 - 1.4)) < 1e-14
+    # ellipsoid along z
+    x, g = ray([0, -2, 4], [0, 0, -1])
+    assert g == gid("egg") and abs(x - (4 - 1.3)) < 1e-14
+    # non-unit direction: the distance is in units of |vec|
+    x, g = ray([0, -2, 4], [0, 0, -2])
+    assert abs(x - (4 - 1.3) / 2) < 1e-14
+    # box from the side, then a miss just past its edge
+    x, g = ray([3, 0.29, 3], [-1, 0, 0])
+    assert g == gid("brick") and abs(x - 2.8) < 1e-14
+    x, g = ray([3, 0.31, 3.2], [-1, 0, 0])
+    assert g == -1 and x == -1
+    # from inside a sphere: the far wall
+    x, g = ray([2, 0, 1], [1, 0, 0])
+    assert g == gid("ball") and abs(x - 0.25) < 1e-14
+    # a plane seen from behind is not hit
+    x, g = ray([0.9, 0.9, -1], [0, 0, 1], exclude=0)
+    assert g != gid("floor")
