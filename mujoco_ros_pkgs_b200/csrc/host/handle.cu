@@ -255,10 +255,6 @@ static int check_supported(const b2mjModel* m) {
     set_error("unknown solver");
     return B2MJ_EUNSUPPORTED;
   }
-  if (m->opt.noslip_iterations > 0) {
-    set_error("noslip post-solver is not implemented");
-    return B2MJ_EUNSUPPORTED;
-  }
   if ((m->opt.density > 0 || m->opt.viscosity > 0) &&
       (m->opt.integrator == B2MJ_INT_IMPLICIT || m->opt.integrator == B2MJ_INT_IMPLICITFAST)) {
     set_error("fluid forces with an implicit integrator need the fluid velocity derivatives (mjd_inertiaBoxFluid): not implemented");
@@ -312,14 +308,16 @@ static int make_layout(Handle* h) {
   xs[XF_QLOC] = 0;
   xs[XF_QH] = m->nM;
   xs[XF_QHDIAGINV] = nv;
-  xs[XF_EFC_MINVJT] = pgs ? m->njmax * nv : 0;
-  xs[XF_EFC_ARDIAG] = pgs ? m->njmax : 0;
+  const bool dual = pgs || m->opt.noslip_iterations > 0;  // mj_isDual: the noslip pass runs on the dual problem
+  xs[XF_EFC_MINVJT] = dual ? m->njmax * nv : 0;
+  xs[XF_EFC_ARDIAG] = dual ? m->njmax : 0;
   for (int i = XF_VEC0; i <= XF_VEC5; i++) xs[i] = nv;
   xs[XF_EFC_JAREF] = m->njmax;
   xs[XF_EFC_JV] = pgs ? 0 : m->njmax;
   xs[XF_EFC_QUAD] = pgs ? 0 : 3 * m->njmax;
   // team mode (kernels/team.cuh): wide Newton models get one env per CTA and 8 warps; H then has an odd leading dimension
-  d.team_warps = (newton && nv >= B2K_TEAM_MIN_NV && !getenv("B2MJ_NO_TEAM")) ? B2K_TEAM_WARPS : 1;
+  // (the noslip pass is single-warp code over dense J rows: no team mode with it)
+  d.team_warps = (newton && nv >= B2K_TEAM_MIN_NV && m->opt.noslip_iterations <= 0 && !getenv("B2MJ_NO_TEAM")) ? B2K_TEAM_WARPS : 1;
   if (d.team_warps > 1 && getenv("B2MJ_TEAM_WARPS")) d.team_warps = std::max(2, std::min(16, atoi(getenv("B2MJ_TEAM_WARPS"))));
   d.ldh = nv | 1;  // odd: lanes walking a column (or owning a row each) hit distinct shared-memory banks
   xs[XF_NEWTON_H] = newton ? nv * d.ldh : 0;

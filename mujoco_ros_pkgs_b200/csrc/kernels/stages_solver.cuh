@@ -46,7 +46,8 @@ __device__ __forceinline__ unsigned arSmemOffset(const Env e, int nefc) {
 }
 
 // G = J W (rows of J pushed through inv(L)) and AR = G diag(1/D) G' + R
-__device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
+// want_ar = false (noslip pass after a primal solver): only G and the diagonal, which the matrix-free sweeps need
+__device__ __noinline__ void stage_projectConstraint(const Env e, int nefc, bool want_ar = true) {
   if (!nefc) return;
   const DevModel& m = c_dm;
   const int nv = m.nv;
@@ -77,7 +78,7 @@ __device__ __noinline__ void stage_projectConstraint(const Env e, int nefc) {
   }
   WSYNC();
   double* ard = e.XG(XF_EFC_ARDIAG);
-  if (nefc <= B2K_PGS_REGROWS) {
+  if (want_ar && nefc <= B2K_PGS_REGROWS) {
     double* AR = arPtr(e, nefc);
     // lower triangle incl. diagonal, mirrored
     B2K_NOUNROLL for (int item = e.lane; item < nefc * nefc; item += B2K_G) {
@@ -547,6 +548,117 @@ __device__ __noinline__ int solvePGS_free(const Env e, int nefc, double* avec) {
     improvement *= scale;
     iter++;
     if (improvement < m.opt.tolerance) break;
+  }
+  return iter;
+}
+
+// mj_solNoSlip: modified PGS over the friction-loss rows and the friction dimensions of contacts on the dual problem
+// WITHOUT the regulariser R; normal forces stay as the main solver left them (opt.noslip_iterations > 0; the reference
+// exposes "Noslip Iter" / "Noslip Tol" at mujoco_ros/src/viewer.cpp:590-591).  Matrix-free like solvePGS_free: the
+// unregularised A = J inv(M) J' is never formed, blocks and residuals come from row products with G = J inv(L) and the
+// running vector avec = inv(M) J' f.  Every lane computes the same scalars; lane 0 (or lanes < dim) commits the forces.
+__device__ __noinline__ int solveNoSlip(const Env e, int nefc, double* avec) {
+  const DevModel& m = c_dm;
+  const int nv = m.nv;
+  EfcPtrs P = efcPtrs(e);
+  const double* G = e.XG(XF_EFC_MINVJT);
+  const bool dense = m.dense_small;
+  const double* U = dense ? P.J : G;
+  const double* dinv = dense ? nullptr : e.DG(B2MJ_F_QLDIAGINV);
+  const int* c_dim = e.IG(B2MJ_F_CONTACT_DIM);
+  const double* c_fri = e.DG(B2MJ_F_CONTACT_FRICTION);
+  const double scale = 1 / (m.env_scalars[0] * max(1, nv));
+  FORL(k, nv) {
+    double s = 0;
+    B2K_NOUNROLL for (int i = 0; i < nefc; i++) s += U[i * nv + k] * P.force[i];
+    avec[k] = dinv ? s * dinv[k] : s;
+  }
+  WSYNC();
+  int iter = 0;
+  while (iter < m.opt.noslip_iterations) {
+    double improvement = 0;
+    if (iter == 0) {
+      double s = 0;
+      FORL(i, nefc) s += 0.5 * P.force[i] * P.force[i] * P.R[i];
+      improvement = warpSum(e.mask, s);
+    }
+    B2K_NOUNROLL for (int i = 0; i < nefc; i++) {
+      const int type = P.type[i];
+      int base, bd;  // block of rows [base, base + bd) updated together
+      if (type == B2MJ_CNSTR_FRICTION_DOF || type == B2MJ_CNSTR_FRICTION_TENDON) { base = i; bd = 1; }
+      else if (type == B2MJ_CNSTR_CONTACT_PYRAMIDAL) { base = i; bd = 2; }
+      else if (type == B2MJ_CNSTR_CONTACT_ELLIPTIC) { base = i + 1; bd = c_dim[P.id[i]] - 1; }
+      else continue;
+      const int con = P.id[i];
+      const int npair = type == B2MJ_CNSTR_CONTACT_PYRAMIDAL ? c_dim[con] - 1 : 1;
+      B2K_NOUNROLL for (int pr = 0; pr < npair; pr++, base += (type == B2MJ_CNSTR_CONTACT_PYRAMIDAL ? 2 : 0)) {
+        if (bd <= 0) break;
+        double Ac[25], res[5], oldf[5], f[5];
+        B2K_NOUNROLL for (int j = 0; j < bd; j++) {
+          B2K_NOUNROLL for (int k = 0; k < bd; k++) Ac[j * bd + k] = rowDotW(e, G + (base + j) * nv, U + (base + k) * nv, dinv, nv);
+          oldf[j] = P.force[base + j];
+          res[j] = P.b[base + j] + rowDot(e, G + (base + j) * nv, avec, nv);
+        }
+        if (bd == 1 && type != B2MJ_CNSTR_CONTACT_ELLIPTIC) {
+          const double fl = P.floss[base];
+          f[0] = clampd(oldf[0] - res[0] / Ac[0], -fl, fl);
+        } else if (type == B2MJ_CNSTR_CONTACT_PYRAMIDAL) {
+          const double bc0 = res[0] - Ac[0] * oldf[0] - Ac[1] * oldf[1];
+          const double bc1 = res[1] - Ac[2] * oldf[0] - Ac[3] * oldf[1];
+          const double mid = 0.5 * (oldf[0] + oldf[1]);
+          const double K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2], K0 = mid * (Ac[0] - Ac[3]) + bc0 - bc1;
+          if (K1 < B2K_MINVAL) { f[0] = mid; f[1] = mid; }
+          else {
+            const double y = -K0 / K1;
+            if (y < -mid) { f[0] = 0; f[1] = 2 * mid; }
+            else if (y > mid) { f[0] = 2 * mid; f[1] = 0; }
+            else { f[0] = mid + y; f[1] = mid - y; }
+          }
+        } else {
+          const double fn = P.force[i];
+          const double* mu = c_fri + 5 * con;
+          double bc[5];
+          B2K_NOUNROLL for (int j = 0; j < bd; j++) {
+            double t = res[j];
+            B2K_NOUNROLL for (int k = 0; k < bd; k++) t -= Ac[j * bd + k] * oldf[k];
+            bc[j] = t;
+          }
+          if (fn < B2K_MINVAL) {
+            B2K_NOUNROLL for (int j = 0; j < bd; j++) f[j] = 0;
+          } else {
+            const int active = QCQP(f, Ac, bc, mu, fn, bd);
+            if (active) {
+              double t = 0;
+              B2K_NOUNROLL for (int j = 0; j < bd; j++) t += (f[j] / mu[j]) * (f[j] / mu[j]);
+              t = sqrt(fn * fn / fmax(B2K_MINVAL, t));
+              B2K_NOUNROLL for (int j = 0; j < bd; j++) f[j] *= t;
+            }
+          }
+        }
+        double change = 0, delta[5];
+        B2K_NOUNROLL for (int j = 0; j < bd; j++) delta[j] = f[j] - oldf[j];
+        B2K_NOUNROLL for (int j = 0; j < bd; j++) {
+          double t = 0;
+          B2K_NOUNROLL for (int k = 0; k < bd; k++) t += Ac[j * bd + k] * delta[k];
+          change += 0.5 * delta[j] * t + delta[j] * res[j];
+        }
+        if (change > 1e-10) {
+          change = 0;
+          B2K_NOUNROLL for (int j = 0; j < bd; j++) { delta[j] = 0; f[j] = oldf[j]; }
+        }
+        improvement -= change;
+        B2K_NOUNROLL for (int j = 0; j < bd; j++) {
+          if (delta[j] != 0) FORL(k, nv) avec[k] += delta[j] * U[(base + j) * nv + k] * (dinv ? dinv[k] : 1.0);
+        }
+        if (e.lane < bd) P.force[base + e.lane] = f[e.lane];
+        WSYNC();
+      }
+      if (type == B2MJ_CNSTR_CONTACT_PYRAMIDAL) i += 2 * (c_dim[con] - 1) - 1;
+      else if (type == B2MJ_CNSTR_CONTACT_ELLIPTIC) i += c_dim[con] - 1;
+    }
+    improvement *= scale;
+    iter++;
+    if (improvement < m.opt.noslip_tolerance) break;
   }
   return iter;
 }
@@ -1184,6 +1296,16 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
     WSYNC();
     iters = solvePrimal(e, nefc, ncon, newton);
     FORL(i, nv) warm[i] = qacc[i];
+    WSYNC();
+  }
+  // noslip pass: after the warm start of the next step has been saved
+  if (m.opt.noslip_iterations > 0) {
+    if (m.opt.solver != B2MJ_SOL_PGS) stage_projectConstraint(e, nefc, false);
+    iters += solveNoSlip(e, nefc, e.X(XF_VEC1));
+    mulJacTVec_warp(e, nefc, qfc, P.force);
+    double* tmp = e.X(XF_VEC2);
+    solveM_warp(e, tmp, qfc);
+    FORL(i, nv) qacc[i] = qas[i] + tmp[i];
     WSYNC();
   }
   return iters;

@@ -15,6 +15,7 @@ from parity_util import (TOL, compare_forward_fields, ctrl_sample, injected_step
 pytestmark = pytest.mark.gpu
 
 PGS, CG, NEWTON = 0, 1, 2
+STATE = ("qpos", "qvel", "act", "qacc_warmstart", "time", "ctrl")
 PYR, ELL = 0, 1
 EULER, RK4, IMPLICIT, IMPLICITFAST = 0, 1, 2, 3
 
@@ -201,6 +202,57 @@ def test_fluid_forces(name, integ, capi, orc, BatchSim):
     rng = np.random.default_rng(5)
     worst, _ = injected_steps(model, sim, oracles, 30, rng, tag=f"fluid:{name}")
     print(f"fluid {name}: injected-step worst {worst:.2e}")
+
+
+NOSLIP = [
+    ("panda_like.xml", PGS, PYR, 450, 30, 0.1, 16),
+    ("panda_like.xml", PGS, ELL, 450, 30, 0.1, 16),
+    ("panda_like.xml", NEWTON, ELL, 450, 30, 0.1, 16),
+    ("box_stack.xml", PGS, PYR, 150, 30, 0.1, 8),
+    ("box_stack.xml", NEWTON, ELL, 150, 30, 0.1, 8),
+    ("box_stack.xml", CG, PYR, 150, 30, 0.1, 8),
+    ("humanoid_like.xml", NEWTON, PYR, 120, 25, 0.02, 8),      # sparse L'DL path, friction-loss rows
+    ("humanoid_like.xml", PGS, ELL, 120, 25, 0.02, 8),
+    ("hand_like.xml", NEWTON, ELL, 100, 15, 0.02, 8),           # RK4: the noslip pass runs in every sub-step
+    ("bin.xml", NEWTON, ELL, 100, 6, 0.02, 2),                  # nv = 120: single-warp path instead of the team
+]
+
+
+@pytest.mark.parametrize("name,solver,cone,settle,nchk,amp,nenv", NOSLIP)
+def test_noslip_pass(name, solver, cone, settle, nchk, amp, nenv, capi, orc, BatchSim):
+    """opt.noslip_iterations > 0 (viewer.cpp:590-591): the unregularised friction sweep after the main solver."""
+    model = variant(capi, name, solver, cone)
+    model.opt.noslip_iterations = 4
+    model.opt.noslip_tolerance = 1e-12
+    tag = f"noslip:{name}[sol{solver} cone{cone}]"
+    qpos, qvel = perturbed(model, nenv, 41, amp)
+    rng = np.random.default_rng(17)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    for s in range(settle):
+        if model.nu and s % 25 == 0:
+            sim.set("ctrl", ctrl_sample(model, rng, nenv))
+        sim.step(1)
+    assert np.all(np.isfinite(sim.get("qpos")))
+    oracles = make_oracles(orc, model, sim.get("qpos"), sim.get("qvel"))
+    worst, max_nefc = injected_steps(model, sim, oracles, nchk, rng, tol=1e-4 if solver == CG else TOL, tag=tag)
+    # the pass must have run: solver_iter counts main + noslip iterations on both sides
+    st = {k: sim.get(k) for k in STATE if model.field_size_by_name(k) > 0}
+    sim.keep_intermediates(True)
+    sim.forward()
+    it = sim.get("solver_iter")[:, 0]
+    ff = sim.get("efc_force")
+    nefc = sim.get("nefc")[:, 0]
+    for e, o in enumerate(oracles):
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.forward()
+        if solver != CG:
+            assert int(o.get("solver_iter")[0]) == int(it[e]), (e, it[e], o.get("solver_iter"))
+        n = int(nefc[e])
+        assert rel(ff[e][:n], o.get("efc_force")[:n]) < (1e-3 if solver == CG else 1e-6), (e, n)
+    print(f"{tag}: injected-step worst {worst:.2e}, max nefc {max_nefc}")
 
 
 RANGE_SCENE = """

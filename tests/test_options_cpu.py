@@ -150,3 +150,43 @@ def test_ray_hits_caps_and_edges(capi, orc):
     # a plane seen from behind is not hit
     x, g = ray([0.9, 0.9, -1], [0, 0, 1], exclude=0)
     assert g != gid("floor")
+
+
+SLOPE = """
+<mujoco>
+  <option timestep="0.002" gravity="{gx} 0 -9.81" cone="{cone}" solver="{solver}" noslip_iterations="{ns}" noslip_tolerance="1e-10"/>
+  <worldbody>
+    <geom type="plane" size="5 5 0.1" friction="1 0.005 0.0001"/>
+    <body pos="0 0 0.1">
+      <freejoint/>
+      <geom type="box" size="0.1 0.1 0.1" friction="1 0.005 0.0001"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+@pytest.mark.parametrize("cone", ["pyramidal", "elliptic"])
+@pytest.mark.parametrize("solver", ["PGS", "Newton"])
+def test_noslip_removes_the_creep_of_soft_friction(capi, orc, cone, solver):
+    """A box on a floor pushed sideways well inside the friction cone: the regularised contact model lets it creep,
+    the noslip pass (viewer.cpp:590-591 exposes it) holds it.  Closed form: none -- the check is the ratio."""
+    drift = {}
+    for ns in (0, 20):
+        m = capi.Model.from_xml_string(SLOPE.format(gx=3.0, cone=cone, solver=solver, ns=ns))
+        o = orc.Oracle(m)
+        o.step(500)
+        drift[ns] = abs(o.get("qvel")[0])
+        assert abs(o.get("qpos")[2] - 0.1) < 2e-3        # still resting on the floor
+    assert drift[0] > 1e-4                               # soft friction creeps
+    assert drift[20] < 0.02 * drift[0], drift            # noslip holds
+
+
+def test_noslip_keeps_sliding_contacts_sliding(capi, orc):
+    """Outside the cone (tangential pull 1.5 g with mu = 1) the box must still accelerate at about (1.5 - 1) g."""
+    flat = SLOPE.replace('pos="0 0 0.1"', 'pos="0 0 0.01"').replace('size="0.1 0.1 0.1"', 'size="0.4 0.4 0.01"')  # cannot tip
+    m = capi.Model.from_xml_string(flat.format(gx=1.5 * 9.81, cone="elliptic", solver="Newton", ns=20))
+    o = orc.Oracle(m)
+    o.step(250)
+    a = o.get("qvel")[0] / (250 * 0.002)
+    assert abs(a - 0.5 * 9.81) < 0.05 * 9.81, a
