@@ -141,6 +141,7 @@ typedef struct b2mjStatistic {
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(nwrap) X(neq)          \
   X(nsensor) X(nsensordata) X(nM) X(nmocap) X(nexclude) X(ncollpair) X(nconmax) X(njmax)          \
   X(nnames) X(nlevel) X(ntree)                                                                    \
+  X(nmesh) X(nmeshvert)                                                                           \
   X(nkey) X(nkeyq) X(nkeyv) X(nkeya) X(nkeyu) X(nkeymp) X(nkeymq) /* keyframes; nkeyq = nkey*nq, ... (flat arrays) */
 
 /* X(ctype, name, rows(size field), cols) */
@@ -171,6 +172,9 @@ typedef struct b2mjStatistic {
   X(double, geom_solimp, ngeom, 5) X(double, geom_size, ngeom, 3) X(double, geom_rbound, ngeom, 1)\
   X(double, geom_pos, ngeom, 3) X(double, geom_quat, ngeom, 4) X(double, geom_friction, ngeom, 3) \
   X(double, geom_margin, ngeom, 1) X(double, geom_gap, ngeom, 1) X(double, geom_rgba, ngeom, 4)   \
+  X(int, geom_dataid, ngeom, 1) /* mesh id of a mesh geom, else -1 */                             \
+  X(int, mesh_vertadr, nmesh, 1) X(int, mesh_vertnum, nmesh, 1)                                   \
+  X(double, mesh_vert, nmeshvert, 3) /* convex-hull vertices, mesh frame = centre of mass + principal axes */ \
   X(int, site_bodyid, nsite, 1) X(int, site_type, nsite, 1) X(double, site_size, nsite, 3)        \
   X(double, site_pos, nsite, 3) X(double, site_quat, nsite, 4)                                    \
   X(int, tendon_adr, ntendon, 1) X(int, tendon_num, ntendon, 1) X(int, tendon_limited, ntendon, 1)\

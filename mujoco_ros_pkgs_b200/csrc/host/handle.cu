@@ -236,13 +236,8 @@ static int upload_model(Handle* h) {
 static int check_supported(const b2mjModel* m) {
   for (int p = 0; p < m->ncollpair; p++) {
     const int t1 = m->geom_type[m->collpair_geom1[p]], t2 = m->geom_type[m->collpair_geom2[p]];
-    const bool ok = (t1 == B2MJ_GEOM_PLANE && (t2 == B2MJ_GEOM_SPHERE || t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
-                    (t1 == B2MJ_GEOM_SPHERE && (t2 == B2MJ_GEOM_SPHERE || t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
-                    (t1 == B2MJ_GEOM_CAPSULE && (t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) ||
-                    (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX);
-    if (!ok) {
-      set_error("collision between geom types " + std::to_string(t1) + " and " + std::to_string(t2) +
-                " is not implemented in the CUDA narrowphase (cylinder / ellipsoid / mesh / hfield)");
+    if (t1 == B2MJ_GEOM_HFIELD || t2 == B2MJ_GEOM_HFIELD) {
+      set_error("collision with height fields is not implemented in the CUDA narrowphase");
       return B2MJ_EUNSUPPORTED;
     }
   }

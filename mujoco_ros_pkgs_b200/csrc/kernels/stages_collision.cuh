@@ -8,18 +8,11 @@
 // every contact its final index — no atomics, the contact order is a pure function of the geometry.
 #pragma once
 #include "env_ctx.cuh"
+#include "pair_con.cuh"
+#include "stages_convex.cuh"
 
 namespace b2k {
 
-#define B2K_MAXPAIRCON 8
-#define B2K_MAXPAIRFRAME 4
-
-struct PairCon {
-  double dist[B2K_MAXPAIRCON];
-  double pos[3 * B2K_MAXPAIRCON];
-  double frame[6 * B2K_MAXPAIRFRAME];  // normal + tangent hint per contact, or one for all (shared_frame)
-  int shared_frame;
-};
 
 __device__ __forceinline__ int c_planeSphere(PairCon& o, int n, double margin, const double* pos1, const double* mat1,
                                              const double* pos2, double radius) {
@@ -306,6 +299,8 @@ __device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat
       B2K_NOUNROLL for (int i = 0; i < n; i++) copy3(o.frame + 6 * i + 3, axis);
       return n;
     }
+    if (t2 == B2MJ_GEOM_CYLINDER) return c_planeCylinder(o, margin, pos1, mat1, pos2, mat2, size2);
+    if (t2 == B2MJ_GEOM_ELLIPSOID || t2 == B2MJ_GEOM_MESH) return c_planeConvex(o, margin, pos1, mat1, cvxGeom(gxpos, gxmat, g2));
     if (t2 == B2MJ_GEOM_BOX) {
       double normal[3] = {mat1[2], mat1[5], mat1[8]}, dif[3];
       sub3(dif, pos2, pos1);
@@ -340,7 +335,6 @@ __device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat
       return c_sphereSphere(o, 0, margin, pos1, size1[0], p, size2[0]);
     }
     if (t2 == B2MJ_GEOM_BOX) return c_sphereBox(o, 0, margin, pos1, size1[0], pos2, mat2, size2);
-    return 0;
   }
   if (t1 == B2MJ_GEOM_CAPSULE) {
     if (t2 == B2MJ_GEOM_CAPSULE) {
@@ -395,9 +389,11 @@ __device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat
       }
       return n;
     }
-    return 0;
   }
   if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) return c_boxBox(o, margin, pos1, mat1, size1, pos2, mat2, size2);
+  // every other pair of convex geoms (anything with an ellipsoid, a cylinder or a mesh): the general MPR test
+  if (t1 >= B2MJ_GEOM_SPHERE && t1 <= B2MJ_GEOM_MESH && t2 >= B2MJ_GEOM_SPHERE && t2 <= B2MJ_GEOM_MESH)
+    return c_convexConvex(o, margin, cvxGeom(gxpos, gxmat, g1), cvxGeom(gxpos, gxmat, g2));
   return 0;
 }
 

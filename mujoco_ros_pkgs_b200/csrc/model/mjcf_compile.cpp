@@ -938,6 +938,7 @@ b2mjModel* compile(const XmlNode* root) {
         m->geom_margin[g] = gm.margin;
         m->geom_gap[g] = gm.gap;
         for (int k = 0; k < 4; k++) m->geom_rgba[4 * g + k] = gm.rgba[k];
+        m->geom_dataid[g] = -1;
         double rb = 0;
         switch (gm.type) {
           case B2MJ_GEOM_SPHERE: rb = gm.size[0]; break;
@@ -1361,7 +1362,8 @@ void model_build_collision_pairs(b2mjModel* m) {
           if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_PLANE) continue;
           int mc = 1;
           if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_CAPSULE) mc = 2;
-          else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_CYLINDER) mc = 3;
+          else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_CYLINDER) mc = 4;
+          else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_MESH) mc = 4;
           else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_BOX) mc = 4;
           else if (t1 == B2MJ_GEOM_CAPSULE && t2 == B2MJ_GEOM_CAPSULE) mc = 2;
           else if (t1 == B2MJ_GEOM_CAPSULE && t2 == B2MJ_GEOM_BOX) mc = 2;

@@ -12,14 +12,11 @@
 #include <algorithm>
 #include <cmath>
 
+#include "orc_convex.h"
 #include "orc_math.h"
 #include "orc_types.h"
 
 namespace orc {
-
-struct Con {
-  double dist, pos[3], frame[9];
-};
 
 static int planeSphere(Con* con, double margin, const double* pos1, const double* mat1, const double* pos2, double radius) {
   double normal[3] = {mat1[2], mat1[5], mat1[8]}, tmp[3];
@@ -392,24 +389,33 @@ static int narrowphase(const b2mjModel* m, const OrcData* d, Con* con, int g1, i
   const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
   const double *pos1 = d->geom_xpos + 3 * g1, *mat1 = d->geom_xmat + 9 * g1, *size1 = m->geom_size + 3 * g1;
   const double *pos2 = d->geom_xpos + 3 * g2, *mat2 = d->geom_xmat + 9 * g2, *size2 = m->geom_size + 3 * g2;
+  auto convex = [&](int g, int t, const double* pos, const double* mat, const double* size) {
+    ConvexGeom c{t, pos, mat, size, nullptr, 0};
+    if (t == B2MJ_GEOM_MESH && m->geom_dataid[g] >= 0) {
+      const int id = m->geom_dataid[g];
+      c.vert = m->mesh_vert + 3 * m->mesh_vertadr[id];
+      c.nvert = m->mesh_vertnum[id];
+    }
+    return c;
+  };
   if (t1 == B2MJ_GEOM_PLANE) {
     if (t2 == B2MJ_GEOM_SPHERE) return planeSphere(con, margin, pos1, mat1, pos2, size2[0]);
     if (t2 == B2MJ_GEOM_CAPSULE) return planeCapsule(con, margin, pos1, mat1, pos2, mat2, size2);
     if (t2 == B2MJ_GEOM_BOX) return planeBox(con, margin, pos1, mat1, pos2, mat2, size2);
+    if (t2 == B2MJ_GEOM_CYLINDER) return planeCylinder(con, margin, pos1, mat1, pos2, mat2, size2);
+    if (t2 == B2MJ_GEOM_ELLIPSOID || t2 == B2MJ_GEOM_MESH) return planeConvex(con, margin, pos1, mat1, convex(g2, t2, pos2, mat2, size2));
     return -1;
   }
-  if (t1 == B2MJ_GEOM_SPHERE) {
-    if (t2 == B2MJ_GEOM_SPHERE) return sphereSphere(con, margin, pos1, size1[0], pos2, size2[0]);
-    if (t2 == B2MJ_GEOM_CAPSULE) return sphereCapsule(con, margin, pos1, size1[0], pos2, mat2, size2);
-    if (t2 == B2MJ_GEOM_BOX) return sphereBox(con, margin, pos1, size1[0], pos2, mat2, size2);
-    return -1;
-  }
-  if (t1 == B2MJ_GEOM_CAPSULE) {
-    if (t2 == B2MJ_GEOM_CAPSULE) return capsuleCapsule(con, margin, pos1, mat1, size1, pos2, mat2, size2);
-    if (t2 == B2MJ_GEOM_BOX) return capsuleBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
-    return -1;
-  }
+  // pairs with a dedicated primitive function (mjCOLLISIONFUNC); every other convex pair goes to the general MPR test
+  if (t1 == B2MJ_GEOM_SPHERE && t2 == B2MJ_GEOM_SPHERE) return sphereSphere(con, margin, pos1, size1[0], pos2, size2[0]);
+  if (t1 == B2MJ_GEOM_SPHERE && t2 == B2MJ_GEOM_CAPSULE) return sphereCapsule(con, margin, pos1, size1[0], pos2, mat2, size2);
+  if (t1 == B2MJ_GEOM_SPHERE && t2 == B2MJ_GEOM_BOX) return sphereBox(con, margin, pos1, size1[0], pos2, mat2, size2);
+  if (t1 == B2MJ_GEOM_CAPSULE && t2 == B2MJ_GEOM_CAPSULE) return capsuleCapsule(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+  if (t1 == B2MJ_GEOM_CAPSULE && t2 == B2MJ_GEOM_BOX) return capsuleBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
   if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) return boxBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+  if (t1 >= B2MJ_GEOM_SPHERE && t1 <= B2MJ_GEOM_MESH && t2 >= B2MJ_GEOM_SPHERE && t2 <= B2MJ_GEOM_MESH)
+    return convexConvex(con, margin, convex(g1, t1, pos1, mat1, size1), convex(g2, t2, pos2, mat2, size2),
+                        m->opt.mpr_iterations, m->opt.mpr_tolerance);
   return -1;
 }
 

@@ -255,6 +255,71 @@ def test_noslip_pass(name, solver, cone, settle, nchk, amp, nenv, capi, orc, Bat
     print(f"{tag}: injected-step worst {worst:.2e}, max nefc {max_nefc}")
 
 
+CONVEX_PILE = """
+<mujoco>
+  <option timestep="0.002" solver="Newton" cone="elliptic"/>
+  <worldbody>
+    <geom type="plane" size="3 3 0.1"/>
+    <geom type="box" size="0.3 0.3 0.05" pos="0 0 0.05"/>
+    <geom type="cylinder" size="0.15 0.1" pos="0.6 0 0.1"/>
+    <body pos="0 0 0.4"><freejoint/><geom type="cylinder" size="0.08 0.12" density="600"/></body>
+    <body pos="0.05 0.02 0.75" euler="40 20 0"><freejoint/><geom type="ellipsoid" size="0.07 0.1 0.13" density="600"/></body>
+    <body pos="-0.1 0.05 1.1" euler="0 80 10"><freejoint/><geom type="cylinder" size="0.06 0.15" density="600"/></body>
+    <body pos="0.6 0.02 0.5" euler="10 10 0"><freejoint/><geom type="ellipsoid" size="0.1 0.08 0.06" density="600"/></body>
+    <body pos="0.62 -0.03 0.8"><freejoint/><geom type="sphere" size="0.07" density="600"/></body>
+    <body pos="0.0 0.5 0.3" euler="0 90 0"><freejoint/><geom type="capsule" size="0.05 0.12" density="600"/></body>
+    <body pos="0.02 0.52 0.6" euler="30 0 30"><freejoint/><geom type="ellipsoid" size="0.09 0.06 0.05" density="600"/></body>
+    <body pos="-0.5 -0.5 0.3" euler="20 30 0"><freejoint/><geom type="box" size="0.08 0.06 0.05" density="600"/></body>
+    <body pos="-0.52 -0.48 0.6" euler="70 0 0"><freejoint/><geom type="cylinder" size="0.05 0.1" density="600"/></body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def test_convex_pairs(capi, orc, BatchSim):
+    """Cylinders and ellipsoids against planes, boxes, spheres, capsules and each other: plane-cylinder, plane-convex
+    and the MPR test (stages_convex.cuh).  Both sides run the same portal refinement, so contacts agree to round-off
+    (measured: distance 1e-15, normal 4e-12, per-step state 2e-9); the bounds below leave room for an iterate that lands
+    on the other side of a branch under FMA contraction, which would end one refinement (<= mpr_tolerance) apart."""
+    model = capi.Model.from_xml_string(CONVEX_PILE)
+    nenv = 6
+    qpos, qvel = perturbed(model, nenv, 23, 0.02)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    for _ in range(6):
+        sim.step(50)
+        assert np.all(np.isfinite(sim.get("qpos")))
+    oracles = make_oracles(orc, model, sim.get("qpos"), sim.get("qvel"))
+    st = {k: sim.get(k) for k in STATE if model.field_size_by_name(k) > 0}
+    sim.keep_intermediates(True)
+    sim.forward()
+    ncon = sim.get("ncon")[:, 0]
+    g1, g2 = sim.get("contact_geom1"), sim.get("contact_geom2")
+    dist, pos, frame = sim.get("contact_dist"), sim.get("contact_pos"), sim.get("contact_frame")
+    seen = set()
+    worst_d = worst_n = 0.0
+    for e, o in enumerate(oracles):
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.forward()
+        n = int(o.get("ncon")[0])
+        assert n == int(ncon[e]), (e, n, ncon[e])
+        np.testing.assert_array_equal(g1[e][:n], o.get("contact_geom1")[:n])
+        np.testing.assert_array_equal(g2[e][:n], o.get("contact_geom2")[:n])
+        for c in range(n):
+            seen.add((int(model.geom_type[g1[e][c]]), int(model.geom_type[g2[e][c]])))
+        worst_d = max(worst_d, float(np.max(np.abs(dist[e][:n] - o.get("contact_dist")[:n]))))
+        worst_n = max(worst_n, float(np.max(np.abs(frame[e][:9 * n].reshape(n, 9)[:, :3] - o.get("contact_frame")[:9 * n].reshape(n, 9)[:, :3]))))
+        assert np.max(np.abs(pos[e][:3 * n] - o.get("contact_pos")[:3 * n])) < 5e-3
+    assert worst_d < 2e-6 and worst_n < 1e-3, (worst_d, worst_n)
+    assert (0, 5) in seen and (0, 4) in seen and len([p for p in seen if 4 in p or 5 in p]) >= 5, seen
+    rng = np.random.default_rng(1)
+    sim.keep_intermediates(False)
+    worst, _ = injected_steps(model, sim, oracles, 40, rng, tol=TOL, tag="convex pile")
+    print(f"convex pile: pair types {sorted(seen)}, contact dist worst {worst_d:.1e}, normal worst {worst_n:.1e}, step worst {worst:.1e}")
+
+
 RANGE_SCENE = """
 <mujoco>
   <option timestep="0.002"/>
