@@ -255,16 +255,55 @@ __device__ __noinline__ void stage_tendon_transmission(const Env e) {
   if (m.ntendon) {
     double* tl = e.D(B2MJ_F_TEN_LENGTH);
     double* tJ = e.D(B2MJ_F_TEN_J);
-    FORL(k, m.ntendon * nv) tJ[k] = 0;
-    WSYNC();
-    FORL(i, m.ntendon) {
-      double len = 0;
-      B2K_NOUNROLL for (int w = m.tendon_adr[i]; w < m.tendon_adr[i] + m.tendon_num[i]; w++) {
-        const int jid = m.wrap_objid[w];
-        len += m.wrap_prm[w] * qpos[m.jnt_qposadr[jid]];
-        tJ[i * nv + m.jnt_dofadr[jid]] = m.wrap_prm[w];
+    // one lane per (tendon, dof) entry of ten_J; the lane of dof 0 also accumulates the length.  Fixed tendons: joint
+    // coefficients (mjWRAP_JOINT = 1).  Spatial tendons: site - site segments (mjWRAP_SITE = 3) scaled by the pulley
+    // divisor in force (mjWRAP_PULLEY = 2); the Jacobian entry is the segment direction dotted with the difference of
+    // the two sites' point-Jacobian columns (mj_jacDifPair), formed from cdof and the chain bit masks.
+    const double* sxpos = m.nsite ? e.D(B2MJ_F_SITE_XPOS) : nullptr;
+    const double* cdof = e.D(B2MJ_F_CDOF);
+    const double* com = e.D(B2MJ_F_SUBTREE_COM);
+    FORL(item, m.ntendon * nv) {
+      const int i = item / nv, k = item - i * nv;
+      double len = 0, jk = 0, divisor = 1;
+      const int w0 = m.tendon_adr[i], w1 = w0 + m.tendon_num[i];
+      B2K_NOUNROLL for (int w = w0; w < w1; w++) {
+        const int type = m.wrap_type[w];
+        if (type == 1) {
+          const int jid = m.wrap_objid[w];
+          len += m.wrap_prm[w] * qpos[m.jnt_qposadr[jid]];
+          if (m.jnt_dofadr[jid] == k) jk = m.wrap_prm[w];
+        } else if (type == 2) {
+          divisor = m.wrap_prm[w];
+        } else if (type == 3 && w + 1 < w1 && m.wrap_type[w + 1] == 3) {
+          const int s0 = m.wrap_objid[w], s1 = m.wrap_objid[w + 1], b0 = m.site_bodyid[s0], b1 = m.site_bodyid[s1];
+          const double *p0 = sxpos + 3 * s0, *p1 = sxpos + 3 * s1;
+          double dif[3];
+          sub3(dif, p1, p0);
+          const double seg = normalize3(dif);
+          len += seg / divisor;
+          if (b0 != b1) {
+            const double* cd = cdof + 6 * k;
+            double s = 0;
+            const unsigned* m1 = m.body_dofmask + b1 * m.nmaskword;
+            const unsigned* m0 = m.body_dofmask + b0 * m.nmaskword;
+            if ((m1[k >> 5] >> (k & 31)) & 1u) {
+              double off[3], cr[3];
+              sub3(off, p1, com + 3 * m.body_rootid[b1]);
+              cross(cr, cd, off);
+              s += dif[0] * (cd[3] + cr[0]) + dif[1] * (cd[4] + cr[1]) + dif[2] * (cd[5] + cr[2]);
+            }
+            if ((m0[k >> 5] >> (k & 31)) & 1u) {
+              double off[3], cr[3];
+              sub3(off, p0, com + 3 * m.body_rootid[b0]);
+              cross(cr, cd, off);
+              s -= dif[0] * (cd[3] + cr[0]) + dif[1] * (cd[4] + cr[1]) + dif[2] * (cd[5] + cr[2]);
+            }
+            jk += s / divisor;
+          }
+        }
       }
-      tl[i] = len;
+      tJ[item] = jk;
+      if (k == 0) tl[i] = len;
     }
     WSYNC();
   }

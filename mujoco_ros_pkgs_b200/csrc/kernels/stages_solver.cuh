@@ -420,19 +420,60 @@ __device__ __forceinline__ int solvePGS_own_T(const Env e, int nefc, const doubl
     pcol += nefc;                                                              \
     i++;                                                                       \
   }
+  // The same row with the cost guard taken OFF the serial chain: the candidate change is broadcast at once, the guard
+  // (change > 1e-10: only ever true through round-off, the clamped 1-D minimiser cannot raise the cost) is evaluated
+  // beside the shuffle and only recorded.  A sweep in which some guard fired is thrown away and redone from the saved
+  // (f, r) with the guarded row above, so the result is bitwise the guarded algorithm's; the serial chain per row drops
+  // from FMA, clamp, ADD, FMA, MUL, SETP, SEL, SHFL, FMA to FMA, clamp, ADD, SHFL, FMA.
+#define B2K_PGS_OWN_ROW_FAST(SLOT)                                             \
+  {                                                                            \
+    const double ai = SLOT;                                                    \
+    const double x = f - r * iA;                                               \
+    double fn;                                                                 \
+    if (SIMPLE) {                                                              \
+      fn = (pos && __double2hiint(x) < 0) ? 0.0 : x;                           \
+    } else {                                                                   \
+      fn = x < lo ? lo : x;                                                    \
+      fn = fn > up ? up : fn;                                                  \
+    }                                                                          \
+    const double delta = fn - f;                                               \
+    const double d = __shfl_sync(e.mask, delta, i, B2K_G);                     \
+    const double change = delta * (hA * delta + r);                            \
+    r += ai * d;                                                               \
+    if (lane == i) { f = fn; improvement -= change; fail |= change > 1e-10; }  \
+    SLOT = *pcol;                                                              \
+    pcol += nefc;                                                              \
+    i++;                                                                       \
+  }
   while (iter < maxiter) {
     double improvement = 0;  // this lane's own row only; summed over the warp once per sweep
-    double p0 = q0, p1 = q1;
-    const double* pcol = col + 2 * nefc;
-    int i = 0;
-    B2K_NOUNROLL while (i + 2 <= nefc) {
-      B2K_PGS_OWN_ROW(p0)
-      B2K_PGS_OWN_ROW(p1)
+    const double f_save = f, r_save = r;
+    bool fail = false;
+    {
+      double p0 = q0, p1 = q1;
+      const double* pcol = col + 2 * nefc;
+      int i = 0;
+      B2K_NOUNROLL while (i + 2 <= nefc) {
+        B2K_PGS_OWN_ROW_FAST(p0)
+        B2K_PGS_OWN_ROW_FAST(p1)
+      }
+      if (i < nefc) B2K_PGS_OWN_ROW_FAST(p0)
     }
-    if (i < nefc) B2K_PGS_OWN_ROW(p0)
+    if (__any_sync(e.mask, fail)) {  // redo the sweep with the guard on the chain
+      f = f_save; r = r_save; improvement = 0;
+      double p0 = q0, p1 = q1;
+      const double* pcol = col + 2 * nefc;
+      int i = 0;
+      B2K_NOUNROLL while (i + 2 <= nefc) {
+        B2K_PGS_OWN_ROW(p0)
+        B2K_PGS_OWN_ROW(p1)
+      }
+      if (i < nefc) B2K_PGS_OWN_ROW(p0)
+    }
     iter++;
     if (warpSum(e.mask, improvement) * scale < tol) break;
   }
+#undef B2K_PGS_OWN_ROW_FAST
 #undef B2K_PGS_OWN_ROW
   *f_out = f;
   return iter;

@@ -290,4 +290,8 @@ bool mesh_read_file(const std::string& path, std::vector<double>& pts, std::stri
   return true;
 }
 
+static thread_local std::string g_model_dir;
+void set_model_dir(const std::string& dir) { g_model_dir = dir; }
+const std::string& model_dir() { return g_model_dir; }
+
 }  // namespace b2mj

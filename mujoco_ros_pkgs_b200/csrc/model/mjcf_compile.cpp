@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "hostmath.h"
+#include "mesh.h"
 #include "model_core.h"
 #include "xml_mini.h"
 
@@ -48,6 +49,9 @@ struct Ctx {
   double boundmass = 0, boundinertia = 0;
   std::map<std::string, std::map<std::string, AttrMap>> defaults;  // class -> group -> attrs
   std::map<std::string, std::string> class_parent;
+  std::string meshdir;
+  std::vector<MeshData> meshes;
+  std::map<std::string, int> mesh_id;
 };
 
 std::vector<double> parse_nums(const std::string& s) {
@@ -190,6 +194,8 @@ struct CGeom {
   double solmix = 1, margin = 0, gap = 0, mass = 0;
   double inertia[3] = {0, 0, 0};
   double rgba[4] = {0.5, 0.5, 0.5, 1};
+  int meshid = -1;
+  double mesh_volume = 0, mesh_inertia[3] = {0, 0, 0}, rbound = 0;
   int contype = 1, conaffinity = 1, condim = 3, priority = 0;
 };
 struct CSite {
@@ -216,7 +222,8 @@ int geom_type_from(const XmlNode* n, const std::string& s) {
   if (s == "ellipsoid") return B2MJ_GEOM_ELLIPSOID;
   if (s == "cylinder") return B2MJ_GEOM_CYLINDER;
   if (s == "box") return B2MJ_GEOM_BOX;
-  fail(n, "unsupported geom/site type '" + s + "' (hfield/mesh are out of scope)");
+  if (s == "mesh") return B2MJ_GEOM_MESH;
+  fail(n, "unsupported geom/site type '" + s + "' (hfield is out of scope)");
 }
 
 // volume and principal inertia (unit density scaled by mass later) of a primitive
@@ -255,6 +262,10 @@ void geom_mass_props(const CGeom& g, double density, bool explicit_mass, double*
       I[0] = (g.size[1] * g.size[1] + g.size[2] * g.size[2]) / 3;
       I[1] = (g.size[0] * g.size[0] + g.size[2] * g.size[2]) / 3;
       I[2] = (g.size[0] * g.size[0] + g.size[1] * g.size[1]) / 3;
+      break;
+    case B2MJ_GEOM_MESH:
+      vol = g.mesh_volume;
+      for (int k = 0; k < 3; k++) I[k] = g.mesh_inertia[k] / vol;
       break;
     default: break;  // plane: massless
   }
@@ -379,10 +390,28 @@ struct Builder {
     AttrMap em = effective(ctx, n, childclass);
     A a{em, n};
     g.name = a.str("name");
-    g.type = geom_type_from(n, a.str("type", "sphere"));
+    g.type = geom_type_from(n, a.str("type", a.has("mesh") ? "mesh" : "sphere"));
     int ns = a.vec("size", g.size, 3);
     a.vec("pos", g.pos, 3, 3);
     orientation(ctx, a, g.quat);
+    if (g.type == B2MJ_GEOM_MESH) {
+      // the mesh frame (centre of mass + principal axes) is folded into the geom pose, as the MuJoCo compiler does
+      if (!a.has("mesh")) fail(n, "mesh geom needs a mesh attribute");
+      auto it = ctx.mesh_id.find(a.str("mesh"));
+      if (it == ctx.mesh_id.end()) fail(n, "unknown mesh '" + a.str("mesh") + "'");
+      const MeshData& md = ctx.meshes[it->second];
+      g.meshid = it->second;
+      double off[3], q[4];
+      rotvecquat(off, md.pos, g.quat);
+      for (int k = 0; k < 3; k++) g.pos[k] += off[k];
+      mulquat(q, g.quat, md.quat);
+      std::copy(q, q + 4, g.quat);
+      std::copy(md.aabb, md.aabb + 3, g.size);
+      g.mesh_volume = md.volume;
+      std::copy(md.inertia, md.inertia + 3, g.mesh_inertia);
+      g.rbound = md.rbound;
+      ns = 3;
+    }
     if (a.has("fromto")) {
       double ft[6];
       a.vec("fromto", ft, 6, 6);
@@ -398,7 +427,7 @@ struct Builder {
       else g.size[1] = len / 2;
     } else {
       int need = (g.type == B2MJ_GEOM_SPHERE) ? 1 : (g.type == B2MJ_GEOM_CAPSULE || g.type == B2MJ_GEOM_CYLINDER) ? 2
-                 : (g.type == B2MJ_GEOM_PLANE) ? 0 : 3;
+                 : (g.type == B2MJ_GEOM_PLANE || g.type == B2MJ_GEOM_MESH) ? 0 : 3;
       if (ns < need) fail(n, "geom size needs " + std::to_string(need) + " values");
     }
     int nf = a.vec("friction", g.friction, 3);
@@ -626,6 +655,7 @@ b2mjModel* compile(const XmlNode* root) {
         if (ctx.eulerseq.size() != 3) fail(sec.get(), "eulerseq needs 3 characters");
       }
       if (a.has("autolimits")) ctx.autolimits = a.str("autolimits") == "true";
+      if (a.has("meshdir")) ctx.meshdir = a.str("meshdir");
       if (a.has("inertiafromgeom")) {
         std::string s = a.str("inertiafromgeom");
         ctx.inertiafromgeom = s == "true" ? 1 : s == "false" ? 0 : 2;
@@ -697,6 +727,44 @@ b2mjModel* compile(const XmlNode* root) {
       B.read_defaults(sec.get(), "main", "");
     }
   }
+  // ---- assets: meshes (textures / materials only matter to rendering and are skipped)
+  for (auto& sec : root->children) {
+    if (sec->tag != "asset") continue;
+    for (auto& ch : sec->children) {
+      if (ch->tag != "mesh") continue;
+      AttrMap em = effective(ctx, ch.get(), "");
+      A a{em, ch.get()};
+      std::vector<double> pts;
+      std::string name = a.str("name"), err;
+      if (a.has("vertex")) {
+        pts = parse_nums(a.str("vertex"));
+        if (pts.size() % 3 || pts.size() < 12) fail(ch.get(), "mesh vertex data needs at least 4 points of 3 numbers");
+      } else if (a.has("file")) {
+        std::string file = a.str("file");
+        if (name.empty()) {
+          const size_t sl = file.find_last_of("/\\"), dot = file.find_last_of('.');
+          name = file.substr(sl == std::string::npos ? 0 : sl + 1, dot == std::string::npos ? std::string::npos : dot - (sl == std::string::npos ? 0 : sl + 1));
+        }
+        if (file.empty() || file[0] != '/') {
+          std::string base = ctx.meshdir;
+          if (base.empty() || base[0] != '/') base = model_dir() + (model_dir().empty() || base.empty() ? "" : "/") + base;
+          file = base + (base.empty() ? "" : "/") + file;
+        }
+        if (!mesh_read_file(file, pts, err)) fail(ch.get(), err);
+      } else {
+        fail(ch.get(), "mesh needs a file or a vertex attribute");
+      }
+      if (a.has("refpos") || a.has("refquat")) fail(ch.get(), "mesh refpos / refquat are not supported");
+      if (name.empty()) fail(ch.get(), "mesh needs a name");
+      double scale[3] = {1, 1, 1};
+      a.vec("scale", scale, 3, 3);
+      MeshData md;
+      if (!mesh_process(pts, scale, md, err)) fail(ch.get(), "mesh '" + name + "': " + err);
+      if (ctx.mesh_id.count(name)) fail(ch.get(), "repeated mesh name '" + name + "'");
+      ctx.mesh_id[name] = (int)ctx.meshes.size();
+      ctx.meshes.push_back(std::move(md));
+    }
+  }
 
   // ---- pass 2: kinematic tree
   B.bodies.emplace_back();  // world
@@ -723,7 +791,7 @@ b2mjModel* compile(const XmlNode* root) {
   for (auto& sec : root->children) {
     if (sec->tag == "tendon")
       for (auto& ch : sec->children) {
-        if (ch->tag != "fixed") fail(ch.get(), "only fixed tendons are supported");
+        if (ch->tag != "fixed" && ch->tag != "spatial") fail(ch.get(), "tendons are <fixed> or <spatial>");
         tendon_nodes.push_back(ch.get());
       }
     else if (sec->tag == "actuator")
@@ -764,6 +832,9 @@ b2mjModel* compile(const XmlNode* root) {
   m->ntendon = (int)tendon_nodes.size(); m->nwrap = nwrap; m->nu = (int)act_nodes.size();
   m->neq = (int)eq_nodes.size(); m->nexclude = (int)excl_nodes.size(); m->nsensor = (int)sens_nodes.size();
   m->nsensordata = nsensordata; m->nmocap = nmocap;
+  m->nmesh = (int)ctx.meshes.size();
+  m->nmeshvert = 0;
+  for (auto& md : ctx.meshes) m->nmeshvert += (int)md.vert.size() / 3;
   m->nkey = (int)key_nodes.size();
   m->nkeyq = m->nkey * nq; m->nkeyv = m->nkey * nv; m->nkeyu = m->nkey * m->nu;
   m->nkeymp = m->nkey * 3 * nmocap; m->nkeymq = m->nkey * 4 * nmocap;
@@ -853,6 +924,16 @@ b2mjModel* compile(const XmlNode* root) {
   std::copy(nsn_adr.begin(), nsn_adr.end(), m->name_sensoradr);
   std::copy(ne_adr.begin(), ne_adr.end(), m->name_eqadr);
   std::copy(nk_adr.begin(), nk_adr.end(), m->name_keyadr);
+  {
+    int adr = 0;
+    for (int i = 0; i < m->nmesh; i++) {
+      const MeshData& md = ctx.meshes[i];
+      m->mesh_vertadr[i] = adr;
+      m->mesh_vertnum[i] = (int)md.vert.size() / 3;
+      std::copy(md.vert.begin(), md.vert.end(), m->mesh_vert + 3 * adr);
+      adr += m->mesh_vertnum[i];
+    }
+  }
 
   // ---- fill body / joint / dof / geom / site arrays
   {
@@ -938,7 +1019,7 @@ b2mjModel* compile(const XmlNode* root) {
         m->geom_margin[g] = gm.margin;
         m->geom_gap[g] = gm.gap;
         for (int k = 0; k < 4; k++) m->geom_rgba[4 * g + k] = gm.rgba[k];
-        m->geom_dataid[g] = -1;
+        m->geom_dataid[g] = gm.meshid;
         double rb = 0;
         switch (gm.type) {
           case B2MJ_GEOM_SPHERE: rb = gm.size[0]; break;
@@ -946,6 +1027,7 @@ b2mjModel* compile(const XmlNode* root) {
           case B2MJ_GEOM_CYLINDER: rb = std::sqrt(gm.size[0] * gm.size[0] + gm.size[1] * gm.size[1]); break;
           case B2MJ_GEOM_ELLIPSOID: rb = std::max(gm.size[0], std::max(gm.size[1], gm.size[2])); break;
           case B2MJ_GEOM_BOX: rb = norm3(gm.size); break;
+          case B2MJ_GEOM_MESH: rb = gm.rbound; break;
           default: rb = 0;
         }
         m->geom_rbound[g] = rb;
@@ -1023,6 +1105,35 @@ b2mjModel* compile(const XmlNode* root) {
       if (nsl == 1) sl[1] = sl[0];
       m->tendon_lengthspring[2 * t] = sl[0];
       m->tendon_lengthspring[2 * t + 1] = sl[1];
+      if (n->tag == "spatial") {
+        // path through sites, with pulleys splitting it into branches (mjWRAP_SITE = 3, mjWRAP_PULLEY = 2); wrapping
+        // around sphere / cylinder geoms is not supported
+        int nsite_in_branch = 0;
+        for (auto& ch : n->children) {
+          if (ch->tag == "site") {
+            auto* sn = ch->attr("site");
+            if (!sn) fail(ch.get(), "missing site attribute");
+            m->wrap_type[w] = 3;
+            m->wrap_objid[w] = lookup(B.site_id, ch.get(), "site", *sn);
+            m->wrap_prm[w] = 0;
+            nsite_in_branch++;
+          } else if (ch->tag == "pulley") {
+            if (nsite_in_branch == 1) fail(ch.get(), "a tendon branch needs at least two sites");
+            auto* dv = ch->attr("divisor");
+            if (!dv) fail(ch.get(), "pulley needs a divisor");
+            m->wrap_type[w] = 2;
+            m->wrap_objid[w] = -1;
+            m->wrap_prm[w] = parse_nums(*dv).at(0);
+            if (m->wrap_prm[w] <= 0) fail(ch.get(), "pulley divisor must be positive");
+            nsite_in_branch = 0;
+          } else {
+            fail(ch.get(), "spatial tendon paths accept <site> and <pulley> (geom wrapping is not supported)");
+          }
+          w++;
+        }
+        if (nsite_in_branch < 2) fail(n, "a spatial tendon must end with a branch of at least two sites");
+        continue;
+      }
       for (auto& ch : n->children) {
         if (ch->tag != "joint") fail(ch.get(), "fixed tendon accepts only <joint>");
         auto* jn = ch->attr("joint");
@@ -1432,7 +1543,13 @@ int b2mj_model_from_xml_file(const char* path, b2mjModel** out) {
   }
   std::stringstream ss;
   ss << f.rdbuf();
-  return b2mj_model_from_xml_string(ss.str().c_str(), out);
+  // relative mesh files are resolved against the directory of the model file (plus compiler meshdir)
+  const std::string p(path);
+  const size_t sl = p.find_last_of('/');
+  set_model_dir(sl == std::string::npos ? std::string(".") : p.substr(0, sl));
+  const int rc = b2mj_model_from_xml_string(ss.str().c_str(), out);
+  set_model_dir("");
+  return rc;
 }
 
 }  // extern "C"

@@ -291,15 +291,39 @@ int model_set_const(b2mjModel* m, std::string& err) {
     m->body_invweight0[2 * i + 1] = trr / 3;
   }
   m->stat.meanmass = nb > 1 ? meanmass / (nb - 1) : 0;
-  // tendons (fixed): length0, invweight0
+  // tendons: length0, invweight0 (fixed: joint coefficients; spatial: site path with pulley divisors)
+  std::vector<double> tenJ((size_t)m->ntendon * (nv + 1), 0.0);
   for (int t = 0; t < m->ntendon; t++) {
     std::fill(x.begin(), x.end(), 0.0);
-    std::vector<double> J(nv + 1, 0.0);
-    double len = 0;
-    for (int w = m->tendon_adr[t]; w < m->tendon_adr[t] + m->tendon_num[t]; w++) {
-      int jid = m->wrap_objid[w];
-      len += m->wrap_prm[w] * m->qpos0[m->jnt_qposadr[jid]];
-      J[m->jnt_dofadr[jid]] = m->wrap_prm[w];
+    double* J = &tenJ[(size_t)t * (nv + 1)];
+    double len = 0, divisor = 1;
+    const int w0 = m->tendon_adr[t], w1 = w0 + m->tendon_num[t];
+    for (int w = w0; w < w1; w++) {
+      if (m->wrap_type[w] == 1) {
+        int jid = m->wrap_objid[w];
+        len += m->wrap_prm[w] * m->qpos0[m->jnt_qposadr[jid]];
+        J[m->jnt_dofadr[jid]] = m->wrap_prm[w];
+      } else if (m->wrap_type[w] == 2) {
+        divisor = m->wrap_prm[w];
+      } else if (m->wrap_type[w] == 3 && w + 1 < w1 && m->wrap_type[w + 1] == 3) {
+        const int s0 = m->wrap_objid[w], s1 = m->wrap_objid[w + 1], b0 = m->site_bodyid[s0], b1 = m->site_bodyid[s1];
+        double p0[3], p1[3], dif[3];
+        mulmatvec3(p0, &k.xmat[9 * b0], m->site_pos + 3 * s0);
+        mulmatvec3(p1, &k.xmat[9 * b1], m->site_pos + 3 * s1);
+        for (int c = 0; c < 3; c++) { p0[c] += k.xpos[3 * b0 + c]; p1[c] += k.xpos[3 * b1 + c]; dif[c] = p1[c] - p0[c]; }
+        const double seg = normalize3(dif);
+        len += seg / divisor;
+        if (b0 != b1) {
+          std::vector<double> j0(3 * nv + 3, 0.0), j1(3 * nv + 3, 0.0), jr(3 * nv + 3);
+          jac_point(m, k, j0.data(), jr.data(), p0, b0);
+          jac_point(m, k, j1.data(), jr.data(), p1, b1);
+          for (int c = 0; c < nv; c++) {
+            double sdot = 0;
+            for (int r = 0; r < 3; r++) sdot += dif[r] * (j1[r * nv + c] - j0[r * nv + c]);
+            J[c] += sdot / divisor;
+          }
+        }
+      }
     }
     m->tendon_length0[t] = len;
     for (int c = 0; c < nv; c++) x[c] = J[c];
@@ -319,8 +343,7 @@ int model_set_const(b2mjModel* m, std::string& err) {
       mom[m->jnt_dofadr[id]] = g;
     } else if (m->actuator_trntype[a] == B2MJ_TRN_TENDON) {
       len = g * m->tendon_length0[id];
-      for (int w = m->tendon_adr[id]; w < m->tendon_adr[id] + m->tendon_num[id]; w++)
-        mom[m->jnt_dofadr[m->wrap_objid[w]]] = g * m->wrap_prm[w];
+      for (int c = 0; c < nv; c++) mom[c] = g * tenJ[(size_t)id * (nv + 1) + c];
     }
     m->actuator_length0[a] = len;
     for (int c = 0; c < nv; c++) x[c] = mom[c];

@@ -159,12 +159,35 @@ void tendon(const b2mjModel* m, OrcData* d) {
   const int nv = m->nv;
   if (!m->ntendon) return;
   zero(d->ten_J, m->ntendon * nv);
+  std::vector<double> j0(3 * nv), j1(3 * nv);
   for (int i = 0; i < m->ntendon; i++) {
-    double len = 0;
-    for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) {
-      const int jid = m->wrap_objid[w];
-      len += m->wrap_prm[w] * d->qpos[m->jnt_qposadr[jid]];
-      d->ten_J[i * nv + m->jnt_dofadr[jid]] = m->wrap_prm[w];
+    double len = 0, divisor = 1;
+    const int w0 = m->tendon_adr[i], w1 = w0 + m->tendon_num[i];
+    for (int w = w0; w < w1; w++) {
+      const int type = m->wrap_type[w];
+      if (type == 1) {  // mjWRAP_JOINT: fixed tendon
+        const int jid = m->wrap_objid[w];
+        len += m->wrap_prm[w] * d->qpos[m->jnt_qposadr[jid]];
+        d->ten_J[i * nv + m->jnt_dofadr[jid]] = m->wrap_prm[w];
+      } else if (type == 2) {  // mjWRAP_PULLEY: scales the branches that follow
+        divisor = m->wrap_prm[w];
+      } else if (type == 3 && w + 1 < w1 && m->wrap_type[w + 1] == 3) {  // site - site segment of a spatial tendon
+        const int s0 = m->wrap_objid[w], s1 = m->wrap_objid[w + 1], b0 = m->site_bodyid[s0], b1 = m->site_bodyid[s1];
+        const double *p0 = d->site_xpos + 3 * s0, *p1 = d->site_xpos + 3 * s1;
+        double dif[3];
+        sub3(dif, p1, p0);
+        const double seg = normalize3(dif);
+        len += seg / divisor;
+        if (b0 != b1) {  // mj_jacDifPair: the segment direction dotted with the difference of the point Jacobians
+          jac(m, d, j0.data(), nullptr, p0, b0);
+          jac(m, d, j1.data(), nullptr, p1, b1);
+          for (int k = 0; k < nv; k++) {
+            double s = 0;
+            for (int r = 0; r < 3; r++) s += dif[r] * (j1[r * nv + k] - j0[r * nv + k]);
+            d->ten_J[i * nv + k] += s / divisor;
+          }
+        }
+      }
     }
     d->ten_length[i] = len;
   }

@@ -320,6 +320,123 @@ def test_convex_pairs(capi, orc, BatchSim):
     print(f"convex pile: pair types {sorted(seen)}, contact dist worst {worst_d:.1e}, normal worst {worst_n:.1e}, step worst {worst:.1e}")
 
 
+def test_mesh_geoms(capi, orc, BatchSim):
+    """Convex meshes (hull vertices, stages_convex.cuh): plane-mesh multi-point contacts and MPR against boxes,
+    cylinders, spheres and other meshes."""
+    import itertools
+    cube = " ".join(f"{x} {y} {z}" for x, y, z in itertools.product((-0.08, 0.08), (-0.1, 0.1), (-0.06, 0.06)))
+    rng0 = np.random.default_rng(4)
+    blob = rng0.normal(size=(60, 3))
+    blob = blob / np.linalg.norm(blob, axis=1, keepdims=True) * [0.09, 0.07, 0.11]
+    blob_s = " ".join(f"{x:.17g}" for x in blob.ravel())
+    xml = f"""<mujoco><option timestep="0.002" solver="Newton"/>
+      <asset><mesh name="cube" vertex="{cube}"/><mesh name="tet" vertex="0 0 0 0.2 0 0 0 0.2 0 0 0 0.2"/>
+             <mesh name="blob" vertex="{blob_s}"/></asset>
+      <worldbody>
+        <geom type="plane" size="3 3 0.1"/>
+        <geom type="box" size="0.3 0.3 0.05" pos="0 0 0.05"/>
+        <geom type="mesh" mesh="blob" pos="0.7 0 0.1"/>
+        <body pos="0 0 0.3"><freejoint/><geom type="mesh" mesh="cube" density="600"/></body>
+        <body pos="0.03 0.02 0.6" euler="20 30 0"><freejoint/><geom type="mesh" mesh="tet" density="600"/></body>
+        <body pos="0.7 0.02 0.45" euler="10 0 40"><freejoint/><geom type="mesh" mesh="cube" density="600"/></body>
+        <body pos="-0.6 0 0.3" euler="50 20 0"><freejoint/><geom type="mesh" mesh="blob" density="600"/></body>
+        <body pos="-0.58 0.03 0.6"><freejoint/><geom type="cylinder" size="0.06 0.08" density="600"/></body>
+        <body pos="0 0.7 0.3" euler="0 45 0"><freejoint/><geom type="mesh" mesh="tet" density="600"/></body>
+        <body pos="0.02 0.72 0.55"><freejoint/><geom type="sphere" size="0.07" density="600"/></body>
+      </worldbody></mujoco>"""
+    model = capi.Model.from_xml_string(xml)
+    nenv = 6
+    qpos, qvel = perturbed(model, nenv, 29, 0.02)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    seen = set()
+    for chunk in range(6):   # the piles topple over time: compare the contact sets at several moments
+        sim.keep_intermediates(False)
+        sim.step(50)
+        assert np.all(np.isfinite(sim.get("qpos")))
+        st = {k: sim.get(k) for k in STATE if model.field_size_by_name(k) > 0}
+        sim.keep_intermediates(True)
+        sim.forward()
+        ncon = sim.get("ncon")[:, 0]
+        g1, g2, dist = sim.get("contact_geom1"), sim.get("contact_geom2"), sim.get("contact_dist")
+        for e, o in enumerate(oracles):
+            for k, v in st.items():
+                o.set(k, v[e])
+            o.forward()
+            n = int(o.get("ncon")[0])
+            assert n == int(ncon[e]), (chunk, e, n, ncon[e])
+            np.testing.assert_array_equal(g1[e][:n], o.get("contact_geom1")[:n])
+            np.testing.assert_array_equal(g2[e][:n], o.get("contact_geom2")[:n])
+            if n:
+                assert np.max(np.abs(dist[e][:n] - o.get("contact_dist")[:n])) < 2e-6
+            for c in range(n):
+                seen.add((int(model.geom_type[g1[e][c]]), int(model.geom_type[g2[e][c]])))
+    assert (0, 7) in seen and (7, 7) in seen and (6, 7) in seen, seen
+    sim.keep_intermediates(False)
+    worst, _ = injected_steps(model, sim, oracles, 40, np.random.default_rng(1), tol=TOL, tag="mesh pile")
+    print(f"mesh pile: pair types {sorted(seen)}, step worst {worst:.1e}")
+
+
+SPATIAL = """
+<mujoco>
+  <compiler angle="radian"/>
+  <option timestep="0.002" integrator="{integ}"/>
+  <worldbody>
+    <geom type="plane" size="3 3 0.1"/>
+    <site name="anchor" pos="0 0 1.5"/>
+    <site name="anchor2" pos="0.5 0 1.5"/>
+    <body name="l1" pos="0 0 1">
+      <joint name="j1" type="hinge" axis="0 1 0" damping="0.05"/>
+      <geom type="capsule" fromto="0 0 0 0.5 0 0" size="0.03"/>
+      <site name="mid" pos="0.25 0 0.05"/>
+      <body name="l2" pos="0.5 0 0">
+        <joint name="j2" type="ball" damping="0.02"/>
+        <joint name="j3" type="slide" axis="1 0 0" range="-0.1 0.1" damping="1"/>
+        <geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.03"/>
+        <site name="tip" pos="0.4 0 0.02"/>
+        <site name="tip2" pos="0.2 0.05 0"/>
+      </body>
+    </body>
+    <body pos="0.3 0.6 0.8"><freejoint/><geom type="box" size="0.05 0.05 0.05"/><site name="boxtop" pos="0 0 0.05"/></body>
+  </worldbody>
+  <tendon>
+    <spatial name="cable" stiffness="40" damping="1.5" limited="true" range="0 1.05"><site site="anchor"/><site site="mid"/><site site="tip"/></spatial>
+    <spatial name="block" frictionloss="0.3">
+      <site site="anchor2"/><site site="tip"/><pulley divisor="2"/><site site="anchor2"/><site site="tip2"/>
+      <pulley divisor="2"/><site site="mid"/><site site="tip2"/>
+    </spatial>
+    <spatial name="leash" stiffness="200" springlength="0 0.6"><site site="anchor2"/><site site="boxtop"/></spatial>
+  </tendon>
+  <actuator><motor name="pull" tendon="cable" gear="3" ctrlrange="-2 2"/><position tendon="block" kp="20" kv="0.5" ctrlrange="0.5 1.5"/></actuator>
+  <sensor><tendonpos tendon="cable"/><tendonvel tendon="block"/><tendonlimitfrc tendon="cable"/><actuatorfrc actuator="pull"/></sensor>
+</mujoco>
+"""
+
+
+@pytest.mark.parametrize("integ", ["Euler", "RK4", "implicitfast"])
+def test_spatial_tendons(integ, capi, orc, BatchSim):
+    """Site paths with pulleys driving springs, dampers, limits, friction loss, actuators and sensors."""
+    model = capi.Model.from_xml_string(SPATIAL.format(integ=integ))
+    assert model.ntendon == 3 and model.nwrap == 13
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, 13, 0.2)
+    sim = BatchSim(model, nenv)
+    sim.keep_intermediates(True)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    sim.forward()
+    for o in oracles:
+        o.forward()
+    wf = compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tol=1e-9, tag="spatial")
+    sim.keep_intermediates(False)
+    worst, max_nefc = injected_steps(model, sim, oracles, 150, np.random.default_rng(3), tag=f"spatial:{integ}")
+    assert max_nefc >= 2
+    print(f"spatial tendons [{integ}]: forward fields worst {wf:.1e}, injected-step worst {worst:.1e}, max nefc {max_nefc}")
+
+
 RANGE_SCENE = """
 <mujoco>
   <option timestep="0.002"/>
