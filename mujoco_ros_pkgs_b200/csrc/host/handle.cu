@@ -1030,11 +1030,37 @@ int b2mj_step_host(b2mj_handle* hh, int nsteps, const double* host_ctrl, double*
   CUDA_OK(cudaSetDevice(h->device));
   const b2mjModel* m = h->model;
   unsigned char* base; size_t pitch, es; int n;
-  if (host_ctrl && m->nu) {
+  // Zero-copy exchange for single steps with pinned (page-locked, mapped) host buffers: the step kernel reads each env's
+  // controls straight from host memory when it picks the env up and writes qpos / qvel / sensordata to host memory when
+  // the env's step is done, so the transfers ride under the launch (whose length is set by its slowest env) instead
+  // of bracketing it as four strided copies.  Pageable buffers, multi-step calls and arena dumps take the copy path.
+  auto mapped = [](const void* p) -> void* {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+  };
+  static const bool no_zero_copy = getenv("B2MJ_NO_ZERO_COPY") != nullptr;
+  const bool want_ctrl = host_ctrl && m->nu, want_s = host_sensordata && m->nsensordata;
+  void* z_ctrl = want_ctrl ? mapped(host_ctrl) : nullptr;
+  void* z_qpos = mapped(host_qpos);
+  void* z_qvel = mapped(host_qvel);
+  void* z_sens = want_s ? mapped(host_sensordata) : nullptr;
+  const bool zero_copy = !no_zero_copy && nsteps == 1 && !h->keep_intermediates && (!want_ctrl || z_ctrl) &&
+                         (!host_qpos || z_qpos) && (!host_qvel || z_qvel) && (!want_s || z_sens) &&
+                         (want_ctrl || host_qpos || host_qvel || want_s);
+  h->in_split_step = 0;
+  if (zero_copy) {
+    if (int rc = handle_launch(h, MODE_STEP, 1, static_cast<const double*>(z_ctrl), static_cast<double*>(z_qpos),
+                               static_cast<double*>(z_qvel), static_cast<double*>(z_sens)))
+      return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  if (want_ctrl) {
     if (int rc = locate(h, B2MJ_F_CTRL, true, &base, &pitch, &es, &n)) return rc;
     CUDA_OK(cudaMemcpy2DAsync(base, pitch, host_ctrl, n * es, n * es, h->nenv, cudaMemcpyHostToDevice, h->stream));
   }
-  h->in_split_step = 0;
   if (int rc = handle_launch(h, MODE_STEP, nsteps)) return rc;
   const struct { b2mj_field f; double* dst; } outs[3] = {
       {B2MJ_F_QPOS, host_qpos}, {B2MJ_F_QVEL, host_qvel}, {B2MJ_F_SENSORDATA, host_sensordata}};

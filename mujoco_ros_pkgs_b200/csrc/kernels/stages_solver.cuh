@@ -440,7 +440,7 @@ __device__ __forceinline__ int solvePGS_own_T(const Env e, int nefc, const doubl
     const double d = __shfl_sync(e.mask, delta, i, B2K_G);                     \
     const double change = delta * (hA * delta + r);                            \
     r += ai * d;                                                               \
-    if (lane == i) { f = fn; improvement -= change; fail |= change > 1e-10; }  \
+    if (lane == i) { f = fn; improvement -= change; worst = max(worst, __double2hiint(change)); } \
     SLOT = *pcol;                                                              \
     pcol += nefc;                                                              \
     i++;                                                                       \
@@ -448,7 +448,9 @@ __device__ __forceinline__ int solvePGS_own_T(const Env e, int nefc, const doubl
   while (iter < maxiter) {
     double improvement = 0;  // this lane's own row only; summed over the warp once per sweep
     const double f_save = f, r_save = r;
-    bool fail = false;
+    // largest high word of any row's cost change in this sweep: positive doubles order like their high words, so
+    // worst >= hiword(1e-10) flags every change > 1e-10 (and, conservatively, a few just below: the redo is exact)
+    int worst = (int)0x80000000;
     {
       double p0 = q0, p1 = q1;
       const double* pcol = col + 2 * nefc;
@@ -459,7 +461,7 @@ __device__ __forceinline__ int solvePGS_own_T(const Env e, int nefc, const doubl
       }
       if (i < nefc) B2K_PGS_OWN_ROW_FAST(p0)
     }
-    if (__any_sync(e.mask, fail)) {  // redo the sweep with the guard on the chain
+    if (__any_sync(e.mask, worst >= __double2hiint(1e-10))) {  // redo the sweep with the guard on the chain
       f = f_save; r = r_save; improvement = 0;
       double p0 = q0, p1 = q1;
       const double* pcol = col + 2 * nefc;

@@ -424,6 +424,12 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
       }
     }
 
+    // controls that came from a stream (fused rollout, zero-copy host exchange) are the env's ctrl from now on: the
+    // bulk store below covers segments B + C only, so write segment A's ctrl back by hand
+    if (a.ctrl_seq && m.nu) {
+      const double* ctrl = e.D(B2MJ_F_CTRL);
+      FORL(i, m.nu) rec[m.rec_ctrl + i] = ctrl[i];
+    }
     // ---- results: counters, state record SMEM -> HBM (segments B+C contiguous), optional arena dump ----
     if (lane == 0) {
       int* st = a.stats + (size_t)env * 4;

@@ -467,6 +467,43 @@ def test_step_host_equals_set_step_get(load_model, BatchSim):
         a.step_host(0)
 
 
+def test_step_host_zero_copy_with_pinned_buffers(load_model, BatchSim):
+    """Pinned host buffers take the zero-copy path of b2mj_step_host (the step kernel reads ctrl from and writes qpos /
+    qvel / sensordata to mapped host memory); pageable buffers take the copy path.  Both must be bitwise the plain
+    set / step / get sequence, and the streamed controls must stick as the env's ctrl."""
+    import torch
+
+    model = load_model("panda_like.xml")
+    nenv = 300   # more than one CTA wave worth of 2-env CTAs is not needed; partial last CTA on purpose
+    qpos, qvel = perturbed(model, nenv, 33)
+    rng = np.random.default_rng(9)
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()  # noqa: E731
+    a, b, c = BatchSim(model, nenv), BatchSim(model, nenv), BatchSim(model, nenv)
+    for s_ in (a, b, c):
+        s_.set("qpos", qpos)
+        s_.set("qvel", qvel)
+    pq, pv, ps, pc = pin(nenv, model.nq), pin(nenv, model.nv), pin(nenv, model.nsensordata), pin(nenv, model.nu)
+    hq = np.empty((nenv, model.nq)); hv = np.empty((nenv, model.nv)); hs = np.empty((nenv, model.nsensordata))
+    for k in range(40):
+        ctrl = np.ascontiguousarray(ctrl_sample(model, rng, nenv))
+        np.copyto(pc, ctrl)
+        pq.fill(np.nan); pv.fill(np.nan); ps.fill(np.nan)
+        a.step_host(1, pc, pq, pv, ps)          # zero-copy
+        c.step_host(1, ctrl, hq, hv, hs)        # copies
+        b.set("ctrl", ctrl)
+        b.step(1)
+        for z, h, name in ((pq, hq, "qpos"), (pv, hv, "qvel"), (ps, hs, "sensordata")):
+            ref = b.get(name)
+            np.testing.assert_array_equal(z, ref, err_msg=f"zero-copy {name} step {k}")
+            np.testing.assert_array_equal(h, ref, err_msg=f"copy {name} step {k}")
+    np.testing.assert_array_equal(a.get("ctrl"), b.get("ctrl"))   # streamed controls were written back to the record
+    a.step(2); b.step(2)                                          # and are what a plain step uses next
+    np.testing.assert_array_equal(a.get("qpos"), b.get("qpos"))
+    # outputs only (no ctrl): still zero-copy, ctrl kept
+    a.step_host(1, None, pq, pv, None); b.step(1)
+    np.testing.assert_array_equal(pq, b.get("qpos"))
+
+
 def test_launch_order_does_not_change_results(tmp_path):
     """The heaviest-first launch order (b2k_order_kernel) only permutes which warp runs which env: a contact-rich
     2048-env run must be bitwise identical with the reordering disabled (B2MJ_NO_REORDER=1, separate process)."""

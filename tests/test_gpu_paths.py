@@ -722,16 +722,24 @@ def test_reset_abandons_split_step(capi, BatchSim):
 
 
 def test_unsupported_options_are_rejected(capi, BatchSim):
-    """Fluid forces are not implemented: nonzero density / viscosity / wind must be refused, not ignored."""
-    for attr, val in (("density", 1.2), ("viscosity", 0.01)):
-        m = variant(capi, "pendulum_scene.xml")
-        setattr(m.opt, attr, val)
-        with pytest.raises(capi.B2mjError):
+    """What the step kernel does not implement must be refused, not ignored: fluid forces under an implicit integrator
+    (their velocity derivatives are missing from qDeriv), unknown integrators / solvers."""
+    for integ in (IMPLICIT, IMPLICITFAST):
+        m = variant(capi, "pendulum_scene.xml", integrator=integ)
+        m.opt.density = 1.2
+        with pytest.raises(capi.B2mjError, match="fluid"):
             BatchSim(m, 2)
     m = variant(capi, "pendulum_scene.xml")
-    m.opt.wind[0] = 1.0
-    with pytest.raises(capi.B2mjError):
+    m.opt.integrator = 7
+    with pytest.raises(capi.B2mjError, match="integrator"):
         BatchSim(m, 2)
+    m = variant(capi, "pendulum_scene.xml")
+    m.opt.solver = 5
+    with pytest.raises(capi.B2mjError, match="solver"):
+        BatchSim(m, 2)
+    m = variant(capi, "pendulum_scene.xml")   # fluid forces with Euler are supported (test_fluid_forces)
+    m.opt.density = 1.2
+    BatchSim(m, 2).step(1)
 
 
 @pytest.mark.parametrize("name,nenv,amp", [("humanoid_like.xml", 6, 0.02), ("hand_like.xml", 6, 0.02), ("bin.xml", 3, 0.02)])
