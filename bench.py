@@ -13,7 +13,10 @@ pre-roll a short run (--steps 20) would report that easy regime.  The reference 
                the device-resident ctrl stream and writing the per-step trajectory (CUDA events on the stepping stream).
   per_step_launch  the same K steps as K closed-loop launches (b2mj_set_device(ctrl) + b2mj_step), L2 flushed between.
   e2e          the headline: same metric through the C-ABI with HOST buffers, one b2mj_step_host call per step
-               (ctrl H2D from pinned memory -> step -> qpos / qvel / sensordata D2H -> one synchronisation).
+               (ctrl from pinned host memory -> step -> qpos / qvel / sensordata into pinned host memory -> one
+               synchronisation).  With pinned buffers the step kernel itself moves those bytes over PCIe -- it reads
+               an env's ctrl from host memory when it picks the env up and writes its outputs to host memory when
+               the env's step is done -- so the transfers overlap the launch (B2MJ_NO_ZERO_COPY=1 = staged copies).
   roofline     algorithmic state bytes per env-step x env-steps per launch / kernel time against the
                measured HBM copy bandwidth (MEASURED_PEAKS.json); roofline.fp64 = FP64 instruction rate against the
                DFMA peak measured live on this GPU (b2mj_ubench_dfma) -- the roofline that can actually bind.
@@ -751,7 +754,10 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nenv * nu * 8,
                     "d2h_bytes_per_step": nenv * (model.nq + model.nv + ns) * 8, "steps": KE,
-                    "timing": "wall clock, sync both sides, pinned host buffers, one b2mj_step_host call per step"},
+                    "timing": "wall clock, sync both sides, pinned host buffers, one b2mj_step_host call per step; the step "
+                              "kernel reads ctrl from / writes the outputs to the pinned host buffers itself (zero-copy over "
+                              "PCIe inside the timed region)" if not os.environ.get("B2MJ_NO_ZERO_COPY") else
+                              "wall clock, sync both sides, pinned host buffers, one b2mj_step_host call per step (staged copies)"},
             "gpu_launches": rollout_launches,
             "per_step_launch": {"value": ps_value, "unit": UNIT, "ms_per_step": ps_ms / K, "gpu_launches": ps_launches,
                                 "per_rank_kernel_ms": rank_stats,
