@@ -69,27 +69,13 @@ struct StepCtx {
     sc.t_prev = _now;                                                              \
   }
 
-// mj_forwardSkip split at the control hook.  The step context travels by value (constraint counts packed in the return
-// value): a StepCtx& argument would pin it to local memory, and every stage boundary below would then pay local loads
-// that miss the small L1 left beside the shared-memory carve-out (profiles/r2_ncu_step_summary.txt: 275 local loads per
-// env-step, most of them here).
-#define FWD_SKIPSENSOR 1
-#define FWD_FIRST 2
-#define FWD_SECOND 4
-__device__ __forceinline__ unsigned long long packCounts(int ncon, int nefc, int iters) {
-  return (unsigned long long)(unsigned)ncon | ((unsigned long long)(unsigned)nefc << 20) | ((unsigned long long)(unsigned)iters << 40);
-}
-__device__ __noinline__ unsigned long long forwardPass(const Env e, const LaunchArgs& a, int env, unsigned long long counts,
-                                                       int nsync, int flags) {
+// mj_forwardSkip split at the control hook
+__device__ __noinline__ void forwardPass(const Env e, const LaunchArgs& a, int env, StepCtx& sc, bool skipsensor, bool first_half,
+                            bool second_half) {
   const DevModel& m = c_dm;
-  StepCtx sc;
-  sc.ncon = (int)(counts & 0xfffffu); sc.nefc = (int)((counts >> 20) & 0xfffffu); sc.iters = (int)(counts >> 40);
-  sc.nsync = nsync;
-  sc.t_prev = a.prof ? clock64() : 0;
-  const bool skipsensor = flags & FWD_SKIPSENSOR;
   int* warning = a.warning + (size_t)env * B2MJ_NWARNING;
   const double* xfrc = (m.has_xfrc && a.xfrc) ? a.xfrc + (size_t)env * 6 * m.nbody : nullptr;
-  if (flags & FWD_FIRST) {
+  if (first_half) {
     stage_kinematics(e); PROF_MARK(PROF_KINEMATICS)
     stage_comPos(e); PROF_MARK(PROF_COMPOS)
     stage_tendon_transmission(e); PROF_MARK(PROF_TENDON)
@@ -107,24 +93,14 @@ __device__ __noinline__ unsigned long long forwardPass(const Env e, const Launch
     if (!skipsensor) stage_sensorVel(e, sc.nefc);
     PROF_MARK(PROF_SENSORVEL)
   }
-  if (flags & FWD_SECOND) {
+  if (second_half) {
     stage_actuation(e, warning); PROF_MARK(PROF_ACTUATION)
     stage_acceleration(e, xfrc); PROF_MARK(PROF_ACCELERATION)
     sc.iters = stage_fwdConstraint(e, sc.nefc, sc.ncon); PROF_MARK(PROF_SOLVE)
     if (!skipsensor) stage_sensorAcc(e, sc.nefc, sc.ncon, xfrc);
     PROF_MARK(PROF_SENSORACC)
   }
-  return packCounts(sc.ncon, sc.nefc, sc.iters);
 }
-// call forwardPass on the kernel's register-resident step context; the stage clock restarts after the call
-#define FORWARD_PASS(SKIP, FIRST, SECOND)                                                                      \
-  {                                                                                                             \
-    const unsigned long long _c = forwardPass(e, a, env, packCounts(sc.ncon, sc.nefc, sc.iters), sc.nsync,       \
-                                              ((SKIP) ? FWD_SKIPSENSOR : 0) | ((FIRST) ? FWD_FIRST : 0) |       \
-                                                  ((SECOND) ? FWD_SECOND : 0));                                \
-    sc.ncon = (int)(_c & 0xfffffu); sc.nefc = (int)((_c >> 20) & 0xfffffu); sc.iters = (int)(_c >> 40);          \
-    if (a.prof) sc.t_prev = clock64();                                                                          \
-  }
 
 // mj_RungeKutta(4), in resumable pieces: the fused step runs them back to back around full forward passes; the split
 // step (b2mj_step_begin / b2mj_step_end with the host's control hook in between) runs one piece per launch, so that
@@ -224,11 +200,11 @@ __device__ __noinline__ void rk_finish(const Env e) {
   advance_warp(e, r.dX + 2 * nv, r.dX + nv, r.dX);
 }
 
-__device__ __forceinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
+__device__ __noinline__ void stage_rk4(const Env e, const LaunchArgs& a, int env, StepCtx& sc) {
   rk_init(e);
-  B2K_NOUNROLL for (int s = 1; s < 4; s++) {
+  for (int s = 1; s < 4; s++) {
     rk_setup_stage(e, s);
-    FORWARD_PASS(true, true, true)
+    forwardPass(e, a, env, sc, true, true, true);
     rk_record(e, s);
   }
   rk_finish(e);
@@ -372,7 +348,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
       const bool rk_split = a.mode == MODE_STEP_END && m.opt.integrator == B2MJ_INT_RK4;
       sc.nsync = nsync_main;
       // (split RK4: stages 1..3 are sensor-free forward passes, like the fused mj_RungeKutta)
-      FORWARD_PASS(rk_split && a.rk_stage > 0, first, second)
+      forwardPass(e, a, env, sc, rk_split && a.rk_stage > 0, first, second);
       sc.nsync = 0;
       if (a.mode == MODE_FORWARD || a.mode == MODE_STEP_BEGIN) break;
       if (rk_split && a.rk_stage > 0) {
@@ -381,7 +357,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         rk_record(e, a.rk_stage);
         if (a.rk_stage < 3) {
           rk_setup_stage(e, a.rk_stage + 1);
-          FORWARD_PASS(true, true, false)
+          forwardPass(e, a, env, sc, true, true, false);
         } else {
           rk_finish(e);
         }
@@ -394,13 +370,13 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
         FORL(i, m.nv) bad |= isBad(qa[i]);
         if (__any_sync(e.mask, bad)) {
           resetEnv(e, warning, B2MJ_WARN_BADQACC);
-          FORWARD_PASS(false, true, true)
+          forwardPass(e, a, env, sc, false, true, true);
         }
       }
       if (rk_split) {  // sub-step 0 of a split RK4 step: open sub-step 1 and yield to the host
         rk_init(e);
         rk_setup_stage(e, 1);
-        FORWARD_PASS(true, true, false)
+        forwardPass(e, a, env, sc, true, true, false);
         break;
       }
       if (m.opt.integrator == B2MJ_INT_RK4 && a.mode == MODE_STEP) stage_rk4(e, a, env, sc);
