@@ -335,6 +335,9 @@ static int make_layout(Handle* h) {
   xs[XF_PRIMAL] = pgs ? 0 : 8 * nv;
   xs[XF_EFC_AR] = pgs ? m->njmax * (m->njmax + 4) : 0;
   xs[XF_EFC_AR_S] = pgs ? std::min(m->njmax * (m->njmax + 4), 384) : 0;  // nefc <= 17 stays on chip
+  // triangle pair table (2 bytes per entry): sparse L'DL of qM / qH and the Newton Cholesky index their trailing blocks
+  // through it; team mode has its own factorisation
+  xs[XF_TRI] = (nv <= 255 && d.team_warps == 1 && (!d.dense_small || newton)) ? (nv * (nv + 1) / 2 * 2 + 7) / 8 : 0;
   const bool implicit_full = m->opt.integrator == B2MJ_INT_IMPLICIT;
   xs[XF_IMPL_LU] = implicit_full ? nv * nv : 0;
   xs[XF_IMPL_D] = implicit_full ? 6 * m->nbody * nv : 0;
@@ -553,7 +556,7 @@ static int make_layout(Handle* h) {
     static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
                                    "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",
                                    "SUBTREE_ANGMOM", "BODYVEL", "RK_X0", "RK_XF", "RK_F", "RK_DX", "SCRATCH", "QW", "QHW",
-                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS", "IMPL_LU", "IMPL_D"};
+                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS", "TRI", "IMPL_LU", "IMPL_D"};
     fprintf(stderr, "[b2mj layout] record %d doubles; shared arena %d doubles + %d ints per env\n", d.rec_end, d.arena_s_doubles,
             d.arena_s_ints);
     for (int f = 0; f < B2MJ_NFIELD; f++)

@@ -92,6 +92,7 @@ enum XField {
   XF_EFC_AR_S,      // shared-memory home of AR when nefc*nefc fits (the common case)
   XF_JWIN,          // primal solvers: shared-memory window for the ACTIVE rows of efc_J: [0] = valid flag, rows from +2
   XF_JCOLS,         // team mode: per constraint row {nnz, columns} bytes (team.cuh), njmax * 17 bytes
+  XF_TRI,           // pair table of a row-major lower triangle of order nv, packed a | b << 8 in 16 bits (cholPairTable)
   XF_IMPL_LU,       // implicit integrator: nv*nv dense M - h qDeriv and its LU factors (always in the HBM/L2 arena)
   XF_IMPL_D,        // implicit integrator: 6*nbody*nv body-force derivatives d cfrc / d qvel (always in the HBM/L2 arena)
   XF_COUNT

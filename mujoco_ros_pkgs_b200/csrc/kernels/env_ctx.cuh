@@ -61,6 +61,25 @@ struct Env {
   }
 };
 
+// Pair table of a row-major lower triangle of order nv: entry p -> (a, b <= a) packed a | b << 8 (XF_TRI).  The
+// factorisations (sparse L'DL of qM, Newton Cholesky) hand the entries of their triangular trailing blocks to lanes
+// through it: no integer division, no wasted upper-triangle slots.  Built once per work item.
+__device__ __forceinline__ const unsigned short* triTable(const Env e) {
+  return c_dm.xsize[XF_TRI] > 0 ? reinterpret_cast<const unsigned short*>(e.X(XF_TRI)) : nullptr;
+}
+__device__ __noinline__ void triTableBuild(const Env e) {
+  if (c_dm.xsize[XF_TRI] <= 0) return;
+  unsigned short* tri = reinterpret_cast<unsigned short*>(e.X(XF_TRI));
+  const int n = c_dm.nv, ntri = n * (n + 1) / 2;
+  _Pragma("unroll 1") for (int p = e.lane; p < ntri; p += B2K_G) {
+    int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while (a * (a + 1) / 2 > p) a--;
+    while ((a + 1) * (a + 2) / 2 <= p) a++;
+    tri[p] = (unsigned short)(a | ((p - a * (a + 1) / 2) << 8));
+  }
+  __syncwarp(e.mask);
+}
+
 // The megakernel is instruction-fetch bound (profiles/): run-time-bounded loops stay rolled so their bodies are
 // re-executed from the instruction cache instead of being fetched as straight-line copies.
 #define B2K_NOUNROLL _Pragma("unroll 1")

@@ -339,14 +339,24 @@ __device__ __noinline__ void factorLD2(const Env e, double* A, double* Bm, doubl
   const int nv = m.nv;
   const int half = Bm ? (e.lane / (B2K_G / 2)) : 0, sub = Bm ? (e.lane % (B2K_G / 2)) : e.lane, stride = Bm ? B2K_G / 2 : B2K_G;
   double* LD = half ? Bm : A;
+  const unsigned short* tri = triTable(e);
   for (int k = nv - 1; k >= 0; k--) {
     const int d = m.dof_nanc[k];
     if (d == 0) continue;
     const int Mkk = m.dof_Madr[k];
     const double inv = 1.0 / LD[Mkk];
-    B2K_NOUNROLL for (int idx = sub; idx < d * d; idx += stride) {
-      const int a = idx / d, c = idx - a * d;
-      if (c < d - a) LD[m.M_ancadr[Mkk + 1 + a] + c] -= LD[Mkk + 1 + a] * LD[Mkk + 1 + a + c] * inv;
+    if (tri) {
+      // entries (a, c < d - a) of the ancestor block through the pair table: (x, y <= x) -> a = d - 1 - x, c = y
+      B2K_NOUNROLL for (int p = sub; p < d * (d + 1) / 2; p += stride) {
+        const unsigned t = tri[p];
+        const int a = d - 1 - (int)(t & 255u), c = (int)(t >> 8);
+        LD[m.M_ancadr[Mkk + 1 + a] + c] -= LD[Mkk + 1 + a] * LD[Mkk + 1 + a + c] * inv;
+      }
+    } else {
+      B2K_NOUNROLL for (int idx = sub; idx < d * d; idx += stride) {
+        const int a = idx / d, c = idx - a * d;
+        if (c < d - a) LD[m.M_ancadr[Mkk + 1 + a] + c] -= LD[Mkk + 1 + a] * LD[Mkk + 1 + a + c] * inv;
+      }
     }
     WSYNC();
     B2K_NOUNROLL for (int c = sub; c < d; c += stride) LD[Mkk + 1 + c] *= inv;

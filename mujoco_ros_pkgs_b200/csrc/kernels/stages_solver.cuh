@@ -738,13 +738,21 @@ __device__ __forceinline__ double dot_warp(const Env e, const double* a, const d
 template <bool SM>
 __device__ __forceinline__ double* newtonH(const Env e) { return SM ? e.X(XF_NEWTON_H) : e.XG(XF_NEWTON_H); }
 
-// Right-looking Cholesky, lane i owns row i of the trailing block: per pivot the column is scaled, then every lane
-// updates its own row entries (j < k <= i) in a rolled loop whose iterations are independent -- one broadcast read of
-// L(k, j), one read-modify-write of A(i, k) -- so the only serial chain per pivot is pivot -> sqrt -> reciprocal ->
-// column.  The left-looking form it replaces paid a 5-round shuffle reduction plus a dependent dot product per pivot
-// (profiles/r2b_ncu_c4_lines.txt: 9 % of the C4 step).  ld is odd (handle.cu), so the lanes' rows fall in distinct banks.
+// Pair table of the trailing blocks (env_ctx.cuh::triTable): one table serves every pivot, because a row-major lower
+// triangle of order m is the prefix p < m (m + 1) / 2 of the enumeration.
+__device__ __forceinline__ const unsigned short* cholPairTable(const Env e, int n) {
+  (void)n;
+  return triTable(e);
+}
+
+// Right-looking Cholesky.  Per pivot the column is scaled, then the trailing block A(i, k) -= L(i, j) L(k, j),
+// j < k <= i, is updated with ALL lanes busy: entry p of the block goes to lane p mod 32 through the pair table
+// (row-major, so a warp's entries sit in one or two rows: consecutive addresses, L(i, j) a broadcast, L(k, j) a walk
+// down column j with the odd leading dimension) -- n^3 / 192 warp passes instead of the n^2 / 2 of one row per lane.
+// The only serial chain per pivot is pivot -> sqrt -> reciprocal -> column.  Every entry sees the same subtractions
+// in the same order as in the row-per-lane form (tri == nullptr, kept for matrices whose table does not fit).
 template <bool SM>
-__device__ __noinline__ void cholFactor_warp(const Env e, int n, int ld, double mindiag) {
+__device__ __noinline__ void cholFactor_warp(const Env e, int n, int ld, double mindiag, const unsigned short* tri) {
   double* A = newtonH<SM>(e);
   double* invd = e.X(XF_PRIMAL) + 7 * n;
   B2K_NOUNROLL for (int j = 0; j < n; j++) {
@@ -754,18 +762,34 @@ __device__ __noinline__ void cholFactor_warp(const Env e, int n, int ld, double 
     B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += B2K_G) A[i * ld + j] *= inv;
     WSYNC();
     if (e.lane == 0) { A[j * ld + j] = ljj; invd[j] = inv; }
-    const double* Lj = A + j;  // column j: L(k, j) = Lj[k * ld]
-    B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += B2K_G) {
-      double* Ai = A + i * ld;
-      const double lij = Ai[j];
-      int k = j + 1;
-      B2K_NOUNROLL for (; k + 2 <= i + 1; k += 2) {
-        const double a0 = Ai[k] - lij * Lj[k * ld];
-        const double a1 = Ai[k + 1] - lij * Lj[(k + 1) * ld];
-        Ai[k] = a0;
-        Ai[k + 1] = a1;
+    if (tri) {
+      const int mrem = n - j - 1, cnt = mrem * (mrem + 1) / 2;
+      double* base = A + (j + 1) * ld;  // row j + 1
+      B2K_NOUNROLL for (int p = e.lane; p < cnt; p += 2 * B2K_G) {
+        const unsigned t0 = tri[p];
+        double* r0 = base + (t0 & 255u) * ld;
+        const double v0 = r0[j + 1 + (t0 >> 8)] - r0[j] * base[(t0 >> 8) * ld + j];
+        if (p + B2K_G < cnt) {
+          const unsigned t1 = tri[p + B2K_G];
+          double* r1 = base + (t1 & 255u) * ld;
+          r1[j + 1 + (t1 >> 8)] -= r1[j] * base[(t1 >> 8) * ld + j];
+        }
+        r0[j + 1 + (t0 >> 8)] = v0;
       }
-      if (k <= i) Ai[k] -= lij * Lj[k * ld];
+    } else {
+      const double* Lj = A + j;  // column j: L(k, j) = Lj[k * ld]
+      B2K_NOUNROLL for (int i = j + 1 + e.lane; i < n; i += B2K_G) {
+        double* Ai = A + i * ld;
+        const double lij = Ai[j];
+        int k = j + 1;
+        B2K_NOUNROLL for (; k + 2 <= i + 1; k += 2) {
+          const double a0 = Ai[k] - lij * Lj[k * ld];
+          const double a1 = Ai[k + 1] - lij * Lj[(k + 1) * ld];
+          Ai[k] = a0;
+          Ai[k + 1] = a1;
+        }
+        if (k <= i) Ai[k] -= lij * Lj[k * ld];
+      }
     }
     WSYNC();
   }
@@ -844,6 +868,7 @@ struct PrimalCtx {
   double *Jaref, *Jv, *quad, *Ma, *Mv, *grad, *Mgrad, *search, *gradold, *Mgradold, *invd, *H;
   double quadGauss[3];
   double cost, gauss, scale;
+  const unsigned short* tri;  // pair table of the Cholesky (cholPairTable), or null
 };
 
 struct LSPoint {
@@ -993,13 +1018,13 @@ __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
       WSYNC();
       r += dim - 1;
     }
-    cholFactor_warp<SM>(e, nv, ld, B2K_MINVAL);
+    cholFactor_warp<SM>(e, nv, ld, B2K_MINVAL, nullptr);  // XF_SCRATCH holds the column lists here
     return;
   }
 #endif
   hessianJTDJ_reg<10>(e, c, P, H, ld, c_dim, cH);
   WSYNC();
-  cholFactor_warp<SM>(e, nv, ld, B2K_MINVAL);
+  cholFactor_warp<SM>(e, nv, ld, B2K_MINVAL, c.tri);
 }
 __device__ __forceinline__ void primalHessian(const Env e, PrimalCtx& c) {
   if (c_dm.xoff_s[XF_NEWTON_H] >= 0) primalHessianT<true>(e, c);
@@ -1166,6 +1191,7 @@ __device__ __noinline__ int solvePrimal(const Env e, int nefc, int ncon, bool ne
   c.Jaref = e.XG(XF_EFC_JAREF); c.Jv = e.XG(XF_EFC_JV); c.quad = e.XG(XF_EFC_QUAD);
   c.H = newton ? e.XG(XF_NEWTON_H) : nullptr;
   c.scale = 1 / (m.env_scalars[0] * max(1, nv));
+  c.tri = (newton && m.team_warps == 1 && nv <= B2K_SPARSE_H_MIN_NV) ? cholPairTable(e, nv) : nullptr;
   double* qacc = e.D(B2MJ_F_QACC);
 
   SPROF_DECL

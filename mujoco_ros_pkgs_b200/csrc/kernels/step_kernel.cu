@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
       WSYNC();
     }
 
+    triTableBuild(e);
     // ---- state record: HBM -> SMEM with one TMA bulk copy (segments A+B are contiguous) ----
     const unsigned load_bytes = (unsigned)(m.rec_C_begin - m.rec_A_begin) * 8u;
     if (!bar_ready) {
