@@ -83,6 +83,9 @@ __device__ __noinline__ void triTableBuild(const Env e) {
 // The megakernel is instruction-fetch bound (profiles/): run-time-bounded loops stay rolled so their bodies are
 // re-executed from the instruction cache instead of being fetched as straight-line copies.
 #define B2K_NOUNROLL _Pragma("unroll 1")
+// Row dot products whose operand streams from the env's L2 arena (efc_J): four loads in flight per trip, ONE accumulator,
+// so the summation order -- and the result -- is that of the rolled loop while the exposed L2 latency drops fourfold.
+#define B2K_UNROLL4 _Pragma("unroll 4")
 
 // lane-strided loop; never unrolled: trip counts are 1-2 for the models this kernel targets and the
 // megakernel is instruction-cache bound, so code size matters more than loop overhead

@@ -440,7 +440,7 @@ __device__ __noinline__ void stage_referenceConstraint(const Env e, int nefc) {
   const double* qvel = e.D(B2MJ_F_QVEL);
   FORL(i, nefc) {
     double s = 0;
-    B2K_NOUNROLL for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qvel[k];
+    B2K_UNROLL4 for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qvel[k];
     P.vel[i] = s;
     P.aref[i] = -P.KBIP[4 * i + 1] * s - P.KBIP[4 * i] * P.KBIP[4 * i + 2] * (P.pos[i] - P.margin[i]);
   }

@@ -399,7 +399,7 @@ __device__ __forceinline__ void mulWT(const Env e, double* y, const double* W, c
   const DevModel& m = c_dm;
   FORL(k, m.nv) {
     double s = x[k];
-    B2K_NOUNROLL for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
+    B2K_UNROLL4 for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
     y[k] = s;
   }
 }
@@ -409,14 +409,14 @@ __device__ __noinline__ void solveW_warp(const Env e, double* x, const double* W
   const DevModel& m = c_dm;
   FORL(k, m.nv) {
     double s = x[k];
-    B2K_NOUNROLL for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
+    B2K_UNROLL4 for (int p = m.dof_descadr[k]; p < m.dof_descadr[k + 1]; p++) s += W[m.dof_desc_adr[p]] * x[m.dof_desc_dof[p]];
     tmp[k] = s * dinv[k];
   }
   WSYNC();
   FORL(i, m.nv) {
     const int row = m.dof_Madr[i] + 1, d = m.dof_nanc[i];
     double s = tmp[i];
-    B2K_NOUNROLL for (int a = 0; a < d; a++) s += W[row + a] * tmp[m.M_col[row + a]];
+    B2K_UNROLL4 for (int a = 0; a < d; a++) s += W[row + a] * tmp[m.M_col[row + a]];
     x[i] = s;
   }
   WSYNC();
@@ -448,8 +448,8 @@ __device__ __noinline__ void mulM_warp(const Env e, double* res, const double* v
   FORL(i, m.nv) {
     const int row = m.dof_Madr[i], d = m.dof_nanc[i];
     double s = qM[row] * vec[i];
-    B2K_NOUNROLL for (int a = 0; a < d; a++) s += qM[row + 1 + a] * vec[m.M_col[row + 1 + a]];
-    B2K_NOUNROLL for (int p = m.dof_descadr[i]; p < m.dof_descadr[i + 1]; p++) s += qM[m.dof_desc_adr[p]] * vec[m.dof_desc_dof[p]];
+    B2K_UNROLL4 for (int a = 0; a < d; a++) s += qM[row + 1 + a] * vec[m.M_col[row + 1 + a]];
+    B2K_UNROLL4 for (int p = m.dof_descadr[i]; p < m.dof_descadr[i + 1]; p++) s += qM[m.dof_desc_adr[p]] * vec[m.dof_desc_dof[p]];
     res[i] = s;
   }
   WSYNC();

@@ -716,7 +716,7 @@ __device__ __forceinline__ void mulJacVec_warp(const Env e, int nefc, double* re
   const double* J = solveJ(e);
   FORL(i, nefc) {
     double s = 0;
-    B2K_NOUNROLL for (int k = 0; k < nv; k++) s += J[i * nv + k] * vec[k];
+    B2K_UNROLL4 for (int k = 0; k < nv; k++) s += J[i * nv + k] * vec[k];
     res[i] = s;
   }
   WSYNC();
@@ -1262,7 +1262,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
   // efc_b = J qacc_smooth - aref
   FORL(i, nefc) {
     double s = 0;
-    B2K_NOUNROLL for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qas[k];
+    B2K_UNROLL4 for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * qas[k];
     P.b[i] = s - P.aref[i];
   }
   WSYNC();
@@ -1279,7 +1279,7 @@ __device__ __noinline__ int stage_fwdConstraint(const Env e, int nefc, int ncon)
     if (warmstart) {
       FORL(i, nefc) {
         double s = 0;
-        B2K_NOUNROLL for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * warm[k];
+        B2K_UNROLL4 for (int k = 0; k < nv; k++) s += P.J[i * nv + k] * warm[k];
         jar[i] = s - P.aref[i];
       }
       WSYNC();
