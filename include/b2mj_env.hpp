@@ -166,6 +166,15 @@ class BatchEnv {
   } settings_;
 
   // ---- model loading (mujoco_env.cpp:771-911: file path or XML string through the VFS) ----
+  // viewer.cpp:1735-1745 ("load key": copy of key_qpos / key_qvel / key_act / key_mpos / key_mquat into mjData, here
+  // with mj_resetDataKeyframe semantics) for the whole batch.  Returns false for a key the model does not have.
+  bool loadKeyframe(int key) {
+    MutexLock lock(physics_thread_mutex_);
+    if (!handle_ || b2mj_reset_keyframe(handle_, key, nullptr) != B2MJ_OK) return false;
+    data_->invalidate();
+    return true;
+  }
+
   bool load(const std::string& filename) { return loadImpl(filename, false); }
   bool loadFromString(const std::string& xml) { return loadImpl(xml, true); }
   const std::string& loadError() const { return load_error_; }
@@ -307,14 +316,6 @@ class BatchEnv {
     settings_.reset_request.store(0);
   }
 
-  // viewer.cpp:1735-1745 ("load key": mj_resetDataKeyframe-style copy of key_qpos / key_qvel / key_act / key_mpos /
-  // key_mquat into mjData), for the whole batch.  Returns false for a key the model does not have.
-  bool loadKeyframe(int key) {
-    if (!handle_ || b2mj_reset_keyframe(handle_, key, nullptr) != 0) return false;
-    data_->invalidate();
-    return true;
-  }
-
   // mujoco_env.cpp:266-402.  Values are broadcast to every env of the batch.
   void loadInitialJointStates() {
     auto parse = [](const std::string& s, std::vector<double>& out) {
@@ -415,7 +416,9 @@ class BatchEnv {
   bool loadImpl(const std::string& src, bool is_string) {
     MutexLock lock(physics_thread_mutex_);
     b2mjModel* m = nullptr;
-    const int rc = is_string ? b2mj_model_from_xml_string(src.c_str(), &m) : b2mj_model_from_xml_file(src.c_str(), &m);
+    // files dispatch on their extension like the reference's loader (mujoco_env.cpp:771-911: .mjb -> mj_loadModel,
+    // else mj_loadXML): ".b2mjb" is this library's binary model format, anything else is MJCF
+    const int rc = is_string ? b2mj_model_from_xml_string(src.c_str(), &m) : b2mj_model_from_file(src.c_str(), &m);
     if (rc != B2MJ_OK) { load_error_ = b2mj_last_error(); return false; }
     b2mj_handle* h = nullptr;
     if (b2mj_create(m, nenv_, device_, &h) != B2MJ_OK) {

@@ -159,6 +159,52 @@ static void test_reset() {  // :480-530
   }
 }
 
+static void test_keyframes_and_binary_models() {  // viewer.cpp:1735-1745 "load key"; mujoco_env.cpp:771-911 extension dispatch
+  const char* xml =
+      "<mujoco><option timestep=\"0.002\"/><worldbody><body pos=\"0 0 1\"><joint name=\"h\" type=\"hinge\" axis=\"0 1 0\"/>"
+      "<geom type=\"capsule\" fromto=\"0 0 0 0.3 0 0\" size=\"0.02\"/></body></worldbody>"
+      "<keyframe><key name=\"bent\" time=\"0.5\" qpos=\"0.7\" qvel=\"-1.5\"/></keyframe></mujoco>";
+  BatchEnv env(g_nenv);
+  EXPECT_TRUE(env.loadFromString(xml));
+  const b2mjModel* m = env.getModelPtr();
+  EXPECT_TRUE(m->nkey == 1);
+  EXPECT_TRUE(b2mj_name2id(m, B2MJ_OBJ_KEY, "bent") == 0);
+  EXPECT_FALSE(env.loadKeyframe(3));
+  EXPECT_TRUE(env.loadKeyframe(0));
+  {
+    BatchEnv::MutexLock lock(env.physics_thread_mutex_);
+    BatchData* d = env.getDataPtr();
+    d->invalidate();
+    for (int e = 0; e < env.nenv(); e++) {
+      EXPECT_DOUBLE_EQ(d->row(B2MJ_F_QPOS, e)[0], 0.7);
+      EXPECT_DOUBLE_EQ(d->row(B2MJ_F_QVEL, e)[0], -1.5);
+      EXPECT_DOUBLE_EQ(d->time(e), 0.5);
+    }
+  }
+  // save as a binary model, load it through the extension dispatch, step both: identical
+  const std::string path = "/tmp/b2mj_test_model.b2mjb";
+  EXPECT_TRUE(b2mj_model_save_binary(m, path.c_str()) == B2MJ_OK);
+  BatchEnv env2(g_nenv);
+  EXPECT_TRUE(env2.load(path));
+  EXPECT_TRUE(env2.getModelPtr()->nkey == 1);
+  EXPECT_TRUE(env2.loadKeyframe(0));
+  env.startPhysicsLoop();
+  env2.startPhysicsLoop();
+  EXPECT_TRUE(env.step(50));
+  EXPECT_TRUE(env2.step(50));
+  {
+    BatchEnv::MutexLock l1(env.physics_thread_mutex_);
+    BatchEnv::MutexLock l2(env2.physics_thread_mutex_);
+    env.getDataPtr()->invalidate();
+    env2.getDataPtr()->invalidate();
+    EXPECT_DOUBLE_EQ(env.getDataPtr()->row(B2MJ_F_QPOS, 0)[0], env2.getDataPtr()->row(B2MJ_F_QPOS, 0)[0]);
+    EXPECT_NEAR(env.getDataPtr()->time(0), 0.5 + 50 * 0.002, 1e-12);
+  }
+  BatchEnv env3(g_nenv);
+  EXPECT_FALSE(env3.load("/tmp/does_not_exist.b2mjb"));
+  std::remove(path.c_str());
+}
+
 static void test_plugin_callbacks() {  // mujoco_ros_plugin_test.cpp:97-121 + order + counts
   BatchEnv env(g_nenv);
   auto* tp = new TestPlugin();
@@ -491,6 +537,7 @@ int main(int argc, char** argv) {
   test_step_while_paused();
   test_num_steps_exit();
   test_reset();
+  test_keyframes_and_binary_models();
   test_plugin_callbacks();
   test_hook_semantics();
   test_initial_joint_states();
