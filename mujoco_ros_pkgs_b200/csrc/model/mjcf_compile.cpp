@@ -508,8 +508,10 @@ struct Builder {
           mat2quat(q, V);
           mulquat(b.iquat, b.iquat, q);
         } else fail(ch.get(), "inertial needs diaginertia or fullinertia");
-      } else if (t == "light" || t == "camera" || t == "composite" || t == "include") {
-        // rendering-only or unsupported sugar: ignored
+      } else if (t == "light" || t == "camera") {
+        // rendering only: no effect on the physics
+      } else if (t == "composite") {
+        fail(ch.get(), "composite bodies are not supported (expand them in the model file)");
       } else {
         fail(ch.get(), "unsupported element inside body");
       }
@@ -624,6 +626,37 @@ const SensorSpec kSensors[] = {
     {"subtreeangmom", B2MJ_SENS_SUBTREEANGMOM, 3, B2MJ_STAGE_VEL, 0, "body", B2MJ_OBJ_BODY},
     {"clock", B2MJ_SENS_CLOCK, 1, B2MJ_STAGE_POS, 0, nullptr, B2MJ_OBJ_UNKNOWN},
 };
+
+// <include file="..."/>: the children of the included file's root element replace the include element, wherever it
+// stands (MuJoCo's semantics); relative paths resolve against the directory of the main model file.
+void expand_includes(XmlNode* n, int depth) {
+  if (depth > 16) fail(n, "includes nested too deeply (cycle?)");
+  for (size_t i = 0; i < n->children.size();) {
+    XmlNode* ch = n->children[i].get();
+    if (ch->tag != "include") {
+      expand_includes(ch, depth);
+      i++;
+      continue;
+    }
+    auto* fa = ch->attr("file");
+    if (!fa) fail(ch, "include needs a file attribute");
+    std::string path = *fa;
+    if (path.empty() || path[0] != '/') path = model_dir() + (model_dir().empty() ? "" : "/") + path;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) fail(ch, "cannot open included file '" + path + "'");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::string err;
+    auto inc = xml_parse(ss.str(), err);
+    if (!inc) fail(ch, "included file '" + path + "': " + err);
+    if (inc->tag != "mujoco" && inc->tag != "mujocoinclude") fail(ch, "included file '" + path + "' must have a <mujoco> or <mujocoinclude> root");
+    expand_includes(inc.get(), depth + 1);
+    std::vector<std::unique_ptr<XmlNode>> kids = std::move(inc->children);
+    n->children.erase(n->children.begin() + (long)i);
+    for (size_t k = 0; k < kids.size(); k++) n->children.insert(n->children.begin() + (long)(i + k), std::move(kids[k]));
+    i += kids.size();
+  }
+}
 
 b2mjModel* compile(const XmlNode* root) {
   if (root->tag != "mujoco") fail(root, "root element must be <mujoco>");
@@ -1520,6 +1553,7 @@ int b2mj_model_from_xml_string(const char* xml, b2mjModel** out) {
     return B2MJ_EPARSE;
   }
   try {
+    expand_includes(root.get(), 0);
     *out = compile(root.get());
   } catch (const CompileError& e) {
     set_error(e.msg);

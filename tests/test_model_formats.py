@@ -150,3 +150,32 @@ def test_gpu_reset_keyframe_matches_oracle(capi, orc):
     assert np.max(np.abs(gq[0] - o.get("qpos")) / (1 + np.abs(o.get("qpos")))) < 1e-8
     with pytest.raises(capi.B2mjError):
         sim.reset_keyframe(2)
+
+
+def test_include_files_are_expanded_in_place(capi, tmp_path):
+    """<include file=.../> anywhere in the tree (MJCF's way of splitting robot / scene files); the reference loads such
+    models through mj_loadXML (mujoco_env.cpp:840-843)."""
+    (tmp_path / "arm.xml").write_text("""<mujocoinclude>
+      <body name="upper" pos="0 0 1"><joint name="sh" type="hinge" axis="0 1 0"/>
+        <geom type="capsule" fromto="0 0 0 0.3 0 0" size="0.03"/>
+        <include file="fore.xml"/>
+      </body></mujocoinclude>""")
+    (tmp_path / "fore.xml").write_text("""<mujoco><body name="fore" pos="0.3 0 0"><joint name="el" type="hinge" axis="0 1 0"/>
+      <geom type="capsule" fromto="0 0 0 0.25 0 0" size="0.025"/></body></mujoco>""")
+    (tmp_path / "act.xml").write_text('<mujoco><actuator><motor joint="sh"/><motor joint="el"/></actuator></mujoco>')
+    main = tmp_path / "scene.xml"
+    main.write_text("""<mujoco><option timestep="0.002"/><worldbody><geom type="plane" size="2 2 0.1"/>
+      <include file="arm.xml"/></worldbody><include file="act.xml"/></mujoco>""")
+    m = capi.Model.from_xml_file(str(main))
+    assert (m.nbody, m.njnt, m.nu, m.ngeom) == (3, 2, 2, 3)
+    assert m.name2id(capi.OBJ_BODY, "fore") == 2 and m.body_parentid[2] == 1
+    with pytest.raises(capi.B2mjError, match="cannot open included file"):
+        capi.Model.from_xml_string('<mujoco><include file="nope.xml"/></mujoco>')
+    (tmp_path / "loop.xml").write_text('<mujoco><include file="loop.xml"/></mujoco>')
+    with pytest.raises(capi.B2mjError, match="nested too deeply"):
+        capi.Model.from_xml_file(str(tmp_path / "loop.xml"))
+
+
+def test_composite_is_rejected_not_ignored(capi):
+    with pytest.raises(capi.B2mjError, match="composite"):
+        capi.Model.from_xml_string('<mujoco><worldbody><body><composite type="grid" count="2 2 1"/></body></worldbody></mujoco>')
