@@ -63,7 +63,7 @@ enum { B2MJ_GAIN_FIXED = 0, B2MJ_GAIN_AFFINE = 1 };
 enum { B2MJ_BIAS_NONE = 0, B2MJ_BIAS_AFFINE = 1 };
 enum { B2MJ_OBJ_UNKNOWN = 0, B2MJ_OBJ_BODY = 1, B2MJ_OBJ_XBODY = 2, B2MJ_OBJ_JOINT = 3, B2MJ_OBJ_DOF = 4,
        B2MJ_OBJ_GEOM = 5, B2MJ_OBJ_SITE = 6, B2MJ_OBJ_CAMERA = 7, B2MJ_OBJ_TENDON = 16,
-       B2MJ_OBJ_ACTUATOR = 17, B2MJ_OBJ_SENSOR = 18, B2MJ_OBJ_EQUALITY = 15, B2MJ_OBJ_KEY = 21 };
+       B2MJ_OBJ_ACTUATOR = 17, B2MJ_OBJ_SENSOR = 18, B2MJ_OBJ_PAIR = 13, B2MJ_OBJ_EQUALITY = 15, B2MJ_OBJ_KEY = 21 };
 enum { B2MJ_STAGE_NONE = 0, B2MJ_STAGE_POS = 1, B2MJ_STAGE_VEL = 2, B2MJ_STAGE_ACC = 3 };
 enum { B2MJ_DATATYPE_REAL = 0, B2MJ_DATATYPE_POSITIVE = 1, B2MJ_DATATYPE_AXIS = 2, B2MJ_DATATYPE_QUATERNION = 3 };
 /* sensor enum: the 36 types the reference's sensor plugin names (mujoco_sensor_handler_plugin.cpp:70-105) */
@@ -141,7 +141,7 @@ typedef struct b2mjStatistic {
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(nwrap) X(neq)          \
   X(nsensor) X(nsensordata) X(nM) X(nmocap) X(nexclude) X(ncollpair) X(nconmax) X(njmax)          \
   X(nnames) X(nlevel) X(ntree)                                                                    \
-  X(nmesh) X(nmeshvert)                                                                           \
+  X(npair) X(nmesh) X(nmeshvert)                                                                           \
   X(nkey) X(nkeyq) X(nkeyv) X(nkeya) X(nkeyu) X(nkeymp) X(nkeymq) /* keyframes; nkeyq = nkey*nq, ... (flat arrays) */
 
 /* X(ctype, name, rows(size field), cols) */
@@ -199,6 +199,10 @@ typedef struct b2mjStatistic {
   X(int, exclude_signature, nexclude, 1)                                                          \
   X(int, collpair_geom1, ncollpair, 1) X(int, collpair_geom2, ncollpair, 1)                       \
   X(int, collpair_slotadr, ncollpair, 1) X(int, collpair_maxcon, ncollpair, 1)                    \
+  X(int, collpair_pairid, ncollpair, 1) /* explicit <contact><pair> behind the candidate, or -1 */ \
+  X(int, pair_geom1, npair, 1) X(int, pair_geom2, npair, 1) X(int, pair_dim, npair, 1)            \
+  X(double, pair_solref, npair, 2) X(double, pair_solimp, npair, 5) X(double, pair_margin, npair, 1) \
+  X(double, pair_gap, npair, 1) X(double, pair_friction, npair, 5) X(int, name_pairadr, npair, 1) \
   X(int, sensor_type, nsensor, 1) X(int, sensor_datatype, nsensor, 1)                             \
   X(int, sensor_needstage, nsensor, 1) X(int, sensor_objtype, nsensor, 1)                         \
   X(int, sensor_objid, nsensor, 1) X(int, sensor_reftype, nsensor, 1)                             \

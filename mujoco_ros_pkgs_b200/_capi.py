@@ -125,7 +125,7 @@ def check(rc: int, what: str = "") -> int:
 
 # object types (b2mj.h)
 OBJ_BODY, OBJ_XBODY, OBJ_JOINT, OBJ_DOF, OBJ_GEOM, OBJ_SITE = 1, 2, 3, 4, 5, 6
-OBJ_EQUALITY, OBJ_TENDON, OBJ_ACTUATOR, OBJ_SENSOR, OBJ_KEY = 15, 16, 17, 18, 21
+OBJ_EQUALITY, OBJ_TENDON, OBJ_ACTUATOR, OBJ_SENSOR, OBJ_KEY, OBJ_PAIR = 15, 16, 17, 18, 21, 13
 
 
 class Model:

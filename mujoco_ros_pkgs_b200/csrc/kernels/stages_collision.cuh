@@ -426,13 +426,14 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
     const int p = base + e.lane;
     PairCon pc;
     pc.shared_frame = 0;
-    int num = 0, g1 = 0, g2 = 0;
+    int num = 0, g1 = 0, g2 = 0, pid = -1;
     double margin = 0, gap = 0;
     if (p < m.ncollpair) {
       g1 = m.collpair_geom1[p];
       g2 = m.collpair_geom2[p];
-      margin = fmax(m.geom_margin[g1], m.geom_margin[g2]);
-      gap = fmax(m.geom_gap[g1], m.geom_gap[g2]);
+      pid = m.collpair_pairid[p];  // explicit <contact><pair>: its own margin / gap / contact parameters
+      margin = pid >= 0 ? m.pair_margin[pid] : fmax(m.geom_margin[g1], m.geom_margin[g2]);
+      gap = pid >= 0 ? m.pair_gap[pid] : fmax(m.geom_gap[g1], m.geom_gap[g2]);
       const double r1 = m.geom_rbound[g1], r2 = m.geom_rbound[g2];
       bool cull = false;
       if (r1 > 0 && r2 > 0) {
@@ -452,8 +453,13 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
     const int total = __shfl_sync(e.mask, incl, B2K_G - 1, B2K_G);
     if (num > 0) {
       int condim;
-      double solref[2], solimp[5], fri[3];
-      if (m.geom_priority[g1] != m.geom_priority[g2]) {
+      double solref[2], solimp[5], fri[3], fri5[5];
+      if (pid >= 0) {
+        condim = m.pair_dim[pid];
+        for (int i = 0; i < 2; i++) solref[i] = m.pair_solref[2 * pid + i];
+        for (int i = 0; i < 5; i++) solimp[i] = m.pair_solimp[5 * pid + i];
+        for (int i = 0; i < 5; i++) fri5[i] = m.pair_friction[5 * pid + i];
+      } else if (m.geom_priority[g1] != m.geom_priority[g2]) {
         const int gi = m.geom_priority[g1] > m.geom_priority[g2] ? g1 : g2;
         condim = m.geom_condim[gi];
         for (int i = 0; i < 2; i++) solref[i] = m.geom_solref[2 * gi + i];
@@ -487,9 +493,13 @@ __device__ __noinline__ int stage_collision(const Env e, int* warning) {
         const double inc = margin - gap;
         c_inc[c] = inc;
         double* f = c_fri + 5 * c;
-        f[0] = f[1] = fmax(B2MJ_MINMU, fri[0]);
-        f[2] = fmax(B2MJ_MINMU, fri[1]);
-        f[3] = f[4] = fmax(B2MJ_MINMU, fri[2]);
+        if (pid >= 0) {
+          for (int k = 0; k < 5; k++) f[k] = fmax(B2MJ_MINMU, fri5[k]);
+        } else {
+          f[0] = f[1] = fmax(B2MJ_MINMU, fri[0]);
+          f[2] = fmax(B2MJ_MINMU, fri[1]);
+          f[3] = f[4] = fmax(B2MJ_MINMU, fri[2]);
+        }
         c_solref[2 * c] = solref[0]; c_solref[2 * c + 1] = solref[1];
         for (int k = 0; k < 5; k++) c_solimp[5 * c + k] = solimp[k];
         c_mu[c] = 0;

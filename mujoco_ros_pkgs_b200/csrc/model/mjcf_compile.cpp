@@ -820,7 +820,7 @@ b2mjModel* compile(const XmlNode* root) {
   }
 
   // ---- tendons, actuators, equality, excludes, sensors: collected as nodes, resolved after ids exist
-  std::vector<const XmlNode*> tendon_nodes, act_nodes, eq_nodes, excl_nodes, sens_nodes, key_nodes;
+  std::vector<const XmlNode*> tendon_nodes, act_nodes, eq_nodes, excl_nodes, sens_nodes, key_nodes, pair_nodes;
   for (auto& sec : root->children) {
     if (sec->tag == "tendon")
       for (auto& ch : sec->children) {
@@ -834,7 +834,8 @@ b2mjModel* compile(const XmlNode* root) {
     else if (sec->tag == "contact")
       for (auto& ch : sec->children) {
         if (ch->tag == "exclude") excl_nodes.push_back(ch.get());
-        else fail(ch.get(), "only <exclude> is supported inside <contact>");
+        else if (ch->tag == "pair") pair_nodes.push_back(ch.get());
+        else fail(ch.get(), "<contact> accepts <pair> and <exclude>");
       }
     else if (sec->tag == "sensor")
       for (auto& ch : sec->children) sens_nodes.push_back(ch.get());
@@ -868,6 +869,7 @@ b2mjModel* compile(const XmlNode* root) {
   m->nmesh = (int)ctx.meshes.size();
   m->nmeshvert = 0;
   for (auto& md : ctx.meshes) m->nmeshvert += (int)md.vert.size() / 3;
+  m->npair = (int)pair_nodes.size();
   m->nkey = (int)key_nodes.size();
   m->nkeyq = m->nkey * nq; m->nkeyv = m->nkey * nv; m->nkeyu = m->nkey * m->nu;
   m->nkeymp = m->nkey * 3 * nmocap; m->nkeymq = m->nkey * 4 * nmocap;
@@ -905,7 +907,7 @@ b2mjModel* compile(const XmlNode* root) {
 
   // pre-build names so nnames is known
   std::vector<int> nb_adr(nbody), nj_adr(njnt), ng_adr(ngeom), ns_adr(nsite), nt_adr(m->ntendon), na_adr(m->nu),
-      nsn_adr(m->nsensor), ne_adr(m->neq), nk_adr(m->nkey);
+      nsn_adr(m->nsensor), ne_adr(m->neq), nk_adr(m->nkey), np_adr(m->npair);
   {
     int j = 0, g = 0, s = 0;
     for (int i = 0; i < nbody; i++) {
@@ -943,6 +945,8 @@ b2mjModel* compile(const XmlNode* root) {
       ne_adr[i] = names.add(eq_nodes[i]->attr("name") ? *eq_nodes[i]->attr("name") : "");
     for (size_t i = 0; i < key_nodes.size(); i++)
       nk_adr[i] = names.add(key_nodes[i]->attr("name") ? *key_nodes[i]->attr("name") : "");
+    for (size_t i = 0; i < pair_nodes.size(); i++)
+      np_adr[i] = names.add(pair_nodes[i]->attr("name") ? *pair_nodes[i]->attr("name") : "");
   }
   m->nnames = (int)names.buf.size();
   m->ntree = 0;
@@ -957,6 +961,7 @@ b2mjModel* compile(const XmlNode* root) {
   std::copy(nsn_adr.begin(), nsn_adr.end(), m->name_sensoradr);
   std::copy(ne_adr.begin(), ne_adr.end(), m->name_eqadr);
   std::copy(nk_adr.begin(), nk_adr.end(), m->name_keyadr);
+  std::copy(np_adr.begin(), np_adr.end(), m->name_pairadr);
   {
     int adr = 0;
     for (int i = 0; i < m->nmesh; i++) {
@@ -1448,6 +1453,35 @@ b2mjModel* compile(const XmlNode* root) {
     }
   }
 
+  // ---- explicit contact pairs: parameters not given are filled from the two geoms with the rules the collision
+  //      driver applies to dynamic pairs (max condim / friction / margin / gap, solmix-weighted solref / solimp)
+  for (size_t i = 0; i < pair_nodes.size(); i++) {
+    const XmlNode* n = pair_nodes[i];
+    AttrMap em = effective(ctx, n, "");
+    A a{em, n};
+    if (!a.has("geom1") || !a.has("geom2")) fail(n, "pair needs geom1 and geom2");
+    const int g1 = lookup(B.geom_id, n, "geom", a.str("geom1")), g2 = lookup(B.geom_id, n, "geom", a.str("geom2"));
+    if (m->geom_bodyid[g1] == m->geom_bodyid[g2]) fail(n, "pair geoms belong to the same body");
+    m->pair_geom1[i] = g1;
+    m->pair_geom2[i] = g2;
+    m->pair_dim[i] = a.integer("condim", std::max(m->geom_condim[g1], m->geom_condim[g2]));
+    if (m->pair_dim[i] != 1 && m->pair_dim[i] != 3 && m->pair_dim[i] != 4 && m->pair_dim[i] != 6) fail(n, "condim must be 1,3,4 or 6");
+    const double s1 = m->geom_solmix[g1], s2 = m->geom_solmix[g2];
+    const double mix = (s1 >= B2MJ_MINVAL && s2 >= B2MJ_MINVAL) ? s1 / (s1 + s2) : (s1 < B2MJ_MINVAL && s2 < B2MJ_MINVAL) ? 0.5 : (s1 < B2MJ_MINVAL ? 0.0 : 1.0);
+    const double *ra = m->geom_solref + 2 * g1, *rb = m->geom_solref + 2 * g2;
+    for (int k = 0; k < 2; k++) m->pair_solref[2 * i + k] = (ra[0] > 0 && rb[0] > 0) ? mix * ra[k] + (1 - mix) * rb[k] : std::min(ra[k], rb[k]);
+    for (int k = 0; k < 5; k++) m->pair_solimp[5 * i + k] = mix * m->geom_solimp[5 * g1 + k] + (1 - mix) * m->geom_solimp[5 * g2 + k];
+    double f3[3];
+    for (int k = 0; k < 3; k++) f3[k] = std::max(m->geom_friction[3 * g1 + k], m->geom_friction[3 * g2 + k]);
+    double f5[5] = {f3[0], f3[0], f3[1], f3[2], f3[2]};
+    a.vec("friction", f5, 5);
+    std::copy(f5, f5 + 5, m->pair_friction + 5 * i);
+    a.vec("solref", m->pair_solref + 2 * i, 2, 2);
+    a.vec("solimp", m->pair_solimp + 5 * i, 5, 3);
+    m->pair_margin[i] = a.num("margin", std::max(m->geom_margin[g1], m->geom_margin[g2]));
+    m->pair_gap[i] = a.num("gap", std::max(m->geom_gap[g1], m->geom_gap[g2]));
+  }
+
   std::string err;
   if (model_set_const(m, err)) throw CompileError{err};
   // tendon spring length -1 => use length at qpos0
@@ -1483,53 +1517,72 @@ b2mjModel* compile(const XmlNode* root) {
 // in the order its driver emits contacts (ascending body-pair signature, then geom ids).
 void model_build_collision_pairs(b2mjModel* m) {
   std::free(m->collpair_geom1); std::free(m->collpair_geom2);
-  std::free(m->collpair_slotadr); std::free(m->collpair_maxcon);
-  m->collpair_geom1 = m->collpair_geom2 = m->collpair_slotadr = m->collpair_maxcon = nullptr;
-  std::vector<int> g1s, g2s, maxc;
+  std::free(m->collpair_slotadr); std::free(m->collpair_maxcon); std::free(m->collpair_pairid);
+  m->collpair_geom1 = m->collpair_geom2 = m->collpair_slotadr = m->collpair_maxcon = m->collpair_pairid = nullptr;
+  struct Cand { int sig, g1, g2, maxcon, pairid; };
+  std::vector<Cand> cand;
+  auto maxcon_of = [&](int t1, int t2) {
+    if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_CAPSULE) return 2;
+    if (t1 == B2MJ_GEOM_PLANE && (t2 == B2MJ_GEOM_CYLINDER || t2 == B2MJ_GEOM_MESH || t2 == B2MJ_GEOM_BOX)) return 4;
+    if (t1 == B2MJ_GEOM_CAPSULE && (t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) return 2;
+    if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) return 8;
+    return 1;
+  };
+  auto push = [&](int ga, int gb, int pairid) {
+    int x = ga, y = gb;
+    if (m->geom_type[x] > m->geom_type[y]) std::swap(x, y);  // narrowphase table is upper-triangular in type
+    const int t1 = m->geom_type[x], t2 = m->geom_type[y];
+    if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_PLANE) return;
+    const int b1 = std::min(m->geom_bodyid[ga], m->geom_bodyid[gb]), b2 = std::max(m->geom_bodyid[ga], m->geom_bodyid[gb]);
+    cand.push_back({(b1 << 16) + b2, x, y, maxcon_of(t1, t2), pairid});
+  };
+  // explicit pairs (opt.collision all / predefined): no contype / conaffinity, parent or exclude filtering
+  std::set<std::pair<int, int>> explicit_pairs;
+  if (m->opt.collision != 2)
+    for (int p = 0; p < m->npair; p++) {
+      push(m->pair_geom1[p], m->pair_geom2[p], p);
+      explicit_pairs.insert({std::min(m->pair_geom1[p], m->pair_geom2[p]), std::max(m->pair_geom1[p], m->pair_geom2[p])});
+    }
+  // dynamic pairs (opt.collision all / dynamic); a geom pair that is also listed explicitly is left to its explicit entry
   const bool filterparent = !(m->opt.disableflags & B2MJ_DSBL_FILTERPARENT);
   std::set<int> excl(m->exclude_signature, m->exclude_signature + m->nexclude);
-  for (int b1 = 0; b1 < m->nbody; b1++)
-    for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
-      if (!m->body_geomnum[b1] || !m->body_geomnum[b2]) continue;
-      int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
-      if (w1 == w2) continue;
-      int p1 = m->body_weldid[m->body_parentid[w1]], p2 = m->body_weldid[m->body_parentid[w2]];
-      if (filterparent && w1 != 0 && w2 != 0 && (w1 == p2 || w2 == p1)) continue;
-      if (excl.count((b1 << 16) + b2)) continue;
-      for (int ga = m->body_geomadr[b1]; ga < m->body_geomadr[b1] + m->body_geomnum[b1]; ga++)
-        for (int gb = m->body_geomadr[b2]; gb < m->body_geomadr[b2] + m->body_geomnum[b2]; gb++) {
-          bool ok = (m->geom_contype[ga] & m->geom_conaffinity[gb]) || (m->geom_contype[gb] & m->geom_conaffinity[ga]);
-          if (!ok) continue;
-          int x = ga, y = gb;
-          if (m->geom_type[x] > m->geom_type[y]) std::swap(x, y);  // narrowphase table is upper-triangular in type
-          int t1 = m->geom_type[x], t2 = m->geom_type[y];
-          if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_PLANE) continue;
-          int mc = 1;
-          if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_CAPSULE) mc = 2;
-          else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_CYLINDER) mc = 4;
-          else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_MESH) mc = 4;
-          else if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_BOX) mc = 4;
-          else if (t1 == B2MJ_GEOM_CAPSULE && t2 == B2MJ_GEOM_CAPSULE) mc = 2;
-          else if (t1 == B2MJ_GEOM_CAPSULE && t2 == B2MJ_GEOM_BOX) mc = 2;
-          else if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) mc = 8;
-          g1s.push_back(x);
-          g2s.push_back(y);
-          maxc.push_back(mc);
-        }
-    }
-  m->ncollpair = (int)g1s.size();
-  size_t n = g1s.size() ? g1s.size() : 1;
+  if (m->opt.collision != 1)
+    for (int b1 = 0; b1 < m->nbody; b1++)
+      for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
+        if (!m->body_geomnum[b1] || !m->body_geomnum[b2]) continue;
+        int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
+        if (w1 == w2) continue;
+        int p1 = m->body_weldid[m->body_parentid[w1]], p2 = m->body_weldid[m->body_parentid[w2]];
+        if (filterparent && w1 != 0 && w2 != 0 && (w1 == p2 || w2 == p1)) continue;
+        if (excl.count((b1 << 16) + b2)) continue;
+        for (int ga = m->body_geomadr[b1]; ga < m->body_geomadr[b1] + m->body_geomnum[b1]; ga++)
+          for (int gb = m->body_geomadr[b2]; gb < m->body_geomadr[b2] + m->body_geomnum[b2]; gb++) {
+            bool ok = (m->geom_contype[ga] & m->geom_conaffinity[gb]) || (m->geom_contype[gb] & m->geom_conaffinity[ga]);
+            if (!ok || explicit_pairs.count({std::min(ga, gb), std::max(ga, gb)})) continue;
+            push(ga, gb, -1);
+          }
+      }
+  // contacts come out in body-pair signature order; within a body pair explicit pairs first (in pair order), then the
+  // dynamic geom pairs in geom order
+  std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) {
+    if (a.sig != b.sig) return a.sig < b.sig;
+    return (a.pairid >= 0) > (b.pairid >= 0);
+  });
+  m->ncollpair = (int)cand.size();
+  size_t n = cand.size() ? cand.size() : 1;
   m->collpair_geom1 = (int*)std::calloc(n, sizeof(int));
   m->collpair_geom2 = (int*)std::calloc(n, sizeof(int));
   m->collpair_slotadr = (int*)std::calloc(n, sizeof(int));
   m->collpair_maxcon = (int*)std::calloc(n, sizeof(int));
+  m->collpair_pairid = (int*)std::calloc(n, sizeof(int));
   int slots = 0;
-  for (size_t i = 0; i < g1s.size(); i++) {
-    m->collpair_geom1[i] = g1s[i];
-    m->collpair_geom2[i] = g2s[i];
-    m->collpair_maxcon[i] = maxc[i];
+  for (size_t i = 0; i < cand.size(); i++) {
+    m->collpair_geom1[i] = cand[i].g1;
+    m->collpair_geom2[i] = cand[i].g2;
+    m->collpair_maxcon[i] = cand[i].maxcon;
+    m->collpair_pairid[i] = cand[i].pairid;
     m->collpair_slotadr[i] = slots;
-    slots += maxc[i];
+    slots += cand[i].maxcon;
   }
   m->nconmax = slots;
 }

@@ -285,6 +285,7 @@ static const int* name_adr_table(const b2mjModel* m, int objtype, int* count) {
     case B2MJ_OBJ_SENSOR: *count = m->nsensor; return m->name_sensoradr;
     case B2MJ_OBJ_EQUALITY: *count = m->neq; return m->name_eqadr;
     case B2MJ_OBJ_KEY: *count = m->nkey; return m->name_keyadr;
+    case B2MJ_OBJ_PAIR: *count = m->npair; return m->name_pairadr;
     default: *count = 0; return nullptr;
   }
 }

@@ -426,8 +426,9 @@ void collision(const b2mjModel* m, OrcData* d) {
   if (m->nconmax == 0) return;
   for (int p = 0; p < m->ncollpair; p++) {
     const int g1 = m->collpair_geom1[p], g2 = m->collpair_geom2[p];
-    const double margin = std::fmax(m->geom_margin[g1], m->geom_margin[g2]);
-    const double gap = std::fmax(m->geom_gap[g1], m->geom_gap[g2]);
+    const int pid = m->collpair_pairid[p];  // explicit <contact><pair>: its own margin / gap / contact parameters
+    const double margin = pid >= 0 ? m->pair_margin[pid] : std::fmax(m->geom_margin[g1], m->geom_margin[g2]);
+    const double gap = pid >= 0 ? m->pair_gap[pid] : std::fmax(m->geom_gap[g1], m->geom_gap[g2]);
     // bounding-sphere filter (planes: signed distance to the plane)
     const double r1 = m->geom_rbound[g1], r2 = m->geom_rbound[g2];
     if (r1 > 0 && r2 > 0) {
@@ -446,8 +447,13 @@ void collision(const b2mjModel* m, OrcData* d) {
     if (num <= 0) continue;
     // contact parameters (mixing rules of mj_collideGeoms)
     int condim;
-    double solref[2], solimp[5], fri[3];
-    if (m->geom_priority[g1] != m->geom_priority[g2]) {
+    double solref[2], solimp[5], fri[3], fri5[5];
+    if (pid >= 0) {
+      condim = m->pair_dim[pid];
+      copy(solref, m->pair_solref + 2 * pid, 2);
+      copy(solimp, m->pair_solimp + 5 * pid, 5);
+      copy(fri5, m->pair_friction + 5 * pid, 5);
+    } else if (m->geom_priority[g1] != m->geom_priority[g2]) {
       int gi = m->geom_priority[g1] > m->geom_priority[g2] ? g1 : g2;
       condim = m->geom_condim[gi];
       copy(solref, m->geom_solref + 2 * gi, 2);
@@ -478,9 +484,13 @@ void collision(const b2mjModel* m, OrcData* d) {
       makeFrame(d->contact_frame + 9 * c);
       d->contact_includemargin[c] = margin - gap;
       double* f = d->contact_friction + 5 * c;
-      f[0] = f[1] = std::fmax(B2MJ_MINMU, fri[0]);
-      f[2] = std::fmax(B2MJ_MINMU, fri[1]);
-      f[3] = f[4] = std::fmax(B2MJ_MINMU, fri[2]);
+      if (pid >= 0) {
+        for (int k = 0; k < 5; k++) f[k] = std::fmax(B2MJ_MINMU, fri5[k]);
+      } else {
+        f[0] = f[1] = std::fmax(B2MJ_MINMU, fri[0]);
+        f[2] = std::fmax(B2MJ_MINMU, fri[1]);
+        f[3] = f[4] = std::fmax(B2MJ_MINMU, fri[2]);
+      }
       copy(d->contact_solref + 2 * c, solref, 2);
       copy(d->contact_solimp + 5 * c, solimp, 5);
       d->contact_mu[c] = 0;

@@ -179,3 +179,87 @@ def test_include_files_are_expanded_in_place(capi, tmp_path):
 def test_composite_is_rejected_not_ignored(capi):
     with pytest.raises(capi.B2mjError, match="composite"):
         capi.Model.from_xml_string('<mujoco><worldbody><body><composite type="grid" count="2 2 1"/></body></worldbody></mujoco>')
+
+
+PAIRS = """
+<mujoco>
+  <option timestep="0.002" collision="{mode}"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="2 2 0.1" friction="0.3 0.005 0.0001"/>
+    <body name="a" pos="0 0 0.1"><freejoint/><geom name="ga" type="sphere" size="0.1" friction="0.5 0.005 0.0001" contype="0" conaffinity="0"/></body>
+    <body name="b" pos="0.5 0 0.1"><freejoint/><geom name="gb" type="sphere" size="0.1" friction="0.5 0.005 0.0001"/></body>
+    <body name="c" pos="0.5 0 0.29"><freejoint/><geom name="gc" type="sphere" size="0.1"/></body>
+  </worldbody>
+  <contact>
+    <pair name="grip" geom1="ga" geom2="floor" condim="4" friction="2 2 0.1 0.01 0.01" solref="0.01 1" margin="0.02" gap="0.005"/>
+    <pair geom1="gc" geom2="gb"/>
+    <exclude body1="b" body2="c"/>
+  </contact>
+</mujoco>
+"""
+
+
+def test_explicit_contact_pairs(capi, orc):
+    """<contact><pair>: own parameters, no contype / conaffinity / exclude filtering, merged with the dynamic pairs in
+    body-pair order; option collision = all / predefined / dynamic selects the sources."""
+    m = capi.Model.from_xml_string(PAIRS.format(mode="all"))
+    gid = lambda n: m.name2id(capi.OBJ_GEOM, n)
+    assert m.npair == 2 and m.name2id(capi.OBJ_PAIR, "grip") == 0
+    cand = list(zip(m.collpair_geom1.tolist(), m.collpair_geom2.tolist(), m.collpair_pairid.tolist()))
+    # floor-ga only through its pair (ga has contype 0), floor-gb and floor-gc dynamic, gb-gc through its pair although
+    # the bodies are excluded; ga-gb / ga-gc filtered out by contype
+    assert (gid("floor"), gid("ga"), 0) in cand and (gid("floor"), gid("gb"), -1) in cand and (gid("floor"), gid("gc"), -1) in cand
+    assert (gid("gb"), gid("gc"), 1) in cand or (gid("gc"), gid("gb"), 1) in cand
+    assert len(cand) == 4
+    np.testing.assert_allclose(m.pair_friction[1], [1, 1, 0.005, 0.0001, 0.0001])   # filled from the geoms (max rule)
+    o = orc.Oracle(m)
+    o.forward()
+    n = int(o.get("ncon")[0])
+    g1, g2 = o.get("contact_geom1")[:n].tolist(), o.get("contact_geom2")[:n].tolist()
+    assert n == 3 and (gid("floor"), gid("ga")) in zip(g1, g2) and (gid("gc"), gid("gb")) in zip(g1, g2)  # pair order kept
+    k = list(zip(g1, g2)).index((gid("floor"), gid("ga")))
+    assert o.get("contact_dim")[k] == 4
+    np.testing.assert_allclose(o.get("contact_friction").reshape(-1, 5)[k], [2, 2, 0.1, 0.01, 0.01])
+    np.testing.assert_allclose(o.get("contact_solref").reshape(-1, 2)[k], [0.01, 1])
+    assert abs(o.get("contact_includemargin")[k] - 0.015) < 1e-15
+    k2 = list(zip(g1, g2)).index((gid("gc"), gid("gb")))
+    assert abs(o.get("contact_dist")[k2] + 0.01) < 1e-12 and o.get("contact_dim")[k2] == 3
+    for mode, want in (("predefined", 2), ("dynamic", 2)):
+        mm = capi.Model.from_xml_string(PAIRS.format(mode=mode))
+        assert mm.ncollpair == want, (mode, mm.ncollpair)
+        assert all((p >= 0) == (mode == "predefined") for p in mm.collpair_pairid)
+
+
+@pytest.mark.gpu
+def test_gpu_explicit_contact_pairs(capi, orc):
+    from mujoco_ros_pkgs_b200.batch import BatchSim
+
+    m = capi.Model.from_xml_string(PAIRS.format(mode="all"))
+    nenv = 4
+    sim = BatchSim(m, nenv)
+    sim.keep_intermediates(True)
+    rng = np.random.default_rng(0)
+    qpos = np.tile(m.qpos0, (nenv, 1))
+    qpos[:, [0, 7, 14]] += rng.uniform(-0.02, 0.02, (nenv, 3))
+    qvel = rng.uniform(-0.5, 0.5, (nenv, m.nv))
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = []
+    for e in range(nenv):
+        o = orc.Oracle(m)
+        o.set("qpos", qpos[e]); o.set("qvel", qvel[e])
+        oracles.append(o)
+    for s in range(120):
+        sim.step(1)
+        for o in oracles:
+            o.step(1)
+        if s % 20 == 19:
+            sim.forward()
+            for e, o in enumerate(oracles):
+                o.forward()
+                n = int(o.get("ncon")[0])
+                assert int(sim.get("ncon")[e, 0]) == n
+                for k in ("contact_geom1", "contact_geom2", "contact_dim"):
+                    np.testing.assert_array_equal(sim.get(k)[e][:n], o.get(k)[:n])
+                np.testing.assert_allclose(sim.get("contact_friction")[e][:5 * n], o.get("contact_friction")[:5 * n], rtol=0, atol=0)
+                np.testing.assert_allclose(sim.get("qpos")[e], o.get("qpos"), rtol=0, atol=1e-9)
