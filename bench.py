@@ -22,7 +22,7 @@ pre-roll a short run (--steps 20) would report that easy regime.  The reference 
                DFMA peak measured live on this GPU (b2mj_ubench_dfma) -- the roofline that can actually bind.
   parity       the gate reported with every number: 64-env subsample of the timed state, per-step
                state-injected comparison with the CPU oracle + free-running end state + contact-pair indices.
-  publish      (N > 1) the one exchange step of the path: per-step launches WITH the NCCL all-gather of
+  publish      (N > 1) the one exchange step of the path, two ways: per-step launches WITH the NCCL all-gather of
                qpos | qvel | sensordata every step, against the same steps without it.
   configs      the other BASELINE configs at their per-GPU batch (C3 hand through the robot_hw path, C4 humanoid +
                sensor readout (+ publish), C5 bin) and, for N > 1, C2 strong-scaled (4096 / N envs per GPU), each with
@@ -697,6 +697,43 @@ def main():
                    "gathered_equals_plain_all_gather": pub_ok, "gpu_launches": pb_launches,
                    "how": "leg A's K closed-loop steps, each followed by b2mj_allgather_publish_multi (one pack kernel + one "
                           "ncclAllGather over NVLink); CUDA events per step, max over ranks", "per_rank": per_rank_stats(C, pb_arr)}
+
+        # ---- the same exchange FUSED into the step kernel: every finished env's row is stored straight into every
+        #      rank's gathered slab over NVLink peer memory (b2mj_step_publish), a stream-ordered flag wait follows
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, sim.publish_fused_create(world, rank, fields))
+            sim.publish_fused_connect(handles)
+            dist.barrier()
+            fused_ptr = [0]
+
+            def fused_step(k):
+                if nu:
+                    sim.set_device("ctrl", tctrl[k].data_ptr(), nu)
+                sim.step_publish()
+                fused_ptr[0], _ = sim.publish_fused_wait()
+
+            pf_ms, pf_arr, pf_launches = time_per_step(C, sim, snap, W, K, fused_step)
+
+            class _Slab:
+                __cuda_array_interface__ = {"shape": (world, nenv, row), "typestr": "<f8", "data": (fused_ptr[0], False), "version": 3}
+
+            fused_slab = torch.as_tensor(_Slab(), device=dev).clone()
+            mine = torch.from_numpy(np.concatenate([sim.get(f) for f in fields], axis=1)).to(dev)
+            dist.all_gather_into_tensor(allv, mine)
+            fused_ok = bool(torch.equal(allv, fused_slab))
+            (pf_ms_max,) = reduce_max(C, pf_ms)
+            publish["fused"] = {"us_per_step": 1e3 * (pf_ms_max - ps_ms_max) / K,
+                                "overhead_pct": 100.0 * (pf_ms_max - ps_ms_max) / ps_ms_max,
+                                "with_publish_value": nenv * world * K / (pf_ms_max * 1e-3), "unit": UNIT,
+                                "gathered_equals_plain_all_gather": fused_ok, "gpu_launches": pf_launches,
+                                "how": "leg A's K closed-loop steps as b2mj_step_publish (the step kernel stores each finished "
+                                       "env's row into every rank's slab through CUDA-IPC peer pointers and its last env raises "
+                                       "the rank's flag in every peer) + b2mj_publish_fused_wait (stream-ordered spin on the "
+                                       "local flags); no NCCL call; "
+                                       "CUDA events per step, max over ranks", "per_rank": per_rank_stats(C, pf_arr)}
+        except Exception as ex:  # peer access unavailable on this box: report, keep the NCCL number
+            publish["fused"] = {"unavailable": str(ex)[:200]}
 
     clocks = sampler.stop()
     wall = time.perf_counter() - wall0

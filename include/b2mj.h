@@ -452,6 +452,25 @@ int b2mj_allgather_publish_multi(b2mj_handle* h, const b2mj_field* fields, int n
  * *count_per_env = sum of the field counts */
 int b2mj_publish_pack(b2mj_handle* h, const b2mj_field* fields, int nfields, double** dev_slab, int* count_per_env);
 
+/* ---- fused step + publish over NVLink peer memory (the all-gather folded into the step kernel) ----
+ * The reference publishes every env's state after the step (mujoco_env.cpp:593-595 lastStage callbacks ->
+ * mujoco_sensor_handler_plugin.cpp:175-437).  With one process per GPU the gathered slab [world][nenv][count] is what a
+ * device-side consumer of the aggregated state reads; b2mj_allgather_publish builds it with a pack kernel + ncclAllGather
+ * AFTER the step.  The fused form makes the step kernel itself the collective: when an env's step is done its warp
+ * stores the env's row straight into EVERY rank's slab through peer (CUDA-IPC mapped, NVLink) pointers, so the exchange
+ * rides under the launch instead of following it; the env whose row leaves last raises this rank's sequence flag in
+ * every peer (system-scope fences), and b2mj_publish_fused_wait is a stream-ordered spin on the local flags.  Slabs are double buffered by sequence
+ * parity: with every rank issuing step_publish -> wait -> (consumer) per step on one stream no slab is overwritten
+ * while a peer still reads it.  Fields must live in the state record (qpos, qvel, act, qacc, sensordata, time, ...).
+ *   create : allocates this rank's slabs + flags, returns their 64-byte CUDA IPC handle (exchange it out of band)
+ *   connect: all_handles = [world][64] bytes in rank order; opens the peers' memory
+ *   step_publish: one b2mj_step with the fused stores;  wait: returns the DEVICE pointer of the slab just completed */
+int b2mj_publish_fused_create(b2mj_handle* h, int world, int rank, const b2mj_field* fields, int nfields,
+                              unsigned char* ipc_handle_out /* [64] */);
+int b2mj_publish_fused_connect(b2mj_handle* h, const unsigned char* all_handles /* [world][64] */);
+int b2mj_step_publish(b2mj_handle* h);
+int b2mj_publish_fused_wait(b2mj_handle* h, double** dev_gathered, int* count_per_env);
+
 /* introspection for the benchmark / roofline */
 typedef struct b2mjLaunchInfo {
   int warps_per_cta;

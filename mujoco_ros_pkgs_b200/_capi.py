@@ -83,7 +83,8 @@ EXPORTS = [
     "b2mj_set_env_models", "b2mj_register_collision_function", "b2mj_reset_collision_functions",
     "b2mj_robot_hw_configure", "b2mj_robot_hw_write", "b2mj_robot_hw_read", "b2mj_robot_hw_state_ptrs", "b2mj_sensor_configure_noise",
     "b2mj_sensor_readout", "b2mj_sensor_readout_device", "b2mj_allgather_publish", "b2mj_allgather_publish_multi",
-    "b2mj_publish_pack", "b2mj_ubench_dfma", "b2mj_launch_info", "b2mj_stage_profile", "b2mj_stage_name", "b2mj_env_cycles", "b2mj_last_error", "b2mj_version",
+    "b2mj_publish_pack", "b2mj_publish_fused_create", "b2mj_publish_fused_connect", "b2mj_step_publish",
+    "b2mj_publish_fused_wait", "b2mj_ubench_dfma", "b2mj_launch_info", "b2mj_stage_profile", "b2mj_stage_name", "b2mj_env_cycles", "b2mj_last_error", "b2mj_version",
     "b2mj_device_count",
 ]
 

@@ -49,6 +49,10 @@ lib.b2mj_sensor_readout.argtypes = [_vp, _vp, _vp]
 lib.b2mj_allgather_publish.argtypes = [_vp, C.c_int, _vp, _vp]
 lib.b2mj_allgather_publish_multi.argtypes = [_vp, C.POINTER(C.c_int), C.c_int, _vp, _vp]
 lib.b2mj_publish_pack.argtypes = [_vp, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp), C.POINTER(C.c_int)]
+lib.b2mj_publish_fused_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _vp]
+lib.b2mj_publish_fused_connect.argtypes = [_vp, _vp]
+lib.b2mj_step_publish.argtypes = [_vp]
+lib.b2mj_publish_fused_wait.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int)]
 lib.b2mj_sensor_readout_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
 lib.b2mj_robot_hw_state_ptrs.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
 lib.b2mj_ubench_dfma.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -255,6 +259,28 @@ class BatchSim:
     def allgather_publish_multi(self, names, comm_ptr, dst_dev_ptr: int):
         ids, n = self.publish_fields(names)
         check(lib.b2mj_allgather_publish_multi(self._h, ids, n, comm_ptr, _vp(dst_dev_ptr)), "allgather_publish_multi")
+
+    def publish_fused_create(self, world: int, rank: int, names) -> bytes:
+        """Allocate this rank's gathered slabs for the fused step + publish; returns the 64-byte CUDA IPC handle."""
+        ids = (C.c_int * len(names))(*[_capi.field_id(n) for n in names])
+        out = (C.c_ubyte * 64)()
+        check(lib.b2mj_publish_fused_create(self._h, world, rank, ids, len(names), C.cast(out, _vp)), "publish_fused_create")
+        return bytes(out)
+
+    def publish_fused_connect(self, handles):
+        """handles: the IPC handles of all ranks in rank order (each 64 bytes)."""
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(lib.b2mj_publish_fused_connect(self._h, C.cast(buf, _vp)), "publish_fused_connect")
+
+    def step_publish(self):
+        check(lib.b2mj_step_publish(self._h), "step_publish")
+
+    def publish_fused_wait(self):
+        """Stream-ordered wait for every rank's row of the step just published: (device pointer, count per env)."""
+        ptr, cnt = _vp(), C.c_int()
+        check(lib.b2mj_publish_fused_wait(self._h, C.byref(ptr), C.byref(cnt)), "publish_fused_wait")
+        return ptr.value, cnt.value
 
     def publish_pack(self, names):
         ids, n = self.publish_fields(names)

@@ -674,6 +674,8 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
   static const bool reorder = !getenv("B2MJ_NO_REORDER");
   a.perm = (reorder && h->perm_valid && !a.sched) ? h->perm : nullptr;
   a.env_model = nullptr;
+  a.pub = h->launch_pub;
+  a.pub_seq = h->launch_pub_seq;
   int rc;
   if (h->n_env_models > 0) {  // per-env model variants: the kernel build that reads every model array per env
     a.env_model = h->env_model_idx;
@@ -766,6 +768,7 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->env_blob);
   cudaFree(h->env_model_idx);
   handle_free_plugins(h);
+  handle_free_fused_publish(h);
   b2mj_model_free(h->model);
   delete h;
 }

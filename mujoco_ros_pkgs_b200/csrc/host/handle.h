@@ -9,6 +9,7 @@
 namespace b2mj {
 
 struct RobotHWState;
+struct FusedPublish;
 struct SensorReadoutState;
 
 struct Handle {
@@ -58,6 +59,10 @@ struct Handle {
   double* publish_slab = nullptr;       // staging of b2mj_allgather_publish (per handle: device- and stream-local)
   size_t publish_slab_n = 0;
 
+  FusedPublish* fused_pub = nullptr;    // b2mj_publish_fused_*: peer slabs, flags, sequence
+  const b2k::PubArgs* launch_pub = nullptr;  // set for the duration of a b2mj_step_publish launch
+  int launch_pub_seq = 0;
+
   RobotHWState* robot_hw = nullptr;
   SensorReadoutState* sensor_ro = nullptr;
 };
@@ -65,6 +70,7 @@ struct Handle {
 int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq = nullptr, double* traj_qpos = nullptr,
                   double* traj_qvel = nullptr, double* traj_sensor = nullptr, int chunk = 0);
 void handle_free_plugins(Handle* h);
+void handle_free_fused_publish(Handle* h);
 void handle_reset_plugins(Handle* h, const uint8_t* env_mask);
 
 }  // namespace b2mj

@@ -718,3 +718,170 @@ int b2mj_allgather_publish(b2mj_handle* hh, b2mj_field f, void* nccl_comm, void*
 }
 
 }  // extern "C"
+
+// ---- fused step + publish over peer memory (include/b2mj.h) ----
+struct b2mj::FusedPublish {
+  int world = 0, rank = 0, count = 0;
+  b2k::PubArgs args{};           // host image; slab pointers rewritten per sequence parity
+  b2k::PubArgs* dev_args[2] = {nullptr, nullptr};
+  unsigned char* local = nullptr;                      // one allocation: slab[0] | slab[1] | flags
+  unsigned char* peer[B2K_PUB_MAX_RANKS] = {nullptr};  // base of every rank's allocation in this address space
+  bool opened[B2K_PUB_MAX_RANKS] = {false};
+  size_t slab_bytes = 0;
+  int seq = 0;
+  bool connected = false;
+  double* slab_of(int r, int parity) const { return reinterpret_cast<double*>(peer[r] + (size_t)parity * slab_bytes); }
+  int* flags_of(int r) const { return reinterpret_cast<int*>(peer[r] + 2 * slab_bytes); }
+};
+
+__global__ void publish_wait_kernel(const int* flags, int nranks, int seq) {
+  const int r = threadIdx.x;
+  if (r < nranks) {
+    const volatile int* f = flags + r;
+    while (*f < seq) __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+void b2mj::handle_free_fused_publish(Handle* h) {
+  FusedPublish* p = h->fused_pub;
+  if (!p) return;
+  for (int r = 0; r < p->world; r++)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->peer[r]);
+  cudaFree(p->local);
+  cudaFree(p->dev_args[0]);
+  cudaFree(p->dev_args[1]);
+  delete p;
+  h->fused_pub = nullptr;
+}
+
+extern "C" {
+
+int b2mj_publish_fused_create(b2mj_handle* hh, int world, int rank, const b2mj_field* fields, int nfields,
+                              unsigned char* ipc_handle_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || world < 1 || world > B2K_PUB_MAX_RANKS || rank < 0 || rank >= world || !fields || nfields < 1 ||
+      nfields > B2K_PUB_MAX_FIELDS || !ipc_handle_out) {
+    set_error("b2mj_publish_fused_create: bad argument (world <= " + std::to_string(B2K_PUB_MAX_RANKS) + ", 1.." +
+              std::to_string(B2K_PUB_MAX_FIELDS) + " fields)");
+    return B2MJ_EINVAL;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  handle_free_fused_publish(h);
+  FusedPublish* p = new FusedPublish();
+  p->world = world;
+  p->rank = rank;
+  const b2k::DevModel& d = h->dm;
+  int count = 0;
+  p->args.nfields = 0;
+  for (int i = 0; i < nfields; i++) {
+    int off = -1;
+    switch (fields[i]) {
+      case B2MJ_F_CTRL: off = d.rec_ctrl; break;
+      case B2MJ_F_QFRC_APPLIED: off = d.rec_qfrc_applied; break;
+      case B2MJ_F_QPOS: off = d.rec_qpos; break;
+      case B2MJ_F_QVEL: off = d.rec_qvel; break;
+      case B2MJ_F_ACT: off = d.rec_act; break;
+      case B2MJ_F_QACC_WARMSTART: off = d.rec_warm; break;
+      case B2MJ_F_TIME: off = d.rec_time; break;
+      case B2MJ_F_QACC: off = d.rec_qacc; break;
+      case B2MJ_F_SENSORDATA: off = d.rec_sensordata; break;
+      case B2MJ_F_ACT_DOT: off = d.rec_act_dot; break;
+      default: break;
+    }
+    if (off < 0) {
+      delete p;
+      set_error("b2mj_publish_fused_create: only fields of the state record can be published from inside the step kernel");
+      return B2MJ_EINVAL;
+    }
+    const int n = d.fsize[fields[i]];
+    if (n == 0) continue;
+    p->args.foff[p->args.nfields] = off;
+    p->args.fcnt[p->args.nfields] = n;
+    p->args.nfields++;
+    count += n;
+  }
+  if (count == 0) { delete p; set_error("b2mj_publish_fused_create: nothing to publish"); return B2MJ_EINVAL; }
+  p->count = count;
+  p->args.nranks = world;
+  p->args.rank = rank;
+  p->args.count = count;
+  p->slab_bytes = (((size_t)world * h->nenv * count * sizeof(double)) + 255) & ~(size_t)255;
+  const size_t total = 2 * p->slab_bytes + 256;
+  if (cudaMalloc(&p->local, total) != cudaSuccess) { delete p; set_error("b2mj_publish_fused_create: out of device memory"); return B2MJ_ECUDA; }
+  cudaMemset(p->local, 0, total);
+  cudaMalloc(&p->dev_args[0], sizeof(b2k::PubArgs));
+  cudaMalloc(&p->dev_args[1], sizeof(b2k::PubArgs));
+  cudaIpcMemHandle_t hd;
+  if (cudaIpcGetMemHandle(&hd, p->local) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(p->local); cudaFree(p->dev_args[0]); cudaFree(p->dev_args[1]);
+    delete p;
+    set_error("b2mj_publish_fused_create: cudaIpcGetMemHandle failed");
+    return B2MJ_ECUDA;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::memcpy(ipc_handle_out, &hd, 64);
+  p->peer[rank] = p->local;
+  h->fused_pub = p;
+  return 0;
+}
+
+int b2mj_publish_fused_connect(b2mj_handle* hh, const unsigned char* all_handles) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !h->fused_pub || !all_handles) { set_error("b2mj_publish_fused_connect: create first"); return B2MJ_EINVAL; }
+  FusedPublish* p = h->fused_pub;
+  CUDA_OK(cudaSetDevice(h->device));
+  for (int r = 0; r < p->world; r++) {
+    if (r == p->rank) continue;
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, all_handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    const cudaError_t err = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      set_error(std::string("b2mj_publish_fused_connect: cannot open the slab of rank ") + std::to_string(r) + ": " +
+                cudaGetErrorString(err));
+      return B2MJ_ECUDA;
+    }
+    p->peer[r] = static_cast<unsigned char*>(ptr);
+    p->opened[r] = true;
+  }
+  for (int par = 0; par < 2; par++) {
+    b2k::PubArgs a = p->args;
+    for (int r = 0; r < p->world; r++) { a.slab[r] = p->slab_of(r, par); a.flags[r] = p->flags_of(r); }
+    a.done = reinterpret_cast<unsigned*>(p->local + 2 * p->slab_bytes + 128);
+    CUDA_OK(cudaMemcpy(p->dev_args[par], &a, sizeof(a), cudaMemcpyHostToDevice));
+  }
+  p->connected = true;
+  return 0;
+}
+
+int b2mj_step_publish(b2mj_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !h->fused_pub || !h->fused_pub->connected) { set_error("b2mj_step_publish: create + connect first"); return B2MJ_EINVAL; }
+  FusedPublish* p = h->fused_pub;
+  CUDA_OK(cudaSetDevice(h->device));
+  p->seq++;
+  h->in_split_step = 0;
+  h->launch_pub = p->dev_args[p->seq & 1];
+  h->launch_pub_seq = p->seq;
+  const int rc = handle_launch(h, b2k::MODE_STEP, 1);
+  h->launch_pub = nullptr;
+  return rc;
+}
+
+int b2mj_publish_fused_wait(b2mj_handle* hh, double** dev_gathered, int* count_per_env) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !h->fused_pub || !h->fused_pub->connected) { set_error("b2mj_publish_fused_wait: create + connect first"); return B2MJ_EINVAL; }
+  FusedPublish* p = h->fused_pub;
+  CUDA_OK(cudaSetDevice(h->device));
+  publish_wait_kernel<<<1, 32, 0, h->stream>>>(p->flags_of(p->rank), p->world, p->seq);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  if (dev_gathered) *dev_gathered = p->slab_of(p->rank, p->seq & 1);
+  if (count_per_env) *count_per_env = p->count;
+  return 0;
+}
+
+}  // extern "C"

@@ -156,6 +156,17 @@ struct DevModel {
   int ldh;                 // leading dimension of the Newton Hessian (odd in team mode: conflict-free column walks)
 };
 
+// fused publish (b2mj_step_publish): where the finished env's row goes in every rank's gathered slab
+#define B2K_PUB_MAX_RANKS 16
+#define B2K_PUB_MAX_FIELDS 8
+struct PubArgs {
+  int nranks, rank, count, nfields;
+  int foff[B2K_PUB_MAX_FIELDS], fcnt[B2K_PUB_MAX_FIELDS];  // record offsets / lengths of the published fields
+  double* slab[B2K_PUB_MAX_RANKS];                          // [world][nenv][count] in rank r's memory (peer mapped)
+  int* flags[B2K_PUB_MAX_RANKS];                            // [world] sequence flags in rank r's memory (peer mapped)
+  unsigned* done;                                           // local counter of envs whose rows are out (self-resetting)
+};
+
 struct LaunchArgs {
   double* rec;             // [nenv][rec_pitch]
   double* garena_d;        // [nenv][arena_g_doubles]
@@ -182,6 +193,8 @@ struct LaunchArgs {
   int sync_stages;         // CTA-wide lockstep at stage boundaries (instruction / constant cache locality)
   const int* perm;         // [nenv] launch slot -> env, heaviest envs first (b2k_order_kernel), or null = identity
   const int* env_model;    // [nenv] model variant of each env (per-env-model build only), or null
+  const PubArgs* pub;      // fused publish targets (device memory), or null
+  int pub_seq;             // sequence number this launch raises in every rank's flag array once all rows are out
   unsigned long long* prof; // [PROF_COUNT] per-stage SM-cycle totals over all envs, or null (b2mj_stage_profile)
 };
 

@@ -407,6 +407,31 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
       const double* ctrl = e.D(B2MJ_F_CTRL);
       FORL(i, m.nu) rec[m.rec_ctrl + i] = ctrl[i];
     }
+    // fused publish: this env's row into every rank's gathered slab, straight from the record image in shared memory
+    // (peer stores over NVLink; they overlap the rest of the launch, whose length the slowest env sets)
+    if (a.pub) {
+      const PubArgs& p = *a.pub;
+      B2K_NOUNROLL for (int r = 0; r < p.nranks; r++) {
+        double* dst = p.slab[r] + ((size_t)p.rank * a.nenv + env) * p.count;
+        B2K_NOUNROLL for (int f = 0; f < p.nfields; f++) {
+          const double* src = sd + p.foff[f];
+          FORL(i, p.fcnt[f]) dst[i] = src[i];
+          dst += p.fcnt[f];
+        }
+      }
+      // the env whose rows leave last raises this rank's sequence flag in every peer: the launch IS the collective,
+      // no second kernel.  Every lane fences its own peer stores at system scope before the warp's arrival is counted.
+      __threadfence_system();
+      WSYNC();
+      if (lane == 0) {
+        const unsigned prev = atomicAdd(p.done, 1u);
+        if (prev == (unsigned)a.nenv - 1u) {
+          *p.done = 0;
+          __threadfence_system();
+          B2K_NOUNROLL for (int r = 0; r < p.nranks; r++) *reinterpret_cast<volatile int*>(p.flags[r] + p.rank) = a.pub_seq;
+        }
+      }
+    }
     // ---- results: counters, state record SMEM -> HBM (segments B+C contiguous), optional arena dump ----
     if (lane == 0) {
       int* st = a.stats + (size_t)env * 4;
