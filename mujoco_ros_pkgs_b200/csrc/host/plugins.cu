@@ -729,16 +729,22 @@ struct b2mj::FusedPublish {
   bool opened[B2K_PUB_MAX_RANKS] = {false};
   size_t slab_bytes = 0;
   int seq = 0;
-  bool connected = false;
+  bool connected = false, waits_issued = false;
+  int* timed_out = nullptr;  // mapped host memory, set by the wait kernel when a peer never shows up
   double* slab_of(int r, int parity) const { return reinterpret_cast<double*>(peer[r] + (size_t)parity * slab_bytes); }
   int* flags_of(int r) const { return reinterpret_cast<int*>(peer[r] + 2 * slab_bytes); }
 };
 
-__global__ void publish_wait_kernel(const int* flags, int nranks, int seq) {
+__global__ void publish_wait_kernel(const int* flags, int nranks, int seq, long long timeout_cycles, int* timed_out) {
   const int r = threadIdx.x;
   if (r < nranks) {
     const volatile int* f = flags + r;
-    while (*f < seq) __nanosleep(200);
+    const long long t0 = clock64();
+    while (*f < seq) {
+      __nanosleep(200);
+      // a peer that died must not hang this GPU: give up after the timeout and let the caller see it
+      if (clock64() - t0 > timeout_cycles) { if (timed_out) *reinterpret_cast<volatile int*>(timed_out) = 1; break; }
+    }
   }
   __threadfence_system();
 }
@@ -749,6 +755,7 @@ void b2mj::handle_free_fused_publish(Handle* h) {
   for (int r = 0; r < p->world; r++)
     if (p->opened[r]) cudaIpcCloseMemHandle(p->peer[r]);
   cudaFree(p->local);
+  if (p->timed_out) cudaFreeHost(p->timed_out);
   cudaFree(p->dev_args[0]);
   cudaFree(p->dev_args[1]);
   delete p;
@@ -810,6 +817,8 @@ int b2mj_publish_fused_create(b2mj_handle* hh, int world, int rank, const b2mj_f
   const size_t total = 2 * p->slab_bytes + 256;
   if (cudaMalloc(&p->local, total) != cudaSuccess) { delete p; set_error("b2mj_publish_fused_create: out of device memory"); return B2MJ_ECUDA; }
   cudaMemset(p->local, 0, total);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&p->timed_out), sizeof(int), cudaHostAllocMapped) == cudaSuccess) *p->timed_out = 0;
+  else { cudaGetLastError(); p->timed_out = nullptr; }
   cudaMalloc(&p->dev_args[0], sizeof(b2k::PubArgs));
   cudaMalloc(&p->dev_args[1], sizeof(b2k::PubArgs));
   cudaIpcMemHandle_t hd;
@@ -876,7 +885,13 @@ int b2mj_publish_fused_wait(b2mj_handle* hh, double** dev_gathered, int* count_p
   if (!h || !h->fused_pub || !h->fused_pub->connected) { set_error("b2mj_publish_fused_wait: create + connect first"); return B2MJ_EINVAL; }
   FusedPublish* p = h->fused_pub;
   CUDA_OK(cudaSetDevice(h->device));
-  publish_wait_kernel<<<1, 32, 0, h->stream>>>(p->flags_of(p->rank), p->world, p->seq);
+  // the timeout marker lives in mapped host memory: the host reads it without synchronising the stream
+  if (p->timed_out && *reinterpret_cast<volatile int*>(p->timed_out)) {
+    set_error("b2mj_publish_fused_wait: a peer did not publish within the timeout (its process died or never stepped)");
+    return B2MJ_ECUDA;
+  }
+  publish_wait_kernel<<<1, 32, 0, h->stream>>>(p->flags_of(p->rank), p->world, p->seq, /* ~5 s */ 10000000000LL, p->timed_out);
+  p->waits_issued = true;
   CUDA_OK(cudaGetLastError());
   h->launches++;
   if (dev_gathered) *dev_gathered = p->slab_of(p->rank, p->seq & 1);
