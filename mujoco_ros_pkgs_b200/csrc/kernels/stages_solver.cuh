@@ -799,9 +799,10 @@ __device__ __noinline__ void cholFactor_warp(const Env e, int n, int ld, double 
 // Written block-wise -- the outer loop over the 32-entry blocks is unrolled so that every register slot is named
 // statically; the round-1 form indexed the slots through run-time predicates, which put the vector in LOCAL memory
 // with eight branches per step (800 cycles per substitution step, 194 k cycles per solve at nv = 120, ~38 k at nv = 24).
-#define B2K_CHOL_SLOTS (B2K_NEWTON_MAX_NV / 32)
-template <bool SM>
-__device__ __noinline__ void cholSolve_warp(const Env e, int n, int ld) {
+#define B2K_CHOL_SLOTS_MAX (B2K_NEWTON_MAX_NV / 32)
+// B2K_CHOL_SLOTS = register slots per lane: 1 serves n <= 32 without the predicated-off updates of the wider form
+template <bool SM, int B2K_CHOL_SLOTS>
+__device__ __noinline__ void cholSolve_warpT(const Env e, int n, int ld) {
   // Mgrad = inv(H) grad on the solver's work vectors (XF_PRIMAL: Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
   const double* L = newtonH<SM>(e);
   double* wv = e.X(XF_PRIMAL);
@@ -926,6 +927,17 @@ __device__ __forceinline__ void hessianJTDJ_reg(const Env e, const PrimalCtx& c,
       } else if (st == B2MJ_CSTATE_CONE) {
         const int con = P.id[r], dim = c_dim[con];
         const double* Hc = cH + 36 * con;
+        // B = Hc J_block (dim x nv) once per cone, by the whole warp; an entry then needs dim products instead of
+        // dim^2.  B(a, j) is formed with the loop order the entry-wise form used, so the sums are bitwise the same.
+        double* Bm = e.X(XF_SCRATCH);  // dim * nv <= 6 nv doubles; free during the dense Newton solve
+        WSYNC();
+        B2K_NOUNROLL for (int t = e.lane; t < dim * nv; t += B2K_G) {
+          const int a = t / nv, j = t - a * nv;
+          double u = 0;
+          B2K_NOUNROLL for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + j];
+          Bm[t] = u;
+        }
+        WSYNC();
 #pragma unroll
         for (int k = 0; k < NI; k++) {
           double sk = s[k];
@@ -933,9 +945,7 @@ __device__ __forceinline__ void hessianJTDJ_reg(const Env e, const PrimalCtx& c,
           B2K_NOUNROLL for (int a = 0; a < dim; a++) {
             const double Ja = P.J[(r + a) * nv + oi];
             if (Ja == 0) continue;
-            double u = 0;
-            B2K_NOUNROLL for (int b = 0; b < dim; b++) u += Hc[a * dim + b] * P.J[(r + b) * nv + oj];
-            sk += Ja * u;
+            sk += Ja * Bm[a * nv + oj];
           }
           s[k] = sk;
         }
@@ -1037,8 +1047,13 @@ __device__ void primalGradient(const Env e, PrimalCtx& c) {
   FORL(i, c.nv) c.grad[i] = c.Ma[i] - qs[i] - qc[i];
   WSYNC();
   if (c.newton) {
-    if (c_dm.xoff_s[XF_NEWTON_H] >= 0) cholSolve_warp<true>(e, c.nv, c_dm.ldh);
-    else cholSolve_warp<false>(e, c.nv, c_dm.ldh);
+    if (c_dm.xoff_s[XF_NEWTON_H] >= 0) {
+      if (c.nv <= 32) cholSolve_warpT<true, 1>(e, c.nv, c_dm.ldh);
+      else cholSolve_warpT<true, B2K_CHOL_SLOTS_MAX>(e, c.nv, c_dm.ldh);
+    } else {
+      if (c.nv <= 32) cholSolve_warpT<false, 1>(e, c.nv, c_dm.ldh);
+      else cholSolve_warpT<false, B2K_CHOL_SLOTS_MAX>(e, c.nv, c_dm.ldh);
+    }
   } else {
     solveM_warp(e, c.Mgrad, c.grad);
   }
