@@ -574,6 +574,7 @@ static int make_layout(Handle* h) {
     return B2MJ_EUNSUPPORTED;
   }
   h->warps_per_cta = bestW;
+  h->resident_envs = bestEnv * sms;
   h->smem_bytes = (size_t)bestW * (env_bytes + (d.team_warps > 1 ? 64 : 16));
   // Rollout shape: half of an SM's resident envs per CTA, stages lock-stepped with a CTA barrier.  Warps that
   // run the same stage together share instruction fetches -- the fused rollout is fetch bound (ncu: 12.7
@@ -689,11 +690,16 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
     return B2MJ_ECUDA;
   }
   h->launches++;
-  // heaviest-first launch order for the next launch, from the solver work this one recorded (only worth a kernel
-  // when the batch spans more than one wave)
-  if (reorder && mode != MODE_FORWARD && mode != MODE_STEP_BEGIN && h->nenv >= 1024) {
+  // heaviest-first launch order for the next launch, from the cost this one recorded per env (only worth a kernel
+  // when the batch spans more than one wave: C5 has 512 envs and 148 slots)
+  // (after a multi-step rollout the residency is a sum over steps and the lock-stepped rollout CTAs do better with
+  // heavy and light envs mixed: the coarse rows x iterations classes of the last step stay in use there, measured
+  // 13.2 M against 12.9 M env-steps/s on the C2 rollout)
+  static const int order_legacy = getenv("B2MJ_ORDER_LEGACY") ? 1 : 0;
+  if (reorder && mode != MODE_FORWARD && mode != MODE_STEP_BEGIN &&
+      (order_legacy ? h->nenv >= 1024 : h->nenv > std::max(h->resident_envs, 32))) {
     if (!h->perm) CUDA_OK(cudaMalloc(&h->perm, (size_t)h->nenv * sizeof(int)));
-    const int orc = b2k_launch_order(h->stats, h->nenv, h->perm, h->stream);
+    const int orc = b2k_launch_order(h->stats, h->nenv, h->perm, (order_legacy || nsteps > 1) ? 1 : 0, h->stream);
     if (orc != 0) {
       set_error(std::string("order kernel launch failed: ") + cudaGetErrorString((cudaError_t)orc));
       return B2MJ_ECUDA;

@@ -39,6 +39,7 @@ struct Handle {
   unsigned long long* prof = nullptr;  // [PROF_COUNT] stage cycle totals (b2mj_stage_profile), null = off
 
   int warps_per_cta = 4;
+  int resident_envs = 0;          // envs the whole GPU keeps resident at the step launch shape (make_layout)
   int rollout_warps_per_cta = 0;  // CTA shape of the static fused rollout (lock-stepped stages), 0 = same as steps
   size_t smem_bytes = 0;
   size_t smem_target_bytes = 0;   // 0 = default policy

@@ -909,13 +909,11 @@ __device__ __forceinline__ void hessianJTDJ_reg(const Env e, const PrimalCtx& c,
 #pragma unroll
     for (int k = 0; k < NI; k++) {
       const int idx = base + e.lane + 32 * k;
-      int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-      while (i * (i + 1) / 2 > idx) i--;
-      while ((i + 1) * (i + 2) / 2 <= idx) i++;
-      const int j = idx - i * (i + 1) / 2;
       const bool ok = idx < ntri;
-      ij[k] = ok ? (unsigned)i | ((unsigned)j << 8) : 0u;
-      s[k] = ok ? H[i * ld + j] : 0.0;
+      // (i, j) of entry idx from the pair table the Cholesky uses (a square root and two search loops per entry
+      // here were 3.9 % of a C4 step, profiles/r2b_ncu_lines_c4.txt)
+      ij[k] = ok ? (unsigned)c.tri[idx] : 0u;
+      s[k] = ok ? H[(ij[k] & 255u) * ld + (ij[k] >> 8)] : 0.0;
     }
     B2K_NOUNROLL for (int r = 0; r < nefc; r++) {
       const int st = P.state[r];

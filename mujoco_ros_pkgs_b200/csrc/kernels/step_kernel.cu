@@ -533,21 +533,38 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
 }
 
 #ifndef B2K_PER_ENV_MODEL  /* launch order, attributes and occupancy are shared with the main build */
-// Launch order for the next launch: envs sorted into weight classes by the solver work of their last step
-// (constraint rows x iterations), heaviest first.  A launch ends when its slowest env does; an env with 21 rows at the
-// 100-iteration PGS cap takes 4x the median step, and if it starts in the second wave its whole run is added to the
-// launch.  Contact states persist from step to step, so last step's work predicts this step's.  One CTA.
-#define B2K_ORDER_CLASSES 4
-// Stable counting sort (deterministic launch order: within a class envs keep their index order).
-__global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* __restrict__ perm) {
-  __shared__ int count[B2K_ORDER_CLASSES], cursor[B2K_ORDER_CLASSES];
+// Launch order for the next launch: envs sorted heaviest first by what their LAST step cost.  A launch ends when its
+// slowest env does; an env with 21 rows at the 100-iteration PGS cap takes 4x the median step, and if it starts in the
+// second wave its whole run is added to the launch.  Contact states persist from step to step, so last step's cost
+// predicts this step's.  Weight = the env's measured residency of the last launch (stats[3], 1024-cycle units): it
+// ranks PGS, CG and Newton envs, collision-heavy envs and RK4 sub-steps alike (round 2 used rows x iterations in four
+// fixed classes tuned on the PGS config; every env of the Newton configs fell into the two lightest classes, so their
+// launches ran 40-55 % over the balanced bound).  64 linear classes up to the launch's maximum; one CTA.
+// Stable counting sort: within a class envs keep their index order.  The order never changes results
+// (tests/test_gpu_paths.py::test_launch_order_does_not_change_results).
+#define B2K_ORDER_CLASSES 64
+__global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* __restrict__ perm, int legacy) {
+  __shared__ int count[B2K_ORDER_CLASSES], cursor[B2K_ORDER_CLASSES], wmax;
   __shared__ int wtot[32][B2K_ORDER_CLASSES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x < B2K_ORDER_CLASSES) count[threadIdx.x] = 0;
+  if (threadIdx.x == 0) wmax = 0;
   __syncthreads();
+  if (!legacy) {
+    int mx = 0;
+    for (int e = threadIdx.x; e < nenv; e += blockDim.x) mx = max(mx, stats[4 * e + 3]);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) atomicMax(&wmax, mx);
+    __syncthreads();
+  }
+  const long long span = (long long)wmax + 1;
   auto cls = [&](int e) {
-    const int w = stats[4 * e + 1] * stats[4 * e + 2];
-    return w >= 1200 ? 0 : w >= 400 ? 1 : w >= 100 ? 2 : 3;
+    if (legacy) {  // rows x iterations in the four round-2 classes (B2MJ_ORDER_LEGACY=1, kept for A/B runs)
+      const int w = stats[4 * e + 1] * stats[4 * e + 2];
+      return w >= 1200 ? 0 : w >= 400 ? 1 : w >= 100 ? 2 : 3;
+    }
+    const int k = (int)(((long long)max(stats[4 * e + 3], 0) * B2K_ORDER_CLASSES) / span);
+    return B2K_ORDER_CLASSES - 1 - min(k, B2K_ORDER_CLASSES - 1);
   };
   for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&count[cls(e)], 1);  // integer totals: order-free
   __syncthreads();
@@ -559,13 +576,12 @@ __global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* _
   for (int base = 0; base < nenv; base += blockDim.x) {
     const int e = base + threadIdx.x;
     const int c = e < nenv ? cls(e) : -1;
-    int rank = 0;
-#pragma unroll
-    for (int k = 0; k < B2K_ORDER_CLASSES; k++) {
-      const unsigned b = __ballot_sync(0xffffffffu, c == k);
-      if (c == k) rank = __popc(b & ((1u << lane) - 1u));
-      if (lane == 0) wtot[warp][k] = __popc(b);
-    }
+    for (int k = lane; k < B2K_ORDER_CLASSES; k += 32) wtot[warp][k] = 0;
+    __syncwarp();
+    // lanes of the warp that share a class: rank inside the group in lane (= env index) order
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (c >= 0 && rank == 0) wtot[warp][c] = __popc(peers);
     __syncthreads();
     if (c >= 0) {
       int off = cursor[c];
@@ -582,8 +598,8 @@ __global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* _
   }
 }
 
-extern "C" int b2k_launch_order(const int* stats, int nenv, int* perm, cudaStream_t stream) {
-  b2k_order_kernel<<<1, 1024, 0, stream>>>(stats, nenv, perm);
+extern "C" int b2k_launch_order(const int* stats, int nenv, int* perm, int legacy, cudaStream_t stream) {
+  b2k_order_kernel<<<1, 1024, 0, stream>>>(stats, nenv, perm, legacy);
   return (int)cudaGetLastError();
 }
 
