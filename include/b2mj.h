@@ -141,7 +141,7 @@ typedef struct b2mjStatistic {
   X(nq) X(nv) X(nu) X(na) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(nwrap) X(neq)          \
   X(nsensor) X(nsensordata) X(nM) X(nmocap) X(nexclude) X(ncollpair) X(nconmax) X(njmax)          \
   X(nnames) X(nlevel) X(ntree)                                                                    \
-  X(npair) X(nmesh) X(nmeshvert)                                                                           \
+  X(npair) X(nmesh) X(nmeshvert) X(nhfield) X(nhfielddata)                                                 \
   X(nkey) X(nkeyq) X(nkeyv) X(nkeya) X(nkeyu) X(nkeymp) X(nkeymq) /* keyframes; nkeyq = nkey*nq, ... (flat arrays) */
 
 /* X(ctype, name, rows(size field), cols) */
@@ -175,6 +175,10 @@ typedef struct b2mjStatistic {
   X(int, geom_dataid, ngeom, 1) /* mesh id of a mesh geom, else -1 */                             \
   X(int, mesh_vertadr, nmesh, 1) X(int, mesh_vertnum, nmesh, 1)                                   \
   X(double, mesh_vert, nmeshvert, 3) /* convex-hull vertices, mesh frame = centre of mass + principal axes */ \
+  /* height fields: geom_dataid of an hfield geom is the hfield id; size = (x radius, y radius, elevation, base); */ \
+  /* data row-major [nrow][ncol], normalised to [0, 1], (0, 0) at the (-x, -y) corner (mjModel.hfield_*) */         \
+  X(int, hfield_nrow, nhfield, 1) X(int, hfield_ncol, nhfield, 1) X(int, hfield_adr, nhfield, 1)  \
+  X(double, hfield_size, nhfield, 4) X(double, hfield_data, nhfielddata, 1)                       \
   X(int, site_bodyid, nsite, 1) X(int, site_type, nsite, 1) X(double, site_size, nsite, 3)        \
   X(double, site_pos, nsite, 3) X(double, site_quat, nsite, 4)                                    \
   X(int, tendon_adr, ntendon, 1) X(int, tendon_num, ntendon, 1) X(int, tendon_limited, ntendon, 1)\

@@ -236,8 +236,8 @@ static int upload_model(Handle* h) {
 static int check_supported(const b2mjModel* m) {
   for (int p = 0; p < m->ncollpair; p++) {
     const int t1 = m->geom_type[m->collpair_geom1[p]], t2 = m->geom_type[m->collpair_geom2[p]];
-    if (t1 == B2MJ_GEOM_HFIELD || t2 == B2MJ_GEOM_HFIELD) {
-      set_error("collision with height fields is not implemented in the CUDA narrowphase");
+    if (t2 == B2MJ_GEOM_HFIELD || (t1 == B2MJ_GEOM_HFIELD && m->geom_dataid[m->collpair_geom1[p]] < 0)) {
+      set_error("height field pair without a narrowphase function (plane-hfield, hfield-hfield, or an hfield geom without data)");
       return B2MJ_EUNSUPPORTED;
     }
   }

@@ -4,7 +4,7 @@
 namespace b2k {
 
 #define B2K_MAXPAIRCON 8
-#define B2K_MAXPAIRFRAME 4
+#define B2K_MAXPAIRFRAME 8  /* height-field pairs: every contact has its own normal */
 
 struct PairCon {
   double dist[B2K_MAXPAIRCON];

@@ -391,6 +391,10 @@ __device__ __noinline__ int narrowphase(const double* gxpos, const double* gxmat
     }
   }
   if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) return c_boxBox(o, margin, pos1, mat1, size1, pos2, mat2, size2);
+  if (t1 == B2MJ_GEOM_HFIELD) {
+    if (t2 < B2MJ_GEOM_SPHERE || t2 > B2MJ_GEOM_MESH || m.geom_dataid[g1] < 0) return 0;
+    return c_hfieldConvex(o, margin, pos1, mat1, m.geom_dataid[g1], cvxGeom(gxpos, gxmat, g2), m.geom_rbound[g2]);
+  }
   // every other pair of convex geoms (anything with an ellipsoid, a cylinder or a mesh): the general MPR test
   if (t1 >= B2MJ_GEOM_SPHERE && t1 <= B2MJ_GEOM_MESH && t2 >= B2MJ_GEOM_SPHERE && t2 <= B2MJ_GEOM_MESH)
     return c_convexConvex(o, margin, cvxGeom(gxpos, gxmat, g1), cvxGeom(gxpos, gxmat, g2));

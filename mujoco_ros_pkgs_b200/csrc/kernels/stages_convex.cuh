@@ -246,7 +246,7 @@ __device__ __noinline__ void mprFindPos(const MprSupp* p, double* pos) {
 }
 
 // one contact from the penetration query of the two geoms inflated by margin / 2 each (mjc_Convex)
-__device__ __noinline__ int c_convexConvex(PairCon& o, double margin, const CvxGeom& ga, const CvxGeom& gb) {
+__device__ __noinline__ int c_convexConvexAt(PairCon& o, int n, double margin, const CvxGeom& ga, const CvxGeom& gb) {
   const DevModel& m = c_dm;
   const double inflate = 0.5 * margin, tol = m.opt.mpr_tolerance;
   const int maxit = m.opt.mpr_iterations;
@@ -337,11 +337,102 @@ __device__ __noinline__ int c_convexConvex(PairCon& o, double margin, const CvxG
     }
   }
   if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) return 0;
-  o.dist[0] = margin - depth;
-  copy3(o.frame, dir);
-  zero3(o.frame + 3);
-  copy3(o.pos, pos);
+  o.dist[n] = margin - depth;
+  copy3(o.frame + 6 * n, dir);
+  zero3(o.frame + 6 * n + 3);
+  copy3(o.pos + 3 * n, pos);
   return 1;
+}
+__device__ __forceinline__ int c_convexConvex(PairCon& o, double margin, const CvxGeom& ga, const CvxGeom& gb) {
+  return c_convexConvexAt(o, 0, margin, ga, gb);
+}
+
+// height field (geom 1) vs convex geom (mjc_ConvexHField): the geom's bounding box in the hfield frame selects a
+// sub-grid; every grid triangle under it, extruded down to -base, is a six-vertex prism tested with the MPR query -- one
+// contact per penetrating prism, up to the B2K_MAXPAIRCON a lane holds (MuJoCo: mjMAXCONPAIR = 50).  The prism is handed
+// to the support mapping as a six-vertex hull around its own centroid (the MPR's interior point).  All prisms of a pair
+// are walked by the lane that owns the pair.
+__device__ __noinline__ int c_hfieldConvex(PairCon& o, double margin, const double* pos1, const double* mat1, int hid,
+                                           const CvxGeom& gb, double rbound2) {
+  const DevModel& m = c_dm;
+  const double* hsize = m.hfield_size + 4 * hid;
+  const int nrow = m.hfield_nrow[hid], ncol = m.hfield_ncol[hid];
+  const double* data = m.hfield_data + m.hfield_adr[hid];
+  double dif[3], pos[3];
+  sub3(dif, gb.pos, pos1);
+  rotVecMatT(pos, dif, mat1);
+  const double r2 = rbound2 + margin;
+  if (pos[0] > hsize[0] + r2 || pos[0] < -hsize[0] - r2 || pos[1] > hsize[1] + r2 || pos[1] < -hsize[1] - r2 ||
+      pos[2] > hsize[2] + r2 || pos[2] < -hsize[3] - r2)
+    return 0;
+  double xmin[3], xmax[3];
+  B2K_NOUNROLL for (int i = 0; i < 3; i++) {
+    double dirw[3], sp[3], loc[3];
+    const double ax[3] = {mat1[i], mat1[3 + i], mat1[6 + i]};
+    copy3(dirw, ax);
+    cvxSupport(gb, dirw, sp);
+    sub3(dif, sp, pos1);
+    rotVecMatT(loc, dif, mat1);
+    xmax[i] = loc[i] + margin;
+    scl3(dirw, ax, -1.0);
+    cvxSupport(gb, dirw, sp);
+    sub3(dif, sp, pos1);
+    rotVecMatT(loc, dif, mat1);
+    xmin[i] = loc[i] - margin;
+  }
+  if (xmin[0] > hsize[0] || xmax[0] < -hsize[0] || xmin[1] > hsize[1] || xmax[1] < -hsize[1] || xmin[2] > hsize[2] ||
+      xmax[2] < -hsize[3])
+    return 0;
+  int cmin = (int)floor((xmin[0] + hsize[0]) / (2 * hsize[0]) * (ncol - 1));
+  int cmax = (int)ceil((xmax[0] + hsize[0]) / (2 * hsize[0]) * (ncol - 1));
+  int rmin = (int)floor((xmin[1] + hsize[1]) / (2 * hsize[1]) * (nrow - 1));
+  int rmax = (int)ceil((xmax[1] + hsize[1]) / (2 * hsize[1]) * (nrow - 1));
+  cmin = max(cmin, 0);
+  rmin = max(rmin, 0);
+  cmax = min(cmax, ncol - 1);
+  rmax = min(rmax, nrow - 1);
+  const double dx = 2 * hsize[0] / (ncol - 1), dy = 2 * hsize[1] / (nrow - 1);
+  double prism[18], vrel[18], cl[3], cw[3];
+  B2K_NOUNROLL for (int k = 0; k < 18; k++) prism[k] = 0;
+  CvxGeom ga;
+  ga.type = B2MJ_GEOM_MESH;
+  ga.nvert = 6;
+  ga.pos = cw;
+  ga.mat = mat1;
+  ga.size = hsize;  // unused by the hull support
+  ga.vert = vrel;
+  int cnt = 0;
+  B2K_NOUNROLL for (int r = rmin; r < rmax; r++) {
+    int nvert = 0;
+    B2K_NOUNROLL for (int c = cmin; c <= cmax; c++) {
+      B2K_NOUNROLL for (int i = 0; i < 2; i++) {
+        const int rr = r + (i == 0 ? 1 : 0);
+        B2K_NOUNROLL for (int k = 0; k < 3; k++) {
+          prism[k] = prism[3 + k]; prism[3 + k] = prism[6 + k];
+          prism[9 + k] = prism[12 + k]; prism[12 + k] = prism[15 + k];
+        }
+        prism[6] = prism[15] = dx * c - hsize[0];
+        prism[7] = prism[16] = dy * rr - hsize[1];
+        prism[8] = -hsize[3];
+        prism[17] = data[rr * ncol + c] * hsize[2];
+        if (++nvert <= 2) continue;
+        if (prism[11] < xmin[2] && prism[14] < xmin[2] && prism[17] < xmin[2]) continue;
+        B2K_NOUNROLL for (int k = 0; k < 3; k++) {
+          double s = 0;
+          B2K_NOUNROLL for (int v = 0; v < 6; v++) s += prism[3 * v + k];
+          s /= 6;
+          cl[k] = s;
+          B2K_NOUNROLL for (int v = 0; v < 6; v++) vrel[3 * v + k] = prism[3 * v + k] - s;
+        }
+        rotVecMat(cw, cl, mat1);
+        addTo3(cw, pos1);
+        if (c_convexConvexAt(o, cnt, margin, ga, gb) == 1) {
+          if (++cnt >= B2K_MAXPAIRCON) return cnt;
+        }
+      }
+    }
+  }
+  return cnt;
 }
 
 }  // namespace b2k

@@ -52,6 +52,9 @@ struct Ctx {
   std::string meshdir;
   std::vector<MeshData> meshes;
   std::map<std::string, int> mesh_id;
+  struct HField { int nrow = 0, ncol = 0; double size[4] = {0, 0, 0, 0}; std::vector<double> data; };
+  std::vector<HField> hfields;
+  std::map<std::string, int> hfield_id;
 };
 
 std::vector<double> parse_nums(const std::string& s) {
@@ -223,7 +226,8 @@ int geom_type_from(const XmlNode* n, const std::string& s) {
   if (s == "cylinder") return B2MJ_GEOM_CYLINDER;
   if (s == "box") return B2MJ_GEOM_BOX;
   if (s == "mesh") return B2MJ_GEOM_MESH;
-  fail(n, "unsupported geom/site type '" + s + "' (hfield is out of scope)");
+  if (s == "hfield") return B2MJ_GEOM_HFIELD;
+  fail(n, "unsupported geom/site type '" + s + "'");
 }
 
 // volume and principal inertia (unit density scaled by mass later) of a primitive
@@ -390,7 +394,7 @@ struct Builder {
     AttrMap em = effective(ctx, n, childclass);
     A a{em, n};
     g.name = a.str("name");
-    g.type = geom_type_from(n, a.str("type", a.has("mesh") ? "mesh" : "sphere"));
+    g.type = geom_type_from(n, a.str("type", a.has("mesh") ? "mesh" : a.has("hfield") ? "hfield" : "sphere"));
     int ns = a.vec("size", g.size, 3);
     a.vec("pos", g.pos, 3, 3);
     orientation(ctx, a, g.quat);
@@ -412,6 +416,21 @@ struct Builder {
       g.rbound = md.rbound;
       ns = 3;
     }
+    if (g.type == B2MJ_GEOM_HFIELD) {
+      // mjCGeom::Compile: the geom takes its size from the hfield asset (x, y radii; z = elevation / 4 + base / 2, a
+      // bounding value only: the collision code reads hfield_size); rbound covers the whole slab
+      if (!a.has("hfield")) fail(n, "hfield geom needs an hfield attribute");
+      auto it = ctx.hfield_id.find(a.str("hfield"));
+      if (it == ctx.hfield_id.end()) fail(n, "unknown hfield '" + a.str("hfield") + "'");
+      const Ctx::HField& hf = ctx.hfields[it->second];
+      g.meshid = it->second;
+      g.size[0] = hf.size[0];
+      g.size[1] = hf.size[1];
+      g.size[2] = 0.25 * hf.size[2] + 0.5 * hf.size[3];
+      const double zmax = std::max(hf.size[2], hf.size[3]);
+      g.rbound = std::sqrt(hf.size[0] * hf.size[0] + hf.size[1] * hf.size[1] + zmax * zmax);
+      ns = 3;
+    }
     if (a.has("fromto")) {
       double ft[6];
       a.vec("fromto", ft, 6, 6);
@@ -427,7 +446,7 @@ struct Builder {
       else g.size[1] = len / 2;
     } else {
       int need = (g.type == B2MJ_GEOM_SPHERE) ? 1 : (g.type == B2MJ_GEOM_CAPSULE || g.type == B2MJ_GEOM_CYLINDER) ? 2
-                 : (g.type == B2MJ_GEOM_PLANE || g.type == B2MJ_GEOM_MESH) ? 0 : 3;
+                 : (g.type == B2MJ_GEOM_PLANE || g.type == B2MJ_GEOM_MESH || g.type == B2MJ_GEOM_HFIELD) ? 0 : 3;
       if (ns < need) fail(n, "geom size needs " + std::to_string(need) + " values");
     }
     int nf = a.vec("friction", g.friction, 3);
@@ -798,6 +817,72 @@ b2mjModel* compile(const XmlNode* root) {
       ctx.meshes.push_back(std::move(md));
     }
   }
+  // ---- assets: height fields.  MuJoCo 2.3.7 takes the elevation from a file (PNG, or the custom binary format
+  // (int32) nrow, (int32) ncol, (float32) data[nrow * ncol]) or leaves it zero for the program to fill; the inline
+  // `elevation` attribute of later MuJoCo versions is accepted too.  PNG decoding is the reference's vendored lodepng
+  // (out of scope) and is rejected by name.  mjCHField::Compile normalises the data to [0, 1].
+  for (auto& sec : root->children) {
+    if (sec->tag != "asset") continue;
+    for (auto& ch : sec->children) {
+      if (ch->tag != "hfield") continue;
+      AttrMap em = effective(ctx, ch.get(), "");
+      A a{em, ch.get()};
+      Ctx::HField hf;
+      std::string name = a.str("name");
+      if (a.vec("size", hf.size, 4) != 4) fail(ch.get(), "hfield size needs 4 values (x radius, y radius, elevation, base)");
+      for (int k = 0; k < 4; k++)
+        if (!(hf.size[k] > 0)) fail(ch.get(), "hfield size values must be positive");
+      if (a.has("file")) {
+        std::string file = a.str("file");
+        if (name.empty()) {
+          const size_t sl = file.find_last_of("/\\"), dot = file.find_last_of('.');
+          const size_t b0 = sl == std::string::npos ? 0 : sl + 1;
+          name = file.substr(b0, dot == std::string::npos || dot < b0 ? std::string::npos : dot - b0);
+        }
+        if (file.size() >= 4 && (file.substr(file.size() - 4) == ".png" || file.substr(file.size() - 4) == ".PNG"))
+          fail(ch.get(), "hfield PNG files are not supported (no PNG decoder): use the binary format or the elevation attribute");
+        if (file.empty() || file[0] != '/') {
+          std::string base = ctx.meshdir;
+          if (base.empty() || base[0] != '/') base = model_dir() + (model_dir().empty() || base.empty() ? "" : "/") + base;
+          file = base + (base.empty() ? "" : "/") + file;
+        }
+        FILE* fp = std::fopen(file.c_str(), "rb");
+        if (!fp) fail(ch.get(), "cannot open hfield file '" + file + "'");
+        int32_t dims[2] = {0, 0};
+        bool ok = std::fread(dims, sizeof(int32_t), 2, fp) == 2 && dims[0] >= 2 && dims[1] >= 2 && (int64_t)dims[0] * dims[1] < (1 << 26);
+        std::vector<float> buf;
+        if (ok) {
+          buf.resize((size_t)dims[0] * dims[1]);
+          ok = std::fread(buf.data(), sizeof(float), buf.size(), fp) == buf.size();
+        }
+        std::fclose(fp);
+        if (!ok) fail(ch.get(), "hfield file '" + file + "' is not (int32 nrow, int32 ncol, float32 data[nrow * ncol])");
+        hf.nrow = dims[0];
+        hf.ncol = dims[1];
+        hf.data.assign(buf.begin(), buf.end());
+      } else {
+        hf.nrow = a.integer("nrow", 0);
+        hf.ncol = a.integer("ncol", 0);
+        if (hf.nrow < 2 || hf.ncol < 2) fail(ch.get(), "hfield needs a file, or nrow >= 2 and ncol >= 2");
+        hf.data.assign((size_t)hf.nrow * hf.ncol, 0.0);
+        if (a.has("elevation")) {
+          std::vector<double> ev = parse_nums(a.str("elevation"));
+          if (ev.size() != hf.data.size()) fail(ch.get(), "hfield elevation needs nrow * ncol values");
+          for (size_t k = 0; k < ev.size(); k++) hf.data[k] = (double)(float)ev[k];  // mjModel.hfield_data is float
+        }
+      }
+      if (name.empty()) fail(ch.get(), "hfield needs a name");
+      double emin = 1e10, emax = -1e10;
+      for (double v : hf.data) { emin = std::min(emin, v); emax = std::max(emax, v); }
+      for (double& v : hf.data) {
+        v -= emin;
+        if (emax - emin > 1e-15) v = (double)(float)(v / (emax - emin));
+      }
+      if (ctx.hfield_id.count(name)) fail(ch.get(), "repeated hfield name '" + name + "'");
+      ctx.hfield_id[name] = (int)ctx.hfields.size();
+      ctx.hfields.push_back(std::move(hf));
+    }
+  }
 
   // ---- pass 2: kinematic tree
   B.bodies.emplace_back();  // world
@@ -869,6 +954,9 @@ b2mjModel* compile(const XmlNode* root) {
   m->nmesh = (int)ctx.meshes.size();
   m->nmeshvert = 0;
   for (auto& md : ctx.meshes) m->nmeshvert += (int)md.vert.size() / 3;
+  m->nhfield = (int)ctx.hfields.size();
+  m->nhfielddata = 0;
+  for (auto& hf : ctx.hfields) m->nhfielddata += (int)hf.data.size();
   m->npair = (int)pair_nodes.size();
   m->nkey = (int)key_nodes.size();
   m->nkeyq = m->nkey * nq; m->nkeyv = m->nkey * nv; m->nkeyu = m->nkey * m->nu;
@@ -971,6 +1059,16 @@ b2mjModel* compile(const XmlNode* root) {
       std::copy(md.vert.begin(), md.vert.end(), m->mesh_vert + 3 * adr);
       adr += m->mesh_vertnum[i];
     }
+    adr = 0;
+    for (int i = 0; i < m->nhfield; i++) {
+      const Ctx::HField& hf = ctx.hfields[i];
+      m->hfield_nrow[i] = hf.nrow;
+      m->hfield_ncol[i] = hf.ncol;
+      m->hfield_adr[i] = adr;
+      std::copy(hf.size, hf.size + 4, m->hfield_size + 4 * i);
+      std::copy(hf.data.begin(), hf.data.end(), m->hfield_data + adr);
+      adr += (int)hf.data.size();
+    }
   }
 
   // ---- fill body / joint / dof / geom / site arrays
@@ -1066,6 +1164,7 @@ b2mjModel* compile(const XmlNode* root) {
           case B2MJ_GEOM_ELLIPSOID: rb = std::max(gm.size[0], std::max(gm.size[1], gm.size[2])); break;
           case B2MJ_GEOM_BOX: rb = norm3(gm.size); break;
           case B2MJ_GEOM_MESH: rb = gm.rbound; break;
+          case B2MJ_GEOM_HFIELD: rb = gm.rbound; break;
           default: rb = 0;
         }
         m->geom_rbound[g] = rb;
@@ -1526,6 +1625,9 @@ void model_build_collision_pairs(b2mjModel* m) {
     if (t1 == B2MJ_GEOM_PLANE && (t2 == B2MJ_GEOM_CYLINDER || t2 == B2MJ_GEOM_MESH || t2 == B2MJ_GEOM_BOX)) return 4;
     if (t1 == B2MJ_GEOM_CAPSULE && (t2 == B2MJ_GEOM_CAPSULE || t2 == B2MJ_GEOM_BOX)) return 2;
     if (t1 == B2MJ_GEOM_BOX && t2 == B2MJ_GEOM_BOX) return 8;
+    // one contact per penetrated prism of the sub-grid under the geom; MuJoCo stops at mjMAXCONPAIR = 50, this
+    // library at the 8 contacts a pair's lane can hold (kernels/pair_con.cuh)
+    if (t1 == B2MJ_GEOM_HFIELD) return 8;
     return 1;
   };
   auto push = [&](int ga, int gb, int pairid) {
@@ -1533,6 +1635,7 @@ void model_build_collision_pairs(b2mjModel* m) {
     if (m->geom_type[x] > m->geom_type[y]) std::swap(x, y);  // narrowphase table is upper-triangular in type
     const int t1 = m->geom_type[x], t2 = m->geom_type[y];
     if (t1 == B2MJ_GEOM_PLANE && t2 == B2MJ_GEOM_PLANE) return;
+    if (t2 == B2MJ_GEOM_HFIELD) return;  // plane-hfield, hfield-hfield: no entry in mjCOLLISIONFUNC
     const int b1 = std::min(m->geom_bodyid[ga], m->geom_bodyid[gb]), b2 = std::max(m->geom_bodyid[ga], m->geom_bodyid[gb]);
     cand.push_back({(b1 << 16) + b2, x, y, maxcon_of(t1, t2), pairid});
   };

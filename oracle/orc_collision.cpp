@@ -406,6 +406,13 @@ static int narrowphase(const b2mjModel* m, const OrcData* d, Con* con, int g1, i
     if (t2 == B2MJ_GEOM_ELLIPSOID || t2 == B2MJ_GEOM_MESH) return planeConvex(con, margin, pos1, mat1, convex(g2, t2, pos2, mat2, size2));
     return -1;
   }
+  if (t1 == B2MJ_GEOM_HFIELD) {  // mjc_ConvexHField for every convex geom type
+    if (t2 < B2MJ_GEOM_SPHERE || t2 > B2MJ_GEOM_MESH || m->geom_dataid[g1] < 0) return -1;
+    const int h = m->geom_dataid[g1];
+    return hfieldConvex(con, 8, margin, pos1, mat1, m->hfield_size + 4 * h, m->hfield_nrow[h], m->hfield_ncol[h],
+                        m->hfield_data + m->hfield_adr[h], convex(g2, t2, pos2, mat2, size2), m->geom_rbound[g2],
+                        m->opt.mpr_iterations, m->opt.mpr_tolerance);
+  }
   // pairs with a dedicated primitive function (mjCOLLISIONFUNC); every other convex pair goes to the general MPR test
   if (t1 == B2MJ_GEOM_SPHERE && t2 == B2MJ_GEOM_SPHERE) return sphereSphere(con, margin, pos1, size1[0], pos2, size2[0]);
   if (t1 == B2MJ_GEOM_SPHERE && t2 == B2MJ_GEOM_CAPSULE) return sphereCapsule(con, margin, pos1, size1[0], pos2, mat2, size2);

@@ -364,4 +364,90 @@ int convexConvex(Con* con, double margin, const ConvexGeom& g1, const ConvexGeom
   return 1;
 }
 
+// ---- height field vs convex geom (mjc_ConvexHField).  The geom's bounding box in the hfield frame (support points
+// along the six axis directions) selects a sub-grid; every grid triangle under it is extruded down to -base into a
+// six-vertex prism (vertices arrive strip-wise: row r + 1 then row r for every column, each new vertex closing a
+// triangle with the previous two) and tested against the geom with the MPR penetration query, one contact per
+// penetrating prism, the prism being object 1.  Differences from MuJoCo 2.3.7, stated: (i) the margin is handled as
+// in mjc_Convex (both objects inflated by margin / 2, dist = margin - depth) where MuJoCo raises the prism tops by the
+// margin; identical at the default margin 0; (ii) at most `maxcon` (8) contacts per pair where MuJoCo stops at
+// mjMAXCONPAIR = 50.  Recalled from memory, neither MuJoCo nor libccd is in /root/reference: "parity unpinned".
+int hfieldConvex(Con* con, int maxcon, double margin, const double* pos1, const double* mat1, const double* hsize, int nrow,
+                 int ncol, const double* data, const ConvexGeom& g2, double rbound2, int mpr_iterations, double mpr_tolerance) {
+  // geom centre in the hfield frame: slab test against the bounding sphere
+  double dif[3], pos[3];
+  sub3(dif, g2.pos, pos1);
+  rotVecMatT(pos, dif, mat1);
+  const double r2 = rbound2 + margin;
+  for (int i = 0; i < 2; i++)
+    if (pos[i] > hsize[i] + r2 || pos[i] < -hsize[i] - r2) return 0;
+  if (pos[2] > hsize[2] + r2 || pos[2] < -hsize[3] - r2) return 0;
+  // bounding box of the geom in the hfield frame from its support mapping
+  double xmin[3], xmax[3];
+  for (int i = 0; i < 3; i++) {
+    double dirw[3], sp[3], loc[3];
+    const double ax[3] = {mat1[i], mat1[3 + i], mat1[6 + i]};  // hfield axis i in world coordinates
+    copy3(dirw, ax);
+    convexSupport(g2, dirw, sp);
+    sub3(dif, sp, pos1);
+    rotVecMatT(loc, dif, mat1);
+    xmax[i] = loc[i] + margin;
+    scl3(dirw, ax, -1.0);
+    convexSupport(g2, dirw, sp);
+    sub3(dif, sp, pos1);
+    rotVecMatT(loc, dif, mat1);
+    xmin[i] = loc[i] - margin;
+  }
+  if (xmin[0] > hsize[0] || xmax[0] < -hsize[0] || xmin[1] > hsize[1] || xmax[1] < -hsize[1] || xmin[2] > hsize[2] ||
+      xmax[2] < -hsize[3])
+    return 0;
+  // sub-grid under the box
+  int cmin = (int)std::floor((xmin[0] + hsize[0]) / (2 * hsize[0]) * (ncol - 1));
+  int cmax = (int)std::ceil((xmax[0] + hsize[0]) / (2 * hsize[0]) * (ncol - 1));
+  int rmin = (int)std::floor((xmin[1] + hsize[1]) / (2 * hsize[1]) * (nrow - 1));
+  int rmax = (int)std::ceil((xmax[1] + hsize[1]) / (2 * hsize[1]) * (nrow - 1));
+  cmin = cmin < 0 ? 0 : cmin;
+  rmin = rmin < 0 ? 0 : rmin;
+  cmax = cmax > ncol - 1 ? ncol - 1 : cmax;
+  rmax = rmax > nrow - 1 ? nrow - 1 : rmax;
+  const double dx = 2 * hsize[0] / (ncol - 1), dy = 2 * hsize[1] / (nrow - 1);
+  double prism[18] = {0};  // vertices 0-2 bottom, 3-5 top, hfield frame
+  double vrel[18], cl[3], cw[3];  // the prism as a six-vertex hull around its own centroid (the MPR's interior point)
+  const double zero_size[3] = {0, 0, 0};
+  ConvexGeom g1{B2MJ_GEOM_MESH, cw, mat1, zero_size, vrel, 6};
+  int cnt = 0;
+  for (int r = rmin; r < rmax; r++) {
+    int nvert = 0;
+    for (int c = cmin; c <= cmax; c++) {
+      for (int i = 0; i < 2; i++) {
+        const int rr = r + (i == 0 ? 1 : 0);
+        // shift the strip: the two newest columns of the prism move down, the new vertex enters at slots 2 / 5
+        for (int k = 0; k < 3; k++) {
+          prism[k] = prism[3 + k]; prism[3 + k] = prism[6 + k];
+          prism[9 + k] = prism[12 + k]; prism[12 + k] = prism[15 + k];
+        }
+        prism[6] = prism[15] = dx * c - hsize[0];
+        prism[7] = prism[16] = dy * rr - hsize[1];
+        prism[8] = -hsize[3];
+        prism[17] = data[rr * ncol + c] * hsize[2];
+        if (++nvert <= 2) continue;
+        // prism entirely below the geom's lowest point: nothing to test
+        if (prism[11] < xmin[2] && prism[14] < xmin[2] && prism[17] < xmin[2]) continue;
+        for (int k = 0; k < 3; k++) {
+          cl[k] = 0;
+          for (int v = 0; v < 6; v++) cl[k] += prism[3 * v + k];
+          cl[k] /= 6;
+          for (int v = 0; v < 6; v++) vrel[3 * v + k] = prism[3 * v + k] - cl[k];
+        }
+        rotVecMat(cw, cl, mat1);
+        addTo3(cw, pos1);
+        if (convexConvex(con + cnt, margin, g1, g2, mpr_iterations, mpr_tolerance) == 1) {
+          if (++cnt >= maxcon) return cnt;
+        }
+      }
+    }
+  }
+  return cnt;
+}
+
 }  // namespace orc

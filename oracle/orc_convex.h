@@ -22,5 +22,7 @@ int planeCylinder(Con* con, double margin, const double* pos1, const double* mat
 int planeConvex(Con* con, double margin, const double* pos1, const double* mat1, const ConvexGeom& g);
 int convexConvex(Con* con, double margin, const ConvexGeom& g1, const ConvexGeom& g2, int mpr_iterations, double mpr_tolerance);
 void convexSupport(const ConvexGeom& g, const double* dir, double* res);
+int hfieldConvex(Con* con, int maxcon, double margin, const double* pos1, const double* mat1, const double* hsize, int nrow,
+                 int ncol, const double* data, const ConvexGeom& g2, double rbound2, int mpr_iterations, double mpr_tolerance);
 
 }  // namespace orc

@@ -1,0 +1,131 @@
+"""Height fields (MuJoCo mjc_ConvexHField, reached by the reference through mj_step,
+mujoco_env.cpp:498): asset compile facts, closed-form answers of the oracle that involve no MuJoCo (a flat field is a
+plane, a linear ramp is a tilted plane), and GPU-vs-oracle parity for every convex geom type on a bumpy terrain."""
+import struct
+
+import numpy as np
+import pytest
+
+
+def scene(hf, geoms, opt=""):
+    bodies = "".join(f'<body pos="{p}"><freejoint/>{g}</body>' for p, g in geoms)
+    return (f'<mujoco><option timestep="0.002" {opt}/><asset>{hf}</asset><worldbody>'
+            f'<geom name="terrain" type="hfield" hfield="t"/>{bodies}</worldbody></mujoco>')
+
+
+def bumpy(nrow=9, ncol=11, seed=4):
+    rng = np.random.default_rng(seed)
+    el = rng.uniform(0, 1, (nrow, ncol))
+    return el, f'<hfield name="t" nrow="{nrow}" ncol="{ncol}" size="0.6 0.5 0.08 0.05" elevation="{" ".join(map(str, el.ravel()))}"/>'
+
+
+def test_hfield_compile_facts(capi, tmp_path):
+    el, hf = bumpy()
+    m = capi.Model.from_xml_string(scene(hf, [("0 0 0.3", '<geom type="sphere" size="0.05"/>')]))
+    assert (m.nhfield, m.nhfielddata) == (1, 99)
+    assert (m.hfield_nrow[0], m.hfield_ncol[0], m.hfield_adr[0]) == (9, 11, 0)
+    np.testing.assert_allclose(m.hfield_size, [[0.6, 0.5, 0.08, 0.05]])
+    # normalised to [0, 1] in float32 like mjModel.hfield_data
+    f = el.astype(np.float32).astype(np.float64)
+    want = ((f - f.min()) / (f.max() - f.min())).astype(np.float32)
+    np.testing.assert_allclose(m.hfield_data.ravel(), want.ravel(), rtol=0, atol=1e-7)
+    assert m.hfield_data.min() == 0.0 and m.hfield_data.max() == 1.0
+    # the geom takes its size from the asset; massless; bounding sphere covers the slab
+    assert m.geom_type[0] == 1 and m.geom_dataid[0] == 0
+    np.testing.assert_allclose(m.geom_size[0], [0.6, 0.5, 0.25 * 0.08 + 0.5 * 0.05])
+    np.testing.assert_allclose(m.geom_rbound[0], np.sqrt(0.6 ** 2 + 0.5 ** 2 + 0.08 ** 2))
+    assert m.body_mass[0] == 0
+    assert m.ncollpair == 1 and m.nconmax == 8
+    # the custom binary format of MuJoCo: int32 nrow, int32 ncol, float32 data
+    with open(tmp_path / "t.bin", "wb") as fp:
+        fp.write(struct.pack("<2i", 9, 11))
+        fp.write(el.astype("<f4").tobytes())
+    (tmp_path / "m.xml").write_text(scene('<hfield name="t" file="t.bin" size="0.6 0.5 0.08 0.05"/>',
+                                          [("0 0 0.3", '<geom type="sphere" size="0.05"/>')]))
+    mb = capi.Model.from_xml_file(str(tmp_path / "m.xml"))
+    np.testing.assert_array_equal(mb.hfield_data, m.hfield_data)
+    # PNG needs the decoder the survey puts out of scope: rejected by name, not ignored
+    with pytest.raises(capi.B2mjError, match="PNG"):
+        capi.Model.from_xml_string(scene('<hfield name="t" file="t.png" size="1 1 1 1"/>', []))
+    # plane-hfield and hfield-hfield have no narrowphase function: no candidate pairs
+    m2 = capi.Model.from_xml_string(scene(hf, []).replace("</worldbody>", '<geom type="plane" size="1 1 .1"/></worldbody>'))
+    assert m2.ncollpair == 0
+
+
+def test_flat_hfield_is_a_plane(capi, orc):
+    flat = '<hfield name="t" nrow="5" ncol="7" size="1 0.8 0.3 0.1"/>'
+    m = capi.Model.from_xml_string(scene(flat, [("0.03 0.02 0.2", '<geom type="sphere" size="0.1"/>')]))
+    mp = capi.Model.from_xml_string('<mujoco><option timestep="0.002"/><worldbody><geom type="plane" size="1 1 .1"/>'
+                                    '<body pos="0.03 0.02 0.2"><freejoint/><geom type="sphere" size="0.1"/></body>'
+                                    '</worldbody></mujoco>')
+    o, op = orc.Oracle(m), orc.Oracle(mp)
+    for _ in range(1500):
+        o.step(1)
+        op.step(1)
+    assert o.get("ncon")[0] == 1
+    # rest height within the MPR tolerance (1e-6) of the analytic plane-sphere contact
+    assert abs(o.get("qpos")[2] - op.get("qpos")[2]) < 5e-6
+    np.testing.assert_allclose(o.get("contact_frame")[:3], [0, 0, 1], atol=1e-6)
+
+
+def test_ramp_hfield_matches_the_tilted_plane(capi, orc):
+    nrow, ncol = 4, 6
+    el = " ".join(str(c / (ncol - 1)) for r in range(nrow) for c in range(ncol))
+    hf = f'<hfield name="t" nrow="{nrow}" ncol="{ncol}" size="1 0.8 0.5 0.1" elevation="{el}"/>'
+    c = np.array([0.03, 0.02, 0.36])
+    for geom, reach in (('<geom type="sphere" size="0.1"/>', 0.1), ('<geom type="ellipsoid" size="0.1 0.1 0.1"/>', 0.1)):
+        m = capi.Model.from_xml_string(scene(hf, [(" ".join(map(str, c)), geom)]))
+        o = orc.Oracle(m)
+        o.forward()
+        assert o.get("ncon")[0] == 1
+        n = np.array([-0.25, 0, 1.0])  # z = 0.25 (x + 1)
+        n /= np.linalg.norm(n)
+        dist = (c[2] - 0.25 * (c[0] + 1)) * n[2] - reach
+        assert abs(o.get("contact_dist")[0] - dist) < 5e-6
+        np.testing.assert_allclose(o.get("contact_frame")[:3], n, atol=5e-6)
+
+
+def test_box_on_flat_hfield_gets_one_contact_per_prism_and_settles(capi, orc):
+    flat = '<hfield name="t" nrow="3" ncol="3" size="0.2 0.2 0.3 0.1"/>'
+    m = capi.Model.from_xml_string(scene(flat, [("0.01 0.02 0.06", '<geom type="box" size="0.05 0.05 0.05"/>')]))
+    o = orc.Oracle(m)
+    for _ in range(1000):
+        o.step(1)
+    assert 1 <= o.get("ncon")[0] <= 8
+    assert abs(o.get("qpos")[2] - 0.05) < 2e-3 and np.abs(o.get("qvel")).max() < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["Newton", "PGS"])
+def test_hfield_gpu_parity(capi, orc, solver):
+    from mujoco_ros_pkgs_b200.batch import BatchSim
+    from parity_util import compare_forward_fields, injected_steps, make_oracles, perturbed
+
+    _, hf = bumpy()
+    geoms = [("-0.3 -0.2 0.16", '<geom type="sphere" size="0.05"/>'),
+             ("-0.1 0.1 0.17", '<geom type="capsule" size="0.03 0.05"/>'),
+             ("0.1 -0.1 0.18", '<geom type="box" size="0.04 0.05 0.03"/>'),
+             ("0.3 0.2 0.17", '<geom type="ellipsoid" size="0.05 0.03 0.04"/>'),
+             ("0.25 -0.25 0.17", '<geom type="cylinder" size="0.04 0.03"/>'),
+             ("-0.3 0.3 0.17", '<geom type="mesh" mesh="tet"/>')]
+    hf += '<mesh name="tet" vertex="0 0 0  0.08 0 0  0 0.08 0  0 0 0.08  0.05 0.05 0.05"/>'
+    model = capi.Model.from_xml_string(scene(hf, geoms, f'solver="{solver}" cone="elliptic"'))
+    nenv = 8
+    qpos, qvel = perturbed(model, nenv, seed=11, amp=0.03)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    # let the pile land so that contacts exist, then compare every field and take injected steps
+    sim.step(120)
+    q, v = sim.get("qpos"), sim.get("qvel")
+    sim.keep_intermediates(True)
+    sim.forward()
+    oracles = make_oracles(orc, model, q, v)
+    for o in oracles:
+        o.forward()
+    assert sim.get("ncon").max() >= 3
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied", "qacc", "qacc_warmstart", "efc_force", "qfrc_constraint",
+                                                            "efc_state", "sensordata", "act_dot"}, tag="hfield")
+    sim.keep_intermediates(False)
+    worst, max_nefc = injected_steps(model, sim, oracles, 120, np.random.default_rng(2), tag="hfield")
+    assert worst < 1e-5 and max_nefc > 0
