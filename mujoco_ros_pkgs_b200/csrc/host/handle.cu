@@ -673,7 +673,40 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
   if (const char* env = getenv("B2MJ_STAGE_SYNC")) a.sync_stages = atoi(env) ? 1 : 0;
   const size_t smem = h->smem_bytes / h->warps_per_cta * W;
   static const bool reorder = !getenv("B2MJ_NO_REORDER");
+  static const int order_legacy = getenv("B2MJ_ORDER_LEGACY") ? 1 : 0;
+  static const bool order_sync = order_legacy || getenv("B2MJ_ORDER_SYNC");
   a.perm = (reorder && h->perm_valid && !a.sched) ? h->perm : nullptr;
+  a.cost = nullptr;
+  // Single-step launches of a batch wider than one wave refresh the launch order OFF the critical path: the order kernel
+  // of launch k runs on a side stream under launch k + 1 (one CTA; it takes the first slot a finished env frees), and
+  // launch k + 1 uses the order of launch k - 1.  Contact states persist over steps, so a prediction that is one step
+  // older orders as well, and the ~10 us order kernel no longer sits between two steps (C2: 353 us per step).
+  // Worth it where the order kernel is a visible share of the step -- small models (nv <= 16, the dense-inverse class):
+  // C2 per-step 11.55 M -> 11.78 M env-steps/s.  Where a step takes milliseconds the one-step-older prediction costs
+  // more than the 10 us it hides (C3 450 k -> 416 k, C4 -1 %, C5 -2 %): those keep the synchronous refresh.
+  static const char* async_env = getenv("B2MJ_ORDER_ASYNC");
+  const bool async_model = async_env ? atoi(async_env) != 0 : h->dm.dense_small != 0;
+  const bool order_async = reorder && !order_sync && async_model && nsteps == 1 && !a.sched && (mode == MODE_STEP || mode == MODE_STEP_END) &&
+                           h->nenv > std::max(h->resident_envs, 32);
+  if (order_async) {
+    if (!h->order_stream) {
+      CUDA_OK(cudaStreamCreateWithFlags(&h->order_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        CUDA_OK(cudaEventCreateWithFlags(&h->order_step_done[i], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->order_done[i], cudaEventDisableTiming));
+      }
+      CUDA_OK(cudaMalloc(&h->perm_async, (size_t)2 * h->nenv * sizeof(int)));
+      CUDA_OK(cudaMalloc(&h->cost, (size_t)2 * h->nenv * sizeof(int)));
+    }
+    const uint64_t n = h->order_n;  // this launch is followed by order kernel n + 1
+    if (n >= 2) {
+      // order kernel n - 1 (finished under the previous launch) wrote perm_async[(n - 1) & 1] and was the last reader of
+      // the cost buffer this launch overwrites
+      CUDA_OK(cudaStreamWaitEvent(h->stream, h->order_done[(n - 1) & 1], 0));
+      a.perm = h->perm_async + (size_t)((n - 1) & 1) * h->nenv;
+    }  // (the first two launches keep whatever order a synchronous refresh left, or the identity)
+    a.cost = h->cost + (size_t)((n + 1) & 1) * h->nenv;
+  }
   a.env_model = nullptr;
   a.pub = h->launch_pub;
   a.pub_seq = h->launch_pub_seq;
@@ -690,16 +723,27 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
     return B2MJ_ECUDA;
   }
   h->launches++;
-  // heaviest-first launch order for the next launch, from the cost this one recorded per env (only worth a kernel
+  // heaviest-first launch order for the next launches, from the cost this one recorded per env (only worth a kernel
   // when the batch spans more than one wave: C5 has 512 envs and 148 slots)
-  // (after a multi-step rollout the residency is a sum over steps and the lock-stepped rollout CTAs do better with
-  // heavy and light envs mixed: the coarse rows x iterations classes of the last step stay in use there, measured
-  // 13.2 M against 12.9 M env-steps/s on the C2 rollout)
-  static const int order_legacy = getenv("B2MJ_ORDER_LEGACY") ? 1 : 0;
-  if (reorder && mode != MODE_FORWARD && mode != MODE_STEP_BEGIN &&
-      (order_legacy ? h->nenv >= 1024 : h->nenv > std::max(h->resident_envs, 32))) {
+  if (order_async) {
+    const uint64_t j = ++h->order_n;
+    CUDA_OK(cudaEventRecord(h->order_step_done[j & 1], h->stream));
+    CUDA_OK(cudaStreamWaitEvent(h->order_stream, h->order_step_done[j & 1], 0));
+    const int orc = b2k_launch_order(h->stats, h->cost + (size_t)(j & 1) * h->nenv, h->nenv,
+                                     h->perm_async + (size_t)(j & 1) * h->nenv, 0, h->order_stream);
+    if (orc != 0) {
+      set_error(std::string("order kernel launch failed: ") + cudaGetErrorString((cudaError_t)orc));
+      return B2MJ_ECUDA;
+    }
+    CUDA_OK(cudaEventRecord(h->order_done[j & 1], h->order_stream));
+    h->launches++;
+  } else if (reorder && mode != MODE_FORWARD && mode != MODE_STEP_BEGIN &&
+             (order_legacy ? h->nenv >= 1024 : h->nenv > std::max(h->resident_envs, 32))) {
+    // synchronous refresh (rollouts, B2MJ_ORDER_SYNC / B2MJ_ORDER_LEGACY).  After a multi-step rollout the residency is a
+    // sum over steps and the lock-stepped rollout CTAs do better with heavy and light envs mixed: the coarse rows x
+    // iterations classes of the last step stay in use there (13.2 M against 12.9 M env-steps/s on the C2 rollout)
     if (!h->perm) CUDA_OK(cudaMalloc(&h->perm, (size_t)h->nenv * sizeof(int)));
-    const int orc = b2k_launch_order(h->stats, h->nenv, h->perm, (order_legacy || nsteps > 1) ? 1 : 0, h->stream);
+    const int orc = b2k_launch_order(h->stats, nullptr, h->nenv, h->perm, (order_legacy || nsteps > 1) ? 1 : 0, h->stream);
     if (orc != 0) {
       set_error(std::string("order kernel launch failed: ") + cudaGetErrorString((cudaError_t)orc));
       return B2MJ_ECUDA;
@@ -770,6 +814,13 @@ void b2mj_destroy(b2mj_handle* hh) {
   cudaFree(h->prof);
   cudaFree(h->sched);
   cudaFree(h->perm);
+  if (h->order_stream) {
+    cudaStreamSynchronize(h->order_stream);
+    cudaStreamDestroy(h->order_stream);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(h->order_step_done[i]); cudaEventDestroy(h->order_done[i]); }
+  }
+  cudaFree(h->perm_async);
+  cudaFree(h->cost);
   cudaFree(h->publish_slab);
   cudaFree(h->env_blob);
   cudaFree(h->env_model_idx);

@@ -35,6 +35,13 @@ struct Handle {
   unsigned char* mask_dev = nullptr;
   int* perm = nullptr;                 // [nenv] launch slot -> env, heaviest first (refreshed after every step launch)
   int perm_valid = 0;
+  // asynchronous order refresh of single-step launches (handle_launch): the order kernel runs on a side stream under the
+  // NEXT step launch, which uses the order computed one launch earlier
+  int* perm_async = nullptr;           // [2][nenv]
+  int* cost = nullptr;                 // [2][nenv] per-env residency written by the step kernel
+  cudaStream_t order_stream = nullptr;
+  cudaEvent_t order_step_done[2] = {nullptr, nullptr}, order_done[2] = {nullptr, nullptr};
+  uint64_t order_n = 0;                // order kernels issued so far; kernel j reads cost[j & 1], writes perm_async[j & 1]
   int* sched = nullptr;                // [1 + nenv] ticket counter + per-env chunk progress (persistent rollout)
   unsigned long long* prof = nullptr;  // [PROF_COUNT] stage cycle totals (b2mj_stage_profile), null = off
 

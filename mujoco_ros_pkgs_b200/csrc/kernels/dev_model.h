@@ -192,6 +192,7 @@ struct LaunchArgs {
   int chunk;               // steps per ticket
   int sync_stages;         // CTA-wide lockstep at stage boundaries (instruction / constant cache locality)
   const int* perm;         // [nenv] launch slot -> env, heaviest envs first (b2k_order_kernel), or null = identity
+  int* cost;               // [nenv] this launch's per-env residency (1024-cycle units) for the asynchronous order refresh, or null
   const int* env_model;    // [nenv] model variant of each env (per-env-model build only), or null
   const PubArgs* pub;      // fused publish targets (device memory), or null
   int pub_seq;             // sequence number this launch raises in every rank's flag array once all rows are out

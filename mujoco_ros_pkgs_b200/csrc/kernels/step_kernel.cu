@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(B2K_MAX_THREADS, B2K_MIN_CTAS) b2k_step_kernel
     if (lane == 0) {
       int* st = a.stats + (size_t)env * 4;
       st[0] = sc.ncon; st[1] = sc.nefc; st[2] = sc.iters;
-      st[3] = (int)((clock64() - t_item0) >> 10);  // this work item's residency in 1024-cycle units (diagnostic)
+      st[3] = (int)((clock64() - t_item0) >> 10);  // this work item's residency in 1024-cycle units
+      if (a.cost) a.cost[env] = st[3];
       e.I(B2MJ_F_SOLVER_ITER)[0] = sc.iters;
       for (int k = 0; k < B2MJ_NWARNING; k++) e.I(B2MJ_F_WARNING)[k] = warning[k];
     }
@@ -543,7 +544,8 @@ extern "C" int b2k_launch_step(const DevModel* m, const LaunchArgs* a, int warps
 // Stable counting sort: within a class envs keep their index order.  The order never changes results
 // (tests/test_gpu_paths.py::test_launch_order_does_not_change_results).
 #define B2K_ORDER_CLASSES 64
-__global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* __restrict__ perm, int legacy) {
+__global__ void b2k_order_kernel(const int* __restrict__ stats, const int* __restrict__ wt, int wstride, int nenv,
+                                 int* __restrict__ perm, int legacy) {
   __shared__ int count[B2K_ORDER_CLASSES], cursor[B2K_ORDER_CLASSES], wmax;
   __shared__ int wtot[32][B2K_ORDER_CLASSES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -552,7 +554,7 @@ __global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* _
   __syncthreads();
   if (!legacy) {
     int mx = 0;
-    for (int e = threadIdx.x; e < nenv; e += blockDim.x) mx = max(mx, stats[4 * e + 3]);
+    for (int e = threadIdx.x; e < nenv; e += blockDim.x) mx = max(mx, wt[(size_t)wstride * e]);
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) atomicMax(&wmax, mx);
     __syncthreads();
@@ -563,7 +565,7 @@ __global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* _
       const int w = stats[4 * e + 1] * stats[4 * e + 2];
       return w >= 1200 ? 0 : w >= 400 ? 1 : w >= 100 ? 2 : 3;
     }
-    const int k = (int)(((long long)max(stats[4 * e + 3], 0) * B2K_ORDER_CLASSES) / span);
+    const int k = (int)(((long long)max(wt[(size_t)wstride * e], 0) * B2K_ORDER_CLASSES) / span);
     return B2K_ORDER_CLASSES - 1 - min(k, B2K_ORDER_CLASSES - 1);
   };
   for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&count[cls(e)], 1);  // integer totals: order-free
@@ -598,8 +600,9 @@ __global__ void b2k_order_kernel(const int* __restrict__ stats, int nenv, int* _
   }
 }
 
-extern "C" int b2k_launch_order(const int* stats, int nenv, int* perm, int legacy, cudaStream_t stream) {
-  b2k_order_kernel<<<1, 1024, 0, stream>>>(stats, nenv, perm, legacy);
+// cost == null: the weights are the residencies in stats[4 e + 3]; else a dense [nenv] array (asynchronous refresh)
+extern "C" int b2k_launch_order(const int* stats, const int* cost, int nenv, int* perm, int legacy, cudaStream_t stream) {
+  b2k_order_kernel<<<1, 1024, 0, stream>>>(stats, cost ? cost : stats + 3, cost ? 1 : 4, nenv, perm, legacy);
   return (int)cudaGetLastError();
 }
 

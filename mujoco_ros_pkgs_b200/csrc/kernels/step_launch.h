@@ -23,5 +23,5 @@ int b2k_em_launch_step(const b2k::DevModel* m, const b2k::LaunchArgs* a, int war
 #endif
 int b2k_step_kernel_attrs(int* regs, int* static_smem, int* max_threads);
 int b2k_occupancy(int threads, size_t smem_bytes, int* ctas_per_sm);
-int b2k_launch_order(const int* stats, int nenv, int* perm, int legacy, cudaStream_t stream);
+int b2k_launch_order(const int* stats, const int* cost, int nenv, int* perm, int legacy, cudaStream_t stream);
 }
