@@ -64,8 +64,8 @@ def load_peaks():
 
 def load_profile_constants(model_name):
     """Per-env-step counters of the dominant kernel from the committed ncu capture of the fused rollout launch
-    (profiles/r2b_traffic.json, else earlier rounds): DRAM bytes and FP64 thread-instructions.  PROFILE CONSTANTS, not live."""
-    for name in ("r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):
+    (profiles/r2c_traffic.json, else earlier rounds): DRAM bytes and FP64 thread-instructions.  PROFILE CONSTANTS, not live."""
+    for name in ("r2c_traffic.json", "r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
