@@ -662,11 +662,17 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
     a.sched = h->sched;
     a.chunk = chunk;
   }
-  // per-step launches start every warp in step anyway (stage barriers measured no gain there); the static fused
-  // rollout uses its wide lock-stepped shape
+  // Launch shape.  The static fused rollout uses its wide lock-stepped shape.  A per-step launch of up to two waves starts
+  // every warp in step anyway and keeps the small CTAs (a finished env frees its slot at once; the wide shape measured
+  // -4 % at 4096 envs).  Beyond that the small CTAs of the later waves start whenever a slot frees, the fourteen warps of
+  // an SM drift into fourteen different stages and the kernel turns instruction-fetch bound: per-env residency doubles
+  // (213 k -> 462 k cycles at 16384 envs) and throughput FALLS with the batch (11.8 M at 4096 envs, 7.0 M at 65536).
+  // With the lock-stepped shape it keeps rising: 13.2 M at 8192, 15.2 M at 65536 (profiles/r2c_batch_sweep.txt).
   int W = h->warps_per_cta;
   a.sync_stages = 0;
-  if (mode == MODE_STEP && nsteps > 1 && !a.sched && !h->keep_intermediates && h->rollout_warps_per_cta > 0) {
+  static const char* step_wide_env = getenv("B2MJ_STEP_WIDE");
+  const bool step_wide = step_wide_env ? atoi(step_wide_env) != 0 : (double)h->nenv > 2.5 * std::max(1, h->resident_envs);
+  if (mode == MODE_STEP && (nsteps > 1 || step_wide) && !a.sched && !h->keep_intermediates && h->rollout_warps_per_cta > 0) {
     W = h->rollout_warps_per_cta;
     a.sync_stages = 1;
   }
@@ -944,7 +950,10 @@ int b2mj_rollout(b2mj_handle* hh, int nsteps, const double* dev_ctrl, double* de
       const double slots = (double)per_sm * h->warps_per_cta * sms;
       const double waves = h->nenv / slots;
       const double idle = std::ceil(waves) - waves;  // empty fraction of the last wave
-      if (waves > 1.0 && idle > 0.35) chunk = 64;
+      // ... as a share of the whole launch: the ticketed grid gives up the lock-stepped instruction fetch (-25 %), so it
+      // only pays when the empty tail is a large part of the launch (1.4 waves), never for a long one (65536 envs = 31.6
+      // waves ran ticketed under the round-2 rule `idle > 0.35` and lost a third: 9.0 M against 14 M env-steps/s)
+      if (waves > 1.0 && idle / std::ceil(waves) > 0.2) chunk = 64;
     }
   }
   if (const char* env = getenv("B2MJ_ROLLOUT_CHUNK")) chunk = atoi(env);
