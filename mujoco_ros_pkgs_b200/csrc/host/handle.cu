@@ -455,6 +455,15 @@ static int make_layout(Handle* h) {
       order.push_back({1, XF_EFC_MINVJT});
     }
     const bool no_promote = getenv("B2MJ_NO_PROMOTE") != nullptr;
+    std::vector<Cand> rest(cands.begin(), cands.end());
+    std::stable_sort(rest.begin(), rest.end(), [](const Cand& a, const Cand& b) { return a.bytes < b.bytes; });
+    std::vector<std::pair<int, int>> rest_order;
+    for (const Cand& c : rest) rest_order.push_back({c.is_x, c.id});
+    // place(E): everything back to the L2 arena, then promotion at residency E; returns the rows of the efc_J window
+    auto place = [&](int Etarget) -> int {
+    const int E = Etarget;
+    for (const Cand& c : cands) { if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1; }
+    xs[XF_JWIN] = 0;
     int promote_left = getenv("B2MJ_PROMOTE_MAX") ? atoi(getenv("B2MJ_PROMOTE_MAX")) : 1 << 30;  // experiment knob
     auto promote = [&](const std::vector<std::pair<int, int>>& list) {
     for (const auto& o : list) {
@@ -484,11 +493,27 @@ static int make_layout(Handle* h) {
       xs[XF_JWIN] = d.jwin_rows ? 2 + d.jwin_rows * nv : 0;
     }
     // the rest, smallest first
-    std::vector<Cand> rest(cands.begin(), cands.end());
-    std::stable_sort(rest.begin(), rest.end(), [](const Cand& a, const Cand& b) { return a.bytes < b.bytes; });
-    std::vector<std::pair<int, int>> rest_order;
-    for (const Cand& c : rest) rest_order.push_back({c.is_x, c.id});
     promote(rest_order);
+    return d.jwin_rows;
+    };
+    place(E);
+    // The wave count is a crude model of a launch whose envs differ 3x in cost.  Measured on C4 (2048 humanoid envs):
+    // at 5 envs/SM only the Hessian fits on chip and every access of the line search / update to Jaref, Jv, quad, D,
+    // state, force is an L2 round trip: 1.20 M env-steps/s per step; at 4 envs/SM the whole hot set is in shared memory:
+    // 1.26 M (fused rollout 1.41 M against 1.21 M); 3 envs/SM 1.06 M.  So from five envs per SM on, one env of
+    // residency is given up when that is what brings the solver's per-iteration working set on chip
+    // (profiles/r2c_shape_sweep.txt).
+    auto hot_on_chip = [&]() {
+      for (int x : {XF_NEWTON_H, XF_EFC_JAREF, XF_EFC_JV, XF_EFC_QUAD})
+        if (xs[x] && xcold[x]) return false;
+      for (int f : {B2MJ_F_EFC_D, B2MJ_F_EFC_STATE, B2MJ_F_EFC_FORCE, B2MJ_F_EFC_AREF, B2MJ_F_EFC_TYPE, B2MJ_F_EFC_ID})
+        if (d.fsize[f] && cold[f]) return false;
+      return true;
+    };
+    if (!pgs && d.team_warps == 1 && E >= 5 && !getenv("B2MJ_ENVS_PER_SM") && !getenv("B2MJ_NO_HOTSET_TRADE") && !hot_on_chip()) {
+      place(E - 1);
+      if (!hot_on_chip()) place(E);
+    }
   }
   // global (full) arena offsets (after every size is final: the efc_J window above is sized last)
   int gd = 0, gi = 0;
@@ -676,6 +701,10 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
     W = h->rollout_warps_per_cta;
     a.sync_stages = 1;
   }
+  // Newton / CG models: the CTA mates of a per-step or rollout launch meet at every stage boundary as well -- their
+  // code path is the longest in the kernel and two or three warps per SM running it out of step miss the instruction
+  // cache on nearly every line (C3: per-step +3.7 %, fused rollout +16 %; C2 / PGS per-step launches measured -1 %)
+  if (W >= 2 && h->model->opt.solver != B2MJ_SOL_PGS && h->dm.team_warps == 1 && !h->keep_intermediates) a.sync_stages = 1;
   if (const char* env = getenv("B2MJ_STAGE_SYNC")) a.sync_stages = atoi(env) ? 1 : 0;
   const size_t smem = h->smem_bytes / h->warps_per_cta * W;
   static const bool reorder = !getenv("B2MJ_NO_REORDER");
