@@ -707,6 +707,7 @@ int handle_launch(Handle* h, int mode, int nsteps, const double* ctrl_seq, doubl
   if (W >= 2 && h->model->opt.solver != B2MJ_SOL_PGS && h->dm.team_warps == 1 && !h->keep_intermediates) a.sync_stages = 1;
   if (const char* env = getenv("B2MJ_STAGE_SYNC")) a.sync_stages = atoi(env) ? 1 : 0;
   const size_t smem = h->smem_bytes / h->warps_per_cta * W;
+  h->last_warps_per_cta = W;
   static const bool reorder = !getenv("B2MJ_NO_REORDER");
   static const int order_legacy = getenv("B2MJ_ORDER_LEGACY") ? 1 : 0;
   static const bool order_sync = order_legacy || getenv("B2MJ_ORDER_SYNC");
@@ -1370,9 +1371,12 @@ int b2mj_launch_info(b2mj_handle* hh, b2mjLaunchInfo* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h || !out) return B2MJ_EINVAL;
   const DevModel& d = h->dm;
-  out->warps_per_cta = h->warps_per_cta;
-  out->ctas = (h->nenv + h->warps_per_cta - 1) / h->warps_per_cta;
-  out->smem_bytes_per_cta = (int)h->smem_bytes;
+  // the shape of the most recent launch (per-step launches of long batches and fused rollouts use the wide lock-stepped
+  // CTA), else the per-step shape chosen at create time
+  const int W = h->last_warps_per_cta > 0 ? h->last_warps_per_cta : h->warps_per_cta;
+  out->warps_per_cta = W;
+  out->ctas = (h->nenv + W - 1) / W;
+  out->smem_bytes_per_cta = (int)(h->smem_bytes / h->warps_per_cta * W);
   out->arena_doubles_per_env = d.arena_g_doubles;
   out->arena_in_smem = h->arena_in_smem;
   // bytes the fused step moves per env: load A+B, store B+C

@@ -47,6 +47,7 @@ struct Handle {
 
   int warps_per_cta = 4;
   int resident_envs = 0;          // envs the whole GPU keeps resident at the step launch shape (make_layout)
+  int last_warps_per_cta = 0;     // shape of the most recent step / rollout launch (b2mj_launch_info reports it)
   int rollout_warps_per_cta = 0;  // CTA shape of the static fused rollout (lock-stepped stages), 0 = same as steps
   size_t smem_bytes = 0;
   size_t smem_target_bytes = 0;   // 0 = default policy
