@@ -233,6 +233,14 @@ static int upload_model(Handle* h) {
   return 0;
 }
 
+// largest contact dimension the model can produce (geom condim, explicit pair dim): sizes the per-contact cone Hessian
+static int model_max_condim(const b2mjModel* m) {
+  int mx = 1;
+  for (int g = 0; g < m->ngeom; g++) mx = std::max(mx, m->geom_condim[g]);
+  for (int p = 0; p < m->npair; p++) mx = std::max(mx, m->pair_dim[p]);
+  return std::min(mx, 6);
+}
+
 static int check_supported(const b2mjModel* m) {
   for (int p = 0; p < m->ncollpair; p++) {
     const int t1 = m->geom_type[m->collpair_geom1[p]], t2 = m->geom_type[m->collpair_geom2[p]];
@@ -315,9 +323,12 @@ static int make_layout(Handle* h) {
   d.team_warps = (newton && nv >= B2K_TEAM_MIN_NV && m->opt.noslip_iterations <= 0 && !getenv("B2MJ_NO_TEAM")) ? B2K_TEAM_WARPS : 1;
   if (d.team_warps > 1 && getenv("B2MJ_TEAM_WARPS")) d.team_warps = std::max(2, std::min(16, atoi(getenv("B2MJ_TEAM_WARPS"))));
   d.ldh = nv | 1;  // odd: lanes walking a column (or owning a row each) hit distinct shared-memory banks
-  xs[XF_NEWTON_H] = newton ? nv * d.ldh : 0;
+  xs[XF_NEWTON_H] = !newton ? 0 : d.team_warps > 1 ? nv * (nv + 1) / 2 : nv * d.ldh;  // team mode: packed lower triangle
   xs[XF_JCOLS] = d.team_warps > 1 ? (m->njmax * 17 + 7) / 8 : 0;
-  xs[XF_CONTACT_H] = (newton && m->opt.cone == B2MJ_CONE_ELLIPTIC) ? 36 * m->nconmax : 0;
+  // cone Hessian blocks: dim x dim per contact, dim <= the largest condim of the model (9 doubles for condim 3, not the
+  // 36 of condim 6: C5's 160 contact slots shrink from 46 KB to 11.5 KB and come on chip)
+  d.conh_stride = model_max_condim(m) * model_max_condim(m);
+  xs[XF_CONTACT_H] = (newton && m->opt.cone == B2MJ_CONE_ELLIPTIC) ? d.conh_stride * m->nconmax : 0;
   xs[XF_SUBTREE_LINVEL] = d.need_subtreevel ? 3 * m->nbody : 0;
   xs[XF_SUBTREE_ANGMOM] = d.need_subtreevel ? 3 * m->nbody : 0;
   xs[XF_BODYVEL] = d.need_subtreevel ? 6 * m->nbody : 0;
@@ -1228,6 +1239,10 @@ int b2mj_model_update(b2mj_handle* hh, const b2mjModel* m) {
     return B2MJ_EINVAL;
   }
   if (int rc = check_supported(m)) return rc;
+  if (model_max_condim(m) * model_max_condim(m) > h->dm.conh_stride) {
+    set_error("b2mj_model_update: the edit raises the largest condim of the model (per-contact arrays are sized by it); create a new handle");
+    return B2MJ_EINVAL;
+  }
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   if (h->n_env_models) b2mj_set_env_models(hh, nullptr, 0, nullptr);  // a broadcast update replaces per-env variants
@@ -1296,6 +1311,10 @@ int b2mj_set_env_models(b2mj_handle* hh, const b2mjModel* const* models, int nmo
       return B2MJ_EINVAL;
     }
     if (int rc = check_supported(m)) return rc;
+    if (model_max_condim(m) * model_max_condim(m) > h->dm.conh_stride) {
+      set_error("b2mj_set_env_models: variant " + std::to_string(v) + " raises the largest condim of the model; create the handle from the variant with the largest condim");
+      return B2MJ_EINVAL;
+    }
     // topology (parents, addresses, types, pair table) and the reset pose are shared: only parameters may differ
     const bool same_topology =
         !std::memcmp(m->body_parentid, o->body_parentid, sizeof(int) * o->nbody) &&

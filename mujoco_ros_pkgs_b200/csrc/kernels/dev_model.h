@@ -73,7 +73,7 @@ enum XField {
   XF_EFC_JAREF,     // njmax
   XF_EFC_JV,        // njmax
   XF_EFC_QUAD,      // 3*njmax
-  XF_NEWTON_H,      // nv*nv
+  XF_NEWTON_H,      // nv*ldh; team mode: packed lower triangle, nv (nv + 1) / 2
   XF_CONTACT_H,     // 36*nconmax
   XF_SUBTREE_LINVEL,// 3*nbody
   XF_SUBTREE_ANGMOM,// 3*nbody
@@ -154,6 +154,7 @@ struct DevModel {
   int team_warps;          // warps per env: 1, or 8 for wide Newton models (team.cuh): one env per CTA, helpers on call
   int jwin_rows;           // rows the efc_J window holds (0 = no window)
   int ldh;                 // leading dimension of the Newton Hessian (odd in team mode: conflict-free column walks)
+  int conh_stride;         // doubles per contact in XF_CONTACT_H: (largest condim of the model)^2, not 36 (make_layout)
 };
 
 // fused publish (b2mj_step_publish): where the finished env's row goes in every rank's gathered slab

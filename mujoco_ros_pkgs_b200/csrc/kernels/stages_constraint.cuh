@@ -526,7 +526,7 @@ __device__ __noinline__ double constraintUpdate_warp(const Env e, int nefc, int 
         B2K_NOUNROLL for (int j = 1; j < dim; j++) P.force[i + j] = -f0 / T * U[j] * fri[j - 1];
         B2K_NOUNROLL for (int j = 0; j < dim; j++) P.state[i + j] = B2MJ_CSTATE_CONE;
         if (coneHessian) {
-          double* H = cH + 36 * c;
+          double* H = cH + c_dm.conh_stride * c;
           double g[6];
           g[0] = 0;
           B2K_NOUNROLL for (int j = 1; j < dim; j++) g[j] = U[j] * fri[j - 1] / T;

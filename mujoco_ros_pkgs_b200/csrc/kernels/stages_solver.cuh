@@ -801,7 +801,10 @@ __device__ __noinline__ void cholFactor_warp(const Env e, int n, int ld, double 
 // with eight branches per step (800 cycles per substitution step, 194 k cycles per solve at nv = 120, ~38 k at nv = 24).
 #define B2K_CHOL_SLOTS_MAX (B2K_NEWTON_MAX_NV / 32)
 // B2K_CHOL_SLOTS = register slots per lane: 1 serves n <= 32 without the predicated-off updates of the wider form
-template <bool SM, int B2K_CHOL_SLOTS>
+// PK: the factor is the packed lower triangle of team mode (team.cuh), row r at r (r + 1) / 2
+template <bool PK>
+__device__ __forceinline__ int hix(int r, int c, int ld) { return PK ? ((r * (r + 1)) >> 1) + c : r * ld + c; }
+template <bool SM, int B2K_CHOL_SLOTS, bool PK = false>
 __device__ __noinline__ void cholSolve_warpT(const Env e, int n, int ld) {
   // Mgrad = inv(H) grad on the solver's work vectors (XF_PRIMAL: Ma, Mv, grad, Mgrad, search, gradold, Mgradold, invdiag)
   const double* L = newtonH<SM>(e);
@@ -823,11 +826,11 @@ __device__ __noinline__ void cholSolve_warpT(const Env e, int n, int ld) {
         const int i = i0 + ii;
         const double yi = __shfl_sync(e.mask, t[bi], ii) * invd[i];
         if (lane == ii) t[bi] = yi;
-        else if (lane > ii && lane + i0 < n) t[bi] -= L[(lane + i0) * ld + i] * yi;
+        else if (lane > ii && lane + i0 < n) t[bi] -= L[hix<PK>(lane + i0, i, ld)] * yi;
 #pragma unroll
         for (int s = bi + 1; s < B2K_CHOL_SLOTS; s++) {
           const int k = lane + 32 * s;
-          if (k < n) t[s] -= L[k * ld + i] * yi;
+          if (k < n) t[s] -= L[hix<PK>(k, i, ld)] * yi;
         }
       }
     }
@@ -841,7 +844,7 @@ __device__ __noinline__ void cholSolve_warpT(const Env e, int n, int ld) {
       B2K_NOUNROLL for (int ii = cnt - 1; ii >= 0; ii--) {
         const int i = i0 + ii;
         const double xi = __shfl_sync(e.mask, t[bi], ii) * invd[i];
-        const double* Li = L + i * ld;
+        const double* Li = L + hix<PK>(i, 0, ld);
         if (lane == ii) t[bi] = xi;
         else if (lane < ii) t[bi] -= Li[lane + i0] * xi;
 #pragma unroll
@@ -924,7 +927,7 @@ __device__ __forceinline__ void hessianJTDJ_reg(const Env e, const PrimalCtx& c,
         for (int k = 0; k < NI; k++) s[k] += Dr * Jr[ij[k] & 255u] * Jr[ij[k] >> 8];
       } else if (st == B2MJ_CSTATE_CONE) {
         const int con = P.id[r], dim = c_dim[con];
-        const double* Hc = cH + 36 * con;
+        const double* Hc = cH + c_dm.conh_stride * con;
         // B = Hc J_block (dim x nv) once per cone, by the whole warp; an entry then needs dim products instead of
         // dim^2.  B(a, j) is formed with the loop order the entry-wise form used, so the sums are bitwise the same.
         double* Bm = e.X(XF_SCRATCH);  // dim * nv <= 6 nv doubles; free during the dense Newton solve
@@ -1012,7 +1015,7 @@ __device__ __noinline__ void primalHessianT(const Env e, PrimalCtx& c) {
         if (st == B2MJ_CSTATE_QUADRATIC) {
           s += P.D[r] * P.J[r * nv + i] * P.J[r * nv + j];
         } else {
-          const double* Hc = cH + 36 * P.id[r];
+          const double* Hc = cH + c_dm.conh_stride * P.id[r];
           B2K_NOUNROLL for (int p = 0; p < dim; p++) {
             const double Ja = P.J[(r + p) * nv + i];
             if (Ja == 0) continue;
@@ -1045,7 +1048,9 @@ __device__ void primalGradient(const Env e, PrimalCtx& c) {
   FORL(i, c.nv) c.grad[i] = c.Ma[i] - qs[i] - qc[i];
   WSYNC();
   if (c.newton) {
-    if (c_dm.xoff_s[XF_NEWTON_H] >= 0) {
+    if (c_dm.team_warps > 1) {  // team mode: packed factor in shared memory
+      cholSolve_warpT<true, B2K_CHOL_SLOTS_MAX, true>(e, c.nv, c_dm.ldh);
+    } else if (c_dm.xoff_s[XF_NEWTON_H] >= 0) {
       if (c.nv <= 32) cholSolve_warpT<true, 1>(e, c.nv, c_dm.ldh);
       else cholSolve_warpT<true, B2K_CHOL_SLOTS_MAX>(e, c.nv, c_dm.ldh);
     } else {
