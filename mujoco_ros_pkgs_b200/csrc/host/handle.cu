@@ -475,6 +475,7 @@ static int make_layout(Handle* h) {
     const int E = Etarget;
     for (const Cand& c : cands) { if (c.is_x) xcold[c.id] = 1; else cold[c.id] = 1; }
     xs[XF_JWIN] = 0;
+    xs[XF_JVALS] = 0;
     int promote_left = getenv("B2MJ_PROMOTE_MAX") ? atoi(getenv("B2MJ_PROMOTE_MAX")) : 1 << 30;  // experiment knob
     auto promote = [&](const std::vector<std::pair<int, int>>& list) {
     for (const auto& o : list) {
@@ -488,7 +489,16 @@ static int make_layout(Handle* h) {
       else promote_left--;
     }
     };
-    promote(order);
+    // team mode sizes its mirror of the Jacobian entries (below) right after the per-iteration arrays, ahead of the
+    // once-per-step ones at the tail of `order`
+    std::vector<std::pair<int, int>> hot_order, warm_order;
+    for (const auto& o : order) {
+      const bool warm = !o.first && (o.second == B2MJ_F_EFC_B || o.second == B2MJ_F_EFC_J || o.second == B2MJ_F_EFC_VEL ||
+                                     o.second == B2MJ_F_EFC_POS || o.second == B2MJ_F_EFC_MARGIN);
+      (warm ? warm_order : hot_order).push_back(o);
+    }
+    const bool jvals_first = d.team_warps > 1 && !no_promote && !getenv("B2MJ_NO_JVALS");
+    if (jvals_first) promote(hot_order); else promote(order);
     // primal solvers: whatever shared memory is still free at this residency becomes a window for the ACTIVE rows of
     // efc_J (stages_constraint.cuh::solveJ), when the full njmax-row Jacobian itself stayed in L2
     d.jwin_rows = 0;
@@ -502,6 +512,22 @@ static int make_layout(Handle* h) {
       // (rows beyond what a step ever uses would only crowd out the cold arrays below: cap at 64)
       d.jwin_rows = lo >= 4 ? std::min(lo, 64) : 0;
       xs[XF_JWIN] = d.jwin_rows ? 2 + d.jwin_rows * nv : 0;
+    }
+    // team mode: the non-zero entries of efc_J rows (at most 16 per row, the column lists of XF_JCOLS) mirrored in
+    // shared memory for as many rows as fit -- the J' D J build, J v and J' f then read LDS instead of paying an L2 round
+    // trip per constraint row on a serial chain (team.cuh)
+    d.jvals_rows = 0;
+    xs[XF_JVALS] = 0;
+    if (jvals_first) {
+      int lo = 0, hi = m->njmax;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        xs[XF_JVALS] = mid * 16;
+        if (envs_per_sm(nullptr) >= E) lo = mid; else hi = mid - 1;
+      }
+      d.jvals_rows = lo >= 32 ? lo : 0;
+      xs[XF_JVALS] = d.jvals_rows * 16;
+      promote(warm_order);
     }
     // the rest, smallest first
     promote(rest_order);
@@ -592,7 +618,7 @@ static int make_layout(Handle* h) {
     static const char* xnames[] = {"QLOC", "QH", "QHDIAGINV", "EFC_MINVJT", "EFC_ARDIAG", "VEC0", "VEC1", "VEC2", "VEC3", "VEC4",
                                    "VEC5", "EFC_JAREF", "EFC_JV", "EFC_QUAD", "NEWTON_H", "CONTACT_H", "SUBTREE_LINVEL",
                                    "SUBTREE_ANGMOM", "BODYVEL", "RK_X0", "RK_XF", "RK_F", "RK_DX", "SCRATCH", "QW", "QHW",
-                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS", "TRI", "IMPL_LU", "IMPL_D"};
+                                   "EFC_AR", "MINV", "HINV", "PRIMAL", "EFC_AR_S", "JWIN", "JCOLS", "TRI", "IMPL_LU", "IMPL_D", "JVALS"};
     fprintf(stderr, "[b2mj layout] record %d doubles; shared arena %d doubles + %d ints per env\n", d.rec_end, d.arena_s_doubles,
             d.arena_s_ints);
     for (int f = 0; f < B2MJ_NFIELD; f++)

@@ -95,6 +95,7 @@ enum XField {
   XF_TRI,           // pair table of a row-major lower triangle of order nv, packed a | b << 8 in 16 bits (cholPairTable)
   XF_IMPL_LU,       // implicit integrator: nv*nv dense M - h qDeriv and its LU factors (always in the HBM/L2 arena)
   XF_IMPL_D,        // implicit integrator: 6*nbody*nv body-force derivatives d cfrc / d qvel (always in the HBM/L2 arena)
+  XF_JVALS,         // team mode: the non-zero entries of the first jvals_rows rows of efc_J, [row][16] aligned with XF_JCOLS
   XF_COUNT
 };
 
@@ -153,6 +154,7 @@ struct DevModel {
   unsigned char collfunc[64];  // narrowphase override per geom-type pair [t1 * 8 + t2]: B2MJ_COLLFN_* (0 = built in)
   int team_warps;          // warps per env: 1, or 8 for wide Newton models (team.cuh): one env per CTA, helpers on call
   int jwin_rows;           // rows the efc_J window holds (0 = no window)
+  int jvals_rows;          // team mode: rows of efc_J whose non-zero entries are mirrored in shared memory (XF_JVALS)
   int ldh;                 // leading dimension of the Newton Hessian (odd in team mode: conflict-free column walks)
   int conh_stride;         // doubles per contact in XF_CONTACT_H: (largest condim of the model)^2, not 36 (make_layout)
 };

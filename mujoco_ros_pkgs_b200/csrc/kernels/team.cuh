@@ -50,6 +50,8 @@ __device__ __forceinline__ TeamCtl* team_ctl() {
   return reinterpret_cast<TeamCtl*>(b2k_smem + (size_t)team_slot() * B2K_TEAM_HDR + 16);
 }
 __device__ __forceinline__ unsigned char* team_jcols(const Env e) { return reinterpret_cast<unsigned char*>(e.X(XF_JCOLS)); }
+// XF_JVALS: J[r][cols[a]] for the first jvals_rows rows, [row][B2K_JCOLS_K], aligned with the row's column list
+__device__ __forceinline__ double* team_jvals(const Env e) { return e.X(XF_JVALS); }
 
 // ---- TEAM_JCOLS: per constraint row the sorted list of columns where the row (or, for a row of an elliptic contact,
 // any row of that contact) is non-zero.  One warp per row, ballot compaction over 32-column chunks.
@@ -78,6 +80,10 @@ __device__ void team_build_jcols(const Env e, int nefc) {
       nnz += __popc(b);
     }
     if (lane == 0) row[0] = (unsigned char)(nnz > B2K_JCOLS_K ? 255 : nnz);
+    if (r < m.jvals_rows && nnz <= B2K_JCOLS_K) {  // mirror the row's entries at the listed columns (one L2 trip, all rows in flight)
+      __syncwarp();
+      if (lane < nnz) team_jvals(e)[(size_t)r * B2K_JCOLS_K + lane] = J[(size_t)r * nv + row[1 + lane]];
+    }
   }
 }
 
@@ -122,8 +128,14 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
       // inside the accumulation loop made the build a chain of dependent L2 gathers (465 k cycles per build).
       const int myc = lane < nnz ? row[1 + lane] : -1;
       double jv[6], wv[6];
+      if (r + dim <= m.jvals_rows) {  // the block's entries are mirrored in shared memory
+        const double* jvs = team_jvals(e) + (size_t)r * B2K_JCOLS_K + lane;
 #pragma unroll
-      for (int p = 0; p < 6; p++) jv[p] = (p < dim && myc >= 0) ? Jr[p * nv + myc] : 0.0;
+        for (int p = 0; p < 6; p++) jv[p] = (p < dim && myc >= 0) ? jvs[p * B2K_JCOLS_K] : 0.0;
+      } else {
+#pragma unroll
+        for (int p = 0; p < 6; p++) jv[p] = (p < dim && myc >= 0) ? Jr[p * nv + myc] : 0.0;
+      }
       if (st == B2MJ_CSTATE_CONE) {
         const double* Hc = cH + c_dm.conh_stride * P.id[r];
 #pragma unroll
@@ -247,7 +259,10 @@ __device__ __forceinline__ void mulJacVec_sparse(const Env e, int nefc, double* 
     const unsigned char* row = jc + (size_t)i * B2K_JCOLS_STRIDE;
     const double* Ji = J + (size_t)i * nv;
     double s = 0;
-    if (row[0] != 255) {
+    if (row[0] != 255 && i < c_dm.jvals_rows) {
+      const double* jvs = team_jvals(e) + (size_t)i * B2K_JCOLS_K;
+      for (int a = 0; a < row[0]; a++) s += jvs[a] * vec[row[1 + a]];
+    } else if (row[0] != 255) {
       for (int a = 0; a < row[0]; a++) { const int k = row[1 + a]; s += Ji[k] * vec[k]; }
     } else {
       for (int k = 0; k < nv; k++) s += Ji[k] * vec[k];
@@ -268,7 +283,9 @@ __device__ __forceinline__ void mulJacTVec_sparse(const Env e, int nefc, double*
     if (fi == 0) continue;
     const unsigned char* row = jc + (size_t)i * B2K_JCOLS_STRIDE;
     const double* Ji = J + (size_t)i * nv;
-    if (row[0] != 255) {
+    if (row[0] != 255 && i < c_dm.jvals_rows) {
+      if (e.lane < row[0]) res[row[1 + e.lane]] += team_jvals(e)[(size_t)i * B2K_JCOLS_K + e.lane] * fi;
+    } else if (row[0] != 255) {
       if (e.lane < row[0]) { const int k = row[1 + e.lane]; res[k] += Ji[k] * fi; }
     } else {
       FORL(k, nv) res[k] += Ji[k] * fi;
