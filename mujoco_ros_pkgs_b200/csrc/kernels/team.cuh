@@ -87,6 +87,42 @@ __device__ void team_build_jcols(const Env e, int nefc) {
   }
 }
 
+// One sparse constraint row (DIM = 1, D_r J_r' J_r) or elliptic-cone block (DIM = contact dimension, J_b' Hc J_b) added to the
+// H rows this warp owns.  Lane b holds column cols[b] of the block; the J entries of an owned row come from the lane that
+// holds that column, by shuffle.  DIM is a template constant so that the 6 x 6 worst case costs nothing at dim 3 (the
+// run-time-bounded form predicated 36 multiply-adds and 6 shuffles per owned row off and on: 3.1 k cycles per block);
+// the sums are formed in the order of that form.
+template <int DIM, bool CONE>
+__device__ __forceinline__ void team_jtdj_sparse(double* H, const double* jvsrc, int jvstride, const double* Hc, double Dr, int myc,
+                                                 bool own) {
+  double jv[DIM], wv[DIM];
+#pragma unroll
+  for (int p = 0; p < DIM; p++) jv[p] = myc >= 0 ? jvsrc[p * jvstride] : 0.0;
+  if (CONE) {
+#pragma unroll
+    for (int p = 0; p < DIM; p++) {
+      double u = 0;
+#pragma unroll
+      for (int q = 0; q < DIM; q++) u += Hc[p * DIM + q] * jv[q];
+      wv[p] = u;
+    }
+  }
+  unsigned mine = __ballot_sync(0xffffffffu, own);
+  while (mine) {
+    const int a = __ffs(mine) - 1;
+    mine &= mine - 1;
+    const int i = __shfl_sync(0xffffffffu, myc, a);
+    double acc = 0;
+    if (!CONE) {
+      acc = (Dr * __shfl_sync(0xffffffffu, jv[0], a)) * jv[0];
+    } else {
+#pragma unroll
+      for (int p = 0; p < DIM; p++) acc += __shfl_sync(0xffffffffu, jv[p], a) * wv[p];
+    }
+    if (myc >= 0 && myc <= i) H[(((i) * ((i) + 1)) >> 1) + myc] += acc;
+  }
+}
+
 // ---- TEAM_HESSIAN_CHOL
 // The team's Hessian is the PACKED lower triangle, row i at i (i + 1) / 2: 58 KB instead of 116 KB at nv = 120, which is
 // what lets the rest of the solver's working set (cone blocks, efc_type / id, friction) share the SM's shared memory
@@ -96,6 +132,7 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
   const DevModel& m = c_dm;
   const int nv = m.nv, T = team_T(), tid = team_tid(), w = tid >> 5, lane = tid & 31, TW = m.team_warps;
   double* H = e.X(XF_NEWTON_H);  // team mode: always in the shared arena (make_layout), addressed as shared memory
+  const bool pow2 = (TW & (TW - 1)) == 0;
   double* invd = e.X(XF_PRIMAL) + 7 * nv;
   const double* qM = e.D(B2MJ_F_QM);
   EfcPtrs P = efcPtrs(e);
@@ -127,46 +164,17 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
       // values J[.][i] of an owned H row i then come from the lane that holds column i, by shuffle.  Fetching them
       // inside the accumulation loop made the build a chain of dependent L2 gathers (465 k cycles per build).
       const int myc = lane < nnz ? row[1 + lane] : -1;
-      double jv[6], wv[6];
-      if (r + dim <= m.jvals_rows) {  // the block's entries are mirrored in shared memory
-        const double* jvs = team_jvals(e) + (size_t)r * B2K_JCOLS_K + lane;
-#pragma unroll
-        for (int p = 0; p < 6; p++) jv[p] = (p < dim && myc >= 0) ? jvs[p * B2K_JCOLS_K] : 0.0;
+      const bool own = myc >= 0 && (pow2 ? (myc & (TW - 1)) : (myc % TW)) == w;
+      const bool mirrored = r + dim <= m.jvals_rows;  // the block's entries are in shared memory (XF_JVALS)
+      const double* jvsrc = mirrored ? team_jvals(e) + (size_t)r * B2K_JCOLS_K + lane : Jr + max(myc, 0);
+      const int jvstride = mirrored ? B2K_JCOLS_K : nv;
+      if (st == B2MJ_CSTATE_QUADRATIC) {
+        team_jtdj_sparse<1, false>(H, jvsrc, jvstride, nullptr, P.D[r], myc, own);
       } else {
-#pragma unroll
-        for (int p = 0; p < 6; p++) jv[p] = (p < dim && myc >= 0) ? Jr[p * nv + myc] : 0.0;
-      }
-      if (st == B2MJ_CSTATE_CONE) {
         const double* Hc = cH + c_dm.conh_stride * P.id[r];
-#pragma unroll
-        for (int p = 0; p < 6; p++) {
-          double u = 0;
-          if (p < dim) {
-#pragma unroll
-            for (int q = 0; q < 6; q++)
-              if (q < dim) u += Hc[p * dim + q] * jv[q];
-          }
-          wv[p] = u;
-        }
-      } else {
-        const double Dr = P.D[r];
-#pragma unroll
-        for (int p = 0; p < 6; p++) wv[p] = Dr;
-      }
-      unsigned mine = __ballot_sync(0xffffffffu, myc >= 0 && (myc % TW) == w);
-      while (mine) {
-        const int a = __ffs(mine) - 1;
-        mine &= mine - 1;
-        const int i = __shfl_sync(0xffffffffu, myc, a);
-        double acc = 0;
-        if (st == B2MJ_CSTATE_QUADRATIC) {
-          acc = (wv[0] * __shfl_sync(0xffffffffu, jv[0], a)) * jv[0];
-        } else {
-#pragma unroll
-          for (int p = 0; p < 6; p++)
-            if (p < dim) acc += __shfl_sync(0xffffffffu, jv[p], a) * wv[p];
-        }
-        if (myc >= 0 && myc <= i) H[TRI(i) + myc] += acc;
+        if (dim == 3) team_jtdj_sparse<3, true>(H, jvsrc, jvstride, Hc, 0.0, myc, own);
+        else if (dim == 4) team_jtdj_sparse<4, true>(H, jvsrc, jvstride, Hc, 0.0, myc, own);
+        else if (dim == 6) team_jtdj_sparse<6, true>(H, jvsrc, jvstride, Hc, 0.0, myc, own);
       }
     } else {
       // dense row / block: every owned H row i, lanes over the columns j <= i
@@ -204,12 +212,20 @@ __device__ void team_hessian_chol(const Env e, int nefc, bool cone) {
     for (int i = j + 1 + tid; i < nv; i += T) H[TRI(i) + j] *= inv;
     team_bar();
     if (tid == 0) { H[TRI(j) + j] = ljj; invd[j] = inv; }
-    // trailing update: one warp per row i, lanes over the columns j < k <= i
-    for (int i = j + 1 + w; i < nv; i += TW) {
+    // trailing update: a warp takes rows i and i + TW together (two independent chains in flight and one load of
+    // L(k, j) serving both), lanes over the columns j < k <= i.  Every entry still sees exactly one subtraction per pivot.
+    for (int i = j + 1 + w; i < nv; i += 2 * TW) {
+      const int i2 = i + TW;
       double* Hi = H + TRI(i);
-      const double lij = Hi[j];
-      if (lij == 0) continue;  // block structure: most of a contact-sparse factor is exact zeros
-      for (int k = j + 1 + lane; k <= i; k += 32) Hi[k] -= lij * H[TRI(k) + j];
+      double* Hi2 = H + TRI(i2 < nv ? i2 : i);
+      const double lij = Hi[j], lij2 = i2 < nv ? Hi2[j] : 0.0;
+      // block structure: most of a contact-sparse factor is exact zeros
+      const int kend = lij2 != 0 ? i2 : (lij != 0 ? i : -1);
+      for (int k = j + 1 + lane; k <= kend; k += 32) {
+        const double lkj = H[TRI(k) + j];
+        if (lij != 0 && k <= i) Hi[k] -= lij * lkj;
+        if (lij2 != 0) Hi2[k] -= lij2 * lkj;
+      }
     }
     team_bar();
   }
