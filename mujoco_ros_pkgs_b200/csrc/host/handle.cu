@@ -537,8 +537,8 @@ static int make_layout(Handle* h) {
     // The wave count is a crude model of a launch whose envs differ 3x in cost.  Measured on C4 (2048 humanoid envs):
     // at 5 envs/SM only the Hessian fits on chip and every access of the line search / update to Jaref, Jv, quad, D,
     // state, force is an L2 round trip: 1.20 M env-steps/s per step; at 4 envs/SM the whole hot set is in shared memory:
-    // 1.26 M (fused rollout 1.41 M against 1.21 M); 3 envs/SM 1.06 M.  So from five envs per SM on, one env of
-    // residency is given up when that is what brings the solver's per-iteration working set on chip
+    // 1.26 M (fused rollout 1.41 M against 1.21 M); 3 envs/SM 1.06 M.  So from five envs per SM on, one or two envs
+    // of residency are given up when that is what brings the solver's per-iteration working set on chip
     // (profiles/r2c_shape_sweep.txt).
     auto hot_on_chip = [&]() {
       for (int x : {XF_NEWTON_H, XF_EFC_JAREF, XF_EFC_JV, XF_EFC_QUAD})
@@ -548,8 +548,14 @@ static int make_layout(Handle* h) {
       return true;
     };
     if (!pgs && d.team_warps == 1 && E >= 5 && !getenv("B2MJ_ENVS_PER_SM") && !getenv("B2MJ_NO_HOTSET_TRADE") && !hot_on_chip()) {
-      place(E - 1);
-      if (!hot_on_chip()) place(E);
+      // (up to two envs: 1536 hand envs would run 6 per SM with nothing but H on chip, 0.398 M env-steps/s; 5 per SM
+      // still leaves type / id / friction in L2, 0.421 M; 4 per SM 0.445 M)
+      bool ok = false;
+      for (int Et = E - 1; Et >= std::max(4, E - 2) && !ok; Et--) {
+        place(Et);
+        ok = hot_on_chip();
+      }
+      if (!ok) place(E);
     }
   }
   // global (full) arena offsets (after every size is final: the efc_J window above is sized last)
