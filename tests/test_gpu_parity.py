@@ -506,7 +506,9 @@ def test_step_host_zero_copy_with_pinned_buffers(load_model, BatchSim):
 
 def test_launch_order_does_not_change_results(tmp_path):
     """The heaviest-first launch order (b2k_order_kernel) only permutes which warp runs which env: a contact-rich
-    2048-env run must be bitwise identical with the reordering disabled (B2MJ_NO_REORDER=1, separate process)."""
+    4096-env run (two waves: the order is refreshed after every step, on the side stream for this small model) must be
+    bitwise identical with the synchronous refresh (B2MJ_ORDER_SYNC=1) and with the reordering disabled
+    (B2MJ_NO_REORDER=1); separate processes, the switches are read once."""
     import subprocess
     import sys
 
@@ -517,7 +519,7 @@ def test_launch_order_does_not_change_results(tmp_path):
         "from mujoco_ros_pkgs_b200.batch import BatchSim\n"
         "m = _capi.Model.from_xml_file(%r)\n"
         "rng = np.random.default_rng(2)\n"
-        "n = 2048\n"
+        "n = 4096\n"
         "sim = BatchSim(m, n)\n"
         "sim.set('qpos', np.tile(m.qpos0, (n, 1)) + rng.uniform(-0.3, 0.3, (n, m.nq)))\n"
         "lo, hi = m.actuator_ctrlrange[:, 0], m.actuator_ctrlrange[:, 1]\n"
@@ -528,10 +530,11 @@ def test_launch_order_does_not_change_results(tmp_path):
         "np.save(sys.argv[1], np.concatenate([sim.get('qpos'), sim.get('qvel'), sim.get('nefc').astype(float)], axis=1))\n"
     ) % (ROOT, os.path.join(ROOT, "mujoco_ros_pkgs_b200", "models", "panda_like.xml"))
     outs = []
-    for tag, extra in (("on", {}), ("off", {"B2MJ_NO_REORDER": "1"})):
+    for tag, extra in (("on", {}), ("sync", {"B2MJ_ORDER_SYNC": "1"}), ("off", {"B2MJ_NO_REORDER": "1"})):
         out = str(tmp_path / f"state_{tag}.npy")
         env = dict(os.environ, **extra)
         subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=600)
         outs.append(np.load(out))
     assert outs[0][:, -1].max() >= 8, "the run should reach contact-rich states"
-    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
+    np.testing.assert_array_equal(outs[1], outs[2])
