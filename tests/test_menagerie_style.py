@@ -190,3 +190,184 @@ def test_menagerie_style_panda_gpu_parity(panda, capi, orc):
     sim.keep_intermediates(False)
     worst, _ = injected_steps(model, sim, oracles, 150, np.random.default_rng(3), tag="menagerie-panda")
     assert worst < 1e-5
+
+
+# ---- a menagerie-style Shadow Hand (public structure of mujoco_menagerie/shadow_hand/right_hand.xml, one finger kept):
+# four levels of nested default classes, <position> actuators whose kp / ctrlrange / forcerange come from the joint's class,
+# a class on the mesh assets, impratio + elliptic cones, a coupled-joint tendon actuator, a contact exclude, sensors
+HAND_XML = r'''<mujoco model="right_shadow_hand">
+  <compiler angle="radian" meshdir="assets" autolimits="true"/>
+  <option impratio="10" cone="elliptic"/>
+  <default>
+    <default class="right_hand">
+      <mesh scale="1 1 1"/>
+      <joint axis="1 0 0" damping="0.05" armature="0.0002" frictionloss="0.01"/>
+      <position forcerange="-1 1"/>
+      <default class="wrist">
+        <joint damping="0.5"/>
+        <default class="wrist_y">
+          <joint axis="0 1 0" range="-0.523599 0.174533"/>
+          <position kp="10" ctrlrange="-0.523599 0.174533" forcerange="-10 10"/>
+        </default>
+        <default class="wrist_x">
+          <joint range="-0.698132 0.488692"/>
+          <position kp="8" ctrlrange="-0.698132 0.488692" forcerange="-5 5"/>
+        </default>
+      </default>
+      <default class="knuckle">
+        <joint axis="0 -1 0" range="-0.349066 0.349066"/>
+        <position kp="1" ctrlrange="-0.349066 0.349066"/>
+      </default>
+      <default class="proximal">
+        <joint range="-0.261799 1.5708"/>
+        <position kp="1" ctrlrange="-0.261799 1.5708"/>
+      </default>
+      <default class="middle_distal">
+        <joint range="0 1.5708"/>
+        <position kp="1" ctrlrange="0 3.1415"/>
+      </default>
+      <default class="plastic">
+        <geom solimp="0.5 0.99 0.0001" solref="0.005 1"/>
+        <default class="plastic_visual">
+          <geom type="mesh" material="black" contype="0" conaffinity="0" group="2"/>
+        </default>
+        <default class="plastic_collision">
+          <geom group="3"/>
+        </default>
+      </default>
+    </default>
+  </default>
+  <asset>
+    <material name="black" specular="0.5" shininess="0.25" rgba="0.16355 0.16355 0.16355 1"/>
+    <mesh class="right_hand" file="forearm_collision.obj"/>
+    <mesh class="right_hand" file="palm.obj"/>
+    <mesh class="right_hand" file="f_proximal.obj"/>
+    <mesh class="right_hand" file="f_distal_pst.obj"/>
+  </asset>
+  <contact>
+    <exclude body1="rh_wrist" body2="rh_forearm"/>
+  </contact>
+  <worldbody>
+    <body name="rh_forearm" childclass="right_hand" quat="0 1 0 1" pos="0 0 0.3">
+      <inertial mass="3" pos="0 0 0.09" diaginertia="0.0138 0.0138 0.00744"/>
+      <geom class="plastic_visual" mesh="forearm_collision"/>
+      <geom class="plastic_collision" type="mesh" mesh="forearm_collision"/>
+      <body name="rh_wrist" pos="0.01 0 0.21301" quat="1 0 0 1">
+        <inertial mass="0.1" pos="0 0 0.029" quat="0.5 0.5 0.5 0.5" diaginertia="6.4e-05 4.38e-05 3.5e-05"/>
+        <joint class="wrist_y" name="rh_WRJ2"/>
+        <geom class="plastic_collision" size="0.0135 0.015" quat="1 1 0 0" type="capsule"/>
+        <body name="rh_palm" pos="0 0 0.034">
+          <inertial mass="0.3" pos="0 0 0.035" quat="1 0 0 1" diaginertia="0.0005287 0.0003581 0.000191"/>
+          <joint class="wrist_x" name="rh_WRJ1"/>
+          <site name="grasp_site" pos="0 -.035 0.09" group="4"/>
+          <geom class="plastic_visual" mesh="palm"/>
+          <geom class="plastic_collision" size="0.031 0.0035 0.049" pos="0.011 0.0085 0.038" type="box"/>
+          <body name="rh_ffknuckle" pos="0.033 0 0.095">
+            <inertial mass="0.008" pos="0 0 0" quat="0.5 0.5 -0.5 0.5" diaginertia="3.2e-07 2.6e-07 2.6e-07"/>
+            <joint class="knuckle" name="rh_FFJ4"/>
+            <body name="rh_ffproximal">
+              <inertial mass="0.03" pos="0 0 0.0225" quat="1 0 0 1" diaginertia="1e-05 9.8e-06 1.8e-06"/>
+              <joint class="proximal" name="rh_FFJ3"/>
+              <geom class="plastic_visual" mesh="f_proximal"/>
+              <geom class="plastic_collision" size="0.009 0.02" pos="0 0 0.025" type="capsule"/>
+              <body name="rh_ffmiddle" pos="0 0 0.045">
+                <inertial mass="0.017" pos="0 0 0.0125" quat="1 0 0 1" diaginertia="2.7e-06 2.6e-06 8.7e-07"/>
+                <joint class="middle_distal" name="rh_FFJ2"/>
+                <geom class="plastic_collision" size="0.009 0.0125" pos="0 0 0.0125" type="capsule"/>
+                <body name="rh_ffdistal" pos="0 0 0.025">
+                  <inertial mass="0.013" pos="0 0 0.0130769" quat="1 0 0 1" diaginertia="1.28092e-06 1.12092e-06 5.3e-07"/>
+                  <joint class="middle_distal" name="rh_FFJ1"/>
+                  <geom class="plastic_visual" mesh="f_distal_pst"/>
+                  <geom class="plastic_collision" type="mesh" mesh="f_distal_pst"/>
+                </body>
+              </body>
+            </body>
+          </body>
+        </body>
+      </body>
+    </body>
+    <geom name="floor" type="plane" size="0 0 0.05"/>
+  </worldbody>
+  <tendon>
+    <fixed name="rh_FFT1">
+      <joint joint="rh_FFJ2" coef="1"/>
+      <joint joint="rh_FFJ1" coef="1"/>
+    </fixed>
+  </tendon>
+  <actuator>
+    <position name="rh_A_WRJ2" joint="rh_WRJ2" class="wrist_y"/>
+    <position name="rh_A_WRJ1" joint="rh_WRJ1" class="wrist_x"/>
+    <position name="rh_A_FFJ4" joint="rh_FFJ4" class="knuckle"/>
+    <position name="rh_A_FFJ3" joint="rh_FFJ3" class="proximal"/>
+    <position name="rh_A_FFJ0" tendon="rh_FFT1" class="middle_distal"/>
+  </actuator>
+  <sensor>
+    <jointpos name="rh_FFJ3_pos" joint="rh_FFJ3"/>
+    <actuatorfrc name="rh_A_FFJ0_frc" actuator="rh_A_FFJ0"/>
+  </sensor>
+</mujoco>
+'''
+
+
+def _write_hand_assets(d):
+    (d / "assets").mkdir(exist_ok=True)
+    faces = [(0, 1, 3), (0, 3, 2), (4, 6, 7), (4, 7, 5), (0, 4, 5), (0, 5, 1), (2, 3, 7), (2, 7, 6), (0, 2, 6), (0, 6, 4), (1, 5, 7),
+             (1, 7, 3)]
+    for n, h in [("forearm_collision", (0.03, 0.03, 0.08)), ("palm", (0.04, 0.01, 0.05)), ("f_proximal", (0.008, 0.008, 0.02)),
+                 ("f_distal_pst", (0.007, 0.007, 0.012))]:
+        c = [(sx * h[0], sy * h[1], sz * h[2]) for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]
+        (d / "assets" / f"{n}.obj").write_text("# v\n" + "".join(f"v {v[0]} {v[1]} {v[2]}\n" for v in c) +
+                                              "".join(f"f {a + 1} {b + 1} {e + 1}\n" for a, b, e in faces))
+
+
+@pytest.fixture()
+def hand(capi, tmp_path):
+    _write_hand_assets(tmp_path)
+    p = tmp_path / "hand.xml"
+    p.write_text(HAND_XML)
+    return capi.Model.from_xml_file(str(p))
+
+
+def test_menagerie_style_shadow_hand_compiles_verbatim(hand):
+    m = hand
+    assert (m.nq, m.nv, m.nu, m.nbody, m.ngeom, m.ntendon, m.nexclude, m.nsensor) == (6, 6, 5, 8, 11, 1, 1, 2)
+    assert (m.opt.impratio, m.opt.cone) == (10.0, 1)
+    # class chain right_hand -> wrist -> wrist_y / wrist_x; right_hand -> knuckle / proximal / middle_distal
+    np.testing.assert_allclose(m.dof_damping, [0.5, 0.5, 0.05, 0.05, 0.05, 0.05])
+    np.testing.assert_allclose(m.dof_frictionloss, 0.01)
+    np.testing.assert_allclose(m.dof_armature, 0.0002)
+    np.testing.assert_allclose(m.jnt_axis, [[0, 1, 0], [1, 0, 0], [0, -1, 0], [1, 0, 0], [1, 0, 0], [1, 0, 0]])
+    np.testing.assert_allclose(m.jnt_range[:, 1], [0.174533, 0.488692, 0.349066, 1.5708, 1.5708, 1.5708])
+    # <position class=...>: kp as gain and -kp as the position bias, limits from the class, the tendon-driven one too
+    np.testing.assert_allclose(m.actuator_gainprm[:, 0], [10, 8, 1, 1, 1])
+    np.testing.assert_allclose(m.actuator_biasprm[:, 1], [-10, -8, -1, -1, -1])
+    np.testing.assert_allclose(m.actuator_forcerange, [[-10, 10], [-5, 5], [-1, 1], [-1, 1], [-1, 1]])
+    np.testing.assert_allclose(m.actuator_ctrlrange[4], [0, 3.1415])
+    assert m.actuator_trntype.tolist() == [0, 0, 0, 0, 3]
+    # plastic class on every hand geom (visual ones do not collide); the floor keeps the global defaults
+    assert m.geom_contype.tolist() == [1, 0, 1, 1, 0, 1, 0, 1, 1, 0, 1]
+    np.testing.assert_allclose(m.geom_solref[0], [0.02, 1])
+    np.testing.assert_allclose(m.geom_solref[1:], np.tile([0.005, 1], (10, 1)))
+    np.testing.assert_allclose(m.geom_solimp[1:, :3], np.tile([0.5, 0.99, 0.0001], (10, 1)))
+
+
+@pytest.mark.gpu
+def test_menagerie_style_shadow_hand_gpu_parity(hand, capi, orc):
+    from mujoco_ros_pkgs_b200.batch import BatchSim
+    from parity_util import compare_forward_fields, injected_steps, make_oracles, perturbed
+
+    model, nenv = hand, 6
+    qpos, qvel = perturbed(model, nenv, seed=8, amp=0.1)
+    qpos = np.clip(qpos, model.jnt_range[:, 0], model.jnt_range[:, 1])
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    sim.keep_intermediates(True)
+    sim.forward()
+    oracles = make_oracles(orc, model, qpos, qvel)
+    for o in oracles:
+        o.forward()
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag="menagerie-hand")
+    sim.keep_intermediates(False)
+    worst, _ = injected_steps(model, sim, oracles, 150, np.random.default_rng(4), tag="menagerie-hand")
+    assert worst < 1e-5
