@@ -52,6 +52,18 @@ def test_hfield_compile_facts(capi, tmp_path):
     assert m2.ncollpair == 0
 
 
+def test_hfield_survives_the_binary_model_format_and_set_const(capi, tmp_path):
+    _, hf = bumpy(5, 6)
+    m = capi.Model.from_xml_string(scene(hf, [("0 0 0.3", '<geom type="box" size="0.05 0.04 0.03"/>')]))
+    path = str(tmp_path / "terrain.b2mjb")
+    m.save_binary(path)
+    m2 = capi.Model.load_binary(path)
+    for name in ("hfield_nrow", "hfield_ncol", "hfield_adr", "hfield_size", "hfield_data", "geom_dataid", "geom_size",
+                 "geom_rbound", "collpair_geom1", "collpair_geom2", "collpair_maxcon"):
+        np.testing.assert_array_equal(getattr(m, name), getattr(m2, name), err_msg=name)
+    assert (m2.nhfield, m2.nhfielddata, m2.nconmax) == (1, 30, 8)
+
+
 def test_flat_hfield_is_a_plane(capi, orc):
     flat = '<hfield name="t" nrow="5" ncol="7" size="1 0.8 0.3 0.1"/>'
     m = capi.Model.from_xml_string(scene(flat, [("0.03 0.02 0.2", '<geom type="sphere" size="0.1"/>')]))
