@@ -737,6 +737,7 @@ def main():
 
     clocks = sampler.stop()
     wall = time.perf_counter() - wall0
+    rollout_rank_stats = per_rank_stats(C, [step_ms])  # every rank's own rollout launch: attributes a weak-scaling loss
     step_ms, ps_ms, e2e_s = reduce_max(C, step_ms, ps_ms, e2e_s)
     value = nenv * world * K / (step_ms * 1e-3)
     ps_value = nenv * world * K / (ps_ms * 1e-3)
@@ -796,6 +797,7 @@ def main():
                               "PCIe inside the timed region)" if not os.environ.get("B2MJ_NO_ZERO_COPY") else
                               "wall clock, sync both sides, pinned host buffers, one b2mj_step_host call per step (staged copies)"},
             "gpu_launches": rollout_launches,
+            "per_rank_rollout_ms": [{"rank": r["rank"], "ms": r["median_ms"]} for r in rollout_rank_stats],
             "per_step_launch": {"value": ps_value, "unit": UNIT, "ms_per_step": ps_ms / K, "gpu_launches": ps_launches,
                                 "per_rank_kernel_ms": rank_stats,
                                 "note": "K x (b2mj_set_device(ctrl) + b2mj_step(1) + launch-order refresh), CUDA events per step, "
