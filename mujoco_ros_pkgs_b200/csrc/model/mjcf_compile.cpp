@@ -374,6 +374,11 @@ struct Builder {
     bool ang = (j.type == B2MJ_JNT_HINGE || j.type == B2MJ_JNT_BALL) && ctx.degrees;
     if (ang) { j.range[0] *= kPi / 180; j.range[1] *= kPi / 180; }
     j.margin = a.num("margin", 0);
+    if (a.has("springdamper")) {  // (time constant, damping ratio) -> stiffness / damping from the joint inertia: not implemented
+      double sd[2] = {0, 0};
+      a.vec("springdamper", sd, 2, 2);
+      if (sd[0] > 0 && sd[1] > 0) fail(n, "joint springdamper is not supported (give stiffness and damping explicitly)");
+    }
     j.ref = a.num("ref", 0);
     j.springref = a.num("springref", 0);
     if (j.type == B2MJ_JNT_HINGE && ctx.degrees) { j.ref *= kPi / 180; j.springref *= kPi / 180; }
@@ -453,6 +458,11 @@ struct Builder {
     (void)nf;
     a.vec("solref", g.solref, 2, 2);
     a.vec("solimp", g.solimp, 5, 3);
+    // physics-relevant geom attributes this compiler does not implement are refused, not ignored
+    if (a.has("fluidshape") && a.str("fluidshape") != "none")
+      fail(n, "geom fluidshape='" + a.str("fluidshape") + "' (ellipsoid fluid model) is not supported: only the inertia-box model is");
+    if (a.has("fluidcoef")) fail(n, "geom fluidcoef (ellipsoid fluid model) is not supported");
+    if (a.has("shellinertia") && a.str("shellinertia") == "true") fail(n, "geom shellinertia is not supported");
     g.solmix = a.num("solmix", 1);
     g.margin = a.num("margin", 0);
     g.gap = a.num("gap", 0);
@@ -1225,6 +1235,7 @@ b2mjModel* compile(const XmlNode* root) {
       m->tendon_range[2 * t] = rng[0];
       m->tendon_range[2 * t + 1] = rng[1];
       m->tendon_margin[t] = a.num("margin", 0);
+      if (a.has("armature") && a.num("armature", 0) != 0) fail(tendon_nodes[t], "tendon armature is not supported");
       m->tendon_stiffness[t] = a.num("stiffness", 0);
       m->tendon_damping[t] = a.num("damping", 0);
       m->tendon_frictionloss[t] = a.num("frictionloss", 0);
