@@ -775,12 +775,24 @@ b2mjModel* compile(const XmlNode* root) {
             {"warmstart", B2MJ_DSBL_WARMSTART}, {"filterparent", B2MJ_DSBL_FILTERPARENT},
             {"actuation", B2MJ_DSBL_ACTUATION}, {"refsafe", B2MJ_DSBL_REFSAFE}, {"sensor", B2MJ_DSBL_SENSOR},
             {"midphase", B2MJ_DSBL_MIDPHASE}, {"eulerdamp", B2MJ_DSBL_EULERDAMP}};
-        for (auto& kv : fl->attrs)
+        for (auto& kv : fl->attrs) {
+          bool known = false;
           for (auto& d : dis)
             if (kv.first == d.first) {
+              known = true;
               if (kv.second == "disable") o.disableflags |= d.second;
               else o.disableflags &= ~d.second;
             }
+          if (known) continue;
+          // enable flags.  energy / fwdinv only add outputs this library does not expose: accepted, no effect on the
+          // state.  The others change the dynamics or the sensor values and are not implemented: refused when enabled.
+          if (kv.first == "energy" || kv.first == "fwdinv") continue;
+          if (kv.first == "override" || kv.first == "sensornoise" || kv.first == "multiccd" || kv.first == "island") {
+            if (kv.second == "enable") fail(fl, "option flag " + kv.first + "=\"enable\" is not supported");
+            continue;
+          }
+          fail(fl, "unknown option flag '" + kv.first + "'");
+        }
       }
     } else if (sec->tag == "size") {
       nconmax_user = a.integer("nconmax", -1);

@@ -108,3 +108,13 @@ def test_unsupported_physics_attributes_are_refused_not_ignored(capi):
         with pytest.raises(capi.B2mjError, match=word):
             capi.Model.from_xml_string(base % (joint, geom, extra))
     capi.Model.from_xml_string(base % ("", 'fluidshape="none"', ""))  # the default value is fine
+    # enable flags that change the dynamics or the sensor values are refused when switched on; energy / fwdinv only add
+    # outputs and are accepted; a misspelt flag is an error
+    flagged = '<mujoco><option><flag %s/></option><worldbody><body><freejoint/><geom size="0.1"/></body></worldbody></mujoco>'
+    for flag in ("override", "sensornoise", "multiccd"):
+        with pytest.raises(capi.B2mjError, match=flag):
+            capi.Model.from_xml_string(flagged % f'{flag}="enable"')
+        capi.Model.from_xml_string(flagged % f'{flag}="disable"')
+    capi.Model.from_xml_string(flagged % 'energy="enable" fwdinv="enable"')
+    with pytest.raises(capi.B2mjError, match="unknown option flag"):
+        capi.Model.from_xml_string(flagged % 'gravty="disable"')
