@@ -46,7 +46,8 @@ struct Ctx {
   bool autolimits = true;
   std::string eulerseq = "xyz";
   int inertiafromgeom = 2;  // 0 false, 1 true, 2 auto
-  double boundmass = 0, boundinertia = 0;
+  double boundmass = 0, boundinertia = 0, settotalmass = -1;
+  int inertiagroup[2] = {0, 5};  // geom groups that count for inertia inference (compiler inertiagrouprange)
   std::map<std::string, std::map<std::string, AttrMap>> defaults;  // class -> group -> attrs
   std::map<std::string, std::string> class_parent;
   std::string meshdir;
@@ -199,7 +200,7 @@ struct CGeom {
   double rgba[4] = {0.5, 0.5, 0.5, 1};
   int meshid = -1;
   double mesh_volume = 0, mesh_inertia[3] = {0, 0, 0}, rbound = 0;
-  int contype = 1, conaffinity = 1, condim = 3, priority = 0;
+  int contype = 1, conaffinity = 1, condim = 3, priority = 0, group = 0;
 };
 struct CSite {
   std::string name;
@@ -468,6 +469,7 @@ struct Builder {
     g.gap = a.num("gap", 0);
     a.vec("rgba", g.rgba, 4, 1);  // only alpha matters to the physics: mj_ray skips fully transparent geoms
     g.contype = a.integer("contype", 1);
+    g.group = a.integer("group", 0);
     g.conaffinity = a.integer("conaffinity", 1);
     g.condim = a.integer("condim", 3);
     g.priority = a.integer("priority", 0);
@@ -555,7 +557,7 @@ struct Builder {
     if (ctx.inertiafromgeom == 0) return;
     std::vector<const CGeom*> gs;
     for (auto& g : b.geoms)
-      if (g.mass > 0) gs.push_back(&g);
+      if (g.mass > 0 && g.group >= ctx.inertiagroup[0] && g.group <= ctx.inertiagroup[1]) gs.push_back(&g);
     if (gs.empty()) return;
     if (gs.size() == 1) {
       copy3(b.ipos, gs[0]->pos);
@@ -721,6 +723,15 @@ b2mjModel* compile(const XmlNode* root) {
       if (a.has("inertiafromgeom")) {
         std::string s = a.str("inertiafromgeom");
         ctx.inertiafromgeom = s == "true" ? 1 : s == "false" ? 0 : 2;
+      }
+      ctx.boundmass = a.num("boundmass", ctx.boundmass);
+      ctx.boundinertia = a.num("boundinertia", ctx.boundinertia);
+      ctx.settotalmass = a.num("settotalmass", ctx.settotalmass);
+      if (a.has("inertiagrouprange")) {
+        double r[2] = {0, 5};
+        a.vec("inertiagrouprange", r, 2, 2);
+        ctx.inertiagroup[0] = (int)std::lround(r[0]);
+        ctx.inertiagroup[1] = (int)std::lround(r[1]);
       }
     } else if (sec->tag == "option") {
       b2mjOption& o = m->opt;
@@ -1604,8 +1615,37 @@ b2mjModel* compile(const XmlNode* root) {
     m->pair_gap[i] = a.num("gap", std::max(m->geom_gap[g1], m->geom_gap[g2]));
   }
 
+  // compiler boundmass / boundinertia (lower bounds for every body but the world) and settotalmass (all masses and
+  // inertias rescaled so that the model weighs this much): mjCModel::Compile order, before the derived constants
+  for (int i = 1; i < m->nbody; i++) {
+    if (ctx.boundmass > 0) m->body_mass[i] = std::max(m->body_mass[i], ctx.boundmass);
+    if (ctx.boundinertia > 0)
+      for (int k = 0; k < 3; k++) m->body_inertia[3 * i + k] = std::max(m->body_inertia[3 * i + k], ctx.boundinertia);
+  }
+  if (ctx.settotalmass > 0) {
+    double total = 0;
+    for (int i = 1; i < m->nbody; i++) total += m->body_mass[i];
+    if (total > 0) {
+      const double scale = ctx.settotalmass / total;
+      for (int i = 1; i < m->nbody; i++) {
+        m->body_mass[i] *= scale;
+        for (int k = 0; k < 3; k++) m->body_inertia[3 * i + k] *= scale;
+      }
+    }
+  }
   std::string err;
   if (model_set_const(m, err)) throw CompileError{err};
+  // <statistic>: values given in the file override the computed ones (meaninertia scales the solver tolerances)
+  for (auto& sec : root->children) {
+    if (sec->tag != "statistic") continue;
+    AttrMap em = effective(ctx, sec.get(), "");
+    A a{em, sec.get()};
+    m->stat.meaninertia = a.num("meaninertia", m->stat.meaninertia);
+    m->stat.meanmass = a.num("meanmass", m->stat.meanmass);
+    m->stat.meansize = a.num("meansize", m->stat.meansize);
+    m->stat.extent = a.num("extent", m->stat.extent);
+    a.vec("center", m->stat.center, 3, 3);
+  }
   // tendon spring length -1 => use length at qpos0
   for (int t = 0; t < m->ntendon; t++)
     for (int k = 0; k < 2; k++)

@@ -118,3 +118,27 @@ def test_unsupported_physics_attributes_are_refused_not_ignored(capi):
     capi.Model.from_xml_string(flagged % 'energy="enable" fwdinv="enable"')
     with pytest.raises(capi.B2mjError, match="unknown option flag"):
         capi.Model.from_xml_string(flagged % 'gravty="disable"')
+
+
+def test_compiler_mass_options_and_statistic_overrides(capi):
+    """compiler settotalmass / boundmass / boundinertia / inertiagrouprange and <statistic> overrides change the
+    dynamics (masses, inertias, the solver's meaninertia scale) and were dropped silently before round 2c."""
+    body = ('<worldbody><body pos="0 0 1"><joint type="hinge"/><geom size="0.1" group="2"/><geom size="0.05" pos="0.2 0 0"/>'
+            '<body pos="0 0 2"><joint type="hinge"/><geom size="0.1"/></body></body></worldbody>')
+    mk = lambda c, extra="": capi.Model.from_xml_string(f"<mujoco><compiler {c}/>{extra}{body}</mujoco>")  # noqa: E731
+    m0 = mk("")
+    v1, v2 = 4000 / 3 * np.pi * 0.1 ** 3, 4000 / 3 * np.pi * 0.05 ** 3  # density 1000
+    np.testing.assert_allclose(m0.body_mass, [0, v1 + v2, v1], rtol=1e-12)
+    m = mk('settotalmass="5"')
+    np.testing.assert_allclose(m.body_mass.sum(), 5, rtol=1e-12)
+    np.testing.assert_allclose(m.body_mass[1:] / m0.body_mass[1:], 5 / m0.body_mass.sum(), rtol=1e-12)
+    np.testing.assert_allclose(m.body_inertia[1:] / m0.body_inertia[1:], 5 / m0.body_mass.sum(), rtol=1e-12)
+    m = mk('inertiagrouprange="0 1"')  # the group-2 sphere no longer counts: the body is the small sphere alone
+    np.testing.assert_allclose(m.body_mass[1], v2, rtol=1e-12)
+    np.testing.assert_allclose(m.body_ipos[1], [0.2, 0, 0], atol=1e-15)
+    m = mk('boundmass="6" boundinertia="0.5"')
+    np.testing.assert_allclose(m.body_mass, [0, 6, 6])
+    np.testing.assert_allclose(m.body_inertia[1:], 0.5)
+    assert m.stat.meaninertia > m0.stat.meaninertia
+    m = mk("", '<statistic meaninertia="2.5" extent="3" center="0 0 1"/>')
+    assert (m.stat.meaninertia, m.stat.extent, list(m.stat.center)) == (2.5, 3.0, [0, 0, 1])
