@@ -375,6 +375,8 @@ struct Builder {
     bool ang = (j.type == B2MJ_JNT_HINGE || j.type == B2MJ_JNT_BALL) && ctx.degrees;
     if (ang) { j.range[0] *= kPi / 180; j.range[1] *= kPi / 180; }
     j.margin = a.num("margin", 0);
+    if (a.has("actuatorfrcrange") || (a.has("actuatorfrclimited") && a.str("actuatorfrclimited") == "true"))
+      fail(n, "joint actuatorfrcrange (clamp on the total actuator force of a joint) is not supported");
     if (a.has("springdamper")) {  // (time constant, damping ratio) -> stiffness / damping from the joint inertia: not implemented
       double sd[2] = {0, 0};
       a.vec("springdamper", sd, 2, 2);
@@ -1355,6 +1357,7 @@ b2mjModel* compile(const XmlNode* root) {
         m->actuator_dyntype[i] = s == "none" ? B2MJ_DYN_NONE : s == "integrator" ? B2MJ_DYN_INTEGRATOR
                                  : s == "filter" ? B2MJ_DYN_FILTER : -1;
         if (m->actuator_dyntype[i] < 0) fail(n, "unsupported dyntype '" + s + "'");
+        if (a.has("actearly") && a.str("actearly") == "true") fail(n, "actuator actearly is not supported");
         s = a.str("gaintype", "fixed");
         m->actuator_gaintype[i] = s == "fixed" ? B2MJ_GAIN_FIXED : s == "affine" ? B2MJ_GAIN_AFFINE : -1;
         if (m->actuator_gaintype[i] < 0) fail(n, "unsupported gaintype '" + s + "'");

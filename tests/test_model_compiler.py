@@ -103,6 +103,7 @@ def test_unsupported_physics_attributes_are_refused_not_ignored(capi):
                                      ("", 'shellinertia="true"', "", "shellinertia"),
                                      ("", 'fluidshape="ellipsoid"', "", "fluidshape"),
                                      ("", 'fluidcoef="0.5 0.25 1.5 1 1"', "", "fluidcoef"),
+                                     ('actuatorfrcrange="-1 1"', "", "", "actuatorfrcrange"),
                                      ("", "", '<tendon><fixed armature="1"><joint joint="j" coef="1"/></fixed></tendon>',
                                       "armature")):
         with pytest.raises(capi.B2mjError, match=word):
