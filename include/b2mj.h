@@ -86,6 +86,10 @@ enum {
   B2MJ_DSBL_FILTERPARENT = 1 << 9, B2MJ_DSBL_ACTUATION = 1 << 10, B2MJ_DSBL_REFSAFE = 1 << 11,
   B2MJ_DSBL_SENSOR = 1 << 12, B2MJ_DSBL_MIDPHASE = 1 << 13, B2MJ_DSBL_EULERDAMP = 1 << 14
 };
+/* mjtEnableBit.  Only OVERRIDE has an effect (applied by the model compiler: every geom / pair takes the o_* contact
+ * parameters); ENERGY / FWDINV add outputs this library does not expose; the others are refused by the compiler. */
+enum { B2MJ_ENBL_OVERRIDE = 1 << 0, B2MJ_ENBL_ENERGY = 1 << 1, B2MJ_ENBL_FWDINV = 1 << 2, B2MJ_ENBL_SENSORNOISE = 1 << 3,
+       B2MJ_ENBL_MULTICCD = 1 << 4 };
 /* warnings (mjtWarning order) */
 enum {
   B2MJ_WARN_INERTIA = 0, B2MJ_WARN_CONTACTFULL = 1, B2MJ_WARN_CNSTRFULL = 2, B2MJ_WARN_VGEOMFULL = 3,

@@ -702,6 +702,7 @@ b2mjModel* compile(const XmlNode* root) {
     ~Guard() { if (m) b2mj_model_free(m); }
   } guard{m};
   int nconmax_user = -1, njmax_user = -1;
+  bool override_contacts = false;  // <flag override="enable">
 
   // ---- pass 1: compiler / option / size / defaults (they may appear anywhere, any number of times)
   for (auto& sec : root->children) {
@@ -800,7 +801,11 @@ b2mjModel* compile(const XmlNode* root) {
           // enable flags.  energy / fwdinv only add outputs this library does not expose: accepted, no effect on the
           // state.  The others change the dynamics or the sensor values and are not implemented: refused when enabled.
           if (kv.first == "energy" || kv.first == "fwdinv") continue;
-          if (kv.first == "override" || kv.first == "sensornoise" || kv.first == "multiccd" || kv.first == "island") {
+          if (kv.first == "override") {  // implemented at compile time, below: contact parameters rewritten to the o_* values
+            override_contacts = kv.second == "enable";
+            continue;
+          }
+          if (kv.first == "sensornoise" || kv.first == "multiccd" || kv.first == "island") {
             if (kv.second == "enable") fail(fl, "option flag " + kv.first + "=\"enable\" is not supported");
             continue;
           }
@@ -1618,6 +1623,25 @@ b2mjModel* compile(const XmlNode* root) {
     m->pair_gap[i] = a.num("gap", std::max(m->geom_gap[g1], m->geom_gap[g2]));
   }
 
+  // <flag override="enable"> (mjENBL_OVERRIDE): every contact takes margin o_margin, gap 0 and the o_solref / o_solimp
+  // reference and impedance.  The mixing rules reproduce a value both geoms share, so writing the override into every
+  // geom and explicit pair at compile time is the same as overriding every contact at run time; enableflags keeps the
+  // bit for the record.
+  if (override_contacts) {
+    m->opt.enableflags |= B2MJ_ENBL_OVERRIDE;
+    for (int g = 0; g < m->ngeom; g++) {
+      m->geom_margin[g] = m->opt.o_margin;
+      m->geom_gap[g] = 0;
+      std::copy(m->opt.o_solref, m->opt.o_solref + 2, m->geom_solref + 2 * g);
+      std::copy(m->opt.o_solimp, m->opt.o_solimp + 5, m->geom_solimp + 5 * g);
+    }
+    for (int i = 0; i < m->npair; i++) {
+      m->pair_margin[i] = m->opt.o_margin;
+      m->pair_gap[i] = 0;
+      std::copy(m->opt.o_solref, m->opt.o_solref + 2, m->pair_solref + 2 * i);
+      std::copy(m->opt.o_solimp, m->opt.o_solimp + 5, m->pair_solimp + 5 * i);
+    }
+  }
   // compiler boundmass / boundinertia (lower bounds for every body but the world) and settotalmass (all masses and
   // inertias rescaled so that the model weighs this much): mjCModel::Compile order, before the derived constants
   for (int i = 1; i < m->nbody; i++) {

@@ -112,7 +112,7 @@ def test_unsupported_physics_attributes_are_refused_not_ignored(capi):
     # enable flags that change the dynamics or the sensor values are refused when switched on; energy / fwdinv only add
     # outputs and are accepted; a misspelt flag is an error
     flagged = '<mujoco><option><flag %s/></option><worldbody><body><freejoint/><geom size="0.1"/></body></worldbody></mujoco>'
-    for flag in ("override", "sensornoise", "multiccd"):
+    for flag in ("sensornoise", "multiccd"):
         with pytest.raises(capi.B2mjError, match=flag):
             capi.Model.from_xml_string(flagged % f'{flag}="enable"')
         capi.Model.from_xml_string(flagged % f'{flag}="disable"')
@@ -143,3 +143,25 @@ def test_compiler_mass_options_and_statistic_overrides(capi):
     assert m.stat.meaninertia > m0.stat.meaninertia
     m = mk("", '<statistic meaninertia="2.5" extent="3" center="0 0 1"/>')
     assert (m.stat.meaninertia, m.stat.extent, list(m.stat.center)) == (2.5, 3.0, [0, 0, 1])
+
+
+def test_override_flag_rewrites_every_contact_parameter(capi, orc):
+    """<flag override="enable">: every contact takes o_margin (gap 0), o_solref, o_solimp -- applied by the compiler to
+    all geoms and explicit pairs (the mixing rules reproduce a shared value), so the step needs no run-time switch."""
+    xml = ('<mujoco><option o_margin="0.01" o_solref="0.05 0.8" o_solimp="0.8 0.9 0.002"><flag override="%s"/></option>'
+           '<worldbody><geom name="g1" type="plane" size="1 1 .1" solref="0.01 1" margin="0.003"/><body pos="0 0 0.105"><freejoint/>'
+           '<geom name="g2" size="0.1" solref="0.02 1.2"/></body><body pos="1 0 0.105"><freejoint/><geom size="0.1" gap="0.001"/>'
+           '</body></worldbody><contact><pair geom1="g1" geom2="g2" solref="0.03 1" margin="0.2"/></contact></mujoco>')
+    on, off = capi.Model.from_xml_string(xml % "enable"), capi.Model.from_xml_string(xml % "disable")
+    assert (on.opt.enableflags, off.opt.enableflags) == (1, 0)
+    o = orc.Oracle(on)
+    o.forward()
+    n = int(o.get("ncon")[0])
+    assert n == 2  # the explicit pair and the dynamic plane-sphere pair
+    np.testing.assert_allclose(o.get("contact_solref")[:2 * n].reshape(n, 2), np.tile([0.05, 0.8], (n, 1)))
+    np.testing.assert_allclose(o.get("contact_solimp")[:5 * n].reshape(n, 5), np.tile([0.8, 0.9, 0.002, 0.5, 2], (n, 1)))
+    np.testing.assert_allclose(o.get("contact_includemargin")[:n], 0.01)
+    o2 = orc.Oracle(off)
+    o2.forward()
+    np.testing.assert_allclose(o2.get("contact_solref")[:2], [0.03, 1])
+    np.testing.assert_allclose(o2.get("contact_includemargin")[:1], 0.2)
