@@ -186,6 +186,7 @@ struct CJoint {
   double range[2] = {0, 0};
   int limited = 0;
   double margin = 0, ref = 0, springref = 0, stiffness = 0, damping = 0, armature = 0, frictionloss = 0;
+  double springdamper[2] = {0, 0};  // (time constant, damping ratio): stiffness / damping derived from dof_invweight0 after set_const
   double solref_lim[2] = {0.02, 1}, solimp_lim[5] = {0.9, 0.95, 0.001, 0.5, 2};
   double solref_fri[2] = {0.02, 1}, solimp_fri[5] = {0.9, 0.95, 0.001, 0.5, 2};
 };
@@ -377,11 +378,7 @@ struct Builder {
     j.margin = a.num("margin", 0);
     if (a.has("actuatorfrcrange") || (a.has("actuatorfrclimited") && a.str("actuatorfrclimited") == "true"))
       fail(n, "joint actuatorfrcrange (clamp on the total actuator force of a joint) is not supported");
-    if (a.has("springdamper")) {  // (time constant, damping ratio) -> stiffness / damping from the joint inertia: not implemented
-      double sd[2] = {0, 0};
-      a.vec("springdamper", sd, 2, 2);
-      if (sd[0] > 0 && sd[1] > 0) fail(n, "joint springdamper is not supported (give stiffness and damping explicitly)");
-    }
+    if (a.has("springdamper")) a.vec("springdamper", j.springdamper, 2, 2);
     j.ref = a.num("ref", 0);
     j.springref = a.num("springref", 0);
     if (j.type == B2MJ_JNT_HINGE && ctx.degrees) { j.ref *= kPi / 180; j.springref *= kPi / 180; }
@@ -1662,6 +1659,26 @@ b2mjModel* compile(const XmlNode* root) {
   }
   std::string err;
   if (model_set_const(m, err)) throw CompileError{err};
+  // joint springdamper = (time constant tau, damping ratio zeta): stiffness and damping of the mass-spring-damper formed
+  // with the joint's effective inertia at qpos0, I = ndof / sum(dof_invweight0) (the free joint's translational and
+  // rotational weights differ, hence the average) -- k = I / (tau^2 zeta^2), b = 2 I / tau, the same relation as solref;
+  // overrides the joint's own stiffness / damping and runs after set_const (mjCModel::AutoSpringDamper)
+  {
+    int j = 0;
+    for (int i = 0; i < m->nbody; i++)
+      for (auto& jn : B.bodies[i].joints) {
+        if (jn.springdamper[0] > 0 && jn.springdamper[1] > 0) {
+          const int dof = m->jnt_dofadr[j];
+          const int ndof = jn.type == B2MJ_JNT_FREE ? 6 : jn.type == B2MJ_JNT_BALL ? 3 : 1;
+          double w = 0;
+          for (int k = 0; k < ndof; k++) w += m->dof_invweight0[dof + k];
+          const double I = ndof / std::max(1e-15, w), tau = jn.springdamper[0], zeta = jn.springdamper[1];
+          m->jnt_stiffness[j] = I / std::max(1e-15, tau * tau * zeta * zeta);
+          for (int k = 0; k < ndof; k++) m->dof_damping[dof + k] = 2 * I / std::max(1e-15, tau);
+        }
+        j++;
+      }
+  }
   // <statistic>: values given in the file override the computed ones (meaninertia scales the solver tolerances)
   for (auto& sec : root->children) {
     if (sec->tag != "statistic") continue;

@@ -96,11 +96,10 @@ def test_set_const_is_idempotent(load_model, capi):
 
 def test_unsupported_physics_attributes_are_refused_not_ignored(capi):
     """Attributes that would change the dynamics but are not implemented must fail the compile instead of being dropped
-    (round-1 verdict: "silently ignored" options): the ellipsoid fluid model, shell inertia, springdamper, tendon armature."""
+    (round-1 verdict: "silently ignored" options): the ellipsoid fluid model, shell inertia, tendon armature."""
     base = ('<mujoco><worldbody><body pos="0 0 1"><joint name="j" type="hinge" %s/><geom size="0.1" %s/></body></worldbody>'
             '%s</mujoco>')
-    for joint, geom, extra, word in (('springdamper="0.1 1"', "", "", "springdamper"),
-                                     ("", 'shellinertia="true"', "", "shellinertia"),
+    for joint, geom, extra, word in (("", 'shellinertia="true"', "", "shellinertia"),
                                      ("", 'fluidshape="ellipsoid"', "", "fluidshape"),
                                      ("", 'fluidcoef="0.5 0.25 1.5 1 1"', "", "fluidcoef"),
                                      ('actuatorfrcrange="-1 1"', "", "", "actuatorfrcrange"),
@@ -119,6 +118,40 @@ def test_unsupported_physics_attributes_are_refused_not_ignored(capi):
     capi.Model.from_xml_string(flagged % 'energy="enable" fwdinv="enable"')
     with pytest.raises(capi.B2mjError, match="unknown option flag"):
         capi.Model.from_xml_string(flagged % 'gravty="disable"')
+
+
+def test_joint_springdamper_sets_stiffness_and_damping_from_the_effective_inertia(capi, orc):
+    """springdamper="tau zeta": k = I / (tau zeta)^2, b = 2 I / tau with I = ndof / sum(dof_invweight0) at qpos0
+    (mjCModel::AutoSpringDamper), overriding the joint's own stiffness / damping.  Checked on a pendulum whose effective
+    inertia is known in closed form, and dynamically: the oracle's free response decays with time constant tau."""
+    tau, zeta = 0.25, 0.5
+    xml = ('<mujoco><option gravity="0 0 0" timestep="0.0005"/><worldbody><body><joint name="j" axis="0 1 0" stiffness="3" '
+           f'damping="7" springdamper="{tau} {zeta}"/><geom size="0.05" pos="0 0 -0.4" mass="2"/></body>'
+           '<body pos="1 0 0"><freejoint/><geom size="0.1" mass="3"/></body></worldbody></mujoco>')
+    m = capi.Model.from_xml_string(xml)
+    inertia = 2 * 0.4 ** 2 + 0.4 * 2 * 0.05 ** 2  # point mass at 0.4 m + the sphere's own 2/5 m r^2
+    np.testing.assert_allclose(1 / m.dof_invweight0[0], inertia, rtol=1e-12)
+    np.testing.assert_allclose(m.jnt_stiffness[0], inertia / (tau * zeta) ** 2, rtol=1e-12)
+    np.testing.assert_allclose(m.dof_damping[0], 2 * inertia / tau, rtol=1e-12)
+    assert m.jnt_stiffness[1] == 0 and not m.dof_damping[1:].any()  # joints without the attribute are untouched
+    # free joint: one damping value on all six dofs from the averaged weight
+    mf = capi.Model.from_xml_string('<mujoco><worldbody><body><joint type="free" springdamper="0.1 1"/><geom size="0.1" mass="3"/>'
+                                    '</body></worldbody></mujoco>')
+    avg = 6 / mf.dof_invweight0[:6].sum()
+    np.testing.assert_allclose(mf.dof_damping[:6], 2 * avg / 0.1, rtol=1e-12)
+    np.testing.assert_allclose(mf.jnt_stiffness[0], avg / 0.01, rtol=1e-12)
+    # free response from q0: envelope exp(-t / tau), so the amplitude one time constant later is below q0 / e
+    o = orc.Oracle(m)
+    q = o.get("qpos").copy()
+    q[0] = 0.2
+    o.set("qpos", q)
+    n = int(round(tau / 0.0005))
+    peak = 0.0
+    for k in range(3 * n):
+        o.step()
+        if k >= n:
+            peak = max(peak, abs(o.get("qpos")[0]))
+    assert 0.2 * np.exp(-3) < peak < 0.2 * np.exp(-1) * 1.3
 
 
 def test_compiler_mass_options_and_statistic_overrides(capi):
