@@ -67,7 +67,9 @@ std::vector<double> parse_nums(const std::string& s) {
 }
 
 std::string group_of(const std::string& tag) {
-  if (tag == "motor" || tag == "position" || tag == "velocity" || tag == "general") return "actuator";
+  if (tag == "motor" || tag == "position" || tag == "velocity" || tag == "general" || tag == "intvelocity" || tag == "damper" ||
+      tag == "cylinder")
+    return "actuator";
   if (tag == "freejoint") return "freejoint";
   if (tag == "fixed" || tag == "spatial") return "tendon";
   if (tag == "connect" || tag == "weld") return "equality";
@@ -1331,8 +1333,8 @@ b2mjModel* compile(const XmlNode* root) {
     for (size_t i = 0; i < act_nodes.size(); i++) {
       const XmlNode* n = act_nodes[i];
       const std::string& tag = n->tag;
-      if (tag != "motor" && tag != "position" && tag != "velocity" && tag != "general")
-        fail(n, "unsupported actuator type");
+      if (group_of(tag) != "actuator")
+        fail(n, "unsupported actuator type '" + tag + "' (muscle and adhesion actuators are out of scope)");
       AttrMap em = effective(ctx, n, "");
       A a{em, n};
       double* gain = m->actuator_gainprm + B2MJ_NGAIN * i;
@@ -1354,6 +1356,25 @@ b2mjModel* compile(const XmlNode* root) {
         gain[0] = kv;
         m->actuator_biastype[i] = B2MJ_BIAS_AFFINE;
         bias[2] = -kv;
+      } else if (tag == "intvelocity") {  // position servo on the integrated control: act' = ctrl, force = kp (act - q)
+        double kp = a.num("kp", 1);
+        gain[0] = kp;
+        m->actuator_dyntype[i] = B2MJ_DYN_INTEGRATOR;
+        m->actuator_biastype[i] = B2MJ_BIAS_AFFINE;
+        bias[1] = -kp;
+      } else if (tag == "damper") {  // force = -kv * velocity * ctrl: affine gain on the velocity, ctrl >= 0 required
+        double kv = a.num("kv", 0);
+        if (kv < 0) fail(n, "damping coefficient cannot be negative");
+        gain[0] = 0;
+        gain[2] = -kv;
+        m->actuator_gaintype[i] = B2MJ_GAIN_AFFINE;
+      } else if (tag == "cylinder") {  // pneumatic / hydraulic cylinder: first-order pressure filter, force = area * act + bias
+        dyn[0] = a.num("timeconst", 1);
+        gain[0] = a.num("area", 1);
+        if (a.has("diameter")) { const double d = a.num("diameter", 0); gain[0] = M_PI / 4 * d * d; }
+        a.vec("bias", bias, 3, 3);
+        m->actuator_dyntype[i] = B2MJ_DYN_FILTER;
+        m->actuator_biastype[i] = B2MJ_BIAS_AFFINE;
       } else if (tag == "general") {
         std::string s = a.str("dyntype", "none");
         m->actuator_dyntype[i] = s == "none" ? B2MJ_DYN_NONE : s == "integrator" ? B2MJ_DYN_INTEGRATOR
@@ -1380,6 +1401,10 @@ b2mjModel* compile(const XmlNode* root) {
       m->actuator_ctrllimited[i] = cl == -1 ? (ctx.autolimits && hcr) : cl;
       m->actuator_forcelimited[i] = fl == -1 ? (ctx.autolimits && hfr) : fl;
       m->actuator_actlimited[i] = al == -1 ? (ctx.autolimits && har) : al;
+      if (tag == "damper") {
+        if (!m->actuator_ctrllimited[i]) fail(n, "damper actuators need a control range (ctrllimited)");
+        if (cr[0] < 0 || cr[1] < 0) fail(n, "damper control range cannot be negative");
+      }
       std::memcpy(m->actuator_ctrlrange + 2 * i, cr, sizeof(cr));
       std::memcpy(m->actuator_forcerange + 2 * i, fr, sizeof(fr));
       std::memcpy(m->actuator_actrange + 2 * i, ar, sizeof(ar));

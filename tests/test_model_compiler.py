@@ -154,6 +154,35 @@ def test_joint_springdamper_sets_stiffness_and_damping_from_the_effective_inerti
     assert 0.2 * np.exp(-3) < peak < 0.2 * np.exp(-1) * 1.3
 
 
+def test_actuator_shortcuts_equal_their_general_form(capi):
+    """<intvelocity>, <damper>, <cylinder> are shorthands for <general> (MuJoCo XML reference, actuator section): every
+    actuator array must equal the spelled-out form, which the GPU path tests (affine gain / bias, integrator, filter)."""
+    body = ('<mujoco><worldbody><body><joint name="j" axis="0 1 0"/><geom size="0.1"/></body></worldbody><actuator>%s'
+            '</actuator></mujoco>')
+    pairs = [
+        ('<intvelocity joint="j" kp="30" actrange="-1 1"/>',
+         '<general joint="j" dyntype="integrator" gainprm="30" biastype="affine" biasprm="0 -30 0" actrange="-1 1"/>'),
+        ('<damper joint="j" kv="4" ctrlrange="0 2"/>',
+         '<general joint="j" gaintype="affine" gainprm="0 0 -4" ctrlrange="0 2"/>'),
+        ('<cylinder joint="j" timeconst="0.3" diameter="0.2" bias="1 -2 -0.5"/>',
+         f'<general joint="j" dyntype="filter" dynprm="0.3" gainprm="{np.pi / 4 * 0.04!r}" biastype="affine" biasprm="1 -2 -0.5"/>'),
+        ('<cylinder joint="j" area="0.7"/>',
+         '<general joint="j" dyntype="filter" dynprm="1" gainprm="0.7" biastype="affine"/>'),
+    ]
+    fields = ("actuator_dyntype", "actuator_gaintype", "actuator_biastype", "actuator_dynprm", "actuator_gainprm",
+              "actuator_biasprm", "actuator_ctrllimited", "actuator_ctrlrange", "actuator_actlimited", "actuator_actrange",
+              "actuator_actadr", "actuator_trnid", "actuator_gear")
+    for short, general in pairs:
+        a, b = capi.Model.from_xml_string(body % short), capi.Model.from_xml_string(body % general)
+        assert a.na == b.na
+        for f in fields:
+            np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f"{short}: {f}")
+    for bad, word in (('<damper joint="j" kv="4"/>', "control range"), ('<damper joint="j" kv="4" ctrlrange="-1 1"/>', "negative"),
+                      ('<damper joint="j" kv="-1" ctrlrange="0 1"/>', "negative"), ('<muscle joint="j"/>', "muscle")):
+        with pytest.raises(capi.B2mjError, match=word):
+            capi.Model.from_xml_string(body % bad)
+
+
 def test_compiler_mass_options_and_statistic_overrides(capi):
     """compiler settotalmass / boundmass / boundinertia / inertiagrouprange and <statistic> overrides change the
     dynamics (masses, inertias, the solver's meaninertia scale) and were dropped silently before round 2c."""
