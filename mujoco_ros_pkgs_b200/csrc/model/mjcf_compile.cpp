@@ -20,6 +20,7 @@
 
 #include "hostmath.h"
 #include "mesh.h"
+#include "png_gray.h"
 #include "model_core.h"
 #include "xml_mini.h"
 
@@ -858,8 +859,8 @@ b2mjModel* compile(const XmlNode* root) {
   }
   // ---- assets: height fields.  MuJoCo 2.3.7 takes the elevation from a file (PNG, or the custom binary format
   // (int32) nrow, (int32) ncol, (float32) data[nrow * ncol]) or leaves it zero for the program to fill; the inline
-  // `elevation` attribute of later MuJoCo versions is accepted too.  PNG decoding is the reference's vendored lodepng
-  // (out of scope) and is rejected by name.  mjCHField::Compile normalises the data to [0, 1].
+  // `elevation` attribute of later MuJoCo versions is accepted too.  PNG files go through png_gray.cpp (our own decoder;
+  // the reference's vendored lodepng is out of scope).  mjCHField::Compile normalises the data to [0, 1].
   for (auto& sec : root->children) {
     if (sec->tag != "asset") continue;
     for (auto& ch : sec->children) {
@@ -878,8 +879,7 @@ b2mjModel* compile(const XmlNode* root) {
           const size_t b0 = sl == std::string::npos ? 0 : sl + 1;
           name = file.substr(b0, dot == std::string::npos || dot < b0 ? std::string::npos : dot - b0);
         }
-        if (file.size() >= 4 && (file.substr(file.size() - 4) == ".png" || file.substr(file.size() - 4) == ".PNG"))
-          fail(ch.get(), "hfield PNG files are not supported (no PNG decoder): use the binary format or the elevation attribute");
+        const bool png = file.size() >= 4 && (file.substr(file.size() - 4) == ".png" || file.substr(file.size() - 4) == ".PNG");
         if (file.empty() || file[0] != '/') {
           std::string base = ctx.meshdir;
           if (base.empty() || base[0] != '/') base = model_dir() + (model_dir().empty() || base.empty() ? "" : "/") + base;
@@ -887,6 +887,21 @@ b2mjModel* compile(const XmlNode* root) {
         }
         FILE* fp = std::fopen(file.c_str(), "rb");
         if (!fp) fail(ch.get(), "cannot open hfield file '" + file + "'");
+        if (png) {  // 8-bit grey image, image row 0 = the far (+y) edge of the field (mjCHField::LoadPNG flips the rows)
+          std::vector<uint8_t> bytes, img;
+          uint8_t chunk[65536];
+          for (size_t got; (got = std::fread(chunk, 1, sizeof(chunk), fp)) > 0;) bytes.insert(bytes.end(), chunk, chunk + got);
+          std::fclose(fp);
+          unsigned w = 0, h = 0;
+          std::string perr;
+          if (!png_decode_gray8(bytes.data(), bytes.size(), img, w, h, perr)) fail(ch.get(), "hfield file '" + file + "': " + perr);
+          if (w < 2 || h < 2) fail(ch.get(), "hfield file '" + file + "' needs at least 2 x 2 pixels");
+          hf.nrow = (int)h;
+          hf.ncol = (int)w;
+          hf.data.resize((size_t)w * h);
+          for (unsigned r = 0; r < h; r++)
+            for (unsigned c = 0; c < w; c++) hf.data[c + (size_t)(h - 1 - r) * w] = img[c + (size_t)r * w];
+        } else {
         int32_t dims[2] = {0, 0};
         bool ok = std::fread(dims, sizeof(int32_t), 2, fp) == 2 && dims[0] >= 2 && dims[1] >= 2 && (int64_t)dims[0] * dims[1] < (1 << 26);
         std::vector<float> buf;
@@ -899,6 +914,7 @@ b2mjModel* compile(const XmlNode* root) {
         hf.nrow = dims[0];
         hf.ncol = dims[1];
         hf.data.assign(buf.begin(), buf.end());
+        }
       } else {
         hf.nrow = a.integer("nrow", 0);
         hf.ncol = a.integer("ncol", 0);

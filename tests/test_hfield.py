@@ -44,12 +44,111 @@ def test_hfield_compile_facts(capi, tmp_path):
                                           [("0 0 0.3", '<geom type="sphere" size="0.05"/>')]))
     mb = capi.Model.from_xml_file(str(tmp_path / "m.xml"))
     np.testing.assert_array_equal(mb.hfield_data, m.hfield_data)
-    # PNG needs the decoder the survey puts out of scope: rejected by name, not ignored
-    with pytest.raises(capi.B2mjError, match="PNG"):
+    # a PNG that does not exist is an error, not an empty field
+    with pytest.raises(capi.B2mjError, match="cannot open"):
         capi.Model.from_xml_string(scene('<hfield name="t" file="t.png" size="1 1 1 1"/>', []))
     # plane-hfield and hfield-hfield have no narrowphase function: no candidate pairs
     m2 = capi.Model.from_xml_string(scene(hf, []).replace("</worldbody>", '<geom type="plane" size="1 1 .1"/></worldbody>'))
     assert m2.ncollpair == 0
+
+
+def _png(pix, ctype, depth, filt="cycle", palette=None, level=6, split=1, interlace=0):
+    """Writes a PNG by hand (zlib + CRC from the Python standard library): pix is (h, w, channels) of unsigned samples of
+    `depth` bits; filt is a filter type 0-4 or "cycle"; split = number of IDAT chunks."""
+    import zlib
+    h, w, ch = pix.shape
+    rows = []
+    for r in range(h):
+        if depth == 16:
+            line = pix[r].astype(">u2").tobytes()
+        elif depth == 8:
+            line = pix[r].astype("u1").tobytes()
+        else:
+            bits = "".join(format(int(v), f"0{depth}b") for v in pix[r].ravel())
+            bits += "0" * (-len(bits) % 8)
+            line = bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+        rows.append(np.frombuffer(line, np.uint8).astype(int))
+    bpp = max(1, ch * depth // 8)
+    out, prev = bytearray(), np.zeros_like(rows[0])
+    for r, cur in enumerate(rows):
+        f = r % 5 if filt == "cycle" else filt
+        a = np.concatenate([np.zeros(bpp, int), cur[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+        c = np.concatenate([np.zeros(bpp, int), prev[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+        b = prev
+        if f == 4:
+            pp = a + b - c
+            pa, pb, pc = abs(pp - a), abs(pp - b), abs(pp - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+        else:
+            pred = [0 * a, a, b, (a + b) // 2][f]
+        out.append(f)
+        out += bytes(((cur - pred) % 256).astype(np.uint8))
+        prev = cur
+    z = zlib.compress(bytes(out), level)
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+    png += chunk(b"tEXt", b"Comment\0ancillary chunks are skipped")
+    if palette is not None:
+        png += chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    step = -(-len(z) // split)
+    for i in range(0, len(z), step):
+        png += chunk(b"IDAT", z[i:i + step])
+    return png + chunk(b"IEND", b"")
+
+
+def test_hfield_from_png_every_colour_type_depth_and_filter(capi, tmp_path):
+    """<hfield file="*.png"> (mjCHField::LoadPNG): 8-bit grey whatever the file holds -- red channel of colour images,
+    high byte of 16-bit samples, scaled shallow greys, palette lookup -- rows flipped so image row 0 is the +y edge, then
+    normalised to [0, 1].  Files are written here byte by byte; the compressor is Python's zlib (stored, fixed and
+    dynamic DEFLATE blocks through the compression level), the decoder is the library's own."""
+    rng = np.random.default_rng(7)
+    h, w = 13, 17
+
+    def load(png):
+        (tmp_path / "t.png").write_bytes(png)
+        (tmp_path / "m.xml").write_text(scene('<hfield file="t.png" size="0.6 0.5 0.08 0.05"/>', []))
+        return capi.Model.from_xml_file(str(tmp_path / "m.xml"))
+
+    def expect(grey8):
+        g = grey8[::-1].astype(np.float64)
+        return ((g - g.min()) / (g.max() - g.min())).astype(np.float32)
+
+    cases = []
+    for depth in (1, 2, 4, 8, 16):
+        pix = rng.integers(0, 2 ** depth, (h, w, 1))
+        grey = pix[..., 0] >> 8 if depth == 16 else pix[..., 0] * 255 // (2 ** depth - 1)
+        cases.append((f"grey{depth}", _png(pix, 0, depth), grey))
+    for ctype, ch in ((2, 3), (4, 2), (6, 4)):
+        for depth in (8, 16):
+            pix = rng.integers(0, 2 ** depth, (h, w, ch))
+            cases.append((f"type{ctype}/{depth}", _png(pix, ctype, depth), pix[..., 0] >> (depth - 8)))
+    for depth in (1, 2, 4, 8):
+        pal = rng.integers(0, 256, (2 ** depth, 3))
+        pix = rng.integers(0, 2 ** depth, (h, w, 1))
+        cases.append((f"palette{depth}", _png(pix, 3, depth, palette=pal), pal[pix[..., 0], 0]))
+    smooth = (np.add.outer(np.arange(h) * 9, np.arange(w) * 5) % 256)[..., None]  # long matches: overlapping copies
+    for f in range(5):
+        cases.append((f"filter{f}", _png(smooth, 0, 8, filt=f), smooth[..., 0]))
+    for level in (0, 1, 9):  # 0 = stored blocks; 1 = mostly fixed Huffman on short input; 9 = dynamic
+        cases.append((f"level{level}", _png(smooth, 0, 8, level=level, split=3), smooth[..., 0]))
+    big = rng.integers(0, 256, (300, 260, 1))  # > 64 KB of raw data: several stored blocks at level 0, 32 KB window
+    cases.append(("big-stored", _png(big, 0, 8, level=0), big[..., 0]))
+    cases.append(("big-dynamic", _png(big // 16 * 16, 0, 8, level=9, split=4), big[..., 0] // 16 * 16))
+    for name, png, grey in cases:
+        m = load(png)
+        assert (m.hfield_nrow[0], m.hfield_ncol[0]) == grey.shape, name
+        np.testing.assert_array_equal(m.hfield_data.reshape(grey.shape), expect(grey), err_msg=name)
+    assert len(cases) == 25
+
+    good = _png(smooth, 0, 8)
+    bad = bytearray(good)
+    bad[60] ^= 0x40  # a flipped bit inside the IDAT body: the chunk CRC catches it
+    for png, word in ((bytes(bad), "CRC"), (good[:-30], "truncated|missing"), (b"GIF89a" + good[6:], "signature"),
+                      (_png(smooth, 0, 8, interlace=1), "interlaced")):
+        with pytest.raises(capi.B2mjError, match=word):
+            load(png)
 
 
 def test_hfield_survives_the_binary_model_format_and_set_const(capi, tmp_path):
