@@ -141,6 +141,12 @@ def test_hfield_from_png_every_colour_type_depth_and_filter(capi, tmp_path):
         assert (m.hfield_nrow[0], m.hfield_ncol[0]) == grey.shape, name
         np.testing.assert_array_equal(m.hfield_data.reshape(grey.shape), expect(grey), err_msg=name)
     assert len(cases) == 25
+    # the same elevations given inline produce the same arrays (the inline path is the one the GPU terrain tests use)
+    el8 = rng.integers(0, 256, (h, w))
+    inline = capi.Model.from_xml_string(scene(f'<hfield name="t" nrow="{h}" ncol="{w}" size="0.6 0.5 0.08 0.05" '
+                                              f'elevation="{" ".join(map(str, el8.ravel()))}"/>', []))
+    from_file = load(_png(el8[::-1, :, None], 0, 8))  # arrays are views into the model: keep it alive
+    np.testing.assert_array_equal(from_file.hfield_data, inline.hfield_data)
 
     good = _png(smooth, 0, 8)
     bad = bytearray(good)
