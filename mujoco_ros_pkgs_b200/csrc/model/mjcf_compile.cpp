@@ -322,6 +322,18 @@ void eig3(const double* A_in, double* eval, double* V) {
   if (dot3(cr, c2) < 0) { V[2] = -V[2]; V[5] = -V[5]; V[8] = -V[8]; }
 }
 
+// <frame pos=.. quat=.. childclass=..> (MuJoCo 3 files): a pure coordinate transform applied to everything it
+// contains; it leaves no trace in the model.  F = pose of the enclosing frames relative to the body.
+struct Frame {
+  double pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0};
+  bool identity = true;
+};
+struct PendingBody {
+  const XmlNode* node;
+  Frame frame;
+  std::string childclass;
+};
+
 struct Builder {
   Ctx ctx;
   std::vector<CBody> bodies;
@@ -494,35 +506,51 @@ struct Builder {
     b.sites.push_back(s);
   }
 
-  void read_body(const XmlNode* n, int parent, std::string childclass) {
-    int id = (int)bodies.size();
-    if (n->tag == "worldbody") {
-      id = 0;
-    } else {
-      bodies.emplace_back();
-      CBody& b = bodies.back();
-      b.parent = parent;
-      AttrMap em;
-      for (auto& kv : n->attrs) em[kv.first] = kv.second;
-      A a{em, n};
-      b.name = a.str("name");
-      a.vec("pos", b.pos, 3, 3);
-      orientation(ctx, a, b.quat);
-      b.mocap = a.str("mocap", "false") == "true";
-      b.gravcomp = a.num("gravcomp", 0);
-      if (a.has("childclass")) childclass = a.str("childclass");
+  static void frame_apply(const Frame& F, double* pos, double* quat) {
+    if (F.identity) return;
+    double p[3], q[4];
+    rotvecquat(p, pos, F.quat);
+    for (int k = 0; k < 3; k++) pos[k] = F.pos[k] + p[k];
+    if (quat) {
+      mulquat(q, F.quat, quat);
+      std::copy(q, q + 4, quat);
     }
+  }
+
+  // the non-body children of a body or frame node, in document order; child bodies are queued with their frame
+  void read_children(const XmlNode* n, int id, const std::string& childclass, const Frame& F, std::vector<PendingBody>& queue) {
     for (auto& ch : n->children) {
       const std::string& t = ch->tag;
-      if (t == "body") continue;
-      if (t == "joint" || t == "freejoint") {
+      if (t == "body") {
+        queue.push_back({ch.get(), F, childclass});
+      } else if (t == "frame") {
+        AttrMap em;
+        for (auto& kv : ch->attrs) em[kv.first] = kv.second;
+        A a{em, ch.get()};
+        Frame G;
+        a.vec("pos", G.pos, 3, 3);
+        orientation(ctx, a, G.quat);
+        frame_apply(F, G.pos, G.quat);
+        G.identity = false;
+        read_children(ch.get(), id, a.has("childclass") ? a.str("childclass") : childclass, G, queue);
+      } else if (t == "joint" || t == "freejoint") {
         if (id == 0) fail(ch.get(), "joints are not allowed in the world body");
         read_joint(ch.get(), childclass, bodies[id]);
+        CJoint& j = bodies[id].joints.back();
+        if (!F.identity) {
+          double ax[3];
+          frame_apply(F, j.pos, nullptr);
+          rotvecquat(ax, j.axis, F.quat);
+          std::copy(ax, ax + 3, j.axis);
+        }
       } else if (t == "geom") {
         read_geom(ch.get(), childclass, bodies[id]);
+        frame_apply(F, bodies[id].geoms.back().pos, bodies[id].geoms.back().quat);
       } else if (t == "site") {
         read_site(ch.get(), childclass, bodies[id]);
+        frame_apply(F, bodies[id].sites.back().pos, bodies[id].sites.back().quat);
       } else if (t == "inertial") {
+        if (!F.identity) fail(ch.get(), "inertial is not allowed inside a frame");
         CBody& b = bodies[id];
         AttrMap em;
         for (auto& kv : ch->attrs) em[kv.first] = kv.second;
@@ -545,13 +573,37 @@ struct Builder {
         // rendering only: no effect on the physics
       } else if (t == "composite") {
         fail(ch.get(), "composite bodies are not supported (expand them in the model file)");
+      } else if (t == "replicate") {
+        fail(ch.get(), "replicate is not supported (expand the copies in the model file)");
       } else {
         fail(ch.get(), "unsupported element inside body");
       }
     }
+  }
+
+  void read_body(const XmlNode* n, int parent, std::string childclass, const Frame& F = Frame()) {
+    int id = (int)bodies.size();
+    if (n->tag == "worldbody") {
+      id = 0;
+    } else {
+      bodies.emplace_back();
+      CBody& b = bodies.back();
+      b.parent = parent;
+      AttrMap em;
+      for (auto& kv : n->attrs) em[kv.first] = kv.second;
+      A a{em, n};
+      b.name = a.str("name");
+      a.vec("pos", b.pos, 3, 3);
+      orientation(ctx, a, b.quat);
+      frame_apply(F, b.pos, b.quat);
+      b.mocap = a.str("mocap", "false") == "true";
+      b.gravcomp = a.num("gravcomp", 0);
+      if (a.has("childclass")) childclass = a.str("childclass");
+    }
+    std::vector<PendingBody> queue;
+    read_children(n, id, childclass, Frame(), queue);
     if (id != 0 && bodies[id].mocap && !bodies[id].joints.empty()) fail(n, "mocap body cannot have joints");
-    for (auto& ch : n->children)
-      if (ch->tag == "body") read_body(ch.get(), id, childclass);
+    for (auto& pb : queue) read_body(pb.node, id, pb.childclass, pb.frame);
   }
 
   void body_inertia_from_geoms(CBody& b) {

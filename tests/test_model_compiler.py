@@ -227,3 +227,66 @@ def test_override_flag_rewrites_every_contact_parameter(capi, orc):
     o2.forward()
     np.testing.assert_allclose(o2.get("contact_solref")[:2], [0.03, 1])
     np.testing.assert_allclose(o2.get("contact_includemargin")[:1], 0.2)
+
+
+def test_frame_elements_are_pure_coordinate_transforms(capi):
+    """<frame> (MuJoCo 3 model files): everything inside takes the frame's pose -- geoms, sites, joint anchors and axes,
+    child bodies, nested frames, fromto geoms -- and its childclass; the frame itself leaves nothing in the model.  The
+    expected model is the same scene with every pose composed here with numpy and written out flat."""
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1:] @ b[1:], *(a[0] * b[1:] + b[0] * a[1:] + np.cross(a[1:], b[1:]))])
+
+    def rot(q, v):
+        return qmul(qmul(q, np.array([0, *v])), q * [1, -1, -1, -1])[1:]
+
+    def compose(F, pos, quat=(1, 0, 0, 0)):
+        return F[0] + rot(F[1], np.asarray(pos, float)), qmul(F[1], np.asarray(quat, float))
+
+    def fmt(v):
+        return " ".join(repr(float(x)) for x in v)
+    s, c = np.sin(np.pi / 4), np.cos(np.pi / 4)
+    F1 = (np.array([0, 0, 1.0]), np.array([c, 0, 0, s]))          # pos 0 0 1, 90 deg about z
+    F2 = (np.array([0, .5, 0]), np.array([c, s, 0, 0]))           # inside body a: 90 deg about x
+    F3 = compose(F2, [.1, .1, .1])                                # nested in F2, no rotation of its own
+    qa = np.array([np.cos(np.pi / 12), 0, np.sin(np.pi / 12), 0])  # body a: 30 deg about y
+    framed = f"""<mujoco><default><default class="c"><geom size="0.03" friction="0.5 0.01 0.001"/></default></default><worldbody>
+      <frame pos="0 0 1" quat="{fmt(F1[1])}">
+        <geom name="g0" type="box" size=".1 .2 .3" pos="1 0 0"/>
+        <body name="a" pos="1 0 0" quat="{fmt(qa)}">
+          <joint name="ja" axis="1 0 0"/><geom name="ga" size="0.1"/>
+          <frame pos="0 .5 0" quat="{fmt(F2[1])}" childclass="c">
+            <joint name="jb" type="slide" axis="0 0 1" pos="0 0 .1"/>
+            <geom name="gb" type="capsule" fromto="0 0 0 0 0 .2"/>
+            <site name="sb" pos=".1 0 0" quat="{fmt(qa)}"/>
+            <frame pos=".1 .1 .1"><body name="b" pos="0 0 .2"><joint name="jc" axis="0 1 0"/><geom name="gc" size=".05"/></body></frame>
+          </frame>
+          <body name="c" pos="0 0 -.3"><joint name="jd" axis="0 0 1"/><geom name="gd" size=".04"/></body>
+        </body>
+      </frame></worldbody></mujoco>"""
+    g0, a = compose(F1, [1, 0, 0]), compose(F1, [1, 0, 0], qa)
+    sb, b = compose(F2, [.1, 0, 0], qa), compose(F3, [0, 0, .2])
+    ft = np.concatenate([compose(F2, [0, 0, 0])[0], compose(F2, [0, 0, .2])[0]])
+    flat = f"""<mujoco><worldbody>
+      <geom name="g0" type="box" size=".1 .2 .3" pos="{fmt(g0[0])}" quat="{fmt(g0[1])}"/>
+      <body name="a" pos="{fmt(a[0])}" quat="{fmt(a[1])}">
+        <joint name="ja" axis="1 0 0"/><geom name="ga" size="0.1"/>
+        <joint name="jb" type="slide" axis="{fmt(rot(F2[1], [0, 0, 1]))}" pos="{fmt(compose(F2, [0, 0, .1])[0])}"/>
+        <geom name="gb" type="capsule" fromto="{fmt(ft)}" size="0.03" friction="0.5 0.01 0.001"/>
+        <site name="sb" pos="{fmt(sb[0])}" quat="{fmt(sb[1])}"/>
+        <body name="b" pos="{fmt(b[0])}" quat="{fmt(b[1])}"><joint name="jc" axis="0 1 0"/><geom name="gc" size=".05" friction="0.5 0.01 0.001"/></body>
+        <body name="c" pos="0 0 -.3"><joint name="jd" axis="0 0 1"/><geom name="gd" size=".04"/></body>
+      </body></worldbody></mujoco>"""
+    mf, me = capi.Model.from_xml_string(framed), capi.Model.from_xml_string(flat)
+    assert (mf.nbody, mf.njnt, mf.ngeom, mf.nsite) == (me.nbody, me.njnt, me.ngeom, me.nsite) == (4, 4, 5, 1)
+    for f in ("body_parentid", "jnt_bodyid", "jnt_type", "geom_bodyid", "geom_type", "site_bodyid"):
+        np.testing.assert_array_equal(getattr(mf, f), getattr(me, f), err_msg=f)
+    for f in ("body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "jnt_pos", "jnt_axis", "geom_pos",
+              "geom_size", "geom_friction", "site_pos", "site_quat", "dof_invweight0", "body_invweight0"):
+        np.testing.assert_allclose(getattr(mf, f), getattr(me, f), rtol=1e-12, atol=1e-14, err_msg=f)
+    # q and -q are the same rotation (the fromto capsule comes out with the other sign)
+    np.testing.assert_allclose(np.abs(np.sum(mf.geom_quat.reshape(-1, 4) * me.geom_quat.reshape(-1, 4), axis=1)), 1, atol=1e-14)
+    assert [mf.name2id(capi.OBJ_BODY, n) for n in "abc"] == [1, 2, 3]  # document order, depth first
+    for bad, word in (('<frame><inertial pos="0 0 0" mass="1" diaginertia="1 1 1"/></frame>', "inertial"),
+                      ('<replicate count="3"><geom size=".1"/></replicate>', "replicate")):
+        with pytest.raises(capi.B2mjError, match=word):
+            capi.Model.from_xml_string(f'<mujoco><worldbody><body>{bad}</body></worldbody></mujoco>')
