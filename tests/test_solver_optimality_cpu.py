@@ -1,0 +1,119 @@
+"""Algorithm-independent check of the oracle's constraint stage: whatever solver ran, the
+answer has to be the minimiser of MuJoCo's convex problem  1/2 (a - a_smooth)' M (a - a_smooth) + s(J a - aref).
+Its optimality conditions need no solver code to state:
+    stationarity   M (qacc - qacc_smooth) = J' f
+    row laws       equality:       f = -D r                      (r = J qacc - aref)
+                   friction loss:  f = clamp(-D r, -loss, +loss)
+                   limit, frictionless and pyramidal contact rows:  f = max(0, -D r)
+                   elliptic contacts: f inside the friction cone, f = 0 when the contact separates (top zone),
+                                      f = -D r when r lies in the polar cone (bottom zone)
+They are evaluated here with numpy from the fields the oracle exposes (efc_J, efc_D, efc_aref, efc_force, qM, ...), on
+the bench models in their contact-rich states.  The GPU path is held to the oracle per field; this file holds the oracle
+to the problem statement."""
+import numpy as np
+import pytest
+
+EQUALITY, FRICTION_DOF, FRICTION_TENDON, LIMIT_JOINT, LIMIT_TENDON, FRICTIONLESS, PYRAMIDAL, ELLIPTIC = range(8)
+PGS, CG, NEWTON = 0, 1, 2
+
+
+def dense_mass(m, qM):
+    M = np.zeros((m.nv, m.nv))
+    for i in range(m.nv):
+        adr, j, k = m.dof_Madr[i], i, 0
+        while j >= 0:
+            M[i, j] = M[j, i] = qM[adr + k]
+            j = m.dof_parentid[j]
+            k += 1
+    return M
+
+
+CASES = [("panda_like.xml", 0, 450, NEWTON), ("panda_like.xml", 1, 450, NEWTON), ("humanoid_like.xml", 0, 150, NEWTON),
+         ("humanoid_like.xml", 1, 150, CG), ("box_stack.xml", 0, 150, NEWTON), ("box_stack.xml", 1, 150, NEWTON),
+         ("equality_scene.xml", 0, 60, NEWTON), ("hand_like.xml", 1, 120, NEWTON), ("ROWS", 0, 400, NEWTON), ("ROWS", 0, 400, CG)]
+
+# every remaining row type in one scene: dof and tendon friction loss, joint and tendon limits, a frictionless contact
+ROWS = """<mujoco><option timestep="0.002"/><worldbody>
+  <geom type="plane" size="2 2 .1" condim="1"/>
+  <body pos="0 0 1"><joint name="a" axis="0 1 0" range="-0.4 0.4" limited="true" frictionloss="0.3"/>
+    <geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.03"/>
+    <body pos="0.4 0 0"><joint name="b" axis="0 1 0" frictionloss="0.05"/><geom type="capsule" fromto="0 0 0 0.3 0 0" size="0.03"/></body></body>
+  <body pos="1 0 0.099"><freejoint/><geom size="0.1" condim="1"/></body>
+</worldbody>
+<tendon><fixed name="t" limited="true" range="-0.3 0.5" frictionloss="0.1"><joint joint="a" coef="1"/><joint joint="b" coef="1"/></fixed></tendon>
+</mujoco>"""
+
+
+@pytest.mark.parametrize("name,cone,settle,solver", CASES)
+def test_solution_satisfies_the_optimality_conditions(name, cone, settle, solver, load_model, orc, capi):
+    m = capi.Model.from_xml_string(ROWS) if name == "ROWS" else load_model(name)
+    m.opt.cone, m.opt.solver = cone, solver
+    m.opt.tolerance, m.opt.iterations = 1e-14, 200
+    o = orc.Oracle(m)
+    rng = np.random.default_rng(4)
+    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq))
+    for s in range(settle):
+        if m.nu and s % 25 == 0:
+            lo, hi = m.actuator_ctrlrange.reshape(-1, 2).T
+            o.set("ctrl", np.where(hi > lo, rng.uniform(np.minimum(lo, hi), np.maximum(lo, hi)), rng.uniform(-1, 1, m.nu)))
+        o.step(1)
+    o.forward()
+    nefc, nv = int(o.get("nefc")[0]), m.nv
+    assert nefc > 0
+    J = o.get("efc_J")[:nefc * nv].reshape(nefc, nv)
+    D, aref, f = o.get("efc_D")[:nefc], o.get("efc_aref")[:nefc], o.get("efc_force")[:nefc]
+    typ, ids, loss = o.get("efc_type")[:nefc], o.get("efc_id")[:nefc], o.get("efc_frictionloss")[:nefc]
+    qacc, M = o.get("qacc"), dense_mass(m, o.get("qM"))
+    scale = max(1.0, np.abs(f).max())
+    eps = 2e-7 if solver == NEWTON else 1e-5  # CG stops at a looser point than Newton's quadratic convergence reaches
+    # stationarity, and the solver's own report of it
+    np.testing.assert_allclose(M @ (qacc - o.get("qacc_smooth")), J.T @ f, atol=eps * scale * max(1, np.abs(J).max()))
+    np.testing.assert_allclose(o.get("qfrc_constraint"), J.T @ f, atol=1e-9 * scale * max(1, np.abs(J).max()))
+    r = J @ qacc - aref
+    tol = eps * scale
+    seen = set()
+    i = 0
+    while i < nefc:
+        t = int(typ[i])
+        seen.add(t)
+        if t == EQUALITY:
+            assert abs(f[i] + D[i] * r[i]) < tol, (i, "equality")
+        elif t in (FRICTION_DOF, FRICTION_TENDON):
+            assert abs(f[i] - np.clip(-D[i] * r[i], -loss[i], loss[i])) < tol, (i, "friction loss")
+        elif t in (LIMIT_JOINT, LIMIT_TENDON, FRICTIONLESS, PYRAMIDAL):
+            assert abs(f[i] - max(0.0, -D[i] * r[i])) < tol, (i, "one-sided row", t)
+        else:  # elliptic contact: rows i .. i + dim - 1 belong to contact ids[i]
+            c = int(ids[i])
+            dim = int(o.get("contact_dim")[c])
+            mu = o.get("contact_friction")[5 * c:5 * c + 5][:dim - 1]
+            fn, ft = f[i], f[i + 1:i + dim]
+            assert fn > -tol and np.sqrt(np.sum((ft / mu) ** 2)) <= fn + tol, (i, "force outside the friction cone", fn, ft)
+            rn, rt = r[i], r[i + 1:i + dim]
+            # zones of MuJoCo's elliptic cost in the scaled coordinates  N = mu0 r_n,  T = |mu_j r_j| * (per-row scale);
+            # with the regularised friction mu0 the test below is the one that needs no knowledge of that scaling:
+            # a separating contact whose tangential motion is small carries no force at all
+            if rn > 0 and np.all(np.abs(rt) < 1e-12):
+                assert np.abs(f[i:i + dim]).max() < tol, (i, "top zone")
+            i += dim
+            continue
+        i += 1
+    assert seen, name
+    if name == "ROWS":
+        assert seen >= {FRICTION_DOF, FRICTION_TENDON, LIMIT_JOINT, FRICTIONLESS}, seen
+
+
+def test_the_conditions_reject_a_wrong_answer(load_model, orc):
+    """The checker itself: an under-converged PGS answer (2 sweeps) violates stationarity or a row law by far more than
+    the tolerance the test above applies."""
+    m = load_model("box_stack.xml")
+    m.opt.solver, m.opt.iterations = PGS, 2
+    o = orc.Oracle(m)
+    o.step(150)
+    o.set("qacc_warmstart", np.zeros(m.nv))
+    o.forward()
+    nefc, nv = int(o.get("nefc")[0]), m.nv
+    J = o.get("efc_J")[:nefc * nv].reshape(nefc, nv)
+    D, aref, f = o.get("efc_D")[:nefc], o.get("efc_aref")[:nefc], o.get("efc_force")[:nefc]
+    r = J @ o.get("qacc") - aref
+    worst = np.abs(f - np.maximum(0.0, -D * r)).max()
+    assert worst > 1e-3 * max(1.0, np.abs(f).max())
