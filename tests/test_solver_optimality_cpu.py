@@ -117,3 +117,72 @@ def test_the_conditions_reject_a_wrong_answer(load_model, orc):
     r = J @ o.get("qacc") - aref
     worst = np.abs(f - np.maximum(0.0, -D * r)).max()
     assert worst > 1e-3 * max(1.0, np.abs(f).max())
+
+
+def impedance(solimp, x):
+    """MuJoCo's documented impedance curve d(r) (XML reference, solimp): x = pos - margin."""
+    d0, dw = np.clip(solimp[:2], 1e-4, 0.9999)
+    width, mid, power = max(0.0, solimp[2]), np.clip(solimp[3], 1e-4, 0.9999), max(1.0, solimp[4])
+    if d0 == dw or width <= 1e-15:
+        return 0.5 * (d0 + dw)
+    x = abs(x) / width
+    if x >= 1 or x <= 0:
+        return dw if x >= 1 else d0
+    if power == 1:
+        y = x
+    elif x <= mid:
+        y = x ** power / mid ** (power - 1)
+    else:
+        y = 1 - (1 - x) ** power / (1 - mid) ** (power - 1)
+    return d0 + y * (dw - d0)
+
+
+def stiffness_damping(solref, solimp, dt):
+    dmax = np.clip(solimp[1], 1e-4, 0.9999)
+    if solref[0] > 0 and solref[1] > 0:
+        tc = max(solref[0], 2 * dt)  # refsafe
+        return 1 / (dmax * dmax * tc * tc * solref[1] * solref[1]), 2 / (dmax * tc)
+    return -solref[0] / (dmax * dmax), -solref[1] / dmax
+
+
+@pytest.mark.parametrize("name,cone,settle", [("panda_like.xml", 0, 450), ("humanoid_like.xml", 1, 150), ("box_stack.xml", 0, 150),
+                                               ("equality_scene.xml", 0, 60), ("ROWS", 0, 400)])
+def test_constraint_parameters_follow_the_documented_formulas(name, cone, settle, load_model, orc, capi):
+    """Row M6 against MuJoCo's published definitions (Computation chapter, "solver parameters"): reference acceleration
+    aref = -B vel - K d (pos - margin), regulariser R = (1 - d) / d * diagApprox, D = 1 / R, with (K, B) from solref
+    (time constant clamped at two time steps) and the impedance d from the solimp curve -- recomputed here with numpy
+    from the per-row inputs the oracle exposes."""
+    m = capi.Model.from_xml_string(ROWS) if name == "ROWS" else load_model(name)
+    m.opt.cone = cone
+    o = orc.Oracle(m)
+    rng = np.random.default_rng(9)
+    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq))
+    o.step(settle)
+    o.forward()
+    nefc = int(o.get("nefc")[0])
+    typ, ids = o.get("efc_type")[:nefc], o.get("efc_id")[:nefc]
+    pos, margin, vel = o.get("efc_pos")[:nefc], o.get("efc_margin")[:nefc], o.get("efc_vel")[:nefc]
+    kbip = o.get("efc_KBIP")[:4 * nefc].reshape(nefc, 4)
+    aref, R, D, diag = (o.get(k)[:nefc] for k in ("efc_aref", "efc_R", "efc_D", "efc_diagApprox"))
+    np.testing.assert_allclose(aref, -kbip[:, 1] * vel - kbip[:, 0] * kbip[:, 2] * (pos - margin), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(D * R, 1, rtol=1e-12)
+    dt, checked, first_of_contact = m.opt.timestep, 0, {}
+    for i in range(nefc):
+        t, k = int(typ[i]), int(ids[i])
+        if t == LIMIT_JOINT:
+            solref, solimp = m.jnt_solref.reshape(-1, 2)[k], m.jnt_solimp.reshape(-1, 5)[k]
+        elif t == EQUALITY:
+            solref, solimp = m.eq_solref.reshape(-1, 2)[k], m.eq_solimp.reshape(-1, 5)[k]
+        elif t in (FRICTIONLESS, PYRAMIDAL, ELLIPTIC):
+            if t == ELLIPTIC and first_of_contact.setdefault(k, i) != i:
+                continue  # tangential rows of an elliptic contact: scaled from the normal row, not from this formula
+            solref, solimp = o.get("contact_solref")[2 * k:2 * k + 2], o.get("contact_solimp")[5 * k:5 * k + 5]
+        else:
+            continue
+        d = impedance(solimp, pos[i] - margin[i])
+        K, B = stiffness_damping(solref, solimp, dt)
+        np.testing.assert_allclose(kbip[i, :3], [K, B, d], rtol=1e-12, err_msg=f"row {i} type {t}")
+        if t != PYRAMIDAL:  # pyramid edges carry an extra friction-dependent factor
+            np.testing.assert_allclose(R[i], max(1e-15, (1 - d) / d * diag[i]), rtol=1e-12, err_msg=f"row {i} type {t}")
+        checked += 1
+    assert checked >= 2, (name, checked)
