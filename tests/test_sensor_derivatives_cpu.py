@@ -1,0 +1,79 @@
+"""Row M10 held to definitions instead of to a restated formula: velocity sensors are time derivatives of position
+sensors, acceleration sensors are time derivatives of velocity sensors (plus the gravity offset MuJoCo's accelerations
+carry), body-frame sensors are the world-frame ones rotated into the site frame.  Central differences over the
+oracle's own forward pass; no sensor code is involved in computing the expected values."""
+import numpy as np
+import pytest
+
+from test_solver_optimality_cpu import integrate_pos
+
+XML = """<mujoco><option timestep="0.002" gravity="0 0 -9.81"/><worldbody>
+  <body name="root" pos="0 0 1"><freejoint/><geom type="box" size="0.1 0.06 0.04"/>
+    <site name="s0" pos="0.05 0.02 0.03" euler="0.3 -0.2 0.5"/>
+    <body name="arm" pos="0.1 0 0"><joint name="h" axis="0 1 0" pos="0 0 0.01"/><geom type="capsule" fromto="0 0 0 0.25 0 0" size="0.03"/>
+      <body name="tip" pos="0.25 0 0"><joint name="b" type="ball"/><geom type="ellipsoid" size="0.06 0.04 0.03" pos="0.05 0 0"/>
+        <site name="s1" pos="0.08 0.01 -0.02" euler="-0.4 0.1 0.7"/>
+        <body name="rod" pos="0.1 0 0"><joint name="sl" type="slide" axis="0.6 0 0.8"/><geom size="0.03"/><site name="s2" pos="0 0.02 0"/></body>
+      </body></body></body>
+</worldbody><sensor>
+  %s
+  <subtreecom name="com" body="arm"/><subtreelinvel name="comvel" body="arm"/>
+  <ballquat name="bq" joint="b"/><ballangvel name="bw" joint="b"/><jointpos name="jp" joint="sl"/><jointvel name="jv" joint="sl"/>
+</sensor></mujoco>"""
+PER_SITE = ('<framepos name="p{0}" objtype="site" objname="{0}"/><framequat name="q{0}" objtype="site" objname="{0}"/>'
+            '<framelinvel name="v{0}" objtype="site" objname="{0}"/><frameangvel name="w{0}" objtype="site" objname="{0}"/>'
+            '<framelinacc name="a{0}" objtype="site" objname="{0}"/><frameangacc name="al{0}" objtype="site" objname="{0}"/>'
+            '<velocimeter name="vm{0}" site="{0}"/><gyro name="gy{0}" site="{0}"/><accelerometer name="ac{0}" site="{0}"/>'
+            '<framexaxis name="x{0}" objtype="site" objname="{0}"/><frameyaxis name="y{0}" objtype="site" objname="{0}"/>'
+            '<framezaxis name="z{0}" objtype="site" objname="{0}"/>')
+SITES = ("s0", "s1", "s2")
+
+
+def qmul(a, b):
+    return np.array([a[0] * b[0] - a[1:] @ b[1:], *(a[0] * b[1:] + b[0] * a[1:] + np.cross(a[1:], b[1:]))])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_velocity_and_acceleration_sensors_are_time_derivatives(seed, capi, orc):
+    m = capi.Model.from_xml_string(XML % "".join(PER_SITE.format(s) for s in SITES))
+    o = orc.Oracle(m)
+    rng = np.random.default_rng(seed)
+    q0 = m.qpos0.copy()
+    q0[3:7] = rng.normal(size=4)
+    q0[3:7] /= np.linalg.norm(q0[3:7])
+    q0[8:12] = rng.normal(size=4)
+    q0[8:12] /= np.linalg.norm(q0[8:12])
+    q0[7], q0[12] = rng.uniform(-1, 1), rng.uniform(-0.05, 0.05)
+    v0 = rng.uniform(-2, 2, m.nv)
+
+    def read(q, v):
+        o.set("qpos", q)
+        o.set("qvel", v)
+        o.forward()
+        sd = o.get("sensordata").copy()
+        out = {}
+        for i in range(m.nsensor):
+            out[m.id2name(capi.OBJ_SENSOR, i)] = sd[m.sensor_adr[i]:m.sensor_adr[i] + m.sensor_dim[i]]
+        return out, o.get("qacc").copy()
+    now, qacc = read(q0, v0)
+    h = 1e-5
+    # the state a moment later / earlier along the true motion: q advanced with v (+ h^2/2 qacc), v with qacc
+    fwd, _ = read(integrate_pos(m, integrate_pos(m, q0, v0, h), qacc, 0.5 * h * h), v0 + h * qacc)
+    bwd, _ = read(integrate_pos(m, integrate_pos(m, q0, v0, -h), qacc, 0.5 * h * h), v0 - h * qacc)
+    ddt = lambda k: (fwd[k] - bwd[k]) / (2 * h)  # noqa: E731
+    g = np.array([0, 0, 9.81])
+    for s in SITES:
+        R = np.stack([now["x" + s], now["y" + s], now["z" + s]], axis=1)  # site axes as columns
+        np.testing.assert_allclose(now["v" + s], ddt("p" + s), rtol=1e-6, atol=1e-7, err_msg=f"framelinvel {s}")
+        w_fd = 2 * qmul(ddt("q" + s), now["q" + s] * [1, -1, -1, -1])[1:]  # world-frame angular velocity from dq/dt
+        np.testing.assert_allclose(now["w" + s], w_fd, rtol=1e-6, atol=1e-7, err_msg=f"frameangvel {s}")
+        np.testing.assert_allclose(now["vm" + s], R.T @ now["v" + s], rtol=1e-10, atol=1e-12, err_msg=f"velocimeter {s}")
+        np.testing.assert_allclose(now["gy" + s], R.T @ now["w" + s], rtol=1e-10, atol=1e-12, err_msg=f"gyro {s}")
+        # MuJoCo's accelerations are relative to a world that accelerates at -gravity
+        np.testing.assert_allclose(now["a" + s], ddt("v" + s) + g, rtol=2e-5, atol=2e-5, err_msg=f"framelinacc {s}")
+        np.testing.assert_allclose(now["al" + s], ddt("w" + s), rtol=2e-5, atol=2e-5, err_msg=f"frameangacc {s}")
+        np.testing.assert_allclose(now["ac" + s], R.T @ now["a" + s], rtol=1e-10, atol=1e-11, err_msg=f"accelerometer {s}")
+    np.testing.assert_allclose(now["comvel"], ddt("com"), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(now["jv"], ddt("jp"), rtol=1e-6, atol=1e-8)
+    bw_fd = 2 * qmul(now["bq"] * [1, -1, -1, -1], ddt("bq"))[1:]  # ball joint: angular velocity in the child frame
+    np.testing.assert_allclose(now["bw"], bw_fd, rtol=1e-6, atol=1e-7)
