@@ -18,8 +18,14 @@ XML = """<mujoco><option timestep="0.002" gravity="0 0 -9.81"/><worldbody>
 </worldbody><sensor>
   %s
   <subtreecom name="com" body="arm"/><subtreelinvel name="comvel" body="arm"/>
+  <subtreecom name="rodcom" body="rod"/><force name="frc" site="s2"/>
+  <tendonpos name="tp" tendon="t"/><tendonvel name="tv" tendon="t"/><actuatorpos name="ap" actuator="act"/>
+  <actuatorvel name="av" actuator="act"/><actuatorpos name="ap2" actuator="act2"/><actuatorvel name="av2" actuator="act2"/>
   <ballquat name="bq" joint="b"/><ballangvel name="bw" joint="b"/><jointpos name="jp" joint="sl"/><jointvel name="jv" joint="sl"/>
-</sensor></mujoco>"""
+</sensor>
+<tendon><spatial name="t"><site site="s0"/><site site="s1"/><pulley divisor="2"/><site site="s1"/><site site="s2"/></spatial></tendon>
+<actuator><general name="act" tendon="t" gear="3"/><general name="act2" joint="h" gear="-2"/></actuator>
+</mujoco>"""
 PER_SITE = ('<framepos name="p{0}" objtype="site" objname="{0}"/><framequat name="q{0}" objtype="site" objname="{0}"/>'
             '<framelinvel name="v{0}" objtype="site" objname="{0}"/><frameangvel name="w{0}" objtype="site" objname="{0}"/>'
             '<framelinacc name="a{0}" objtype="site" objname="{0}"/><frameangacc name="al{0}" objtype="site" objname="{0}"/>'
@@ -75,5 +81,15 @@ def test_velocity_and_acceleration_sensors_are_time_derivatives(seed, capi, orc)
         np.testing.assert_allclose(now["ac" + s], R.T @ now["a" + s], rtol=1e-10, atol=1e-11, err_msg=f"accelerometer {s}")
     np.testing.assert_allclose(now["comvel"], ddt("com"), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(now["jv"], ddt("jp"), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(now["tv"], ddt("tp"), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(now["av"], ddt("ap"), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(now["av2"], ddt("ap2"), rtol=1e-6, atol=1e-8)
+    assert abs(now["av"][0]) > 1e-3 and abs(now["av"][0] - 3 * now["tv"][0]) < 1e-12
+    # force sensor on a leaf body with nothing else acting on it: Newton's second law for the body, in the site frame
+    # (MuJoCo's sign: the force the parent exerts on the child; accelerations carry the gravity offset)
+    a_com = (fwd["rodcom"] - 2 * now["rodcom"] + bwd["rodcom"]) / (h * h)
+    mass = m.body_mass[m.name2id(capi.OBJ_BODY, "rod")]
+    R2 = np.stack([now["xs2"], now["ys2"], now["zs2"]], axis=1)
+    np.testing.assert_allclose(now["frc"], R2.T @ (mass * (a_com + g)), rtol=1e-3, atol=2e-3 * mass * 9.81)
     bw_fd = 2 * qmul(now["bq"] * [1, -1, -1, -1], ddt("bq"))[1:]  # ball joint: angular velocity in the child frame
     np.testing.assert_allclose(now["bw"], bw_fd, rtol=1e-6, atol=1e-7)
