@@ -93,3 +93,43 @@ def test_velocity_and_acceleration_sensors_are_time_derivatives(seed, capi, orc)
     np.testing.assert_allclose(now["frc"], R2.T @ (mass * (a_com + g)), rtol=1e-3, atol=2e-3 * mass * 9.81)
     bw_fd = 2 * qmul(now["bq"] * [1, -1, -1, -1], ddt("bq"))[1:]  # ball joint: angular velocity in the child frame
     np.testing.assert_allclose(now["bw"], bw_fd, rtol=1e-6, atol=1e-7)
+
+
+REST = """<mujoco><compiler angle="radian"/><option timestep="0.002"/><worldbody>
+  <geom type="plane" size="2 2 .1"/>
+  <body name="ball" pos="0 0 0.1"><freejoint/><geom size="0.1" mass="1.5"/><site name="pad" type="sphere" size="0.12"/>
+    <site name="mag" euler="0.4 0.3 -0.6"/></body>
+  <body name="arm" pos="1 0 1"><joint name="h" axis="0 1 0" range="-0.5 0.5" limited="true" damping="0.5"/>
+    <geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.02" mass="0.8"/></body>
+  <body name="lift" pos="2 0 1"><joint name="s" type="slide" axis="0 0 1" damping="5"/><geom size="0.05" mass="2"/></body>
+</worldbody>
+<actuator><motor name="m" joint="s" gear="4" ctrlrange="-10 10"/></actuator>
+<sensor><touch name="touch" site="pad"/><magnetometer name="mag" site="mag"/><clock name="clock"/>
+  <jointlimitpos name="lp" joint="h"/><jointlimitvel name="lv" joint="h"/><jointlimitfrc name="lf" joint="h"/>
+  <actuatorfrc name="af" actuator="m"/><jointactuatorfrc name="jaf" joint="s"/><jointpos name="hp" joint="h"/>
+  <framezaxis name="mz" objtype="site" objname="mag"/><framexaxis name="mx" objtype="site" objname="mag"/>
+  <frameyaxis name="my" objtype="site" objname="mag"/></sensor></mujoco>"""
+
+
+@pytest.mark.parametrize("cone", ["pyramidal", "elliptic"])
+def test_force_like_sensors_at_rest_equal_the_static_loads(cone, capi, orc):
+    """Scene at rest: the touch sensor reads the ball's weight, the joint-limit force the gravity torque of the arm
+    resting on its limit, the actuator force sensor ctrl and the joint one gear x ctrl, the magnetometer the model's magnetic vector in the
+    site frame, the clock the time."""
+    m = capi.Model.from_xml_string(REST.replace('timestep="0.002"', f'timestep="0.002" cone="{cone}"'))
+    o = orc.Oracle(m)
+    o.set("ctrl", [2 * 9.81 / 4])  # holds the lift against gravity
+    o.step(3000)
+    sd = o.get("sensordata")
+    val = {m.id2name(capi.OBJ_SENSOR, i): sd[m.sensor_adr[i]:m.sensor_adr[i] + m.sensor_dim[i]] for i in range(m.nsensor)}
+    assert abs(val["touch"][0] - 1.5 * 9.81) < 1e-6 * 1.5 * 9.81
+    theta = val["hp"][0]
+    assert 0.5 < theta < 0.51  # resting just past the upper limit (positive rotation about y lowers the arm)
+    np.testing.assert_allclose(val["lf"][0], 0.8 * 9.81 * 0.2 * np.cos(theta), rtol=1e-6)
+    np.testing.assert_allclose(val["lp"][0], 0.5 - theta, rtol=1e-9)  # distance to the limit, negative when violated
+    assert abs(val["lv"][0]) < 1e-8
+    np.testing.assert_allclose(val["af"], [2 * 9.81 / 4], rtol=1e-12)  # the scalar actuator force; the gear sits in the moment arm
+    np.testing.assert_allclose(val["jaf"], [2 * 9.81], rtol=1e-12)
+    R = np.stack([val["mx"], val["my"], val["mz"]], axis=1)
+    np.testing.assert_allclose(val["mag"], R.T @ np.asarray(m.opt.magnetic), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(val["clock"], [o.get("time")[0] - 0.002], rtol=1e-12)  # sensors are computed before the time advances
