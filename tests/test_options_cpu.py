@@ -190,3 +190,24 @@ def test_noslip_keeps_sliding_contacts_sliding(capi, orc):
     o.step(250)
     a = o.get("qvel")[0] / (250 * 0.002)
     assert abs(a - 0.5 * 9.81) < 0.05 * 9.81, a
+
+
+def test_gravity_compensation_closed_forms(capi, orc):
+    """body gravcomp (mjModel.body_gravcomp, applied in mj_passive): a force -gravcomp * m * g at the body's centre of
+    mass.  gravcomp = 1 floats a free body (no torque even with an off-centre geom), 0.5 halves its fall, 2 makes it rise;
+    on a hinge the passive torque is the compensated share of the gravity torque; the gravity disable flag removes it."""
+    xml = ('<mujoco><option %s/><worldbody>'
+           '<body pos="0 0 1" gravcomp="%g"><freejoint/><geom type="box" size=".1 .05 .02" pos=".3 .1 0" mass="2"/></body>'
+           '<body pos="1 0 1" gravcomp="0.75"><joint name="h" axis="0 1 0"/><geom type="capsule" fromto="0 0 0 .4 0 0" size=".02" mass="0.8"/>'
+           '</body></worldbody></mujoco>')
+    for gc, az in ((1.0, 0.0), (0.5, -9.81 / 2), (2.0, 9.81), (0.0, -9.81)):
+        o = orc.Oracle(capi.Model.from_xml_string(xml % ("", gc)))
+        o.forward()
+        np.testing.assert_allclose(o.get("qacc")[:6], [0, 0, az, 0, 0, 0], atol=1e-12)
+        # hinge: gravity torque m g l/2 about +y lowers the arm; 75 % of it is compensated
+        np.testing.assert_allclose(o.get("qfrc_passive")[6], -0.75 * 0.8 * 9.81 * 0.2, rtol=1e-12)
+        inertia = o.get("qM")[-1]
+        np.testing.assert_allclose(o.get("qacc")[6], 0.25 * 0.8 * 9.81 * 0.2 / inertia, rtol=1e-12)
+    o = orc.Oracle(capi.Model.from_xml_string(xml % ('><flag gravity="disable"/></option><option', 1.0)))
+    o.forward()
+    assert not o.get("qfrc_passive").any() and not o.get("qacc").any()

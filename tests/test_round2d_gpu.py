@@ -45,6 +45,36 @@ def test_springdamper_and_actuator_shorthands(integ, capi, orc):
     assert np.abs(sim.get("act")).max() > 1e-3 and worst < 1e-8, worst  # smooth dynamics: far inside the 1e-5 bar
 
 
+def test_gravity_compensation(capi, orc):
+    """body gravcomp (a passive force at each compensated body's centre of mass): forward fields and injected steps."""
+    from mujoco_ros_pkgs_b200.batch import BatchSim
+    from parity_util import compare_forward_fields
+
+    xml = ARM % "Euler"
+    xml = xml.replace('<body pos="0.3 0 0">', '<body pos="0.3 0 0" gravcomp="0.6">').replace(
+        '<body pos="1 0 1">', '<body pos="1 0 1" gravcomp="1.3">').replace('<body pos="0.25 0 0">', '<body pos="0.25 0 0" gravcomp="1">')
+    model = capi.Model.from_xml_string(xml)
+    assert np.count_nonzero(model.body_gravcomp) == 3
+    nenv = 8
+    rng = np.random.default_rng(8)
+    qpos, qvel = perturbed(model, nenv, seed=6, amp=0.3)
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    worst, _ = injected_steps(model, sim, oracles, 40, rng, tag="gravcomp")
+    assert worst < 1e-8, worst
+    sim.keep_intermediates(True)
+    sim.forward()
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "act", "ctrl")}
+    for e, o in enumerate(oracles):
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.forward()
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag="gravcomp")
+    assert np.abs(sim.get("qfrc_passive")).max() > 0.1
+
+
 def test_png_terrain(capi, orc, tmp_path):
     """The same terrain as tests/test_hfield.py's box case, quantised to 8 bits and read from a PNG file: identical
     arrays to the inline-elevation model (rows flipped back), the contact set after touch-down equal to the oracle's,
