@@ -122,6 +122,7 @@ def test_warmstart_and_eulerdamp_flags(capi, orc):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(60, method="thread")
 @pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: not yet run on hardware; an XPASS in "
                    "the driver's log is the first confirmation, an xfail a device-side difference to chase")
 @pytest.mark.parametrize("flag", [f for f in FLAGS if f != "contact"])
