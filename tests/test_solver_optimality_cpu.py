@@ -32,7 +32,8 @@ def dense_mass(m, qM):
 
 CASES = [("panda_like.xml", 0, 450, NEWTON), ("panda_like.xml", 1, 450, NEWTON), ("humanoid_like.xml", 0, 150, NEWTON),
          ("humanoid_like.xml", 1, 150, CG), ("box_stack.xml", 0, 150, NEWTON), ("box_stack.xml", 1, 150, NEWTON),
-         ("equality_scene.xml", 0, 60, NEWTON), ("hand_like.xml", 1, 120, NEWTON), ("ROWS", 0, 400, NEWTON), ("ROWS", 0, 400, CG)]
+         ("equality_scene.xml", 0, 60, NEWTON), ("hand_like.xml", 1, 120, NEWTON), ("ROWS", 0, 400, NEWTON), ("ROWS", 0, 400, CG),
+         ("CONDIM", 0, 200, NEWTON), ("CONDIM", 1, 200, NEWTON), ("CONDIM", 1, 200, CG)]
 
 # every remaining row type in one scene: dof and tendon friction loss, joint and tendon limits, a frictionless contact
 ROWS = """<mujoco><option timestep="0.002"/><worldbody>
@@ -46,14 +47,42 @@ ROWS = """<mujoco><option timestep="0.002"/><worldbody>
 </mujoco>"""
 
 
+# contact dimensions 1 / 4 / 6 (torsional and rolling friction rows), margin + gap, solmix / priority mixing, spinning and
+# rolling bodies so that the extra friction rows carry force
+CONDIM = """<mujoco><option timestep="0.002" impratio="3"/><worldbody>
+  <geom name="floor" type="plane" size="3 3 .1" condim="3" friction="0.9 0.02 0.01" margin="0.004" gap="0.001" solmix="2"/>
+  <body pos="0 0 0.1"><freejoint/><geom size="0.1" condim="4" friction="0.6 0.03 0.002" priority="1"/></body>
+  <body pos="0.5 0 0.1"><freejoint/><geom size="0.1" condim="6" friction="0.7 0.01 0.004" solref="0.01 0.8" solmix="0.5"/></body>
+  <geom type="box" size="0.3 0.3 0.1" pos="1 0 0.1" condim="1"/>
+  <body pos="1 0 0.25"><freejoint/><geom type="box" size="0.08 0.06 0.05" condim="1"/></body>
+  <body pos="1.5 0 0.05"><freejoint/><geom type="capsule" size="0.05 0.1" euler="90 0 0" condim="6" margin="0.01" gap="0.003"/></body>
+  <body pos="0.5 0.5 0.32"><freejoint/><geom size="0.08" condim="4"/></body>
+  <body pos="0.5 0.5 0.1"><freejoint/><geom size="0.12" condim="6" friction="0.5 0.02 0.003"/></body>
+</worldbody></mujoco>"""
+
+
+def load_case(name, capi):
+    if name == "ROWS":
+        return capi.Model.from_xml_string(ROWS), None
+    if name == "CONDIM":
+        m = capi.Model.from_xml_string(CONDIM)
+        v = np.zeros(m.nv)
+        for b in range(6):  # every body slides, spins about the vertical and rolls
+            v[6 * b:6 * b + 6] = [0.3, -0.2, 0, 1.0, -2.0, 6.0]
+        return m, v
+    return capi.Model.from_xml_file(model_path(name)), None  # options are edited: not the shared cached model
+
+
 @pytest.mark.parametrize("name,cone,settle,solver", CASES)
 def test_solution_satisfies_the_optimality_conditions(name, cone, settle, solver, orc, capi):
-    m = capi.Model.from_xml_string(ROWS) if name == "ROWS" else capi.Model.from_xml_file(model_path(name))  # options are edited: not the shared cached model
+    m, v0 = load_case(name, capi)
     m.opt.cone, m.opt.solver = cone, solver
     m.opt.tolerance, m.opt.iterations = 1e-14, 200
     o = orc.Oracle(m)
     rng = np.random.default_rng(4)
-    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq))
+    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq) * (v0 is None))
+    if v0 is not None:
+        o.set("qvel", v0)
     for s in range(settle):
         if m.nu and s % 25 == 0:
             lo, hi = m.actuator_ctrlrange.reshape(-1, 2).T
@@ -102,6 +131,10 @@ def test_solution_satisfies_the_optimality_conditions(name, cone, settle, solver
     assert seen, name
     if name == "ROWS":
         assert seen >= {FRICTION_DOF, FRICTION_TENDON, LIMIT_JOINT, FRICTIONLESS}, seen
+    if name == "CONDIM":
+        dims = set(int(d) for d in o.get("contact_dim")[:int(o.get("ncon")[0])])
+        assert dims >= {1, 4, 6} and FRICTIONLESS in seen, (dims, seen)
+        assert np.abs(f).max() > 1 and nefc >= (30 if cone == 0 else 18), nefc
 
 
 def test_the_conditions_reject_a_wrong_answer(capi, orc):
@@ -265,3 +298,46 @@ def test_constraint_jacobian_is_the_derivative_of_the_residual(name, cone, settl
         np.testing.assert_allclose((J @ v)[want], fd[want], rtol=2e-5, atol=2e-6, err_msg=f"{name} trial {trial}")
         checked += 1
     assert checked >= 2, (name, checked)
+
+
+@pytest.mark.parametrize("cone", ["elliptic", "pyramidal"])
+def test_torsional_and_rolling_friction_saturate_at_mu_times_normal_force(cone, capi, orc):
+    """condim 4 / 6 semantics in closed form: a sphere spinning about the contact normal is braked by the torque
+    mu_torsion N, a sphere rolling without slipping by the torque mu_roll N (both coefficients are lengths):
+    alpha = mu_t N / I  and  a = mu_r N / (1.4 m r) for a solid sphere.
+    N is the weight under pyramidal cones.  Under elliptic cones the restated primal cost couples the rows: a saturated
+    friction row raises the normal force of that step (the fast-spinning sphere sees up to five times its weight at
+    single steps, 15 % over its weight on average here) -- whether libmujoco does the same is part of the unpinned
+    parity, so the elliptic case takes N from the solver's own normal forces."""
+    xml = f"""<mujoco><option timestep="0.001" cone="{cone}"/><worldbody>
+      <geom type="plane" size="5 5 .1" condim="6" friction="1 0.03 0.004"/>
+      <body pos="0 0 0.1"><freejoint/><geom size="0.1" condim="4" friction="1 0.03 0.004"/></body>
+      <body pos="1 0 0.1"><freejoint/><geom size="0.1" condim="6" friction="1 0.03 0.004"/></body>
+    </worldbody></mujoco>"""
+    m = capi.Model.from_xml_string(xml)
+    o = orc.Oracle(m)
+    o.step(300)  # settle on the plane
+    v = np.zeros(12)
+    v[5] = 40.0              # first sphere: spin about the vertical
+    v[6], v[10] = 1.0, 10.0  # second: rolls along +x without slipping (omega_y = v / r)
+    o.set("qvel", v)
+    o.step(50)
+    a = o.get("qvel").copy()
+    mass, r, steps = m.body_mass[1], 0.1, 200
+    normal = np.zeros(2)
+    for _ in range(steps):
+        o.step(1)
+        if cone == "elliptic":  # the spinning sphere hops (see above): a step without its contact adds no force
+            f = o.get("efc_force")
+            for c in range(int(o.get("ncon")[0])):
+                ball, adr = int(o.get("contact_geom2")[c]) - 1, int(o.get("contact_efc_address")[c])
+                normal[ball] += f[adr]
+                scaled = f[adr + 1:adr + 6] / [1, 1, 0.03, 0.004, 0.004]
+                assert abs(np.linalg.norm(scaled) - f[adr]) < 1e-6 * f[adr], (ball, f[adr:adr + 6])  # on the cone boundary
+    b = o.get("qvel").copy()
+    N = normal / steps if cone == "elliptic" else np.full(2, mass * 9.81)
+    alpha, decel = -(b[5] - a[5]) / (steps * 0.001), -(b[6] - a[6]) / (steps * 0.001)
+    tol = 0.01 if cone == "elliptic" else 0.08  # the pyramid only approximates the friction limit
+    assert abs(alpha / (0.03 * N[0] / (0.4 * mass * r * r)) - 1) < tol, (alpha, N)
+    assert abs(decel / (0.004 * N[1] / (1.4 * mass * r)) - 1) < tol, (decel, N)
+    assert abs(b[10] * r - b[6]) < 1e-3  # still rolling without slipping

@@ -148,3 +148,36 @@ def test_flag_gpu_parity(flag, capi, orc):
             o.set(k, v[e])
         o.forward()
     compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag=f"flag {flag}")
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(60, method="thread")
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: not yet run on hardware")
+@pytest.mark.parametrize("cone,solver", [(0, 2), (1, 2), (1, 0), (0, 1)])
+def test_contact_dimensions_margin_gap_mixing_gpu_parity(cone, solver, capi, orc):
+    """condim 1 / 4 / 6 rows (torsional, rolling), margin + gap, solmix / priority: no bench model has them."""
+    from mujoco_ros_pkgs_b200.batch import BatchSim
+    from parity_util import compare_forward_fields, injected_steps, make_oracles, perturbed
+    from test_solver_optimality_cpu import load_case
+
+    model, v0 = load_case("CONDIM", capi)
+    model.opt.cone, model.opt.solver = cone, solver
+    nenv = 8
+    rng = np.random.default_rng(5)
+    qpos, _ = perturbed(model, nenv, seed=4, amp=0.0)
+    qvel = np.tile(v0, (nenv, 1)) * rng.uniform(0.5, 1.5, (nenv, 1))
+    sim = BatchSim(model, nenv)
+    sim.set("qpos", qpos)
+    sim.set("qvel", qvel)
+    sim.step(150)
+    oracles = make_oracles(orc, model, qpos, qvel)
+    _, max_nefc = injected_steps(model, sim, oracles, 30, rng, tag=f"condim cone {cone} solver {solver}")
+    assert max_nefc >= 18
+    sim.keep_intermediates(True)
+    sim.forward()
+    st = {k: sim.get(k) for k in ("qpos", "qvel", "qacc_warmstart")}
+    for e, o in enumerate(oracles):
+        for k, v in st.items():
+            o.set(k, v[e])
+        o.forward()
+    compare_forward_fields(capi, model, sim, oracles, skip={"xfrc_applied"}, tag="condim")
