@@ -301,3 +301,43 @@ def test_box_stack_rests(orc, load_model):
     assert q[9] == pytest.approx(0.2 + 0.12 + 0.05, abs=3e-3)
     assert np.abs(o.get("qvel")).max() < 1e-3
     assert o.get("ncon")[0] == 8
+
+
+def test_energy_and_momentum_of_a_mixed_joint_tree(orc, capi):
+    """Free + hinge + ball + slide chain with off-centre inertias, no dissipation, RK4: total energy 1/2 v'Mv - sum m g.x
+    is conserved under gravity (pins the bias forces against the mass matrix), and without gravity so are the linear
+    momentum and the angular momentum about the origin of the floating tree (pins the free / ball joint conventions)."""
+    from test_sensor_derivatives_cpu import XML
+    from test_solver_optimality_cpu import dense_mass
+
+    xml = XML % ""
+    xml = (xml[:xml.index("<sensor>")] + '<sensor><subtreecom body="root"/><subtreelinvel body="root"/><subtreeangmom body="root"/>'
+           "</sensor></mujoco>")
+    for gravity in ("0 0 -9.81", "0 0 0"):
+        m = capi.Model.from_xml_string(xml.replace('timestep="0.002" gravity="0 0 -9.81"',
+                                                   f'timestep="0.0005" integrator="RK4" gravity="{gravity}"'))
+        o = orc.Oracle(m)
+        rng = np.random.default_rng(1)
+        q = m.qpos0.copy()
+        q[3:7] = [0.8, 0.2, -0.4, 0.4]
+        q[3:7] /= np.linalg.norm(q[3:7])
+        o.set("qpos", q)
+        o.set("qvel", rng.uniform(-2, 2, m.nv))
+        masses = m.body_mass
+
+        def invariants():
+            o.forward()
+            v = o.get("qvel")
+            x = o.get("xipos").reshape(-1, 3)
+            energy = 0.5 * v @ dense_mass(m, o.get("qM")) @ v + 9.81 * (masses @ x[:, 2]) * (gravity != "0 0 0")
+            com, sv, sm = o.get("sensordata")[:9].reshape(3, 3)  # of the whole floating tree
+            total = masses.sum()
+            return energy, total * sv, sm + total * np.cross(com, sv)
+        e0, p0, l0 = invariants()
+        o.step(2000)  # one second
+        e1, p1, l1 = invariants()
+        assert abs(e1 - e0) < 2e-8 * max(1.0, abs(e0)), (e0, e1)
+        if gravity == "0 0 0":
+            np.testing.assert_allclose(p1, p0, rtol=0, atol=1e-7)  # RK4 truncation over 2000 steps, not round-off
+            np.testing.assert_allclose(l1, l0, rtol=0, atol=1e-7)
+            assert np.linalg.norm(l0) > 1e-3 and np.linalg.norm(p0) > 1e-3

@@ -52,6 +52,8 @@ def main(out):
         <geom type="capsule" fromto="0 0 0 .1 0 0" size=".02"/><site name="s2" pos=".1 0 0"/></body></body>
     <body name="b3" pos="1 0 1"><joint name="j2" type="ball"/><geom type="mesh" mesh="m3"/><geom type="ellipsoid" size=".1 .05 .03"/></body>
     <body name="b4" pos="0 1 1"><joint name="j3" type="slide" axis="0 0 1"/><geom type="mesh" mesh="m4"/><geom type="cylinder" size=".05 .1"/></body>
+    <frame pos="0 0 .5" euler="0 0 45" childclass="a"><geom size=".02" pos="2 0 0"/><frame pos=".1 0 0"><body name="fb" pos="0 2 0" gravcomp="1">
+      <joint name="jf" axis="1 0 0"/><geom size=".05"/></body></frame></frame>
     <body name="mc" mocap="true" pos="0 0 2"><geom type="box" size=".05 .05 .05" contype="0" conaffinity="0"/></body>
   </worldbody>
   <contact><exclude body1="b1" body2="b2"/><pair geom1="1" geom2="0" condim="3"/></contact>
@@ -62,7 +64,7 @@ def main(out):
     <cylinder tendon="t2" timeconst=".1" area=".01"/><general tendon="t1" gaintype="affine" gainprm="1 .1 .1"/></actuator>
   <sensor><jointpos joint="j1"/><framepos objtype="site" objname="s1"/><accelerometer site="s2"/><tendonpos tendon="t1"/>
     <actuatorfrc actuator="0"/></sensor>
-  <keyframe><key name="k" time="1" qpos="0 0 1 1 0 0 0 .1 1 0 0 0 .2" ctrl="1 0 0 0 0"/></keyframe>
+  <keyframe><key name="k" time="1" qpos="0 0 1 1 0 0 0 .1 1 0 0 0 .2 0" ctrl="1 0 0 0 0"/></keyframe>
 </mujoco>
 """.replace('geom1="1" geom2="0"', 'geom1="g_a" geom2="g_b"').replace('<geom type="hfield" hfield="h1"/>', '<geom name="g_b" type="hfield" hfield="h1"/>').replace(
         '<geom type="mesh" mesh="m1"/>', '<geom name="g_a" type="mesh" mesh="m1"/>').replace('actuator="0"', 'actuator="a0"').replace(
