@@ -64,6 +64,9 @@ CONDIM = """<mujoco><option timestep="0.002" impratio="3"/><worldbody>
 def load_case(name, capi):
     if name == "ROWS":
         return capi.Model.from_xml_string(ROWS), None
+    if name == "ROWS_DIRECT":  # negative solref = stiffness and damping given directly; a power-3 impedance curve
+        return capi.Model.from_xml_string(ROWS.replace('frictionloss="0.3"', 'frictionloss="0.3" solreflimit="-800 -30" '
+                                                       'solimplimit="0.8 0.97 0.01 0.3 3"')), None
     if name == "CONDIM":
         m = capi.Model.from_xml_string(CONDIM)
         v = np.zeros(m.nv)
@@ -181,17 +184,20 @@ def stiffness_damping(solref, solimp, dt):
 
 
 @pytest.mark.parametrize("name,cone,settle", [("panda_like.xml", 0, 450), ("humanoid_like.xml", 1, 150), ("box_stack.xml", 0, 150),
-                                               ("equality_scene.xml", 0, 60), ("ROWS", 0, 400)])
+                                               ("equality_scene.xml", 0, 60), ("ROWS", 0, 400), ("ROWS_DIRECT", 0, 400),
+                                               ("CONDIM", 1, 200)])
 def test_constraint_parameters_follow_the_documented_formulas(name, cone, settle, orc, capi):
     """Row M6 against MuJoCo's published definitions (Computation chapter, "solver parameters"): reference acceleration
     aref = -B vel - K d (pos - margin), regulariser R = (1 - d) / d * diagApprox, D = 1 / R, with (K, B) from solref
     (time constant clamped at two time steps) and the impedance d from the solimp curve -- recomputed here with numpy
     from the per-row inputs the oracle exposes."""
-    m = capi.Model.from_xml_string(ROWS) if name == "ROWS" else capi.Model.from_xml_file(model_path(name))  # options are edited: not the shared cached model
+    m, v0 = load_case(name, capi)
     m.opt.cone = cone
     o = orc.Oracle(m)
     rng = np.random.default_rng(9)
-    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq))
+    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq) * (v0 is None))
+    if v0 is not None:
+        o.set("qvel", v0)
     o.step(settle)
     o.forward()
     nefc = int(o.get("nefc")[0])
@@ -254,11 +260,11 @@ def test_constraint_jacobian_is_the_derivative_of_the_residual(name, cone, settl
     """efc_J against central differences of efc_pos along random generalised velocities: joint limits, connect / joint
     equalities, frictionless contacts and the normal rows of elliptic contacts (distance of the nearest points --
     collision and contact Jacobian together).  Involves no formula from the oracle's own derivation."""
-    m = capi.Model.from_xml_string(ROWS) if name == "ROWS" else capi.Model.from_xml_file(model_path(name))  # options are edited: not the shared cached model
+    m, v0 = load_case(name, capi)
     m.opt.cone = cone
     o = orc.Oracle(m)
     rng = np.random.default_rng(12)
-    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq))
+    o.set("qpos", m.qpos0 + rng.uniform(-0.05, 0.05, m.nq) * (v0 is None))
     o.step(settle)
     q0 = o.get("qpos").copy()
     o.set("qvel", np.zeros(m.nv))
