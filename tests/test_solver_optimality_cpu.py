@@ -347,3 +347,28 @@ def test_torsional_and_rolling_friction_saturate_at_mu_times_normal_force(cone, 
     assert abs(alpha / (0.03 * N[0] / (0.4 * mass * r * r)) - 1) < tol, (alpha, N)
     assert abs(decel / (0.004 * N[1] / (1.4 * mass * r)) - 1) < tol, (decel, N)
     assert abs(b[10] * r - b[6]) < 1e-3  # still rolling without slipping
+
+
+def test_limit_margins_activate_rows_before_the_limit(capi, orc):
+    """joint / tendon margin: the limit row exists as soon as the distance to the limit drops below the margin, with
+    efc_pos = that distance and the impedance evaluated at distance - margin."""
+    xml = """<mujoco><compiler angle="radian"/><option gravity="0 0 0"/><worldbody>
+      <body><joint name="a" axis="0 1 0" range="-0.5 0.5" limited="true" margin="0.05"/><geom size="0.1" pos="0.3 0 0"/>
+        <body pos="0.3 0 0"><joint name="b" axis="0 1 0"/><geom size="0.05" pos="0.2 0 0"/></body></body></worldbody>
+      <tendon><fixed name="t" limited="true" range="-1 0.6" margin="0.1"><joint joint="a" coef="1"/><joint joint="b" coef="1"/></fixed></tendon>
+    </mujoco>"""
+    m = capi.Model.from_xml_string(xml)
+    for qa, qb, expect in ((0.40, 0.0, []), (0.47, 0.0, [(LIMIT_JOINT, 0.03, 0.05)]), (0.47, 0.1, [(LIMIT_JOINT, 0.03, 0.05), (LIMIT_TENDON, 0.03, 0.1)]),
+                           (-0.48, -0.45, [(LIMIT_JOINT, 0.02, 0.05), (LIMIT_TENDON, 0.07, 0.1)])):
+        o = orc.Oracle(m)
+        o.set("qpos", [qa, qb])
+        o.forward()
+        n = int(o.get("nefc")[0])
+        got = [(int(o.get("efc_type")[i]), o.get("efc_pos")[i], o.get("efc_margin")[i]) for i in range(n)]
+        assert len(got) == len(expect), (qa, qb, got)
+        for g, e in zip(got, expect):
+            assert g[0] == e[0]
+            np.testing.assert_allclose(g[1:], e[1:], atol=1e-12)
+        for i in range(n):
+            solimp = (m.jnt_solimp.reshape(-1, 5)[0] if got[i][0] == LIMIT_JOINT else m.tendon_solimp_lim.reshape(-1, 5)[0])
+            np.testing.assert_allclose(o.get("efc_KBIP")[4 * i + 2], impedance(solimp, got[i][1] - got[i][2]), rtol=1e-12)
