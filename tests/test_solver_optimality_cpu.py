@@ -257,8 +257,8 @@ def integrate_pos(m, q, v, eps):
 @pytest.mark.parametrize("name,cone,settle", [("ROWS", 1, 400), ("humanoid_like.xml", 1, 150), ("hand_like.xml", 1, 120),
                                                ("equality_scene.xml", 0, 60), ("panda_like.xml", 1, 450)])
 def test_constraint_jacobian_is_the_derivative_of_the_residual(name, cone, settle, orc, capi):
-    """efc_J against central differences of efc_pos along random generalised velocities: joint limits, connect / joint
-    equalities, frictionless contacts and the normal rows of elliptic contacts (distance of the nearest points --
+    """efc_J against central differences of efc_pos along random generalised velocities: joint limits, connect / weld /
+    joint / tendon equalities, frictionless contacts and the normal rows of elliptic contacts (distance of the nearest points --
     collision and contact Jacobian together).  Involves no formula from the oracle's own derivation."""
     m, v0 = load_case(name, capi)
     m.opt.cone = cone
@@ -281,7 +281,7 @@ def test_constraint_jacobian_is_the_derivative_of_the_residual(name, cone, settl
     want, first = [], {}
     for i in range(len(typ)):
         t, k = int(typ[i]), int(ids[i])
-        if t == LIMIT_JOINT or t == FRICTIONLESS or (t == EQUALITY and eq_type[k] in (0, 2)):  # connect, joint
+        if t == LIMIT_JOINT or t == FRICTIONLESS or (t == EQUALITY and eq_type[k] in (0, 1, 2, 3)):  # connect, weld, joint, tendon
             want.append(i)
         elif t == ELLIPTIC and first.setdefault(k, i) == i:
             # sphere-box / capsule-box are constructions of our own: once the sphere centre or the
