@@ -255,7 +255,8 @@ def integrate_pos(m, q, v, eps):
 
 
 @pytest.mark.parametrize("name,cone,settle", [("ROWS", 1, 400), ("humanoid_like.xml", 1, 150), ("hand_like.xml", 1, 120),
-                                               ("equality_scene.xml", 0, 60), ("panda_like.xml", 1, 450)])
+                                               ("equality_scene.xml", 0, 60), ("panda_like.xml", 1, 450),
+                                               ("humanoid_like.xml", 0, 150), ("panda_like.xml", 0, 450)])
 def test_constraint_jacobian_is_the_derivative_of_the_residual(name, cone, settle, orc, capi):
     """efc_J against central differences of efc_pos along random generalised velocities: joint limits, connect / weld /
     joint / tendon equalities, frictionless contacts and the normal rows of elliptic contacts (distance of the nearest points --
@@ -291,7 +292,16 @@ def test_constraint_jacobian_is_the_derivative_of_the_residual(name, cone, settl
             if 6 in types and 0 not in types:
                 continue
             want.append(i)
+        elif t == PYRAMIDAL and first.setdefault(k, i) == i:
+            # edges come in pairs J_n +- mu J_t: the mean of a pair is the normal row, its residual the distance
+            types = {int(m.geom_type[g]) for g in geoms[k]}
+            if 6 in types and 0 not in types:
+                continue
+            want.append(i)
+            J[i] = 0.5 * (J[i] + J[i + 1])
     assert len(want) >= 2, (name, len(want))
+    if cone == 0 and name == "humanoid_like.xml":
+        assert any(int(typ[i]) == PYRAMIDAL for i in want)
     eps, checked = 1e-6, 0
     for trial in range(4):
         v = rng.uniform(-1, 1, m.nv)
