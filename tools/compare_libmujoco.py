@@ -64,6 +64,20 @@ def main():
     for k in g.files:
         if k.endswith("__xml"):
             sources["ref_" + k[:-5]] = bytes(g[k]).decode()
+    # scenes of the CPU tests that lean on recalled MuJoCo behaviour: every constraint row type, contact dimensions
+    # 1 / 4 / 6 with margin / gap / solmix / priority (incl. the normal-force coupling of saturated elliptic friction),
+    # every disable flag, the sensor chain, springdamper + actuator shorthands
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_round2d_gpu
+    import test_sensor_derivatives_cpu as tsd
+    import test_solver_optimality_cpu as tso
+    import test_zz_disable_flags as tdf
+    sources.update({"t_rows": tso.ROWS, "t_condim_pyramidal": tso.CONDIM,
+                    "t_condim_elliptic": tso.CONDIM.replace('impratio="3"', 'impratio="3" cone="elliptic"'),
+                    "t_sensors": tsd.XML % "".join(tsd.PER_SITE.format(s) for s in tsd.SITES), "t_rest": tsd.REST,
+                    "t_arm_shorthands": test_round2d_gpu.ARM % "Euler"})
+    for flag in tdf.FLAGS:
+        sources["t_flag_" + flag] = tdf.SCENE.format(flag=flag, solver="Newton")
     worst_all = 0.0
     for name, xml in sources.items():
         mm = mj.MjModel.from_xml_string(xml)
