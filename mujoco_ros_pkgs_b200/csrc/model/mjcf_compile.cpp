@@ -503,6 +503,19 @@ struct Builder {
     a.vec("size", s.size, 3);
     a.vec("pos", s.pos, 3, 3);
     orientation(ctx, a, s.quat);
+    if (a.has("fromto")) {  // as for geoms: midpoint, z axis along the segment, half length into the size
+      double ft[6];
+      a.vec("fromto", ft, 6, 6);
+      if (s.type != B2MJ_GEOM_CAPSULE && s.type != B2MJ_GEOM_CYLINDER && s.type != B2MJ_GEOM_BOX && s.type != B2MJ_GEOM_ELLIPSOID)
+        fail(n, "fromto needs capsule/cylinder/box/ellipsoid");
+      double v[3] = {ft[0] - ft[3], ft[1] - ft[4], ft[2] - ft[5]};
+      const double len = norm3(v);
+      if (len < 1e-14) fail(n, "fromto points coincide");
+      for (int i = 0; i < 3; i++) s.pos[i] = 0.5 * (ft[i] + ft[i + 3]);
+      z2quat(s.quat, v);
+      if (s.type == B2MJ_GEOM_BOX || s.type == B2MJ_GEOM_ELLIPSOID) { s.size[1] = s.size[0]; s.size[2] = len / 2; }
+      else s.size[1] = len / 2;
+    }
     b.sites.push_back(s);
   }
 

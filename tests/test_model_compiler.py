@@ -290,3 +290,18 @@ def test_frame_elements_are_pure_coordinate_transforms(capi):
                       ('<replicate count="3"><geom size=".1"/></replicate>', "replicate")):
         with pytest.raises(capi.B2mjError, match=word):
             capi.Model.from_xml_string(f'<mujoco><worldbody><body>{bad}</body></worldbody></mujoco>')
+
+
+def test_site_fromto_matches_the_geom_rule(capi):
+    """<site fromto="..."> (capsule / cylinder / box / ellipsoid sites): midpoint, z axis along the segment and half
+    length, exactly as for a geom with the same attribute."""
+    x = ('<mujoco><worldbody><body><geom type="{0}" fromto="0.1 0 0 0.1 0.2 0.3" size="0.02"/>'
+         '<site type="{0}" fromto="0.1 0 0 0.1 0.2 0.3" size="0.02"/></body></worldbody></mujoco>')
+    for kind in ("capsule", "cylinder", "box", "ellipsoid"):
+        m = capi.Model.from_xml_string(x.format(kind))
+        np.testing.assert_array_equal(m.site_pos, m.geom_pos)
+        np.testing.assert_array_equal(m.site_quat, m.geom_quat)
+        n = 2 if kind in ("capsule", "cylinder") else 3
+        np.testing.assert_array_equal(m.site_size.ravel()[:n], m.geom_size.ravel()[:n])
+    with pytest.raises(capi.B2mjError, match="fromto"):
+        capi.Model.from_xml_string(x.format("sphere"))
