@@ -322,6 +322,30 @@ void eig3(const double* A_in, double* eval, double* V) {
   if (dot3(cr, c2) < 0) { V[2] = -V[2]; V[5] = -V[5]; V[8] = -V[8]; }
 }
 
+// MuJoCo validates every element against its schema: an attribute it does not know is an error, not a no-op.  Same here
+// for the elements that carry physics (MuJoCo 2.3.7 attribute lists); a misspelt or newer-version attribute would
+// otherwise be dropped silently and the model would simulate something else.
+void check_attributes(const XmlNode* n, const char* const* known) {
+  for (auto& kv : n->attrs) {
+    bool ok = false;
+    for (const char* const* k = known; *k && !ok; k++) ok = kv.first == *k;
+    if (!ok) fail(n, "unknown attribute '" + kv.first + "'");
+  }
+}
+const char* const kGeomAttrs[] = {"name", "class", "type", "contype", "conaffinity", "condim", "group", "priority", "size",
+    "material", "rgba", "friction", "mass", "density", "shellinertia", "solmix", "solref", "solimp", "margin", "gap", "fromto",
+    "pos", "quat", "axisangle", "xyaxes", "zaxis", "euler", "hfield", "mesh", "fitscale", "user", "fluidshape", "fluidcoef", nullptr};
+const char* const kSiteAttrs[] = {"name", "class", "type", "group", "pos", "quat", "axisangle", "xyaxes", "zaxis", "euler",
+    "material", "size", "fromto", "rgba", "user", nullptr};
+const char* const kJointAttrs[] = {"name", "class", "type", "group", "pos", "axis", "springdamper", "limited", "actuatorfrclimited",
+    "solreflimit", "solimplimit", "solreffriction", "solimpfriction", "stiffness", "range", "actuatorfrcrange", "margin", "ref",
+    "springref", "armature", "damping", "frictionloss", "user", nullptr};
+const char* const kFreeJointAttrs[] = {"name", "group", nullptr};
+const char* const kBodyAttrs[] = {"name", "childclass", "mocap", "pos", "quat", "axisangle", "xyaxes", "zaxis", "euler", "gravcomp",
+    "user", nullptr};
+const char* const kInertialAttrs[] = {"pos", "quat", "axisangle", "xyaxes", "zaxis", "euler", "mass", "diaginertia", "fullinertia", nullptr};
+const char* const kFrameAttrs[] = {"name", "childclass", "pos", "quat", "axisangle", "xyaxes", "zaxis", "euler", nullptr};
+
 // <frame pos=.. quat=.. childclass=..> (MuJoCo 3 files): a pure coordinate transform applied to everything it
 // contains; it leaves no trace in the model.  F = pose of the enclosing frames relative to the body.
 struct Frame {
@@ -364,6 +388,7 @@ struct Builder {
   }
 
   void read_joint(const XmlNode* n, const std::string& childclass, CBody& b) {
+    check_attributes(n, n->tag == "freejoint" ? kFreeJointAttrs : kJointAttrs);
     CJoint j;
     AttrMap em = effective(ctx, n, childclass);
     A a{em, n};
@@ -410,6 +435,7 @@ struct Builder {
   }
 
   void read_geom(const XmlNode* n, const std::string& childclass, CBody& b) {
+    check_attributes(n, kGeomAttrs);
     CGeom g;
     AttrMap em = effective(ctx, n, childclass);
     A a{em, n};
@@ -495,6 +521,7 @@ struct Builder {
   }
 
   void read_site(const XmlNode* n, const std::string& childclass, CBody& b) {
+    check_attributes(n, kSiteAttrs);
     CSite s;
     AttrMap em = effective(ctx, n, childclass);
     A a{em, n};
@@ -537,6 +564,7 @@ struct Builder {
       if (t == "body") {
         queue.push_back({ch.get(), F, childclass});
       } else if (t == "frame") {
+        check_attributes(ch.get(), kFrameAttrs);
         AttrMap em;
         for (auto& kv : ch->attrs) em[kv.first] = kv.second;
         A a{em, ch.get()};
@@ -564,6 +592,7 @@ struct Builder {
         frame_apply(F, bodies[id].sites.back().pos, bodies[id].sites.back().quat);
       } else if (t == "inertial") {
         if (!F.identity) fail(ch.get(), "inertial is not allowed inside a frame");
+        check_attributes(ch.get(), kInertialAttrs);
         CBody& b = bodies[id];
         AttrMap em;
         for (auto& kv : ch->attrs) em[kv.first] = kv.second;
@@ -599,6 +628,7 @@ struct Builder {
     if (n->tag == "worldbody") {
       id = 0;
     } else {
+      check_attributes(n, kBodyAttrs);
       bodies.emplace_back();
       CBody& b = bodies.back();
       b.parent = parent;

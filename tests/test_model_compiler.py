@@ -305,3 +305,21 @@ def test_site_fromto_matches_the_geom_rule(capi):
         np.testing.assert_array_equal(m.site_size.ravel()[:n], m.geom_size.ravel()[:n])
     with pytest.raises(capi.B2mjError, match="fromto"):
         capi.Model.from_xml_string(x.format("sphere"))
+
+
+def test_unknown_attributes_on_physics_elements_are_errors(capi):
+    """MuJoCo validates elements against its schema; a misspelt attribute must not be dropped silently (the model would
+    simulate something else).  Checked for body / inertial / joint / freejoint / geom / site / frame."""
+    base = '<mujoco><worldbody><body {0}><inertial pos="0 0 0" mass="1" diaginertia="1 1 1" {1}/><joint {2}/><geom size="0.1" {3}/><site {4}/></body></worldbody></mujoco>'
+    capi.Model.from_xml_string(base.format("", "", "", "", ""))
+    for k, (attr, where) in enumerate((('gravcmp="1"', "body"), ('fulinertia="1 1 1 0 0 0"', "inertial"), ('dampng="2"', "joint"),
+                                       ('fricton="1 0 0"', "geom"), ('fromt="0 0 0 1 0 0"', "site"))):
+        args = [""] * 5
+        args[k] = attr
+        with pytest.raises(capi.B2mjError, match=f"<{where}>: unknown attribute '{attr.split('=')[0]}'"):
+            capi.Model.from_xml_string(base.format(*args))
+    with pytest.raises(capi.B2mjError, match="unknown attribute 'damping'"):
+        capi.Model.from_xml_string('<mujoco><worldbody><body><freejoint damping="1"/><geom size=".1"/></body></worldbody></mujoco>')
+    # every schema attribute that only matters to rendering or bookkeeping is accepted
+    capi.Model.from_xml_string('<mujoco><worldbody><body name="b" user="1 2"><joint group="2" user="3"/><geom size="0.1" material="m" '
+                               'rgba="1 0 0 1" user="1"/><site material="m" rgba="0 1 0 1" group="3" user="4"/></body></worldbody></mujoco>')
