@@ -444,6 +444,8 @@ struct Builder {
     int ns = a.vec("size", g.size, 3);
     a.vec("pos", g.pos, 3, 3);
     orientation(ctx, a, g.quat);
+    if (g.type != B2MJ_GEOM_MESH && a.has("mesh"))  // MuJoCo then fits the primitive to the mesh and ignores size
+      fail(n, "fitting a primitive geom to a mesh (type other than mesh together with a mesh attribute) is not supported");
     if (g.type == B2MJ_GEOM_MESH) {
       // the mesh frame (centre of mass + principal axes) is folded into the geom pose, as the MuJoCo compiler does
       if (!a.has("mesh")) fail(n, "mesh geom needs a mesh attribute");

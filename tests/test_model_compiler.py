@@ -323,3 +323,14 @@ def test_unknown_attributes_on_physics_elements_are_errors(capi):
     # every schema attribute that only matters to rendering or bookkeeping is accepted
     capi.Model.from_xml_string('<mujoco><worldbody><body name="b" user="1 2"><joint group="2" user="3"/><geom size="0.1" material="m" '
                                'rgba="1 0 0 1" user="1"/><site material="m" rgba="0 1 0 1" group="3" user="4"/></body></worldbody></mujoco>')
+
+
+def test_primitive_fitted_to_a_mesh_is_refused(capi):
+    """<geom type="box" mesh="..."> asks MuJoCo to fit the primitive to the mesh (size is then ignored): not implemented,
+    so it must not compile to a box of the given size."""
+    xml = ('<mujoco><asset><mesh name="m" vertex="0 0 0 1 0 0 0 1 0 0 0 1"/></asset><worldbody><body>'
+           '<geom type="%s" mesh="m" size=".1 .1 .1"/></body></worldbody></mujoco>')
+    capi.Model.from_xml_string(xml % "mesh")
+    for kind in ("box", "sphere", "capsule"):
+        with pytest.raises(capi.B2mjError, match="fitting a primitive"):
+            capi.Model.from_xml_string(xml % kind)
